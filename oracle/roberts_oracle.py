@@ -1,0 +1,435 @@
+"""CPU oracle for the Roberts (1983) boundary-integral RK4 time step.
+
+TEST INFRASTRUCTURE ONLY.  This module restates, in vectorised NumPy, the
+arithmetic of the reference's CUDA path (CuSuperHelium) for one RHS evaluation
+and one classical RK4 step.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
+The product path (``superfluid_dynamics_b200``) never does.
+
+Reference citations use the prefixes of SURVEY.md:
+  L/ = CuSuperHelium/CuSuperHelium/         (CUDA library)
+  T/ = CuSuperHelium/CuSuperHelium.Tests/   (gtest fixtures)
+  P/ = CuSuperHelium/Python/                (NumPy statement of the water path)
+
+Parity pinning (see tests/test_oracle.py and tests/golden/):
+  * water path: pinned against P/WaterIntegralCalculator.py run in the build
+    container (golden vectors committed under tests/golden/), and against the
+    closed forms / host loops of T/MatrixMTests.cuh.
+  * helium finite-depth path (createFiniteDepthMKernel,
+    createHeliumVelocityMatrices, compute_rhs_helium_phi_expression*): the
+    reference holds no CPU statement, no test and no golden vector for these
+    kernels -> "parity unpinned"; restated from the CUDA source only.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import numpy as np
+
+PI = math.pi
+ALPHA_HAMAKER = 3.5e-24  # L/constants.cuh:11
+
+
+# --------------------------------------------------------------------------
+# problem description (L/ProblemProperties.hpp:5-32)
+# --------------------------------------------------------------------------
+@dataclasses.dataclass
+class ProblemProperties:
+    L: float = 1.0
+    rho: float = 1.0
+    U: float = 0.0
+    kappa: float = 0.0
+    depth: float = 1.0
+    initial_amplitude: float = 1.0
+    use_expansions: bool = False
+    expansion_order: int = 1
+    infinite_depth: bool = False
+    base_length: float = 1.0
+    base_time: float = 1.0
+    base_energy: float = 1.0
+    base_acceleration: float = 1.0
+
+
+def adimensionalize_properties(props: ProblemProperties, rho_helium: float = 150.0) -> ProblemProperties:
+    """SI -> nondimensional conversion of L/Export.cu:1222-1246."""
+    p = dataclasses.replace(props)
+    p.base_length = p.L / (2.0 * PI)
+    p.base_acceleration = 3 * ALPHA_HAMAKER / p.depth ** 4
+    p.base_time = math.sqrt(p.base_length / p.base_acceleration)
+    p.base_energy = 3.0 * rho_helium * ALPHA_HAMAKER * p.base_length ** 4 / p.depth ** 4
+    surface_tension_factor = rho_helium * p.base_length ** 3 / (p.base_time * p.base_time)
+    p.kappa = p.kappa / surface_tension_factor
+    p.depth = p.depth / p.base_length
+    p.rho = p.rho / rho_helium
+    return p
+
+
+def adimensionalize_rk4_options(time_step: float, t0: float, t1: float, props: ProblemProperties):
+    """L/Export.cu:1213-1220."""
+    return time_step / props.base_time, t0 / props.base_time, t1 / props.base_time
+
+
+# --------------------------------------------------------------------------
+# initial surfaces (T/MatrixMTests.cuh:19-67, P/StokeWaves.py:3-8,
+# L/SimulationFunctions.cuh:18-28)
+# --------------------------------------------------------------------------
+def trochoid(N: int, h: float, omega: float = 1.0, t: float = 0.0, rho: float = 0.0):
+    """Z = X + iY and Phi of the analytic trochoidal wave sampled at alpha_j = 2 pi j / N."""
+    a = 2.0 * PI * np.arange(N) / N
+    X = a - h * np.sin(a - omega * t)
+    Y = h * np.cos(a - omega * t)
+    Phi = h * (1.0 + rho) * omega * np.sin(a - omega * t)
+    return X + 1j * Y, Phi.astype(np.float64)
+
+
+def trochoid_derivatives(N: int, h: float, omega: float = 1.0, t: float = 0.0, rho: float = 0.0):
+    """Per-index analytic derivatives of the trochoid (prepareZPhi, T/MatrixMTests.cuh:51-67)."""
+    a = 2.0 * PI * np.arange(N) / N
+    s = 2.0 * PI / N
+    Zp = (1 - h * np.cos(a - omega * t)) * s + 1j * (-h * np.sin(a - omega * t)) * s
+    Zpp = (h * np.sin(a - omega * t)) * s * s + 1j * (-h * np.cos(a - omega * t)) * s * s
+    PhiP = h * (1.0 + rho) * omega * np.cos(a - omega * t) * s
+    return Zp, Zpp, PhiP
+
+
+def sinusoid(N: int, eps: float):
+    """Small-amplitude deep-water wave: X=alpha, Y=eps cos, Phi=eps sin."""
+    a = 2.0 * PI * np.arange(N) / N
+    return a + 1j * eps * np.cos(a), eps * np.sin(a)
+
+
+def pack_state(Z: np.ndarray, Phi: np.ndarray) -> np.ndarray:
+    """[Z | Phi+0i] complex128 layout of L/BaseBoundaryIntegrator.cuh:141-145."""
+    return np.concatenate([np.asarray(Z, np.complex128).ravel(), np.asarray(Phi, np.float64).ravel().astype(np.complex128)])
+
+
+# --------------------------------------------------------------------------
+# spectral derivatives
+# --------------------------------------------------------------------------
+def d1_cuda(x: np.ndarray) -> np.ndarray:
+    """First derivative per index, CUDA semantics (L/utilities.cuh:106-148 + L/Derivatives.cuh:190-257).
+
+    modes 0..N/2-1: *ik ; mode N/2: *i*pi*(N/2) ; mode N/2+1: zeroed ; modes > N/2+1: *i(k-N).
+    The 1/n of the unnormalised inverse cuFFT is folded into the multiply.
+    Operates along the last axis (batched layout [b][N])."""
+    x = np.asarray(x, np.complex128)
+    n = x.shape[-1]
+    c = np.fft.fft(x, axis=-1)
+    i = np.arange(n)
+    fac = np.where(i < n // 2, i, i - n).astype(np.float64)
+    r = np.empty_like(c)
+    # result.x = -i*y/n ; result.y = i*x/n   (same operation order as the kernel)
+    r.real = -fac * c.imag / float(n)
+    r.imag = fac * c.real / float(n)
+    if n // 2 < n:
+        m = n // 2
+        r[..., m] = (-PI * m * c[..., m].imag / float(n)) + 1j * (PI * m * c[..., m].real / float(n))
+    if n // 2 + 1 < n:
+        r[..., n // 2 + 1] = 0.0
+    return np.fft.ifft(r, axis=-1) * n  # unnormalised inverse
+
+
+def d2_cuda(x: np.ndarray) -> np.ndarray:
+    """Second derivative per index (L/utilities.cuh:178-200): *(-k^2)/n for every mode."""
+    x = np.asarray(x, np.complex128)
+    n = x.shape[-1]
+    c = np.fft.fft(x, axis=-1)
+    i = np.arange(n)
+    fac = np.where(i <= n // 2, i, i - n).astype(np.float64)
+    r = -(fac * fac) * c / float(n)
+    return np.fft.ifft(r, axis=-1) * n
+
+
+def d1_python(x: np.ndarray) -> np.ndarray:
+    """First derivative, semantics of P/Derivatives.py:6-18 (differs from CUDA at the Nyquist mode only)."""
+    x = np.asarray(x, np.complex128)
+    n = x.shape[-1]
+    idx = np.fft.fftshift(np.arange(-n / 2, n / 2))
+    c = np.fft.fft(x, axis=-1)
+    nyq = c[..., n // 2].copy()
+    r = 1j * idx * c
+    if n // 2 + 1 < n:
+        r[..., n // 2 + 1] = 0
+    r[..., n // 2] = -PI * np.real(nyq)
+    return np.fft.ifft(r, axis=-1)
+
+
+def d2_python(x: np.ndarray) -> np.ndarray:
+    """P/Derivatives.py:19-27."""
+    x = np.asarray(x, np.complex128)
+    n = x.shape[-1]
+    idx = np.power(1j * np.fft.fftshift(np.arange(-n / 2, n / 2)), 2)
+    return np.fft.ifft(np.fft.fft(x, axis=-1) * idx, axis=-1)
+
+
+def fft_derivative(x, scale=1.0, second=False, deriv="cuda"):
+    """FftDerivative<N,B>::exec (L/Derivatives.cuh:190-257)."""
+    if deriv == "cuda":
+        r = d2_cuda(x) if second else d1_cuda(x)
+    else:
+        r = d2_python(x) if second else d1_python(x)
+    return r * scale if scale != 1.0 else r
+
+
+def zphi_derivative(Z, Phi, props: ProblemProperties, deriv="cuda"):
+    """ZPhiDerivative<N,B>::exec (L/Derivatives.cuh:311-384).  Returns Zp, PhiPrime (complex), Zpp."""
+    Z = np.asarray(Z, np.complex128)
+    n = Z.shape[-1]
+    j = np.arange(n, dtype=np.float64)
+    zlin = 2 * PI * j / n
+    philin = -(1 + props.rho) * PI * props.U / n * j
+    zper = Z - zlin
+    phiper = np.asarray(Phi, np.complex128) - philin
+    s = 2.0 * PI / n
+    Zpp = fft_derivative(zper, 4.0 * PI * PI / (n * n), second=True, deriv=deriv)
+    Zp = fft_derivative(zper, s, deriv=deriv)
+    PhiP = fft_derivative(phiper, s, deriv=deriv)
+    Zp = Zp + s
+    if props.U != 0:
+        PhiP = PhiP + (-(1 + props.rho) * PI * props.U / n)
+    return Zp, PhiP, Zpp
+
+
+# --------------------------------------------------------------------------
+# cotangent kernels
+# --------------------------------------------------------------------------
+def cot(z):
+    """cot(z) = 1/tan(z) as in L/utilities.cuh:312-315."""
+    return 1.0 / np.tan(z)
+
+
+def _cot_green(Z):
+    """C[k, j] = cot((Z_k - Z_j)/2) (L/utilities.cuh:347-350); diagonal set to 0."""
+    d = 0.5 * (Z[:, None] - Z[None, :])
+    np.fill_diagonal(d, 1.0)  # placeholder, avoids the pole
+    C = cot(d)
+    np.fill_diagonal(C, 0.0)
+    return C
+
+
+def create_M(Z, Zp, Zpp, rho: float) -> np.ndarray:
+    """createMKernel (L/createM.cuh:43-63).  Returns M[k, j] (row k, col j).
+
+    The device buffer is column-major A[k + j*n]; use ``M.T.ravel()`` /
+    ``order='F'`` to compare with the flat device layout."""
+    C = _cot_green(np.asarray(Z, np.complex128))
+    M = 0.25 * (1 - rho) / PI * (Zp[:, None] * C).imag
+    np.fill_diagonal(M, 0.5 * (1 + rho) + 0.25 * (1 - rho) / PI * (Zpp / Zp).imag)
+    return M
+
+
+def create_finite_depth_M(Z, Zp, Zpp, h: float, infinite_depth: bool = False) -> np.ndarray:
+    """createFiniteDepthMKernel (L/createM.cuh:65-92).  The image term carries no Zp_k factor (quirk 4)."""
+    Z = np.asarray(Z, np.complex128)
+    C = _cot_green(Z)
+    M = 0.25 / PI * (Zp[:, None] * C).imag
+    diag = 0.5 + 0.25 / PI * (Zpp / Zp).imag
+    if not infinite_depth:
+        img = cot(0.5 * (Z[:, None] - np.conj(Z)[None, :]) + 1j * h)
+        M = M - 0.25 / PI * img.imag
+        diag = diag - 0.25 / PI * cot(1j * (Z.imag + h)).imag
+    np.fill_diagonal(M, diag)
+    return M
+
+
+def velocity_matrices(Z, Zp, Zpp, lower: bool = True):
+    """createVelocityMatrices (L/WaterVelocities.cuh:38-70).  Returns V1[k, j], V2[k]."""
+    Z = np.asarray(Z, np.complex128)
+    C = _cot_green(Z)
+    V1 = 1j * (-1.0 / (4.0 * PI) * C)
+    diag = 1j * (-1.0 / (4.0 * PI) * Zpp / np.power(Zp, 2.0))
+    diag = diag + 1.0 / (2.0 * Zp) if lower else diag - 0.5 / Zp
+    np.fill_diagonal(V1, diag)
+    V2 = 1j * (1.0 / (2.0 * PI * Zp))
+    return V1, V2
+
+
+def helium_velocity_matrices(Z, Zp, Zpp, h: float, lower: bool = True, infinite_depth: bool = False):
+    """createHeliumVelocityMatrices (L/WaterVelocities.cuh:72-107)."""
+    Z = np.asarray(Z, np.complex128)
+    C = _cot_green(Z)
+    V1 = 1j * (-1.0 / (4.0 * PI) * C)
+    diag = 1j * (-1.0 / (4.0 * PI) * Zpp / np.power(Zp, 2.0))
+    if not infinite_depth:
+        V1 = V1 + 1j * (1.0 / (4.0 * PI) * cot(0.5 * (Z[:, None] - np.conj(Z)[None, :]) + 1j * h))
+        diag = diag + 1j * (1.0 / (4.0 * PI) * cot(1j * (Z.imag + h)))
+    diag = diag + 1.0 / (2.0 * Zp) if lower else diag - 0.5 / Zp
+    np.fill_diagonal(V1, diag)
+    V2 = 1j * (1.0 / (2.0 * PI * Zp))
+    return V1, V2
+
+
+# --------------------------------------------------------------------------
+# dPhi/dt
+# --------------------------------------------------------------------------
+def rhs_phi_water(Z, V1, V2, rho: float):
+    """compute_rhs_phi_expression (L/createM.cuh:96-107) including the V1[1] quirk on the dot product."""
+    v1a = V1.real ** 2 + V1.imag ** 2
+    v2a = V2.real ** 2 + V2.imag ** 2
+    dot = V1[1].real * V2.real + V1.imag * V2.imag
+    return -(1 + rho) * Z.imag + 0.5 * v1a + 0.5 * rho * v2a - rho * dot
+
+
+def rhs_phi_helium(Z, V1, h: float):
+    """compute_rhs_helium_phi_expression (L/createM.cuh:109-117)."""
+    vdw = h / 3.0
+    return vdw * np.power(1.0 + Z.imag / h, -3.0) - vdw + 0.5 * V1.real * V1.real + 0.5 * V1.imag * V1.imag
+
+
+def rhs_phi_helium_surface_tension(Z, Zp, Zpp, V1, h: float, kappa: float):
+    """compute_rhs_helium_phi_expression_with_surface_tension (L/createM.cuh:195-211)."""
+    curv = (Zp.real * Zpp.imag - Zp.imag * Zpp.real) / np.power(Zp.real ** 2 + Zp.imag ** 2, 1.5)
+    v1a = V1.real ** 2 + V1.imag ** 2
+    return 20.447761896665416 * h / 3.0 * (1.0 / np.power(1.0 + Z.imag / h, 3) - 1) + 0.5 * v1a + kappa * curv
+
+
+def rhs_phi_helium_expansion(Z, V1, h: float, order: int = 2):
+    """compute_rhs_helium_phi_expression_expansion_terms (L/createM.cuh:171-193); switch fall-through."""
+    kin = 0.5 * V1.real * V1.real + 0.5 * V1.imag * V1.imag
+    vdw = np.zeros_like(kin)
+    if order == 3:
+        vdw = vdw + (-10.0 / 3.0 * np.power(Z.imag, 3.0) / (h * h))
+    if order in (2, 3):
+        vdw = vdw + 2.0 * np.power(Z.imag, 2.0) / h
+    if order in (1, 2, 3):
+        vdw = vdw + (-Z.imag)
+    return vdw + kin
+
+
+# --------------------------------------------------------------------------
+# one RHS (L/BaseBoundaryIntegrator.cuh:138-306)
+# --------------------------------------------------------------------------
+PHYSICS = ("water", "helium", "helium_inf")
+
+
+def rhs_single(Z, Phi, props: ProblemProperties, physics: str = "water", deriv: str = "cuda", full: bool = False):
+    """One RHS evaluation for one surface.  Returns (velocities u+iv, dPhi/dt[, intermediates])."""
+    n = len(Z)
+    Z = np.asarray(Z, np.complex128)
+    Zp, PhiPc, Zpp = zphi_derivative(Z, Phi, props, deriv)
+    b = PhiPc.real.copy()  # complex_to_real, L/BaseBoundaryIntegrator.cuh:299
+    if physics == "water":
+        M = create_M(Z, Zp, Zpp, props.rho)  # L/WaterBoundaryProblem.cuh:19
+    elif physics == "helium":
+        M = create_finite_depth_M(Z, Zp, Zpp, props.depth, props.infinite_depth)  # L/HeliumBoundaryProblem.cuh:17
+    elif physics == "helium_inf":
+        M = create_M(Z, Zp, Zpp, props.depth)  # depth in the rho slot, L/HeliumBoundaryProblem.cuh:61 (quirk 6)
+    else:
+        raise ValueError(physics)
+    a = np.linalg.solve(M, b)  # MatrixSolver::solve, partial-pivot LU, L/MatrixSolver.cuh:114-125
+    ap = fft_derivative(a.astype(np.complex128), 2.0 * PI / n, deriv=deriv)  # L/BaseBoundaryIntegrator.cuh:201-203
+
+    def vel(lower):
+        if physics == "helium":
+            V1, V2 = helium_velocity_matrices(Z, Zp, Zpp, props.depth, lower, props.infinite_depth)
+        else:
+            V1, V2 = velocity_matrices(Z, Zp, Zpp, lower)
+        w = V2 * ap + V1 @ a.astype(np.complex128)  # L/WaterVelocities.cuh:217-224
+        return np.conj(w)  # :241
+
+    v_lower = vel(True)
+    v_upper = vel(False)
+    if physics == "water":
+        dphi = rhs_phi_water(Z, v_lower, v_upper, props.rho)
+    elif physics == "helium":
+        if props.use_expansions:
+            dphi = rhs_phi_helium_expansion(Z, v_lower, props.depth, props.expansion_order)
+        elif props.kappa != 0.0:
+            dphi = rhs_phi_helium_surface_tension(Z, Zp, Zpp, v_lower, props.depth, props.kappa)
+        else:
+            dphi = rhs_phi_helium(Z, v_lower, props.depth)
+    else:
+        dphi = rhs_phi_helium(Z, v_lower, props.depth)
+    if full:
+        return v_lower, dphi, dict(Zp=Zp, Zpp=Zpp, PhiPrime=b, M=M, a=a, aprime=ap, v_upper=v_upper)
+    return v_lower, dphi
+
+
+def rhs(state: np.ndarray, N: int, batch: int, props: ProblemProperties, physics="water", deriv="cuda") -> np.ndarray:
+    """AutonomousProblem::run on the packed complex state [Z_b0..Z_b(B-1) | Phi_b0..] (L/BaseBoundaryIntegrator.cuh:141-146)."""
+    state = np.asarray(state, np.complex128)
+    out = np.zeros_like(state)
+    for b in range(batch):
+        Z = state[b * N:(b + 1) * N]
+        Phi = state[batch * N + b * N: batch * N + (b + 1) * N]
+        v, dphi = rhs_single(Z, Phi, props, physics, deriv)
+        out[b * N:(b + 1) * N] = v
+        out[batch * N + b * N: batch * N + (b + 1) * N] = dphi
+    return out
+
+
+# --------------------------------------------------------------------------
+# classical RK4 (L/AutonomousRungeKuttaStepper.cuh:124-307, 344-374, 418-437)
+# --------------------------------------------------------------------------
+def rk4_step(f, y0: np.ndarray, dt: float) -> np.ndarray:
+    k1 = f(y0)
+    y1 = y0 + (dt * 0.5) * k1
+    k2 = f(y1)
+    y2 = y0 + (dt * 0.5) * k2
+    k3 = f(y2)
+    y3 = y0 + dt * k3
+    k4 = f(y3)
+    ksum = k1 + 2.0 * k2 + 2.0 * k3 + k4  # add_k_vectors, L/utilities.cuh:78-83
+    return y0 + (dt / 6.0) * ksum
+
+
+def rk4_num_steps(t0: float, t1: float, dt: float) -> int:
+    """steps = size_t((t1 - t0)/dt), truncation (L/AutonomousRungeKuttaStepper.cuh:421)."""
+    return int((t1 - t0) / dt)
+
+
+def rk4_evolve(f, y0: np.ndarray, t0: float, t1: float, dt: float, trajectory: bool = False):
+    y = np.array(y0, np.complex128)
+    steps = rk4_num_steps(t0, t1, dt)
+    t = t0
+    times, states = [], []
+    for _ in range(steps):
+        y = rk4_step(f, y, dt)
+        t += dt
+        if trajectory:
+            times.append(t)
+            states.append(y.copy())
+    if trajectory:
+        return y, np.array(times), np.array(states)
+    return y
+
+
+# --------------------------------------------------------------------------
+# diagnostics (L/Energies.cuh:136-204 functors, scaling :61-128); batch 0 only
+# --------------------------------------------------------------------------
+def energies(Z, Zp, Phi, vel, props: ProblemProperties, physics="water") -> dict:
+    Z = np.asarray(Z, np.complex128)
+    Phi = np.asarray(Phi, np.complex128)
+    U, rho = props.U, props.rho
+    kin = (Phi.real + 0.5 * U * (1.0 + rho) * Z.real) * (-1.0 * Zp.imag * vel.real + Zp.real * vel.imag) \
+        - 0.5 * U * ((vel.real + rho * vel.real) * Zp.real + (vel.imag + rho * vel.imag) * Zp.imag
+                     + 0.5 * U * (1.0 - rho) * Zp.real) * Z.imag
+    out = {"kinetic": kin.sum() * 0.25 / PI}
+    if physics == "water":
+        out["potential"] = (Z.imag * Z.imag * Zp.real).sum() * 0.25 * (1.0 + rho) / PI
+    else:
+        out["potential"] = (1 / np.power(1 + Z.imag / props.depth, 2) - 1.0).sum() * props.depth ** 2 / 6.0
+    out["surface"] = (np.sqrt(Zp.real ** 2 + Zp.imag ** 2).sum() - 2.0 * PI) * props.kappa / (2.0 * PI)
+    out["volume_flux"] = (vel.imag * Zp.real + vel.real * Zp.imag).sum() * 0.5 / PI
+    return out
+
+
+def volume(Z, Zp) -> float:
+    """Area under the surface per period, sum Y_j X'_j (SURVEY.md section 8d 'Parity')."""
+    return float((Z.imag * Zp.real).sum())
+
+
+# --------------------------------------------------------------------------
+# blocked row sample of the M*x / velocity operators (CPU baseline at N too large
+# for a dense matrix)
+# --------------------------------------------------------------------------
+def cot_rowsum(Z, x, rows) -> np.ndarray:
+    """S_k = sum_{j != k} cot((Z_k - Z_j)/2) x_j for the listed rows k."""
+    Z = np.asarray(Z, np.complex128)
+    rows = np.asarray(rows)
+    d = 0.5 * (Z[rows, None] - Z[None, :])
+    d[np.arange(len(rows)), rows] = 1.0
+    C = cot(d)
+    C[np.arange(len(rows)), rows] = 0.0
+    return C @ np.asarray(x, np.complex128)
