@@ -1,0 +1,206 @@
+/* roberts_b200.h -- C ABI of libroberts_b200.so
+ *
+ * B200-native (sm_100a) implementation of the Roberts (1983) boundary-integral
+ * RK4 time step of CuSuperHelium.  Plain pointers and sizes only; every entry
+ * point names the reference interface it replaces (paths relative to the
+ * reference repository; L/ = CuSuperHelium/CuSuperHelium/).
+ *
+ * Conventions
+ *   - all functions return 0 on success, -1 on error (message on stderr and in
+ *     rb_last_error()), like the reference exports (L/Export.cu: try/catch -> -1).
+ *   - "dev" pointers are CUDA device pointers on the handle's device; "host"
+ *     pointers are ordinary host memory.
+ *   - complex numbers are interleaved (re, im) doubles, 16-byte aligned
+ *     (== cuda::std::complex<double> == c_double, L/constants.cuh:12, L/ExportTypes.cuh:7).
+ *   - state layout [Z_b0 .. Z_b(B-1) | Phi_b0 .. Phi_b(B-1)], 2*B*N complex
+ *     (L/BaseBoundaryIntegrator.cuh:141-145); rhs layout [u+iv | dPhi/dt + 0i].
+ *   - N and the batch size are runtime values (the reference fixes them as
+ *     template parameters and dispatches through switch tables, L/Export.cu:560-599).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef ROBERTS_B200_H
+#define ROBERTS_B200_H
+
+#include <stddef.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RB_API __declspec(dllexport)
+#else
+#define RB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct rb_complex { double re, im; } rb_complex;      /* L/ExportTypes.cuh:7 c_double */
+typedef struct rb_solver rb_solver;                           /* opaque: one RHS assembler + work buffers */
+typedef struct rb_stepper rb_stepper;                         /* opaque: RK4 stepper bound to a solver */
+
+/* physics plugin selector == which BoundaryProblem<N,B> subclass the reference would instantiate */
+enum rb_physics {
+    RB_WATER = 0,        /* WaterBoundaryProblem            L/WaterBoundaryProblem.cuh:8-39   */
+    RB_HELIUM = 1,       /* HeliumBoundaryProblem           L/HeliumBoundaryProblem.cuh:6-47  */
+    RB_HELIUM_INF = 2    /* HeliumInfiniteDepthBoundaryProblem  L/HeliumBoundaryProblem.cuh:50-81 */
+};
+
+/* how the vortex-sheet strength system M a = Re(Phi') is solved (replaces MatrixSolver<N,B>::solve,
+ * L/MatrixSolver.cuh:114-172, cuSOLVER LU) */
+enum rb_solve_mode {
+    RB_SOLVE_MATRIX_FREE = 0,  /* Richardson/Neumann iteration on the second-kind system, M never stored */
+    RB_SOLVE_DENSE_LU = 1      /* assemble M in HBM, in-place partial-pivot LU (validation path, small N) */
+};
+
+/* how the iteration is started */
+enum rb_guess_mode {
+    RB_GUESS_COLD = 0,     /* a0 = omega * b (first Neumann term); results independent of call history */
+    RB_GUESS_WARM = 1      /* previous solution of this solver (or the stepper's stage history) */
+};
+
+/* mirrors ProblemProperties (L/ProblemProperties.hpp:5-32), nondimensional values */
+typedef struct rb_props {
+    double rho;            /* density ratio upper/lower                                    */
+    double U;              /* mean shear; Phi carries the linear part -(1+rho) pi U j / N  */
+    double kappa;          /* surface tension                                              */
+    double depth;          /* film depth h (helium)                                        */
+    int use_expansions;    /* HeliumBoundaryProblem::CalculateRhsPhi switch, :35-46        */
+    int expansion_order;
+    int infinite_depth;
+    int physics;           /* enum rb_physics                                              */
+    int solve_mode;        /* enum rb_solve_mode                                           */
+    int guess_mode;        /* enum rb_guess_mode                                           */
+    int max_iterations;    /* cap on M*x applications per solve (0 -> default 200)         */
+    int compute_energies;  /* 1: evaluate the Energies.cuh sums on every RHS (reference behaviour) */
+    double tolerance;      /* relative residual ||b - M a|| / ||b|| (0 -> default 1e-13)   */
+} rb_props;
+
+/* ---- library / device ---------------------------------------------------------------- */
+RB_API const char* rb_last_error(void);
+RB_API int rb_version(void);
+RB_API int rb_device_count(void);                 /* 0 without a GPU; never falls back to the CPU */
+RB_API int rb_set_device(int device);             /* replaces setDevice(), L/utilities.cuh:15-27 (device 0 hard-wired there) */
+RB_API void rb_default_props(rb_props* p);        /* ProblemProperties defaults, water, rho = 0 */
+
+/* ---- RHS assembler == BaseBoundaryIntegralCalculator<N,B> (L/BaseBoundaryIntegrator.cuh:10-85) ---- */
+RB_API rb_solver* rb_create(int N, int batch, const rb_props* props);            /* ctor  :89-108  */
+RB_API int rb_destroy(rb_solver* s);                                             /* dtor  :111-135 */
+RB_API int rb_set_stream(rb_solver* s, void* cuda_stream);                       /* setStream :37-40 */
+RB_API int rb_rhs(rb_solver* s, const rb_complex* state_dev, rb_complex* rhs_dev);   /* run / runTimeStep :138-273, 310-314 */
+RB_API int rb_vorticities(rb_solver* s, const rb_complex* state_dev);            /* calculateVorticities :276-306 */
+RB_API double* rb_dev_a(rb_solver* s);                                           /* getDevA   :21-24 */
+RB_API rb_complex* rb_dev_zp(rb_solver* s);                                      /* getDevZp  :25-27 */
+RB_API rb_complex* rb_dev_zpp(rb_solver* s);                                     /* getDevZpp :28-30 */
+RB_API rb_complex* rb_dev_velocities_upper(rb_solver* s);                        /* devVelocitiesUpper :43 */
+RB_API double* rb_dev_phi_prime(rb_solver* s);                                   /* devPhiPrime :46 */
+RB_API int rb_synchronize(rb_solver* s);
+/* energies of the last RHS: out[0] kinetic, [1] potential (gravitational or van der Waals), [2] surface,
+ * [3] volume flux, [4] volume sum(Y X').  Replaces EnergyBase::getEnergy x4 (L/Energies.cuh:229-235) + VolumeFlux. */
+RB_API int rb_energies(rb_solver* s, double out_host[5]);
+/* statistics of the last solve: out[0] M*x applications, [1] converged flag, [2] relative residual */
+RB_API int rb_solve_stats(rb_solver* s, double out_host[3]);
+
+/* ---- spectral derivatives (L/Derivatives.cuh) ---- */
+/* ZPhiDerivative<N,B>::exec :311-384 */
+RB_API int rb_zphi_derivative(rb_solver* s, const rb_complex* Z_dev, const rb_complex* Phi_dev,
+                              rb_complex* Zp_dev, rb_complex* PhiPrime_dev, rb_complex* Zpp_dev);
+/* FftDerivative<N,B>::exec :190-257 (second != 0 -> doubleDev) */
+RB_API int rb_fft_derivative(rb_solver* s, const rb_complex* in_dev, rb_complex* out_dev, int second, double scaling);
+
+/* ---- kernels the reference's tests launch by name (materialised, column-major A[k + j*n + b*n*n]) ---- */
+RB_API int rb_create_M(double* A_dev, const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp,
+                       double rho, int n, size_t batch, void* stream);                            /* createMKernel L/createM.cuh:43-63 */
+RB_API int rb_create_finite_depth_M(double* A_dev, const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp,
+                                    double h, int n, size_t batch, int infinite_depth, void* stream); /* createFiniteDepthMKernel :65-92 */
+RB_API int rb_velocity_matrices(const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp, int n,
+                                rb_complex* V1, rb_complex* V2, int lower, size_t batch, void* stream); /* createVelocityMatrices L/WaterVelocities.cuh:38-70 */
+RB_API int rb_helium_velocity_matrices(const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp, double h, int n,
+                                       rb_complex* V1, rb_complex* V2, int lower, size_t batch, int infinite_depth,
+                                       void* stream);                                             /* createHeliumVelocityMatrices :72-107 */
+RB_API int rb_rhs_phi_water(const rb_complex* Z, const rb_complex* V1, const rb_complex* V2, rb_complex* result,
+                            double rho, int n, void* stream);                                     /* compute_rhs_phi_expression L/createM.cuh:96-107 */
+RB_API int rb_rhs_phi_helium(const rb_complex* Z, const rb_complex* V1, rb_complex* result, double h, int n,
+                             void* stream);                                                       /* compute_rhs_helium_phi_expression :109-117 */
+RB_API int rb_rhs_phi_helium_surface_tension(const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp,
+                                             const rb_complex* V1, rb_complex* result, double h, double kappa, int n,
+                                             void* stream);                                       /* ..._with_surface_tension :200-211 */
+RB_API int rb_rhs_phi_helium_expansion(const rb_complex* Z, const rb_complex* V1, rb_complex* result, double h, int n,
+                                       int order, void* stream);                                  /* ..._expansion_terms :171-193 */
+/* materialised operator applied by this library's own kernels: y = V1*a + V2.*aprime, conj (VelocityCalculator, L/WaterVelocities.cuh:206-242) */
+RB_API int rb_cotangent_sum(rb_solver* s, const rb_complex* Z_dev, const double* x_dev, rb_complex* S_dev);
+                                                  /* S_k = sum_{j!=k} cot((Z_k-Z_j)/2) x_j, the matrix-free core (needs Zp/Zpp: call after rb_vorticities or rb_zphi_derivative) */
+
+/* ---- RK4 stepper == AutonomousRungeKuttaStepper<std_complex, 2N> (L/AutonomousRungeKuttaStepper.cuh:24-121) ---- */
+RB_API rb_stepper* rb_rk4_create(rb_solver* s, double tstep);                    /* ctor :91-105 */
+RB_API int rb_rk4_destroy(rb_stepper* st);
+RB_API int rb_rk4_set_time_step(rb_stepper* st, double tstep);                   /* setTimeStep :31-36 */
+RB_API int rb_rk4_initialize(rb_stepper* st, rb_complex* y0, int on_device);     /* initialize :310-329: on_device aliases the caller's buffer */
+RB_API int rb_rk4_step(rb_stepper* st);                                          /* runStep :124-307 */
+/* runEvolution :418-437: steps = size_t((t1-t0)/dt); returns the number of steps taken through *steps_out */
+RB_API int rb_rk4_evolve(rb_stepper* st, double t0, double t1, size_t* steps_out);
+RB_API int rb_rk4_run_steps(rb_stepper* st, size_t steps);                       /* the hot loop without the time bookkeeping */
+RB_API rb_complex* rb_rk4_dev_state(rb_stepper* st);                             /* devY0 */
+RB_API int rb_rk4_get_state(rb_stepper* st, rb_complex* y_host);                 /* D2H of devY0 */
+RB_API double rb_rk4_current_time(rb_stepper* st);
+/* trajectory logging (TrajectoryLogger<T,N>, L/TrajectoryLogger.cuh:7-73): every `every` steps into a device ring, 0 = off */
+RB_API int rb_rk4_set_logging(rb_stepper* st, size_t every, size_t capacity);
+RB_API int rb_rk4_copy_trajectory(rb_stepper* st, double** times_out, size_t* times_count,
+                                  rb_complex** states_out, size_t* states_count);  /* copyTimesToHost/copyStatesToHost; free with rb_free */
+RB_API void rb_free(void* p);
+/* generic stage kernels (cublasZaxpy x4 + add_k_vectors, :349-361, L/utilities.cuh:78-83) for callers that own the loop */
+RB_API int rb_rk4_stage_update(rb_complex* y_out, const rb_complex* y0, const rb_complex* k, double c, size_t n, void* stream);
+RB_API int rb_rk4_final_update(rb_complex* y0, const rb_complex* k1, const rb_complex* k2, const rb_complex* k3,
+                               const rb_complex* k4, double h, size_t n, void* stream);
+
+/* ---- multi-GPU: row blocks of the interaction operators sharded over ranks (new; the reference is single-GPU) ---- */
+#define RB_UNIQUE_ID_BYTES 128
+RB_API int rb_comm_unique_id(char id_out[RB_UNIQUE_ID_BYTES]);                   /* rank 0; ship to the others out of band */
+RB_API int rb_comm_init(rb_solver* s, int rank, int nranks, const char id[RB_UNIQUE_ID_BYTES]);
+RB_API int rb_comm_destroy(rb_solver* s);
+
+/* ---- measurement helpers ---- */
+RB_API int rb_measure_fp64_peak(double* tflops_out, void* stream);               /* DFMA-only kernel: the FP64 roofline denominator */
+RB_API int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* ms_per_sweep_out, double* pairs_per_sweep_out);
+
+/* ---- legacy exports (same names and argument meaning as L/Export.cuh:27-70; SI inputs, nondimensionalised inside,
+ *      HeliumBoundaryProblem hard-wired as in L/Export.cu:205-207) ---- */
+RB_API int calculateRHSFromVectors(const double* x, const double* y, const double* phi, double* vx, double* vy, double* rhsPhi,
+                                   double L, double rho, double kappa, double depth, size_t N);       /* L/Export.cuh:31 */
+RB_API int calculateRHS256FromVectors(const double* x, const double* y, const double* phi, double* vx, double* vy,
+                                      double* rhsPhi, double L, double rho, double kappa, double depth); /* :30 */
+RB_API int calculateRHS2048FromVectors(const double* x, const double* y, const double* phi, double* vx, double* vy,
+                                       double* rhsPhi, double L, double rho, double kappa, double depth); /* :33 */
+RB_API int calculateRHS256FromVectorsBatched(const double* x, const double* y, const double* phi, double* vx, double* vy,
+                                             double* rhsPhi, double L, double rho, double kappa, double depth,
+                                             int batchSize);                                           /* :51 */
+RB_API int calculateVorticities256FromVectors(const rb_complex* Z, const rb_complex* phi, double* a, rb_complex* Zp,
+                                              rb_complex* Zpp, double L, double rho, double kappa, double depth); /* :48 */
+RB_API int calculateDerivativeFFT256(const rb_complex* input, rb_complex* output);                     /* :49 */
+
+typedef struct SimProperties {            /* L/ExportTypes.cuh:8-20 */
+    double L, rho, kappa, depth;
+    bool use_expansions;
+    int expansion_order;
+    bool infinite_depth;
+} SimProperties;
+typedef struct RK4SolverOptions {         /* L/ExportTypes.cuh:35-40 */
+    double timeStep, t0, t1;
+    bool returnTrajectory;
+} RK4SolverOptions;
+/* declared by the reference (L/Export.cuh:69-70) but a stub there (L/Export.cu:767-777); implemented here.
+ * initialState = [x | y | phi] (3N doubles, SI time in the options, lengths already in units of L/2pi as the
+ * reference's callers pass them); *statesOut = statesCount x 3N doubles, *timesOut = timesCount doubles, malloc'd;
+ * release with integrateSimulationRK4_freeMemory. */
+RB_API int integrateSimulationRK4(double* initialState, double** statesOut, size_t* statesCount, double** timesOut,
+                                  size_t* timesCount, SimProperties* simProperties, RK4SolverOptions* rkOptions, size_t N);
+RB_API int integrateSimulationRK4_freeMemory(double* statesOut, double* timesOut);
+/* nondimensional variant of the same call (no SI conversion, physics selectable): the plain RK4 path used by bench.py's e2e leg */
+RB_API int rb_integrate_rk4_host(const double* initialState_host, double* finalState_host, size_t N, size_t batch,
+                                 const rb_props* props, double dt, size_t steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBERTS_B200_H */

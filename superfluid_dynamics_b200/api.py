@@ -1,0 +1,357 @@
+"""Host-side mirror of the reference's solver / time-stepper interface for the Roberts BIE RK4 path.
+
+Class and method names follow CuSuperHelium (L/ = CuSuperHelium/CuSuperHelium/):
+    ProblemProperties                    L/ProblemProperties.hpp:5-32
+    WaterBoundaryProblem / HeliumBoundaryProblem / HeliumInfiniteDepthBoundaryProblem
+                                         L/WaterBoundaryProblem.cuh, L/HeliumBoundaryProblem.cuh
+    BaseBoundaryIntegralCalculator       L/BaseBoundaryIntegrator.cuh:10-85   (run, runTimeStep, calculateVorticities, getDevA..)
+    AutonomousRungeKuttaStepper          L/AutonomousRungeKuttaStepper.cuh:24-121 (initialize, runStep, runEvolution, setTimeStep)
+    createMKernel, createFiniteDepthMKernel, createVelocityMatrices, createHeliumVelocityMatrices,
+    compute_rhs_phi_expression, ...      the kernels the reference's tests launch by name
+Device memory is held in torch tensors (complex128 / float64 on a CUDA device); every computation goes through the C ABI of
+libroberts_b200.so.  N and the batch size are runtime values here (template parameters in the reference).
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+PHYSICS = {"water": _lib.RB_WATER, "helium": _lib.RB_HELIUM, "helium_inf": _lib.RB_HELIUM_INF}
+
+
+@dataclasses.dataclass
+class ProblemProperties:
+    """L/ProblemProperties.hpp:5-32 (nondimensional)."""
+    L: float = 1.0
+    rho: float = 1.0
+    U: float = 0.0
+    kappa: float = 0.0
+    depth: float = 1.0
+    initial_amplitude: float = 1.0
+    use_expansions: bool = False
+    expansion_order: int = 1
+    infinite_depth: bool = False
+
+
+class _BoundaryProblem:
+    physics = "water"
+
+    def __init__(self, properties: ProblemProperties):
+        self.properties = properties
+
+
+class WaterBoundaryProblem(_BoundaryProblem):
+    physics = "water"
+
+
+class HeliumBoundaryProblem(_BoundaryProblem):
+    physics = "helium"
+
+
+class HeliumInfiniteDepthBoundaryProblem(_BoundaryProblem):
+    physics = "helium_inf"
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device tensors must be contiguous CUDA tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _DevView:
+    """Zero-copy view of library-owned device memory as a torch tensor (float64)."""
+
+    def __init__(self, ptr, n_doubles, device_index):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+        self._dev = device_index
+
+
+def _view(ptr, n_doubles, device, complex_=False):
+    t = torch.as_tensor(_DevView(ptr, n_doubles, device.index), device=device)
+    return torch.view_as_complex(t.view(-1, 2)) if complex_ else t
+
+
+class BaseBoundaryIntegralCalculator:
+    """RHS assembler: BaseBoundaryIntegralCalculator<N, batchSize>(ProblemProperties&, BoundaryProblem<N,batchSize>&)."""
+
+    def __init__(self, N: int, batchSize: int, problemProperties: ProblemProperties, boundaryProblem: _BoundaryProblem = None,
+                 device=None, solve_mode: str = "matrix_free", guess: str = "cold", tolerance: float = 1e-13,
+                 max_iterations: int = 200, compute_energies: bool = False):
+        lib = _lib.load()
+        if lib.rb_device_count() == 0:
+            raise _lib.RobertsError("no CUDA device: superfluid_dynamics_b200 has no CPU path")
+        self.lib = lib
+        self.N, self.batchSize = int(N), int(batchSize)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.properties = problemProperties
+        physics = boundaryProblem.physics if boundaryProblem is not None else "water"
+        self.physics = physics
+        p = _lib.rb_props()
+        lib.rb_default_props(ctypes.byref(p))
+        p.rho, p.U, p.kappa, p.depth = problemProperties.rho, problemProperties.U, problemProperties.kappa, problemProperties.depth
+        p.use_expansions = int(problemProperties.use_expansions)
+        p.expansion_order = int(problemProperties.expansion_order)
+        p.infinite_depth = int(problemProperties.infinite_depth)
+        p.physics = PHYSICS[physics]
+        p.solve_mode = _lib.RB_SOLVE_DENSE_LU if solve_mode == "dense_lu" else _lib.RB_SOLVE_MATRIX_FREE
+        p.guess_mode = _lib.RB_GUESS_WARM if guess == "warm" else _lib.RB_GUESS_COLD
+        p.max_iterations = max_iterations
+        p.compute_energies = int(compute_energies)
+        p.tolerance = tolerance
+        self._props = p
+        with torch.cuda.device(self.device):
+            check(lib.rb_set_device(self.device.index), "rb_set_device")
+            self.handle = lib.rb_create(self.N, self.batchSize, ctypes.byref(p))
+        if not self.handle:
+            raise _lib.RobertsError("rb_create: " + lib.rb_last_error().decode())
+        self.setStream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.rb_destroy(h)
+
+    # --- AutonomousProblem<std_complex, 2N*batch> ---
+    def setStream(self, stream):
+        check(self.lib.rb_set_stream(self.handle, ctypes.c_void_p(int(stream))), "rb_set_stream")
+
+    def run(self, initialState: torch.Tensor, rhs: torch.Tensor):
+        check(self.lib.rb_rhs(self.handle, _ptr(initialState), _ptr(rhs)), "rb_rhs")
+
+    runTimeStep = run
+
+    def calculateVorticities(self, initialState: torch.Tensor):
+        check(self.lib.rb_vorticities(self.handle, _ptr(initialState)), "rb_vorticities")
+
+    def getDevA(self):
+        return _view(self.lib.rb_dev_a(self.handle), self.N * self.batchSize, self.device)
+
+    def getDevZp(self):
+        return _view(self.lib.rb_dev_zp(self.handle), 2 * self.N * self.batchSize, self.device, True)
+
+    def getDevZpp(self):
+        return _view(self.lib.rb_dev_zpp(self.handle), 2 * self.N * self.batchSize, self.device, True)
+
+    @property
+    def devVelocitiesUpper(self):
+        return _view(self.lib.rb_dev_velocities_upper(self.handle), 2 * self.N * self.batchSize, self.device, True)
+
+    @property
+    def devPhiPrime(self):
+        return _view(self.lib.rb_dev_phi_prime(self.handle), self.N * self.batchSize, self.device)
+
+    def synchronize(self):
+        check(self.lib.rb_synchronize(self.handle), "rb_synchronize")
+
+    def energies(self):
+        out = (ctypes.c_double * 5)()
+        check(self.lib.rb_energies(self.handle, out), "rb_energies")
+        return dict(kinetic=out[0], potential=out[1], surface=out[2], volume_flux=out[3], volume=out[4])
+
+    def solve_stats(self):
+        out = (ctypes.c_double * 3)()
+        check(self.lib.rb_solve_stats(self.handle, out), "rb_solve_stats")
+        return dict(iterations=int(out[0]), converged=bool(out[1]), residual=out[2])
+
+    # --- derivatives (ZPhiDerivative / FftDerivative) ---
+    def zPhiDerivative(self, Z, Phi):
+        Zp, PhiP, Zpp = torch.empty_like(Z), torch.empty_like(Z), torch.empty_like(Z)
+        check(self.lib.rb_zphi_derivative(self.handle, _ptr(Z), _ptr(Phi), _ptr(Zp), _ptr(PhiP), _ptr(Zpp)), "rb_zphi_derivative")
+        return Zp, PhiP, Zpp
+
+    def fftDerivative(self, x, doubleDev=False, scaling=1.0):
+        out = torch.empty_like(x)
+        check(self.lib.rb_fft_derivative(self.handle, _ptr(x), _ptr(out), int(doubleDev), float(scaling)), "rb_fft_derivative")
+        return out
+
+    def cotangentSum(self, Z, x):
+        S = torch.empty_like(Z)
+        check(self.lib.rb_cotangent_sum(self.handle, _ptr(Z), _ptr(x), _ptr(S)), "rb_cotangent_sum")
+        return S
+
+    def benchSweep(self, state, reps=10):
+        ms, pairs = ctypes.c_float(), ctypes.c_double()
+        check(self.lib.rb_bench_sweep(self.handle, _ptr(state), reps, ctypes.byref(ms), ctypes.byref(pairs)), "rb_bench_sweep")
+        return ms.value, pairs.value
+
+
+class AutonomousRungeKuttaStepper:
+    """AutonomousRungeKuttaStepper<std_complex, 2N>(AutonomousProblem&, tstep, logger)."""
+
+    def __init__(self, autonomousProblem: BaseBoundaryIntegralCalculator, tstep: float = 1e-2):
+        self.problem = autonomousProblem
+        self.lib = autonomousProblem.lib
+        self.handle = self.lib.rb_rk4_create(autonomousProblem.handle, float(tstep))
+        if not self.handle:
+            raise _lib.RobertsError("rb_rk4_create: " + self.lib.rb_last_error().decode())
+        self._keep = None
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.rb_rk4_destroy(h)
+
+    def setTimeStep(self, tstep):
+        check(self.lib.rb_rk4_set_time_step(self.handle, float(tstep)), "rb_rk4_set_time_step")
+
+    def setOptions(self, initial_timestep):
+        self.setTimeStep(initial_timestep)
+
+    def initialize(self, devY0, onDevice=False):
+        if onDevice:
+            self._keep = devY0
+            check(self.lib.rb_rk4_initialize(self.handle, _ptr(devY0), 1), "rb_rk4_initialize")
+        else:
+            host = np.ascontiguousarray(np.asarray(devY0, dtype=np.complex128))
+            check(self.lib.rb_rk4_initialize(self.handle, host.ctypes.data_as(ctypes.c_void_p), 0), "rb_rk4_initialize")
+
+    def runStep(self, _step=0):
+        check(self.lib.rb_rk4_step(self.handle), "rb_rk4_step")
+
+    def runSteps(self, steps):
+        check(self.lib.rb_rk4_run_steps(self.handle, int(steps)), "rb_rk4_run_steps")
+
+    def runEvolution(self, startTime, endTime):
+        n = ctypes.c_size_t()
+        check(self.lib.rb_rk4_evolve(self.handle, float(startTime), float(endTime), ctypes.byref(n)), "rb_rk4_evolve")
+        return n.value
+
+    def getState(self):
+        n = 2 * self.problem.N * self.problem.batchSize
+        host = np.empty(n, np.complex128)
+        check(self.lib.rb_rk4_get_state(self.handle, host.ctypes.data_as(ctypes.c_void_p)), "rb_rk4_get_state")
+        return host
+
+    def currentTime(self):
+        return self.lib.rb_rk4_current_time(self.handle)
+
+    def setLogging(self, every, capacity):
+        check(self.lib.rb_rk4_set_logging(self.handle, int(every), int(capacity)), "rb_rk4_set_logging")
+
+    def copyTrajectory(self):
+        tp, tc = ctypes.POINTER(ctypes.c_double)(), ctypes.c_size_t()
+        sp, sc = ctypes.c_void_p(), ctypes.c_size_t()
+        check(self.lib.rb_rk4_copy_trajectory(self.handle, ctypes.byref(tp), ctypes.byref(tc), ctypes.byref(sp), ctypes.byref(sc)),
+              "rb_rk4_copy_trajectory")
+        n = 2 * self.problem.N * self.problem.batchSize
+        times = np.ctypeslib.as_array(tp, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
+        if sc.value:
+            buf = (ctypes.c_double * (2 * n * sc.value)).from_address(sp.value)
+            states = np.frombuffer(buf, dtype=np.complex128).reshape(sc.value, n).copy()
+        else:
+            states = np.zeros((0, n), np.complex128)
+        self.lib.rb_free(ctypes.cast(tp, ctypes.c_void_p))
+        self.lib.rb_free(sp)
+        return times, states
+
+
+# ---- the kernels the reference's tests launch by name ------------------------------------------
+def createMKernel(A, Z, Zp, Zpp, rho, n, batchSize=1):
+    check(_lib.load().rb_create_M(_ptr(A), _ptr(Z), _ptr(Zp), _ptr(Zpp), float(rho), int(n), int(batchSize), _stream_ptr(A.device)),
+          "rb_create_M")
+
+
+def createFiniteDepthMKernel(A, Z, Zp, Zpp, h, n, batchSize=1, infinite_depth=False):
+    check(_lib.load().rb_create_finite_depth_M(_ptr(A), _ptr(Z), _ptr(Zp), _ptr(Zpp), float(h), int(n), int(batchSize),
+                                               int(infinite_depth), _stream_ptr(A.device)), "rb_create_finite_depth_M")
+
+
+def createVelocityMatrices(Z, Zp, Zpp, N, out1, out2, lower=True, batchSize=1):
+    check(_lib.load().rb_velocity_matrices(_ptr(Z), _ptr(Zp), _ptr(Zpp), int(N), _ptr(out1), _ptr(out2), int(lower),
+                                           int(batchSize), _stream_ptr(Z.device)), "rb_velocity_matrices")
+
+
+def createHeliumVelocityMatrices(Z, Zp, Zpp, h, N, out1, out2, lower=True, batchSize=1, infinite_depth=False):
+    check(_lib.load().rb_helium_velocity_matrices(_ptr(Z), _ptr(Zp), _ptr(Zpp), float(h), int(N), _ptr(out1), _ptr(out2),
+                                                  int(lower), int(batchSize), int(infinite_depth), _stream_ptr(Z.device)),
+          "rb_helium_velocity_matrices")
+
+
+def compute_rhs_phi_expression(Z, V1, V2, result, rho, N):
+    check(_lib.load().rb_rhs_phi_water(_ptr(Z), _ptr(V1), _ptr(V2), _ptr(result), float(rho), int(N), _stream_ptr(Z.device)),
+          "rb_rhs_phi_water")
+
+
+def compute_rhs_helium_phi_expression(Z, V1, result, h, N):
+    check(_lib.load().rb_rhs_phi_helium(_ptr(Z), _ptr(V1), _ptr(result), float(h), int(N), _stream_ptr(Z.device)),
+          "rb_rhs_phi_helium")
+
+
+def compute_rhs_helium_phi_expression_with_surface_tension(Z, Zp, Zpp, V1, result, h, kappa, N):
+    check(_lib.load().rb_rhs_phi_helium_surface_tension(_ptr(Z), _ptr(Zp), _ptr(Zpp), _ptr(V1), _ptr(result), float(h),
+                                                        float(kappa), int(N), _stream_ptr(Z.device)),
+          "rb_rhs_phi_helium_surface_tension")
+
+
+def compute_rhs_helium_phi_expression_expansion_terms(Z, V1, result, h, N, order=2):
+    check(_lib.load().rb_rhs_phi_helium_expansion(_ptr(Z), _ptr(V1), _ptr(result), float(h), int(N), int(order),
+                                                  _stream_ptr(Z.device)), "rb_rhs_phi_helium_expansion")
+
+
+def measure_fp64_peak(device=None):
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    out = ctypes.c_double()
+    check(_lib.load().rb_measure_fp64_peak(ctypes.byref(out), _stream_ptr(device)), "rb_measure_fp64_peak")
+    return out.value
+
+
+# ---- legacy host-vector exports (L/Export.cuh) -------------------------------------------------
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def calculateRHSFromVectors(x, y, phi, L, rho, kappa, depth, batchSize=None):
+    lib = _lib.load()
+    x, y, phi = (np.ascontiguousarray(v, np.float64) for v in (x, y, phi))
+    vx, vy, dphi = np.empty_like(x), np.empty_like(x), np.empty_like(x)
+    if batchSize is None:
+        rc = lib.calculateRHSFromVectors(_dp(x), _dp(y), _dp(phi), _dp(vx), _dp(vy), _dp(dphi), L, rho, kappa, depth, x.size)
+    else:
+        rc = lib.calculateRHS256FromVectorsBatched(_dp(x), _dp(y), _dp(phi), _dp(vx), _dp(vy), _dp(dphi), L, rho, kappa, depth,
+                                                   int(batchSize))
+    check(rc, "calculateRHSFromVectors")
+    return vx, vy, dphi
+
+
+def integrateSimulationRK4(initialState, simProperties: _lib.SimProperties, rkOptions: _lib.RK4SolverOptions, N):
+    """Linux-safe binding of the export the reference declares (L/Export.cuh:69); structs go by reference."""
+    lib = _lib.load()
+    st = np.ascontiguousarray(initialState, np.float64)
+    so, to = ctypes.POINTER(ctypes.c_double)(), ctypes.POINTER(ctypes.c_double)()
+    sc, tc = ctypes.c_size_t(), ctypes.c_size_t()
+    check(lib.integrateSimulationRK4(_dp(st), ctypes.byref(so), ctypes.byref(sc), ctypes.byref(to), ctypes.byref(tc),
+                                     ctypes.byref(simProperties), ctypes.byref(rkOptions), int(N)), "integrateSimulationRK4")
+    states = np.ctypeslib.as_array(so, shape=(sc.value, 3 * N)).copy() if sc.value else np.zeros((0, 3 * N))
+    times = np.ctypeslib.as_array(to, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
+    lib.integrateSimulationRK4_freeMemory(so, to)
+    return states, times
+
+
+def integrate_rk4_host(initialState, N, batch, properties: ProblemProperties, physics, dt, steps, guess="warm",
+                       tolerance=1e-13):
+    lib = _lib.load()
+    p = _lib.rb_props()
+    lib.rb_default_props(ctypes.byref(p))
+    p.rho, p.U, p.kappa, p.depth = properties.rho, properties.U, properties.kappa, properties.depth
+    p.use_expansions, p.expansion_order = int(properties.use_expansions), int(properties.expansion_order)
+    p.infinite_depth = int(properties.infinite_depth)
+    p.physics = PHYSICS[physics]
+    p.guess_mode = _lib.RB_GUESS_WARM if guess == "warm" else _lib.RB_GUESS_COLD
+    p.tolerance = tolerance
+    st = np.ascontiguousarray(initialState, np.float64)
+    out = np.empty_like(st)
+    check(lib.rb_integrate_rk4_host(_dp(st), _dp(out), int(N), int(batch), ctypes.byref(p), float(dt), int(steps)),
+          "rb_integrate_rk4_host")
+    return out

@@ -1,0 +1,142 @@
+// internal.cuh -- shared declarations of libroberts_b200 (not part of the ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+namespace rb {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPiHi = 6.283185307179586;            // fl(2 pi)
+constexpr double kTwoPiLo = 2.4492935982947064e-16;       // 2 pi - fl(2 pi)
+
+// ---- tiling constants of the pair-interaction (cotangent-sum) kernels -------------------
+constexpr int kCell = 256;           // points per cell == targets (rows) per CTA == max source tile
+constexpr int kSweepThreads = 128;   // threads per CTA of the sweep kernel
+constexpr int kRowsPerThread = 2;    // register blocking: kCell == kSweepThreads * kRowsPerThread
+constexpr int kMinCellsForLocal = 4; // below this every tile uses the global exponentials
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess) {
+        throw std::runtime_error(std::string(what) + " failed at " + file + ":" + std::to_string(line) + ": " +
+                                 cudaGetErrorString(e));
+    }
+}
+#define RB_CUDA(x) ::rb::cuda_check((x), #x, __FILE__, __LINE__)
+
+// per-solve control block living in device memory (read by every sweep CTA)
+struct SolveCtrl {
+    int done;            // 1: converged (or gave up) -> later sweeps of this solve return immediately
+    int iters;           // M*x applications performed
+    int final_buf;       // which of the two iterate buffers holds the answer
+    int converged;       // 1 if the tolerance was met
+    double rel2;         // last max_b ||r||^2/||b||^2
+    double prev_rel2;
+    unsigned long long max_rel2_bits;   // atomicMax accumulator over batch members (non-negative doubles order as uint64)
+    unsigned int members_done;          // level-3 ticket
+    unsigned int pad;
+};
+
+// geometry of the surface, per point; all arrays are [batch][N]
+struct Geometry {
+    const double2* Z;      // surface points
+    double2* Zp;           // dZ/dj
+    double2* Zpp;          // d2Z/dj2
+    double2* EG;           // exp(i z)                      global exponentials
+    double2* P0;           // expm1(i (z - zc[cell(z)]))    local, own cell centre
+    double2* Pm;           // ... relative to the previous cell's centre
+    double2* Pp;           // ... relative to the next cell's centre
+    double2* EI;           // exp(i (conj z - 2 i h))       image sources (finite-depth helium) or nullptr
+    double* Mdiag;         // diagonal of M
+    double2* V1diag;       // diagonal of V1 (lower fluid)
+    double2* V2;           // i / (2 pi Zp)
+    double* b;             // Re(Phi')
+};
+
+enum SweepMode { kSweepMV = 0, kSweepVEL = 1, kSweepRAW = 2 };
+
+struct SweepArgs {
+    // sizes
+    int N, batch, ncell;             // ncell = ceil(N / kCell)
+    int tile;                        // sources per smem tile (64, 128 or 256; divides kCell)
+    int tiles_per_chunk;             // source tiles handled by one CTA
+    int nchunks;                     // gridDim.y
+    int row_cell0, row_cells;        // this rank's range of row cells (multi-GPU row sharding)
+    int use_local;                   // near-field tiles use cell-local exponentials
+    int has_image;                   // finite-depth helium image sum
+    // inputs
+    Geometry g;
+    const double* x;                 // MV: iterate in; VEL/RAW: strengths a (real), [batch][N]
+    double* x_out;                   // MV: iterate out
+    const double* xsum_part;         // [batch][ncell] partial sums of x per cell (producer epilogue)
+    double* xsum_part_out;           // MV: partial sums of the new iterate
+    double* rnorm_part;              // MV: [batch][ncell] partial sums of r^2
+    const double* bnorm_part;        // [batch][ncell] partial sums of b^2
+    // workspaces
+    double2* partial;                // [batch][nchunks][N] partial T sums
+    double2* partial_img;            // same for the image sum
+    unsigned int* cell_tickets;      // [batch][ncell]   level-1 counters (zero on entry, reset on exit)
+    unsigned int* member_tickets;    // [batch]          level-2 counters
+    SolveCtrl* ctrl;
+    // physics
+    double cK;                       // (1-rho)/(4 pi)   (helium: 1/(4 pi))
+    double omega;                    // Richardson relaxation 2/(1+rho)
+    double rho;
+    double depth;
+    double tol2;                     // tolerance^2
+    int max_iters;
+    int rhs_phi_kind;                // VEL epilogue: 0 none, 1 water rho==0, 2 helium vdw, 3 helium expansion, 4 helium + surface tension
+    int expansion_order;
+    double kappa;
+    int skip_if_done;                // MV sweeps: return at once when ctrl->done
+    int out_buf;                     // MV sweeps: index (0/1) of the iterate buffer x_out lives in
+    // VEL outputs
+    const double2* aprime;           // da/dj (complex, imaginary part kept as the reference does)
+    double2* vel_lower;              // u + i v   -> rhs[0 .. BN)
+    double2* vel_upper;              // upper-fluid velocities
+    double2* dphi;                   // dPhi/dt + 0 i -> rhs[BN .. 2BN)  (nullptr: separate kernel)
+    double2* raw_out;                // RAW: S_k = sum_{j!=k} cot((z_k - z_j)/2) x_j
+};
+
+// ---- launch wrappers (each defined in the .cu named in the comment) -----------------------
+// pair_kernels.cu
+void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int batch, int ncell, int physics,
+                     double rhoM, double depth, int finite_image, int use_local, cudaStream_t st);
+void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st);
+void launch_guess(const double* b, const double* warm, double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl,
+                  double omega, int N, int batch, int ncell, cudaStream_t st);
+// spectral.cu
+void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, double2* out_phiper, int N, int batch,
+                       double rho, double U, cudaStream_t st);
+void launch_spectral_multiply_zphi(const double2* hatZ, const double2* hatPhi, double2* out_d1z, double2* out_d2z,
+                                   double2* out_d1phi, int N, int batch, cudaStream_t st);
+void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch, int second, cudaStream_t st);
+void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int batch, double rho, double U, cudaStream_t st);
+void launch_scale(double2* v, double s, size_t n, cudaStream_t st);
+void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
+                         double* xsum_part, int N, int batch, int ncell, cudaStream_t st);
+// dense_kernels.cu
+void launch_create_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double rho, int n, size_t batch,
+                     cudaStream_t st);
+void launch_create_finite_depth_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double h, int n,
+                                  size_t batch, bool infinite_depth, cudaStream_t st);
+void launch_velocity_matrices(const double2* Z, const double2* Zp, const double2* Zpp, int n, double2* V1, double2* V2,
+                              bool lower, size_t batch, bool helium, double h, bool infinite_depth, cudaStream_t st);
+void launch_rhs_phi_water(const double2* Z, const double2* V1, const double2* V2, double2* result, double rho, int n,
+                          cudaStream_t st);
+void launch_rhs_phi_helium(const double2* Z, const double2* V1, double2* result, double h, int n, cudaStream_t st);
+void launch_rhs_phi_helium_st(const double2* Z, const double2* Zp, const double2* Zpp, const double2* V1, double2* result,
+                              double h, double kappa, int n, cudaStream_t st);
+void launch_rhs_phi_helium_exp(const double2* Z, const double2* V1, double2* result, double h, int n, int order,
+                               cudaStream_t st);
+void launch_energies(const double2* Z, const double2* Zp, const double2* Phi, const double2* vel, double* out5, int N,
+                     int physics, double rho, double U, double depth, double kappa, cudaStream_t st);
+void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st);
+// stepper_kernels.cu
+void launch_stage_update(double2* y_out, const double2* y0, const double2* k, double c, size_t n, cudaStream_t st);
+void launch_final_update(double2* y0, const double2* k1, const double2* k2, const double2* k3, const double2* k4, double h,
+                         size_t n, cudaStream_t st);
+void launch_fp64_peak(double* sink, int iters, int blocks, cudaStream_t st);
+
+}  // namespace rb

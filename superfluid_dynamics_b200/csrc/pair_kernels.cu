@@ -1,0 +1,512 @@
+// pair_kernels.cu -- the O(N^2) cotangent-kernel sums of the Roberts boundary-integral method, matrix-free.
+//
+// Replaces (reference, L/ = CuSuperHelium/CuSuperHelium/):
+//   createMKernel / createFiniteDepthMKernel + cusolverDnDgetrf/Dgetrs   (L/createM.cuh:43-92, L/MatrixSolver.cuh:114-125)
+//   createVelocityMatrices / createHeliumVelocityMatrices + cublasZgemv  (L/WaterVelocities.cuh:38-107, 206-242)
+// Both the application of M to a vector and the velocity summation reduce to the same complex row sum
+//     S_k = sum_{j != k} cot((z_k - z_j)/2) x_j ,  x real,
+// which is evaluated here without transcendental functions in the inner loop:
+//     cot((z_k - z_j)/2) = i (E_k + E_j)/(E_k - E_j) = i [ 1 + 2 E_j/(E_k - E_j) ],   E = exp(i z)
+//     S_k = i [ (sum_j x_j - x_k) + 2 T_k ],   T_k = sum_{j != k} F_j / (E_k - E_j),   F_j = x_j E_j .
+// Near the diagonal E_k - E_j cancels; there the same formula is used with cell-local exponentials
+//     P = expm1(i (z - z_c)),  E_k - E_j = E_c (P_k - P_j),  F_j = x_j (1 + P_j),
+// z_c the centre of the source cell, which keeps every matrix entry accurate to ~1e-14 relative.
+// Inner loop: 13 FP64-pipe instructions per pair (2 DADD, 3 DMUL, 8 DFMA) + one MUFU.RCP64H.
+#include "internal.cuh"
+
+namespace rb {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {
+    // MUFU.RCP64H seed (>= 20 bits) + one cubically convergent step: relative error <= seed^3 < 1e-18
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
+__device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ double2 ldcg_d2(const double2* p) { return __ldcg(p); }
+
+// deterministic block sum of n values from global memory (fixed thread count, fixed tree)
+template <int THREADS>
+__device__ double block_sum_fixed(const double* p, int n, double* sred) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += THREADS) s += ldcg_d(p + i);
+    sred[threadIdx.x] = s;
+    __syncthreads();
+#pragma unroll
+    for (int w = THREADS / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sred[threadIdx.x] += sred[threadIdx.x + w];
+        __syncthreads();
+    }
+    double r = sred[0];
+    __syncthreads();
+    return r;
+}
+
+// deterministic block reduction of one register value
+template <int THREADS>
+__device__ double block_reduce_fixed(double v, double* sred) {
+    sred[threadIdx.x] = v;
+    __syncthreads();
+#pragma unroll
+    for (int w = THREADS / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) sred[threadIdx.x] += sred[threadIdx.x + w];
+        __syncthreads();
+    }
+    double r = sred[0];
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
+    double inv = 1.0 / (b.x * b.x + b.y * b.y);
+    return make_double2((a.x * b.x + a.y * b.y) * inv, (a.y * b.x - a.x * b.y) * inv);
+}
+
+// expm1(i (dx + i dy)) = exp(-dy) (cos dx + i sin dx) - 1, accurate for small |d|
+__device__ __forceinline__ double2 cexpm1_i(double dx, double dy) {
+    double s, c;
+    sincos(dx, &s, &c);
+    double em = expm1(-dy);
+    double sh = sin(0.5 * dx);
+    // (1+em) c - 1 = em c + (c - 1) = em c - 2 sin^2(dx/2)
+    return make_double2(fma(em, c, -2.0 * sh * sh), (1.0 + em) * s);
+}
+
+__device__ __forceinline__ int centre_index(int cell, int N) {
+    int i = cell * kCell + kCell / 2;
+    return i < N ? i : N - 1;
+}
+
+// local coordinate of point z relative to the centre zc, wrapped to the nearest period in x with a two-word 2 pi
+__device__ __forceinline__ double2 local_coord(double2 z, double2 zc) {
+    // exact difference hi + lo (TwoSum)
+    double hi = z.x - zc.x;
+    double bb = hi - z.x;
+    double lo = (z.x - (hi - bb)) + (-zc.x - bb);
+    double m = rint(hi * (1.0 / kTwoPiHi));
+    double dx = ((hi - m * kTwoPiHi) + lo) - m * kTwoPiLo;   // m in {-1,0,1}: m*kTwoPiHi exact, hi - m*2pi exact (Sterbenz) when wrapped
+    return cexpm1_i(dx, z.y - zc.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry: everything that depends on the surface only (once per RHS, reused by every sweep)
+// ------------------------------------------------------------------------------------------------
+__global__ void geometry_kernel(Geometry g, const double2* __restrict__ phiprime_c, int N, int batch, int ncell, int physics,
+                                double rhoM, double depth, int finite_image, int use_local) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)N * batch) return;
+    int b = (int)(tid / N);
+    int i = (int)(tid - (size_t)b * N);
+    const double2* Zb = g.Z + (size_t)b * N;
+    double2 z = Zb[i];
+    double2 zp = g.Zp[tid];
+    double2 zpp = g.Zpp[tid];
+
+    double s, c;
+    sincos(z.x, &s, &c);
+    double em = exp(-z.y);
+    g.EG[tid] = make_double2(em * c, em * s);
+    if (finite_image) {
+        double ep = exp(z.y + 2.0 * depth);
+        g.EI[tid] = make_double2(ep * c, ep * s);
+    }
+    if (use_local) {
+        int cell = i / kCell;
+        int cm = cell == 0 ? ncell - 1 : cell - 1;
+        int cp = cell == ncell - 1 ? 0 : cell + 1;
+        g.P0[tid] = local_coord(z, Zb[centre_index(cell, N)]);
+        g.Pm[tid] = local_coord(z, Zb[centre_index(cm, N)]);
+        g.Pp[tid] = local_coord(z, Zb[centre_index(cp, N)]);
+    }
+    // diagonal terms (without the image contribution: the image sum runs over every j including j == k)
+    double2 q = cdiv(zpp, zp);                       // Zpp/Zp
+    double cK = 0.25 * (1.0 - rhoM) / kPi;
+    g.Mdiag[tid] = 0.5 * (1.0 + rhoM) + cK * q.y;    // L/createM.cuh:56, :79
+    double2 q2 = cdiv(q, zp);                        // Zpp/Zp^2
+    double2 hz = cdiv(make_double2(0.5, 0.0), zp);   // 1/(2 Zp)
+    // -i/(4 pi) * q2 + 1/(2 Zp)   (L/WaterVelocities.cuh:55-59), multiply_by_i(-(1/4pi) q2) = (q2.y/(4pi), -q2.x/(4pi))
+    g.V1diag[tid] = make_double2(q2.y * (0.25 / kPi) + hz.x, -q2.x * (0.25 / kPi) + hz.y);
+    double2 iz = cdiv(make_double2(1.0 / (2.0 * kPi), 0.0), zp);
+    g.V2[tid] = make_double2(-iz.y, iz.x);           // i/(2 pi Zp)   (:66)
+    if (phiprime_c) g.b[tid] = phiprime_c[tid].x;    // complex_to_real, L/BaseBoundaryIntegrator.cuh:299
+}
+
+void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int batch, int ncell, int physics, double rhoM,
+                     double depth, int finite_image, int use_local, cudaStream_t st) {
+    size_t n = (size_t)N * batch;
+    int threads = 128;
+    geometry_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(g, phiprime_c, N, batch, ncell, physics, rhoM,
+                                                                                   depth, finite_image, use_local);
+    RB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// start of a solve: initial iterate, its per-cell sums, per-cell ||b||^2, control block reset
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__ b, const double* __restrict__ warm,
+                                                       double* __restrict__ x0, double* __restrict__ xsum_part,
+                                                       double* __restrict__ bnorm_part, SolveCtrl* ctrl, double omega, int N,
+                                                       int ncell) {
+    __shared__ double sred[kCell];
+    int cell = blockIdx.x, bm = blockIdx.y;
+    int i = cell * kCell + threadIdx.x;
+    double xv = 0.0, bv = 0.0;
+    if (i < N) {
+        size_t o = (size_t)bm * N + i;
+        bv = b[o];
+        xv = warm ? warm[o] : omega * bv;
+        x0[o] = xv;
+    }
+    double sx = block_reduce_fixed<kCell>(xv, sred);
+    double sb = block_reduce_fixed<kCell>(bv * bv, sred);
+    if (threadIdx.x == 0) {
+        xsum_part[(size_t)bm * ncell + cell] = sx;
+        bnorm_part[(size_t)bm * ncell + cell] = sb;
+        if (cell == 0 && bm == 0) {
+            ctrl->done = 0;
+            ctrl->iters = 0;
+            ctrl->final_buf = 0;
+            ctrl->converged = 0;
+            ctrl->rel2 = 0.0;
+            ctrl->prev_rel2 = 1e300;
+            ctrl->max_rel2_bits = 0ull;
+            ctrl->members_done = 0u;
+        }
+    }
+}
+
+void launch_guess(const double* b, const double* warm, double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl,
+                  double omega, int N, int batch, int ncell, cudaStream_t st) {
+    guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(b, warm, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell);
+    RB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// end of a solve: pick the iterate buffer the control block names, publish a (real + complex) and its per-cell sums
+// (real_to_complex of L/BaseBoundaryIntegrator.cuh:201 is folded in)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __restrict__ buf0, const double* __restrict__ buf1,
+                                                              const SolveCtrl* ctrl, double* __restrict__ a_out,
+                                                              double2* __restrict__ a_complex, double* __restrict__ xsum_part,
+                                                              int N, int ncell) {
+    __shared__ double sred[kCell];
+    const double* src = (ctrl && ctrl->final_buf) ? buf1 : buf0;
+    int cell = blockIdx.x, bm = blockIdx.y;
+    int i = cell * kCell + threadIdx.x;
+    double v = 0.0;
+    if (i < N) {
+        size_t o = (size_t)bm * N + i;
+        v = src[o];
+        if (a_out) a_out[o] = v;
+        if (a_complex) a_complex[o] = make_double2(v, 0.0);
+    }
+    double sx = block_reduce_fixed<kCell>(v, sred);
+    if (threadIdx.x == 0 && xsum_part) xsum_part[(size_t)bm * ncell + cell] = sx;
+}
+
+void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
+                         double* xsum_part, int N, int batch, int ncell, cudaStream_t st) {
+    finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, ctrl, a_out, a_complex, xsum_part, N, ncell);
+    RB_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// the sweep
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) SrcEntry {   // one source point in shared memory: 2 x LDS.128, broadcast to the warp
+    double p, q;                  // e_j
+    double fr, fi;                // F_j = x_j E_j
+};
+
+template <bool DIAG>
+__device__ __forceinline__ void tile_accumulate(const SrcEntry* __restrict__ sh, int tile, const double2 (&ek)[kRowsPerThread],
+                                                const int (&sd)[kRowsPerThread], double2 (&acc)[kRowsPerThread]) {
+#pragma unroll 4
+    for (int s = 0; s < tile; ++s) {
+        const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
+        const double2 f = *reinterpret_cast<const double2*>(&sh[s].fr);
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+            double dr = ek[r].x - e.x;
+            double di = ek[r].y - e.y;
+            double n2 = fma(di, di, dr * dr);
+            double inv = fast_rcp(n2);
+            if (DIAG) inv = (s == sd[r]) ? 0.0 : inv;
+            double tr = fma(f.y, di, f.x * dr);        // Re(F conj(d))
+            double ti = fma(f.y, dr, -(f.x * di));     // Im(F conj(d))
+            acc[r].x = fma(tr, inv, acc[r].x);
+            acc[r].y = fma(ti, inv, acc[r].y);
+        }
+    }
+}
+
+template <int MODE, bool IMAGE>
+__global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a) {
+    __shared__ SrcEntry sh[kCell];
+    __shared__ SrcEntry shI[IMAGE ? kCell : 1];
+    __shared__ double sred[kSweepThreads];
+    __shared__ unsigned int s_ticket;
+
+    if (MODE == kSweepMV && a.skip_if_done) {
+        if (*reinterpret_cast<volatile int*>(&a.ctrl->done)) return;
+    }
+    const int t = threadIdx.x;
+    const int cellK = a.row_cell0 + blockIdx.x;
+    const int chunk = blockIdx.y;
+    const int bm = blockIdx.z;
+    const int N = a.N;
+    const size_t boff = (size_t)bm * N;
+    const double* __restrict__ x = a.x + boff;
+    const double2* __restrict__ EG = a.g.EG + boff;
+    const double2* __restrict__ P0 = a.g.P0 + boff;
+
+    int krow[kRowsPerThread];
+    int lrow[kRowsPerThread];
+    double2 acc[kRowsPerThread], accI[kRowsPerThread], ekG[kRowsPerThread];
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+        lrow[r] = t + r * kSweepThreads;
+        krow[r] = cellK * kCell + lrow[r];
+        acc[r] = make_double2(0.0, 0.0);
+        accI[r] = make_double2(0.0, 0.0);
+        ekG[r] = krow[r] < N ? EG[krow[r]] : make_double2(3.0e150, 0.0);
+    }
+
+    const int tile = a.tile;
+    const int tile0 = chunk * a.tiles_per_chunk;
+    for (int it = 0; it < a.tiles_per_chunk; ++it) {
+        const int j0 = (tile0 + it) * tile;
+        if (j0 >= N) break;
+        const int cellJ = j0 / kCell;
+        int dist = cellJ - cellK;
+        if (dist < 0) dist += a.ncell;
+        const bool near = a.use_local && (dist == 0 || dist == 1 || dist == a.ncell - 1);
+        // ---- stage the source tile -------------------------------------------------------
+        __syncthreads();
+        for (int s = t; s < tile; s += kSweepThreads) {
+            int j = j0 + s;
+            SrcEntry e;
+            if (j < N) {
+                double xj = x[j];
+                if (near) {
+                    double2 p = P0[j];
+                    e.p = p.x; e.q = p.y;
+                    e.fr = xj * (1.0 + p.x); e.fi = xj * p.y;
+                } else {
+                    double2 g = EG[j];
+                    e.p = g.x; e.q = g.y;
+                    e.fr = xj * g.x; e.fi = xj * g.y;
+                }
+                sh[s] = e;
+                if (IMAGE) {
+                    double2 gi = a.g.EI[boff + j];
+                    SrcEntry ei;
+                    ei.p = gi.x; ei.q = gi.y; ei.fr = xj * gi.x; ei.fi = xj * gi.y;
+                    shI[s] = ei;
+                }
+            } else {
+                e.p = 1.0e150; e.q = 0.0; e.fr = 0.0; e.fi = 0.0;   // contributes exactly 0
+                sh[s] = e;
+                if (IMAGE) shI[s] = e;
+            }
+        }
+        // ---- this tile's view of the targets ---------------------------------------------
+        double2 ek[kRowsPerThread];
+        int sd[kRowsPerThread];
+        const double2* __restrict__ tk = EG;
+        if (near) tk = (dist == 0) ? P0 : (dist == 1 ? a.g.Pp + boff : a.g.Pm + boff);
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+            ek[r] = krow[r] < N ? tk[krow[r]] : make_double2(3.0e150, 0.0);
+            sd[r] = lrow[r] - (j0 - cellJ * kCell);
+        }
+        __syncthreads();
+        if (dist == 0) tile_accumulate<true>(sh, tile, ek, sd, acc);
+        else           tile_accumulate<false>(sh, tile, ek, sd, acc);
+        if (IMAGE) tile_accumulate<false>(shI, tile, ekG, sd, accI);
+    }
+
+    // ---- publish the partial sums, elect the finishing CTA of this row cell --------------------
+    const size_t pbase = ((size_t)bm * a.nchunks + chunk) * N;
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+        if (krow[r] < N) {
+            a.partial[pbase + krow[r]] = acc[r];
+            if (IMAGE) a.partial_img[pbase + krow[r]] = accI[r];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned int* cticket = a.cell_tickets + (size_t)bm * a.ncell + cellK;
+    if (t == 0) s_ticket = atomicAdd(cticket, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)(a.nchunks - 1)) return;
+    __threadfence();
+    if (t == 0) *cticket = 0u;   // ready for the next launch
+
+    // ---- finishing CTA: fixed-order reduction over chunks + epilogue ---------------------------
+    double2 T[kRowsPerThread], TI[kRowsPerThread];
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+        T[r] = make_double2(0.0, 0.0);
+        TI[r] = make_double2(0.0, 0.0);
+    }
+    for (int c = 0; c < a.nchunks; ++c) {
+        const size_t pb = ((size_t)bm * a.nchunks + c) * N;
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+            if (krow[r] < N) {
+                double2 v = ldcg_d2(a.partial + pb + krow[r]);
+                T[r].x += v.x; T[r].y += v.y;
+                if (IMAGE) {
+                    double2 w = ldcg_d2(a.partial_img + pb + krow[r]);
+                    TI[r].x += w.x; TI[r].y += w.y;
+                }
+            }
+        }
+    }
+    const double sumx = block_sum_fixed<kSweepThreads>(a.xsum_part + (size_t)bm * a.ncell, a.ncell, sred);
+    const double inv4pi = 0.25 / kPi;
+
+    if (MODE == kSweepMV) {
+        double sx = 0.0, sr = 0.0;
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+            if (krow[r] < N) {
+                const size_t o = boff + krow[r];
+                double xk = x[krow[r]];
+                double2 zp = a.g.Zp[o];
+                double Ar = (sumx - xk) + 2.0 * T[r].x;
+                double Ai = 2.0 * T[r].y;
+                // Im(Zp * S) with S = i A  ->  Re(Zp A)
+                double Kx = a.cK * (zp.x * Ar - zp.y * Ai);
+                if (IMAGE) Kx -= inv4pi * (sumx + 2.0 * TI[r].x);   // -(1/4pi) Im(S_img), S_img = i (sumx + 2 T_img)
+                double Mx = fma(a.g.Mdiag[o], xk, Kx);
+                double res = a.g.b[o] - Mx;
+                double xn = fma(a.omega, res, xk);
+                a.x_out[o] = xn;
+                sx += xn;
+                sr += res * res;
+            }
+        }
+        sx = block_reduce_fixed<kSweepThreads>(sx, sred);
+        sr = block_reduce_fixed<kSweepThreads>(sr, sred);
+        if (t == 0) {
+            a.xsum_part_out[(size_t)bm * a.ncell + cellK] = sx;
+            a.rnorm_part[(size_t)bm * a.ncell + cellK] = sr;
+            __threadfence();
+            s_ticket = atomicAdd(a.member_tickets + bm, 1u);
+        }
+        __syncthreads();
+        if (s_ticket != (unsigned)(a.row_cells - 1)) return;
+        // ---- level 2: last row cell of this batch member ---------------------------------------
+        __threadfence();
+        double rn = block_sum_fixed<kSweepThreads>(a.rnorm_part + (size_t)bm * a.ncell + a.row_cell0, a.row_cells, sred);
+        double bn = block_sum_fixed<kSweepThreads>(a.bnorm_part + (size_t)bm * a.ncell, a.ncell, sred);
+        if (t == 0) {
+            a.member_tickets[bm] = 0u;
+            double rel2 = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
+            if (!(rel2 == rel2)) rel2 = 1e300;   // NaN -> "not converged"
+            atomicMax(&a.ctrl->max_rel2_bits, (unsigned long long)__double_as_longlong(rel2));
+            __threadfence();
+            unsigned int m = atomicAdd(&a.ctrl->members_done, 1u);
+            if (m == (unsigned)(a.batch - 1)) {
+                // ---- level 3: last member -> decide ------------------------------------------------
+                __threadfence();
+                unsigned long long bits = atomicAdd(&a.ctrl->max_rel2_bits, 0ull);
+                double worst = __longlong_as_double((long long)bits);
+                volatile SolveCtrl* c = a.ctrl;
+                int iters = c->iters + 1;
+                double prev = c->prev_rel2;
+                bool conv = worst <= a.tol2;
+                bool stagnated = iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
+                c->iters = iters;
+                c->rel2 = worst;
+                c->prev_rel2 = worst;
+                c->final_buf = a.out_buf;
+                if (conv || stagnated || iters >= a.max_iters) {
+                    c->converged = (conv || stagnated) ? 1 : 0;
+                    c->done = 1;
+                }
+                c->max_rel2_bits = 0ull;
+                c->members_done = 0u;
+                __threadfence();
+            }
+        }
+        return;
+    }
+
+    if (MODE == kSweepVEL) {
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+            if (krow[r] < N) {
+                const size_t o = boff + krow[r];
+                double ak = x[krow[r]];
+                double2 zp = a.g.Zp[o];
+                double2 v1d = a.g.V1diag[o];
+                double2 v2 = a.g.V2[o];
+                double2 ap = a.aprime[o];
+                // w = (-i/4pi) S + V1diag a + V2 a',  S = i A  ->  A/(4 pi)
+                double wr = inv4pi * ((sumx - ak) + 2.0 * T[r].x) + v1d.x * ak + (v2.x * ap.x - v2.y * ap.y);
+                double wi = inv4pi * (2.0 * T[r].y) + v1d.y * ak + (v2.x * ap.y + v2.y * ap.x);
+                if (IMAGE) {   // + (i/4pi) S_img = -(sumx + 2 T_img)/(4 pi)
+                    wr -= inv4pi * (sumx + 2.0 * TI[r].x);
+                    wi -= inv4pi * (2.0 * TI[r].y);
+                }
+                a.vel_lower[o] = make_double2(wr, -wi);            // conj, L/WaterVelocities.cuh:241
+                double2 az = cdiv(make_double2(ak, 0.0), zp);       // upper fluid: diagonal -1/(2Zp) instead of +1/(2Zp)
+                a.vel_upper[o] = make_double2(wr - az.x, -(wi - az.y));
+                if (a.dphi) {
+                    double y = a.g.Z[o].y;
+                    double kin = 0.5 * wr * wr + 0.5 * wi * wi;
+                    double d;
+                    if (a.rhs_phi_kind == 1) {
+                        d = -y + 0.5 * (wr * wr + wi * wi);        // L/createM.cuh:105 at rho = 0
+                    } else {
+                        double vdw = a.depth / 3.0;                // L/createM.cuh:113-115
+                        d = vdw * pow(1.0 + y / a.depth, -3.0) - vdw + kin;
+                    }
+                    a.dphi[o] = make_double2(d, 0.0);
+                }
+            }
+        }
+        return;
+    }
+
+    // RAW: S_k = i A_k
+#pragma unroll
+    for (int r = 0; r < kRowsPerThread; ++r) {
+        if (krow[r] < N) {
+            double xk = x[krow[r]];
+            double Ar = (sumx - xk) + 2.0 * T[r].x;
+            double Ai = 2.0 * T[r].y;
+            a.raw_out[boff + krow[r]] = make_double2(-Ai, Ar);
+        }
+    }
+}
+
+void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st) {
+    dim3 grid(a.row_cells, a.nchunks, a.batch);
+    dim3 block(kSweepThreads);
+    if (a.has_image) {
+        if (mode == kSweepMV) sweep_kernel<kSweepMV, true><<<grid, block, 0, st>>>(a);
+        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, true><<<grid, block, 0, st>>>(a);
+        else throw std::runtime_error("raw cotangent sum with image term is not defined");
+    } else {
+        if (mode == kSweepMV) sweep_kernel<kSweepMV, false><<<grid, block, 0, st>>>(a);
+        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, false><<<grid, block, 0, st>>>(a);
+        else sweep_kernel<kSweepRAW, false><<<grid, block, 0, st>>>(a);
+    }
+    RB_CUDA(cudaGetLastError());
+}
+
+}  // namespace rb

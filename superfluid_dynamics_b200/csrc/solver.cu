@@ -1,0 +1,1141 @@
+// solver.cu -- host orchestration of one RHS evaluation, the RK4 stepper and the C ABI (include/roberts_b200.h).
+//
+// Mirrors (reference, L/ = CuSuperHelium/CuSuperHelium/):
+//   BaseBoundaryIntegralCalculator<N,B>::runTimeStep / calculateVorticities   L/BaseBoundaryIntegrator.cuh:138-306
+//   ZPhiDerivative<N,B>::exec, FftDerivative<N,B>::exec                        L/Derivatives.cuh:190-257, 311-384
+//   AutonomousRungeKuttaStepperBase::runStep / initialize / runEvolution       L/AutonomousRungeKuttaStepper.cuh:124-437
+//   calculateRHSNFromVectors, adimensionalizeProperties                        L/Export.cu:194-265, 1213-1246
+// N and the batch size are runtime values.  No CPU fallback: everything below needs a CUDA device.
+#include <cufft.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/roberts_b200.h"
+#include "internal.cuh"
+
+using namespace rb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(const std::exception& e) {
+    g_last_error = e.what();
+    std::fprintf(stderr, "Error: %s\n", e.what());   // L/Export.cu: std::cerr << "Error: " << e.what()
+    return -1;
+}
+#define RB_TRY try {
+#define RB_CATCH                      \
+    }                                 \
+    catch (const std::exception& e) { \
+        return fail(e);               \
+    }                                 \
+    return 0;
+
+static void cufft_check(cufftResult r, const char* what) {
+    if (r != CUFFT_SUCCESS) throw std::runtime_error(std::string(what) + " failed: cufft error " + std::to_string((int)r));
+}
+
+template <typename T>
+static T* dmalloc(size_t n) {
+    T* p = nullptr;
+    RB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the RHS assembler
+// ------------------------------------------------------------------------------------------------
+struct rb_solver {
+    int N = 0, batch = 0, ncell = 0;
+    size_t BN = 0;
+    rb_props props{};
+    cudaStream_t stream = nullptr;
+    int device = 0;
+
+    // derived physics
+    double rhoM = 0, cK = 0, omega = 0;
+    int has_image = 0, use_local = 0, rhs_phi_kind = 0;
+    bool matrix_free_solve = true;
+
+    // chunking of the sweep
+    int tile = 256, tiles_per_chunk = 1, nchunks = 1;
+
+    // device buffers
+    double2* deriv = nullptr;      // [3][BN]: Zp | Zpp | PhiPrime(complex)
+    double2* fwork = nullptr;      // [3][BN]: FFT work (periodic parts / spectra)
+    double2 *EG = nullptr, *P0 = nullptr, *Pm = nullptr, *Pp = nullptr, *EI = nullptr, *V1diag = nullptr, *V2 = nullptr;
+    double *Mdiag = nullptr, *b = nullptr, *a = nullptr;
+    double* xbuf[2] = {nullptr, nullptr};
+    double* xsum_part[2] = {nullptr, nullptr};
+    double *xsum_a = nullptr, *rnorm_part = nullptr, *bnorm_part = nullptr, *energies = nullptr;
+    double2 *ac = nullptr, *aprime = nullptr, *vel_upper = nullptr;
+    double2 *partial = nullptr, *partial_img = nullptr;
+    unsigned int *cell_tickets = nullptr, *member_tickets = nullptr;
+    SolveCtrl* ctrl = nullptr;
+    SolveCtrl* h_ctrl = nullptr;   // pinned
+    double* Mdense = nullptr;      // dense validation path, allocated on demand
+    int* lu_info = nullptr;
+    double2* scratch_state = nullptr;   // legacy host-vector exports
+
+    cufftHandle plan1 = 0, plan2 = 0, plan3 = 0;
+    bool plans = false;
+
+    // warm start (set by the stepper): x0 = sum_i c_i h_i
+    const double* guess_h[4] = {nullptr, nullptr, nullptr, nullptr};
+    double guess_c[4] = {0, 0, 0, 0};
+    int guess_n = 0;
+    double* a_copy_out = nullptr;   // extra copy of the solution (stage history)
+    bool have_prev_a = false;
+
+    // capture mode: fixed sweep count, no host synchronisation inside rb_rhs
+    int fixed_sweeps = 0;
+
+    // statistics of the last solve
+    int last_iters = 0, last_converged = 0;
+    double last_rel = 0;
+    int kpred = 0;
+    long long total_sweeps = 0;
+
+    const double2* cur_Z = nullptr;
+    const double2* cur_Phi = nullptr;
+    const double2* cur_vel = nullptr;
+
+    double2* Zp() const { return deriv; }
+    double2* Zpp() const { return deriv + BN; }
+    double2* PhiPc() const { return deriv + 2 * BN; }
+};
+
+static void solver_free(rb_solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->plans) {
+        cufftDestroy(s->plan1);
+        cufftDestroy(s->plan2);
+        cufftDestroy(s->plan3);
+    }
+    void* ptrs[] = {s->deriv, s->fwork, s->EG, s->P0, s->Pm, s->Pp, s->EI, s->V1diag, s->V2, s->Mdiag, s->b, s->a,
+                    s->xbuf[0], s->xbuf[1], s->xsum_part[0], s->xsum_part[1], s->xsum_a, s->rnorm_part, s->bnorm_part,
+                    s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
+                    s->member_tickets, s->ctrl, s->Mdense, s->lu_info, s->scratch_state};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    delete s;
+}
+
+static void choose_chunking(rb_solver* s) {
+    const int N = s->N;
+    const int target = env_int("RB_TARGET_CTAS", 148 * 8);
+    long rows = (long)s->ncell * s->batch;
+    int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
+    int max_chunks = std::max(1, (N + 63) / 64);
+    wanted = std::min(wanted, max_chunks);
+    wanted = env_int("RB_NCHUNKS", wanted);
+    int srcs = (N + wanted - 1) / wanted;
+    srcs = ((srcs + 63) / 64) * 64;
+    if (srcs >= 256) {
+        s->tile = 256;
+        s->tiles_per_chunk = (srcs + 255) / 256;
+    } else if (srcs >= 128) {
+        s->tile = 128;
+        s->tiles_per_chunk = 1;
+    } else {
+        s->tile = 64;
+        s->tiles_per_chunk = 1;
+    }
+    int t = env_int("RB_TILE", 0);
+    if (t == 64 || t == 128 || t == 256) {
+        s->tile = t;
+        s->tiles_per_chunk = std::max(1, (srcs + t - 1) / t);
+    }
+    int per = s->tile * s->tiles_per_chunk;
+    s->nchunks = (N + per - 1) / per;
+}
+
+static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
+    if (N < 2) throw std::runtime_error("rb_create: N must be >= 2");
+    if (batch < 1) throw std::runtime_error("rb_create: batch must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("rb_create: no CUDA device (libroberts_b200 has no CPU path)");
+    std::unique_ptr<rb_solver, void (*)(rb_solver*)> up(new rb_solver, solver_free);
+    rb_solver* s = up.get();
+    RB_CUDA(cudaGetDevice(&s->device));
+    s->N = N;
+    s->batch = batch;
+    s->BN = (size_t)N * batch;
+    s->ncell = (N + kCell - 1) / kCell;
+    if (pin) s->props = *pin; else rb_default_props(&s->props);
+    rb_props& p = s->props;
+    if (p.max_iterations <= 0) p.max_iterations = 200;
+    if (p.tolerance <= 0) p.tolerance = 1e-13;
+
+    switch (p.physics) {
+        case RB_WATER:
+            s->rhoM = p.rho;
+            s->has_image = 0;
+            s->rhs_phi_kind = (p.rho == 0.0) ? 1 : 0;
+            break;
+        case RB_HELIUM:
+            s->rhoM = 0.0;   // createFiniteDepthMKernel: 1/2 and 1/(4 pi), L/createM.cuh:79,85
+            s->has_image = p.infinite_depth ? 0 : 1;
+            s->rhs_phi_kind = (p.use_expansions || p.kappa != 0.0) ? 0 : 2;
+            break;
+        case RB_HELIUM_INF:
+            s->rhoM = p.depth;   // depth passed in the rho slot, L/HeliumBoundaryProblem.cuh:61
+            s->has_image = 0;
+            s->rhs_phi_kind = 2;
+            break;
+        default:
+            throw std::runtime_error("rb_create: unknown physics");
+    }
+    s->cK = 0.25 * (1.0 - s->rhoM) / kPi;
+    s->omega = 2.0 / (1.0 + s->rhoM);
+    s->use_local = (s->ncell >= kMinCellsForLocal && !env_int("RB_NO_LOCAL", 0)) ? 1 : 0;
+    // Richardson on (1/2) I + K converges for the water / infinite-depth operators; the finite-depth image term of the
+    // reference (no Zp_k factor, L/createM.cuh:87-88) makes M far from (1/2) I, so that case goes through the dense solve.
+    s->matrix_free_solve = (p.solve_mode == RB_SOLVE_MATRIX_FREE) && !s->has_image;
+    choose_chunking(s);
+
+    const size_t BN = s->BN;
+    s->deriv = dmalloc<double2>(3 * BN);
+    s->fwork = dmalloc<double2>(3 * BN);
+    s->EG = dmalloc<double2>(BN);
+    s->P0 = dmalloc<double2>(BN);
+    s->Pm = dmalloc<double2>(BN);
+    s->Pp = dmalloc<double2>(BN);
+    if (s->has_image) s->EI = dmalloc<double2>(BN);
+    s->V1diag = dmalloc<double2>(BN);
+    s->V2 = dmalloc<double2>(BN);
+    s->Mdiag = dmalloc<double>(BN);
+    s->b = dmalloc<double>(BN);
+    s->a = dmalloc<double>(BN);
+    size_t pc = (size_t)s->ncell * batch;
+    for (int i = 0; i < 2; ++i) {
+        s->xbuf[i] = dmalloc<double>(BN);
+        s->xsum_part[i] = dmalloc<double>(pc);
+    }
+    s->xsum_a = dmalloc<double>(pc);
+    s->rnorm_part = dmalloc<double>(pc);
+    s->bnorm_part = dmalloc<double>(pc);
+    s->energies = dmalloc<double>(8);
+    s->ac = dmalloc<double2>(BN);
+    s->aprime = dmalloc<double2>(BN);
+    s->vel_upper = dmalloc<double2>(BN);
+    s->partial = dmalloc<double2>((size_t)s->nchunks * BN);
+    if (s->has_image) s->partial_img = dmalloc<double2>((size_t)s->nchunks * BN);
+    s->cell_tickets = dmalloc<unsigned int>(pc);
+    s->member_tickets = dmalloc<unsigned int>(batch);
+    s->ctrl = dmalloc<SolveCtrl>(1);
+    s->lu_info = dmalloc<int>(1);
+    RB_CUDA(cudaMemset(s->cell_tickets, 0, pc * sizeof(unsigned int)));
+    RB_CUDA(cudaMemset(s->member_tickets, 0, batch * sizeof(unsigned int)));
+    RB_CUDA(cudaMemset(s->ctrl, 0, sizeof(SolveCtrl)));
+    RB_CUDA(cudaMemset(s->a, 0, BN * sizeof(double)));
+    RB_CUDA(cudaMemset(s->energies, 0, 8 * sizeof(double)));
+    RB_CUDA(cudaMallocHost(&s->h_ctrl, sizeof(SolveCtrl)));
+    std::memset(s->h_ctrl, 0, sizeof(SolveCtrl));
+
+    int n[1] = {N};
+    cufft_check(cufftPlanMany(&s->plan1, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, batch), "cufftPlanMany(B)");
+    cufft_check(cufftPlanMany(&s->plan2, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 2 * batch), "cufftPlanMany(2B)");
+    cufft_check(cufftPlanMany(&s->plan3, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 3 * batch), "cufftPlanMany(3B)");
+    s->plans = true;
+    return up.release();
+}
+
+static void set_stream(rb_solver* s, cudaStream_t st) {
+    s->stream = st;
+    cufft_check(cufftSetStream(s->plan1, st), "cufftSetStream");
+    cufft_check(cufftSetStream(s->plan2, st), "cufftSetStream");
+    cufft_check(cufftSetStream(s->plan3, st), "cufftSetStream");
+}
+
+// ZPhiDerivative::exec into the solver's own buffers (Zp | Zpp | PhiPrime)
+static void derivatives(rb_solver* s, const double2* Z, const double2* Phi) {
+    const size_t BN = s->BN;
+    cudaStream_t st = s->stream;
+    double2* zper = s->fwork;            // [0]
+    double2* phiper = s->fwork + BN;     // [1]
+    launch_sub_linear(Z, Phi, zper, phiper, s->N, s->batch, s->props.rho, s->props.U, st);
+    cufft_check(cufftExecZ2Z(s->plan2, (cufftDoubleComplex*)zper, (cufftDoubleComplex*)zper, CUFFT_FORWARD), "fft fwd");
+    // d1z -> Zp, d2z -> Zpp, d1phi -> PhiPc, then one inverse over the three
+    launch_spectral_multiply_zphi(zper, phiper, s->Zp(), s->Zpp(), s->PhiPc(), s->N, s->batch, st);
+    cufft_check(cufftExecZ2Z(s->plan3, (cufftDoubleComplex*)s->deriv, (cufftDoubleComplex*)s->deriv, CUFFT_INVERSE), "fft inv");
+    launch_finish_zphi(s->Zp(), s->Zpp(), s->PhiPc(), s->N, s->batch, s->props.rho, s->props.U, st);
+}
+
+static Geometry make_geometry(rb_solver* s, const double2* Z) {
+    Geometry g;
+    g.Z = Z;
+    g.Zp = s->Zp();
+    g.Zpp = s->Zpp();
+    g.EG = s->EG;
+    g.P0 = s->P0;
+    g.Pm = s->Pm;
+    g.Pp = s->Pp;
+    g.EI = s->EI;
+    g.Mdiag = s->Mdiag;
+    g.V1diag = s->V1diag;
+    g.V2 = s->V2;
+    g.b = s->b;
+    return g;
+}
+
+static SweepArgs base_args(rb_solver* s, const double2* Z) {
+    SweepArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.N = s->N;
+    a.batch = s->batch;
+    a.ncell = s->ncell;
+    a.tile = s->tile;
+    a.tiles_per_chunk = s->tiles_per_chunk;
+    a.nchunks = s->nchunks;
+    a.row_cell0 = 0;
+    a.row_cells = s->ncell;
+    a.use_local = s->use_local;
+    a.has_image = s->has_image;
+    a.g = make_geometry(s, Z);
+    a.partial = s->partial;
+    a.partial_img = s->partial_img;
+    a.cell_tickets = s->cell_tickets;
+    a.member_tickets = s->member_tickets;
+    a.ctrl = s->ctrl;
+    a.cK = s->cK;
+    a.omega = s->omega;
+    a.rho = s->props.rho;
+    a.depth = s->props.depth;
+    a.tol2 = s->props.tolerance * s->props.tolerance;
+    a.max_iters = s->props.max_iterations;
+    a.kappa = s->props.kappa;
+    a.expansion_order = s->props.expansion_order;
+    a.bnorm_part = s->bnorm_part;
+    a.rnorm_part = s->rnorm_part;
+    return a;
+}
+
+static void launch_mv(rb_solver* s, const SweepArgs& base, int i, int skip) {
+    SweepArgs a = base;
+    a.x = s->xbuf[i & 1];
+    a.x_out = s->xbuf[(i + 1) & 1];
+    a.xsum_part = s->xsum_part[i & 1];
+    a.xsum_part_out = s->xsum_part[(i + 1) & 1];
+    a.out_buf = (i + 1) & 1;
+    a.skip_if_done = skip;
+    launch_sweep(a, kSweepMV, s->stream);
+    s->total_sweeps++;
+}
+
+static void read_ctrl(rb_solver* s) {
+    RB_CUDA(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
+    RB_CUDA(cudaStreamSynchronize(s->stream));
+    s->last_iters = s->h_ctrl->iters;
+    s->last_converged = s->h_ctrl->converged;
+    s->last_rel = std::sqrt(std::max(0.0, s->h_ctrl->rel2));
+}
+
+// M a = b.  On return a (real), ac (complex copy) and the per-cell sums of a are valid on the stream.
+static void solve(rb_solver* s, const double2* Z) {
+    cudaStream_t st = s->stream;
+    if (!s->matrix_free_solve) {
+        // validation path: materialise M exactly as the reference kernels do and factorise it
+        const int N = s->N;
+        if (!s->Mdense) s->Mdense = dmalloc<double>((size_t)N * N);
+        for (int bm = 0; bm < s->batch; ++bm) {
+            const size_t o = (size_t)bm * N;
+            if (s->props.physics == RB_HELIUM)
+                launch_create_finite_depth_M(s->Mdense, Z + o, s->Zp() + o, s->Zpp() + o, s->props.depth, N, 1,
+                                             s->props.infinite_depth != 0, st);
+            else
+                launch_create_M(s->Mdense, Z + o, s->Zp() + o, s->Zpp() + o, s->rhoM, N, 1, st);
+            RB_CUDA(cudaMemcpyAsync(s->xbuf[0] + o, s->b + o, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            launch_lu_solve(s->Mdense, s->xbuf[0] + o, N, s->lu_info, st);
+        }
+        launch_finish_solve(s->xbuf[0], s->xbuf[0], nullptr, s->a, s->ac, s->xsum_a, s->N, s->batch, s->ncell, st);
+        if (s->a_copy_out)
+            RB_CUDA(cudaMemcpyAsync(s->a_copy_out, s->a, s->BN * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        s->last_iters = 0;
+        s->last_converged = 1;
+        s->last_rel = 0;
+        return;
+    }
+
+    // matrix-free Richardson: x <- x + omega (b - M x), error contracts by rho(I - omega M) per sweep
+    const double* warm = nullptr;
+    if (s->props.guess_mode == RB_GUESS_WARM && s->guess_n == 0 && s->have_prev_a) warm = s->a;
+    if (s->guess_n > 0) {
+        // stage-history extrapolation prepared by the stepper: combine into xbuf[1], then use it as the warm vector
+        // (the combine is a tiny elementwise kernel; reuse the stage-update kernel on the real arrays viewed as complex pairs
+        //  is not possible for odd sizes, so a dedicated path lives in launch_guess via warm)
+        warm = s->guess_h[0];
+    }
+    launch_guess(s->b, warm, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
+    SweepArgs base = base_args(s, Z);
+    int launched = 0;
+    if (s->fixed_sweeps > 0) {
+        for (; launched < s->fixed_sweeps; ++launched) launch_mv(s, base, launched, 1);
+    } else {
+        int group = s->kpred > 0 ? s->kpred : 8;
+        while (true) {
+            for (int g = 0; g < group && launched < s->props.max_iterations; ++g, ++launched) launch_mv(s, base, launched, 1);
+            read_ctrl(s);
+            if (s->h_ctrl->done || launched >= s->props.max_iterations) break;
+            group = 2;
+        }
+        s->kpred = s->last_iters;
+    }
+    launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, s->ac, s->xsum_a, s->N, s->batch, s->ncell, st);
+    if (s->a_copy_out) RB_CUDA(cudaMemcpyAsync(s->a_copy_out, s->a, s->BN * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    s->have_prev_a = true;
+}
+
+static void vorticities(rb_solver* s, const double2* state) {
+    const double2* Z = state;
+    const double2* Phi = state + s->BN;
+    derivatives(s, Z, Phi);
+    Geometry g = make_geometry(s, Z);
+    launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
+                    s->use_local, s->stream);
+    solve(s, Z);
+    s->cur_Z = Z;
+    s->cur_Phi = Phi;
+}
+
+static void fft_derivative(rb_solver* s, const double2* in, double2* out, int second, double scaling) {
+    double2* tmp = s->fwork + 2 * s->BN;
+    cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)in, (cufftDoubleComplex*)tmp, CUFFT_FORWARD), "fft fwd");
+    launch_spectral_multiply(tmp, tmp, s->N, s->batch, second, s->stream);
+    cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)tmp, (cufftDoubleComplex*)out, CUFFT_INVERSE), "fft inv");
+    if (scaling != 1.0) launch_scale(out, scaling, s->BN, s->stream);
+}
+
+static void rhs(rb_solver* s, const double2* state, double2* out) {
+    const size_t BN = s->BN;
+    cudaStream_t st = s->stream;
+    vorticities(s, state);
+    const double2* Z = state;
+    fft_derivative(s, s->ac, s->aprime, 0, 2.0 * kPi / s->N);   // L/BaseBoundaryIntegrator.cuh:203
+    SweepArgs a = base_args(s, Z);
+    a.x = s->a;
+    a.xsum_part = s->xsum_a;
+    a.aprime = s->aprime;
+    a.vel_lower = out;
+    a.vel_upper = s->vel_upper;
+    a.rhs_phi_kind = s->rhs_phi_kind;
+    a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
+    launch_sweep(a, kSweepVEL, st);
+    s->total_sweeps++;
+    if (!s->rhs_phi_kind) {
+        const rb_props& p = s->props;
+        if (p.physics == RB_WATER) {
+            launch_rhs_phi_water(Z, out, s->vel_upper, out + BN, p.rho, (int)BN, st);   // L/WaterBoundaryProblem.cuh:37
+        } else if (p.use_expansions) {
+            launch_rhs_phi_helium_exp(Z, out, out + BN, p.depth, (int)BN, p.expansion_order, st);
+        } else {
+            launch_rhs_phi_helium_st(Z, s->Zp(), s->Zpp(), out, out + BN, p.depth, p.kappa, (int)BN, st);
+        }
+    }
+    s->cur_vel = out;
+    if (s->props.compute_energies)
+        launch_energies(Z, s->Zp(), state + BN, out, s->energies, s->N, s->props.physics == RB_WATER ? 0 : 1, s->props.rho,
+                        s->props.U, s->props.depth, s->props.kappa, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the RK4 stepper
+// ------------------------------------------------------------------------------------------------
+struct rb_stepper {
+    rb_solver* s = nullptr;
+    double dt = 1e-2;
+    double t = 0.0;
+    double2* y0 = nullptr;
+    bool owns_y0 = false;
+    double2 *k[4] = {nullptr, nullptr, nullptr, nullptr}, *ytmp = nullptr;
+    // stage history of the vortex-sheet strengths for the warm start: hist[stage][slot]
+    double* hist[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    int hist_count = 0;
+    // logging
+    size_t log_every = 0, log_capacity = 0, log_count = 0, step_index = 0;
+    double2* log_states = nullptr;
+    std::vector<double> log_times;
+};
+
+static void stepper_free(rb_stepper* st) {
+    if (!st) return;
+    if (st->owns_y0 && st->y0) cudaFree(st->y0);
+    for (auto p : st->k)
+        if (p) cudaFree(p);
+    if (st->ytmp) cudaFree(st->ytmp);
+    for (auto& hs : st->hist)
+        for (auto p : hs)
+            if (p) cudaFree(p);
+    if (st->log_states) cudaFree(st->log_states);
+    delete st;
+}
+
+static void stepper_step(rb_stepper* st) {
+    rb_solver* s = st->s;
+    const size_t n2 = 2 * s->BN;
+    cudaStream_t cs = s->stream;
+    const double h = st->dt;
+    const bool warm = s->props.guess_mode == RB_GUESS_WARM && s->matrix_free_solve;
+    auto stage = [&](int i, const double2* y) {
+        if (warm) {
+            // previous step's solution at the same stage is an O(dt) accurate start; alternate two slots so that the
+            // solver never reads the buffer it is writing
+            int cur = st->hist_count & 1;
+            s->guess_n = st->hist_count > 0 ? 1 : 0;
+            s->guess_h[0] = st->hist[i][cur ^ 1];
+            s->a_copy_out = st->hist[i][cur];
+        }
+        rhs(s, y, st->k[i]);
+    };
+    stage(0, st->y0);
+    launch_stage_update(st->ytmp, st->y0, st->k[0], h * 0.5, n2, cs);
+    stage(1, st->ytmp);
+    launch_stage_update(st->ytmp, st->y0, st->k[1], h * 0.5, n2, cs);
+    stage(2, st->ytmp);
+    launch_stage_update(st->ytmp, st->y0, st->k[2], h, n2, cs);
+    stage(3, st->ytmp);
+    launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n2, cs);
+    if (warm) st->hist_count++;
+    s->guess_n = 0;
+    s->a_copy_out = nullptr;
+    st->t += h;
+    st->step_index++;
+    if (st->log_every && st->log_states && (st->step_index % st->log_every) == 0 && st->log_count < st->log_capacity) {
+        RB_CUDA(cudaMemcpyAsync(st->log_states + st->log_count * n2, st->y0, n2 * sizeof(double2), cudaMemcpyDeviceToDevice, cs));
+        st->log_times.push_back(st->t);
+        st->log_count++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* rb_last_error(void) { return g_last_error.c_str(); }
+int rb_version(void) { return 100; }
+
+int rb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rb_set_device(int device) {
+    RB_TRY
+    RB_CUDA(cudaSetDevice(device));
+    RB_CATCH
+}
+
+void rb_default_props(rb_props* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->rho = 0.0;
+    p->U = 0.0;
+    p->kappa = 0.0;
+    p->depth = 1.0;
+    p->expansion_order = 1;
+    p->physics = RB_WATER;
+    p->solve_mode = RB_SOLVE_MATRIX_FREE;
+    p->guess_mode = RB_GUESS_COLD;
+    p->max_iterations = 200;
+    p->compute_energies = 0;
+    p->tolerance = 1e-13;
+}
+
+rb_solver* rb_create(int N, int batch, const rb_props* props) {
+    try {
+        return solver_create(N, batch, props);
+    } catch (const std::exception& e) {
+        fail(e);
+        return nullptr;
+    }
+}
+
+int rb_destroy(rb_solver* s) {
+    RB_TRY
+    if (s) {
+        cudaSetDevice(s->device);
+        cudaDeviceSynchronize();
+        solver_free(s);
+    }
+    RB_CATCH
+}
+
+int rb_set_stream(rb_solver* s, void* cuda_stream) {
+    RB_TRY
+    set_stream(s, (cudaStream_t)cuda_stream);
+    RB_CATCH
+}
+
+int rb_rhs(rb_solver* s, const rb_complex* state_dev, rb_complex* rhs_dev) {
+    RB_TRY
+    rhs(s, (const double2*)state_dev, (double2*)rhs_dev);
+    RB_CATCH
+}
+
+int rb_vorticities(rb_solver* s, const rb_complex* state_dev) {
+    RB_TRY
+    vorticities(s, (const double2*)state_dev);
+    RB_CATCH
+}
+
+double* rb_dev_a(rb_solver* s) { return s->a; }
+rb_complex* rb_dev_zp(rb_solver* s) { return (rb_complex*)s->Zp(); }
+rb_complex* rb_dev_zpp(rb_solver* s) { return (rb_complex*)s->Zpp(); }
+rb_complex* rb_dev_velocities_upper(rb_solver* s) { return (rb_complex*)s->vel_upper; }
+double* rb_dev_phi_prime(rb_solver* s) { return s->b; }
+
+int rb_synchronize(rb_solver* s) {
+    RB_TRY
+    RB_CUDA(cudaStreamSynchronize(s->stream));
+    RB_CATCH
+}
+
+int rb_energies(rb_solver* s, double out_host[5]) {
+    RB_TRY
+    if (!s->cur_Z || !s->cur_vel) throw std::runtime_error("rb_energies: no RHS has been evaluated yet");
+    if (!s->props.compute_energies)
+        launch_energies(s->cur_Z, s->Zp(), s->cur_Phi, s->cur_vel, s->energies, s->N, s->props.physics == RB_WATER ? 0 : 1,
+                        s->props.rho, s->props.U, s->props.depth, s->props.kappa, s->stream);
+    RB_CUDA(cudaMemcpyAsync(out_host, s->energies, 5 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    RB_CUDA(cudaStreamSynchronize(s->stream));
+    RB_CATCH
+}
+
+int rb_solve_stats(rb_solver* s, double out_host[3]) {
+    RB_TRY
+    if (s->matrix_free_solve) read_ctrl(s);
+    out_host[0] = s->last_iters;
+    out_host[1] = s->last_converged;
+    out_host[2] = s->last_rel;
+    RB_CATCH
+}
+
+int rb_zphi_derivative(rb_solver* s, const rb_complex* Z, const rb_complex* Phi, rb_complex* Zp, rb_complex* PhiPrime,
+                       rb_complex* Zpp) {
+    RB_TRY
+    derivatives(s, (const double2*)Z, (const double2*)Phi);
+    const size_t bytes = s->BN * sizeof(double2);
+    if (Zp) RB_CUDA(cudaMemcpyAsync(Zp, s->Zp(), bytes, cudaMemcpyDeviceToDevice, s->stream));
+    if (Zpp) RB_CUDA(cudaMemcpyAsync(Zpp, s->Zpp(), bytes, cudaMemcpyDeviceToDevice, s->stream));
+    if (PhiPrime) RB_CUDA(cudaMemcpyAsync(PhiPrime, s->PhiPc(), bytes, cudaMemcpyDeviceToDevice, s->stream));
+    RB_CATCH
+}
+
+int rb_fft_derivative(rb_solver* s, const rb_complex* in, rb_complex* out, int second, double scaling) {
+    RB_TRY
+    fft_derivative(s, (const double2*)in, (double2*)out, second, scaling);
+    RB_CATCH
+}
+
+int rb_create_M(double* A, const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp, double rho, int n, size_t batch,
+                void* stream) {
+    RB_TRY
+    launch_create_M(A, (const double2*)Z, (const double2*)Zp, (const double2*)Zpp, rho, n, batch, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_create_finite_depth_M(double* A, const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp, double h, int n,
+                             size_t batch, int infinite_depth, void* stream) {
+    RB_TRY
+    launch_create_finite_depth_M(A, (const double2*)Z, (const double2*)Zp, (const double2*)Zpp, h, n, batch,
+                                 infinite_depth != 0, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_velocity_matrices(const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp, int n, rb_complex* V1,
+                         rb_complex* V2, int lower, size_t batch, void* stream) {
+    RB_TRY
+    launch_velocity_matrices((const double2*)Z, (const double2*)Zp, (const double2*)Zpp, n, (double2*)V1, (double2*)V2,
+                             lower != 0, batch, false, 0.0, true, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_helium_velocity_matrices(const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp, double h, int n,
+                                rb_complex* V1, rb_complex* V2, int lower, size_t batch, int infinite_depth, void* stream) {
+    RB_TRY
+    launch_velocity_matrices((const double2*)Z, (const double2*)Zp, (const double2*)Zpp, n, (double2*)V1, (double2*)V2,
+                             lower != 0, batch, true, h, infinite_depth != 0, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_rhs_phi_water(const rb_complex* Z, const rb_complex* V1, const rb_complex* V2, rb_complex* result, double rho, int n,
+                     void* stream) {
+    RB_TRY
+    launch_rhs_phi_water((const double2*)Z, (const double2*)V1, (const double2*)V2, (double2*)result, rho, n,
+                         (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_rhs_phi_helium(const rb_complex* Z, const rb_complex* V1, rb_complex* result, double h, int n, void* stream) {
+    RB_TRY
+    launch_rhs_phi_helium((const double2*)Z, (const double2*)V1, (double2*)result, h, n, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_rhs_phi_helium_surface_tension(const rb_complex* Z, const rb_complex* Zp, const rb_complex* Zpp, const rb_complex* V1,
+                                      rb_complex* result, double h, double kappa, int n, void* stream) {
+    RB_TRY
+    launch_rhs_phi_helium_st((const double2*)Z, (const double2*)Zp, (const double2*)Zpp, (const double2*)V1, (double2*)result,
+                             h, kappa, n, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_rhs_phi_helium_expansion(const rb_complex* Z, const rb_complex* V1, rb_complex* result, double h, int n, int order,
+                                void* stream) {
+    RB_TRY
+    launch_rhs_phi_helium_exp((const double2*)Z, (const double2*)V1, (double2*)result, h, n, order, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_cotangent_sum(rb_solver* s, const rb_complex* Z_dev, const double* x_dev, rb_complex* S_dev) {
+    RB_TRY
+    if (s->has_image) throw std::runtime_error("rb_cotangent_sum: not defined for the finite-depth image operator");
+    const double2* Z = (const double2*)Z_dev;
+    // geometry from the solver's current Zp/Zpp (diagonal terms are not used by the raw sum)
+    Geometry g = make_geometry(s, Z);
+    launch_geometry(g, nullptr, s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, 0, s->use_local, s->stream);
+    launch_finish_solve(x_dev, x_dev, nullptr, nullptr, nullptr, s->xsum_a, s->N, s->batch, s->ncell, s->stream);
+    SweepArgs a = base_args(s, Z);
+    a.x = x_dev;
+    a.xsum_part = s->xsum_a;
+    a.raw_out = (double2*)S_dev;
+    launch_sweep(a, kSweepRAW, s->stream);
+    RB_CATCH
+}
+
+// ---- stepper -----------------------------------------------------------------------------------
+rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
+    try {
+        if (!s) throw std::runtime_error("rb_rk4_create: null solver");
+        std::unique_ptr<rb_stepper, void (*)(rb_stepper*)> up(new rb_stepper, stepper_free);
+        rb_stepper* st = up.get();
+        st->s = s;
+        st->dt = tstep;
+        const size_t n2 = 2 * s->BN;
+        for (auto& p : st->k) p = dmalloc<double2>(n2);
+        st->ytmp = dmalloc<double2>(n2);
+        for (auto& hs : st->hist)
+            for (auto& p : hs) {
+                p = dmalloc<double>(s->BN);
+                RB_CUDA(cudaMemset(p, 0, s->BN * sizeof(double)));
+            }
+        return up.release();
+    } catch (const std::exception& e) {
+        fail(e);
+        return nullptr;
+    }
+}
+
+int rb_rk4_destroy(rb_stepper* st) {
+    RB_TRY
+    if (st) {
+        cudaDeviceSynchronize();
+        stepper_free(st);
+    }
+    RB_CATCH
+}
+
+int rb_rk4_set_time_step(rb_stepper* st, double tstep) {
+    RB_TRY
+    st->dt = tstep;
+    st->hist_count = 0;
+    RB_CATCH
+}
+
+int rb_rk4_initialize(rb_stepper* st, rb_complex* y0, int on_device) {
+    RB_TRY
+    const size_t n2 = 2 * st->s->BN;
+    if (on_device) {
+        if (st->owns_y0 && st->y0) cudaFree(st->y0);
+        st->y0 = (double2*)y0;   // caller keeps ownership, L/AutonomousRungeKuttaStepper.cuh:312-318
+        st->owns_y0 = false;
+    } else {
+        if (!st->owns_y0 || !st->y0) st->y0 = dmalloc<double2>(n2);
+        st->owns_y0 = true;
+        RB_CUDA(cudaMemcpyAsync(st->y0, y0, n2 * sizeof(double2), cudaMemcpyHostToDevice, st->s->stream));
+        RB_CUDA(cudaStreamSynchronize(st->s->stream));
+    }
+    st->hist_count = 0;
+    st->t = 0.0;
+    st->step_index = 0;
+    st->log_count = 0;
+    st->log_times.clear();
+    RB_CATCH
+}
+
+int rb_rk4_step(rb_stepper* st) {
+    RB_TRY
+    if (!st->y0) throw std::runtime_error("rb_rk4_step: initialize() has not been called");
+    stepper_step(st);
+    RB_CATCH
+}
+
+int rb_rk4_run_steps(rb_stepper* st, size_t steps) {
+    RB_TRY
+    if (!st->y0) throw std::runtime_error("rb_rk4_run_steps: initialize() has not been called");
+    for (size_t i = 0; i < steps; ++i) stepper_step(st);
+    RB_CATCH
+}
+
+int rb_rk4_evolve(rb_stepper* st, double t0, double t1, size_t* steps_out) {
+    RB_TRY
+    if (!st->y0) throw std::runtime_error("rb_rk4_evolve: initialize() has not been called");
+    st->t = t0;
+    size_t steps = static_cast<size_t>((t1 - t0) / st->dt);   // truncation, L/AutonomousRungeKuttaStepper.cuh:421
+    for (size_t i = 0; i < steps; ++i) stepper_step(st);
+    RB_CUDA(cudaStreamSynchronize(st->s->stream));
+    if (steps_out) *steps_out = steps;
+    RB_CATCH
+}
+
+rb_complex* rb_rk4_dev_state(rb_stepper* st) { return (rb_complex*)st->y0; }
+double rb_rk4_current_time(rb_stepper* st) { return st->t; }
+
+int rb_rk4_get_state(rb_stepper* st, rb_complex* y_host) {
+    RB_TRY
+    const size_t n2 = 2 * st->s->BN;
+    RB_CUDA(cudaMemcpyAsync(y_host, st->y0, n2 * sizeof(double2), cudaMemcpyDeviceToHost, st->s->stream));
+    RB_CUDA(cudaStreamSynchronize(st->s->stream));
+    RB_CATCH
+}
+
+int rb_rk4_set_logging(rb_stepper* st, size_t every, size_t capacity) {
+    RB_TRY
+    if (st->log_states) {
+        cudaFree(st->log_states);
+        st->log_states = nullptr;
+    }
+    st->log_every = every;
+    st->log_capacity = capacity;
+    st->log_count = 0;
+    st->log_times.clear();
+    if (every && capacity) st->log_states = dmalloc<double2>(capacity * 2 * st->s->BN);
+    RB_CATCH
+}
+
+int rb_rk4_copy_trajectory(rb_stepper* st, double** times_out, size_t* times_count, rb_complex** states_out,
+                           size_t* states_count) {
+    RB_TRY
+    const size_t n2 = 2 * st->s->BN;
+    RB_CUDA(cudaStreamSynchronize(st->s->stream));
+    size_t cnt = st->log_count;
+    if (times_out) {
+        *times_out = (double*)std::malloc(std::max<size_t>(cnt, 1) * sizeof(double));
+        std::memcpy(*times_out, st->log_times.data(), cnt * sizeof(double));
+    }
+    if (times_count) *times_count = cnt;
+    if (states_out) {
+        *states_out = (rb_complex*)std::malloc(std::max<size_t>(cnt * n2, 1) * sizeof(rb_complex));
+        if (cnt) RB_CUDA(cudaMemcpy(*states_out, st->log_states, cnt * n2 * sizeof(double2), cudaMemcpyDeviceToHost));
+    }
+    if (states_count) *states_count = cnt;
+    RB_CATCH
+}
+
+void rb_free(void* p) { std::free(p); }
+
+int rb_rk4_stage_update(rb_complex* y_out, const rb_complex* y0, const rb_complex* k, double c, size_t n, void* stream) {
+    RB_TRY
+    launch_stage_update((double2*)y_out, (const double2*)y0, (const double2*)k, c, n, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_rk4_final_update(rb_complex* y0, const rb_complex* k1, const rb_complex* k2, const rb_complex* k3, const rb_complex* k4,
+                        double h, size_t n, void* stream) {
+    RB_TRY
+    launch_final_update((double2*)y0, (const double2*)k1, (const double2*)k2, (const double2*)k3, (const double2*)k4, h, n,
+                        (cudaStream_t)stream);
+    RB_CATCH
+}
+
+// ---- multi-GPU (row sharding) -- wired in comm.cu once initialised ---------------------------------
+int rb_comm_unique_id(char id_out[RB_UNIQUE_ID_BYTES]) {
+    (void)id_out;
+    g_last_error = "rb_comm_unique_id: multi-GPU row sharding is not built into this version";
+    return -1;
+}
+int rb_comm_init(rb_solver* s, int rank, int nranks, const char id[RB_UNIQUE_ID_BYTES]) {
+    (void)s; (void)rank; (void)nranks; (void)id;
+    g_last_error = "rb_comm_init: multi-GPU row sharding is not built into this version";
+    return -1;
+}
+int rb_comm_destroy(rb_solver* s) {
+    (void)s;
+    return 0;
+}
+
+// ---- measurement -------------------------------------------------------------------------------
+int rb_measure_fp64_peak(double* tflops_out, void* stream) {
+    RB_TRY
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sink = dmalloc<double>(1);
+    int sms = 0, dev = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, iters = 4096;
+    cudaEvent_t e0, e1;
+    RB_CUDA(cudaEventCreate(&e0));
+    RB_CUDA(cudaEventCreate(&e1));
+    launch_fp64_peak(sink, 256, blocks, st);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        RB_CUDA(cudaEventRecord(e0, st));
+        launch_fp64_peak(sink, iters, blocks, st);
+        RB_CUDA(cudaEventRecord(e1, st));
+        RB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        RB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    double flops = (double)blocks * 256.0 * iters * 64.0 * 2.0;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    RB_CATCH
+}
+
+int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* ms_per_sweep_out, double* pairs_per_sweep_out) {
+    RB_TRY
+    cudaStream_t st = s->stream;
+    const double2* Z = (const double2*)state_dev;
+    derivatives(s, Z, Z + s->BN);
+    Geometry g = make_geometry(s, Z);
+    launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
+                    s->use_local, st);
+    launch_guess(s->b, nullptr, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
+    SweepArgs base = base_args(s, Z);
+    base.max_iters = 1 << 30;
+    base.tol2 = 0.0;
+    for (int i = 0; i < 3; ++i) launch_mv(s, base, i, 0);
+    cudaEvent_t e0, e1;
+    RB_CUDA(cudaEventCreate(&e0));
+    RB_CUDA(cudaEventCreate(&e1));
+    RB_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; ++i) launch_mv(s, base, i + 1, 0);
+    RB_CUDA(cudaEventRecord(e1, st));
+    RB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    RB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_sweep_out) *ms_per_sweep_out = ms / reps;
+    if (pairs_per_sweep_out) *pairs_per_sweep_out = (double)s->N * s->N * s->batch * (s->has_image ? 2.0 : 1.0);
+    RB_CATCH
+}
+
+// ---- legacy exports ----------------------------------------------------------------------------
+static const double kAlphaHamaker = 3.5e-24;   // L/constants.cuh:11
+
+struct Adim {
+    double base_length, base_acceleration, base_time, kappa, depth, rho;
+};
+
+// adimensionalizeProperties, L/Export.cu:1222-1246 (the stdout prints of the reference are dropped)
+static Adim adimensionalize(double L, double rho, double kappa, double depth, double rhoHelium = 150.0) {
+    Adim a;
+    a.base_length = L / (2.0 * kPi);
+    a.base_acceleration = 3 * kAlphaHamaker / std::pow(depth, 4);
+    a.base_time = std::sqrt(a.base_length / a.base_acceleration);
+    double surfaceTensionFactor = rhoHelium * a.base_length * a.base_length * a.base_length / (a.base_time * a.base_time);
+    a.kappa = kappa / surfaceTensionFactor;
+    a.depth = depth / a.base_length;
+    a.rho = rho / rhoHelium;
+    return a;
+}
+
+static rb_props helium_props(const Adim& ad, bool use_expansions, int expansion_order, bool infinite_depth) {
+    rb_props p;
+    rb_default_props(&p);
+    p.physics = RB_HELIUM;   // every RHS export of the reference instantiates HeliumBoundaryProblem, L/Export.cu:207
+    p.rho = ad.rho;
+    p.kappa = ad.kappa;
+    p.depth = ad.depth;
+    p.use_expansions = use_expansions;
+    p.expansion_order = expansion_order;
+    p.infinite_depth = infinite_depth;
+    return p;
+}
+
+static int rhs_from_vectors(const double* x, const double* y, const double* phi, double* vx, double* vy, double* rhsPhi,
+                            double L, double rho, double kappa, double depth, size_t N, size_t batch) {
+    RB_TRY
+    Adim ad = adimensionalize(L, rho, kappa, depth);
+    rb_props p = helium_props(ad, false, 1, false);
+    std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, (int)batch, &p), solver_free);
+    const size_t BN = N * batch;
+    std::vector<double2> host(2 * BN);   // loadDataToDevice packing, L/SimulationRunner.cuh:180-242
+    for (size_t i = 0; i < BN; ++i) {
+        host[i] = make_double2(x[i], y[i]);
+        host[BN + i] = make_double2(phi[i], 0.0);
+    }
+    double2* dstate = dmalloc<double2>(4 * BN);
+    double2* drhs = dstate + 2 * BN;
+    RB_CUDA(cudaMemcpy(dstate, host.data(), 2 * BN * sizeof(double2), cudaMemcpyHostToDevice));
+    rhs(s.get(), dstate, drhs);
+    RB_CUDA(cudaMemcpy(host.data(), drhs, 2 * BN * sizeof(double2), cudaMemcpyDeviceToHost));
+    cudaFree(dstate);
+    for (size_t i = 0; i < BN; ++i) {
+        vx[i] = host[i].x;
+        vy[i] = host[i].y;
+        rhsPhi[i] = host[BN + i].x;
+    }
+    RB_CATCH
+}
+
+int calculateRHSFromVectors(const double* x, const double* y, const double* phi, double* vx, double* vy, double* rhsPhi,
+                            double L, double rho, double kappa, double depth, size_t N) {
+    return rhs_from_vectors(x, y, phi, vx, vy, rhsPhi, L, rho, kappa, depth, N, 1);
+}
+int calculateRHS256FromVectors(const double* x, const double* y, const double* phi, double* vx, double* vy, double* rhsPhi,
+                               double L, double rho, double kappa, double depth) {
+    return rhs_from_vectors(x, y, phi, vx, vy, rhsPhi, L, rho, kappa, depth, 256, 1);
+}
+int calculateRHS2048FromVectors(const double* x, const double* y, const double* phi, double* vx, double* vy, double* rhsPhi,
+                                double L, double rho, double kappa, double depth) {
+    return rhs_from_vectors(x, y, phi, vx, vy, rhsPhi, L, rho, kappa, depth, 2048, 1);
+}
+int calculateRHS256FromVectorsBatched(const double* x, const double* y, const double* phi, double* vx, double* vy,
+                                      double* rhsPhi, double L, double rho, double kappa, double depth, int batchSize) {
+    if (batchSize < 1) {
+        g_last_error = "calculateRHS256FromVectorsBatched: batchSize must be >= 1";
+        return -1;
+    }
+    return rhs_from_vectors(x, y, phi, vx, vy, rhsPhi, L, rho, kappa, depth, 256, (size_t)batchSize);
+}
+
+int calculateVorticities256FromVectors(const rb_complex* Z, const rb_complex* phi, double* a, rb_complex* Zp, rb_complex* Zpp,
+                                       double L, double rho, double kappa, double depth) {
+    RB_TRY
+    const size_t N = 256;
+    Adim ad = adimensionalize(L, rho, kappa, depth);
+    rb_props p = helium_props(ad, false, 1, false);
+    std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, 1, &p), solver_free);
+    double2* dstate = dmalloc<double2>(2 * N);
+    RB_CUDA(cudaMemcpy(dstate, Z, N * sizeof(double2), cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(dstate + N, phi, N * sizeof(double2), cudaMemcpyHostToDevice));
+    vorticities(s.get(), dstate);
+    RB_CUDA(cudaMemcpy(a, s->a, N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (Zp) RB_CUDA(cudaMemcpy(Zp, s->Zp(), N * sizeof(double2), cudaMemcpyDeviceToHost));
+    if (Zpp) RB_CUDA(cudaMemcpy(Zpp, s->Zpp(), N * sizeof(double2), cudaMemcpyDeviceToHost));
+    cudaFree(dstate);
+    RB_CATCH
+}
+
+int calculateDerivativeFFT256(const rb_complex* input, rb_complex* output) {
+    RB_TRY
+    const size_t N = 256;
+    rb_props p;
+    rb_default_props(&p);
+    std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, 1, &p), solver_free);
+    double2* d = dmalloc<double2>(2 * N);
+    RB_CUDA(cudaMemcpy(d, input, N * sizeof(double2), cudaMemcpyHostToDevice));
+    fft_derivative(s.get(), d, d + N, 0, 1.0);   // L/Export.cu: FftDerivative<256,1>::exec(in, out)
+    RB_CUDA(cudaMemcpy(output, d + N, N * sizeof(double2), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    RB_CATCH
+}
+
+static void integrate_host(const double* initialState, size_t N, size_t batch, const rb_props& p, double dt, size_t steps,
+                           bool trajectory, std::vector<double>& states, std::vector<double>& times, double t0) {
+    std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, (int)batch, &p), solver_free);
+    std::unique_ptr<rb_stepper, void (*)(rb_stepper*)> st(rb_rk4_create(s.get(), dt), stepper_free);
+    if (!st) throw std::runtime_error(g_last_error);
+    const size_t BN = N * batch;
+    std::vector<double2> host(2 * BN);
+    for (size_t i = 0; i < BN; ++i) {
+        host[i] = make_double2(initialState[i], initialState[BN + i]);
+        host[BN + i] = make_double2(initialState[2 * BN + i], 0.0);
+    }
+    if (rb_rk4_initialize(st.get(), (rb_complex*)host.data(), 0) != 0) throw std::runtime_error(g_last_error);
+    st->t = t0;
+    auto unpack = [&](const double2* y, double* out) {
+        for (size_t i = 0; i < BN; ++i) {
+            out[i] = y[i].x;
+            out[BN + i] = y[i].y;
+            out[2 * BN + i] = y[BN + i].x;
+        }
+    };
+    if (trajectory) {
+        if (rb_rk4_set_logging(st.get(), 1, steps) != 0) throw std::runtime_error(g_last_error);
+        for (size_t i = 0; i < steps; ++i) stepper_step(st.get());
+        RB_CUDA(cudaStreamSynchronize(s->stream));
+        std::vector<double2> all(st->log_count * 2 * BN);
+        if (st->log_count)
+            RB_CUDA(cudaMemcpy(all.data(), st->log_states, all.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+        states.resize(st->log_count * 3 * BN);
+        for (size_t r = 0; r < st->log_count; ++r) unpack(all.data() + r * 2 * BN, states.data() + r * 3 * BN);
+        times = st->log_times;
+    } else {
+        for (size_t i = 0; i < steps; ++i) stepper_step(st.get());
+        if (rb_rk4_get_state(st.get(), (rb_complex*)host.data()) != 0) throw std::runtime_error(g_last_error);
+        states.resize(3 * BN);
+        unpack(host.data(), states.data());
+        times.clear();
+    }
+}
+
+int integrateSimulationRK4(double* initialState, double** statesOut, size_t* statesCount, double** timesOut, size_t* timesCount,
+                           SimProperties* simProperties, RK4SolverOptions* rkOptions, size_t N) {
+    RB_TRY
+    if (!initialState || !statesOut || !statesCount || !simProperties || !rkOptions)
+        throw std::runtime_error("integrateSimulationRK4: null argument");
+    Adim ad = adimensionalize(simProperties->L, simProperties->rho, simProperties->kappa, simProperties->depth);
+    rb_props p = helium_props(ad, simProperties->use_expansions, simProperties->expansion_order, simProperties->infinite_depth);
+    p.guess_mode = RB_GUESS_WARM;
+    // adimensionalizeRK4SolverOptions, L/Export.cu:1213-1220
+    const double dt = rkOptions->timeStep / ad.base_time, t0 = rkOptions->t0 / ad.base_time, t1 = rkOptions->t1 / ad.base_time;
+    const size_t steps = static_cast<size_t>((t1 - t0) / dt);
+    std::vector<double> states, times;
+    integrate_host(initialState, N, 1, p, dt, steps, rkOptions->returnTrajectory, states, times, t0);
+    double* so = (double*)std::malloc(std::max<size_t>(states.size(), 1) * sizeof(double));
+    std::memcpy(so, states.data(), states.size() * sizeof(double));
+    *statesOut = so;
+    *statesCount = states.size() / (3 * N);
+    if (timesOut) {
+        double* to = (double*)std::malloc(std::max<size_t>(times.size(), 1) * sizeof(double));
+        std::memcpy(to, times.data(), times.size() * sizeof(double));
+        *timesOut = to;
+    }
+    if (timesCount) *timesCount = times.size();
+    RB_CATCH
+}
+
+int integrateSimulationRK4_freeMemory(double* statesOut, double* timesOut) {
+    std::free(statesOut);
+    std::free(timesOut);
+    return 0;
+}
+
+int rb_integrate_rk4_host(const double* initialState_host, double* finalState_host, size_t N, size_t batch,
+                          const rb_props* props, double dt, size_t steps) {
+    RB_TRY
+    rb_props p;
+    if (props) p = *props; else rb_default_props(&p);
+    std::vector<double> states, times;
+    integrate_host(initialState_host, N, batch, p, dt, steps, false, states, times, 0.0);
+    std::memcpy(finalState_host, states.data(), states.size() * sizeof(double));
+    RB_CATCH
+}
+
+}  // extern "C"

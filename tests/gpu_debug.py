@@ -1,0 +1,162 @@
+"""Diagnostic sweep over the CUDA path (prints errors instead of asserting).  Run under gpurun:
+    python tests/gpu_debug.py > gpurun_out/debug.log 2>&1
+"""
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import roberts_oracle as ro  # noqa: E402
+from superfluid_dynamics_b200 import api  # noqa: E402
+
+dev = torch.device("cuda:0")
+
+
+def T(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev)
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def section(name, fn):
+    t = time.time()
+    try:
+        fn()
+    except Exception:
+        print(f"[{name}] EXCEPTION")
+        traceback.print_exc()
+    print(f"[{name}] done in {time.time() - t:.2f}s", flush=True)
+
+
+def dense():
+    for N, h, t in ((2, 0.5, 0.0), (4, 0.5, 0.1), (8, 0.5, 0.1), (64, 0.3, 0.0)):
+        Z, Phi = ro.trochoid(N, h, 10.0, t)
+        Zp, Zpp, _ = ro.trochoid_derivatives(N, h, 10.0, t)
+        A = torch.empty(N * N, dtype=torch.float64, device=dev)
+        api.createMKernel(A, T(Z), T(Zp), T(Zpp), 0.0, N)
+        print("createM", N, rel(A.cpu().numpy().reshape(N, N).T, ro.create_M(Z, Zp, Zpp, 0.0)))
+        api.createFiniteDepthMKernel(A, T(Z), T(Zp), T(Zpp), 0.3, N, 1, False)
+        print("createFiniteDepthM", N, rel(A.cpu().numpy().reshape(N, N).T, ro.create_finite_depth_M(Z, Zp, Zpp, 0.3)))
+        V1 = torch.empty(N * N, dtype=torch.complex128, device=dev)
+        V2 = torch.empty(N, dtype=torch.complex128, device=dev)
+        for lower in (True, False):
+            api.createVelocityMatrices(T(Z), T(Zp), T(Zpp), N, V1, V2, lower)
+            e1, e2 = ro.velocity_matrices(Z, Zp, Zpp, lower)
+            print("V1/V2", N, lower, rel(V1.cpu().numpy().reshape(N, N).T, e1), rel(V2.cpu().numpy(), e2))
+            api.createHeliumVelocityMatrices(T(Z), T(Zp), T(Zpp), 0.3, N, V1, V2, lower)
+            e1, e2 = ro.helium_velocity_matrices(Z, Zp, Zpp, 0.3, lower)
+            print("helium V1/V2", N, lower, rel(V1.cpu().numpy().reshape(N, N).T, e1), rel(V2.cpu().numpy(), e2))
+
+
+def derivs():
+    for N in (4, 8, 64, 1024, 1000):
+        Z, Phi = ro.trochoid(N, 0.5, 10.0, 0.0)
+        props = api.ProblemProperties(rho=0.0)
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+        Zp, PhiP, Zpp = calc.zPhiDerivative(T(Z), T(Phi.astype(np.complex128)))
+        eZp, ePhiP, eZpp = ro.zphi_derivative(Z, Phi, ro.ProblemProperties(rho=0.0), "cuda")
+        print("zphi", N, np.abs(Zp.cpu().numpy() - eZp).max(), np.abs(Zpp.cpu().numpy() - eZpp).max(),
+              np.abs(PhiP.cpu().numpy() - ePhiP).max())
+        x = np.cos(3 * np.arange(N) * 2 * np.pi / N) + 0.1 * np.random.default_rng(0).standard_normal(N)
+        d = calc.fftDerivative(T(x.astype(np.complex128)), False, 0.5)
+        print("fftDerivative", N, np.abs(d.cpu().numpy() - ro.fft_derivative(x, 0.5)).max())
+        d = calc.fftDerivative(T(x.astype(np.complex128)), True, 1.0)
+        print("fftDerivative2", N, np.abs(d.cpu().numpy() - ro.fft_derivative(x, 1.0, second=True)).max())
+
+
+def cotsum():
+    for N, h in ((64, 0.3), (256, 0.3), (1000, 0.4), (1024, 0.4), (4096, 0.4), (5000, 0.2)):
+        Z, Phi = ro.trochoid(N, h)
+        props = api.ProblemProperties(rho=0.0)
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+        calc.zPhiDerivative(T(Z), T(Phi.astype(np.complex128)))
+        x = np.cos(3 * 2 * np.pi * np.arange(N) / N) + 0.3 * np.sin(2 * np.pi * np.arange(N) / N) + 0.1
+        S = calc.cotangentSum(T(Z), T(x)).cpu().numpy()
+        rows = np.arange(N) if N <= 1024 else np.r_[0:4, N - 4:N, N // 2 - 2:N // 2 + 2, 255:258, 511:514]
+        e = ro.cot_rowsum(Z, x, rows)
+        print("cotsum", N, h, rel(S[rows], e), "nan" if np.isnan(S).any() else "")
+
+
+def full_rhs():
+    for physics, N, h, B in (("water", 64, 0.1, 1), ("water", 64, 0.4, 1), ("water", 256, 0.4, 1), ("water", 1000, 0.3, 1),
+                             ("water", 1024, 0.4, 1), ("water", 2048, 0.4, 1), ("water", 128, 0.3, 3),
+                             ("helium_inf", 256, 0.05, 1), ("helium", 256, 0.01, 1), ("helium", 128, 0.02, 2)):
+        rho = 0.0
+        depth = 0.3 if physics != "water" else 1.0
+        props = api.ProblemProperties(rho=rho, depth=depth)
+        oprops = ro.ProblemProperties(rho=rho, depth=depth)
+        prob = {"water": api.WaterBoundaryProblem, "helium": api.HeliumBoundaryProblem,
+                "helium_inf": api.HeliumInfiniteDepthBoundaryProblem}[physics](props)
+        states = []
+        for b in range(B):
+            Z, Phi = ro.trochoid(N, h * (1 + 0.3 * b))
+            states.append((Z, Phi))
+        st = np.concatenate([s[0] for s in states] + [s[1].astype(np.complex128) for s in states])
+        for mode in ("matrix_free", "dense_lu"):
+            calc = api.BaseBoundaryIntegralCalculator(N, B, props, prob, solve_mode=mode)
+            out = torch.zeros(2 * N * B, dtype=torch.complex128, device=dev)
+            calc.run(T(st), out)
+            torch.cuda.synchronize()
+            e = ro.rhs(st, N, B, oprops, physics, "cuda")
+            o = out.cpu().numpy()
+            stats = calc.solve_stats()
+            print("rhs", physics, N, h, B, mode, "vel", rel(o[:N * B], e[:N * B]), "dphi", rel(o[N * B:], e[N * B:]), stats)
+            _, _, aux = ro.rhs_single(states[0][0], states[0][1], oprops, physics, "cuda", full=True)
+            print("    a", rel(calc.getDevA().cpu().numpy()[:N], aux["a"]), "upper",
+                  rel(calc.devVelocitiesUpper.cpu().numpy()[:N], aux["v_upper"]))
+
+
+def rk4():
+    for N, h, steps in ((64, 0.1, 100), (64, 0.4, 100), (256, 0.3, 100), (1024, 0.4, 20)):
+        props = api.ProblemProperties(rho=0.0)
+        oprops = ro.ProblemProperties(rho=0.0)
+        Z, Phi = ro.trochoid(N, h)
+        y0 = ro.pack_state(Z, Phi)
+        f = lambda s: ro.rhs(s, N, 1, oprops, "water", "cuda")
+        ye = y0.copy()
+        for _ in range(steps):
+            ye = ro.rk4_step(f, ye, 1e-3)
+        for guess in ("cold", "warm"):
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess=guess)
+            stp = api.AutonomousRungeKuttaStepper(calc, 1e-3)
+            stp.initialize(y0, False)
+            t0 = time.time()
+            stp.runSteps(steps)
+            y = stp.getState()
+            dt = time.time() - t0
+            print("rk4", N, h, steps, guess, "Z", rel(y[:N], ye[:N]), "Phi", rel(y[N:], ye[N:]), f"{steps / dt:.1f} steps/s",
+                  calc.solve_stats())
+
+
+def speed():
+    print("fp64 peak TFLOP/s", api.measure_fp64_peak())
+    for N in (1024, 4096, 16384, 65536):
+        props = api.ProblemProperties(rho=0.0)
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+        Z, Phi = ro.trochoid(N, 0.4)
+        st = T(ro.pack_state(Z, Phi))
+        ms, pairs = calc.benchSweep(st, 10)
+        print(f"sweep N={N}: {ms * 1e3:.1f} us, {pairs / ms / 1e9:.3f} Gpairs/ms = {20 * pairs / (ms * 1e-3) / 1e12:.2f} TFLOP/s (20 flop/pair)")
+        out = torch.zeros_like(st)
+        calc.run(st, out)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(5):
+            calc.run(st, out)
+        torch.cuda.synchronize()
+        print(f"   rhs {1e3 * (time.time() - t0) / 5:.3f} ms", calc.solve_stats())
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["dense", "derivs", "cotsum", "full_rhs", "rk4", "speed"]
+    print(torch.cuda.get_device_name(0))
+    for w in which:
+        section(w, globals()[w])
