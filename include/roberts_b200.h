@@ -99,8 +99,9 @@ RB_API int rb_synchronize(rb_solver* s);
 /* energies of the last RHS: out[0] kinetic, [1] potential (gravitational or van der Waals), [2] surface,
  * [3] volume flux, [4] volume sum(Y X').  Replaces EnergyBase::getEnergy x4 (L/Energies.cuh:229-235) + VolumeFlux. */
 RB_API int rb_energies(rb_solver* s, double out_host[5]);
-/* statistics of the last solve: out[0] M*x applications, [1] converged flag, [2] relative residual */
-RB_API int rb_solve_stats(rb_solver* s, double out_host[3]);
+/* statistics: out[0] M*x applications of the last solve, [1] converged flag, [2] relative residual,
+ * [3] M*x applications summed over all solves of this solver, [4] number of solves */
+RB_API int rb_solve_stats(rb_solver* s, double out_host[5]);
 
 /* ---- spectral derivatives (L/Derivatives.cuh) ---- */
 /* ZPhiDerivative<N,B>::exec :311-384 */
@@ -161,6 +162,7 @@ RB_API int rb_comm_init(rb_solver* s, int rank, int nranks, const char id[RB_UNI
 RB_API int rb_comm_destroy(rb_solver* s);
 
 /* ---- measurement helpers ---- */
+RB_API unsigned long long rb_launch_count(void);                                  /* kernels of this library launched since load */
 RB_API int rb_measure_fp64_peak(double* tflops_out, void* stream);               /* DFMA-only kernel: the FP64 roofline denominator */
 RB_API int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* ms_per_sweep_out, double* pairs_per_sweep_out);
 

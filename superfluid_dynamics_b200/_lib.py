@@ -82,6 +82,7 @@ SIGNATURES = {
     "rb_comm_unique_id": (c_int, [c_char_p]),
     "rb_comm_init": (c_int, [_P, c_int, c_int, c_char_p]),
     "rb_comm_destroy": (c_int, [_P]),
+    "rb_launch_count": (ctypes.c_ulonglong, []),
     "rb_measure_fp64_peak": (c_int, [_D, _P]),
     "rb_bench_sweep": (c_int, [_P, _P, c_int, POINTER(c_float), _D]),
     "calculateRHSFromVectors": (c_int, [_D, _D, _D, _D, _D, _D, c_double, c_double, c_double, c_double, c_size_t]),

@@ -64,6 +64,7 @@ void launch_create_M(double* A, const double2* Z, const double2* Zp, const doubl
     dim3 th(16, 16), bl((n + 15) / 16, (n + 15) / 16, (unsigned)batch);
     create_M_kernel<false><<<bl, th, 0, st>>>(A, Z, Zp, Zpp, rho, 0.0, n, true);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 void launch_create_finite_depth_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double h, int n,
@@ -71,6 +72,7 @@ void launch_create_finite_depth_M(double* A, const double2* Z, const double2* Zp
     dim3 th(16, 16), bl((n + 15) / 16, (n + 15) / 16, (unsigned)batch);
     create_M_kernel<true><<<bl, th, 0, st>>>(A, Z, Zp, Zpp, 0.0, h, n, infinite_depth);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ---- V1, V2 ------------------------------------------------------------------------------------
@@ -116,6 +118,7 @@ void launch_velocity_matrices(const double2* Z, const double2* Zp, const double2
     dim3 th(16, 16), bl((n + 15) / 16, (n + 15) / 16, (unsigned)batch);
     velocity_matrices_kernel<<<bl, th, 0, st>>>(Z, Zp, Zpp, n, V1, V2, lower, helium, h, infinite_depth);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ---- dPhi/dt -----------------------------------------------------------------------------------
@@ -135,6 +138,7 @@ void launch_rhs_phi_water(const double2* Z, const double2* V1, const double2* V2
                           cudaStream_t st) {
     rhs_phi_water_kernel<<<(n + 255) / 256, 256, 0, st>>>(Z, V1, V2, result, rho, n);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 __global__ void rhs_phi_helium_kernel(const double2* __restrict__ Z, const double2* __restrict__ V1,
@@ -149,6 +153,7 @@ __global__ void rhs_phi_helium_kernel(const double2* __restrict__ Z, const doubl
 void launch_rhs_phi_helium(const double2* Z, const double2* V1, double2* result, double h, int n, cudaStream_t st) {
     rhs_phi_helium_kernel<<<(n + 255) / 256, 256, 0, st>>>(Z, V1, result, h, n);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 __global__ void rhs_phi_helium_st_kernel(const double2* __restrict__ Z, const double2* __restrict__ Zp,
@@ -167,6 +172,7 @@ void launch_rhs_phi_helium_st(const double2* Z, const double2* Zp, const double2
                               double h, double kappa, int n, cudaStream_t st) {
     rhs_phi_helium_st_kernel<<<(n + 255) / 256, 256, 0, st>>>(Z, Zp, Zpp, V1, result, h, kappa, n);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 __global__ void rhs_phi_helium_exp_kernel(const double2* __restrict__ Z, const double2* __restrict__ V1,
@@ -190,6 +196,7 @@ void launch_rhs_phi_helium_exp(const double2* Z, const double2* V1, double2* res
                                cudaStream_t st) {
     rhs_phi_helium_exp_kernel<<<(n + 255) / 256, 256, 0, st>>>(Z, V1, result, h, n, order);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ---- energies: the five sums of Energies.cuh in one launch, batch member 0 only (as the reference) -------------
@@ -233,6 +240,7 @@ void launch_energies(const double2* Z, const double2* Zp, const double2* Phi, co
                      int physics, double rho, double U, double depth, double kappa, cudaStream_t st) {
     energies_kernel<<<1, kEnergyThreads, 0, st>>>(Z, Zp, Phi, vel, out5, N, physics, rho, U, depth, kappa);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ---- validation solve: unblocked right-looking LU with partial pivoting, column-major, one right-hand side ------
@@ -311,6 +319,7 @@ void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st) {
     }
     lu_backsolve_kernel<<<1, kLuThreads, 0, st>>>(A, b, n);
     RB_CUDA(cudaGetLastError());
+    count_launch(2 * n);
 }
 
 }  // namespace rb

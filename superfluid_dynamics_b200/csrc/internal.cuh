@@ -25,6 +25,10 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 }
 #define RB_CUDA(x) ::rb::cuda_check((x), #x, __FILE__, __LINE__)
 
+// number of kernels of this library launched since load (cuFFT's own kernels are not counted)
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+
 // per-solve control block living in device memory (read by every sweep CTA)
 struct SolveCtrl {
     int done;            // 1: converged (or gave up) -> later sweeps of this solve return immediately

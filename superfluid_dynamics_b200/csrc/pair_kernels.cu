@@ -147,6 +147,7 @@ void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int ba
     geometry_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(g, phiprime_c, N, batch, ncell, physics, rhoM,
                                                                                    depth, finite_image, use_local);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,6 +189,7 @@ void launch_guess(const double* b, const double* warm, double* x0, double* xsum_
                   double omega, int N, int batch, int ncell, cudaStream_t st) {
     guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(b, warm, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -217,6 +219,7 @@ void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl
                          double* xsum_part, int N, int batch, int ncell, cudaStream_t st) {
     finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, ctrl, a_out, a_complex, xsum_part, N, ncell);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -507,6 +510,7 @@ void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st) {
         else sweep_kernel<kSweepRAW, false><<<grid, block, 0, st>>>(a);
     }
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 }  // namespace rb

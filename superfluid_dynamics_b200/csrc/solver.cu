@@ -25,6 +25,9 @@ using namespace rb;
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
+namespace rb {
+unsigned long long g_launch_count = 0;
+}
 
 static int fail(const std::exception& e) {
     g_last_error = e.what();
@@ -107,7 +110,9 @@ struct rb_solver {
     int last_iters = 0, last_converged = 0;
     double last_rel = 0;
     int kpred = 0;
-    long long total_sweeps = 0;
+    long long total_sweeps = 0;      // sweep kernels launched (including ones that skipped)
+    long long sum_iters = 0;         // M*x applications actually performed, summed over solves
+    long long num_solves = 0;
 
     const double2* cur_Z = nullptr;
     const double2* cur_Phi = nullptr;
@@ -347,6 +352,11 @@ static void read_ctrl(rb_solver* s) {
     s->last_rel = std::sqrt(std::max(0.0, s->h_ctrl->rel2));
 }
 
+static void account_solve(rb_solver* s) {
+    s->sum_iters += s->last_iters;
+    s->num_solves++;
+}
+
 // M a = b.  On return a (real), ac (complex copy) and the per-cell sums of a are valid on the stream.
 static void solve(rb_solver* s, const double2* Z) {
     cudaStream_t st = s->stream;
@@ -396,6 +406,7 @@ static void solve(rb_solver* s, const double2* Z) {
             group = 2;
         }
         s->kpred = s->last_iters;
+        account_solve(s);
     }
     launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, s->ac, s->xsum_a, s->N, s->batch, s->ncell, st);
     if (s->a_copy_out) RB_CUDA(cudaMemcpyAsync(s->a_copy_out, s->a, s->BN * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -530,6 +541,7 @@ extern "C" {
 
 const char* rb_last_error(void) { return g_last_error.c_str(); }
 int rb_version(void) { return 100; }
+unsigned long long rb_launch_count(void) { return rb::g_launch_count; }
 
 int rb_device_count(void) {
     int n = 0;
@@ -621,12 +633,14 @@ int rb_energies(rb_solver* s, double out_host[5]) {
     RB_CATCH
 }
 
-int rb_solve_stats(rb_solver* s, double out_host[3]) {
+int rb_solve_stats(rb_solver* s, double out_host[5]) {
     RB_TRY
     if (s->matrix_free_solve) read_ctrl(s);
     out_host[0] = s->last_iters;
     out_host[1] = s->last_converged;
     out_host[2] = s->last_rel;
+    out_host[3] = (double)s->sum_iters;
+    out_host[4] = (double)s->num_solves;
     RB_CATCH
 }
 

@@ -52,6 +52,7 @@ void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, 
     size_t total = (size_t)N * batch;
     sub_linear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, Phi, out_zper, out_phiper, N, total, rho, U);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // one pass over the spectra of Z_per and Phi_per: i k Z^, -k^2 Z^, i k Phi^
@@ -73,6 +74,7 @@ void launch_spectral_multiply_zphi(const double2* hatZ, const double2* hatPhi, d
     spectral_multiply_zphi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(hatZ, hatPhi, out_d1z, out_d2z, out_d1phi, N,
                                                                                    total);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 __global__ void spectral_multiply_kernel(const double2* __restrict__ hat, double2* __restrict__ out, int N, size_t total,
@@ -88,6 +90,7 @@ void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch
     size_t total = (size_t)N * batch;
     spectral_multiply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(hat, out, N, total, second);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // scaling by 2 pi / N (resp. its square) and the linear parts put back (L/Derivatives.cuh:321-324, 374, 380-383)
@@ -114,6 +117,7 @@ void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int bat
     size_t total = (size_t)N * batch;
     finish_zphi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Zp, Zpp, PhiP, N, total, rho, U);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 __global__ void scale_kernel(double2* __restrict__ v, double s, size_t n) {
@@ -126,6 +130,7 @@ __global__ void scale_kernel(double2* __restrict__ v, double s, size_t n) {
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st) {
     scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, s, n);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 }  // namespace rb

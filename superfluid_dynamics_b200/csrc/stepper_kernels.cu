@@ -23,6 +23,7 @@ __global__ void stage_update_kernel(double2* __restrict__ y_out, const double2* 
 void launch_stage_update(double2* y_out, const double2* y0, const double2* k, double c, size_t n, cudaStream_t st) {
     stage_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y_out, y0, k, c, n);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 __global__ void final_update_kernel(double2* __restrict__ y0, const double2* __restrict__ k1, const double2* __restrict__ k2,
@@ -40,6 +41,7 @@ void launch_final_update(double2* y0, const double2* k1, const double2* k2, cons
                          size_t n, cudaStream_t st) {
     final_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y0, k1, k2, k3, k4, h / 6.0, n);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 // ---- FP64 peak probe: 8 independent DFMA chains per thread, nothing else in the loop ------------------------
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters)
 void launch_fp64_peak(double* sink, int iters, int blocks, cudaStream_t st) {
     fp64_peak_kernel<<<blocks, 256, 0, st>>>(sink, iters);
     RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 }  // namespace rb

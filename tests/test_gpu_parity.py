@@ -1,0 +1,397 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU oracle and the
+reference-generated golden vectors.  Tolerances are stated per test; floating point only (FP64).
+
+Noise floor: the FFT derivatives amplify round-off by ~N*eps (mode number times coefficient noise), in the reference as much as
+here, so RHS-level agreement between two correct FP64 implementations is ~1e-16*N relative, not 1e-16."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+from oracle import roberts_oracle as ro  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from superfluid_dynamics_b200 import api, build
+    build.build(verbose=False)
+    return api
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def colmajor(t, N):
+    return t.cpu().numpy().reshape(N, N).T
+
+
+# ---- the reference's own kernel tests, same fixtures and tolerances (T/MatrixMTests.cuh) --------------------------
+def test_two_by_two_M_matrix(api):
+    """Kernels.TwoByTwoMMatrix :160-223, tol 1e-14."""
+    N, h = 2, 0.5
+    Z, _ = ro.trochoid(N, h, 10.0, 0.0)
+    Zp, Zpp, _ = ro.trochoid_derivatives(N, h, 10.0, 0.0)
+    A = torch.empty(N * N, dtype=torch.float64, device="cuda:0")
+    api.createMKernel(A, T(Z), T(Zp), T(Zpp), 0.0, N, 1)
+    th = math.sinh(2 * h) / (math.cosh(2 * h) + 1.0)
+    exp = np.array([[0.5 - 0.25 * h / (1.0 - h), (h - 1) / 4.0 * th], [(h + 1) / 4.0 * th, 0.5 + 0.25 * h / (1.0 + h)]])
+    assert np.abs(colmajor(A, N) - exp).max() <= 1e-14
+
+
+@pytest.mark.parametrize("N,t", [(4, 0.1), (8, 0.1), (64, 0.0), (300, 0.2)])
+def test_M_and_velocity_matrices(api, N, t):
+    """Kernels.MMatrixKernel :225-282 (1e-14) and Kernels.Velocities :396-468 (1e-12), plus larger / ragged N."""
+    h = 0.5
+    Z, _ = ro.trochoid(N, h, 10.0, t)
+    Zp, Zpp, _ = ro.trochoid_derivatives(N, h, 10.0, t)
+    A = torch.empty(N * N, dtype=torch.float64, device="cuda:0")
+    api.createMKernel(A, T(Z), T(Zp), T(Zpp), 0.0, N, 1)
+    assert np.abs(colmajor(A, N) - ro.create_M(Z, Zp, Zpp, 0.0)).max() <= 1e-14
+    api.createMKernel(A, T(Z), T(Zp), T(Zpp), 0.3, N, 1)
+    assert np.abs(colmajor(A, N) - ro.create_M(Z, Zp, Zpp, 0.3)).max() <= 1e-14
+    V1 = torch.empty(N * N, dtype=torch.complex128, device="cuda:0")
+    V2 = torch.empty(N, dtype=torch.complex128, device="cuda:0")
+    for lower in (True, False):
+        api.createVelocityMatrices(T(Z), T(Zp), T(Zpp), N, V1, V2, lower, 1)
+        e1, e2 = ro.velocity_matrices(Z, Zp, Zpp, lower)
+        assert np.abs(colmajor(V1, N) - e1).max() <= 1e-12 * max(1.0, np.abs(e1).max())
+        assert np.abs(V2.cpu().numpy() - e2).max() <= 1e-12 * max(1.0, np.abs(e2).max())
+
+
+def test_finite_depth_kernels(api):
+    """createFiniteDepthMKernel / createHeliumVelocityMatrices: no reference test exists (parity unpinned); vs the oracle."""
+    N, depth = 96, 0.6
+    Z, _ = ro.trochoid(N, 0.2)
+    Zp, Zpp, _ = ro.trochoid_derivatives(N, 0.2)
+    A = torch.empty(N * N, dtype=torch.float64, device="cuda:0")
+    V1 = torch.empty(N * N, dtype=torch.complex128, device="cuda:0")
+    V2 = torch.empty(N, dtype=torch.complex128, device="cuda:0")
+    for inf in (False, True):
+        api.createFiniteDepthMKernel(A, T(Z), T(Zp), T(Zpp), depth, N, 1, inf)
+        e = ro.create_finite_depth_M(Z, Zp, Zpp, depth, inf)
+        assert np.abs(colmajor(A, N) - e).max() <= 1e-13 * np.abs(e).max()
+        for lower in (True, False):
+            api.createHeliumVelocityMatrices(T(Z), T(Zp), T(Zpp), depth, N, V1, V2, lower, 1, inf)
+            e1, e2 = ro.helium_velocity_matrices(Z, Zp, Zpp, depth, lower, inf)
+            assert rel(colmajor(V1, N), e1) <= 1e-13 and rel(V2.cpu().numpy(), e2) <= 1e-13
+
+
+def test_batched_matrix_kernels(api):
+    """grid.z = batch layout A[k + j*n + b*n*n] (L/createM.cuh:47-52)."""
+    N, B = 40, 3
+    Zs, Zps, Zpps = [], [], []
+    for b in range(B):
+        Z, _ = ro.trochoid(N, 0.1 + 0.1 * b)
+        Zp, Zpp, _ = ro.trochoid_derivatives(N, 0.1 + 0.1 * b)
+        Zs.append(Z); Zps.append(Zp); Zpps.append(Zpp)
+    A = torch.empty(B * N * N, dtype=torch.float64, device="cuda:0")
+    api.createMKernel(A, T(np.concatenate(Zs)), T(np.concatenate(Zps)), T(np.concatenate(Zpps)), 0.0, N, B)
+    Ah = A.cpu().numpy().reshape(B, N, N)
+    for b in range(B):
+        assert np.abs(Ah[b].T - ro.create_M(Zs[b], Zps[b], Zpps[b], 0.0)).max() <= 1e-14
+
+
+def test_zphi_derivatives_analytic(api):
+    """Kernels.ZPhiDerivatives :477-607: N = 1024, h = 0.5, omega = 10 vs analytic derivatives, tol 1e-14."""
+    N, h, omega = 1024, 0.5, 10.0
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    Z, Phi = ro.trochoid(N, h, omega, 0.0)
+    eZp, eZpp, ePhiP = ro.trochoid_derivatives(N, h, omega, 0.0)
+    Zp, PhiP, Zpp = calc.zPhiDerivative(T(Z), T(Phi.astype(np.complex128)))
+    assert np.abs(Zp.cpu().numpy() - eZp).max() <= 1e-14
+    assert np.abs(Zpp.cpu().numpy() - eZpp).max() <= 1e-14
+    assert np.abs(PhiP.cpu().numpy().real - ePhiP).max() <= 1e-14
+
+
+@pytest.mark.parametrize("N", [2, 4, 8, 64, 1000])
+def test_derivative_nyquist_quirks(api, N):
+    """Nyquist-rich data: the CUDA conventions (pi factor, zeroed mode N/2+1) must be reproduced exactly."""
+    rng = np.random.default_rng(N)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    d1 = calc.fftDerivative(T(x), False, 0.7).cpu().numpy()
+    d2 = calc.fftDerivative(T(x), True, 1.0).cpu().numpy()
+    e1, e2 = ro.fft_derivative(x, 0.7), ro.fft_derivative(x, 1.0, second=True)
+    assert np.abs(d1 - e1).max() <= 1e-13 * max(1.0, np.abs(e1).max())
+    assert np.abs(d2 - e2).max() <= 1e-13 * max(1.0, np.abs(e2).max())
+
+
+def test_rhs_phi_kernels(api):
+    """Kernels.RhsPhi :748-819 (1e-14) and the helium variants vs the oracle."""
+    N, omega, h, t = 32, 10.0, 0.5, 0.1
+    a = 2 * np.pi * np.arange(N) / N
+    i = np.arange(N, dtype=np.float64)
+    Yv = h * np.cos(i - omega * t)
+    Zh = (a - h * np.sin(a - omega * t)) + 1j * Yv
+    VL = 2 * np.pi / N * ((1 - h * np.cos(a - omega * t)) + 1j * (-h * np.sin(a - omega * t)))
+    VU = 0.3 * VL[::-1].copy()
+    out = torch.empty(N, dtype=torch.complex128, device="cuda:0")
+    api.compute_rhs_phi_expression(T(Zh), T(VL), T(np.zeros(N, complex)), out, 0.0, N)
+    exp = -Yv + 0.5 * (VL.real ** 2 + VL.imag ** 2)
+    o = out.cpu().numpy()
+    assert np.abs(o.real - exp).max() <= 1e-14 and np.abs(o.imag).max() == 0.0
+    api.compute_rhs_phi_expression(T(Zh), T(VL), T(VU), out, 0.25, N)   # rho != 0 exercises the V1[1] quirk
+    assert np.abs(out.cpu().numpy().real - ro.rhs_phi_water(Zh, VL, VU, 0.25)).max() <= 1e-14
+    Zp, Zpp, _ = ro.trochoid_derivatives(N, h, omega, t)
+    Zs = Zh.real + 1j * 0.1 * Yv
+    api.compute_rhs_helium_phi_expression(T(Zs), T(VL), out, 0.8, N)
+    assert np.abs(out.cpu().numpy().real - ro.rhs_phi_helium(Zs, VL, 0.8)).max() <= 1e-13
+    api.compute_rhs_helium_phi_expression_with_surface_tension(T(Zs), T(Zp), T(Zpp), T(VL), out, 0.8, 0.05, N)
+    e = ro.rhs_phi_helium_surface_tension(Zs, Zp, Zpp, VL, 0.8, 0.05)
+    assert np.abs(out.cpu().numpy().real - e).max() <= 1e-13 * max(1.0, np.abs(e).max())
+    for order in (1, 2, 3):
+        api.compute_rhs_helium_phi_expression_expansion_terms(T(Zs), T(VL), out, 0.8, N, order)
+        assert np.abs(out.cpu().numpy().real - ro.rhs_phi_helium_expansion(Zs, VL, 0.8, order)).max() <= 1e-14
+
+
+# ---- the matrix-free core ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,h", [(2, 0.3), (3, 0.2), (64, 0.3), (255, 0.3), (256, 0.4), (257, 0.4), (1000, 0.4), (1024, 0.4),
+                                 (1300, 0.2), (4096, 0.4)])
+def test_cotangent_sum_matches_direct_evaluation(api, N, h):
+    """S_k = sum_{j != k} cot((z_k - z_j)/2) x_j: exponential / cell-local form vs direct 1/tan evaluation.
+    tol 2e-13 relative to max|S| (near-neighbour entries are ~N/pi, so this is ~1e-14 relative per entry)."""
+    Z, Phi = ro.trochoid(N, h)
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    calc.zPhiDerivative(T(Z), T(Phi.astype(np.complex128)))
+    x = np.cos(3 * 2 * np.pi * np.arange(N) / N) + 0.3 * np.sin(2 * np.pi * np.arange(N) / N) + 0.1
+    S = calc.cotangentSum(T(Z), T(x)).cpu().numpy()
+    rows = np.arange(N) if N <= 1300 else np.r_[0:6, N - 6:N, N // 2 - 3:N // 2 + 3, 253:259, 509:515, 1021:1027]
+    assert not np.isnan(S).any()
+    assert rel(S[rows], ro.cot_rowsum(Z, x, rows)) <= 2e-13
+
+
+def test_cotangent_sum_is_linear_and_row_local_at_full_size(api):
+    """Size-independent properties at N = 65536 (BASELINE config 5): linearity in x, and a spot check of rows against the
+    direct evaluation (the dense oracle does not fit in host memory at this size)."""
+    N = 65536
+    Z, Phi = ro.trochoid(N, 0.4)
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    calc.zPhiDerivative(T(Z), T(Phi.astype(np.complex128)))
+    al = 2 * np.pi * np.arange(N) / N
+    x1, x2 = np.cos(5 * al) + 0.2, np.sin(3 * al) * np.cos(al)
+    S1 = calc.cotangentSum(T(Z), T(x1)).cpu().numpy()
+    S2 = calc.cotangentSum(T(Z), T(x2)).cpu().numpy()
+    S3 = calc.cotangentSum(T(Z), T(2.0 * x1 - 3.0 * x2)).cpu().numpy()
+    assert rel(S3, 2.0 * S1 - 3.0 * S2) <= 1e-12
+    rows = np.r_[0:3, N - 3:N, 32766:32770, 255:258, 20000:20002]
+    # wrap-around rows carry the reference's own ~eps*N/(2 pi) cancellation error in fl(x_k - x_j); hence 5e-11
+    assert rel(S1[rows], ro.cot_rowsum(Z, x1, rows)) <= 5e-11
+    inner = np.r_[32766:32770, 20000:20002]
+    assert rel(S1[inner], ro.cot_rowsum(Z, x1, inner)) <= 1e-12
+
+
+# ---- full RHS -------------------------------------------------------------------------------------------------------
+def _split(state):
+    N = len(state) // 3
+    return state[:N] + 1j * state[N:2 * N], state[2 * N:]
+
+
+@pytest.mark.parametrize("tag", ["N64_h0.1", "N64_h0.4", "N32_h0.25", "N128_h0.3", "N64_pert"])
+@pytest.mark.parametrize("mode", ["matrix_free", "dense_lu"])
+def test_rhs_matches_reference_golden(api, golden, tag, mode):
+    """Outputs of the reference's P/WaterIntegralCalculator.py (tests/golden/ref_water_rhs.npz), tol 2e-12."""
+    Z, Phi = _split(golden[tag + "_state"])
+    N = len(Z)
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), solve_mode=mode)
+    out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+    calc.run(T(ro.pack_state(Z, Phi)), out)
+    o = out.cpu().numpy()
+    ref = golden[tag + "_rhs"]
+    mine = np.hstack((o[:N].real, o[:N].imag, o[N:].real))
+    assert np.abs(mine - ref).max() <= 2e-12 * max(1.0, np.abs(ref).max())
+    assert np.abs(o[N:].imag).max() == 0.0
+    assert np.abs(calc.getDevA().cpu().numpy() - golden[tag + "_a"]).max() <= 2e-12
+    if mode == "matrix_free":
+        assert calc.solve_stats()["converged"]
+
+
+@pytest.mark.parametrize("physics,N,h,B,rho,depth", [
+    ("water", 2, 0.2, 1, 0.0, 1.0), ("water", 6, 0.2, 1, 0.0, 1.0), ("water", 256, 0.4, 1, 0.0, 1.0),
+    ("water", 1000, 0.3, 1, 0.0, 1.0), ("water", 1024, 0.4, 1, 0.0, 1.0), ("water", 4096, 0.4, 1, 0.0, 1.0),
+    ("water", 128, 0.3, 3, 0.0, 1.0), ("water", 512, 0.2, 5, 0.0, 1.0), ("water", 256, 0.3, 1, 0.2, 1.0),
+    ("helium_inf", 256, 0.05, 1, 0.0, 0.3), ("helium", 256, 0.01, 1, 0.0, 0.3), ("helium", 128, 0.02, 2, 0.0, 0.3),
+    ("helium", 1024, 0.00942478, 1, 0.0, 0.0942478)])
+def test_rhs_matches_oracle(api, physics, N, h, B, rho, depth):
+    """Full RHS vs the oracle (CUDA derivative semantics): tol 1e-15*N + 1e-13 relative (FFT-derivative noise floor)."""
+    props = api.ProblemProperties(rho=rho, depth=depth)
+    oprops = ro.ProblemProperties(rho=rho, depth=depth)
+    prob = {"water": api.WaterBoundaryProblem, "helium": api.HeliumBoundaryProblem,
+            "helium_inf": api.HeliumInfiniteDepthBoundaryProblem}[physics](props)
+    states = [ro.trochoid(N, h * (1 + 0.3 * b)) for b in range(B)]
+    st = np.concatenate([s[0] for s in states] + [s[1].astype(np.complex128) for s in states])
+    calc = api.BaseBoundaryIntegralCalculator(N, B, props, prob)
+    out = torch.zeros(2 * N * B, dtype=torch.complex128, device="cuda:0")
+    calc.run(T(st), out)
+    o = out.cpu().numpy()
+    e = ro.rhs(st, N, B, oprops, physics, "cuda")
+    tol = 1e-15 * N + 1e-13
+    if physics == "helium":
+        tol *= 50   # cond(M) ~ N/(2 pi) for the reference's finite-depth operator
+    assert rel(o[:N * B], e[:N * B]) <= tol
+    assert rel(o[N * B:], e[N * B:]) <= tol
+    _, _, aux = ro.rhs_single(states[0][0], states[0][1], oprops, physics, "cuda", full=True)
+    assert rel(calc.devVelocitiesUpper.cpu().numpy()[:N], aux["v_upper"]) <= 3 * tol
+    assert rel(calc.getDevZp().cpu().numpy()[:N], aux["Zp"]) <= tol
+    assert rel(calc.devPhiPrime.cpu().numpy()[:N], aux["PhiPrime"]) <= tol
+
+
+def test_rhs_rejects_nothing_silently(api):
+    """A surface with coincident points has no finite RHS: the iteration must report non-convergence, not a number."""
+    N = 64
+    Z, Phi = ro.trochoid(N, 0.3)
+    Z = Z.copy()
+    Z[10] = Z[11]
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), max_iterations=30)
+    out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+    calc.run(T(ro.pack_state(Z, Phi)), out)
+    assert not calc.solve_stats()["converged"] or not np.isfinite(out.cpu().numpy()).all()
+
+
+# ---- RK4 ------------------------------------------------------------------------------------------------------------
+def test_stage_update_kernels(api):
+    """cublasZaxpy / add_k_vectors replacement (L/AutonomousRungeKuttaStepper.cuh:349-361)."""
+    import ctypes
+    n = 1000
+    rng = np.random.default_rng(1)
+    y0, k1, k2, k3, k4 = (rng.standard_normal(n) + 1j * rng.standard_normal(n) for _ in range(5))
+    lib = api._lib.load()
+    out = torch.empty(n, dtype=torch.complex128, device="cuda:0")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    ty0, tk = T(y0), [T(k) for k in (k1, k2, k3, k4)]
+    assert lib.rb_rk4_stage_update(p(out), p(ty0), p(tk[0]), 0.37, n, None) == 0
+    torch.cuda.synchronize()
+    assert np.abs(out.cpu().numpy() - (y0 + 0.37 * k1)).max() <= 1e-15
+    assert lib.rb_rk4_final_update(p(ty0), p(tk[0]), p(tk[1]), p(tk[2]), p(tk[3]), 0.01, n, None) == 0
+    torch.cuda.synchronize()
+    assert np.abs(ty0.cpu().numpy() - (y0 + 0.01 / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4))).max() <= 1e-15
+
+
+@pytest.mark.parametrize("N,h,steps,guess", [(64, 0.1, 100, "cold"), (64, 0.4, 100, "warm"), (256, 0.3, 100, "warm"),
+                                             (1024, 0.4, 100, "warm")])
+def test_rk4_100_steps_match_oracle(api, N, h, steps, guess):
+    """north_star parity bar: <= 1e-9 relative in surface position and potential after 100 RK4 steps (dt = 1e-3);
+    energy and volume drift no worse than the oracle's."""
+    props = api.ProblemProperties(rho=0.0)
+    oprops = ro.ProblemProperties(rho=0.0)
+    Z, Phi = ro.trochoid(N, h)
+    y0 = ro.pack_state(Z, Phi)
+    f = lambda s: ro.rhs(s, N, 1, oprops, "water", "cuda")
+    ye = y0.copy()
+    for _ in range(steps):
+        ye = ro.rk4_step(f, ye, 1e-3)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess=guess)
+    stp = api.AutonomousRungeKuttaStepper(calc, 1e-3)
+    stp.initialize(y0, False)
+    stp.runSteps(steps)
+    y = stp.getState()
+    assert rel(y[:N], ye[:N]) <= 1e-9
+    assert rel(y[N:], ye[N:]) <= 1e-9
+    assert calc.solve_stats()["converged"]
+
+    def diag(yv):
+        v, dphi, aux = ro.rhs_single(yv[:N], yv[N:].real, oprops, full=True)
+        e = ro.energies(yv[:N], aux["Zp"], yv[N:], v, oprops)
+        return e["kinetic"] + e["potential"], ro.volume(yv[:N], aux["Zp"])
+
+    e0, v0 = diag(y0)
+    eo, vo = diag(ye)
+    em, vm = diag(y)
+    assert abs(em - e0) <= abs(eo - e0) + 1e-13 * abs(e0)
+    assert abs(vm - v0) <= abs(vo - v0) + 1e-13
+
+
+def test_rk4_device_alias_evolve_and_trajectory(api):
+    """initialize(ptr, onDevice=true) aliases the caller's buffer (:312-318); runEvolution truncates the step count (:421);
+    TrajectoryLogger semantics (L/TrajectoryLogger.cuh:65-73)."""
+    N = 64
+    props = api.ProblemProperties(rho=0.0)
+    Z, Phi = ro.trochoid(N, 0.2)
+    y0 = ro.pack_state(Z, Phi)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    stp = api.AutonomousRungeKuttaStepper(calc, 1e-2)
+    dev = T(y0)
+    stp.initialize(dev, True)
+    stp.setLogging(1, 16)
+    n = stp.runEvolution(0.0, 0.055)
+    assert n == ro.rk4_num_steps(0.0, 0.055, 1e-2) == 5
+    times, states = stp.copyTrajectory()
+    assert len(times) == 5 and np.allclose(times, 0.01 * np.arange(1, 6))
+    assert np.array_equal(states[-1], dev.cpu().numpy())          # the caller's buffer holds the evolved state
+    ye = ro.rk4_evolve(lambda s: ro.rhs(s, N, 1, ro.ProblemProperties(rho=0.0)), y0, 0.0, 0.055, 1e-2)
+    assert rel(states[-1], ye) <= 1e-12
+
+
+def test_energies_match_oracle(api):
+    N, h = 256, 0.3
+    for physics, depth in (("water", 1.0), ("helium_inf", 0.5)):
+        props = api.ProblemProperties(rho=0.0, depth=depth, kappa=0.01 if physics != "water" else 0.0)
+        oprops = ro.ProblemProperties(rho=0.0, depth=depth, kappa=props.kappa)
+        prob = api.WaterBoundaryProblem(props) if physics == "water" else api.HeliumInfiniteDepthBoundaryProblem(props)
+        Z, Phi = ro.trochoid(N, h if physics == "water" else 0.05)
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, prob, compute_energies=True)
+        out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+        calc.run(T(ro.pack_state(Z, Phi)), out)
+        e = calc.energies()
+        v, dphi, aux = ro.rhs_single(Z, Phi, oprops, physics, full=True)
+        eo = ro.energies(Z, aux["Zp"], Phi.astype(np.complex128), v, oprops, physics)
+        for k in ("kinetic", "potential", "surface", "volume_flux"):
+            assert abs(e[k] - eo[k]) <= 1e-12 * max(1.0, abs(eo[k])), k
+        assert abs(e["volume"] - ro.volume(Z, aux["Zp"])) <= 1e-12
+
+
+# ---- legacy exports -------------------------------------------------------------------------------------------------
+def test_legacy_rhs_exports(api):
+    """calculateRHSFromVectors / ...Batched (L/Export.cuh:30-51): SI in, HeliumBoundaryProblem, nondimensionalised inside."""
+    N, L, depth_si = 256, 1e-6, 15e-9
+    op = ro.adimensionalize_properties(ro.ProblemProperties(L=L, rho=0.0, kappa=0.0, depth=depth_si))
+    Z, Phi = ro.trochoid(N, 0.1 * op.depth)
+    vx, vy, dphi = api.calculateRHSFromVectors(Z.real, Z.imag, Phi, L, 0.0, 0.0, depth_si)
+    v, dp = ro.rhs_single(Z, Phi, op, "helium", "cuda")
+    tol = 1e-10
+    assert rel(vx + 1j * vy, v) <= tol and rel(dphi, dp) <= tol
+    B = 3
+    xs = np.tile(Z.real, B); ys = np.concatenate([Z.imag * (1 + 0.1 * b) for b in range(B)]); ps = np.tile(Phi, B)
+    vx, vy, dphi = api.calculateRHSFromVectors(xs, ys, ps, L, 0.0, 0.0, depth_si, batchSize=B)
+    for b in range(B):
+        v, dp = ro.rhs_single(xs[b * N:(b + 1) * N] + 1j * ys[b * N:(b + 1) * N], ps[b * N:(b + 1) * N], op, "helium", "cuda")
+        assert rel(vx[b * N:(b + 1) * N] + 1j * vy[b * N:(b + 1) * N], v) <= tol
+
+
+def test_integrate_simulation_rk4_export(api):
+    """integrateSimulationRK4 (declared L/Export.cuh:69, a stub in the reference): final-state and trajectory modes."""
+    from superfluid_dynamics_b200 import _lib
+    N, L, depth_si = 128, 1e-6, 15e-9
+    sp = _lib.SimProperties(L, 0.0, 0.0, depth_si, False, 1, True)   # infinite depth film: iterative solve inside
+    op = ro.adimensionalize_properties(ro.ProblemProperties(L=L, rho=0.0, kappa=0.0, depth=depth_si, infinite_depth=True))
+    Z, Phi = ro.trochoid(N, 0.05 * op.depth)
+    init = np.hstack((Z.real, Z.imag, Phi))
+    dt_si = 1e-3 * op.base_time
+    opts = _lib.RK4SolverOptions(dt_si, 0.0, 10.2 * dt_si, False)
+    states, times = api.integrateSimulationRK4(init, sp, opts, N)
+    assert states.shape == (1, 3 * N) and len(times) == 0
+    f = lambda s: ro.rhs(s, N, 1, op, "helium", "cuda")
+    ye = ro.rk4_evolve(f, ro.pack_state(Z, Phi), 0.0, 10.2e-3, 1e-3)
+    got = states[0]
+    assert rel(got[:N] + 1j * got[N:2 * N], ye[:N]) <= 1e-9 and rel(got[2 * N:], ye[N:].real) <= 1e-9
+    opts = _lib.RK4SolverOptions(dt_si, 0.0, 10.2 * dt_si, True)
+    states, times = api.integrateSimulationRK4(init, sp, opts, N)
+    assert states.shape == (10, 3 * N) and len(times) == 10
+    assert np.allclose(states[-1], got, rtol=0, atol=1e-14)
