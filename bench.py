@@ -189,6 +189,9 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    # a non-default stream: the library launches (and graph-captures) on torch's current stream, and the CUDA events below are
+    # recorded on that same stream
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     lib = _lib.load()
     N = args.n
     props = api.ProblemProperties(rho=0.0)

@@ -145,6 +145,8 @@ RB_API int rb_rk4_run_steps(rb_stepper* st, size_t steps);                      
 RB_API rb_complex* rb_rk4_dev_state(rb_stepper* st);                             /* devY0 */
 RB_API int rb_rk4_get_state(rb_stepper* st, rb_complex* y_host);                 /* D2H of devY0 */
 RB_API double rb_rk4_current_time(rb_stepper* st);
+/* out[0] CUDA-graph launches (one per step), [1] graph captures, [2] steps redone outside the graph, [3] sweeps recorded per solve */
+RB_API int rb_rk4_stats(rb_stepper* st, double out_host[4]);
 /* trajectory logging (TrajectoryLogger<T,N>, L/TrajectoryLogger.cuh:7-73): every `every` steps into a device ring, 0 = off */
 RB_API int rb_rk4_set_logging(rb_stepper* st, size_t every, size_t capacity);
 RB_API int rb_rk4_copy_trajectory(rb_stepper* st, double** times_out, size_t* times_count,

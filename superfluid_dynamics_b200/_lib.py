@@ -74,6 +74,7 @@ SIGNATURES = {
     "rb_rk4_dev_state": (_P, [_P]),
     "rb_rk4_get_state": (c_int, [_P, _P]),
     "rb_rk4_current_time": (c_double, [_P]),
+    "rb_rk4_stats": (c_int, [_P, _D]),
     "rb_rk4_set_logging": (c_int, [_P, c_size_t, c_size_t]),
     "rb_rk4_copy_trajectory": (c_int, [_P, POINTER(_D), POINTER(c_size_t), POINTER(_P), POINTER(c_size_t)]),
     "rb_free": (None, [_P]),

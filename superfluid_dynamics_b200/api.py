@@ -238,6 +238,11 @@ class AutonomousRungeKuttaStepper:
     def currentTime(self):
         return self.lib.rb_rk4_current_time(self.handle)
 
+    def stats(self):
+        out = (ctypes.c_double * 4)()
+        check(self.lib.rb_rk4_stats(self.handle, out), "rb_rk4_stats")
+        return dict(graph_launches=int(out[0]), graph_captures=int(out[1]), fallback_steps=int(out[2]), graph_sweeps=int(out[3]))
+
     def setLogging(self, every, capacity):
         check(self.lib.rb_rk4_set_logging(self.handle, int(every), int(capacity)), "rb_rk4_set_logging")
 

@@ -58,6 +58,15 @@ struct Geometry {
     double* b;             // Re(Phi')
 };
 
+// solutions of previous steps at one RK stage, kept on the device: slot (counter % ring) is written by the current step
+struct HistoryRing {
+    double* base = nullptr;      // [ring][stride] or nullptr (no history)
+    size_t stride = 0;           // batch * N
+    int ring = 0;                // number of slots (> order so that a repeated step never reads what it overwrote)
+    int order = 0;               // extrapolation order (1..4)
+    const int* counter = nullptr;   // device: steps completed so far
+};
+
 enum SweepMode { kSweepMV = 0, kSweepVEL = 1, kSweepRAW = 2 };
 
 struct SweepArgs {
@@ -108,8 +117,9 @@ struct SweepArgs {
 void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int batch, int ncell, int physics,
                      double rhoM, double depth, int finite_image, int use_local, cudaStream_t st);
 void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st);
-void launch_guess(const double* b, const double* warm, double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl,
-                  double omega, int N, int batch, int ncell, cudaStream_t st);
+void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
+                  double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st);
+void launch_advance_counter(int* counter, cudaStream_t st);
 // spectral.cu
 void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, double2* out_phiper, int N, int batch,
                        double rho, double U, cudaStream_t st);
@@ -119,7 +129,7 @@ void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch
 void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int batch, double rho, double U, cudaStream_t st);
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st);
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
-                         double* xsum_part, int N, int batch, int ncell, cudaStream_t st);
+                         double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st);
 // dense_kernels.cu
 void launch_create_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double rho, int n, size_t batch,
                      cudaStream_t st);

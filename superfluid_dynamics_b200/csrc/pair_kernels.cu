@@ -151,20 +151,42 @@ void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int ba
 }
 
 // ------------------------------------------------------------------------------------------------
-// start of a solve: initial iterate, its per-cell sums, per-cell ||b||^2, control block reset
+// start of a solve: initial iterate, its per-cell sums, per-cell ||b||^2, control block reset.
+// The iterate is, in this order of preference,
+//   (a) the polynomial extrapolation of the solutions found at the same RK stage of the previous `order` steps
+//       (history ring in device memory, position read from a device counter so that one CUDA graph serves every step),
+//   (b) a caller-supplied warm vector,  (c) the first Neumann term omega * b.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__ b, const double* __restrict__ warm,
-                                                       double* __restrict__ x0, double* __restrict__ xsum_part,
-                                                       double* __restrict__ bnorm_part, SolveCtrl* ctrl, double omega, int N,
-                                                       int ncell) {
+                                                       HistoryRing hist, double* __restrict__ x0,
+                                                       double* __restrict__ xsum_part, double* __restrict__ bnorm_part,
+                                                       SolveCtrl* ctrl, double omega, int N, int ncell) {
     __shared__ double sred[kCell];
     int cell = blockIdx.x, bm = blockIdx.y;
     int i = cell * kCell + threadIdx.x;
     double xv = 0.0, bv = 0.0;
+    int cnt = 0, m = 0;
+    if (hist.base) {
+        cnt = *hist.counter;
+        m = cnt < hist.order ? cnt : hist.order;
+    }
     if (i < N) {
         size_t o = (size_t)bm * N + i;
         bv = b[o];
-        xv = warm ? warm[o] : omega * bv;
+        if (m > 0) {
+            // Lagrange extrapolation to the next equally spaced point: m=1: 1 | 2: 2,-1 | 3: 3,-3,1 | 4: 4,-6,4,-1
+            const double c1 = (double)m;
+            const double c2 = m == 2 ? -1.0 : (m == 3 ? -3.0 : -6.0);
+            const double c3 = m == 3 ? 1.0 : 4.0;
+            const double c4 = -1.0;
+            auto slot = [&](int back) { return hist.base + (size_t)((cnt - back) % hist.ring) * hist.stride + o; };
+            xv = c1 * *slot(1);
+            if (m >= 2) xv = fma(c2, *slot(2), xv);
+            if (m >= 3) xv = fma(c3, *slot(3), xv);
+            if (m >= 4) xv = fma(c4, *slot(4), xv);
+        } else {
+            xv = warm ? warm[o] : omega * bv;
+        }
         x0[o] = xv;
     }
     double sx = block_reduce_fixed<kCell>(xv, sred);
@@ -185,21 +207,21 @@ __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__
     }
 }
 
-void launch_guess(const double* b, const double* warm, double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl,
-                  double omega, int N, int batch, int ncell, cudaStream_t st) {
-    guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(b, warm, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell);
+void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
+                  double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st) {
+    guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
 
 // ------------------------------------------------------------------------------------------------
-// end of a solve: pick the iterate buffer the control block names, publish a (real + complex) and its per-cell sums
-// (real_to_complex of L/BaseBoundaryIntegrator.cuh:201 is folded in)
+// end of a solve: pick the iterate buffer the control block names, publish a (real + complex), its per-cell sums and,
+// when a history ring is attached, the ring slot of this step (real_to_complex of L/BaseBoundaryIntegrator.cuh:201 folded in)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __restrict__ buf0, const double* __restrict__ buf1,
                                                               const SolveCtrl* ctrl, double* __restrict__ a_out,
                                                               double2* __restrict__ a_complex, double* __restrict__ xsum_part,
-                                                              int N, int ncell) {
+                                                              HistoryRing hist, int N, int ncell) {
     __shared__ double sred[kCell];
     const double* src = (ctrl && ctrl->final_buf) ? buf1 : buf0;
     int cell = blockIdx.x, bm = blockIdx.y;
@@ -210,14 +232,23 @@ __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __res
         v = src[o];
         if (a_out) a_out[o] = v;
         if (a_complex) a_complex[o] = make_double2(v, 0.0);
+        if (hist.base) hist.base[(size_t)(*hist.counter % hist.ring) * hist.stride + o] = v;
     }
     double sx = block_reduce_fixed<kCell>(v, sred);
     if (threadIdx.x == 0 && xsum_part) xsum_part[(size_t)bm * ncell + cell] = sx;
 }
 
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
-                         double* xsum_part, int N, int batch, int ncell, cudaStream_t st) {
-    finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, ctrl, a_out, a_complex, xsum_part, N, ncell);
+                         double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st) {
+    finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, ctrl, a_out, a_complex, xsum_part, hist, N, ncell);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+__global__ void advance_counter_kernel(int* counter) { *counter += 1; }
+
+void launch_advance_counter(int* counter, cudaStream_t st) {
+    advance_counter_kernel<<<1, 1, 0, st>>>(counter);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }

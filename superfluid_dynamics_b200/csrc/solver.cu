@@ -65,7 +65,8 @@ struct rb_solver {
     int N = 0, batch = 0, ncell = 0;
     size_t BN = 0;
     rb_props props{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream every kernel of this solver is issued on
+    cudaStream_t own_stream = nullptr;   // blocking stream used when the caller hands over the legacy default stream
     int device = 0;
 
     // derived physics
@@ -87,8 +88,9 @@ struct rb_solver {
     double2 *ac = nullptr, *aprime = nullptr, *vel_upper = nullptr;
     double2 *partial = nullptr, *partial_img = nullptr;
     unsigned int *cell_tickets = nullptr, *member_tickets = nullptr;
-    SolveCtrl* ctrl = nullptr;
-    SolveCtrl* h_ctrl = nullptr;   // pinned
+    SolveCtrl* ctrl_all = nullptr;   // [4]: one control block per RK stage (standalone calls use block 0)
+    SolveCtrl* ctrl = nullptr;       // the block the next solve uses
+    SolveCtrl* h_ctrl = nullptr;     // pinned, [4]
     double* Mdense = nullptr;      // dense validation path, allocated on demand
     int* lu_info = nullptr;
     double2* scratch_state = nullptr;   // legacy host-vector exports
@@ -96,11 +98,8 @@ struct rb_solver {
     cufftHandle plan1 = 0, plan2 = 0, plan3 = 0;
     bool plans = false;
 
-    // warm start (set by the stepper): x0 = sum_i c_i h_i
-    const double* guess_h[4] = {nullptr, nullptr, nullptr, nullptr};
-    double guess_c[4] = {0, 0, 0, 0};
-    int guess_n = 0;
-    double* a_copy_out = nullptr;   // extra copy of the solution (stage history)
+    // warm start: stage-history ring attached by the stepper for the next solve (base == nullptr: none)
+    HistoryRing hist;
     bool have_prev_a = false;
 
     // capture mode: fixed sweep count, no host synchronisation inside rb_rhs
@@ -134,10 +133,11 @@ static void solver_free(rb_solver* s) {
     void* ptrs[] = {s->deriv, s->fwork, s->EG, s->P0, s->Pm, s->Pp, s->EI, s->V1diag, s->V2, s->Mdiag, s->b, s->a,
                     s->xbuf[0], s->xbuf[1], s->xsum_part[0], s->xsum_part[1], s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
-                    s->member_tickets, s->ctrl, s->Mdense, s->lu_info, s->scratch_state};
+                    s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
 
@@ -169,6 +169,8 @@ static void choose_chunking(rb_solver* s) {
     int per = s->tile * s->tiles_per_chunk;
     s->nchunks = (N + per - 1) / per;
 }
+
+static void set_stream(rb_solver* s, cudaStream_t st);
 
 static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     if (N < 2) throw std::runtime_error("rb_create: N must be >= 2");
@@ -244,25 +246,33 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     if (s->has_image) s->partial_img = dmalloc<double2>((size_t)s->nchunks * BN);
     s->cell_tickets = dmalloc<unsigned int>(pc);
     s->member_tickets = dmalloc<unsigned int>(batch);
-    s->ctrl = dmalloc<SolveCtrl>(1);
+    s->ctrl_all = dmalloc<SolveCtrl>(4);
+    s->ctrl = s->ctrl_all;
     s->lu_info = dmalloc<int>(1);
     RB_CUDA(cudaMemset(s->cell_tickets, 0, pc * sizeof(unsigned int)));
     RB_CUDA(cudaMemset(s->member_tickets, 0, batch * sizeof(unsigned int)));
-    RB_CUDA(cudaMemset(s->ctrl, 0, sizeof(SolveCtrl)));
+    RB_CUDA(cudaMemset(s->ctrl_all, 0, 4 * sizeof(SolveCtrl)));
     RB_CUDA(cudaMemset(s->a, 0, BN * sizeof(double)));
     RB_CUDA(cudaMemset(s->energies, 0, 8 * sizeof(double)));
-    RB_CUDA(cudaMallocHost(&s->h_ctrl, sizeof(SolveCtrl)));
-    std::memset(s->h_ctrl, 0, sizeof(SolveCtrl));
+    RB_CUDA(cudaMallocHost(&s->h_ctrl, 4 * sizeof(SolveCtrl)));
+    std::memset(s->h_ctrl, 0, 4 * sizeof(SolveCtrl));
 
     int n[1] = {N};
     cufft_check(cufftPlanMany(&s->plan1, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, batch), "cufftPlanMany(B)");
     cufft_check(cufftPlanMany(&s->plan2, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 2 * batch), "cufftPlanMany(2B)");
     cufft_check(cufftPlanMany(&s->plan3, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 3 * batch), "cufftPlanMany(3B)");
     s->plans = true;
+    set_stream(s, nullptr);
     return up.release();
 }
 
 static void set_stream(rb_solver* s, cudaStream_t st) {
+    // The legacy default stream cannot be captured into a CUDA graph.  A blocking stream created here is ordered against the
+    // legacy stream in both directions (implicit synchronisation), so callers that work on stream 0 see the same semantics.
+    if (st == nullptr || st == cudaStreamLegacy) {
+        if (!s->own_stream) RB_CUDA(cudaStreamCreate(&s->own_stream));
+        st = s->own_stream;
+    }
     s->stream = st;
     cufft_check(cufftSetStream(s->plan1, st), "cufftSetStream");
     cufft_check(cufftSetStream(s->plan2, st), "cufftSetStream");
@@ -374,9 +384,7 @@ static void solve(rb_solver* s, const double2* Z) {
             RB_CUDA(cudaMemcpyAsync(s->xbuf[0] + o, s->b + o, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
             launch_lu_solve(s->Mdense, s->xbuf[0] + o, N, s->lu_info, st);
         }
-        launch_finish_solve(s->xbuf[0], s->xbuf[0], nullptr, s->a, s->ac, s->xsum_a, s->N, s->batch, s->ncell, st);
-        if (s->a_copy_out)
-            RB_CUDA(cudaMemcpyAsync(s->a_copy_out, s->a, s->BN * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        launch_finish_solve(s->xbuf[0], s->xbuf[0], nullptr, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
         s->last_iters = 0;
         s->last_converged = 1;
         s->last_rel = 0;
@@ -385,17 +393,14 @@ static void solve(rb_solver* s, const double2* Z) {
 
     // matrix-free Richardson: x <- x + omega (b - M x), error contracts by rho(I - omega M) per sweep
     const double* warm = nullptr;
-    if (s->props.guess_mode == RB_GUESS_WARM && s->guess_n == 0 && s->have_prev_a) warm = s->a;
-    if (s->guess_n > 0) {
-        // stage-history extrapolation prepared by the stepper: combine into xbuf[1], then use it as the warm vector
-        // (the combine is a tiny elementwise kernel; reuse the stage-update kernel on the real arrays viewed as complex pairs
-        //  is not possible for odd sizes, so a dedicated path lives in launch_guess via warm)
-        warm = s->guess_h[0];
-    }
-    launch_guess(s->b, warm, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
+    if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
+    launch_guess(s->b, warm, s->hist, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell,
+                 st);
     SweepArgs base = base_args(s, Z);
     int launched = 0;
     if (s->fixed_sweeps > 0) {
+        // capture mode: a fixed number of sweeps that skip themselves once the control block says done; the caller
+        // inspects the control block after the whole step
         for (; launched < s->fixed_sweeps; ++launched) launch_mv(s, base, launched, 1);
     } else {
         int group = s->kpred > 0 ? s->kpred : 8;
@@ -408,8 +413,7 @@ static void solve(rb_solver* s, const double2* Z) {
         s->kpred = s->last_iters;
         account_solve(s);
     }
-    launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, s->ac, s->xsum_a, s->N, s->batch, s->ncell, st);
-    if (s->a_copy_out) RB_CUDA(cudaMemcpyAsync(s->a_copy_out, s->a, s->BN * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
     s->have_prev_a = true;
 }
 
@@ -468,16 +472,29 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
 // ------------------------------------------------------------------------------------------------
 // the RK4 stepper
 // ------------------------------------------------------------------------------------------------
+constexpr int kHistRing = 5;   // > max order (4): a repeated step never reads a slot it has already overwritten
+
 struct rb_stepper {
     rb_solver* s = nullptr;
     double dt = 1e-2;
     double t = 0.0;
     double2* y0 = nullptr;
     bool owns_y0 = false;
-    double2 *k[4] = {nullptr, nullptr, nullptr, nullptr}, *ytmp = nullptr;
-    // stage history of the vortex-sheet strengths for the warm start: hist[stage][slot]
-    double* hist[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-    int hist_count = 0;
+    double2 *k[4] = {nullptr, nullptr, nullptr, nullptr}, *ytmp = nullptr, *ybackup = nullptr;
+    // stage history of the vortex-sheet strengths for the warm start: hist[stage] = [kHistRing][BN]
+    double* hist[4] = {nullptr, nullptr, nullptr, nullptr};
+    int* d_counter = nullptr;     // device: completed steps since the history was reset
+    int h_counter = 0;            // host mirror
+    int order = 4;                // extrapolation order (RB_GUESS_ORDER)
+    // CUDA graph of one step (fixed number of self-skipping sweeps per solve)
+    bool use_graph = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_sweeps = 0;
+    double graph_dt = 0;
+    double2* graph_y0 = nullptr;
+    int graph_hits_below = 0;     // consecutive steps that needed far fewer sweeps than captured
+    long long graph_launches = 0, graph_captures = 0, fallback_steps = 0;
+    cudaEvent_t ev = nullptr;
     // logging
     size_t log_every = 0, log_capacity = 0, log_count = 0, step_index = 0;
     double2* log_states = nullptr;
@@ -486,31 +503,42 @@ struct rb_stepper {
 
 static void stepper_free(rb_stepper* st) {
     if (!st) return;
+    if (st->graph_exec) cudaGraphExecDestroy(st->graph_exec);
+    if (st->ev) cudaEventDestroy(st->ev);
     if (st->owns_y0 && st->y0) cudaFree(st->y0);
     for (auto p : st->k)
         if (p) cudaFree(p);
     if (st->ytmp) cudaFree(st->ytmp);
-    for (auto& hs : st->hist)
-        for (auto p : hs)
-            if (p) cudaFree(p);
+    if (st->ybackup) cudaFree(st->ybackup);
+    for (auto p : st->hist)
+        if (p) cudaFree(p);
+    if (st->d_counter) cudaFree(st->d_counter);
     if (st->log_states) cudaFree(st->log_states);
     delete st;
 }
 
-static void stepper_step(rb_stepper* st) {
+static void stepper_reset_history(rb_stepper* st) {
+    st->h_counter = 0;
+    RB_CUDA(cudaMemsetAsync(st->d_counter, 0, sizeof(int), st->s->stream));
+}
+
+// the kernel sequence of one RK4 step (L/AutonomousRungeKuttaStepper.cuh:124-307); identical whether it is launched
+// directly or recorded into a graph.  fixed_sweeps > 0: no host synchronisation anywhere inside.
+static void issue_step(rb_stepper* st, int fixed_sweeps) {
     rb_solver* s = st->s;
     const size_t n2 = 2 * s->BN;
     cudaStream_t cs = s->stream;
     const double h = st->dt;
     const bool warm = s->props.guess_mode == RB_GUESS_WARM && s->matrix_free_solve;
+    s->fixed_sweeps = fixed_sweeps;
     auto stage = [&](int i, const double2* y) {
+        s->ctrl = s->ctrl_all + i;
         if (warm) {
-            // previous step's solution at the same stage is an O(dt) accurate start; alternate two slots so that the
-            // solver never reads the buffer it is writing
-            int cur = st->hist_count & 1;
-            s->guess_n = st->hist_count > 0 ? 1 : 0;
-            s->guess_h[0] = st->hist[i][cur ^ 1];
-            s->a_copy_out = st->hist[i][cur];
+            s->hist.base = st->hist[i];
+            s->hist.stride = s->BN;
+            s->hist.ring = kHistRing;
+            s->hist.order = st->order;
+            s->hist.counter = st->d_counter;
         }
         rhs(s, y, st->k[i]);
     };
@@ -522,16 +550,123 @@ static void stepper_step(rb_stepper* st) {
     launch_stage_update(st->ytmp, st->y0, st->k[2], h, n2, cs);
     stage(3, st->ytmp);
     launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n2, cs);
-    if (warm) st->hist_count++;
-    s->guess_n = 0;
-    s->a_copy_out = nullptr;
-    st->t += h;
+    if (warm) launch_advance_counter(st->d_counter, cs);
+    s->hist = HistoryRing();
+    s->ctrl = s->ctrl_all;
+    s->fixed_sweeps = 0;
+}
+
+static void capture_graph(rb_stepper* st, int sweeps) {
+    rb_solver* s = st->s;
+    if (st->graph_exec) {
+        cudaGraphExecDestroy(st->graph_exec);
+        st->graph_exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    const unsigned long long launches_before = rb::g_launch_count;
+    RB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        RB_CUDA(cudaMemcpyAsync(st->ybackup, st->y0, 2 * s->BN * sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+        issue_step(st, sweeps);
+        RB_CUDA(cudaMemcpyAsync(s->h_ctrl, s->ctrl_all, 4 * sizeof(SolveCtrl), cudaMemcpyDeviceToHost, s->stream));
+    } catch (...) {
+        cudaStreamEndCapture(s->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    RB_CUDA(cudaStreamEndCapture(s->stream, &graph));
+    rb::g_launch_count = launches_before;   // recorded, not launched
+    RB_CUDA(cudaGraphInstantiate(&st->graph_exec, graph, 0));
+    RB_CUDA(cudaGraphDestroy(graph));
+    st->graph_sweeps = sweeps;
+    st->graph_dt = st->dt;
+    st->graph_y0 = st->y0;
+    st->graph_hits_below = 0;
+    st->graph_captures++;
+}
+
+static size_t kernels_per_step(rb_solver* s, int sweeps) {
+    // geometry path 4 + guess + sweeps + finish + (multiply, scale) + VEL + optional rhs_phi / energies, per stage; 3 stage updates,
+    // final update, counter
+    size_t per_stage = 4 + 1 + (size_t)sweeps + 1 + 2 + 1 + (s->rhs_phi_kind ? 0 : 1) + (s->props.compute_energies ? 1 : 0);
+    return 4 * per_stage + 5;
+}
+
+static void after_step(rb_stepper* st) {
+    st->t += st->dt;
     st->step_index++;
+    rb_solver* s = st->s;
     if (st->log_every && st->log_states && (st->step_index % st->log_every) == 0 && st->log_count < st->log_capacity) {
-        RB_CUDA(cudaMemcpyAsync(st->log_states + st->log_count * n2, st->y0, n2 * sizeof(double2), cudaMemcpyDeviceToDevice, cs));
+        RB_CUDA(cudaMemcpyAsync(st->log_states + st->log_count * 2 * s->BN, st->y0, 2 * s->BN * sizeof(double2),
+                                cudaMemcpyDeviceToDevice, s->stream));
         st->log_times.push_back(st->t);
         st->log_count++;
     }
+}
+
+static void stepper_step(rb_stepper* st) {
+    rb_solver* s = st->s;
+    const bool graphable = st->use_graph && s->matrix_free_solve;
+    if (!graphable) {
+        issue_step(st, 0);
+        if (s->props.guess_mode == RB_GUESS_WARM && s->matrix_free_solve) st->h_counter++;
+        after_step(st);
+        return;
+    }
+    if (!st->graph_exec || st->graph_dt != st->dt || st->graph_y0 != st->y0) {
+        int sweeps = st->graph_sweeps > 0 ? st->graph_sweeps : std::min(s->props.max_iterations, 24);
+        capture_graph(st, sweeps);
+    }
+    RB_CUDA(cudaGraphLaunch(st->graph_exec, s->stream));
+    rb::count_launch((int)kernels_per_step(s, st->graph_sweeps));
+    st->graph_launches++;
+    RB_CUDA(cudaEventRecord(st->ev, s->stream));
+    RB_CUDA(cudaEventSynchronize(st->ev));
+    int worst = 0;
+    bool all_done = true;
+    for (int i = 0; i < 4; ++i) {
+        const SolveCtrl& c = s->h_ctrl[i];
+        all_done = all_done && c.done;
+        worst = std::max(worst, c.iters);
+    }
+    if (!all_done) {
+        // some solve ran out of recorded sweeps: roll the step back and redo it with the synchronising loop
+        RB_CUDA(cudaMemcpyAsync(st->y0, st->ybackup, 2 * s->BN * sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+        if (s->props.guess_mode == RB_GUESS_WARM) {
+            // the counter was advanced by the failed graph: put it back (slots written by the failed step are rewritten)
+            RB_CUDA(cudaMemcpyAsync(st->d_counter, &st->h_counter, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+            RB_CUDA(cudaStreamSynchronize(s->stream));
+        }
+        issue_step(st, 0);
+        st->fallback_steps++;
+        worst = std::max(worst, s->kpred);
+        int sweeps = std::min(s->props.max_iterations, worst + 4);
+        st->graph_sweeps = sweeps;
+        if (st->graph_exec) {
+            cudaGraphExecDestroy(st->graph_exec);
+            st->graph_exec = nullptr;
+        }
+    } else {
+        for (int i = 0; i < 4; ++i) {
+            s->sum_iters += s->h_ctrl[i].iters;
+            s->num_solves++;
+        }
+        s->last_iters = s->h_ctrl[3].iters;
+        s->last_converged = s->h_ctrl[3].converged;
+        s->last_rel = std::sqrt(std::max(0.0, s->h_ctrl[3].rel2));
+        // shrink the recorded sweep count when it has been clearly too large for a while (each skipped sweep costs a launch)
+        if (st->graph_sweeps - worst >= 4) {
+            if (++st->graph_hits_below >= 8) {
+                st->graph_sweeps = worst + 2;
+                cudaGraphExecDestroy(st->graph_exec);
+                st->graph_exec = nullptr;
+            }
+        } else {
+            st->graph_hits_below = 0;
+        }
+    }
+    if (s->props.guess_mode == RB_GUESS_WARM) st->h_counter++;
+    after_step(st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -728,7 +863,7 @@ int rb_cotangent_sum(rb_solver* s, const rb_complex* Z_dev, const double* x_dev,
     // geometry from the solver's current Zp/Zpp (diagonal terms are not used by the raw sum)
     Geometry g = make_geometry(s, Z);
     launch_geometry(g, nullptr, s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, 0, s->use_local, s->stream);
-    launch_finish_solve(x_dev, x_dev, nullptr, nullptr, nullptr, s->xsum_a, s->N, s->batch, s->ncell, s->stream);
+    launch_finish_solve(x_dev, x_dev, nullptr, nullptr, nullptr, s->xsum_a, HistoryRing(), s->N, s->batch, s->ncell, s->stream);
     SweepArgs a = base_args(s, Z);
     a.x = x_dev;
     a.xsum_part = s->xsum_a;
@@ -748,11 +883,16 @@ rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
         const size_t n2 = 2 * s->BN;
         for (auto& p : st->k) p = dmalloc<double2>(n2);
         st->ytmp = dmalloc<double2>(n2);
-        for (auto& hs : st->hist)
-            for (auto& p : hs) {
-                p = dmalloc<double>(s->BN);
-                RB_CUDA(cudaMemset(p, 0, s->BN * sizeof(double)));
-            }
+        st->ybackup = dmalloc<double2>(n2);
+        for (auto& p : st->hist) {
+            p = dmalloc<double>((size_t)kHistRing * s->BN);
+            RB_CUDA(cudaMemset(p, 0, (size_t)kHistRing * s->BN * sizeof(double)));
+        }
+        st->d_counter = dmalloc<int>(1);
+        RB_CUDA(cudaMemset(st->d_counter, 0, sizeof(int)));
+        RB_CUDA(cudaEventCreateWithFlags(&st->ev, cudaEventDisableTiming));
+        st->order = std::max(1, std::min(4, env_int("RB_GUESS_ORDER", 4)));
+        st->use_graph = env_int("RB_NO_GRAPH", 0) == 0;
         return up.release();
     } catch (const std::exception& e) {
         fail(e);
@@ -772,7 +912,7 @@ int rb_rk4_destroy(rb_stepper* st) {
 int rb_rk4_set_time_step(rb_stepper* st, double tstep) {
     RB_TRY
     st->dt = tstep;
-    st->hist_count = 0;
+    stepper_reset_history(st);
     RB_CATCH
 }
 
@@ -789,7 +929,7 @@ int rb_rk4_initialize(rb_stepper* st, rb_complex* y0, int on_device) {
         RB_CUDA(cudaMemcpyAsync(st->y0, y0, n2 * sizeof(double2), cudaMemcpyHostToDevice, st->s->stream));
         RB_CUDA(cudaStreamSynchronize(st->s->stream));
     }
-    st->hist_count = 0;
+    stepper_reset_history(st);
     st->t = 0.0;
     st->step_index = 0;
     st->log_count = 0;
@@ -823,6 +963,14 @@ int rb_rk4_evolve(rb_stepper* st, double t0, double t1, size_t* steps_out) {
 }
 
 rb_complex* rb_rk4_dev_state(rb_stepper* st) { return (rb_complex*)st->y0; }
+
+int rb_rk4_stats(rb_stepper* st, double out_host[4]) {
+    out_host[0] = (double)st->graph_launches;
+    out_host[1] = (double)st->graph_captures;
+    out_host[2] = (double)st->fallback_steps;
+    out_host[3] = (double)st->graph_sweeps;
+    return 0;
+}
 double rb_rk4_current_time(rb_stepper* st) { return st->t; }
 
 int rb_rk4_get_state(rb_stepper* st, rb_complex* y_host) {
@@ -937,7 +1085,8 @@ int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* m
     Geometry g = make_geometry(s, Z);
     launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
                     s->use_local, st);
-    launch_guess(s->b, nullptr, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
+    launch_guess(s->b, nullptr, HistoryRing(), s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch,
+                 s->ncell, st);
     SweepArgs base = base_args(s, Z);
     base.max_iters = 1 << 30;
     base.tol2 = 0.0;

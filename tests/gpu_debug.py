@@ -133,7 +133,31 @@ def rk4():
             y = stp.getState()
             dt = time.time() - t0
             print("rk4", N, h, steps, guess, "Z", rel(y[:N], ye[:N]), "Phi", rel(y[N:], ye[N:]), f"{steps / dt:.1f} steps/s",
-                  calc.solve_stats())
+                  calc.solve_stats(), stp.stats())
+
+
+def steprate():
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    for N, h, dt, steps in ((256, 0.3, 1e-3, 200), (1024, 0.4, 1e-3, 200), (4096, 0.4, 1e-3, 200), (16384, 0.4, 2e-4, 40),
+                            (65536, 0.4, 1e-4, 20)):
+        for order in (1, 2, 3, 4):
+            os.environ["RB_GUESS_ORDER"] = str(order)
+            props = api.ProblemProperties(rho=0.0)
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+            Z, Phi = ro.trochoid(N, h)
+            st = T(ro.pack_state(Z, Phi))
+            stp.initialize(st, True)
+            stp.runSteps(10)
+            torch.cuda.synchronize()
+            s0 = calc.solve_stats()
+            t0 = time.time()
+            stp.runSteps(steps)
+            torch.cuda.synchronize()
+            el = time.time() - t0
+            s1 = calc.solve_stats()
+            its = (s1["total_iterations"] - s0["total_iterations"]) / max(1, s1["total_solves"] - s0["total_solves"])
+            print(f"steprate N={N} order={order}: {steps / el:.1f} steps/s, {its:.2f} sweeps/solve, {stp.stats()}", flush=True)
 
 
 def speed():
