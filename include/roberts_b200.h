@@ -157,10 +157,15 @@ RB_API int rb_rk4_stage_update(rb_complex* y_out, const rb_complex* y0, const rb
 RB_API int rb_rk4_final_update(rb_complex* y0, const rb_complex* k1, const rb_complex* k2, const rb_complex* k3,
                                const rb_complex* k4, double h, size_t n, void* stream);
 
-/* ---- multi-GPU: row blocks of the interaction operators sharded over ranks (new; the reference is single-GPU) ---- */
-#define RB_UNIQUE_ID_BYTES 128
-RB_API int rb_comm_unique_id(char id_out[RB_UNIQUE_ID_BYTES]);                   /* rank 0; ship to the others out of band */
-RB_API int rb_comm_init(rb_solver* s, int rank, int nranks, const char id[RB_UNIQUE_ID_BYTES]);
+/* ---- multi-GPU (new; the reference is single-GPU, L/utilities.cuh:20): contiguous blocks of 256-row cells of every O(N^2)
+ *      sweep are owned by one rank each; all ranks keep the full state and exchange result rows by peer stores over NVLink into
+ *      a per-rank arena mapped with CUDA IPC.  One process per GPU of one node; ship the handles with any out-of-band channel
+ *      (torch.distributed all_gather in superfluid_dynamics_b200/api.py). ---- */
+RB_API int rb_comm_handle_bytes(void);                                           /* size of one exported handle (64) */
+RB_API int rb_comm_export(rb_solver* s, char* handle_out);                       /* this rank's arena handle */
+RB_API int rb_comm_init(rb_solver* s, int rank, int nranks, const char* handles); /* handles: nranks x rb_comm_handle_bytes() */
+RB_API int rb_comm_row_range(int N, int rank, int nranks, int out_rows[2]);      /* host-only: rows [out[0], out[1]) owned by rank */
+RB_API int rb_comm_error(rb_solver* s);                                          /* 1 if a peer wait timed out */
 RB_API int rb_comm_destroy(rb_solver* s);
 
 /* ---- measurement helpers ---- */

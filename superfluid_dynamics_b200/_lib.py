@@ -80,8 +80,11 @@ SIGNATURES = {
     "rb_free": (None, [_P]),
     "rb_rk4_stage_update": (c_int, [_P, _P, _P, c_double, c_size_t, _P]),
     "rb_rk4_final_update": (c_int, [_P, _P, _P, _P, _P, c_double, c_size_t, _P]),
-    "rb_comm_unique_id": (c_int, [c_char_p]),
+    "rb_comm_handle_bytes": (c_int, []),
+    "rb_comm_export": (c_int, [_P, c_char_p]),
     "rb_comm_init": (c_int, [_P, c_int, c_int, c_char_p]),
+    "rb_comm_row_range": (c_int, [c_int, c_int, c_int, POINTER(c_int)]),
+    "rb_comm_error": (c_int, [_P]),
     "rb_comm_destroy": (c_int, [_P]),
     "rb_launch_count": (ctypes.c_ulonglong, []),
     "rb_measure_fp64_peak": (c_int, [_D, _P]),

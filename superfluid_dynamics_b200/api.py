@@ -182,10 +182,43 @@ class BaseBoundaryIntegralCalculator:
         check(self.lib.rb_cotangent_sum(self.handle, _ptr(Z), _ptr(x), _ptr(S)), "rb_cotangent_sum")
         return S
 
+    # --- multi-GPU: row cells sharded over the ranks of a torch.distributed process group (one process per GPU, one node) ---
+    def initComm(self, rank=None, world=None, group=None):
+        import torch.distributed as dist
+        rank = dist.get_rank(group) if rank is None else rank
+        world = dist.get_world_size(group) if world is None else world
+        nb = self.lib.rb_comm_handle_bytes()
+        mine = ctypes.create_string_buffer(nb)
+        check(self.lib.rb_comm_export(self.handle, mine), "rb_comm_export")
+        blobs = exchange_handles(mine.raw, group)
+        assert len(blobs) == world and all(len(b) == nb for b in blobs)
+        check(self.lib.rb_comm_init(self.handle, int(rank), int(world), b"".join(blobs)), "rb_comm_init")
+        dist.barrier(group)
+        self.rank, self.world = rank, world
+
+    def commError(self):
+        return self.lib.rb_comm_error(self.handle)
+
     def benchSweep(self, state, reps=10):
         ms, pairs = ctypes.c_float(), ctypes.c_double()
         check(self.lib.rb_bench_sweep(self.handle, _ptr(state), reps, ctypes.byref(ms), ctypes.byref(pairs)), "rb_bench_sweep")
         return ms.value, pairs.value
+
+
+def exchange_handles(blob: bytes, group=None):
+    """All-gather one opaque handle per rank (plumbing only: torch.distributed, any backend)."""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, blob, group=group)
+    return out
+
+
+def comm_row_range(N, rank, nranks):
+    """Rows [lo, hi) of the interaction operators owned by `rank` (whole 256-row cells, contiguous)."""
+    out = (ctypes.c_int * 2)()
+    if _lib.load().rb_comm_row_range(int(N), int(rank), int(nranks), out) != 0:
+        raise ValueError("bad rank / nranks")
+    return out[0], out[1]
 
 
 class AutonomousRungeKuttaStepper:

@@ -67,6 +67,21 @@ struct HistoryRing {
     const int* counter = nullptr;   // device: steps completed so far
 };
 
+// multi-GPU view: every rank owns one "arena" allocation with the same layout; arenas of the peers are mapped into this
+// process (CUDA IPC), so a result row is published by storing it at the same offset in every arena over NVLink.
+constexpr int kMaxRanks = 8;
+struct CommView {
+    int nranks = 1;                      // 1: single GPU, plain local stores
+    int rank = 0;
+    char* my_base = nullptr;             // this rank's arena
+    char* peer_base[kMaxRanks] = {};     // every rank's arena as mapped here (peer_base[rank] == my_base)
+    size_t off_rn = 0;                   // double rn[2][kMaxRanks]: per-rank residual sums, double-buffered by iterate parity
+    size_t off_flags = 0;                // unsigned long long flags[kMaxRanks]: epoch of the last signal received from each rank
+    unsigned long long* signal_epoch = nullptr;   // local counters (device memory)
+    unsigned long long* wait_epoch = nullptr;
+    int* error_flag = nullptr;           // set when a wait timed out
+};
+
 enum SweepMode { kSweepMV = 0, kSweepVEL = 1, kSweepRAW = 2 };
 
 struct SweepArgs {
@@ -110,6 +125,7 @@ struct SweepArgs {
     double2* vel_upper;              // upper-fluid velocities
     double2* dphi;                   // dPhi/dt + 0 i -> rhs[BN .. 2BN)  (nullptr: separate kernel)
     double2* raw_out;                // RAW: S_k = sum_{j!=k} cot((z_k - z_j)/2) x_j
+    CommView comm;                   // row sharding over GPUs (nranks == 1: off)
 };
 
 // ---- launch wrappers (each defined in the .cu named in the comment) -----------------------
@@ -120,6 +136,8 @@ void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st);
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st);
 void launch_advance_counter(int* counter, cudaStream_t st);
+void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, const double* bnorm_part, int ncell,
+                      double tol2, int max_iters, cudaStream_t st);
 // spectral.cu
 void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, double2* out_phiper, int N, int batch,
                        double rho, double U, cudaStream_t st);

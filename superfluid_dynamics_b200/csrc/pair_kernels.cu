@@ -63,6 +63,28 @@ __device__ double block_reduce_fixed(double v, double* sred) {
     return r;
 }
 
+// store a result at the same arena offset on every rank (single GPU: a plain store)
+template <typename T>
+__device__ __forceinline__ void mirror_store(const CommView& c, T* local_ptr, T v) {
+    if (c.nranks <= 1) {
+        *local_ptr = v;
+        return;
+    }
+    const size_t off = (size_t)(reinterpret_cast<char*>(local_ptr) - c.my_base);
+    for (int r = 0; r < c.nranks; ++r) *reinterpret_cast<T*>(c.peer_base[r] + off) = v;
+}
+
+// tell every rank that this rank's rows of the current exchange are in place (call after a system-scope fence)
+__device__ __forceinline__ void comm_signal(const CommView& c) {
+    const unsigned long long e = *c.signal_epoch + 1ull;
+    *c.signal_epoch = e;
+    for (int r = 0; r < c.nranks; ++r) {
+        volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(c.peer_base[r] + c.off_flags) + c.rank;
+        *f = e;
+    }
+    __threadfence_system();
+}
+
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -427,17 +449,19 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                 double Mx = fma(a.g.Mdiag[o], xk, Kx);
                 double res = a.g.b[o] - Mx;
                 double xn = fma(a.omega, res, xk);
-                a.x_out[o] = xn;
+                mirror_store(a.comm, a.x_out + o, xn);
                 sx += xn;
                 sr += res * res;
             }
         }
         sx = block_reduce_fixed<kSweepThreads>(sx, sred);
         sr = block_reduce_fixed<kSweepThreads>(sr, sred);
+        if (a.comm.nranks > 1) __threadfence_system();   // this CTA's remote row stores before its ticket
+        __syncthreads();
         if (t == 0) {
-            a.xsum_part_out[(size_t)bm * a.ncell + cellK] = sx;
+            mirror_store(a.comm, a.xsum_part_out + (size_t)bm * a.ncell + cellK, sx);
             a.rnorm_part[(size_t)bm * a.ncell + cellK] = sr;
-            __threadfence();
+            if (a.comm.nranks > 1) __threadfence_system(); else __threadfence();
             s_ticket = atomicAdd(a.member_tickets + bm, 1u);
         }
         __syncthreads();
@@ -445,6 +469,18 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
         // ---- level 2: last row cell of this batch member ---------------------------------------
         __threadfence();
         double rn = block_sum_fixed<kSweepThreads>(a.rnorm_part + (size_t)bm * a.ncell + a.row_cell0, a.row_cells, sred);
+        if (a.comm.nranks > 1) {
+            // row-sharded: publish this rank's residual sum and signal; the decision is taken by comm_wait_kernel on every
+            // rank from the same numbers in the same order
+            if (t == 0) {
+                a.member_tickets[bm] = 0u;
+                double* slot = reinterpret_cast<double*>(a.comm.my_base + a.comm.off_rn) + a.out_buf * kMaxRanks + a.comm.rank;
+                mirror_store(a.comm, slot, rn);
+                __threadfence_system();
+                comm_signal(a.comm);
+            }
+            return;
+        }
         double bn = block_sum_fixed<kSweepThreads>(a.bnorm_part + (size_t)bm * a.ncell, a.ncell, sred);
         if (t == 0) {
             a.member_tickets[bm] = 0u;
@@ -496,7 +532,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                     wr -= inv4pi * (sumx + 2.0 * TI[r].x);
                     wi -= inv4pi * (2.0 * TI[r].y);
                 }
-                a.vel_lower[o] = make_double2(wr, -wi);            // conj, L/WaterVelocities.cuh:241
+                mirror_store(a.comm, a.vel_lower + o, make_double2(wr, -wi));   // conj, L/WaterVelocities.cuh:241
                 double2 az = cdiv(make_double2(ak, 0.0), zp);       // upper fluid: diagonal -1/(2Zp) instead of +1/(2Zp)
                 a.vel_upper[o] = make_double2(wr - az.x, -(wi - az.y));
                 if (a.dphi) {
@@ -509,8 +545,20 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                         double vdw = a.depth / 3.0;                // L/createM.cuh:113-115
                         d = vdw * pow(1.0 + y / a.depth, -3.0) - vdw + kin;
                     }
-                    a.dphi[o] = make_double2(d, 0.0);
+                    mirror_store(a.comm, a.dphi + o, make_double2(d, 0.0));
                 }
+            }
+        }
+        if (a.comm.nranks > 1) {
+            // the last row cell of this rank signals that its rows of k are in every arena
+            __threadfence_system();
+            __syncthreads();
+            if (t == 0) s_ticket = atomicAdd(a.member_tickets + bm, 1u);
+            __syncthreads();
+            if (s_ticket == (unsigned)(a.row_cells - 1) && t == 0) {
+                a.member_tickets[bm] = 0u;
+                __threadfence_system();
+                comm_signal(a.comm);
             }
         }
         return;
@@ -526,6 +574,73 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
             a.raw_out[boff + krow[r]] = make_double2(-Ai, Ar);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-sharded runs: wait until every rank has signalled the current exchange; for a solver sweep also take the convergence
+// decision (identical on every rank: same residual sums, same order)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ctrl, int decide, int parity,
+                                                        const double* __restrict__ bnorm_part, int ncell, double tol2,
+                                                        int max_iters) {
+    const int lane = threadIdx.x;
+    if (decide && *reinterpret_cast<volatile int*>(&ctrl->done)) return;   // the sweep before skipped itself: nothing to wait for
+    const unsigned long long expected = *c.wait_epoch + 1ull;
+    bool timed_out = false;
+    if (lane < c.nranks) {
+        volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(c.my_base + c.off_flags) + lane;
+        const long long t0 = clock64();
+        while (*f < expected) {
+            if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer died; give up instead of hanging the device
+                timed_out = true;
+                break;
+            }
+        }
+    }
+    timed_out = __any_sync(0xffffffffu, timed_out);
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *c.wait_epoch = expected;
+    if (timed_out) {
+        if (lane == 0) {
+            *c.error_flag = 1;
+            ctrl->done = 1;
+            ctrl->converged = 0;
+        }
+        return;
+    }
+    if (!decide) return;
+    // ||b||^2 over all cells: lanes stride, then a fixed-order combine
+    double bl = 0.0;
+    for (int i = lane; i < ncell; i += 32) bl += __ldcg(bnorm_part + i);
+    double bn = 0.0;
+    for (int l = 0; l < 32; ++l) bn += __shfl_sync(0xffffffffu, bl, l);
+    if (lane == 0) {
+        volatile double* rnp = reinterpret_cast<double*>(c.my_base + c.off_rn) + parity * kMaxRanks;
+        double rn = 0.0;
+        for (int r = 0; r < c.nranks; ++r) rn += rnp[r];
+        double worst = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
+        if (!(worst == worst)) worst = 1e300;
+        int iters = ctrl->iters + 1;
+        double prev = ctrl->prev_rel2;
+        bool conv = worst <= tol2;
+        bool stagnated = iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
+        ctrl->iters = iters;
+        ctrl->rel2 = worst;
+        ctrl->prev_rel2 = worst;
+        ctrl->final_buf = parity;
+        if (conv || stagnated || iters >= max_iters) {
+            ctrl->converged = (conv || stagnated) ? 1 : 0;
+            ctrl->done = 1;
+        }
+    }
+}
+
+void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, const double* bnorm_part, int ncell,
+                      double tol2, int max_iters, cudaStream_t st) {
+    comm_wait_kernel<<<1, 32, 0, st>>>(c, ctrl, decide, parity, bnorm_part, ncell, tol2, max_iters);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
 }
 
 void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st) {

@@ -91,6 +91,15 @@ struct rb_solver {
     SolveCtrl* ctrl_all = nullptr;   // [4]: one control block per RK stage (standalone calls use block 0)
     SolveCtrl* ctrl = nullptr;       // the block the next solve uses
     SolveCtrl* h_ctrl = nullptr;     // pinned, [4]
+    // arena: one allocation holding everything a peer rank may write (iterates, their per-cell sums, residual slots, flags,
+    // the four RK stage slopes); identical layout on every rank
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    double2* kbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+    CommView comm;
+    void* peer_mapped[kMaxRanks] = {};
+    unsigned long long* epochs = nullptr;   // [2] signal / wait counters + error flag
+    int row_cell0 = 0, row_cells = 0;
     double* Mdense = nullptr;      // dense validation path, allocated on demand
     int* lu_info = nullptr;
     double2* scratch_state = nullptr;   // legacy host-vector exports
@@ -130,8 +139,10 @@ static void solver_free(rb_solver* s) {
         cufftDestroy(s->plan2);
         cufftDestroy(s->plan3);
     }
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (s->peer_mapped[r]) cudaIpcCloseMemHandle(s->peer_mapped[r]);
     void* ptrs[] = {s->deriv, s->fwork, s->EG, s->P0, s->Pm, s->Pp, s->EI, s->V1diag, s->V2, s->Mdiag, s->b, s->a,
-                    s->xbuf[0], s->xbuf[1], s->xsum_part[0], s->xsum_part[1], s->xsum_a, s->rnorm_part, s->bnorm_part,
+                    s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
                     s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state};
     for (void* p : ptrs)
@@ -144,7 +155,7 @@ static void solver_free(rb_solver* s) {
 static void choose_chunking(rb_solver* s) {
     const int N = s->N;
     const int target = env_int("RB_TARGET_CTAS", 148 * 8);
-    long rows = (long)s->ncell * s->batch;
+    long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
     int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
     int max_chunks = std::max(1, (N + 63) / 64);
     wanted = std::min(wanted, max_chunks);
@@ -231,9 +242,33 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     s->b = dmalloc<double>(BN);
     s->a = dmalloc<double>(BN);
     size_t pc = (size_t)s->ncell * batch;
-    for (int i = 0; i < 2; ++i) {
-        s->xbuf[i] = dmalloc<double>(BN);
-        s->xsum_part[i] = dmalloc<double>(pc);
+    {
+        auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
+        size_t off = 0, ox[2], oxs[2], ok[4];
+        for (int i = 0; i < 2; ++i) { ox[i] = off; off += up256(BN * sizeof(double)); }
+        for (int i = 0; i < 2; ++i) { oxs[i] = off; off += up256(pc * sizeof(double)); }
+        s->comm.off_rn = off; off += up256(2 * kMaxRanks * sizeof(double));
+        s->comm.off_flags = off; off += up256(kMaxRanks * sizeof(unsigned long long));
+        for (int i = 0; i < 4; ++i) { ok[i] = off; off += up256(2 * BN * sizeof(double2)); }
+        s->arena_bytes = off;
+        s->arena = dmalloc<char>(off);
+        RB_CUDA(cudaMemset(s->arena, 0, off));
+        for (int i = 0; i < 2; ++i) {
+            s->xbuf[i] = reinterpret_cast<double*>(s->arena + ox[i]);
+            s->xsum_part[i] = reinterpret_cast<double*>(s->arena + oxs[i]);
+        }
+        for (int i = 0; i < 4; ++i) s->kbuf[i] = reinterpret_cast<double2*>(s->arena + ok[i]);
+        s->epochs = dmalloc<unsigned long long>(4);
+        RB_CUDA(cudaMemset(s->epochs, 0, 4 * sizeof(unsigned long long)));
+        s->comm.nranks = 1;
+        s->comm.rank = 0;
+        s->comm.my_base = s->arena;
+        s->comm.peer_base[0] = s->arena;
+        s->comm.signal_epoch = s->epochs;
+        s->comm.wait_epoch = s->epochs + 1;
+        s->comm.error_flag = reinterpret_cast<int*>(s->epochs + 2);
+        s->row_cell0 = 0;
+        s->row_cells = s->ncell;
     }
     s->xsum_a = dmalloc<double>(pc);
     s->rnorm_part = dmalloc<double>(pc);
@@ -319,8 +354,9 @@ static SweepArgs base_args(rb_solver* s, const double2* Z) {
     a.tile = s->tile;
     a.tiles_per_chunk = s->tiles_per_chunk;
     a.nchunks = s->nchunks;
-    a.row_cell0 = 0;
-    a.row_cells = s->ncell;
+    a.row_cell0 = s->row_cell0;
+    a.row_cells = s->row_cells;
+    a.comm = s->comm;
     a.use_local = s->use_local;
     a.has_image = s->has_image;
     a.g = make_geometry(s, Z);
@@ -352,6 +388,8 @@ static void launch_mv(rb_solver* s, const SweepArgs& base, int i, int skip) {
     a.skip_if_done = skip;
     launch_sweep(a, kSweepMV, s->stream);
     s->total_sweeps++;
+    if (s->comm.nranks > 1)
+        launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, s->bnorm_part, s->ncell, a.tol2, a.max_iters, s->stream);
 }
 
 static void read_ctrl(rb_solver* s) {
@@ -444,6 +482,15 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
     const double2* Z = state;
     fft_derivative(s, s->ac, s->aprime, 0, 2.0 * kPi / s->N);   // L/BaseBoundaryIntegrator.cuh:203
     SweepArgs a = base_args(s, Z);
+    double2* user_out = nullptr;
+    if (s->comm.nranks > 1) {
+        if (!s->rhs_phi_kind) throw std::runtime_error("row-sharded runs need a fused dPhi/dt (water with rho = 0, or helium without expansions / surface tension)");
+        const char* p = reinterpret_cast<const char*>(out);
+        if (p < s->arena || p >= s->arena + s->arena_bytes) {   // rows arrive from the peers inside the arena only
+            user_out = out;
+            out = s->kbuf[0];
+        }
+    }
     a.x = s->a;
     a.xsum_part = s->xsum_a;
     a.aprime = s->aprime;
@@ -453,6 +500,13 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
     a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
     launch_sweep(a, kSweepVEL, st);
     s->total_sweeps++;
+    if (s->comm.nranks > 1) {
+        launch_comm_wait(s->comm, s->ctrl, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
+        if (user_out) {
+            RB_CUDA(cudaMemcpyAsync(user_out, out, 2 * BN * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+            out = user_out;
+        }
+    }
     if (!s->rhs_phi_kind) {
         const rb_props& p = s->props;
         if (p.physics == RB_WATER) {
@@ -506,8 +560,6 @@ static void stepper_free(rb_stepper* st) {
     if (st->graph_exec) cudaGraphExecDestroy(st->graph_exec);
     if (st->ev) cudaEventDestroy(st->ev);
     if (st->owns_y0 && st->y0) cudaFree(st->y0);
-    for (auto p : st->k)
-        if (p) cudaFree(p);
     if (st->ytmp) cudaFree(st->ytmp);
     if (st->ybackup) cudaFree(st->ybackup);
     for (auto p : st->hist)
@@ -589,6 +641,7 @@ static size_t kernels_per_step(rb_solver* s, int sweeps) {
     // geometry path 4 + guess + sweeps + finish + (multiply, scale) + VEL + optional rhs_phi / energies, per stage; 3 stage updates,
     // final update, counter
     size_t per_stage = 4 + 1 + (size_t)sweeps + 1 + 2 + 1 + (s->rhs_phi_kind ? 0 : 1) + (s->props.compute_energies ? 1 : 0);
+    if (s->comm.nranks > 1) per_stage += (size_t)sweeps + 1;   // wait kernels
     return 4 * per_stage + 5;
 }
 
@@ -881,7 +934,7 @@ rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
         st->s = s;
         st->dt = tstep;
         const size_t n2 = 2 * s->BN;
-        for (auto& p : st->k) p = dmalloc<double2>(n2);
+        for (int i = 0; i < 4; ++i) st->k[i] = s->kbuf[i];   // in the solver's arena: peers publish their rows there
         st->ytmp = dmalloc<double2>(n2);
         st->ybackup = dmalloc<double2>(n2);
         for (auto& p : st->hist) {
@@ -1030,20 +1083,86 @@ int rb_rk4_final_update(rb_complex* y0, const rb_complex* k1, const rb_complex* 
     RB_CATCH
 }
 
-// ---- multi-GPU (row sharding) -- wired in comm.cu once initialised ---------------------------------
-int rb_comm_unique_id(char id_out[RB_UNIQUE_ID_BYTES]) {
-    (void)id_out;
-    g_last_error = "rb_comm_unique_id: multi-GPU row sharding is not built into this version";
-    return -1;
-}
-int rb_comm_init(rb_solver* s, int rank, int nranks, const char id[RB_UNIQUE_ID_BYTES]) {
-    (void)s; (void)rank; (void)nranks; (void)id;
-    g_last_error = "rb_comm_init: multi-GPU row sharding is not built into this version";
-    return -1;
-}
-int rb_comm_destroy(rb_solver* s) {
-    (void)s;
+// ---- multi-GPU: row cells of every O(N^2) sweep sharded over the ranks of one node ------------------------------------
+int rb_comm_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int rb_comm_row_range(int N, int rank, int nranks, int out_rows[2]) {
+    // contiguous blocks of whole 256-row cells; host-only arithmetic (no device needed)
+    if (N < 2 || nranks < 1 || rank < 0 || rank >= nranks) return -1;
+    const int ncell = (N + kCell - 1) / kCell;
+    const int per = (ncell + nranks - 1) / nranks;
+    const int c0 = std::min(rank * per, ncell);
+    const int c1 = std::min(c0 + per, ncell);
+    out_rows[0] = std::min(c0 * kCell, N);
+    out_rows[1] = std::min(c1 * kCell, N);
     return 0;
+}
+
+int rb_comm_export(rb_solver* s, char* handle_out) {
+    RB_TRY
+    cudaIpcMemHandle_t h;
+    RB_CUDA(cudaIpcGetMemHandle(&h, s->arena));
+    std::memcpy(handle_out, &h, sizeof(h));
+    RB_CATCH
+}
+
+int rb_comm_init(rb_solver* s, int rank, int nranks, const char* handles) {
+    RB_TRY
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) throw std::runtime_error("rb_comm_init: bad rank / nranks");
+    if (s->batch != 1) throw std::runtime_error("rb_comm_init: row sharding is for batch == 1; ensembles are replicated per rank");
+    if (!s->matrix_free_solve) throw std::runtime_error("rb_comm_init: row sharding needs the matrix-free solve");
+    if (s->ncell < nranks) throw std::runtime_error("rb_comm_init: N too small to give every rank a 256-row cell");
+    RB_CUDA(cudaStreamSynchronize(s->stream));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            s->comm.peer_base[r] = s->arena;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        RB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_mapped[r] = p;
+        s->comm.peer_base[r] = static_cast<char*>(p);
+    }
+    s->comm.nranks = nranks;
+    s->comm.rank = rank;
+    int rows[2];
+    rb_comm_row_range(s->N, rank, nranks, rows);
+    s->row_cell0 = rows[0] / kCell;
+    s->row_cells = (rows[1] - rows[0] + kCell - 1) / kCell;
+    if (s->row_cells < 1) throw std::runtime_error("rb_comm_init: this rank owns no rows");
+    // the sweep's grid now covers the local rows only: re-balance the source chunking and the partial workspace
+    choose_chunking(s);
+    cudaFree(s->partial);
+    s->partial = dmalloc<double2>((size_t)s->nchunks * s->BN);
+    if (s->has_image) {
+        cudaFree(s->partial_img);
+        s->partial_img = dmalloc<double2>((size_t)s->nchunks * s->BN);
+    }
+    RB_CATCH
+}
+
+int rb_comm_error(rb_solver* s) {
+    int e = 0;
+    if (cudaMemcpy(&e, s->comm.error_flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return e;
+}
+
+int rb_comm_destroy(rb_solver* s) {
+    RB_TRY
+    RB_CUDA(cudaStreamSynchronize(s->stream));
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (s->peer_mapped[r]) {
+            cudaIpcCloseMemHandle(s->peer_mapped[r]);
+            s->peer_mapped[r] = nullptr;
+        }
+    s->comm.nranks = 1;
+    s->comm.rank = 0;
+    s->comm.peer_base[0] = s->arena;
+    s->row_cell0 = 0;
+    s->row_cells = s->ncell;
+    RB_CATCH
 }
 
 // ---- measurement -------------------------------------------------------------------------------

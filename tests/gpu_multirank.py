@@ -1,0 +1,70 @@
+"""Row-sharded multi-GPU check, launched with torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/gpu_multirank.py
+Every rank also runs the single-GPU solver on its own device; the sharded state must agree with it to round-off."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import roberts_oracle as ro  # noqa: E402
+from superfluid_dynamics_b200 import api  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", device_id=dev)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    ok = True
+    for N, h, dt, steps in ((4096, 0.4, 1e-3, 20), (16384, 0.3, 2e-4, 10), (65536, 0.4, 1e-4, 5)):
+        props = api.ProblemProperties(rho=0.0)
+        Z, Phi = ro.trochoid(N, h)
+        y0 = ro.pack_state(Z, Phi)
+        single = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), device=dev, guess="warm")
+        s1 = api.AutonomousRungeKuttaStepper(single, dt)
+        st1 = torch.as_tensor(y0, device=dev)
+        s1.initialize(st1, True)
+        s1.runSteps(3)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        s1.runSteps(steps)
+        torch.cuda.synchronize()
+        t_single = (time.time() - t0) / steps
+        sharded = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), device=dev, guess="warm")
+        sharded.initComm(rank, world)
+        s2 = api.AutonomousRungeKuttaStepper(sharded, dt)
+        st2 = torch.as_tensor(y0, device=dev)
+        s2.initialize(st2, True)
+        s2.runSteps(3)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.time()
+        s2.runSteps(steps)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_sh = (time.time() - t0) / steps
+        a, b = st1.cpu().numpy(), st2.cpu().numpy()
+        err = np.abs(a - b).max() / np.abs(a).max()
+        # all ranks must hold the same replica bit for bit
+        ref = st2.clone()
+        dist.broadcast(ref, 0)
+        same = bool((torch.view_as_real(ref) == torch.view_as_real(st2)).all().item())
+        good = err <= 1e-12 and same and sharded.commError() == 0
+        ok = ok and good
+        print(f"[rank {rank}] N={N}: sharded vs single rel err {err:.2e}, replicas identical {same}, "
+              f"{1.0 / t_single:.1f} -> {1.0 / t_sh:.1f} steps/s ({t_single / t_sh:.2f}x on {world} GPUs) "
+              f"{sharded.solve_stats()} {s2.stats()} {'OK' if good else 'FAIL'}", flush=True)
+        del s1, s2, single, sharded
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
