@@ -11,25 +11,12 @@
 //   MatrixSolver<N,1>::solve (cusolverDnDgetrf + Dgetrs)          L/MatrixSolver.cuh:114-125
 // Matrices are column-major A[k + j*n + b*n*n] = entry (row k, col j), exactly as the reference stores them.
 #include "internal.cuh"
+#include "../../include/roberts_b200_device.cuh"
 
 namespace rb {
 
-// cot((a + i b)/2), accurate for every argument (no cosh - cos cancellation):
-//   cot(u + i v) = (sin u cos u - i sinh v cosh v) / (sin^2 u + sinh^2 v)
-__device__ __forceinline__ double2 cot_half(double a, double b) {
-    double u = 0.5 * a, v = 0.5 * b;
-    if (fabs(v) > 300.0) return make_double2(0.0, v > 0 ? -1.0 : 1.0);
-    double su, cu;
-    sincos(u, &su, &cu);
-    double sh = sinh(v), ch = cosh(v);
-    double inv = 1.0 / (su * su + sh * sh);
-    return make_double2(su * cu * inv, -sh * ch * inv);
-}
-
-__device__ __forceinline__ double2 cdivd(double2 a, double2 b) {
-    double inv = 1.0 / (b.x * b.x + b.y * b.y);
-    return make_double2((a.x * b.x + a.y * b.y) * inv, (a.y * b.x - a.x * b.y) * inv);
-}
+using rb_dev::cdivd;
+using rb_dev::cot_half;
 
 // ---- M -----------------------------------------------------------------------------------------
 template <bool FINITE>
@@ -39,24 +26,8 @@ __global__ void create_M_kernel(double* __restrict__ A, const double2* __restric
     int j = blockIdx.y * blockDim.y + threadIdx.y;   // column
     size_t b = blockIdx.z;
     if (k >= n || j >= n) return;
-    size_t idx = (size_t)k + (size_t)j * n + b * (size_t)n * n;
-    const double2 zk = Z[k + b * n], zpk = Zp[k + b * n];
-    const double coef = FINITE ? 0.25 / kPi : 0.25 * (1 - rho) / kPi;
-    double v;
-    if (k == j) {
-        double2 q = cdivd(Zpp[k + b * n], zpk);
-        v = (FINITE ? 0.5 : 0.5 * (1 + rho)) + coef * q.y;
-        if (FINITE && !infinite_depth) v -= 0.25 / kPi * cot_half(0.0, 2.0 * (zk.y + h)).y;   // cot(i (Y + h))
-    } else {
-        const double2 zj = Z[j + b * n];
-        double2 c = cot_half(zk.x - zj.x, zk.y - zj.y);
-        v = coef * (zpk.x * c.y + zpk.y * c.x);                                               // Im(Zp_k * cot)
-        if (FINITE && !infinite_depth) {
-            // 0.5 (Z_k - conj Z_j) + i h  =  ((x_k - x_j) + i (y_k + y_j + 2h)) / 2
-            v -= 0.25 / kPi * cot_half(zk.x - zj.x, zk.y + zj.y + 2.0 * h).y;
-        }
-    }
-    A[idx] = v;
+    A[(size_t)k + (size_t)j * n + b * (size_t)n * n] =
+        rb_dev::M_entry<FINITE>(k, j, Z + b * n, Zp + b * n, Zpp + b * n, rho, h, infinite_depth);
 }
 
 void launch_create_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double rho, int n, size_t batch,
@@ -83,34 +54,8 @@ __global__ void velocity_matrices_kernel(const double2* __restrict__ Z, const do
     int j = blockIdx.y * blockDim.y + threadIdx.y;
     size_t b = blockIdx.z;
     if (k >= n || j >= n) return;
-    size_t idx = (size_t)k + (size_t)j * n + b * (size_t)n * n;
-    const double2 zk = Z[k + b * n];
-    const double q4 = 1.0 / (4.0 * kPi);
-    double2 v;
-    if (k == j) {
-        const double2 zpk = Zp[k + b * n];
-        double2 q2 = cdivd(cdivd(Zpp[k + b * n], zpk), zpk);       // Zpp / Zp^2
-        v = make_double2(q4 * q2.y, -q4 * q2.x);                    // multiply_by_i(-q4 * q2)
-        if (helium && !infinite_depth) {
-            double2 c = cot_half(0.0, 2.0 * (zk.y + h));
-            v.x += -q4 * c.y;                                       // multiply_by_i(q4 * c)
-            v.y += q4 * c.x;
-        }
-        double2 hz = cdivd(make_double2(0.5, 0.0), zpk);
-        if (lower) { v.x += hz.x; v.y += hz.y; } else { v.x -= hz.x; v.y -= hz.y; }
-        double2 iz = cdivd(make_double2(1.0 / (2.0 * kPi), 0.0), zpk);
-        V2[k + b * n] = make_double2(-iz.y, iz.x);
-    } else {
-        const double2 zj = Z[j + b * n];
-        double2 c = cot_half(zk.x - zj.x, zk.y - zj.y);
-        v = make_double2(q4 * c.y, -q4 * c.x);                      // multiply_by_i(-q4 * c)
-        if (helium && !infinite_depth) {
-            double2 ci = cot_half(zk.x - zj.x, zk.y + zj.y + 2.0 * h);
-            v.x += -q4 * ci.y;
-            v.y += q4 * ci.x;
-        }
-    }
-    V1[idx] = v;
+    V1[(size_t)k + (size_t)j * n + b * (size_t)n * n] =
+        rb_dev::V1_entry(k, j, Z + b * n, Zp + b * n, Zpp + b * n, V2 + b * n, lower, helium, h, infinite_depth);
 }
 
 void launch_velocity_matrices(const double2* Z, const double2* Zp, const double2* Zpp, int n, double2* V1, double2* V2,
