@@ -117,6 +117,7 @@ struct SweepArgs {
     int rhs_phi_kind;                // VEL epilogue: 0 none, 1 water rho==0, 2 helium vdw, 3 helium expansion, 4 helium + surface tension
     int expansion_order;
     double kappa;
+    int apply_only;                  // MV sweeps: x_out = M x (no update, no convergence logic) -- the Krylov solver's operator
     int skip_if_done;                // MV sweeps: return at once when ctrl->done
     int out_buf;                     // MV sweeps: index (0/1) of the iterate buffer x_out lives in
     // VEL outputs
@@ -148,6 +149,15 @@ void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int bat
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st);
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
                          double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st);
+// krylov_kernels.cu
+void launch_multi_dot(const double* V, size_t ldv, int nvec, const double* w, double* out, int n, cudaStream_t st);
+void launch_multi_axpy(double* w, const double* V, size_t ldv, int nvec, const double* h, double sign, int n, cudaStream_t st);
+void launch_combine(double* out, const double* V, size_t ldv, int nvec, const double* y, int n, cudaStream_t st);
+void launch_normalize(double* vout, const double* w, const double* nrm2, int n, cudaStream_t st);
+void launch_axpby(double* out, const double* a, double alpha, const double* b, int n, cudaStream_t st);
+void launch_precond_scale(double2* hat, const double* invP, int N, int n, cudaStream_t st);
+void launch_real_to_complex(const double* x, double2* out, int n, cudaStream_t st);
+void launch_complex_to_real(const double2* c, double* out, double scale, int n, cudaStream_t st);
 // dense_kernels.cu
 void launch_create_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double rho, int n, size_t batch,
                      cudaStream_t st);

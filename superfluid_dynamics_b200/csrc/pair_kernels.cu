@@ -447,12 +447,30 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                 double Kx = a.cK * (zp.x * Ar - zp.y * Ai);
                 if (IMAGE) Kx -= inv4pi * (sumx + 2.0 * TI[r].x);   // -(1/4pi) Im(S_img), S_img = i (sumx + 2 T_img)
                 double Mx = fma(a.g.Mdiag[o], xk, Kx);
+                if (a.apply_only) {   // operator application for the Krylov solver: y = M x
+                    mirror_store(a.comm, a.x_out + o, Mx);
+                    continue;
+                }
                 double res = a.g.b[o] - Mx;
                 double xn = fma(a.omega, res, xk);
                 mirror_store(a.comm, a.x_out + o, xn);
                 sx += xn;
                 sr += res * res;
             }
+        }
+        if (a.apply_only) {
+            if (a.comm.nranks > 1) {
+                __threadfence_system();
+                __syncthreads();
+                if (t == 0) s_ticket = atomicAdd(a.member_tickets + bm, 1u);
+                __syncthreads();
+                if (s_ticket == (unsigned)(a.row_cells - 1) && t == 0) {
+                    a.member_tickets[bm] = 0u;
+                    __threadfence_system();
+                    comm_signal(a.comm);
+                }
+            }
+            return;
         }
         sx = block_reduce_fixed<kSweepThreads>(sx, sred);
         sr = block_reduce_fixed<kSweepThreads>(sr, sred);

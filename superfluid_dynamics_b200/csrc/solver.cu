@@ -100,6 +100,11 @@ struct rb_solver {
     void* peer_mapped[kMaxRanks] = {};
     unsigned long long* epochs = nullptr;   // [2] signal / wait counters + error flag
     int row_cell0 = 0, row_cells = 0;
+    // restarted GMRES for the finite-depth helium operator (host-driven, one synchronisation per iteration)
+    bool use_gmres = false;
+    int gm_m = 0;                  // restart length
+    double *gm_V = nullptr, *gm_x = nullptr, *gm_t = nullptr, *gm_dev = nullptr, *gm_invP = nullptr;
+    double* gm_host = nullptr;     // pinned
     double* Mdense = nullptr;      // dense validation path, allocated on demand
     int* lu_info = nullptr;
     double2* scratch_state = nullptr;   // legacy host-vector exports
@@ -144,10 +149,12 @@ static void solver_free(rb_solver* s) {
     void* ptrs[] = {s->deriv, s->fwork, s->EG, s->P0, s->Pm, s->Pp, s->EI, s->V1diag, s->V2, s->Mdiag, s->b, s->a,
                     s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
-                    s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state};
+                    s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state, s->gm_V, s->gm_x, s->gm_t,
+                    s->gm_dev, s->gm_invP};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->gm_host) cudaFreeHost(s->gm_host);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -224,8 +231,10 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     s->omega = 2.0 / (1.0 + s->rhoM);
     s->use_local = (s->ncell >= kMinCellsForLocal && !env_int("RB_NO_LOCAL", 0)) ? 1 : 0;
     // Richardson on (1/2) I + K converges for the water / infinite-depth operators; the finite-depth image term of the
-    // reference (no Zp_k factor, L/createM.cuh:87-88) makes M far from (1/2) I, so that case goes through the dense solve.
-    s->matrix_free_solve = (p.solve_mode == RB_SOLVE_MATRIX_FREE) && !s->has_image;
+    // reference (no Zp_k factor, L/createM.cuh:87-88) spreads the spectrum of M between 1/2 and N/(4 pi): that case is solved
+    // by restarted GMRES on the same matrix-free operator, right-preconditioned with the flat-film symbol of the image term.
+    s->matrix_free_solve = (p.solve_mode == RB_SOLVE_MATRIX_FREE);
+    s->use_gmres = s->matrix_free_solve && s->has_image;
     choose_chunking(s);
 
     const size_t BN = s->BN;
@@ -291,6 +300,28 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     RB_CUDA(cudaMemset(s->energies, 0, 8 * sizeof(double)));
     RB_CUDA(cudaMallocHost(&s->h_ctrl, 4 * sizeof(SolveCtrl)));
     std::memset(s->h_ctrl, 0, 4 * sizeof(SolveCtrl));
+
+    if (s->use_gmres) {
+        s->gm_m = std::max(2, std::min(env_int("RB_GMRES_RESTART", 60), N));
+        s->gm_V = dmalloc<double>((size_t)(s->gm_m + 1) * BN);
+        s->gm_x = dmalloc<double>(BN);
+        s->gm_t = dmalloc<double>(BN);
+        s->gm_dev = dmalloc<double>(4 * (s->gm_m + 4));
+        RB_CUDA(cudaMallocHost(&s->gm_host, 4 * (s->gm_m + 4) * sizeof(double)));
+        s->gm_invP = dmalloc<double>(N);
+        // flat-film symbol of M: 1/2 + (N/4pi) (e^{-2Hm} + e^{-2H(N-m)}) / (1 - e^{-2HN}),  H = depth
+        std::vector<double> invP(N, 2.0);
+        if (env_int("RB_HELIUM_PRECOND", 1)) {
+            const double H = p.depth;
+            for (int m = 0; m < N; ++m) {
+                double sym = (std::exp(-2.0 * H * m) + std::exp(-2.0 * H * (N - m))) / (1.0 - std::exp(-2.0 * H * N));
+                invP[m] = 1.0 / (0.5 + N / (4.0 * kPi) * sym);
+            }
+        } else {
+            std::fill(invP.begin(), invP.end(), 1.0);
+        }
+        RB_CUDA(cudaMemcpy(s->gm_invP, invP.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+    }
 
     int n[1] = {N};
     cufft_check(cufftPlanMany(&s->plan1, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, batch), "cufftPlanMany(B)");
@@ -405,6 +436,133 @@ static void account_solve(rb_solver* s) {
     s->num_solves++;
 }
 
+// ---- restarted GMRES(m), right-preconditioned, classical Gram-Schmidt with re-orthogonalisation -------------------------
+// y = M x for the rows of this rank (published to every rank when sharded); x: any device vector, result in xbuf[1]
+static void apply_M(rb_solver* s, const SweepArgs& base, const double* x) {
+    cudaStream_t st = s->stream;
+    launch_finish_solve(x, x, nullptr, nullptr, nullptr, s->xsum_part[0], HistoryRing(), s->N, s->batch, s->ncell, st);
+    SweepArgs a = base;
+    a.x = x;
+    a.x_out = s->xbuf[1];
+    a.xsum_part = s->xsum_part[0];
+    a.xsum_part_out = s->xsum_part[1];
+    a.apply_only = 1;
+    a.skip_if_done = 0;
+    a.out_buf = 1;
+    launch_sweep(a, kSweepMV, st);
+    s->total_sweeps++;
+    if (s->comm.nranks > 1) launch_comm_wait(s->comm, s->ctrl, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
+}
+
+// out = P^{-1} v  (FFT, divide by the flat-film symbol, inverse FFT); out may alias v
+static void apply_Pinv(rb_solver* s, const double* v, double* out) {
+    cudaStream_t st = s->stream;
+    const int n = (int)s->BN;
+    double2* tmp = s->fwork;   // free between the derivative stage and the a' stage
+    launch_real_to_complex(v, tmp, n, st);
+    cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)tmp, (cufftDoubleComplex*)tmp, CUFFT_FORWARD), "fft fwd");
+    launch_precond_scale(tmp, s->gm_invP, s->N, n, st);
+    cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)tmp, (cufftDoubleComplex*)tmp, CUFFT_INVERSE), "fft inv");
+    launch_complex_to_real(tmp, out, 1.0 / s->N, n, st);
+}
+
+static void gmres_solve(rb_solver* s, const double2* Z) {
+    cudaStream_t st = s->stream;
+    const int n = (int)s->BN, m = s->gm_m;
+    const size_t ld = s->BN;
+    const double tol = s->props.tolerance;
+    double* V = s->gm_V;
+    double* w = s->xbuf[1];
+    double* dh = s->gm_dev;            // [0..m+1] pass 1, [m+2..2m+3] pass 2, then norm, then y
+    double* hh = s->gm_host;
+    const int stride = m + 2;
+    SweepArgs base = base_args(s, Z);
+
+    const double* warm = nullptr;
+    if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
+    launch_guess(s->b, warm, s->hist, s->gm_x, s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
+    if (!warm && !s->hist.base) apply_Pinv(s, s->b, s->gm_x);   // cold start: x0 = P^{-1} b
+
+    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
+    int applies = 0;
+    double rel = 1e300, bnorm = 0.0;
+    bool converged = false;
+    const int max_applies = s->props.max_iterations;
+    for (int restart = 0; restart < 50 && !converged && applies < max_applies; ++restart) {
+        // true residual r = b - M x
+        apply_M(s, base, s->gm_x);
+        applies++;
+        launch_axpby(V, s->b, -1.0, w, n, st);
+        launch_multi_dot(V, ld, 0, V, dh, n, st);           // dh[0] = r.r
+        launch_multi_dot(V, ld, 0, s->b, dh + 1, n, st);     // dh[1] = b.b
+        RB_CUDA(cudaMemcpyAsync(hh, dh, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        const double beta = std::sqrt(hh[0]);
+        bnorm = std::sqrt(hh[1]);
+        rel = bnorm > 0 ? beta / bnorm : (beta == 0 ? 0.0 : 1e300);
+        if (!(rel == rel)) break;                             // NaN: give up, reported as not converged
+        if (rel <= tol) {
+            converged = true;
+            break;
+        }
+        launch_normalize(V, V, dh, n, st);
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int k_used = 0;
+        for (int k = 0; k < m && applies < max_applies; ++k) {
+            apply_Pinv(s, V + (size_t)k * ld, s->gm_t);
+            apply_M(s, base, s->gm_t);                        // w = M P^{-1} v_k
+            applies++;
+            launch_multi_dot(V, ld, k + 1, w, dh, n, st);
+            launch_multi_axpy(w, V, ld, k + 1, dh, -1.0, n, st);
+            launch_multi_dot(V, ld, k + 1, w, dh + stride, n, st);
+            launch_multi_axpy(w, V, ld, k + 1, dh + stride, -1.0, n, st);
+            launch_multi_dot(V, ld, 0, w, dh + 2 * stride, n, st);
+            launch_normalize(V + (size_t)(k + 1) * ld, w, dh + 2 * stride, n, st);
+            RB_CUDA(cudaMemcpyAsync(hh, dh, (2 * stride + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+            RB_CUDA(cudaStreamSynchronize(st));
+            for (int j = 0; j <= k; ++j) H[(size_t)j * m + k] = hh[j] + hh[stride + j];
+            H[(size_t)(k + 1) * m + k] = std::sqrt(std::max(0.0, hh[2 * stride]));
+            for (int j = 0; j < k; ++j) {                    // previous rotations
+                double a0 = H[(size_t)j * m + k], a1 = H[(size_t)(j + 1) * m + k];
+                H[(size_t)j * m + k] = cs[j] * a0 + sn[j] * a1;
+                H[(size_t)(j + 1) * m + k] = -sn[j] * a0 + cs[j] * a1;
+            }
+            double a0 = H[(size_t)k * m + k], a1 = H[(size_t)(k + 1) * m + k];
+            double d = std::hypot(a0, a1);
+            cs[k] = d > 0 ? a0 / d : 1.0;
+            sn[k] = d > 0 ? a1 / d : 0.0;
+            H[(size_t)k * m + k] = d;
+            H[(size_t)(k + 1) * m + k] = 0.0;
+            g[k + 1] = -sn[k] * g[k];
+            g[k] = cs[k] * g[k];
+            k_used = k + 1;
+            rel = std::fabs(g[k + 1]) / bnorm;
+            if (!(rel == rel) || rel <= tol) break;
+        }
+        if (k_used == 0) break;
+        for (int i = k_used - 1; i >= 0; --i) {               // back substitution
+            double acc = g[i];
+            for (int j = i + 1; j < k_used; ++j) acc -= H[(size_t)i * m + j] * y[j];
+            y[i] = acc / H[(size_t)i * m + i];
+        }
+        std::memcpy(hh, y.data(), k_used * sizeof(double));
+        double* dy = dh + 3 * stride;
+        RB_CUDA(cudaMemcpyAsync(dy, hh, k_used * sizeof(double), cudaMemcpyHostToDevice, st));
+        launch_combine(s->gm_t, V, ld, k_used, dy, n, st);
+        apply_Pinv(s, s->gm_t, s->gm_t);
+        launch_axpby(s->gm_x, s->gm_x, 1.0, s->gm_t, n, st);
+        RB_CUDA(cudaStreamSynchronize(st));                   // hh is reused by the next restart
+        if (rel == rel && rel <= tol) converged = true;       // estimate; CGS2 keeps it within round-off of the true residual
+    }
+    s->last_iters = applies;
+    s->last_converged = converged ? 1 : 0;
+    s->last_rel = rel;
+    account_solve(s);
+    launch_finish_solve(s->gm_x, s->gm_x, nullptr, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
+    s->have_prev_a = true;
+}
+
 // M a = b.  On return a (real), ac (complex copy) and the per-cell sums of a are valid on the stream.
 static void solve(rb_solver* s, const double2* Z) {
     cudaStream_t st = s->stream;
@@ -426,6 +584,11 @@ static void solve(rb_solver* s, const double2* Z) {
         s->last_iters = 0;
         s->last_converged = 1;
         s->last_rel = 0;
+        return;
+    }
+
+    if (s->use_gmres) {
+        gmres_solve(s, Z);
         return;
     }
 
@@ -659,7 +822,7 @@ static void after_step(rb_stepper* st) {
 
 static void stepper_step(rb_stepper* st) {
     rb_solver* s = st->s;
-    const bool graphable = st->use_graph && s->matrix_free_solve;
+    const bool graphable = st->use_graph && s->matrix_free_solve && !s->use_gmres;   // GMRES is host-driven
     if (!graphable) {
         issue_step(st, 0);
         if (s->props.guess_mode == RB_GUESS_WARM && s->matrix_free_solve) st->h_counter++;
@@ -823,7 +986,7 @@ int rb_energies(rb_solver* s, double out_host[5]) {
 
 int rb_solve_stats(rb_solver* s, double out_host[5]) {
     RB_TRY
-    if (s->matrix_free_solve) read_ctrl(s);
+    if (s->matrix_free_solve && !s->use_gmres) read_ctrl(s);
     out_host[0] = s->last_iters;
     out_host[1] = s->last_converged;
     out_host[2] = s->last_rel;

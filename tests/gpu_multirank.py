@@ -61,6 +61,33 @@ def main():
               f"{1.0 / t_single:.1f} -> {1.0 / t_sh:.1f} steps/s ({t_single / t_sh:.2f}x on {world} GPUs) "
               f"{sharded.solve_stats()} {s2.stats()} {'OK' if good else 'FAIL'}", flush=True)
         del s1, s2, single, sharded
+    # BASELINE config 4: helium film with van-der-Waals forcing, finite depth d = 0.0942478, N = 16384, row-sharded (GMRES solve)
+    N, depth, dt, steps = 16384, 0.0942478, 1e-3, 3
+    props = api.ProblemProperties(rho=0.0, depth=depth)
+    al = 2 * np.pi * np.arange(N) / N
+    y0 = ro.pack_state(al + 1j * 0.1 * depth * np.cos(al), np.zeros(N))
+    res = []
+    for shard in (False, True):
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumBoundaryProblem(props), device=dev, guess="warm")
+        if shard:
+            calc.initComm(rank, world)
+        stp = api.AutonomousRungeKuttaStepper(calc, dt)
+        st = torch.as_tensor(y0, device=dev)
+        stp.initialize(st, True)
+        stp.runSteps(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.time()
+        stp.runSteps(steps)
+        torch.cuda.synchronize()
+        dist.barrier()
+        res.append((st.cpu().numpy(), (time.time() - t0) / steps, calc.solve_stats()))
+        del stp, calc
+    err = np.abs(res[0][0] - res[1][0]).max() / np.abs(res[0][0]).max()
+    good = err <= 1e-10 and res[1][2]["converged"]
+    ok = ok and good
+    print(f"[rank {rank}] helium N={N} d={depth}: sharded vs single rel err {err:.2e}, {1.0 / res[0][1]:.2f} -> {1.0 / res[1][1]:.2f} "
+          f"steps/s on {world} GPUs, {res[1][2]} {'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

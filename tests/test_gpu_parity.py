@@ -252,6 +252,65 @@ def test_rhs_matches_oracle(api, physics, N, h, B, rho, depth):
     assert rel(calc.devPhiPrime.cpu().numpy()[:N], aux["PhiPrime"]) <= tol
 
 
+def test_helium_gmres_agrees_with_dense_lu_and_reports_convergence(api):
+    """Finite-depth helium operator (spectrum between 1/2 and N/4pi): matrix-free GMRES vs the dense LU validation path."""
+    N, depth = 512, 0.0942478
+    props = api.ProblemProperties(rho=0.0, depth=depth)
+    prob = api.HeliumBoundaryProblem(props)
+    for amp in (0.1, 0.5):
+        al = 2 * np.pi * np.arange(N) / N
+        Z = al - 0.3 * amp * depth * np.sin(al) + 1j * amp * depth * np.cos(al)
+        Phi = 0.2 * amp * depth * np.sin(al)
+        st = T(ro.pack_state(Z, Phi))
+        outs = []
+        for mode in ("matrix_free", "dense_lu"):
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, prob, solve_mode=mode)
+            out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+            calc.run(st, out)
+            outs.append((out.cpu().numpy(), calc.getDevA().cpu().numpy().copy(), calc.solve_stats()))
+        assert outs[0][2]["converged"] and 2 <= outs[0][2]["iterations"] <= 80
+        assert rel(outs[0][1], outs[1][1]) <= 1e-10            # cond(M) ~ N/(2 pi)
+        assert rel(outs[0][0], outs[1][0]) <= 1e-10
+
+
+def test_small_amplitude_wave_follows_linear_dispersion(api):
+    """BASELINE config 2: N = 1024 deep-water wave, g = 1, k = 1: omega^2 = k.  After t the profile is eps cos(x - t) + O(eps^2)."""
+    N, eps, dt, steps = 1024, 1e-4, 1e-3, 400
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(calc, dt)
+    Z, Phi = ro.sinusoid(N, eps)
+    stp.initialize(ro.pack_state(Z, Phi), False)
+    stp.runSteps(steps)
+    y = stp.getState()
+    t = dt * steps
+    assert np.abs(y[:N].imag - eps * np.cos(y[:N].real - t)).max() <= 5 * eps * eps
+    # phase speed: the crest (max of Y) moved by omega t / k = t
+    k = int(np.argmax(y[:N].imag))
+    assert abs(y[k].real % (2 * np.pi) - t) <= 2 * (2 * np.pi / N)
+
+
+def test_ensemble_batch_1024_members_N512(api):
+    """BASELINE config 5 (second half): 1024-member ensemble at N = 512, member m = trochoid h_m = 0.05 + 0.35 m / 1023
+    (SURVEY.md section 8d).  A sample of members is compared with the oracle; all members must converge."""
+    N, B = 512, 1024
+    hs = 0.05 + 0.35 * np.arange(B) / (B - 1)
+    Zs, Ps = zip(*(ro.trochoid(N, h) for h in hs))
+    st = np.concatenate(list(Zs) + [p.astype(np.complex128) for p in Ps])
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, B, props, api.WaterBoundaryProblem(props))
+    out = torch.zeros(2 * N * B, dtype=torch.complex128, device="cuda:0")
+    calc.run(T(st), out)
+    assert calc.solve_stats()["converged"]
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all()
+    oprops = ro.ProblemProperties(rho=0.0)
+    for m in (0, 1, 511, 1022, 1023):
+        v, dphi = ro.rhs_single(Zs[m], Ps[m], oprops, "water", "cuda")
+        assert rel(o[m * N:(m + 1) * N], v) <= 1e-12
+        assert rel(o[B * N + m * N: B * N + (m + 1) * N], dphi) <= 1e-12
+
+
 def test_rhs_rejects_nothing_silently(api):
     """A surface with coincident points has no finite RHS: the iteration must report non-convergence, not a number."""
     N = 64
