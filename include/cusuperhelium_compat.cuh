@@ -1,0 +1,308 @@
+// cusuperhelium_compat.cuh -- the reference's C++ names for the Roberts BIE RK4 path, as thin shims over the C ABI of
+// libroberts_b200.so (include/roberts_b200.h).  Include this instead of the reference's BoundaryProblem.cuh /
+// BaseBoundaryIntegrator.cuh / AutonomousRungeKuttaStepper.cuh / Derivatives.cuh / createM.cuh / WaterVelocities.cuh and link
+// with -lroberts_b200.  Template parameters N / batchSize are kept for source compatibility; underneath N is a runtime value.
+//
+// Reference declarations mirrored (L/ = CuSuperHelium/CuSuperHelium/):
+//   std_complex                         L/constants.cuh:12
+//   ProblemProperties                   L/ProblemProperties.hpp:5-32
+//   AutonomousProblem<T,N>              L/AutonomousProblem.h:9-28
+//   BoundaryProblem<N,B> + Water / Helium / HeliumInfiniteDepth   L/BoundaryProblem.cuh:24-62, L/WaterBoundaryProblem.cuh,
+//                                       L/HeliumBoundaryProblem.cuh
+//   BaseBoundaryIntegralCalculator<N,B> L/BaseBoundaryIntegrator.cuh:10-85
+//   ZPhiDerivative<N,B>, FftDerivative<N,B>   L/Derivatives.cuh:51-108
+//   AutonomousRungeKuttaStepper<T,N>, RK4Options, OdeSolverResult  L/AutonomousRungeKuttaStepper.cuh:24-89, L/RK4Options.h, L/OdeSolver.h
+//   TrajectoryLogger<T,N>               L/TrajectoryLogger.cuh:7-73
+//   createMKernel, createFiniteDepthMKernel, createVelocityMatrices, createHeliumVelocityMatrices,
+//   compute_rhs_phi_expression, compute_rhs_helium_phi_expression   (the __global__ kernels the reference's tests launch)
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda/std/complex>
+
+#include <cstdlib>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "roberts_b200.h"
+#include "roberts_b200_device.cuh"
+
+typedef cuda::std::complex<double> std_complex;
+constexpr double PI_d = 3.14159265358979323846;
+
+struct ProblemProperties {
+    double L = 1.0;
+    double rho = 1.0;
+    double U = 0.0;
+    double kappa = 0.0;
+    double depth = 1.0;
+    double initial_amplitude = 1.0;
+    double y_min = 0, y_max = 0;
+    bool use_expansions = false;
+    int expansion_order = 1;
+    bool infinite_depth = false;
+    double base_length = 1.0, base_time = 1.0, base_energy = 1.0, base_acceleration = 1.0;
+};
+
+struct RK4Options {
+    double initial_timestep = 1e-2;
+    bool returnTrajectory = true;
+};
+
+enum class OdeSolverResult { ReachedEndTime, StiffnessDetected };
+
+inline void rb_compat_check(int rc, const char* what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + rb_last_error());
+}
+
+template <typename T, int N>
+class AutonomousProblem {
+public:
+    virtual ~AutonomousProblem() {}
+    virtual void run(T* initialState, T* rhs) = 0;
+    virtual void setStream(cudaStream_t stream) = 0;
+};
+
+// ---- physics plugins: here they only select which kernels the solver uses -----------------------------------------------
+template <int N, size_t batchSize>
+class BoundaryProblem {
+public:
+    virtual ~BoundaryProblem() {}
+    virtual int physics() const = 0;
+};
+template <int N, size_t batchSize>
+class WaterBoundaryProblem : public BoundaryProblem<N, batchSize> {
+public:
+    explicit WaterBoundaryProblem(ProblemProperties&) {}
+    int physics() const override { return RB_WATER; }
+};
+template <int N, size_t batchSize>
+class HeliumBoundaryProblem : public BoundaryProblem<N, batchSize> {
+public:
+    explicit HeliumBoundaryProblem(ProblemProperties&) {}
+    int physics() const override { return RB_HELIUM; }
+};
+template <int N, size_t batchSize>
+class HeliumInfiniteDepthBoundaryProblem : public BoundaryProblem<N, batchSize> {
+public:
+    explicit HeliumInfiniteDepthBoundaryProblem(ProblemProperties&) {}
+    int physics() const override { return RB_HELIUM_INF; }
+};
+
+// energy handles with the reference's getEnergy() (L/Energies.cuh:229-235)
+class RbEnergyView {
+    rb_solver* s_;
+    int which_;
+public:
+    RbEnergyView(rb_solver* s = nullptr, int which = 0) : s_(s), which_(which) {}
+    double getEnergy() const {
+        double e[5];
+        rb_compat_check(rb_energies(s_, e), "rb_energies");
+        return e[which_];
+    }
+};
+
+template <int N, size_t batchSize>
+class BaseBoundaryIntegralCalculator : public AutonomousProblem<std_complex, 2 * N * (int)batchSize> {
+    rb_solver* s_ = nullptr;
+public:
+    RbEnergyView kineticEnergy, potentialEnergy, surfaceEnergy, volumeFlux;
+    std_complex* devVelocitiesUpper = nullptr;
+    double* devPhiPrime = nullptr;
+
+    BaseBoundaryIntegralCalculator(ProblemProperties& p, BoundaryProblem<N, batchSize>& problem, int guess_mode = RB_GUESS_WARM) {
+        rb_props rp;
+        rb_default_props(&rp);
+        rp.rho = p.rho; rp.U = p.U; rp.kappa = p.kappa; rp.depth = p.depth;
+        rp.use_expansions = p.use_expansions; rp.expansion_order = p.expansion_order; rp.infinite_depth = p.infinite_depth;
+        rp.physics = problem.physics();
+        rp.guess_mode = guess_mode;
+        s_ = rb_create(N, (int)batchSize, &rp);
+        if (!s_) throw std::runtime_error(std::string("rb_create: ") + rb_last_error());
+        kineticEnergy = RbEnergyView(s_, 0); potentialEnergy = RbEnergyView(s_, 1); surfaceEnergy = RbEnergyView(s_, 2);
+        volumeFlux = RbEnergyView(s_, 3);
+        devVelocitiesUpper = reinterpret_cast<std_complex*>(rb_dev_velocities_upper(s_));
+        devPhiPrime = rb_dev_phi_prime(s_);
+    }
+    ~BaseBoundaryIntegralCalculator() override { rb_destroy(s_); }
+    BaseBoundaryIntegralCalculator(const BaseBoundaryIntegralCalculator&) = delete;
+    BaseBoundaryIntegralCalculator& operator=(const BaseBoundaryIntegralCalculator&) = delete;
+
+    void runTimeStep(const std_complex* initialState, std_complex* rhs) {
+        rb_compat_check(rb_rhs(s_, reinterpret_cast<const rb_complex*>(initialState), reinterpret_cast<rb_complex*>(rhs)), "rb_rhs");
+    }
+    void run(std_complex* initialState, std_complex* rhs) override { runTimeStep(initialState, rhs); }
+    void calculateVorticities(const std_complex* initialState) {
+        rb_compat_check(rb_vorticities(s_, reinterpret_cast<const rb_complex*>(initialState)), "rb_vorticities");
+    }
+    double* getDevA() { return rb_dev_a(s_); }
+    std_complex* getDevZp() { return reinterpret_cast<std_complex*>(rb_dev_zp(s_)); }
+    std_complex* getDevZpp() { return reinterpret_cast<std_complex*>(rb_dev_zpp(s_)); }
+    void setStream(cudaStream_t stream) override { rb_compat_check(rb_set_stream(s_, stream), "rb_set_stream"); }
+    rb_solver* handle() { return s_; }
+};
+
+template <int N, size_t batchSize>
+class ZPhiDerivative {
+    rb_solver* s_ = nullptr;
+public:
+    explicit ZPhiDerivative(ProblemProperties& p) {
+        rb_props rp;
+        rb_default_props(&rp);
+        rp.rho = p.rho; rp.U = p.U;
+        s_ = rb_create(N, (int)batchSize, &rp);
+        if (!s_) throw std::runtime_error(std::string("rb_create: ") + rb_last_error());
+    }
+    ~ZPhiDerivative() { rb_destroy(s_); }
+    void exec(const std_complex* Z, const std_complex* Phi, std_complex* ZPrime, std_complex* PhiPrime, std_complex* Zpp) {
+        rb_compat_check(rb_zphi_derivative(s_, (const rb_complex*)Z, (const rb_complex*)Phi, (rb_complex*)ZPrime,
+                                           (rb_complex*)PhiPrime, (rb_complex*)Zpp), "rb_zphi_derivative");
+        rb_synchronize(s_);
+    }
+};
+
+template <int N, int batchSize>
+class FftDerivative {
+    rb_solver* s_ = nullptr;
+public:
+    FftDerivative() {}
+    ~FftDerivative() { if (s_) rb_destroy(s_); }
+    cudaError_t initialize(bool = false) {
+        rb_props rp;
+        rb_default_props(&rp);
+        s_ = rb_create(N, batchSize, &rp);
+        return s_ ? cudaSuccess : cudaErrorUnknown;
+    }
+    void exec(const std_complex* in, std_complex* out, const bool doubleDev = false, double scaling = 1.0, bool = false) {
+        if (!s_) throw std::runtime_error("The FFT class wasn't initialized!");
+        rb_compat_check(rb_fft_derivative(s_, (const rb_complex*)in, (rb_complex*)out, doubleDev, scaling), "rb_fft_derivative");
+        rb_synchronize(s_);
+    }
+};
+
+// ---- trajectory logger + stepper ------------------------------------------------------------------------------------------
+template <typename T, int N>
+class TrajectoryLogger {
+public:
+    size_t every, capacity;
+    rb_stepper* st = nullptr;
+    explicit TrajectoryLogger(size_t log_every = 1, size_t max_states = 1024) : every(log_every), capacity(max_states) {}
+    void copyTimesToHost(double** times, size_t* count) {
+        rb_complex* states = nullptr; size_t ns = 0;
+        rb_compat_check(rb_rk4_copy_trajectory(st, times, count, &states, &ns), "rb_rk4_copy_trajectory");
+        rb_free(states);
+    }
+    void copyStatesToHost(T** states, size_t* count) {
+        double* times = nullptr; size_t nt = 0;
+        rb_compat_check(rb_rk4_copy_trajectory(st, &times, &nt, reinterpret_cast<rb_complex**>(states), count),
+                        "rb_rk4_copy_trajectory");
+        rb_free(times);
+    }
+};
+
+template <typename T, int N>
+class AutonomousRungeKuttaStepper {
+    rb_stepper* st_ = nullptr;
+    std::shared_ptr<TrajectoryLogger<T, N>> logger_;
+public:
+    // the problem must be a BaseBoundaryIntegralCalculator<N/2/B, B>; its solver handle is what the stepper binds to
+    template <int NP, size_t B>
+    AutonomousRungeKuttaStepper(BaseBoundaryIntegralCalculator<NP, B>& problem, double tstep = 1e-2,
+                                std::shared_ptr<TrajectoryLogger<T, N>> logger = nullptr)
+        : logger_(logger) {
+        static_assert(2 * NP * (int)B == N, "state size must be 2 * N * batchSize");
+        st_ = rb_rk4_create(problem.handle(), tstep);
+        if (!st_) throw std::runtime_error(std::string("rb_rk4_create: ") + rb_last_error());
+        if (logger_) {
+            logger_->st = st_;
+            rb_compat_check(rb_rk4_set_logging(st_, logger_->every, logger_->capacity), "rb_rk4_set_logging");
+        }
+    }
+    ~AutonomousRungeKuttaStepper() { rb_rk4_destroy(st_); }
+    void setTimeStep(double tstep) { rb_compat_check(rb_rk4_set_time_step(st_, tstep), "rb_rk4_set_time_step"); }
+    void setOptions(const RK4Options& o) { setTimeStep(o.initial_timestep); }
+    void initialize(T* devY0, bool onDevice = false) {
+        rb_compat_check(rb_rk4_initialize(st_, reinterpret_cast<rb_complex*>(devY0), onDevice), "rb_rk4_initialize");
+        if (logger_) rb_compat_check(rb_rk4_set_logging(st_, logger_->every, logger_->capacity), "rb_rk4_set_logging");
+    }
+    void runStep(int = 0) { rb_compat_check(rb_rk4_step(st_), "rb_rk4_step"); }
+    OdeSolverResult runEvolution(double startTime, double endTime) {
+        size_t n = 0;
+        rb_compat_check(rb_rk4_evolve(st_, startTime, endTime, &n), "rb_rk4_evolve");
+        return OdeSolverResult::ReachedEndTime;
+    }
+    void getState(T* host) { rb_compat_check(rb_rk4_get_state(st_, reinterpret_cast<rb_complex*>(host)), "rb_rk4_get_state"); }
+};
+
+// ---- the kernels the reference's tests launch with <<< >>> (same names, same signatures) ----------------------------------
+__global__ void createMKernel(double* A, const std_complex* const Z, const std_complex* const Zp, const std_complex* const Zpp,
+                              double rho, int n, size_t batchSize) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    size_t b = blockIdx.z;
+    if (b >= batchSize || k >= n || j >= n) return;
+    A[(size_t)k + (size_t)j * n + b * (size_t)n * n] = rb_dev::M_entry<false>(
+        k, j, reinterpret_cast<const double2*>(Z) + b * n, reinterpret_cast<const double2*>(Zp) + b * n,
+        reinterpret_cast<const double2*>(Zpp) + b * n, rho, 0.0, true);
+}
+
+__global__ void createFiniteDepthMKernel(double* A, const std_complex* const Z, const std_complex* const Zp,
+                                         const std_complex* const Zpp, double h, int n, size_t batchSize,
+                                         bool infinite_depth = false) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    size_t b = blockIdx.z;
+    if (b >= batchSize || k >= n || j >= n) return;
+    A[(size_t)k + (size_t)j * n + b * (size_t)n * n] = rb_dev::M_entry<true>(
+        k, j, reinterpret_cast<const double2*>(Z) + b * n, reinterpret_cast<const double2*>(Zp) + b * n,
+        reinterpret_cast<const double2*>(Zpp) + b * n, 0.0, h, infinite_depth);
+}
+
+__global__ void createVelocityMatrices(const std_complex* Z, const std_complex* Zp, const std_complex* Zpp, int N,
+                                       std_complex* out1, std_complex* out2, bool lower = true, size_t batchSize = 1) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    size_t b = blockIdx.z;
+    if (b >= batchSize || k >= N || j >= N) return;
+    double2 v = rb_dev::V1_entry(k, j, reinterpret_cast<const double2*>(Z) + b * N, reinterpret_cast<const double2*>(Zp) + b * N,
+                                 reinterpret_cast<const double2*>(Zpp) + b * N, reinterpret_cast<double2*>(out2) + b * N, lower,
+                                 false, 0.0, true);
+    reinterpret_cast<double2*>(out1)[(size_t)k + (size_t)j * N + b * (size_t)N * N] = v;
+}
+
+__global__ void createHeliumVelocityMatrices(const std_complex* const Z, const std_complex* const Zp,
+                                             const std_complex* const Zpp, double h, int N, std_complex* const out1,
+                                             std_complex* const out2, bool lower, size_t batchSize,
+                                             bool infinite_depth = false) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    size_t b = blockIdx.z;
+    if (b >= batchSize || k >= N || j >= N) return;
+    double2 v = rb_dev::V1_entry(k, j, reinterpret_cast<const double2*>(Z) + b * N, reinterpret_cast<const double2*>(Zp) + b * N,
+                                 reinterpret_cast<const double2*>(Zpp) + b * N, reinterpret_cast<double2*>(out2) + b * N, lower,
+                                 true, h, infinite_depth);
+    reinterpret_cast<double2*>(out1)[(size_t)k + (size_t)j * N + b * (size_t)N * N] = v;
+}
+
+__global__ void compute_rhs_phi_expression(const std_complex* Z, const std_complex* V1, const std_complex* V2,
+                                           std_complex* result, double rho, int N) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        double Z_imag = Z[i].imag();
+        double V1_abs2 = V1[i].real() * V1[i].real() + V1[i].imag() * V1[i].imag();
+        double V2_abs2 = V2[i].real() * V2[i].real() + V2[i].imag() * V2[i].imag();
+        double V1_dot_V2 = V1[1].real() * V2[i].real() + V1[i].imag() * V2[i].imag();   // index 1: as in L/createM.cuh:104
+        result[i] = -(1 + rho) * Z_imag + 0.5 * V1_abs2 + 0.5 * rho * V2_abs2 - rho * V1_dot_V2;
+    }
+}
+
+__global__ void compute_rhs_helium_phi_expression(const std_complex* Z, const std_complex* V1, std_complex* result, double h,
+                                                  int N) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) {
+        double vdw = h / 3.0;
+        result[i] = vdw * pow(1.0 + Z[i].imag() / h, -3.0) - vdw + 0.5 * V1[i].real() * V1[i].real() +
+                    0.5 * V1[i].imag() * V1[i].imag();
+    }
+}

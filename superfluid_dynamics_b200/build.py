@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libroberts_b200.so")
-SOURCES = ["pair_kernels.cu", "spectral.cu", "dense_kernels.cu", "stepper_kernels.cu", "krylov_kernels.cu", "solver.cu"]
+SOURCES = ["pair_kernels.cu", "pair_kernels2.cu", "spectral.cu", "dense_kernels.cu", "stepper_kernels.cu", "krylov_kernels.cu", "solver.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "128"]
@@ -51,5 +51,23 @@ def build(force=False, verbose=True):
     return LIB
 
 
+def build_compat_test(verbose=True):
+    """tests/cpp/compat_test.cu: the reference's kernel tests written against include/cusuperhelium_compat.cuh."""
+    root = os.path.abspath(os.path.join(HERE, ".."))
+    src = os.path.join(root, "tests", "cpp", "compat_test.cu")
+    exe = os.path.join(LIBDIR, "compat_test")
+    deps = [src, os.path.join(root, "include", "cusuperhelium_compat.cuh"), os.path.join(root, "include", "roberts_b200.h"),
+            os.path.join(root, "include", "roberts_b200_device.cuh"), LIB]
+    if _stale(exe, deps):
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-lineinfo", "-std=c++17", "-I",
+               os.path.join(root, "include"), src, "-o", exe, "-L", LIBDIR, "-lroberts_b200", "-Xlinker", "-rpath=$ORIGIN",
+               "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_compat_test())

@@ -127,6 +127,22 @@ struct SweepArgs {
     double2* dphi;                   // dPhi/dt + 0 i -> rhs[BN .. 2BN)  (nullptr: separate kernel)
     double2* raw_out;                // RAW: S_k = sum_{j!=k} cot((z_k - z_j)/2) x_j
     CommView comm;                   // row sharding over GPUs (nranks == 1: off)
+    // persistent one-wave variant (sweep2_kernel): static schedule of row blocks, in-CTA source split, no global partials
+    int v2_RB;                       // rows per row block (multiple of 32 * R)
+    int v2_R;                        // rows per thread (1 or 2)
+    int v2_groups;                   // source groups per CTA; threads = (RB / R) * groups
+    int v2_spg;                      // sources per group per staged tile (power of two >= 32)
+    int v2_TS;                       // staged tile = groups * spg sources
+    int v2_bpm;                      // row blocks per batch member (of this rank's rows)
+    int v2_total_blocks;             // batch * bpm
+    int v2_row_begin, v2_row_end;    // this rank's rows [begin, end)
+    double* v2_rnorm_part;           // [total_blocks] residual sums per row block
+    unsigned int* v2_ticket;         // one counter, zero on entry, reset on exit
+};
+
+struct Sweep2Launch {
+    int grid = 0, threads = 0;
+    size_t smem = 0;
 };
 
 // ---- launch wrappers (each defined in the .cu named in the comment) -----------------------
@@ -134,6 +150,8 @@ struct SweepArgs {
 void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int batch, int ncell, int physics,
                      double rhoM, double depth, int finite_image, int use_local, cudaStream_t st);
 void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st);
+// pair_kernels2.cu
+void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st);
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st);
 void launch_advance_counter(int* counter, cudaStream_t st);

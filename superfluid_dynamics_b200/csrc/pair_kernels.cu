@@ -305,10 +305,37 @@ __device__ __forceinline__ void tile_accumulate(const SrcEntry* __restrict__ sh,
     }
 }
 
+// Solver sweeps need only Re(Zp_k T_k).  Away from the diagonal (no cell-local coordinates, no j == k) the numerator
+//   Re(Zp_k F_j conj(E_k - E_j)) = Re(A_k F_j) - Re(Zp_k) g_j ,   A_k = Zp_k conj(E_k),  g_j = x_j |E_j|^2  (real)
+// costs 3 instructions instead of 4 + 2: 11 FP64-pipe instructions per pair.  The cancellation between the two terms is
+// |E|/|E_k - E_j| <= 1/(cell spacing) ~ 40 (far tiles only), i.e. harmless.
+__device__ __forceinline__ void tile_accumulate_real(const SrcEntry* __restrict__ sh, const double* __restrict__ sg, int tile,
+                                                     const double2 (&ek)[kRowsPerThread], const double2 (&Ak)[kRowsPerThread],
+                                                     const double (&Gre)[kRowsPerThread], double (&accs)[kRowsPerThread]) {
+#pragma unroll 4
+    for (int s = 0; s < tile; ++s) {
+        const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
+        const double2 f = *reinterpret_cast<const double2*>(&sh[s].fr);
+        const double gj = sg[s];
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+            double dr = ek[r].x - e.x;
+            double di = ek[r].y - e.y;
+            double n2 = fma(di, di, dr * dr);
+            double inv = fast_rcp(n2);
+            double t1 = fma(Ak[r].y, f.y, Gre[r] * gj);      // A.im f.im + Re(Zp) g
+            double num = fma(Ak[r].x, f.x, -t1);              // Re(A F) - Re(Zp) g
+            accs[r] = fma(num, inv, accs[r]);
+        }
+    }
+}
+
 template <int MODE, bool IMAGE>
 __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a) {
     __shared__ SrcEntry sh[kCell];
     __shared__ SrcEntry shI[IMAGE ? kCell : 1];
+    __shared__ double shg[kCell];
+    constexpr bool REALPATH = (MODE == kSweepMV) && !IMAGE;   // far tiles of a solver sweep: 11-instruction real-part form
     __shared__ double sred[kSweepThreads];
     __shared__ unsigned int s_ticket;
 
@@ -327,14 +354,24 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 
     int krow[kRowsPerThread];
     int lrow[kRowsPerThread];
-    double2 acc[kRowsPerThread], accI[kRowsPerThread], ekG[kRowsPerThread];
+    double2 acc[kRowsPerThread], accI[kRowsPerThread], ekG[kRowsPerThread], Ak[kRowsPerThread], zpk[kRowsPerThread];
+    double accs[kRowsPerThread], Gre[kRowsPerThread];
 #pragma unroll
     for (int r = 0; r < kRowsPerThread; ++r) {
         lrow[r] = t + r * kSweepThreads;
         krow[r] = cellK * kCell + lrow[r];
         acc[r] = make_double2(0.0, 0.0);
         accI[r] = make_double2(0.0, 0.0);
+        accs[r] = 0.0;
         ekG[r] = krow[r] < N ? EG[krow[r]] : make_double2(3.0e150, 0.0);
+        zpk[r] = make_double2(0.0, 0.0);
+        Ak[r] = make_double2(0.0, 0.0);
+        Gre[r] = 0.0;
+        if (REALPATH && krow[r] < N) {
+            zpk[r] = a.g.Zp[boff + krow[r]];
+            Ak[r] = make_double2(zpk[r].x * ekG[r].x + zpk[r].y * ekG[r].y, zpk[r].y * ekG[r].x - zpk[r].x * ekG[r].y);   // Zp conj(E_k)
+            Gre[r] = zpk[r].x;
+        }
     }
 
     const int tile = a.tile;
@@ -361,6 +398,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                     double2 g = EG[j];
                     e.p = g.x; e.q = g.y;
                     e.fr = xj * g.x; e.fi = xj * g.y;
+                    if (REALPATH) shg[s] = xj * (g.x * g.x + g.y * g.y);
                 }
                 sh[s] = e;
                 if (IMAGE) {
@@ -372,6 +410,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
             } else {
                 e.p = 1.0e150; e.q = 0.0; e.fr = 0.0; e.fi = 0.0;   // contributes exactly 0
                 sh[s] = e;
+                if (REALPATH) shg[s] = 0.0;
                 if (IMAGE) shI[s] = e;
             }
         }
@@ -387,6 +426,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
         }
         __syncthreads();
         if (dist == 0) tile_accumulate<true>(sh, tile, ek, sd, acc);
+        else if (REALPATH && !near) tile_accumulate_real(sh, shg, tile, ek, Ak, Gre, accs);
         else           tile_accumulate<false>(sh, tile, ek, sd, acc);
         if (IMAGE) tile_accumulate<false>(shI, tile, ekG, sd, accI);
     }
@@ -396,6 +436,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 #pragma unroll
     for (int r = 0; r < kRowsPerThread; ++r) {
         if (krow[r] < N) {
+            if (REALPATH) acc[r] = make_double2(zpk[r].x * acc[r].x - zpk[r].y * acc[r].y + accs[r], 0.0);   // Re(Zp T) of this chunk
             a.partial[pbase + krow[r]] = acc[r];
             if (IMAGE) a.partial_img[pbase + krow[r]] = accI[r];
         }
@@ -416,16 +457,29 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
         T[r] = make_double2(0.0, 0.0);
         TI[r] = make_double2(0.0, 0.0);
     }
-    for (int c = 0; c < a.nchunks; ++c) {
-        const size_t pb = ((size_t)bm * a.nchunks + c) * N;
+    {
+        // independent loads are issued in batches of 8 (memory-level parallelism), the additions stay in chunk order
+        constexpr int kBatch = IMAGE ? 4 : 8;
+        const size_t cstride = (size_t)N;
+        const double2* pbase0 = a.partial + (size_t)bm * a.nchunks * N;
+        const double2* ibase0 = IMAGE ? a.partial_img + (size_t)bm * a.nchunks * N : nullptr;
+        for (int c0 = 0; c0 < a.nchunks; c0 += kBatch) {
+            double2 v[kRowsPerThread][kBatch], vi[kRowsPerThread][kBatch];
 #pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
-            if (krow[r] < N) {
-                double2 v = ldcg_d2(a.partial + pb + krow[r]);
-                T[r].x += v.x; T[r].y += v.y;
-                if (IMAGE) {
-                    double2 w = ldcg_d2(a.partial_img + pb + krow[r]);
-                    TI[r].x += w.x; TI[r].y += w.y;
+            for (int u = 0; u < kBatch; ++u) {
+#pragma unroll
+                for (int r = 0; r < kRowsPerThread; ++r) {
+                    const bool ok = (c0 + u) < a.nchunks && krow[r] < N;
+                    v[r][u] = ok ? ldcg_d2(pbase0 + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
+                    if (IMAGE) vi[r][u] = ok ? ldcg_d2(ibase0 + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+#pragma unroll
+                for (int r = 0; r < kRowsPerThread; ++r) {
+                    T[r].x += v[r][u].x; T[r].y += v[r][u].y;
+                    if (IMAGE) { TI[r].x += vi[r][u].x; TI[r].y += vi[r][u].y; }
                 }
             }
         }
@@ -443,8 +497,8 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                 double2 zp = a.g.Zp[o];
                 double Ar = (sumx - xk) + 2.0 * T[r].x;
                 double Ai = 2.0 * T[r].y;
-                // Im(Zp * S) with S = i A  ->  Re(Zp A)
-                double Kx = a.cK * (zp.x * Ar - zp.y * Ai);
+                // Im(Zp * S) with S = i A  ->  Re(Zp A);  the real-part path delivers T[r].x = Re(Zp T) directly
+                double Kx = REALPATH ? a.cK * fma(zp.x, sumx - xk, 2.0 * T[r].x) : a.cK * (zp.x * Ar - zp.y * Ai);
                 if (IMAGE) Kx -= inv4pi * (sumx + 2.0 * TI[r].x);   // -(1/4pi) Im(S_img), S_img = i (sumx + 2 T_img)
                 double Mx = fma(a.g.Mdiag[o], xk, Kx);
                 if (a.apply_only) {   // operator application for the Krylov solver: y = M x

@@ -74,8 +74,14 @@ struct rb_solver {
     int has_image = 0, use_local = 0, rhs_phi_kind = 0;
     bool matrix_free_solve = true;
 
-    // chunking of the sweep
+    // chunking of the tiled sweep (pair_kernels.cu)
     int tile = 256, tiles_per_chunk = 1, nchunks = 1;
+    // schedule of the persistent sweep (pair_kernels2.cu); used whenever there is no image sum
+    bool use_v2 = false;
+    int v2_RB = 0, v2_R = 0, v2_groups = 0, v2_spg = 0, v2_TS = 0, v2_bpm = 0, v2_total_blocks = 0;
+    Sweep2Launch v2l;
+    double* v2_rnorm_part = nullptr;
+    unsigned int* v2_ticket = nullptr;
 
     // device buffers
     double2* deriv = nullptr;      // [3][BN]: Zp | Zpp | PhiPrime(complex)
@@ -150,7 +156,7 @@ static void solver_free(rb_solver* s) {
                     s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
                     s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state, s->gm_V, s->gm_x, s->gm_t,
-                    s->gm_dev, s->gm_invP};
+                    s->gm_dev, s->gm_invP, s->v2_rnorm_part, s->v2_ticket};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
@@ -189,6 +195,83 @@ static void choose_chunking(rb_solver* s) {
 }
 
 static void set_stream(rb_solver* s, cudaStream_t st);
+
+// static schedule of the persistent sweep: row blocks of RB rows, (RB/R) x groups threads, staged tiles of groups*spg sources
+static void plan_sweep2(rb_solver* s) {
+    int nSM = 148;
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
+    const int N = s->N, B = s->batch;
+    const int row_begin = s->row_cell0 * kCell;
+    const int row_end = std::min(N, (s->row_cell0 + s->row_cells) * kCell);
+    const int rows = row_end - row_begin;
+    const long units32 = (long)B * ((rows + 31) / 32);
+    int R, RB;
+    if (units32 <= 2L * nSM) {
+        R = 1;
+        RB = 32;
+    } else {
+        R = 2;
+        const long units64 = (long)B * ((rows + 63) / 64);
+        long m = (units64 + nSM - 1) / nSM;
+        m = std::max(1L, std::min(8L, m));
+        m = std::min<long>(m, (rows + 63) / 64);
+        RB = 64 * (int)m;
+    }
+    RB = env_int("RB_V2_RB", RB);
+    R = env_int("RB_V2_R", R);
+    const int nrt = RB / R;
+    const int max_threads = R == 2 ? 896 : 1024;   // launch bounds of sweep2_kernel<., R>
+    int G = 1;
+    while (nrt * G * 2 <= max_threads && G * 2 <= 32 && N / (G * 2) >= 32) G *= 2;
+    G = env_int("RB_V2_GROUPS", G);
+    const int threads = nrt * G;
+    int n_pow2 = 32;
+    while (n_pow2 < N) n_pow2 <<= 1;
+    const int ts_max = std::min(std::min(threads, 1024), std::max(G * 32, n_pow2));   // one staged entry per thread and tile
+    int spg = 256;
+    while (spg > 32 && G * spg > ts_max) spg >>= 1;
+    s->v2_RB = RB;
+    s->v2_R = R;
+    s->v2_groups = G;
+    s->v2_spg = spg;
+    s->v2_TS = G * spg;
+    s->v2_bpm = (rows + RB - 1) / RB;
+    s->v2_total_blocks = B * s->v2_bpm;
+    s->v2l.grid = std::min(s->v2_total_blocks, env_int("RB_V2_GRID", nSM));
+    s->v2l.threads = threads;
+    s->v2l.smem = (size_t)s->v2_TS * 32 * (s->use_local ? 2 : 1) + (size_t)threads * R * 16 + (size_t)threads * 8 +
+                  (size_t)s->v2_TS * 8;
+    if (s->v2_rnorm_part) cudaFree(s->v2_rnorm_part);
+    s->v2_rnorm_part = dmalloc<double>(s->v2_total_blocks);
+    if (!s->v2_ticket) {
+        s->v2_ticket = dmalloc<unsigned int>(1);
+        RB_CUDA(cudaMemset(s->v2_ticket, 0, sizeof(unsigned int)));
+    }
+    if (threads > max_threads || threads % 32 || s->v2_TS > threads || RB % (32 * R))
+        throw std::runtime_error("plan_sweep2: inconsistent schedule");
+    if (env_int("RB_VERBOSE", 0))
+        std::fprintf(stderr, "[roberts_b200] sweep2 plan: N=%d B=%d rows=[%d,%d) RB=%d R=%d groups=%d spg=%d TS=%d blocks=%d grid=%d threads=%d smem=%zu\n",
+                     N, B, row_begin, row_end, RB, R, G, spg, s->v2_TS, s->v2_total_blocks, s->v2l.grid, threads, s->v2l.smem);
+}
+
+// persistent kernel when its static schedule keeps (nearly) every SM busy or the problem is small; otherwise the tiled kernel,
+// whose source chunking balances mid-size problems better
+static void choose_sweep_kernel(rb_solver* s) {
+    int nSM = 148;
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
+    const int per_cta = (s->v2_total_blocks + s->v2l.grid - 1) / s->v2l.grid;
+    const double eff = (double)s->v2_total_blocks / ((double)per_cta * nSM);
+    bool v2 = !s->has_image && (eff >= 0.95 || (long)s->N * s->batch <= 4096);
+    int force = env_int("RB_SWEEP_V2", -1);
+    if (force >= 0) v2 = !s->has_image && force != 0;
+    s->use_v2 = v2;
+}
+
+static void sweep(rb_solver* s, const SweepArgs& a, int mode) {
+    if (s->use_v2) launch_sweep2(a, s->v2l, mode, s->stream);
+    else launch_sweep(a, mode, s->stream);
+    s->total_sweeps++;
+}
 
 static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     if (N < 2) throw std::runtime_error("rb_create: N must be >= 2");
@@ -328,6 +411,8 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     cufft_check(cufftPlanMany(&s->plan2, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 2 * batch), "cufftPlanMany(2B)");
     cufft_check(cufftPlanMany(&s->plan3, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 3 * batch), "cufftPlanMany(3B)");
     s->plans = true;
+    plan_sweep2(s);
+    choose_sweep_kernel(s);
     set_stream(s, nullptr);
     return up.release();
 }
@@ -406,6 +491,17 @@ static SweepArgs base_args(rb_solver* s, const double2* Z) {
     a.expansion_order = s->props.expansion_order;
     a.bnorm_part = s->bnorm_part;
     a.rnorm_part = s->rnorm_part;
+    a.v2_RB = s->v2_RB;
+    a.v2_R = s->v2_R;
+    a.v2_groups = s->v2_groups;
+    a.v2_spg = s->v2_spg;
+    a.v2_TS = s->v2_TS;
+    a.v2_bpm = s->v2_bpm;
+    a.v2_total_blocks = s->v2_total_blocks;
+    a.v2_row_begin = s->row_cell0 * kCell;
+    a.v2_row_end = std::min(s->N, (s->row_cell0 + s->row_cells) * kCell);
+    a.v2_rnorm_part = s->v2_rnorm_part;
+    a.v2_ticket = s->v2_ticket;
     return a;
 }
 
@@ -417,8 +513,7 @@ static void launch_mv(rb_solver* s, const SweepArgs& base, int i, int skip) {
     a.xsum_part_out = s->xsum_part[(i + 1) & 1];
     a.out_buf = (i + 1) & 1;
     a.skip_if_done = skip;
-    launch_sweep(a, kSweepMV, s->stream);
-    s->total_sweeps++;
+    sweep(s, a, kSweepMV);
     if (s->comm.nranks > 1)
         launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, s->bnorm_part, s->ncell, a.tol2, a.max_iters, s->stream);
 }
@@ -449,8 +544,7 @@ static void apply_M(rb_solver* s, const SweepArgs& base, const double* x) {
     a.apply_only = 1;
     a.skip_if_done = 0;
     a.out_buf = 1;
-    launch_sweep(a, kSweepMV, st);
-    s->total_sweeps++;
+    sweep(s, a, kSweepMV);
     if (s->comm.nranks > 1) launch_comm_wait(s->comm, s->ctrl, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
 }
 
@@ -661,8 +755,7 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
     a.vel_upper = s->vel_upper;
     a.rhs_phi_kind = s->rhs_phi_kind;
     a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
-    launch_sweep(a, kSweepVEL, st);
-    s->total_sweeps++;
+    sweep(s, a, kSweepVEL);
     if (s->comm.nranks > 1) {
         launch_comm_wait(s->comm, s->ctrl, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
         if (user_out) {
@@ -1084,7 +1177,7 @@ int rb_cotangent_sum(rb_solver* s, const rb_complex* Z_dev, const double* x_dev,
     a.x = x_dev;
     a.xsum_part = s->xsum_a;
     a.raw_out = (double2*)S_dev;
-    launch_sweep(a, kSweepRAW, s->stream);
+    sweep(s, a, kSweepRAW);
     RB_CATCH
 }
 
@@ -1295,7 +1388,9 @@ int rb_comm_init(rb_solver* s, int rank, int nranks, const char* handles) {
     s->row_cell0 = rows[0] / kCell;
     s->row_cells = (rows[1] - rows[0] + kCell - 1) / kCell;
     if (s->row_cells < 1) throw std::runtime_error("rb_comm_init: this rank owns no rows");
-    // the sweep's grid now covers the local rows only: re-balance the source chunking and the partial workspace
+    // the sweep's grid now covers the local rows only: re-balance the schedules and the partial workspace
+    plan_sweep2(s);
+    choose_sweep_kernel(s);
     choose_chunking(s);
     cudaFree(s->partial);
     s->partial = dmalloc<double2>((size_t)s->nchunks * s->BN);
@@ -1325,6 +1420,9 @@ int rb_comm_destroy(rb_solver* s) {
     s->comm.peer_base[0] = s->arena;
     s->row_cell0 = 0;
     s->row_cells = s->ncell;
+    plan_sweep2(s);
+    choose_sweep_kernel(s);
+    choose_chunking(s);
     RB_CATCH
 }
 

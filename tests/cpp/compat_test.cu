@@ -1,0 +1,209 @@
+// compat_test.cu -- the reference's own kernel tests, written against the reference's class / kernel names as provided by
+// include/cusuperhelium_compat.cuh, linked with libroberts_b200.so.  Fixtures and tolerances follow
+// CuSuperHelium.Tests/MatrixMTests.cuh (Kernels.TwoByTwoMMatrix :160-223, Kernels.MMatrixKernel :225-282, Kernels.Velocities
+// :396-468, Kernels.ZPhiDerivatives :477-607, Kernels.RhsPhi :748-819) and the App's stepper usage (CuSuperHelium.App/kernel.cu:85-96).
+// Prints one line per test and exits non-zero on any failure.  Needs a GPU.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <vector>
+
+#include "cusuperhelium_compat.cuh"
+
+using cd = std::complex<double>;
+static int failures = 0;
+#define EXPECT_NEAR(a, b, tol, what)                                                            \
+    do {                                                                                        \
+        if (!(std::fabs((a) - (b)) <= (tol))) {                                                 \
+            if (failures < 20) std::printf("  FAIL %s: %.17g vs %.17g\n", what, (double)(a), (double)(b)); \
+            ++failures;                                                                         \
+        }                                                                                       \
+    } while (0)
+
+static double X(double j, double h, double w, double t) { return j - h * std::sin(j - w * t); }
+static double Y(double j, double h, double w, double t) { return h * std::cos(j - w * t); }
+static double Xp(double j, double h, double w, double t) { return 1 - h * std::cos(j - w * t); }
+static double Yp(double j, double h, double w, double t) { return -h * std::sin(j - w * t); }
+static double Xpp(double j, double h, double w, double t) { return h * std::sin(j - w * t); }
+static double Ypp(double j, double h, double w, double t) { return -h * std::cos(j - w * t); }
+static double PhiF(double j, double h, double w, double t, double rho) { return h * (1 + rho) * w * std::sin(j - w * t); }
+
+static void prepareZPhi(std::vector<cd>& Z, std::vector<cd>& Phi, std::vector<cd>& Zp, std::vector<cd>& Zpp, std::vector<cd>& PhiP,
+                        double h, double w, double t, double rho, int N) {
+    for (int i = 0; i < N; i++) {
+        double j = 2 * PI_d * i / (double)N, s = 2.0 * PI_d / N;
+        Z[i] = cd(X(j, h, w, t), Y(j, h, w, t));
+        Phi[i] = PhiF(j, h, w, t, rho);
+        Zp[i] = cd(Xp(j, h, w, t) * s, Yp(j, h, w, t) * s);
+        Zpp[i] = cd(Xpp(j, h, w, t) * s * s, Ypp(j, h, w, t) * s * s);
+        PhiP[i] = h * (1.0 + rho) * w * std::cos(j - w * t) * s;
+    }
+}
+
+template <typename T>
+static T* toDevice(const std::vector<T>& v) {
+    T* d;
+    cudaMalloc(&d, v.size() * sizeof(T));
+    cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
+static void test_matrices(int N, double t) {
+    const double h = 0.5, w = 10, rho = 0;
+    std::vector<cd> Z(N), Phi(N), Zp(N), Zpp(N), PhiP(N);
+    prepareZPhi(Z, Phi, Zp, Zpp, PhiP, h, w, t, rho, N);
+    auto* dZ = (std_complex*)toDevice(Z);
+    auto* dZp = (std_complex*)toDevice(Zp);
+    auto* dZpp = (std_complex*)toDevice(Zpp);
+    double* dM;
+    cudaMalloc(&dM, N * N * sizeof(double));
+    dim3 th(16, 16), bl((N + 15) / 16, (N + 15) / 16);
+    createMKernel<<<bl, th>>>(dM, dZ, dZp, dZpp, 0.0, N, 1);
+    cudaDeviceSynchronize();
+    std::vector<double> M(N * N);
+    cudaMemcpy(M.data(), dM, N * N * sizeof(double), cudaMemcpyDeviceToHost);
+    if (N == 2) {   // closed form, MatrixMTests.cuh:69-87
+        double th2 = std::sinh(2.0 * h) / (std::cosh(2.0 * h) + 1.0);
+        EXPECT_NEAR(M[0 + 0 * N], 0.5 - 0.25 * h / (1.0 - h), 1e-14, "M00");
+        EXPECT_NEAR(M[1 + 1 * N], 0.5 + 0.25 * h / (1.0 + h), 1e-14, "M11");
+        EXPECT_NEAR(M[1 + 0 * N], (h + 1) / 4.0 * th2, 1e-14, "M10");
+        EXPECT_NEAR(M[0 + 1 * N], (h - 1) / 4.0 * th2, 1e-14, "M01");
+    }
+    for (int i = 0; i < N; i++)       // host loop, MatrixMTests.cuh:89-115
+        for (int j = 0; j < N; j++) {
+            double e = (i == j) ? 0.5 * (1 + rho) + 0.25 * (1 - rho) / PI_d * std::imag(Zpp[j] / Zp[j])
+                                : 0.25 * (1.0 - rho) / PI_d * std::imag(Zp[i] / std::tan(0.5 * (Z[i] - Z[j])));
+            EXPECT_NEAR(M[i + j * N], e, 1e-14, "M host loop");
+        }
+    std_complex *dV1, *dV2;
+    cudaMalloc(&dV1, N * N * sizeof(std_complex));
+    cudaMalloc(&dV2, N * sizeof(std_complex));
+    createVelocityMatrices<<<bl, th>>>(dZ, dZp, dZpp, N, dV1, dV2, true);
+    cudaDeviceSynchronize();
+    std::vector<cd> V1(N * N), V2(N);
+    cudaMemcpy(V1.data(), dV1, N * N * sizeof(cd), cudaMemcpyDeviceToHost);
+    cudaMemcpy(V2.data(), dV2, N * sizeof(cd), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < N; i++)       // MatrixMTests.cuh:117-151
+        for (int j = 0; j < N; j++) {
+            cd e = (i == j) ? cd(0, -0.25 / PI_d) * Zpp[j] / (Zp[j] * Zp[j]) + 0.5 / Zp[j]
+                            : cd(0, -0.25 / PI_d) / std::tan(0.5 * (Z[i] - Z[j]));
+            EXPECT_NEAR(V1[i + j * N].real(), e.real(), 1e-12, "V1 re");
+            EXPECT_NEAR(V1[i + j * N].imag(), e.imag(), 1e-12, "V1 im");
+            if (i == j) {
+                cd e2 = cd(0, 0.5) / (PI_d * Zp[j]);
+                EXPECT_NEAR(V2[i].real(), e2.real(), 1e-12, "V2 re");
+                EXPECT_NEAR(V2[i].imag(), e2.imag(), 1e-12, "V2 im");
+            }
+        }
+    cudaFree(dZ); cudaFree(dZp); cudaFree(dZpp); cudaFree(dM); cudaFree(dV1); cudaFree(dV2);
+    std::printf("Kernels.M/Velocities N=%d: failures so far %d\n", N, failures);
+}
+
+static void test_zphi_derivatives() {
+    constexpr int N = 1024;
+    const double h = 0.5, w = 10, t = 0;
+    ProblemProperties properties;
+    properties.rho = 0.0;
+    std::vector<cd> Z(N), Phi(N), Zp(N), Zpp(N), PhiP(N);
+    prepareZPhi(Z, Phi, Zp, Zpp, PhiP, h, w, t, properties.rho, N);
+    auto* dZ = (std_complex*)toDevice(Z);
+    auto* dPhi = (std_complex*)toDevice(Phi);
+    std_complex *dZp, *dZpp, *dPhiP;
+    cudaMalloc(&dZp, N * sizeof(std_complex));
+    cudaMalloc(&dZpp, N * sizeof(std_complex));
+    cudaMalloc(&dPhiP, N * sizeof(std_complex));
+    ZPhiDerivative<N, 1> zPhiDerivative(properties);
+    zPhiDerivative.exec(dZ, dPhi, dZp, dPhiP, dZpp);
+    cudaDeviceSynchronize();
+    std::vector<cd> cZp(N), cZpp(N), cPhiP(N);
+    cudaMemcpy(cZp.data(), dZp, N * sizeof(cd), cudaMemcpyDeviceToHost);
+    cudaMemcpy(cZpp.data(), dZpp, N * sizeof(cd), cudaMemcpyDeviceToHost);
+    cudaMemcpy(cPhiP.data(), dPhiP, N * sizeof(cd), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < N; i++) {
+        EXPECT_NEAR(cZp[i].real(), Zp[i].real(), 1e-14, "Xprime");
+        EXPECT_NEAR(cZp[i].imag(), Zp[i].imag(), 1e-14, "Yprime");
+        EXPECT_NEAR(cZpp[i].real(), Zpp[i].real(), 1e-14, "Xpp");
+        EXPECT_NEAR(cZpp[i].imag(), Zpp[i].imag(), 1e-14, "Ypp");
+        EXPECT_NEAR(cPhiP[i].real(), PhiP[i].real(), 1e-14, "PhiPrime");
+    }
+    std::printf("Kernels.ZPhiDerivatives: failures so far %d\n", failures);
+}
+
+static void test_rhs_phi() {
+    const int N = 32;
+    const double w = 10.0, h = 0.5, t = 0.1;
+    std::vector<cd> Z(N), VL(N), VU(N, 0.0);
+    std::vector<double> e(N);
+    for (int i = 0; i < N; i++) {
+        double j = 2 * PI_d * i / (double)N;
+        double y = Y(i, h, w, t);
+        Z[i] = cd(X(j, h, w, t), y);
+        VL[i] = cd(2 * PI_d / N * Xp(j, h, w, t), 2 * PI_d / N * Yp(j, h, w, t));
+        e[i] = -y + 0.5 * std::norm(VL[i]);
+    }
+    auto* dZ = (std_complex*)toDevice(Z);
+    auto* dVL = (std_complex*)toDevice(VL);
+    auto* dVU = (std_complex*)toDevice(VU);
+    std_complex* dR;
+    cudaMalloc(&dR, N * sizeof(std_complex));
+    compute_rhs_phi_expression<<<1, 256>>>(dZ, dVL, dVU, dR, 0.0, N);
+    cudaDeviceSynchronize();
+    std::vector<cd> r(N);
+    cudaMemcpy(r.data(), dR, N * sizeof(cd), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < N; i++) {
+        EXPECT_NEAR(r[i].real(), e[i], 1e-14, "RhsPhi");
+        EXPECT_NEAR(r[i].imag(), 0.0, 1e-14, "RhsPhi imag");
+    }
+    std::printf("Kernels.RhsPhi: failures so far %d\n", failures);
+}
+
+static void test_stepper() {
+    // App pattern (CuSuperHelium.App/kernel.cu:85-96) on a deep-water wave: after t the profile is eps cos(x - t) + O(eps^2)
+    constexpr int N = 256;
+    const double eps = 1e-4, dt = 1e-2;
+    ProblemProperties properties;
+    properties.rho = 0.0;
+    WaterBoundaryProblem<N, 1> problem(properties);
+    BaseBoundaryIntegralCalculator<N, 1> integrator(properties, problem);
+    auto logger = std::make_shared<TrajectoryLogger<std_complex, 2 * N>>(10, 16);
+    AutonomousRungeKuttaStepper<std_complex, 2 * N> stepper(integrator, dt, logger);
+    RK4Options opts;
+    opts.initial_timestep = dt;
+    stepper.setOptions(opts);
+    std::vector<std_complex> y0(2 * N);
+    for (int i = 0; i < N; i++) {
+        double a = 2 * PI_d * i / N;
+        y0[i] = std_complex(a, eps * std::cos(a));
+        y0[N + i] = std_complex(eps * std::sin(a), 0.0);
+    }
+    stepper.initialize(y0.data(), false);
+    stepper.runEvolution(0.0, 1.0);
+    std::vector<std_complex> y(2 * N);
+    stepper.getState(y.data());
+    const double t = 1.0;
+    for (int i = 0; i < N; i++) EXPECT_NEAR(y[i].imag(), eps * std::cos(y[i].real() - t), 5 * eps * eps, "dispersion");
+    double* times; size_t nt;
+    logger->copyTimesToHost(&times, &nt);
+    EXPECT_NEAR((double)nt, 10.0, 0.0, "logged states");
+    if (nt == 10) EXPECT_NEAR(times[9], 1.0, 1e-12, "last logged time");
+    rb_free(times);
+    double ekin = integrator.kineticEnergy.getEnergy(), epot = integrator.potentialEnergy.getEnergy();
+    EXPECT_NEAR(ekin + epot, 0.5 * eps * eps, 0.02 * eps * eps, "energy of a linear wave = eps^2/2 per unit (g = 1, period 2 pi)/(2 pi)");
+    std::printf("Stepper (App pattern): failures so far %d, E = %.6e\n", failures, ekin + epot);
+}
+
+int main() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        std::printf("no CUDA device\n");
+        return 2;
+    }
+    test_matrices(2, 0.0);
+    test_matrices(4, 0.1);
+    test_matrices(8, 0.1);
+    test_zphi_derivatives();
+    test_rhs_phi();
+    test_stepper();
+    std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
+    return failures ? 1 : 0;
+}

@@ -160,6 +160,33 @@ def steprate():
             print(f"steprate N={N} order={order}: {steps / el:.1f} steps/s, {its:.2f} sweeps/solve, {stp.stats()}", flush=True)
 
 
+def tune():
+    """sweep time vs the CTA-count target of the chunking heuristic"""
+    for N in (4096, 16384, 65536):
+        for target in (148 * 4, 148 * 8, 148 * 16, 148 * 32, 148 * 64):
+            os.environ["RB_TARGET_CTAS"] = str(target)
+            props = api.ProblemProperties(rho=0.0)
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+            Z, Phi = ro.trochoid(N, 0.4)
+            ms, pairs = calc.benchSweep(T(ro.pack_state(Z, Phi)), 20)
+            print(f"tune N={N} target={target}: {ms * 1e3:.1f} us  {20 * pairs / (ms * 1e-3) / 1e12:.2f} TF", flush=True)
+    os.environ.pop("RB_TARGET_CTAS", None)
+
+
+def v2cmp():
+    """tiled (v1) vs persistent (v2) sweep"""
+    for N in (256, 1024, 4096, 8192, 16384, 32768, 65536):
+        for v2 in ("0", "1"):
+            os.environ["RB_SWEEP_V2"] = v2
+            os.environ["RB_VERBOSE"] = "1" if v2 == "1" else "0"
+            props = api.ProblemProperties(rho=0.0)
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+            Z, Phi = ro.trochoid(N, 0.4)
+            ms, pairs = calc.benchSweep(T(ro.pack_state(Z, Phi)), 50 if N <= 16384 else 10)
+            print(f"v2cmp N={N} v2={v2}: {ms * 1e3:.1f} us  {20 * pairs / (ms * 1e-3) / 1e12:.2f} TF", flush=True)
+    os.environ.pop("RB_SWEEP_V2", None); os.environ.pop("RB_VERBOSE", None)
+
+
 def speed():
     print("fp64 peak TFLOP/s", api.measure_fp64_peak())
     for N in (1024, 4096, 16384, 65536):

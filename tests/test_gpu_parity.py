@@ -454,3 +454,38 @@ def test_integrate_simulation_rk4_export(api):
     states, times = api.integrateSimulationRK4(init, sp, opts, N)
     assert states.shape == (10, 3 * N) and len(times) == 10
     assert np.allclose(states[-1], got, rtol=0, atol=1e-14)
+
+
+def test_cpp_compat_header_runs_reference_tests(api):
+    """tests/cpp/compat_test.cu: the reference's gtest fixtures through the reference's C++ names (cusuperhelium_compat.cuh)."""
+    import subprocess
+    from superfluid_dynamics_b200 import build
+    exe = build.build_compat_test(verbose=False)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASSED" in r.stdout
+
+
+def test_graph_rollback_when_recorded_sweeps_do_not_suffice(api):
+    """A steep wave needs more sweeps than the first recorded graph holds (24): the step must be rolled back and redone, and the
+    result must equal the run without graphs."""
+    import os
+    N, h, dt, steps = 256, 0.85, 1e-3, 6
+    Z, Phi = ro.trochoid(N, h)
+    y0 = ro.pack_state(Z, Phi)
+    props = api.ProblemProperties(rho=0.0)
+    res = {}
+    for no_graph in ("0", "1"):
+        os.environ["RB_NO_GRAPH"] = no_graph
+        try:
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+        finally:
+            os.environ.pop("RB_NO_GRAPH", None)
+        stp.initialize(y0, False)
+        stp.runSteps(steps)
+        res[no_graph] = (stp.getState(), stp.stats(), calc.solve_stats())
+    assert res["0"][1]["fallback_steps"] >= 1 and res["0"][1]["graph_launches"] >= steps
+    assert res["1"][1]["graph_launches"] == 0
+    assert res["0"][2]["converged"] and res["1"][2]["converged"]
+    assert rel(res["0"][0], res["1"][0]) <= 1e-12
