@@ -248,7 +248,8 @@ def run_native(args):
     achieved = F_PAIR * pairs / world / (sweep_ms * 1e-3) / 1e12
     it1 = calc.solve_stats()
     mv_per_rhs = (it1["total_iterations"] - it0["total_iterations"]) / max(1, it1["total_solves"] - it0["total_solves"])
-    sweeps_per_step = 4.0 * (mv_per_rhs + 1.0)
+    # all O(N^2) sweeps executed per step: solver sweeps (incl. the combined verify+velocity ones) + velocity-only sweeps
+    sweeps_per_step = (it1["total_iterations"] - it0["total_iterations"] + it1["velocity_sweeps"] - it0["velocity_sweeps"]) / args.steps
     roofline = {"bound": "fp64", "kernel": "rb::sweep_kernel<MV>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "measured live by this library's DFMA-only probe (MEASURED_PEAKS.json holds no FP64 figure); "
@@ -328,7 +329,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the N=4096 and one-call extras")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    # the stepper tunes the number of recorded sweeps and fills its 4-step stage history during the first steps: warm up past that
+    args.warmup = max(args.warmup, 12) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:

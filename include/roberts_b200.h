@@ -100,8 +100,9 @@ RB_API int rb_synchronize(rb_solver* s);
  * [3] volume flux, [4] volume sum(Y X').  Replaces EnergyBase::getEnergy x4 (L/Energies.cuh:229-235) + VolumeFlux. */
 RB_API int rb_energies(rb_solver* s, double out_host[5]);
 /* statistics: out[0] M*x applications of the last solve, [1] converged flag, [2] relative residual,
- * [3] M*x applications summed over all solves of this solver, [4] number of solves */
-RB_API int rb_solve_stats(rb_solver* s, double out_host[5]);
+ * [3] solver sweeps (M*x applications, including the combined verify+velocity sweeps) summed over all solves, [4] number of
+ * solves, [5] velocity-only sweeps */
+RB_API int rb_solve_stats(rb_solver* s, double out_host[6]);
 
 /* ---- spectral derivatives (L/Derivatives.cuh) ---- */
 /* ZPhiDerivative<N,B>::exec :311-384 */

@@ -161,10 +161,10 @@ class BaseBoundaryIntegralCalculator:
         return dict(kinetic=out[0], potential=out[1], surface=out[2], volume_flux=out[3], volume=out[4])
 
     def solve_stats(self):
-        out = (ctypes.c_double * 5)()
+        out = (ctypes.c_double * 6)()
         check(self.lib.rb_solve_stats(self.handle, out), "rb_solve_stats")
         return dict(iterations=int(out[0]), converged=bool(out[1]), residual=out[2], total_iterations=int(out[3]),
-                    total_solves=int(out[4]))
+                    total_solves=int(out[4]), velocity_sweeps=int(out[5]))
 
     # --- derivatives (ZPhiDerivative / FftDerivative) ---
     def zPhiDerivative(self, Z, Phi):

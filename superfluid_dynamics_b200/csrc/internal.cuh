@@ -120,6 +120,9 @@ struct SweepArgs {
     int apply_only;                  // MV sweeps: x_out = M x (no update, no convergence logic) -- the Krylov solver's operator
     int skip_if_done;                // MV sweeps: return at once when ctrl->done
     int out_buf;                     // MV sweeps: index (0/1) of the iterate buffer x_out lives in
+    int combined;                    // VEL sweeps: also evaluate r = b - M x from the same row sums, write x_out = x + omega r and
+                                     // take the convergence decision: "verify the iterate and produce its velocities in one pass"
+    int final_buf_on_done;           // buffer index recorded in ctrl->final_buf when this sweep declares convergence
     // VEL outputs
     const double2* aprime;           // da/dj (complex, imaginary part kept as the reference does)
     double2* vel_lower;              // u + i v   -> rhs[0 .. BN)
@@ -155,8 +158,8 @@ void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStre
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st);
 void launch_advance_counter(int* counter, cudaStream_t st);
-void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, const double* bnorm_part, int ncell,
-                      double tol2, int max_iters, cudaStream_t st);
+void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, int final_buf, const double* bnorm_part,
+                      int ncell, double tol2, int max_iters, cudaStream_t st);
 // spectral.cu
 void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, double2* out_phiper, int N, int batch,
                        double rho, double U, cudaStream_t st);

@@ -305,6 +305,70 @@ __device__ __forceinline__ void tile_accumulate(const SrcEntry* __restrict__ sh,
     }
 }
 
+// closing of a solver sweep (MV, or VEL in combined mode): per-cell sums, tickets, and the convergence decision by the last CTA
+__device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx, double sr, int bm, int cellK, double* sred,
+                                                   unsigned int* s_ticket) {
+    const int t = threadIdx.x;
+    sx = block_reduce_fixed<kSweepThreads>(sx, sred);
+    sr = block_reduce_fixed<kSweepThreads>(sr, sred);
+    if (a.comm.nranks > 1) __threadfence_system();   // this CTA's remote row stores before its ticket
+    __syncthreads();
+    if (t == 0) {
+        mirror_store(a.comm, a.xsum_part_out + (size_t)bm * a.ncell + cellK, sx);
+        a.rnorm_part[(size_t)bm * a.ncell + cellK] = sr;
+        if (a.comm.nranks > 1) __threadfence_system(); else __threadfence();
+        *s_ticket = atomicAdd(a.member_tickets + bm, 1u);
+    }
+    __syncthreads();
+    if (*s_ticket != (unsigned)(a.row_cells - 1)) return;
+    // ---- level 2: last row cell of this batch member ---------------------------------------
+    __threadfence();
+    double rn = block_sum_fixed<kSweepThreads>(a.rnorm_part + (size_t)bm * a.ncell + a.row_cell0, a.row_cells, sred);
+    if (a.comm.nranks > 1) {
+        // row-sharded: publish this rank's residual sum and signal; the decision is taken by comm_wait_kernel on every
+        // rank from the same numbers in the same order
+        if (t == 0) {
+            a.member_tickets[bm] = 0u;
+            double* slot = reinterpret_cast<double*>(a.comm.my_base + a.comm.off_rn) + a.out_buf * kMaxRanks + a.comm.rank;
+            mirror_store(a.comm, slot, rn);
+            __threadfence_system();
+            comm_signal(a.comm);
+        }
+        return;
+    }
+    double bn = block_sum_fixed<kSweepThreads>(a.bnorm_part + (size_t)bm * a.ncell, a.ncell, sred);
+    if (t == 0) {
+        a.member_tickets[bm] = 0u;
+        double rel2 = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
+        if (!(rel2 == rel2)) rel2 = 1e300;   // NaN -> "not converged"
+        atomicMax(&a.ctrl->max_rel2_bits, (unsigned long long)__double_as_longlong(rel2));
+        __threadfence();
+        unsigned int m = atomicAdd(&a.ctrl->members_done, 1u);
+        if (m == (unsigned)(a.batch - 1)) {
+            // ---- level 3: last member -> decide ------------------------------------------------
+            __threadfence();
+            unsigned long long bits = atomicAdd(&a.ctrl->max_rel2_bits, 0ull);
+            double worst = __longlong_as_double((long long)bits);
+            volatile SolveCtrl* c = a.ctrl;
+            int iters = c->iters + 1;
+            double prev = c->prev_rel2;
+            bool conv = worst <= a.tol2;
+            bool stagnated = iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
+            c->iters = iters;
+            c->rel2 = worst;
+            c->prev_rel2 = worst;
+            c->final_buf = a.final_buf_on_done;
+            if (conv || stagnated || iters >= a.max_iters) {
+                c->converged = (conv || stagnated) ? 1 : 0;
+                c->done = 1;
+            }
+            c->max_rel2_bits = 0ull;
+            c->members_done = 0u;
+            __threadfence();
+        }
+    }
+}
+
 // Solver sweeps need only Re(Zp_k T_k).  Away from the diagonal (no cell-local coordinates, no j == k) the numerator
 //   Re(Zp_k F_j conj(E_k - E_j)) = Re(A_k F_j) - Re(Zp_k) g_j ,   A_k = Zp_k conj(E_k),  g_j = x_j |E_j|^2  (real)
 // costs 3 instructions instead of 4 + 2: 11 FP64-pipe instructions per pair.  The cancellation between the two terms is
@@ -339,7 +403,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
     __shared__ double sred[kSweepThreads];
     __shared__ unsigned int s_ticket;
 
-    if (MODE == kSweepMV && a.skip_if_done) {
+    if ((MODE == kSweepMV || MODE == kSweepVEL) && a.skip_if_done) {
         if (*reinterpret_cast<volatile int*>(&a.ctrl->done)) return;
     }
     const int t = threadIdx.x;
@@ -526,68 +590,12 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
             }
             return;
         }
-        sx = block_reduce_fixed<kSweepThreads>(sx, sred);
-        sr = block_reduce_fixed<kSweepThreads>(sr, sred);
-        if (a.comm.nranks > 1) __threadfence_system();   // this CTA's remote row stores before its ticket
-        __syncthreads();
-        if (t == 0) {
-            mirror_store(a.comm, a.xsum_part_out + (size_t)bm * a.ncell + cellK, sx);
-            a.rnorm_part[(size_t)bm * a.ncell + cellK] = sr;
-            if (a.comm.nranks > 1) __threadfence_system(); else __threadfence();
-            s_ticket = atomicAdd(a.member_tickets + bm, 1u);
-        }
-        __syncthreads();
-        if (s_ticket != (unsigned)(a.row_cells - 1)) return;
-        // ---- level 2: last row cell of this batch member ---------------------------------------
-        __threadfence();
-        double rn = block_sum_fixed<kSweepThreads>(a.rnorm_part + (size_t)bm * a.ncell + a.row_cell0, a.row_cells, sred);
-        if (a.comm.nranks > 1) {
-            // row-sharded: publish this rank's residual sum and signal; the decision is taken by comm_wait_kernel on every
-            // rank from the same numbers in the same order
-            if (t == 0) {
-                a.member_tickets[bm] = 0u;
-                double* slot = reinterpret_cast<double*>(a.comm.my_base + a.comm.off_rn) + a.out_buf * kMaxRanks + a.comm.rank;
-                mirror_store(a.comm, slot, rn);
-                __threadfence_system();
-                comm_signal(a.comm);
-            }
-            return;
-        }
-        double bn = block_sum_fixed<kSweepThreads>(a.bnorm_part + (size_t)bm * a.ncell, a.ncell, sred);
-        if (t == 0) {
-            a.member_tickets[bm] = 0u;
-            double rel2 = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
-            if (!(rel2 == rel2)) rel2 = 1e300;   // NaN -> "not converged"
-            atomicMax(&a.ctrl->max_rel2_bits, (unsigned long long)__double_as_longlong(rel2));
-            __threadfence();
-            unsigned int m = atomicAdd(&a.ctrl->members_done, 1u);
-            if (m == (unsigned)(a.batch - 1)) {
-                // ---- level 3: last member -> decide ------------------------------------------------
-                __threadfence();
-                unsigned long long bits = atomicAdd(&a.ctrl->max_rel2_bits, 0ull);
-                double worst = __longlong_as_double((long long)bits);
-                volatile SolveCtrl* c = a.ctrl;
-                int iters = c->iters + 1;
-                double prev = c->prev_rel2;
-                bool conv = worst <= a.tol2;
-                bool stagnated = iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
-                c->iters = iters;
-                c->rel2 = worst;
-                c->prev_rel2 = worst;
-                c->final_buf = a.out_buf;
-                if (conv || stagnated || iters >= a.max_iters) {
-                    c->converged = (conv || stagnated) ? 1 : 0;
-                    c->done = 1;
-                }
-                c->max_rel2_bits = 0ull;
-                c->members_done = 0u;
-                __threadfence();
-            }
-        }
+        solver_sweep_close(a, sx, sr, bm, cellK, sred, &s_ticket);
         return;
     }
 
     if (MODE == kSweepVEL) {
+        double sx = 0.0, sr = 0.0;
 #pragma unroll
         for (int r = 0; r < kRowsPerThread; ++r) {
             if (krow[r] < N) {
@@ -619,7 +627,23 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                     }
                     mirror_store(a.comm, a.dphi + o, make_double2(d, 0.0));
                 }
+                if (a.combined) {
+                    // the same row sum verifies the iterate: r = b - M a, and prepares the next one in case it is needed
+                    double Ar = (sumx - ak) + 2.0 * T[r].x;
+                    double Ai = 2.0 * T[r].y;
+                    double Kx = a.cK * (zp.x * Ar - zp.y * Ai);
+                    if (IMAGE) Kx -= inv4pi * (sumx + 2.0 * TI[r].x);
+                    double res = a.g.b[o] - fma(a.g.Mdiag[o], ak, Kx);
+                    double xn = fma(a.omega, res, ak);
+                    mirror_store(a.comm, a.x_out + o, xn);
+                    sx += xn;
+                    sr += res * res;
+                }
             }
+        }
+        if (a.combined) {
+            solver_sweep_close(a, sx, sr, bm, cellK, sred, &s_ticket);
+            return;
         }
         if (a.comm.nranks > 1) {
             // the last row cell of this rank signals that its rows of k are in every arena
@@ -652,7 +676,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 // row-sharded runs: wait until every rank has signalled the current exchange; for a solver sweep also take the convergence
 // decision (identical on every rank: same residual sums, same order)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ctrl, int decide, int parity,
+__global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ctrl, int decide, int parity, int final_buf,
                                                         const double* __restrict__ bnorm_part, int ncell, double tol2,
                                                         int max_iters) {
     const int lane = threadIdx.x;
@@ -700,7 +724,7 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
         ctrl->iters = iters;
         ctrl->rel2 = worst;
         ctrl->prev_rel2 = worst;
-        ctrl->final_buf = parity;
+        ctrl->final_buf = final_buf;
         if (conv || stagnated || iters >= max_iters) {
             ctrl->converged = (conv || stagnated) ? 1 : 0;
             ctrl->done = 1;
@@ -708,9 +732,9 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
     }
 }
 
-void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, const double* bnorm_part, int ncell,
-                      double tol2, int max_iters, cudaStream_t st) {
-    comm_wait_kernel<<<1, 32, 0, st>>>(c, ctrl, decide, parity, bnorm_part, ncell, tol2, max_iters);
+void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, int final_buf, const double* bnorm_part,
+                      int ncell, double tol2, int max_iters, cudaStream_t st) {
+    comm_wait_kernel<<<1, 32, 0, st>>>(c, ctrl, decide, parity, final_buf, bnorm_part, ncell, tol2, max_iters);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }

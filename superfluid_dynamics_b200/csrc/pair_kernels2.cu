@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
     constexpr bool REALPATH = (MODE == kSweepMV);
     __shared__ unsigned int s_ticket;
 
-    if (MODE == kSweepMV && a.skip_if_done) {
+    if ((MODE == kSweepMV || MODE == kSweepVEL) && a.skip_if_done) {
         if (*reinterpret_cast<volatile int*>(&a.ctrl->done)) return;
     }
     int P2 = 1;
@@ -342,19 +342,25 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
                         }
                         mirror_store2(a.comm, a.dphi + o, make_double2(d, 0.0));
                     }
+                    if (a.combined) {   // verify the iterate with the same row sum: r = b - M a; next iterate in case it is needed
+                        double res = a.g.b[o] - fma(a.g.Mdiag[o], xk, a.cK * (zp.x * Ar - zp.y * Ai));
+                        mirror_store2(a.comm, a.x_out + o, fma(a.omega, res, xk));
+                        sr += res * res;
+                    }
                 } else {
                     a.raw_out[o] = make_double2(-Ai, Ar);
                 }
             }
         }
-        if (MODE == kSweepMV && !a.apply_only) {
+        if ((MODE == kSweepMV && !a.apply_only) || (MODE == kSweepVEL && a.combined)) {
             sr = block_sum_any(sr, sred, T, P2);
             if (t == 0) a.v2_rnorm_part[blk] = sr;
         }
     }
 
     // ---- end of this CTA's schedule: the last CTA of the launch closes the sweep ------------------------------------------------
-    const bool need_close = (MODE == kSweepMV && !a.apply_only) || a.comm.nranks > 1;
+    const bool solver_sweep = (MODE == kSweepMV && !a.apply_only) || (MODE == kSweepVEL && a.combined);
+    const bool need_close = solver_sweep || a.comm.nranks > 1;
     if (!need_close) return;
     if (a.comm.nranks > 1) __threadfence_system(); else __threadfence();
     __syncthreads();
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
     if (t == 0) *a.v2_ticket = 0u;
-    if (MODE != kSweepMV || a.apply_only) {
+    if (!solver_sweep) {
         if (t == 0) {
             __threadfence_system();
             comm_signal2(a.comm);
@@ -410,7 +416,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
         c->iters = iters;
         c->rel2 = worst;
         c->prev_rel2 = worst;
-        c->final_buf = a.out_buf;
+        c->final_buf = a.final_buf_on_done;
         if (conv || stagnated || iters >= a.max_iters) {
             c->converged = (conv || stagnated) ? 1 : 0;
             c->done = 1;

@@ -132,6 +132,8 @@ struct rb_solver {
     long long total_sweeps = 0;      // sweep kernels launched (including ones that skipped)
     long long sum_iters = 0;         // M*x applications actually performed, summed over solves
     long long num_solves = 0;
+    long long vel_sweeps = 0;        // velocity-only sweeps (the combined verify+velocity sweeps are counted in sum_iters)
+    bool combined_ok = true;         // RB_COMBINED=0 disables the combined sweep
 
     const double2* cur_Z = nullptr;
     const double2* cur_Phi = nullptr;
@@ -411,6 +413,7 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     cufft_check(cufftPlanMany(&s->plan2, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 2 * batch), "cufftPlanMany(2B)");
     cufft_check(cufftPlanMany(&s->plan3, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 3 * batch), "cufftPlanMany(3B)");
     s->plans = true;
+    s->combined_ok = env_int("RB_COMBINED", 1) != 0;
     plan_sweep2(s);
     choose_sweep_kernel(s);
     set_stream(s, nullptr);
@@ -512,10 +515,11 @@ static void launch_mv(rb_solver* s, const SweepArgs& base, int i, int skip) {
     a.xsum_part = s->xsum_part[i & 1];
     a.xsum_part_out = s->xsum_part[(i + 1) & 1];
     a.out_buf = (i + 1) & 1;
+    a.final_buf_on_done = (i + 1) & 1;
     a.skip_if_done = skip;
     sweep(s, a, kSweepMV);
     if (s->comm.nranks > 1)
-        launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, s->bnorm_part, s->ncell, a.tol2, a.max_iters, s->stream);
+        launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, a.final_buf_on_done, s->bnorm_part, s->ncell, a.tol2, a.max_iters, s->stream);
 }
 
 static void read_ctrl(rb_solver* s) {
@@ -545,7 +549,7 @@ static void apply_M(rb_solver* s, const SweepArgs& base, const double* x) {
     a.skip_if_done = 0;
     a.out_buf = 1;
     sweep(s, a, kSweepMV);
-    if (s->comm.nranks > 1) launch_comm_wait(s->comm, s->ctrl, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
+    if (s->comm.nranks > 1) launch_comm_wait(s->comm, s->ctrl, 0, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
 }
 
 // out = P^{-1} v  (FFT, divide by the flat-film symbol, inverse FFT); out may alias v
@@ -732,36 +736,28 @@ static void fft_derivative(rb_solver* s, const double2* in, double2* out, int se
     if (scaling != 1.0) launch_scale(out, scaling, s->BN, s->stream);
 }
 
-static void rhs(rb_solver* s, const double2* state, double2* out) {
-    const size_t BN = s->BN;
-    cudaStream_t st = s->stream;
-    vorticities(s, state);
-    const double2* Z = state;
-    fft_derivative(s, s->ac, s->aprime, 0, 2.0 * kPi / s->N);   // L/BaseBoundaryIntegrator.cuh:203
-    SweepArgs a = base_args(s, Z);
-    double2* user_out = nullptr;
+// arena redirection of the RHS output when sharded: rows arrive from the peers inside the arena only
+static double2* redirect_out(rb_solver* s, double2* out, double2** user_out) {
+    *user_out = nullptr;
     if (s->comm.nranks > 1) {
-        if (!s->rhs_phi_kind) throw std::runtime_error("row-sharded runs need a fused dPhi/dt (water with rho = 0, or helium without expansions / surface tension)");
+        if (!s->rhs_phi_kind)
+            throw std::runtime_error("row-sharded runs need a fused dPhi/dt (water with rho = 0, or helium without expansions / surface tension)");
         const char* p = reinterpret_cast<const char*>(out);
-        if (p < s->arena || p >= s->arena + s->arena_bytes) {   // rows arrive from the peers inside the arena only
-            user_out = out;
+        if (p < s->arena || p >= s->arena + s->arena_bytes) {
+            *user_out = out;
             out = s->kbuf[0];
         }
     }
-    a.x = s->a;
-    a.xsum_part = s->xsum_a;
-    a.aprime = s->aprime;
-    a.vel_lower = out;
-    a.vel_upper = s->vel_upper;
-    a.rhs_phi_kind = s->rhs_phi_kind;
-    a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
-    sweep(s, a, kSweepVEL);
-    if (s->comm.nranks > 1) {
-        launch_comm_wait(s->comm, s->ctrl, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
-        if (user_out) {
-            RB_CUDA(cudaMemcpyAsync(user_out, out, 2 * BN * sizeof(double2), cudaMemcpyDeviceToDevice, st));
-            out = user_out;
-        }
+    return out;
+}
+
+static void rhs_tail(rb_solver* s, const double2* state, double2* out, double2* user_out) {
+    const size_t BN = s->BN;
+    cudaStream_t st = s->stream;
+    const double2* Z = state;
+    if (user_out) {
+        RB_CUDA(cudaMemcpyAsync(user_out, out, 2 * BN * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+        out = user_out;
     }
     if (!s->rhs_phi_kind) {
         const rb_props& p = s->props;
@@ -777,6 +773,87 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
     if (s->props.compute_energies)
         launch_energies(Z, s->Zp(), state + BN, out, s->energies, s->N, s->props.physics == RB_WATER ? 0 : 1, s->props.rho,
                         s->props.U, s->props.depth, s->props.kappa, st);
+}
+
+// RHS inside a recorded step: the sweep that verifies an iterate (r = b - M a) also produces its velocities from the same row
+// sums, so a well-started solve costs two sweeps per RHS (one solver sweep + one combined sweep) instead of three.
+// Sequence: guess x0 | sweep: x1, r0 | for each further recorded sweep i: a' of x_i, combined sweep on x_i: velocities(x_i), r_i,
+// x_{i+1}; the first r_i within tolerance ends the solve with a = x_i (later sweeps skip themselves).
+static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
+    const size_t BN = s->BN;
+    cudaStream_t st = s->stream;
+    const double2* Z = state;
+    const double2* Phi = state + BN;
+    derivatives(s, Z, Phi);
+    Geometry g = make_geometry(s, Z);
+    launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
+                    s->use_local, st);
+    s->cur_Z = Z;
+    s->cur_Phi = Phi;
+    double2* user_out = nullptr;
+    out = redirect_out(s, out, &user_out);
+
+    const double* warm = nullptr;
+    if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
+    launch_guess(s->b, warm, s->hist, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell,
+                 st);
+    SweepArgs base = base_args(s, Z);
+    {   // sweep 0 can only improve the iterate (nothing has produced velocities yet): it never declares convergence
+        SweepArgs first = base;
+        first.tol2 = -1.0;
+        launch_mv(s, first, 0, 1);
+    }
+    for (int i = 1; i < s->fixed_sweeps; ++i) {
+        const double* xi = s->xbuf[i & 1];
+        launch_real_to_complex(xi, s->ac, (int)BN, st);
+        fft_derivative(s, s->ac, s->aprime, 0, 2.0 * kPi / s->N);   // L/BaseBoundaryIntegrator.cuh:201-203
+        SweepArgs a = base;
+        a.x = xi;
+        a.x_out = s->xbuf[(i + 1) & 1];
+        a.xsum_part = s->xsum_part[i & 1];
+        a.xsum_part_out = s->xsum_part[(i + 1) & 1];
+        a.out_buf = (i + 1) & 1;
+        a.final_buf_on_done = i & 1;      // the verified iterate is the INPUT of this sweep
+        a.combined = 1;
+        a.skip_if_done = 1;
+        a.aprime = s->aprime;
+        a.vel_lower = out;
+        a.vel_upper = s->vel_upper;
+        a.rhs_phi_kind = s->rhs_phi_kind;
+        a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
+        sweep(s, a, kSweepVEL);
+        if (s->comm.nranks > 1)
+            launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, a.final_buf_on_done, s->bnorm_part, s->ncell, a.tol2, a.max_iters, st);
+    }
+    launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, nullptr, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
+    s->have_prev_a = true;
+    rhs_tail(s, state, out, user_out);
+}
+
+static void rhs(rb_solver* s, const double2* state, double2* out) {
+    if (s->fixed_sweeps >= 2 && s->matrix_free_solve && !s->use_gmres && s->combined_ok) {
+        rhs_combined(s, state, out);
+        return;
+    }
+    const size_t BN = s->BN;
+    cudaStream_t st = s->stream;
+    vorticities(s, state);
+    const double2* Z = state;
+    fft_derivative(s, s->ac, s->aprime, 0, 2.0 * kPi / s->N);   // L/BaseBoundaryIntegrator.cuh:203
+    SweepArgs a = base_args(s, Z);
+    double2* user_out = nullptr;
+    out = redirect_out(s, out, &user_out);
+    a.x = s->a;
+    a.xsum_part = s->xsum_a;
+    a.aprime = s->aprime;
+    a.vel_lower = out;
+    a.vel_upper = s->vel_upper;
+    a.rhs_phi_kind = s->rhs_phi_kind;
+    a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
+    sweep(s, a, kSweepVEL);
+    s->vel_sweeps++;
+    if (s->comm.nranks > 1) launch_comm_wait(s->comm, s->ctrl, 0, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
+    rhs_tail(s, state, out, user_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -896,8 +973,10 @@ static void capture_graph(rb_stepper* st, int sweeps) {
 static size_t kernels_per_step(rb_solver* s, int sweeps) {
     // geometry path 4 + guess + sweeps + finish + (multiply, scale) + VEL + optional rhs_phi / energies, per stage; 3 stage updates,
     // final update, counter
-    size_t per_stage = 4 + 1 + (size_t)sweeps + 1 + 2 + 1 + (s->rhs_phi_kind ? 0 : 1) + (s->props.compute_energies ? 1 : 0);
-    if (s->comm.nranks > 1) per_stage += (size_t)sweeps + 1;   // wait kernels
+    // derivatives + geometry 4, guess, sweeps, per combined sweep (real->complex, multiply, scale), finish, optional dPhi/dt, energies
+    size_t per_stage = 4 + 1 + (size_t)sweeps + 3 * (size_t)(sweeps - 1) + 1 + (s->rhs_phi_kind ? 0 : 1) +
+                       (s->props.compute_energies ? 1 : 0);
+    if (s->comm.nranks > 1) per_stage += (size_t)sweeps;   // wait kernels
     return 4 * per_stage + 5;
 }
 
@@ -923,7 +1002,8 @@ static void stepper_step(rb_stepper* st) {
         return;
     }
     if (!st->graph_exec || st->graph_dt != st->dt || st->graph_y0 != st->y0) {
-        int sweeps = st->graph_sweeps > 0 ? st->graph_sweeps : std::min(s->props.max_iterations, 24);
+        int sweeps = st->graph_sweeps > 0 ? st->graph_sweeps : std::min(s->props.max_iterations, 16);
+        sweeps = std::max(sweeps, 2);
         capture_graph(st, sweeps);
     }
     RB_CUDA(cudaGraphLaunch(st->graph_exec, s->stream));
@@ -964,9 +1044,9 @@ static void stepper_step(rb_stepper* st) {
         s->last_converged = s->h_ctrl[3].converged;
         s->last_rel = std::sqrt(std::max(0.0, s->h_ctrl[3].rel2));
         // shrink the recorded sweep count when it has been clearly too large for a while (each skipped sweep costs a launch)
-        if (st->graph_sweeps - worst >= 4) {
+        if (st->graph_sweeps - worst >= 3) {
             if (++st->graph_hits_below >= 8) {
-                st->graph_sweeps = worst + 2;
+                st->graph_sweeps = worst + 1;
                 cudaGraphExecDestroy(st->graph_exec);
                 st->graph_exec = nullptr;
             }
@@ -1077,7 +1157,7 @@ int rb_energies(rb_solver* s, double out_host[5]) {
     RB_CATCH
 }
 
-int rb_solve_stats(rb_solver* s, double out_host[5]) {
+int rb_solve_stats(rb_solver* s, double out_host[6]) {
     RB_TRY
     if (s->matrix_free_solve && !s->use_gmres) read_ctrl(s);
     out_host[0] = s->last_iters;
@@ -1085,6 +1165,7 @@ int rb_solve_stats(rb_solver* s, double out_host[5]) {
     out_host[2] = s->last_rel;
     out_host[3] = (double)s->sum_iters;
     out_host[4] = (double)s->num_solves;
+    out_host[5] = (double)s->vel_sweeps;
     RB_CATCH
 }
 
