@@ -150,8 +150,9 @@ struct Sweep2Launch {
 
 // ---- launch wrappers (each defined in the .cu named in the comment) -----------------------
 // pair_kernels.cu
-void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int batch, int ncell, int physics,
-                     double rhoM, double depth, int finite_image, int use_local, cudaStream_t st);
+void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, int ncell, int physics,
+                     double rhoM, double depth, int finite_image, int use_local, int raw_derivs, double rho, double U,
+                     cudaStream_t st);
 void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st);
 // pair_kernels2.cu
 void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st);
@@ -166,6 +167,7 @@ void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, 
 void launch_spectral_multiply_zphi(const double2* hatZ, const double2* hatPhi, double2* out_d1z, double2* out_d2z,
                                    double2* out_d1phi, int N, int batch, cudaStream_t st);
 void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch, int second, cudaStream_t st);
+void launch_spectral_multiply_real(const double2* half, double2* out, int N, int batch, double scale, cudaStream_t st);
 void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int batch, double rho, double U, cudaStream_t st);
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st);
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,

@@ -122,8 +122,9 @@ __device__ __forceinline__ double2 local_coord(double2 z, double2 zc) {
 // ------------------------------------------------------------------------------------------------
 // geometry: everything that depends on the surface only (once per RHS, reused by every sweep)
 // ------------------------------------------------------------------------------------------------
-__global__ void geometry_kernel(Geometry g, const double2* __restrict__ phiprime_c, int N, int batch, int ncell, int physics,
-                                double rhoM, double depth, int finite_image, int use_local) {
+__global__ void geometry_kernel(Geometry g, double2* __restrict__ phiprime_c, int N, int batch, int ncell, int physics,
+                                double rhoM, double depth, int finite_image, int use_local, int raw_derivs, double rho,
+                                double U) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)N * batch) return;
     int b = (int)(tid / N);
@@ -132,6 +133,23 @@ __global__ void geometry_kernel(Geometry g, const double2* __restrict__ phiprime
     double2 z = Zb[i];
     double2 zp = g.Zp[tid];
     double2 zpp = g.Zpp[tid];
+    double2 php = phiprime_c ? phiprime_c[tid] : make_double2(0.0, 0.0);
+    if (raw_derivs) {
+        // the arrays hold the unscaled inverse transforms: apply 2 pi / N (squared for Z'') and put the linear parts back
+        // (finish_zphi_kernel of spectral.cu folded in; L/Derivatives.cuh:321-324, 374, 380-383)
+        const double s1 = 2.0 * kPi / N;
+        const double s2 = 4.0 * kPi * kPi / ((double)N * N);
+        zp = make_double2(zp.x * s1 + 2.0 * kPi / N, zp.y * s1);
+        zpp = make_double2(zpp.x * s2, zpp.y * s2);
+        g.Zp[tid] = zp;
+        g.Zpp[tid] = zpp;
+        if (phiprime_c) {
+            php.x *= s1;
+            php.y *= s1;
+            if (U != 0) php.x += -(1 + rho) * kPi * U / N;
+            phiprime_c[tid] = php;
+        }
+    }
 
     double s, c;
     sincos(z.x, &s, &c);
@@ -159,15 +177,16 @@ __global__ void geometry_kernel(Geometry g, const double2* __restrict__ phiprime
     g.V1diag[tid] = make_double2(q2.y * (0.25 / kPi) + hz.x, -q2.x * (0.25 / kPi) + hz.y);
     double2 iz = cdiv(make_double2(1.0 / (2.0 * kPi), 0.0), zp);
     g.V2[tid] = make_double2(-iz.y, iz.x);           // i/(2 pi Zp)   (:66)
-    if (phiprime_c) g.b[tid] = phiprime_c[tid].x;    // complex_to_real, L/BaseBoundaryIntegrator.cuh:299
+    if (phiprime_c) g.b[tid] = php.x;    // complex_to_real, L/BaseBoundaryIntegrator.cuh:299
 }
 
-void launch_geometry(const Geometry& g, const double2* phiprime_c, int N, int batch, int ncell, int physics, double rhoM,
-                     double depth, int finite_image, int use_local, cudaStream_t st) {
+void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, int ncell, int physics, double rhoM,
+                     double depth, int finite_image, int use_local, int raw_derivs, double rho, double U, cudaStream_t st) {
     size_t n = (size_t)N * batch;
     int threads = 128;
     geometry_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(g, phiprime_c, N, batch, ncell, physics, rhoM,
-                                                                                   depth, finite_image, use_local);
+                                                                                   depth, finite_image, use_local, raw_derivs,
+                                                                                   rho, U);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }

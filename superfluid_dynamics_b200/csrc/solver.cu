@@ -115,7 +115,7 @@ struct rb_solver {
     int* lu_info = nullptr;
     double2* scratch_state = nullptr;   // legacy host-vector exports
 
-    cufftHandle plan1 = 0, plan2 = 0, plan3 = 0;
+    cufftHandle plan1 = 0, plan2 = 0, plan3 = 0, plan_d2z = 0;
     bool plans = false;
 
     // warm start: stage-history ring attached by the stepper for the next solve (base == nullptr: none)
@@ -151,6 +151,7 @@ static void solver_free(rb_solver* s) {
         cufftDestroy(s->plan1);
         cufftDestroy(s->plan2);
         cufftDestroy(s->plan3);
+        cufftDestroy(s->plan_d2z);
     }
     for (int r = 0; r < kMaxRanks; ++r)
         if (s->peer_mapped[r]) cudaIpcCloseMemHandle(s->peer_mapped[r]);
@@ -412,6 +413,7 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     cufft_check(cufftPlanMany(&s->plan1, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, batch), "cufftPlanMany(B)");
     cufft_check(cufftPlanMany(&s->plan2, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 2 * batch), "cufftPlanMany(2B)");
     cufft_check(cufftPlanMany(&s->plan3, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 3 * batch), "cufftPlanMany(3B)");
+    cufft_check(cufftPlanMany(&s->plan_d2z, 1, n, nullptr, 1, N, nullptr, 1, N / 2 + 1, CUFFT_D2Z, batch), "cufftPlanMany(D2Z)");
     s->plans = true;
     s->combined_ok = env_int("RB_COMBINED", 1) != 0;
     plan_sweep2(s);
@@ -431,10 +433,11 @@ static void set_stream(rb_solver* s, cudaStream_t st) {
     cufft_check(cufftSetStream(s->plan1, st), "cufftSetStream");
     cufft_check(cufftSetStream(s->plan2, st), "cufftSetStream");
     cufft_check(cufftSetStream(s->plan3, st), "cufftSetStream");
+    cufft_check(cufftSetStream(s->plan_d2z, st), "cufftSetStream");
 }
 
 // ZPhiDerivative::exec into the solver's own buffers (Zp | Zpp | PhiPrime)
-static void derivatives(rb_solver* s, const double2* Z, const double2* Phi) {
+static void derivatives(rb_solver* s, const double2* Z, const double2* Phi, bool finish = true) {
     const size_t BN = s->BN;
     cudaStream_t st = s->stream;
     double2* zper = s->fwork;            // [0]
@@ -444,8 +447,12 @@ static void derivatives(rb_solver* s, const double2* Z, const double2* Phi) {
     // d1z -> Zp, d2z -> Zpp, d1phi -> PhiPc, then one inverse over the three
     launch_spectral_multiply_zphi(zper, phiper, s->Zp(), s->Zpp(), s->PhiPc(), s->N, s->batch, st);
     cufft_check(cufftExecZ2Z(s->plan3, (cufftDoubleComplex*)s->deriv, (cufftDoubleComplex*)s->deriv, CUFFT_INVERSE), "fft inv");
-    launch_finish_zphi(s->Zp(), s->Zpp(), s->PhiPc(), s->N, s->batch, s->props.rho, s->props.U, st);
+    // finish == false: the caller's geometry kernel applies the scaling and the linear parts (one launch less per RHS)
+    if (finish) launch_finish_zphi(s->Zp(), s->Zpp(), s->PhiPc(), s->N, s->batch, s->props.rho, s->props.U, st);
 }
+
+// derivatives + geometry of one RHS (everything that depends on the surface only)
+static void surface_stage(rb_solver* s, const double2* Z, const double2* Phi);
 
 static Geometry make_geometry(rb_solver* s, const double2* Z) {
     Geometry g;
@@ -462,6 +469,22 @@ static Geometry make_geometry(rb_solver* s, const double2* Z) {
     g.V2 = s->V2;
     g.b = s->b;
     return g;
+}
+
+static void surface_stage(rb_solver* s, const double2* Z, const double2* Phi) {
+    derivatives(s, Z, Phi, false);
+    Geometry g = make_geometry(s, Z);
+    launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
+                    s->use_local, 1, s->props.rho, s->props.U, s->stream);
+}
+
+// a' = (2 pi / N) D1(a) for the real vector a: D2Z, coefficient multiply with the scale folded in, inverse Z2Z
+// (L/BaseBoundaryIntegrator.cuh:201-203 does real_to_complex + Z2Z + multiply + Z2Z + scale: five launches)
+static void real_derivative(rb_solver* s, const double* x, double2* out) {
+    double2* half = s->fwork + 2 * s->BN;
+    cufft_check(cufftExecD2Z(s->plan_d2z, (cufftDoubleReal*)x, (cufftDoubleComplex*)half), "fft d2z");
+    launch_spectral_multiply_real(half, out, s->N, s->batch, 2.0 * kPi / s->N, s->stream);
+    cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)out, (cufftDoubleComplex*)out, CUFFT_INVERSE), "fft inv");
 }
 
 static SweepArgs base_args(rb_solver* s, const double2* Z) {
@@ -719,10 +742,7 @@ static void solve(rb_solver* s, const double2* Z) {
 static void vorticities(rb_solver* s, const double2* state) {
     const double2* Z = state;
     const double2* Phi = state + s->BN;
-    derivatives(s, Z, Phi);
-    Geometry g = make_geometry(s, Z);
-    launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
-                    s->use_local, s->stream);
+    surface_stage(s, Z, Phi);
     solve(s, Z);
     s->cur_Z = Z;
     s->cur_Phi = Phi;
@@ -784,10 +804,7 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     cudaStream_t st = s->stream;
     const double2* Z = state;
     const double2* Phi = state + BN;
-    derivatives(s, Z, Phi);
-    Geometry g = make_geometry(s, Z);
-    launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
-                    s->use_local, st);
+    surface_stage(s, Z, Phi);
     s->cur_Z = Z;
     s->cur_Phi = Phi;
     double2* user_out = nullptr;
@@ -805,8 +822,7 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     }
     for (int i = 1; i < s->fixed_sweeps; ++i) {
         const double* xi = s->xbuf[i & 1];
-        launch_real_to_complex(xi, s->ac, (int)BN, st);
-        fft_derivative(s, s->ac, s->aprime, 0, 2.0 * kPi / s->N);   // L/BaseBoundaryIntegrator.cuh:201-203
+        real_derivative(s, xi, s->aprime);
         SweepArgs a = base;
         a.x = xi;
         a.x_out = s->xbuf[(i + 1) & 1];
@@ -839,7 +855,7 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
     cudaStream_t st = s->stream;
     vorticities(s, state);
     const double2* Z = state;
-    fft_derivative(s, s->ac, s->aprime, 0, 2.0 * kPi / s->N);   // L/BaseBoundaryIntegrator.cuh:203
+    real_derivative(s, s->a, s->aprime);   // L/BaseBoundaryIntegrator.cuh:201-203
     SweepArgs a = base_args(s, Z);
     double2* user_out = nullptr;
     out = redirect_out(s, out, &user_out);
@@ -974,7 +990,7 @@ static size_t kernels_per_step(rb_solver* s, int sweeps) {
     // geometry path 4 + guess + sweeps + finish + (multiply, scale) + VEL + optional rhs_phi / energies, per stage; 3 stage updates,
     // final update, counter
     // derivatives + geometry 4, guess, sweeps, per combined sweep (real->complex, multiply, scale), finish, optional dPhi/dt, energies
-    size_t per_stage = 4 + 1 + (size_t)sweeps + 3 * (size_t)(sweeps - 1) + 1 + (s->rhs_phi_kind ? 0 : 1) +
+    size_t per_stage = 3 + 1 + (size_t)sweeps + (size_t)(sweeps - 1) + 1 + (s->rhs_phi_kind ? 0 : 1) +
                        (s->props.compute_energies ? 1 : 0);
     if (s->comm.nranks > 1) per_stage += (size_t)sweeps;   // wait kernels
     return 4 * per_stage + 5;
@@ -1252,7 +1268,8 @@ int rb_cotangent_sum(rb_solver* s, const rb_complex* Z_dev, const double* x_dev,
     const double2* Z = (const double2*)Z_dev;
     // geometry from the solver's current Zp/Zpp (diagonal terms are not used by the raw sum)
     Geometry g = make_geometry(s, Z);
-    launch_geometry(g, nullptr, s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, 0, s->use_local, s->stream);
+    launch_geometry(g, nullptr, s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, 0, s->use_local, 0, 0.0, 0.0,
+                    s->stream);
     launch_finish_solve(x_dev, x_dev, nullptr, nullptr, nullptr, s->xsum_a, HistoryRing(), s->N, s->batch, s->ncell, s->stream);
     SweepArgs a = base_args(s, Z);
     a.x = x_dev;
@@ -1542,10 +1559,7 @@ int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* m
     RB_TRY
     cudaStream_t st = s->stream;
     const double2* Z = (const double2*)state_dev;
-    derivatives(s, Z, Z + s->BN);
-    Geometry g = make_geometry(s, Z);
-    launch_geometry(g, s->PhiPc(), s->N, s->batch, s->ncell, s->props.physics, s->rhoM, s->props.depth, s->has_image,
-                    s->use_local, st);
+    surface_stage(s, Z, Z + s->BN);
     launch_guess(s->b, nullptr, HistoryRing(), s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch,
                  s->ncell, st);
     SweepArgs base = base_args(s, Z);

@@ -93,6 +93,33 @@ void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch
     count_launch();
 }
 
+// first derivative of a REAL sequence from its half spectrum (D2Z transform): the full coefficient array of the reference's
+// Z2Z path is rebuilt with c[N-i] = conj(c[i]); `scale` (2 pi / N) is folded into the coefficients
+__global__ void spectral_multiply_real_kernel(const double2* __restrict__ half, double2* __restrict__ out, int N, size_t total,
+                                              double scale) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= total) return;
+    const int nh = N / 2 + 1;
+    size_t b = tid / N;
+    int i = (int)(tid - b * N);
+    double2 c;
+    if (i < nh) {
+        c = half[b * nh + i];
+    } else {
+        c = half[b * nh + (N - i)];
+        c.y = -c.y;
+    }
+    double2 r = d1_coeff(c, i, N);
+    out[tid] = make_double2(r.x * scale, r.y * scale);
+}
+
+void launch_spectral_multiply_real(const double2* half, double2* out, int N, int batch, double scale, cudaStream_t st) {
+    size_t total = (size_t)N * batch;
+    spectral_multiply_real_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(half, out, N, total, scale);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 // scaling by 2 pi / N (resp. its square) and the linear parts put back (L/Derivatives.cuh:321-324, 374, 380-383)
 __global__ void finish_zphi_kernel(double2* __restrict__ Zp, double2* __restrict__ Zpp, double2* __restrict__ PhiP, int N,
                                    size_t total, double rho, double U) {
