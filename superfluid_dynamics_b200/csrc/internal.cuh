@@ -168,6 +168,10 @@ void launch_spectral_multiply_zphi(const double2* hatZ, const double2* hatPhi, d
                                    double2* out_d1phi, int N, int batch, cudaStream_t st);
 void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch, int second, cudaStream_t st);
 void launch_spectral_multiply_real(const double2* half, double2* out, int N, int batch, double scale, cudaStream_t st);
+void launch_fft_zphi(const double2* Z, const double2* Phi, double2* Zp, double2* Zpp, double2* PhiP, int N, int logN, int batch,
+                     const double2* tw, double rho, double U, cudaStream_t st);
+void launch_fft_real_derivative(const double* x, double2* out, int N, int logN, int batch, const double2* tw, double scale,
+                                const SolveCtrl* ctrl, cudaStream_t st);
 void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int batch, double rho, double U, cudaStream_t st);
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st);
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,

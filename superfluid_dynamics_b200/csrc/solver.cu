@@ -116,6 +116,10 @@ struct rb_solver {
     double2* scratch_state = nullptr;   // legacy host-vector exports
 
     cufftHandle plan1 = 0, plan2 = 0, plan3 = 0, plan_d2z = 0;
+    // shared-memory FFT derivatives (small power-of-two N, launch-bound regime): twiddle table exp(-2 pi i k / N), k < N/2
+    bool own_fft = false;
+    int logN = 0;
+    double2* fft_tw = nullptr;
     bool plans = false;
 
     // warm start: stage-history ring attached by the stepper for the next solve (base == nullptr: none)
@@ -159,7 +163,7 @@ static void solver_free(rb_solver* s) {
                     s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
                     s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state, s->gm_V, s->gm_x, s->gm_t,
-                    s->gm_dev, s->gm_invP, s->v2_rnorm_part, s->v2_ticket};
+                    s->gm_dev, s->gm_invP, s->v2_rnorm_part, s->v2_ticket, s->fft_tw};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
@@ -415,6 +419,23 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     cufft_check(cufftPlanMany(&s->plan3, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 3 * batch), "cufftPlanMany(3B)");
     cufft_check(cufftPlanMany(&s->plan_d2z, 1, n, nullptr, 1, N, nullptr, 1, N / 2 + 1, CUFFT_D2Z, batch), "cufftPlanMany(D2Z)");
     s->plans = true;
+    // the one-CTA radix-2 transform is shared-memory-bandwidth bound (~1.3k cycles per pass at N = 4096): it beats the library's
+    // three launches only in the launch-bound regime (measured: faster at N <= 1024, slower at N = 4096)
+    const int own_fft_max = env_int("RB_OWN_FFT_MAX", 1024);
+    if ((N & (N - 1)) == 0 && N >= 4 && N <= std::min(own_fft_max, 4096) && (long)N * batch <= 4096 && env_int("RB_OWN_FFT", 1)) {
+        s->own_fft = true;
+        while ((1 << s->logN) < N) s->logN++;
+        // per-pass tables: exp(-i pi k / Ns), k < Ns, at offset Ns - 1 (see stage_twiddles in spectral.cu)
+        std::vector<double2> tw(N);
+        for (int Ns = 1; Ns < N; Ns <<= 1)
+            for (int k = 0; k < Ns; ++k) {
+                double ang = -kPi * (double)k / (double)Ns;
+                tw[Ns - 1 + k] = make_double2(std::cos(ang), std::sin(ang));
+            }
+        tw[N - 1] = make_double2(0.0, 0.0);
+        s->fft_tw = dmalloc<double2>(N);
+        RB_CUDA(cudaMemcpy(s->fft_tw, tw.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
+    }
     s->combined_ok = env_int("RB_COMBINED", 1) != 0;
     plan_sweep2(s);
     choose_sweep_kernel(s);
@@ -440,6 +461,11 @@ static void set_stream(rb_solver* s, cudaStream_t st) {
 static void derivatives(rb_solver* s, const double2* Z, const double2* Phi, bool finish = true) {
     const size_t BN = s->BN;
     cudaStream_t st = s->stream;
+    if (s->own_fft) {
+        launch_fft_zphi(Z, Phi, s->Zp(), s->Zpp(), s->PhiPc(), s->N, s->logN, s->batch, s->fft_tw, s->props.rho, s->props.U, st);
+        if (finish) launch_finish_zphi(s->Zp(), s->Zpp(), s->PhiPc(), s->N, s->batch, s->props.rho, s->props.U, st);
+        return;
+    }
     double2* zper = s->fwork;            // [0]
     double2* phiper = s->fwork + BN;     // [1]
     launch_sub_linear(Z, Phi, zper, phiper, s->N, s->batch, s->props.rho, s->props.U, st);
@@ -480,7 +506,11 @@ static void surface_stage(rb_solver* s, const double2* Z, const double2* Phi) {
 
 // a' = (2 pi / N) D1(a) for the real vector a: D2Z, coefficient multiply with the scale folded in, inverse Z2Z
 // (L/BaseBoundaryIntegrator.cuh:201-203 does real_to_complex + Z2Z + multiply + Z2Z + scale: five launches)
-static void real_derivative(rb_solver* s, const double* x, double2* out) {
+static void real_derivative(rb_solver* s, const double* x, double2* out, const SolveCtrl* skip_ctrl = nullptr) {
+    if (s->own_fft) {
+        launch_fft_real_derivative(x, out, s->N, s->logN, s->batch, s->fft_tw, 2.0 * kPi / s->N, skip_ctrl, s->stream);
+        return;
+    }
     double2* half = s->fwork + 2 * s->BN;
     cufft_check(cufftExecD2Z(s->plan_d2z, (cufftDoubleReal*)x, (cufftDoubleComplex*)half), "fft d2z");
     launch_spectral_multiply_real(half, out, s->N, s->batch, 2.0 * kPi / s->N, s->stream);
@@ -822,7 +852,7 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     }
     for (int i = 1; i < s->fixed_sweeps; ++i) {
         const double* xi = s->xbuf[i & 1];
-        real_derivative(s, xi, s->aprime);
+        real_derivative(s, xi, s->aprime, s->ctrl);   // skips itself once the solve is finished
         SweepArgs a = base;
         a.x = xi;
         a.x_out = s->xbuf[(i + 1) & 1];
@@ -990,7 +1020,7 @@ static size_t kernels_per_step(rb_solver* s, int sweeps) {
     // geometry path 4 + guess + sweeps + finish + (multiply, scale) + VEL + optional rhs_phi / energies, per stage; 3 stage updates,
     // final update, counter
     // derivatives + geometry 4, guess, sweeps, per combined sweep (real->complex, multiply, scale), finish, optional dPhi/dt, energies
-    size_t per_stage = 3 + 1 + (size_t)sweeps + (size_t)(sweeps - 1) + 1 + (s->rhs_phi_kind ? 0 : 1) +
+    size_t per_stage = (s->own_fft ? 2 : 3) + 1 + (size_t)sweeps + (size_t)(sweeps - 1) + 1 + (s->rhs_phi_kind ? 0 : 1) +
                        (s->props.compute_energies ? 1 : 0);
     if (s->comm.nranks > 1) per_stage += (size_t)sweeps;   // wait kernels
     return 4 * per_stage + 5;

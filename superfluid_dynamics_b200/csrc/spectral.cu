@@ -120,6 +120,127 @@ void launch_spectral_multiply_real(const double2* half, double2* out, int N, int
     count_launch();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shared-memory FFT derivatives for power-of-two N <= 4096 (one CTA per transform pair): forward transform, coefficient
+// multiply and inverse transform in ONE launch.  At these sizes the library transforms are launch-bound (ncu, N = 4096:
+// 6.5-7.8 us per cuFFT launch, 6 launches per RHS); here the whole derivative costs about one such launch.
+// Radix-2 Stockham autosort (no bit reversal), twiddles exp(-2 pi i k / N) from a host-computed table staged in shared memory.
+// Unnormalised in both directions, like cuFFT: the 1/n sits in the coefficient multiply.
+// ------------------------------------------------------------------------------------------------
+// stage the twiddle table in shared memory (the passes are latency-bound if every pass goes to L2 for its twiddles)
+// table layout: for every pass Ns = 1, 2, 4, .., N/2 the Ns twiddles exp(-i pi k / Ns), k < Ns, stored contiguously at offset
+// Ns - 1 (N - 1 entries in all), so that a warp reads consecutive entries (a strided walk through one exp(-2 pi i k / N) table
+// is a 32-way bank conflict for most passes)
+__device__ __forceinline__ void stage_twiddles(double2* sm_tw, const double2* __restrict__ tw, int N) {
+    for (int i = threadIdx.x; i < N - 1; i += blockDim.x) sm_tw[i] = tw[i];
+}
+
+// Stockham autosort radix-2: natural order in, natural order out, ping-pong between two shared buffers, no bit reversal
+// (a bit-reversed scatter in shared memory is a 32-way bank conflict).  Returns the buffer that holds the result.
+__device__ __forceinline__ double2* fft_stockham(double2* __restrict__ a, double2* __restrict__ b, int N,
+                                                 const double2* __restrict__ tw, bool inverse) {
+    const int T = blockDim.x;
+    const int halfN = N >> 1;
+    for (int Ns = 1; Ns < N; Ns <<= 1) {
+        const double2* __restrict__ twp = tw + (Ns - 1);
+        for (int j = threadIdx.x; j < halfN; j += T) {
+            const int k = j & (Ns - 1);
+            double2 w = twp[k];
+            if (inverse) w.y = -w.y;
+            const double2 v0 = a[j];
+            const double2 v1 = a[j + halfN];
+            const double2 t = make_double2(v1.x * w.x - v1.y * w.y, v1.x * w.y + v1.y * w.x);
+            const int j0 = ((j - k) << 1) + k;
+            b[j0] = make_double2(v0.x + t.x, v0.y + t.y);
+            b[j0 + Ns] = make_double2(v0.x - t.x, v0.y - t.y);
+        }
+        __syncthreads();
+        double2* tmp = a;
+        a = b;
+        b = tmp;
+    }
+    return a;
+}
+
+// blockIdx.x: 0 -> i k Z^ (Zp), 1 -> -k^2 Z^ (Zpp), 2 -> i k Phi^ (PhiPrime); blockIdx.y: batch member.
+// Outputs are the raw inverse transforms (scaling and linear parts are applied by the geometry / finish kernel).
+__global__ void fft_zphi_kernel(const double2* __restrict__ Z, const double2* __restrict__ Phi, double2* __restrict__ Zp,
+                                double2* __restrict__ Zpp, double2* __restrict__ PhiP, int N, int logN,
+                                const double2* __restrict__ tw, double rho, double U) {
+    extern __shared__ double2 sm_fft[];
+    double2* bufA = sm_fft;
+    double2* bufB = sm_fft + N;
+    double2* stw = sm_fft + 2 * N;
+    const int role = blockIdx.x;
+    const size_t off = (size_t)blockIdx.y * N;
+    const double2* in = (role == 2 ? Phi : Z) + off;
+    double2* out = (role == 0 ? Zp : (role == 1 ? Zpp : PhiP)) + off;
+    stage_twiddles(stw, tw, N);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double2 v = in[i];
+        const double lin = role == 2 ? -(1 + rho) * kPi * U / N * (double)i : 2 * kPi * (double)i / N;
+        v.x -= lin;
+        bufA[i] = v;
+    }
+    __syncthreads();
+    double2* r = fft_stockham(bufA, bufB, N, stw, false);
+    double2* o = (r == bufA) ? bufB : bufA;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double2 c = r[i];
+        r[i] = role == 1 ? d2_coeff(c, i, N) : d1_coeff(c, i, N);
+    }
+    __syncthreads();
+    r = fft_stockham(r, o, N, stw, true);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[i] = r[i];
+}
+
+// a' = scale * D1(x) for a real vector x (one CTA per batch member); returns at once when the solve it belongs to is finished
+__global__ void fft_real_derivative_kernel(const double* __restrict__ x, double2* __restrict__ out, int N, int logN,
+                                           const double2* __restrict__ tw, double scale, const SolveCtrl* ctrl) {
+    extern __shared__ double2 sm_fft[];
+    if (ctrl && *reinterpret_cast<const volatile int*>(&ctrl->done)) return;
+    double2* bufA = sm_fft;
+    double2* bufB = sm_fft + N;
+    double2* stw = sm_fft + 2 * N;
+    const size_t off = (size_t)blockIdx.y * N;
+    stage_twiddles(stw, tw, N);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bufA[i] = make_double2(x[off + i], 0.0);
+    __syncthreads();
+    double2* r = fft_stockham(bufA, bufB, N, stw, false);
+    double2* o = (r == bufA) ? bufB : bufA;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double2 c = d1_coeff(r[i], i, N);
+        r[i] = make_double2(c.x * scale, c.y * scale);
+    }
+    __syncthreads();
+    r = fft_stockham(r, o, N, stw, true);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[off + i] = r[i];
+}
+
+static int fft_threads(int N) { return N / 2 >= 1024 ? 1024 : (N / 2 >= 32 ? N / 2 : 32); }
+
+static void fft_smem_attr(const void* fn, size_t bytes) {
+    if (bytes > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+void launch_fft_zphi(const double2* Z, const double2* Phi, double2* Zp, double2* Zpp, double2* PhiP, int N, int logN, int batch,
+                     const double2* tw, double rho, double U, cudaStream_t st) {
+    const size_t bytes = (size_t)(3 * N) * sizeof(double2);
+    fft_smem_attr((const void*)fft_zphi_kernel, bytes);
+    fft_zphi_kernel<<<dim3(Phi ? 3 : 2, batch), fft_threads(N), bytes, st>>>(Z, Phi, Zp, Zpp, PhiP, N, logN, tw, rho, U);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+void launch_fft_real_derivative(const double* x, double2* out, int N, int logN, int batch, const double2* tw, double scale,
+                                const SolveCtrl* ctrl, cudaStream_t st) {
+    const size_t bytes = (size_t)(3 * N) * sizeof(double2);
+    fft_smem_attr((const void*)fft_real_derivative_kernel, bytes);
+    fft_real_derivative_kernel<<<dim3(1, batch), fft_threads(N), bytes, st>>>(x, out, N, logN, tw, scale, ctrl);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 // scaling by 2 pi / N (resp. its square) and the linear parts put back (L/Derivatives.cuh:321-324, 374, 380-383)
 __global__ void finish_zphi_kernel(double2* __restrict__ Zp, double2* __restrict__ Zpp, double2* __restrict__ PhiP, int N,
                                    size_t total, double rho, double U) {
