@@ -172,6 +172,7 @@ RB_API int rb_comm_destroy(rb_solver* s);
 /* ---- measurement helpers ---- */
 RB_API unsigned long long rb_launch_count(void);                                  /* kernels of this library launched since load */
 RB_API int rb_measure_fp64_peak(double* tflops_out, void* stream);               /* DFMA-only kernel: the FP64 roofline denominator */
+RB_API int rb_measure_fp64_rate_3operand(double* tflops_out, void* stream);      /* DFMA with three distinct register operands */
 RB_API int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* ms_per_sweep_out, double* pairs_per_sweep_out);
 
 /* ---- legacy exports (same names and argument meaning as L/Export.cuh:27-70; SI inputs, nondimensionalised inside,

@@ -88,6 +88,7 @@ SIGNATURES = {
     "rb_comm_destroy": (c_int, [_P]),
     "rb_launch_count": (ctypes.c_ulonglong, []),
     "rb_measure_fp64_peak": (c_int, [_D, _P]),
+    "rb_measure_fp64_rate_3operand": (c_int, [_D, _P]),
     "rb_bench_sweep": (c_int, [_P, _P, c_int, POINTER(c_float), _D]),
     "calculateRHSFromVectors": (c_int, [_D, _D, _D, _D, _D, _D, c_double, c_double, c_double, c_double, c_size_t]),
     "calculateRHS256FromVectors": (c_int, [_D, _D, _D, _D, _D, _D, c_double, c_double, c_double, c_double]),

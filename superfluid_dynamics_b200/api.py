@@ -346,6 +346,13 @@ def measure_fp64_peak(device=None):
     return out.value
 
 
+def measure_fp64_rate_3operand(device=None):
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    out = ctypes.c_double()
+    check(_lib.load().rb_measure_fp64_rate_3operand(ctypes.byref(out), _stream_ptr(device)), "rb_measure_fp64_rate_3operand")
+    return out.value
+
+
 # ---- legacy host-vector exports (L/Export.cuh) -------------------------------------------------
 def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))

@@ -207,5 +207,6 @@ void launch_stage_update(double2* y_out, const double2* y0, const double2* k, do
 void launch_final_update(double2* y0, const double2* k1, const double2* k2, const double2* k3, const double2* k4, double h,
                          size_t n, cudaStream_t st);
 void launch_fp64_peak(double* sink, int iters, int blocks, cudaStream_t st);
+void launch_fp64_peak3(double* sink, int iters, int blocks, double seed, cudaStream_t st);
 
 }  // namespace rb

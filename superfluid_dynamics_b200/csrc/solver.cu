@@ -1585,6 +1585,35 @@ int rb_measure_fp64_peak(double* tflops_out, void* stream) {
     RB_CATCH
 }
 
+int rb_measure_fp64_rate_3operand(double* tflops_out, void* stream) {
+    RB_TRY
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sink = dmalloc<double>(1);
+    int sms = 0, dev = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, iters = 4096;
+    cudaEvent_t e0, e1;
+    RB_CUDA(cudaEventCreate(&e0));
+    RB_CUDA(cudaEventCreate(&e1));
+    launch_fp64_peak3(sink, 256, blocks, 1e-9, st);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        RB_CUDA(cudaEventRecord(e0, st));
+        launch_fp64_peak3(sink, iters, blocks, 1e-9, st);
+        RB_CUDA(cudaEventRecord(e1, st));
+        RB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        RB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    *tflops_out = (double)blocks * 256.0 * iters * 64.0 * 2.0 / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    RB_CATCH
+}
+
 int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* ms_per_sweep_out, double* pairs_per_sweep_out) {
     RB_TRY
     cudaStream_t st = s->stream;

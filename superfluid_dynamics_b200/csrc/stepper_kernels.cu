@@ -60,6 +60,36 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters)
     if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
 }
 
+// same probe with three distinct register operands per DFMA (a_i = fma(b_i, c_i, a_i), b and c in registers, not constants):
+// measures what the register file can feed to the FP64 pipe
+__global__ void __launch_bounds__(256) fp64_peak3_kernel(double* sink, int iters, double seed) {
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = threadIdx.x * 1e-3 + i;
+        b[i] = 0.999999 + seed * (i + 1) + threadIdx.x * 1e-12;   // per-thread values: keep them out of the uniform registers
+        c[i] = 1e-7 * (i + 1) + seed + threadIdx.x * 1e-13;
+    }
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(b[i], c[(i + u) & 7], a[i]);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456) sink[0] = s;
+}
+
+void launch_fp64_peak3(double* sink, int iters, int blocks, double seed, cudaStream_t st) {
+    fp64_peak3_kernel<<<blocks, 256, 0, st>>>(sink, iters, seed);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 void launch_fp64_peak(double* sink, int iters, int blocks, cudaStream_t st) {
     fp64_peak_kernel<<<blocks, 256, 0, st>>>(sink, iters);
     RB_CUDA(cudaGetLastError());

@@ -188,7 +188,7 @@ def v2cmp():
 
 
 def speed():
-    print("fp64 peak TFLOP/s", api.measure_fp64_peak())
+    print("fp64 peak TFLOP/s", api.measure_fp64_peak(), " 3-register-operand DFMA:", api.measure_fp64_rate_3operand())
     for N in (1024, 4096, 16384, 65536):
         props = api.ProblemProperties(rho=0.0)
         calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
