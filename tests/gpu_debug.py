@@ -187,6 +187,33 @@ def v2cmp():
     os.environ.pop("RB_SWEEP_V2", None); os.environ.pop("RB_VERBOSE", None)
 
 
+def ensemble():
+    """BASELINE config 5, second half: 1024-member ensemble at N = 512 (replicas only across GPUs)"""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    N, B, dt, steps = 512, 1024, 1e-3, 30
+    hs = 0.05 + 0.35 * np.arange(B) / (B - 1)
+    Zs, Ps = zip(*(ro.trochoid(N, h) for h in hs))
+    y0 = np.concatenate(list(Zs) + [p.astype(np.complex128) for p in Ps])
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, B, props, api.WaterBoundaryProblem(props), guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(calc, dt)
+    st = T(y0)
+    stp.initialize(st, True)
+    stp.runSteps(12)
+    torch.cuda.synchronize()
+    s0 = calc.solve_stats()
+    t0 = time.time()
+    stp.runSteps(steps)
+    torch.cuda.synchronize()
+    el = time.time() - t0
+    s1 = calc.solve_stats()
+    its = (s1["total_iterations"] - s0["total_iterations"]) / max(1, s1["total_solves"] - s0["total_solves"])
+    print(f"ensemble B={B} N={N}: {steps / el:.1f} steps/s = {B * steps / el:.0f} member-steps/s, {its:.2f} sweeps/solve, "
+          f"{stp.stats()} finite={bool(torch.isfinite(torch.view_as_real(st)).all())}", flush=True)
+    ms, pairs = calc.benchSweep(T(y0), 20)
+    print(f"ensemble sweep: {ms * 1e3:.1f} us, {20 * pairs / (ms * 1e-3) / 1e12:.2f} TFLOP/s")
+
+
 def speed():
     print("fp64 peak TFLOP/s", api.measure_fp64_peak(), " 3-register-operand DFMA:", api.measure_fp64_rate_3operand())
     for N in (1024, 4096, 16384, 65536):

@@ -489,3 +489,17 @@ def test_graph_rollback_when_recorded_sweeps_do_not_suffice(api):
     assert res["1"][1]["graph_launches"] == 0
     assert res["0"][2]["converged"] and res["1"][2]["converged"]
     assert rel(res["0"][0], res["1"][0]) <= 1e-12
+
+
+def test_row_sharded_two_gpus_match_single_gpu(api):
+    """N > 1: row-sharded run on two GPUs (torchrun, one rank per GPU) vs the single-GPU run; skipped on a one-GPU box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "gpu_multirank.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert "FAIL" not in r.stdout
