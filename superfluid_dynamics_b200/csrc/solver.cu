@@ -118,6 +118,7 @@ struct rb_solver {
     cufftHandle plan1 = 0, plan2 = 0, plan3 = 0, plan_d2z = 0;
     // shared-memory FFT derivatives (small power-of-two N, launch-bound regime): twiddle table exp(-2 pi i k / N), k < N/2
     bool own_fft = false;
+    bool own_fft_skippable = false;
     int logN = 0;
     double2* fft_tw = nullptr;
     bool plans = false;
@@ -422,8 +423,11 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     // the one-CTA radix-2 transform is shared-memory-bandwidth bound (~1.3k cycles per pass at N = 4096): it beats the library's
     // three launches only in the launch-bound regime (measured: faster at N <= 1024, slower at N = 4096)
     const int own_fft_max = env_int("RB_OWN_FFT_MAX", 1024);
-    if ((N & (N - 1)) == 0 && N >= 4 && N <= std::min(own_fft_max, 4096) && (long)N * batch <= 4096 && env_int("RB_OWN_FFT", 1)) {
-        s->own_fft = true;
+    if ((N & (N - 1)) == 0 && N >= 4 && N <= 4096 && (long)N * batch <= 4096 && env_int("RB_OWN_FFT", 1)) {
+        // up to own_fft_max the fused kernels replace the library everywhere; above it they are only used for the a' of the
+        // surplus (normally skipped) rounds of a recorded step, because they can skip themselves and the library cannot
+        s->own_fft = N <= own_fft_max;
+        s->own_fft_skippable = true;
         while ((1 << s->logN) < N) s->logN++;
         // per-pass tables: exp(-i pi k / Ns), k < Ns, at offset Ns - 1 (see stage_twiddles in spectral.cu)
         std::vector<double2> tw(N);
@@ -852,7 +856,10 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     }
     for (int i = 1; i < s->fixed_sweeps; ++i) {
         const double* xi = s->xbuf[i & 1];
-        real_derivative(s, xi, s->aprime, s->ctrl);   // skips itself once the solve is finished
+        if (i >= 2 && s->own_fft_skippable)   // surplus round: almost always skipped -> use the kernel that can skip itself
+            launch_fft_real_derivative(xi, s->aprime, s->N, s->logN, s->batch, s->fft_tw, 2.0 * kPi / s->N, s->ctrl, st);
+        else
+            real_derivative(s, xi, s->aprime, s->ctrl);   // own kernel: skips itself once the solve is finished
         SweepArgs a = base;
         a.x = xi;
         a.x_out = s->xbuf[(i + 1) & 1];
