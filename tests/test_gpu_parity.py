@@ -273,6 +273,23 @@ def test_helium_gmres_agrees_with_dense_lu_and_reports_convergence(api):
         assert rel(outs[0][0], outs[1][0]) <= 1e-10
 
 
+def test_dense_lu_and_matrix_free_agree_at_N4096(api):
+    """BASELINE config 3: steep trochoid (h = 0.4), N = 4096 -- assemble-and-factorise (the reference's way) vs the matrix-free
+    iteration agree to <= 1e-12 per RHS."""
+    N = 4096
+    Z, Phi = ro.trochoid(N, 0.4)
+    st = T(ro.pack_state(Z, Phi))
+    props = api.ProblemProperties(rho=0.0)
+    outs = []
+    for mode in ("matrix_free", "dense_lu"):
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), solve_mode=mode)
+        out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+        calc.run(st, out)
+        outs.append((out.cpu().numpy(), calc.getDevA().cpu().numpy().copy()))
+    assert rel(outs[0][1], outs[1][1]) <= 1e-12
+    assert rel(outs[0][0], outs[1][0]) <= 1e-12
+
+
 def test_small_amplitude_wave_follows_linear_dispersion(api):
     """BASELINE config 2: N = 1024 deep-water wave, g = 1, k = 1: omega^2 = k.  After t the profile is eps cos(x - t) + O(eps^2)."""
     N, eps, dt, steps = 1024, 1e-4, 1e-3, 400
