@@ -139,6 +139,10 @@ struct SweepArgs {
     int v2_bpm;                      // row blocks per batch member (of this rank's rows)
     int v2_total_blocks;             // batch * bpm
     int v2_row_begin, v2_row_end;    // this rank's rows [begin, end)
+    int v2_split;                    // source parts per row block (work item = row block x part); 1 = no split
+    double2* v2_partial;             // [batch][split][rows] row sums per part (split > 1)
+    double* v2_xs_part;              // [total_blocks * split] sum of x over each part's sources
+    unsigned int* v2_blk_tickets;    // [total_blocks] zero on entry, reset on exit
     double* v2_rnorm_part;           // [total_blocks] residual sums per row block
     unsigned int* v2_ticket;         // one counter, zero on entry, reset on exit
 };

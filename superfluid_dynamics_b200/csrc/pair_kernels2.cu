@@ -156,10 +156,18 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
     const int sublen = SPG < kCell ? SPG : kCell;
     const double inv4pi = 0.25 / kPi;
     const int TB = a.v2_total_blocks;
-    const int b0 = (int)(((long long)blockIdx.x * TB) / gridDim.x);
-    const int b1 = (int)(((long long)(blockIdx.x + 1) * TB) / gridDim.x);
+    const int SX = a.v2_split;                       // source parts per row block (1: no split)
+    const int TI = TB * SX;                          // work items
+    const int NT = (N + TS - 1) / TS;                // staged tiles per member
+    const int i0 = (int)(((long long)blockIdx.x * TI) / gridDim.x);
+    const int i1 = (int)(((long long)(blockIdx.x + 1) * TI) / gridDim.x);
+    __shared__ unsigned int s_part_ticket;
 
-    for (int blk = b0; blk < b1; ++blk) {
+    for (int item = i0; item < i1; ++item) {
+        const int blk = item / SX;
+        const int part = item - blk * SX;
+        const int tile_begin = (int)(((long long)part * NT) / SX);
+        const int tile_end = (int)(((long long)(part + 1) * NT) / SX);
         const int bm = blk / a.v2_bpm;
         const int ib = blk - bm * a.v2_bpm;
         const int row0 = a.v2_row_begin + ib * a.v2_RB;
@@ -242,13 +250,14 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
             }
         };
 
-        prefetch(0);
-        for (int j0 = 0; j0 < N; j0 += TS) {
+        prefetch(tile_begin * TS);
+        for (int tl = tile_begin; tl < tile_end; ++tl) {
+            const int j0 = tl * TS;
             __syncthreads();            // everyone is done with the previous tile
             const bool tile_near = pnear;
             commit(j0);
             __syncthreads();
-            if (j0 + TS < N) prefetch(j0 + TS);   // loads fly while this tile is evaluated
+            if (tl + 1 < tile_end) prefetch(j0 + TS);   // loads fly while this tile is evaluated
             // ---- this group's share of the tile, in pieces that stay inside one 256-point cell --------------------------------
             for (int sub0 = g * SPG; sub0 < (g + 1) * SPG; sub0 += sublen) {
                 const int jj = j0 + sub0;
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
         }
 
         // ---- sum_j x_j (identical in every CTA: same staging pattern, same tree) and the cross-group combine ------------------
-        const double sumx = block_sum_any(xs, sred, T, P2);
+        double sumx = block_sum_any(xs, sred, T, P2);
         if (REALPATH) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {   // Re(Zp T) of this group's sources: complex near part + real far part
@@ -296,6 +305,40 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
                         s.x += v.x; s.y += v.y;
                     }
                     acc[r] = s;
+                }
+            }
+        }
+
+        // ---- source split: publish this part's row sums; the last part of the row block adds them up in part order -----------------
+        if (SX > 1) {
+            const size_t rows_total = (size_t)(a.v2_row_end - a.v2_row_begin);
+            double2* pbase = a.v2_partial + ((size_t)bm * SX) * rows_total;
+            if (g == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (valid[r]) pbase[(size_t)part * rows_total + (krow[r] - a.v2_row_begin)] = acc[r];
+            }
+            if (t == 0) a.v2_xs_part[item] = sumx;
+            __threadfence();
+            __syncthreads();
+            if (t == 0) s_part_ticket = atomicAdd(a.v2_blk_tickets + blk, 1u);
+            __syncthreads();
+            if (s_part_ticket != (unsigned)(SX - 1)) continue;   // another CTA finishes this row block
+            __threadfence();
+            if (t == 0) a.v2_blk_tickets[blk] = 0u;
+            sumx = 0.0;
+            for (int p = 0; p < SX; ++p) sumx += __ldcg(a.v2_xs_part + (size_t)blk * SX + p);
+            if (g == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double2 sacc = make_double2(0.0, 0.0);
+                    if (valid[r]) {
+                        for (int p = 0; p < SX; ++p) {
+                            double2 v = __ldcg(pbase + (size_t)p * rows_total + (krow[r] - a.v2_row_begin));
+                            sacc.x += v.x; sacc.y += v.y;
+                        }
+                    }
+                    acc[r] = sacc;
                 }
             }
         }

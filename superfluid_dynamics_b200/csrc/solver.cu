@@ -80,8 +80,13 @@ struct rb_solver {
     bool use_v2 = false;
     int v2_RB = 0, v2_R = 0, v2_groups = 0, v2_spg = 0, v2_TS = 0, v2_bpm = 0, v2_total_blocks = 0;
     Sweep2Launch v2l;
+    int v2_split = 1;
+    double v2_eff = 0.0;
     double* v2_rnorm_part = nullptr;
     unsigned int* v2_ticket = nullptr;
+    double2* v2_partial = nullptr;
+    double* v2_xs_part = nullptr;
+    unsigned int* v2_blk_tickets = nullptr;
 
     // device buffers
     double2* deriv = nullptr;      // [3][BN]: Zp | Zpp | PhiPrime(complex)
@@ -164,7 +169,8 @@ static void solver_free(rb_solver* s) {
                     s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
                     s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state, s->gm_V, s->gm_x, s->gm_t,
-                    s->gm_dev, s->gm_invP, s->v2_rnorm_part, s->v2_ticket, s->fft_tw};
+                    s->gm_dev, s->gm_invP, s->v2_rnorm_part, s->v2_ticket, s->fft_tw, s->v2_partial, s->v2_xs_part,
+                    s->v2_blk_tickets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
@@ -245,12 +251,44 @@ static void plan_sweep2(rb_solver* s) {
     s->v2_TS = G * spg;
     s->v2_bpm = (rows + RB - 1) / RB;
     s->v2_total_blocks = B * s->v2_bpm;
-    s->v2l.grid = std::min(s->v2_total_blocks, env_int("RB_V2_GRID", nSM));
+    // source split: work items = row blocks x parts; the smallest split that keeps >= 95 % of the SMs busy in every round
+    {
+        const int NT = (N + s->v2_TS - 1) / s->v2_TS;
+        int best = 1;
+        double best_eff = 0.0;
+        for (int sx = 1; sx <= 16 && sx <= NT; sx <<= 1) {
+            const long items = (long)s->v2_total_blocks * sx;
+            const long grid = std::min<long>(items, nSM);
+            const long per = (items + grid - 1) / grid;
+            const double eff = (double)items / ((double)per * nSM);
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best = sx;
+            }
+            if (eff >= 0.95) break;
+        }
+        // measured (B200): with the split the per-item overheads (un-overlapped first prefetch, reductions, fences, tickets) outweigh
+        // the better balance -- N = 8192/16384/32768: 122/287/968 us against 82/250/891 us for the tiled kernel -- so it stays
+        // off unless asked for; mid-size problems and multi-GPU shards use the tiled kernel
+        if (!env_int("RB_V2_SPLIT_AUTO", 0)) best = 1;
+        s->v2_split = std::max(1, std::min(env_int("RB_V2_SPLIT", best), NT));
+        const long items = (long)s->v2_total_blocks * s->v2_split;
+        const long grid = std::min<long>(items, nSM);
+        s->v2_eff = (double)items / ((double)((items + grid - 1) / grid) * nSM);
+    }
+    s->v2l.grid = (int)std::min<long>((long)s->v2_total_blocks * s->v2_split, env_int("RB_V2_GRID", nSM));
     s->v2l.threads = threads;
     s->v2l.smem = (size_t)s->v2_TS * 32 * (s->use_local ? 2 : 1) + (size_t)threads * R * 16 + (size_t)threads * 8 +
                   (size_t)s->v2_TS * 8;
     if (s->v2_rnorm_part) cudaFree(s->v2_rnorm_part);
     s->v2_rnorm_part = dmalloc<double>(s->v2_total_blocks);
+    if (s->v2_partial) cudaFree(s->v2_partial);
+    if (s->v2_xs_part) cudaFree(s->v2_xs_part);
+    if (s->v2_blk_tickets) cudaFree(s->v2_blk_tickets);
+    s->v2_partial = dmalloc<double2>((size_t)B * s->v2_split * std::max(rows, 1));
+    s->v2_xs_part = dmalloc<double>((size_t)s->v2_total_blocks * s->v2_split);
+    s->v2_blk_tickets = dmalloc<unsigned int>(s->v2_total_blocks);
+    RB_CUDA(cudaMemset(s->v2_blk_tickets, 0, (size_t)s->v2_total_blocks * sizeof(unsigned int)));
     if (!s->v2_ticket) {
         s->v2_ticket = dmalloc<unsigned int>(1);
         RB_CUDA(cudaMemset(s->v2_ticket, 0, sizeof(unsigned int)));
@@ -258,8 +296,9 @@ static void plan_sweep2(rb_solver* s) {
     if (threads > max_threads || threads % 32 || s->v2_TS > threads || RB % (32 * R))
         throw std::runtime_error("plan_sweep2: inconsistent schedule");
     if (env_int("RB_VERBOSE", 0))
-        std::fprintf(stderr, "[roberts_b200] sweep2 plan: N=%d B=%d rows=[%d,%d) RB=%d R=%d groups=%d spg=%d TS=%d blocks=%d grid=%d threads=%d smem=%zu\n",
-                     N, B, row_begin, row_end, RB, R, G, spg, s->v2_TS, s->v2_total_blocks, s->v2l.grid, threads, s->v2l.smem);
+        std::fprintf(stderr, "[roberts_b200] sweep2 plan: N=%d B=%d rows=[%d,%d) RB=%d R=%d groups=%d spg=%d TS=%d blocks=%d split=%d grid=%d threads=%d smem=%zu eff=%.3f\n",
+                     N, B, row_begin, row_end, RB, R, G, spg, s->v2_TS, s->v2_total_blocks, s->v2_split, s->v2l.grid, threads,
+                     s->v2l.smem, s->v2_eff);
 }
 
 // persistent kernel when its static schedule keeps (nearly) every SM busy or the problem is small; otherwise the tiled kernel,
@@ -267,8 +306,7 @@ static void plan_sweep2(rb_solver* s) {
 static void choose_sweep_kernel(rb_solver* s) {
     int nSM = 148;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
-    const int per_cta = (s->v2_total_blocks + s->v2l.grid - 1) / s->v2l.grid;
-    const double eff = (double)s->v2_total_blocks / ((double)per_cta * nSM);
+    const double eff = s->v2_eff;
     bool v2 = !s->has_image && (eff >= 0.95 || (long)s->N * s->batch <= 4096);
     int force = env_int("RB_SWEEP_V2", -1);
     if (force >= 0) v2 = !s->has_image && force != 0;
@@ -562,6 +600,10 @@ static SweepArgs base_args(rb_solver* s, const double2* Z) {
     a.v2_row_end = std::min(s->N, (s->row_cell0 + s->row_cells) * kCell);
     a.v2_rnorm_part = s->v2_rnorm_part;
     a.v2_ticket = s->v2_ticket;
+    a.v2_split = s->v2_split;
+    a.v2_partial = s->v2_partial;
+    a.v2_xs_part = s->v2_xs_part;
+    a.v2_blk_tickets = s->v2_blk_tickets;
     return a;
 }
 
