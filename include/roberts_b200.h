@@ -148,6 +148,15 @@ RB_API int rb_rk4_get_state(rb_stepper* st, rb_complex* y_host);                
 RB_API double rb_rk4_current_time(rb_stepper* st);
 /* out[0] CUDA-graph launches (one per step), [1] graph captures, [2] steps redone outside the graph, [3] sweeps recorded per solve */
 RB_API int rb_rk4_stats(rb_stepper* st, double out_host[4]);
+/* quality of the extrapolated initial iterates: out[0..3] relative residual of the guess at RK stage 1..4 of the last step,
+   [4] mask of stages that currently start with a combined (verify + velocity) sweep, [5] solves started that way so far,
+   [6] of those, solves that finished in ONE O(N^2) sweep, [7] policy (0 never, 1 adaptive per stage, 2 always) */
+RB_API int rb_rk4_guess_stats(rb_stepper* st, double out_host[8]);
+RB_API int rb_rk4_set_optimistic(rb_stepper* st, int policy);
+/* initial iterate of every solve: polynomial extrapolation of order `order` (1..6 previous steps, same RK stage) of the recorded
+   solutions; predict = 1 adds one Richardson sweep whose O(N^2) row sums are themselves extrapolated in time (O(N) work),
+   0 = off, -1 = automatic (on when the solve tolerance is >= 4e-13, the round-off floor of that extrapolation). Resets the history. */
+RB_API int rb_rk4_set_guess(rb_stepper* st, int order, int predict);
 /* trajectory logging (TrajectoryLogger<T,N>, L/TrajectoryLogger.cuh:7-73): every `every` steps into a device ring, 0 = off */
 RB_API int rb_rk4_set_logging(rb_stepper* st, size_t every, size_t capacity);
 RB_API int rb_rk4_copy_trajectory(rb_stepper* st, double** times_out, size_t* times_count,
@@ -173,6 +182,9 @@ RB_API int rb_comm_destroy(rb_solver* s);
 RB_API unsigned long long rb_launch_count(void);                                  /* kernels of this library launched since load */
 RB_API int rb_measure_fp64_peak(double* tflops_out, void* stream);               /* DFMA-only kernel: the FP64 roofline denominator */
 RB_API int rb_measure_fp64_rate_3operand(double* tflops_out, void* stream);      /* DFMA with three distinct register operands */
+/* FP64 tensor path (DMMA m8n8k4) beside the FP64 vector pipe: out[2i] = ms, out[2i+1] = TFLOP/s for the per-iteration mixes
+   {8 mma}, {32 fma}, {8 mma + 32 fma}, {4 + 32}, {2 + 32}, {1 + 32}: tells whether the two issue concurrently */
+RB_API int rb_measure_fp64_tensor_overlap(double out_host[12], void* stream);
 RB_API int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* ms_per_sweep_out, double* pairs_per_sweep_out);
 
 /* ---- legacy exports (same names and argument meaning as L/Export.cuh:27-70; SI inputs, nondimensionalised inside,

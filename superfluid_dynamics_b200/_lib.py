@@ -75,6 +75,9 @@ SIGNATURES = {
     "rb_rk4_get_state": (c_int, [_P, _P]),
     "rb_rk4_current_time": (c_double, [_P]),
     "rb_rk4_stats": (c_int, [_P, _D]),
+    "rb_rk4_guess_stats": (c_int, [_P, _D]),
+    "rb_rk4_set_optimistic": (c_int, [_P, c_int]),
+    "rb_rk4_set_guess": (c_int, [_P, c_int, c_int]),
     "rb_rk4_set_logging": (c_int, [_P, c_size_t, c_size_t]),
     "rb_rk4_copy_trajectory": (c_int, [_P, POINTER(_D), POINTER(c_size_t), POINTER(_P), POINTER(c_size_t)]),
     "rb_free": (None, [_P]),
@@ -89,6 +92,7 @@ SIGNATURES = {
     "rb_launch_count": (ctypes.c_ulonglong, []),
     "rb_measure_fp64_peak": (c_int, [_D, _P]),
     "rb_measure_fp64_rate_3operand": (c_int, [_D, _P]),
+    "rb_measure_fp64_tensor_overlap": (c_int, [_D, _P]),
     "rb_bench_sweep": (c_int, [_P, _P, c_int, POINTER(c_float), _D]),
     "calculateRHSFromVectors": (c_int, [_D, _D, _D, _D, _D, _D, c_double, c_double, c_double, c_double, c_size_t]),
     "calculateRHS256FromVectors": (c_int, [_D, _D, _D, _D, _D, _D, c_double, c_double, c_double, c_double]),

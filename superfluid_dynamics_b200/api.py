@@ -276,6 +276,18 @@ class AutonomousRungeKuttaStepper:
         check(self.lib.rb_rk4_stats(self.handle, out), "rb_rk4_stats")
         return dict(graph_launches=int(out[0]), graph_captures=int(out[1]), fallback_steps=int(out[2]), graph_sweeps=int(out[3]))
 
+    def guessStats(self):
+        out = (ctypes.c_double * 8)()
+        check(self.lib.rb_rk4_guess_stats(self.handle, out), "rb_rk4_guess_stats")
+        return dict(first_rel=[out[i] for i in range(4)], opt_mask=int(out[4]), optimistic_solves=int(out[5]),
+                    one_sweep_solves=int(out[6]), policy=int(out[7]))
+
+    def setOptimistic(self, policy):
+        check(self.lib.rb_rk4_set_optimistic(self.handle, int(policy)), "rb_rk4_set_optimistic")
+
+    def setGuess(self, order, predict=-1):
+        check(self.lib.rb_rk4_set_guess(self.handle, int(order), int(predict)), "rb_rk4_set_guess")
+
     def setLogging(self, every, capacity):
         check(self.lib.rb_rk4_set_logging(self.handle, int(every), int(capacity)), "rb_rk4_set_logging")
 
@@ -351,6 +363,15 @@ def measure_fp64_rate_3operand(device=None):
     out = ctypes.c_double()
     check(_lib.load().rb_measure_fp64_rate_3operand(ctypes.byref(out), _stream_ptr(device)), "rb_measure_fp64_rate_3operand")
     return out.value
+
+
+def measure_fp64_tensor_overlap(device=None):
+    """DMMA m8n8k4 beside DFMA: {mix: (ms, TFLOP/s)} for the per-iteration mixes of mma.sync and fma instructions"""
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    out = (ctypes.c_double * 12)()
+    check(_lib.load().rb_measure_fp64_tensor_overlap(out, _stream_ptr(device)), "rb_measure_fp64_tensor_overlap")
+    names = ("8mma", "32fma", "8mma+32fma", "4mma+32fma", "2mma+32fma", "1mma+32fma")
+    return {n: (out[2 * i], out[2 * i + 1]) for i, n in enumerate(names)}
 
 
 # ---- legacy host-vector exports (L/Export.cuh) -------------------------------------------------

@@ -40,6 +40,7 @@ struct SolveCtrl {
     unsigned long long max_rel2_bits;   // atomicMax accumulator over batch members (non-negative doubles order as uint64)
     unsigned int members_done;          // level-3 ticket
     unsigned int pad;
+    double first_rel2;   // residual of the initial iterate (set by the first sweep of the solve): quality of the guess
 };
 
 // geometry of the surface, per point; all arrays are [batch][N]
@@ -65,6 +66,10 @@ struct HistoryRing {
     int ring = 0;                // number of slots (> order so that a repeated step never reads what it overwrote)
     int order = 0;               // extrapolation order (1..4)
     const int* counter = nullptr;   // device: steps completed so far
+    int store_next = 0;          // finish_solve: record the iterate AFTER the verified one (x + omega r, one contraction better)
+    double2* Abase = nullptr;    // [ring][stride] row sums A_k = (sum x - x_k) + 2 T_k of the recorded solutions (S_k = i A_k)
+    int predict = 0;             // guess: x0 = extrap(a) + omega (b - M~ extrap(a)),  M~ x = Mdiag x + cK Re(Zp extrap(A)):
+                                 // one Richardson sweep whose O(N^2) row sums are replaced by their extrapolation in time
 };
 
 // multi-GPU view: every rank owns one "arena" allocation with the same layout; arenas of the peers are mapped into this
@@ -129,6 +134,7 @@ struct SweepArgs {
     double2* vel_upper;              // upper-fluid velocities
     double2* dphi;                   // dPhi/dt + 0 i -> rhs[BN .. 2BN)  (nullptr: separate kernel)
     double2* raw_out;                // RAW: S_k = sum_{j!=k} cot((z_k - z_j)/2) x_j
+    double2* A_out;                  // combined VEL sweeps: A_k of the input iterate (kept for the time extrapolation of the row sums)
     CommView comm;                   // row sharding over GPUs (nranks == 1: off)
     // persistent one-wave variant (sweep2_kernel): static schedule of row blocks, in-CTA source split, no global partials
     int v2_RB;                       // rows per row block (multiple of 32 * R)
@@ -161,7 +167,8 @@ void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st);
 // pair_kernels2.cu
 void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st);
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
-                  double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st);
+                  double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st,
+                  const double2* Zp = nullptr, const double* Mdiag = nullptr, double cK = 0.0);
 void launch_advance_counter(int* counter, cudaStream_t st);
 void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, int final_buf, const double* bnorm_part,
                       int ncell, double tol2, int max_iters, cudaStream_t st);
@@ -179,7 +186,8 @@ void launch_fft_real_derivative(const double* x, double2* out, int N, int logN, 
 void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int batch, double rho, double U, cudaStream_t st);
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st);
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
-                         double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st);
+                         double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st,
+                         const double2* A0 = nullptr, const double2* A1 = nullptr);
 // krylov_kernels.cu
 void launch_multi_dot(const double* V, size_t ldv, int nvec, const double* w, double* out, int n, cudaStream_t st);
 void launch_multi_axpy(double* w, const double* V, size_t ldv, int nvec, const double* h, double sign, int n, cudaStream_t st);
@@ -212,5 +220,6 @@ void launch_final_update(double2* y0, const double2* k1, const double2* k2, cons
                          size_t n, cudaStream_t st);
 void launch_fp64_peak(double* sink, int iters, int blocks, cudaStream_t st);
 void launch_fp64_peak3(double* sink, int iters, int blocks, double seed, cudaStream_t st);
+void launch_fp64_mix(double* sink, int iters, int blocks, int nm, int nf, cudaStream_t st);
 
 }  // namespace rb

@@ -201,7 +201,8 @@ void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, i
 __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__ b, const double* __restrict__ warm,
                                                        HistoryRing hist, double* __restrict__ x0,
                                                        double* __restrict__ xsum_part, double* __restrict__ bnorm_part,
-                                                       SolveCtrl* ctrl, double omega, int N, int ncell) {
+                                                       SolveCtrl* ctrl, double omega, int N, int ncell,
+                                                       const double2* __restrict__ Zp, const double* __restrict__ Mdiag, double cK) {
     __shared__ double sred[kCell];
     int cell = blockIdx.x, bm = blockIdx.y;
     int i = cell * kCell + threadIdx.x;
@@ -215,16 +216,28 @@ __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__
         size_t o = (size_t)bm * N + i;
         bv = b[o];
         if (m > 0) {
-            // Lagrange extrapolation to the next equally spaced point: m=1: 1 | 2: 2,-1 | 3: 3,-3,1 | 4: 4,-6,4,-1
-            const double c1 = (double)m;
-            const double c2 = m == 2 ? -1.0 : (m == 3 ? -3.0 : -6.0);
-            const double c3 = m == 3 ? 1.0 : 4.0;
-            const double c4 = -1.0;
-            auto slot = [&](int back) { return hist.base + (size_t)((cnt - back) % hist.ring) * hist.stride + o; };
-            xv = c1 * *slot(1);
-            if (m >= 2) xv = fma(c2, *slot(2), xv);
-            if (m >= 3) xv = fma(c3, *slot(3), xv);
-            if (m >= 4) xv = fma(c4, *slot(4), xv);
+            // Lagrange extrapolation to the next equally spaced point: c_i = (-1)^(i+1) C(m, i), i = 1..m
+            // (m=1: 1 | 2: 2,-1 | 3: 3,-3,1 | 4: 4,-6,4,-1 | 5: 5,-10,10,-5,1 | 6: 6,-15,20,-15,6,-1)
+            const bool pr = hist.predict && hist.Abase && Zp;
+            double cf = 1.0, Aer = 0.0, Aei = 0.0;
+            xv = 0.0;
+            for (int back = 1; back <= m; ++back) {
+                cf = -cf * (double)(m - back + 1) / (double)back;          // -> (-1)^back C(m, back)
+                const size_t so = (size_t)((cnt - back) % hist.ring) * hist.stride + o;
+                xv = fma(-cf, hist.base[so], xv);
+                if (pr) {
+                    const double2 A = hist.Abase[so];
+                    Aer = fma(-cf, A.x, Aer);
+                    Aei = fma(-cf, A.y, Aei);
+                }
+            }
+            if (pr) {
+                // predicted sweep: the row sums of the extrapolated iterate are the extrapolated row sums (linear in x, smooth in
+                // time); today's Zp_k, Mdiag_k, b_k carry today's round-off noise, which is what the extrapolation cannot know
+                const double2 zp = Zp[o];
+                const double Mx = fma(Mdiag[o], xv, cK * (zp.x * Aer - zp.y * Aei));
+                xv = fma(omega, bv - Mx, xv);
+            }
         } else {
             xv = warm ? warm[o] : omega * bv;
         }
@@ -242,6 +255,7 @@ __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__
             ctrl->converged = 0;
             ctrl->rel2 = 0.0;
             ctrl->prev_rel2 = 1e300;
+            ctrl->first_rel2 = 1e300;
             ctrl->max_rel2_bits = 0ull;
             ctrl->members_done = 0u;
         }
@@ -249,8 +263,10 @@ __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__
 }
 
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
-                  double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st) {
-    guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell);
+                  double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st,
+                  const double2* Zp, const double* Mdiag, double cK) {
+    guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell, Zp, Mdiag,
+                                                       cK);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -260,11 +276,13 @@ void launch_guess(const double* b, const double* warm, const HistoryRing& hist, 
 // when a history ring is attached, the ring slot of this step (real_to_complex of L/BaseBoundaryIntegrator.cuh:201 folded in)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __restrict__ buf0, const double* __restrict__ buf1,
+                                                              const double2* __restrict__ A0, const double2* __restrict__ A1,
                                                               const SolveCtrl* ctrl, double* __restrict__ a_out,
                                                               double2* __restrict__ a_complex, double* __restrict__ xsum_part,
                                                               HistoryRing hist, int N, int ncell) {
     __shared__ double sred[kCell];
     const double* src = (ctrl && ctrl->final_buf) ? buf1 : buf0;
+    const double* nxt = (ctrl && ctrl->final_buf) ? buf0 : buf1;   // combined sweeps: x + omega r of the verified iterate
     int cell = blockIdx.x, bm = blockIdx.y;
     int i = cell * kCell + threadIdx.x;
     double v = 0.0;
@@ -273,15 +291,22 @@ __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __res
         v = src[o];
         if (a_out) a_out[o] = v;
         if (a_complex) a_complex[o] = make_double2(v, 0.0);
-        if (hist.base) hist.base[(size_t)(*hist.counter % hist.ring) * hist.stride + o] = v;
+        if (hist.base) {
+            const size_t so = (size_t)(*hist.counter % hist.ring) * hist.stride + o;
+            const bool keepA = hist.Abase && A0;
+            hist.base[so] = (hist.store_next && !keepA) ? nxt[o] : v;   // with row sums the ring must hold the iterate they belong to
+            if (keepA) hist.Abase[so] = ((ctrl && ctrl->final_buf) ? A1 : A0)[o];
+        }
     }
     double sx = block_reduce_fixed<kCell>(v, sred);
     if (threadIdx.x == 0 && xsum_part) xsum_part[(size_t)bm * ncell + cell] = sx;
 }
 
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
-                         double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st) {
-    finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, ctrl, a_out, a_complex, xsum_part, hist, N, ncell);
+                         double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st,
+                         const double2* A0, const double2* A1) {
+    finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, A0, A1, ctrl, a_out, a_complex, xsum_part, hist, N,
+                                                              ncell);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -376,6 +401,7 @@ __device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx
             c->iters = iters;
             c->rel2 = worst;
             c->prev_rel2 = worst;
+            if (iters == 1) c->first_rel2 = worst;
             c->final_buf = a.final_buf_on_done;
             if (conv || stagnated || iters >= a.max_iters) {
                 c->converged = (conv || stagnated) ? 1 : 0;
@@ -413,12 +439,32 @@ __device__ __forceinline__ void tile_accumulate_real(const SrcEntry* __restrict_
     }
 }
 
+// image sum of a solver sweep: only Re(T_img) enters M x (L/createM.cuh:87-88: the image term carries no Zp_k), so the numerator is
+// Re(F conj(d)) = F_re d_re + F_im d_im: 10 FP64-pipe instructions per pair
+__device__ __forceinline__ void tile_accumulate_image_real(const SrcEntry* __restrict__ sh, int tile,
+                                                           const double2 (&ek)[kRowsPerThread], double2 (&acc)[kRowsPerThread]) {
+#pragma unroll 4
+    for (int s = 0; s < tile; ++s) {
+        const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
+        const double2 f = *reinterpret_cast<const double2*>(&sh[s].fr);
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) {
+            double dr = ek[r].x - e.x;
+            double di = ek[r].y - e.y;
+            double n2 = fma(di, di, dr * dr);
+            double inv = fast_rcp(n2);
+            double tr = fma(f.y, di, f.x * dr);
+            acc[r].x = fma(tr, inv, acc[r].x);
+        }
+    }
+}
+
 template <int MODE, bool IMAGE>
 __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a) {
     __shared__ SrcEntry sh[kCell];
     __shared__ SrcEntry shI[IMAGE ? kCell : 1];
     __shared__ double shg[kCell];
-    constexpr bool REALPATH = (MODE == kSweepMV) && !IMAGE;   // far tiles of a solver sweep: 11-instruction real-part form
+    constexpr bool REALPATH = (MODE == kSweepMV);   // far tiles of a solver sweep: 11-instruction real-part form
     __shared__ double sred[kSweepThreads];
     __shared__ unsigned int s_ticket;
 
@@ -511,7 +557,10 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
         if (dist == 0) tile_accumulate<true>(sh, tile, ek, sd, acc);
         else if (REALPATH && !near) tile_accumulate_real(sh, shg, tile, ek, Ak, Gre, accs);
         else           tile_accumulate<false>(sh, tile, ek, sd, acc);
-        if (IMAGE) tile_accumulate<false>(shI, tile, ekG, sd, accI);
+        if (IMAGE) {
+            if (MODE == kSweepMV) tile_accumulate_image_real(shI, tile, ekG, accI);   // only Re(T_img) is needed
+            else tile_accumulate<false>(shI, tile, ekG, sd, accI);
+        }
     }
 
     // ---- publish the partial sums, elect the finishing CTA of this row cell --------------------
@@ -650,6 +699,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                     // the same row sum verifies the iterate: r = b - M a, and prepares the next one in case it is needed
                     double Ar = (sumx - ak) + 2.0 * T[r].x;
                     double Ai = 2.0 * T[r].y;
+                    if (a.A_out) mirror_store(a.comm, a.A_out + o, make_double2(Ar, Ai));
                     double Kx = a.cK * (zp.x * Ar - zp.y * Ai);
                     if (IMAGE) Kx -= inv4pi * (sumx + 2.0 * TI[r].x);
                     double res = a.g.b[o] - fma(a.g.Mdiag[o], ak, Kx);
@@ -743,6 +793,7 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
         ctrl->iters = iters;
         ctrl->rel2 = worst;
         ctrl->prev_rel2 = worst;
+        if (iters == 1) ctrl->first_rel2 = worst;
         ctrl->final_buf = final_buf;
         if (conv || stagnated || iters >= max_iters) {
             ctrl->converged = (conv || stagnated) ? 1 : 0;

@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
                         mirror_store2(a.comm, a.dphi + o, make_double2(d, 0.0));
                     }
                     if (a.combined) {   // verify the iterate with the same row sum: r = b - M a; next iterate in case it is needed
+                        if (a.A_out) mirror_store2(a.comm, a.A_out + o, make_double2(Ar, Ai));
                         double res = a.g.b[o] - fma(a.g.Mdiag[o], xk, a.cK * (zp.x * Ar - zp.y * Ai));
                         mirror_store2(a.comm, a.x_out + o, fma(a.omega, res, xk));
                         sr += res * res;
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
         c->iters = iters;
         c->rel2 = worst;
         c->prev_rel2 = worst;
+        if (iters == 1) c->first_rel2 = worst;
         c->final_buf = a.final_buf_on_done;
         if (conv || stagnated || iters >= a.max_iters) {
             c->converged = (conv || stagnated) ? 1 : 0;

@@ -107,6 +107,7 @@ struct rb_solver {
     char* arena = nullptr;
     size_t arena_bytes = 0;
     double2* kbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+    double2* Abuf[2] = {nullptr, nullptr};   // row sums A_k of the iterate a combined sweep verified, by iterate-buffer parity (arena)
     CommView comm;
     void* peer_mapped[kMaxRanks] = {};
     unsigned long long* epochs = nullptr;   // [2] signal / wait counters + error flag
@@ -144,6 +145,8 @@ struct rb_solver {
     long long num_solves = 0;
     long long vel_sweeps = 0;        // velocity-only sweeps (the combined verify+velocity sweeps are counted in sum_iters)
     bool combined_ok = true;         // RB_COMBINED=0 disables the combined sweep
+    bool optimistic = false;         // recorded steps: the FIRST sweep is already a combined one (guess expected to verify as is)
+    bool hist_store_next = true;     // RB_HIST_NEXT=0: history keeps the verified iterate instead of its successor
 
     const double2* cur_Z = nullptr;
     const double2* cur_Phi = nullptr;
@@ -382,12 +385,13 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     size_t pc = (size_t)s->ncell * batch;
     {
         auto up256 = [](size_t v) { return (v + 255) / 256 * 256; };
-        size_t off = 0, ox[2], oxs[2], ok[4];
+        size_t off = 0, ox[2], oxs[2], ok[4], oA[2];
         for (int i = 0; i < 2; ++i) { ox[i] = off; off += up256(BN * sizeof(double)); }
         for (int i = 0; i < 2; ++i) { oxs[i] = off; off += up256(pc * sizeof(double)); }
         s->comm.off_rn = off; off += up256(2 * kMaxRanks * sizeof(double));
         s->comm.off_flags = off; off += up256(kMaxRanks * sizeof(unsigned long long));
         for (int i = 0; i < 4; ++i) { ok[i] = off; off += up256(2 * BN * sizeof(double2)); }
+        for (int i = 0; i < 2; ++i) { oA[i] = off; off += up256(BN * sizeof(double2)); }
         s->arena_bytes = off;
         s->arena = dmalloc<char>(off);
         RB_CUDA(cudaMemset(s->arena, 0, off));
@@ -396,6 +400,7 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
             s->xsum_part[i] = reinterpret_cast<double*>(s->arena + oxs[i]);
         }
         for (int i = 0; i < 4; ++i) s->kbuf[i] = reinterpret_cast<double2*>(s->arena + ok[i]);
+        for (int i = 0; i < 2; ++i) s->Abuf[i] = reinterpret_cast<double2*>(s->arena + oA[i]);
         s->epochs = dmalloc<unsigned long long>(4);
         RB_CUDA(cudaMemset(s->epochs, 0, 4 * sizeof(unsigned long long)));
         s->comm.nranks = 1;
@@ -479,6 +484,7 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
         RB_CUDA(cudaMemcpy(s->fft_tw, tw.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
     }
     s->combined_ok = env_int("RB_COMBINED", 1) != 0;
+    s->hist_store_next = env_int("RB_HIST_NEXT", 1) != 0;
     plan_sweep2(s);
     choose_sweep_kernel(s);
     set_stream(s, nullptr);
@@ -889,16 +895,20 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     const double* warm = nullptr;
     if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
     launch_guess(s->b, warm, s->hist, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell,
-                 st);
+                 st, s->Zp(), s->Mdiag, s->cK);
     SweepArgs base = base_args(s, Z);
-    {   // sweep 0 can only improve the iterate (nothing has produced velocities yet): it never declares convergence
+    // optimistic: the extrapolated guess is expected to verify as it stands, so sweep 0 is already a combined sweep and a
+    // well-predicted RHS costs ONE O(N^2) sweep; otherwise sweep 0 is the cheaper solver sweep that cannot declare convergence
+    // (nothing has produced velocities yet)
+    const int first_combined = s->optimistic ? 0 : 1;
+    if (!s->optimistic) {
         SweepArgs first = base;
         first.tol2 = -1.0;
         launch_mv(s, first, 0, 1);
     }
-    for (int i = 1; i < s->fixed_sweeps; ++i) {
+    for (int i = first_combined; i < s->fixed_sweeps; ++i) {
         const double* xi = s->xbuf[i & 1];
-        if (i >= 2 && s->own_fft_skippable)   // surplus round: almost always skipped -> use the kernel that can skip itself
+        if (i >= first_combined + 1 && s->own_fft_skippable)   // surplus round: almost always skipped -> use the kernel that can skip itself
             launch_fft_real_derivative(xi, s->aprime, s->N, s->logN, s->batch, s->fft_tw, 2.0 * kPi / s->N, s->ctrl, st);
         else
             real_derivative(s, xi, s->aprime, s->ctrl);   // own kernel: skips itself once the solve is finished
@@ -916,11 +926,15 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
         a.vel_upper = s->vel_upper;
         a.rhs_phi_kind = s->rhs_phi_kind;
         a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
+        a.A_out = s->hist.Abase ? s->Abuf[i & 1] : nullptr;
         sweep(s, a, kSweepVEL);
         if (s->comm.nranks > 1)
             launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, a.final_buf_on_done, s->bnorm_part, s->ncell, a.tol2, a.max_iters, st);
     }
-    launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, nullptr, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
+    HistoryRing hist_out = s->hist;
+    hist_out.store_next = s->hist_store_next ? 1 : 0;
+    launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, nullptr, s->xsum_a, hist_out, s->N, s->batch, s->ncell, st,
+                        s->hist.Abase ? s->Abuf[0] : nullptr, s->Abuf[1]);
     s->have_prev_a = true;
     rhs_tail(s, state, out, user_out);
 }
@@ -954,7 +968,7 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
 // ------------------------------------------------------------------------------------------------
 // the RK4 stepper
 // ------------------------------------------------------------------------------------------------
-constexpr int kHistRing = 5;   // > max order (4): a repeated step never reads a slot it has already overwritten
+constexpr int kHistRing = 7;   // > max order (6): a repeated step never reads a slot it has already overwritten
 
 struct rb_stepper {
     rb_solver* s = nullptr;
@@ -968,9 +982,17 @@ struct rb_stepper {
     int* d_counter = nullptr;     // device: completed steps since the history was reset
     int h_counter = 0;            // host mirror
     int order = 4;                // extrapolation order (RB_GUESS_ORDER)
+    int predict = 0;              // guess = one Richardson sweep whose row sums are extrapolated in time (RB_GUESS_PREDICT; auto: on
+                                  // for tolerances above the round-off floor of that extrapolation)
     // CUDA graph of one step (fixed number of self-skipping sweeps per solve)
     bool use_graph = true;
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;      // the graph in use (owned by graph_cache)
+    cudaGraphExec_t graph_cache[16] = {};      // one recorded step per mask of optimistic stages
+    int opt_mask = 0;                          // bit i: stage i starts with a combined sweep (its guess verified as it stood lately)
+    int graph_mask = 0;                        // mask graph_exec was recorded with
+    int opt_policy = 1;                        // RB_OPTIMISTIC: 0 never, 1 adaptive per stage, 2 always
+    long long opt_stage_solves = 0, one_sweep_solves = 0;
+    double first_rel[4] = {0, 0, 0, 0};        // residual of the initial iterate of each stage in the last step
     int graph_sweeps = 0;
     double graph_dt = 0;
     double2* graph_y0 = nullptr;
@@ -985,7 +1007,8 @@ struct rb_stepper {
 
 static void stepper_free(rb_stepper* st) {
     if (!st) return;
-    if (st->graph_exec) cudaGraphExecDestroy(st->graph_exec);
+    for (auto& g : st->graph_cache)
+        if (g) cudaGraphExecDestroy(g);
     if (st->ev) cudaEventDestroy(st->ev);
     if (st->owns_y0 && st->y0) cudaFree(st->y0);
     if (st->ytmp) cudaFree(st->ytmp);
@@ -1019,8 +1042,14 @@ static void issue_step(rb_stepper* st, int fixed_sweeps) {
             s->hist.ring = kHistRing;
             s->hist.order = st->order;
             s->hist.counter = st->d_counter;
+            // row-sum history only where the combined sweep produces it (recorded steps of the Richardson path)
+            const bool keepA = st->predict && fixed_sweeps >= 2 && !s->use_gmres && s->combined_ok && !s->has_image;
+            s->hist.Abase = keepA ? reinterpret_cast<double2*>(st->hist[i] + (size_t)kHistRing * s->BN) : nullptr;
+            s->hist.predict = keepA ? 1 : 0;
         }
+        s->optimistic = fixed_sweeps > 0 && ((st->opt_mask >> i) & 1);
         rhs(s, y, st->k[i]);
+        s->optimistic = false;
     };
     stage(0, st->y0);
     launch_stage_update(st->ytmp, st->y0, st->k[0], h * 0.5, n2, cs);
@@ -1038,10 +1067,12 @@ static void issue_step(rb_stepper* st, int fixed_sweeps) {
 
 static void capture_graph(rb_stepper* st, int sweeps) {
     rb_solver* s = st->s;
-    if (st->graph_exec) {
-        cudaGraphExecDestroy(st->graph_exec);
-        st->graph_exec = nullptr;
+    cudaGraphExec_t& slot = st->graph_cache[st->opt_mask & 15];
+    if (slot) {
+        cudaGraphExecDestroy(slot);
+        slot = nullptr;
     }
+    st->graph_exec = nullptr;
     cudaGraph_t graph = nullptr;
     const unsigned long long launches_before = rb::g_launch_count;
     RB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
@@ -1056,8 +1087,10 @@ static void capture_graph(rb_stepper* st, int sweeps) {
     }
     RB_CUDA(cudaStreamEndCapture(s->stream, &graph));
     rb::g_launch_count = launches_before;   // recorded, not launched
-    RB_CUDA(cudaGraphInstantiate(&st->graph_exec, graph, 0));
+    RB_CUDA(cudaGraphInstantiate(&slot, graph, 0));
     RB_CUDA(cudaGraphDestroy(graph));
+    st->graph_exec = slot;
+    st->graph_mask = st->opt_mask;
     st->graph_sweeps = sweeps;
     st->graph_dt = st->dt;
     st->graph_y0 = st->y0;
@@ -1087,6 +1120,15 @@ static void after_step(rb_stepper* st) {
     }
 }
 
+static void invalidate_graphs(rb_stepper* st) {
+    for (auto& g : st->graph_cache)
+        if (g) {
+            cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
+    st->graph_exec = nullptr;
+}
+
 static void stepper_step(rb_stepper* st) {
     rb_solver* s = st->s;
     const bool graphable = st->use_graph && s->matrix_free_solve && !s->use_gmres;   // GMRES is host-driven
@@ -1096,11 +1138,14 @@ static void stepper_step(rb_stepper* st) {
         after_step(st);
         return;
     }
-    if (!st->graph_exec || st->graph_dt != st->dt || st->graph_y0 != st->y0) {
+    if (st->graph_dt != st->dt || st->graph_y0 != st->y0) invalidate_graphs(st);   // recorded constants changed
+    st->graph_exec = st->graph_cache[st->opt_mask & 15];
+    if (!st->graph_exec) {
         int sweeps = st->graph_sweeps > 0 ? st->graph_sweeps : std::min(s->props.max_iterations, 16);
         sweeps = std::max(sweeps, 2);
         capture_graph(st, sweeps);
     }
+    const int mask = st->opt_mask;
     RB_CUDA(cudaGraphLaunch(st->graph_exec, s->stream));
     rb::count_launch((int)kernels_per_step(s, st->graph_sweeps));
     st->graph_launches++;
@@ -1111,7 +1156,8 @@ static void stepper_step(rb_stepper* st) {
     for (int i = 0; i < 4; ++i) {
         const SolveCtrl& c = s->h_ctrl[i];
         all_done = all_done && c.done;
-        worst = std::max(worst, c.iters);
+        // sweeps this solve occupied in the recorded sequence (an optimistic stage has no leading solver sweep)
+        worst = std::max(worst, c.iters + (((mask >> i) & 1) ? 1 : 0));
     }
     if (!all_done) {
         // some solve ran out of recorded sweeps: roll the step back and redo it with the synchronising loop
@@ -1123,18 +1169,35 @@ static void stepper_step(rb_stepper* st) {
         }
         issue_step(st, 0);
         st->fallback_steps++;
+        if (st->predict && s->props.guess_mode == RB_GUESS_WARM) {
+            // the synchronising loop records no row sums: the rings are inconsistent for this step -> start the history afresh
+            stepper_reset_history(st);
+            st->h_counter = -1;   // incremented to 0 below, matching the device counter
+        }
         worst = std::max(worst, s->kpred);
         int sweeps = std::min(s->props.max_iterations, worst + 4);
         st->graph_sweeps = sweeps;
-        if (st->graph_exec) {
-            cudaGraphExecDestroy(st->graph_exec);
-            st->graph_exec = nullptr;
-        }
+        st->opt_mask = st->opt_policy == 2 ? 15 : 0;
+        invalidate_graphs(st);
     } else {
+        const double tol2 = s->props.tolerance * s->props.tolerance;
+        int next_mask = 0;
         for (int i = 0; i < 4; ++i) {
-            s->sum_iters += s->h_ctrl[i].iters;
+            const SolveCtrl& c = s->h_ctrl[i];
+            s->sum_iters += c.iters;
             s->num_solves++;
+            st->first_rel[i] = std::sqrt(std::max(0.0, c.first_rel2));
+            if ((mask >> i) & 1) {
+                st->opt_stage_solves++;
+                if (c.iters == 1) st->one_sweep_solves++;
+            }
+            // adaptive policy: a failed optimistic stage costs 13 + 13 instead of 11 + 13 instructions per pair, a successful one 13
+            // instead of 24, so a stage is optimistic whenever its last guess came within twice the tolerance
+            if (c.first_rel2 <= 4.0 * tol2) next_mask |= 1 << i;
         }
+        if (st->opt_policy == 0) next_mask = 0;
+        if (st->opt_policy == 2) next_mask = 15;
+        st->opt_mask = next_mask;
         s->last_iters = s->h_ctrl[3].iters;
         s->last_converged = s->h_ctrl[3].converged;
         s->last_rel = std::sqrt(std::max(0.0, s->h_ctrl[3].rel2));
@@ -1142,8 +1205,7 @@ static void stepper_step(rb_stepper* st) {
         if (st->graph_sweeps - worst >= 3) {
             if (++st->graph_hits_below >= 8) {
                 st->graph_sweeps = worst + 1;
-                cudaGraphExecDestroy(st->graph_exec);
-                st->graph_exec = nullptr;
+                invalidate_graphs(st);
             }
         } else {
             st->graph_hits_below = 0;
@@ -1371,8 +1433,8 @@ rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
         st->ytmp = dmalloc<double2>(n2);
         st->ybackup = dmalloc<double2>(n2);
         for (auto& p : st->hist) {
-            p = dmalloc<double>((size_t)kHistRing * s->BN);
-            RB_CUDA(cudaMemset(p, 0, (size_t)kHistRing * s->BN * sizeof(double)));
+            p = dmalloc<double>((size_t)3 * kHistRing * s->BN);   // ring of solutions a | ring of their row sums A (complex)
+            RB_CUDA(cudaMemset(p, 0, (size_t)3 * kHistRing * s->BN * sizeof(double)));
         }
         st->d_counter = dmalloc<int>(1);
         RB_CUDA(cudaMemset(st->d_counter, 0, sizeof(int)));
@@ -1380,8 +1442,14 @@ rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
         // extrapolation order of the stage history: 4 points wins where the truncation error of the guess dominates; at large N
         // the round-off noise of the spectral derivatives (~N eps) dominates and the wider stencil amplifies it (measured at
         // N = 65536: 2.00 sweeps per solve with 3 points, 2.10 with 4)
-        st->order = std::max(1, std::min(4, env_int("RB_GUESS_ORDER", s->N >= 32768 ? 3 : 4)));
+        st->order = std::max(1, std::min(kHistRing - 1, env_int("RB_GUESS_ORDER", s->N >= 32768 ? 3 : 4)));
+        {
+            const int pr = env_int("RB_GUESS_PREDICT", -1);
+            st->predict = pr >= 0 ? (pr != 0) : (s->props.tolerance >= 4e-13);
+        }
         st->use_graph = env_int("RB_NO_GRAPH", 0) == 0;
+        st->opt_policy = std::max(0, std::min(2, env_int("RB_OPTIMISTIC", 1)));
+        st->opt_mask = st->opt_policy == 2 ? 15 : 0;
         return up.release();
     } catch (const std::exception& e) {
         fail(e);
@@ -1459,6 +1527,29 @@ int rb_rk4_stats(rb_stepper* st, double out_host[4]) {
     out_host[2] = (double)st->fallback_steps;
     out_host[3] = (double)st->graph_sweeps;
     return 0;
+}
+int rb_rk4_guess_stats(rb_stepper* st, double out_host[8]) {
+    for (int i = 0; i < 4; ++i) out_host[i] = st->first_rel[i];
+    out_host[4] = (double)st->opt_mask;
+    out_host[5] = (double)st->opt_stage_solves;
+    out_host[6] = (double)st->one_sweep_solves;
+    out_host[7] = (double)st->opt_policy;
+    return 0;
+}
+int rb_rk4_set_optimistic(rb_stepper* st, int policy) {
+    if (policy < 0 || policy > 2) return -1;
+    st->opt_policy = policy;
+    st->opt_mask = policy == 2 ? 15 : 0;
+    return 0;
+}
+int rb_rk4_set_guess(rb_stepper* st, int order, int predict) {
+    RB_TRY
+    if (order < 1 || order >= kHistRing) throw std::runtime_error("rb_rk4_set_guess: order must be in 1..6");
+    st->order = order;
+    st->predict = predict < 0 ? (st->s->props.tolerance >= 4e-13) : (predict != 0);
+    stepper_reset_history(st);   // the rings of the two modes hold different iterates
+    invalidate_graphs(st);
+    RB_CATCH
 }
 double rb_rk4_current_time(rb_stepper* st) { return st->t; }
 
@@ -1631,6 +1722,43 @@ int rb_measure_fp64_peak(double* tflops_out, void* stream) {
     }
     double flops = (double)blocks * 256.0 * iters * 64.0 * 2.0;
     *tflops_out = flops / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    RB_CATCH
+}
+
+// DMMA (m8n8k4, 512 flop per warp instruction) beside DFMA (64 flop per warp instruction): out[2*i] = ms, out[2*i+1] = TFLOP/s of
+// mix i in {8 mma, 32 fma, 8+32, 4+32, 2+32, 1+32} per loop iteration
+int rb_measure_fp64_tensor_overlap(double out_host[12], void* stream) {
+    RB_TRY
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sink = dmalloc<double>(1);
+    int sms = 0, dev = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, iters = 2048;
+    cudaEvent_t e0, e1;
+    RB_CUDA(cudaEventCreate(&e0));
+    RB_CUDA(cudaEventCreate(&e1));
+    const int mixes[6][2] = {{8, 0}, {0, 32}, {8, 32}, {4, 32}, {2, 32}, {1, 32}};
+    for (int m = 0; m < 6; ++m) {
+        launch_fp64_mix(sink, 64, blocks, mixes[m][0], mixes[m][1], st);
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            RB_CUDA(cudaEventRecord(e0, st));
+            launch_fp64_mix(sink, iters, blocks, mixes[m][0], mixes[m][1], st);
+            RB_CUDA(cudaEventRecord(e1, st));
+            RB_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            RB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        const double warps = (double)blocks * 8.0;
+        const double flops = warps * iters * (mixes[m][0] * 512.0 + mixes[m][1] * 64.0);
+        out_host[2 * m] = best;
+        out_host[2 * m + 1] = flops / (best * 1e-3) / 1e12;
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);

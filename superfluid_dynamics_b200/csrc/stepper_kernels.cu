@@ -84,6 +84,53 @@ __global__ void __launch_bounds__(256) fp64_peak3_kernel(double* sink, int iters
     if (s == 123.456) sink[0] = s;
 }
 
+// ---- does the FP64 tensor path (DMMA m8n8k4) issue beside the FP64 vector pipe?  NM mma.sync + NF DFMA per loop iteration, all
+// chains independent.  time(NM, NF) ~ max(time(NM, 0), time(0, NF)) means separate pipes, ~ sum means one shared datapath.
+template <int NM, int NF>
+__global__ void __launch_bounds__(256) fp64_mix_kernel(double* sink, int iters, double seed) {
+    double c0[NM > 0 ? NM : 1], c1[NM > 0 ? NM : 1], f[NF > 0 ? NF : 1];
+    const double ma = 0.999999 + seed + threadIdx.x * 1e-12, mb = 1e-3 + seed;
+#pragma unroll
+    for (int i = 0; i < (NM > 0 ? NM : 1); ++i) { c0[i] = threadIdx.x * 1e-3 + i; c1[i] = c0[i] + 0.5; }
+#pragma unroll
+    for (int i = 0; i < (NF > 0 ? NF : 1); ++i) f[i] = threadIdx.x * 1e-3 + i;
+    const double m = 0.999999, c = 1e-7;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < (NM > NF ? NM : NF); ++i) {
+            if (i < NM)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c0[i]), "+d"(c1[i]) : "d"(ma), "d"(mb));
+            if (NM > 0 && NF > NM) {   // spread the DFMAs between the mma instructions
+#pragma unroll
+                for (int u = 0; u < NF / NM; ++u) f[i * (NF / NM) + u] = fma(f[i * (NF / NM) + u], m, c);
+            } else if (i < NF) {
+                f[i] = fma(f[i], m, c);
+            }
+        }
+    }
+    double sum = 0;
+#pragma unroll
+    for (int i = 0; i < (NM > 0 ? NM : 1); ++i) sum += c0[i] + c1[i];
+#pragma unroll
+    for (int i = 0; i < (NF > 0 ? NF : 1); ++i) sum += f[i];
+    if (sum == 123.456) sink[0] = sum;
+}
+
+void launch_fp64_mix(double* sink, int iters, int blocks, int nm, int nf, cudaStream_t st) {
+    const double seed = 1e-9;
+    if (nm == 8 && nf == 0) fp64_mix_kernel<8, 0><<<blocks, 256, 0, st>>>(sink, iters, seed);
+    else if (nm == 0 && nf == 32) fp64_mix_kernel<0, 32><<<blocks, 256, 0, st>>>(sink, iters, seed);
+    else if (nm == 8 && nf == 32) fp64_mix_kernel<8, 32><<<blocks, 256, 0, st>>>(sink, iters, seed);
+    else if (nm == 4 && nf == 32) fp64_mix_kernel<4, 32><<<blocks, 256, 0, st>>>(sink, iters, seed);
+    else if (nm == 2 && nf == 32) fp64_mix_kernel<2, 32><<<blocks, 256, 0, st>>>(sink, iters, seed);
+    else if (nm == 1 && nf == 32) fp64_mix_kernel<1, 32><<<blocks, 256, 0, st>>>(sink, iters, seed);
+    else throw std::runtime_error("fp64_mix: unsupported mix");
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 void launch_fp64_peak3(double* sink, int iters, int blocks, double seed, cudaStream_t st) {
     fp64_peak3_kernel<<<blocks, 256, 0, st>>>(sink, iters, seed);
     RB_CUDA(cudaGetLastError());

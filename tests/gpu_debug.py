@@ -214,6 +214,47 @@ def ensemble():
     print(f"ensemble sweep: {ms * 1e3:.1f} us, {20 * pairs / (ms * 1e-3) / 1e12:.2f} TFLOP/s")
 
 
+def optimistic():
+    """first sweep already combined (verify + velocities) when the guess (extrapolation + predicted row sums) is good enough:
+    sweeps per solve and step rate against the solve tolerance"""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    for N, h, dt, steps in ((1024, 0.4, 1e-3, 200), (4096, 0.4, 1e-3, 200), (16384, 0.4, 2e-4, 60), (65536, 0.4, 1e-4, 30)):
+        ref = None
+        for tol, order, policy, predict in ((1e-13, 4, 0, 0), (1e-13, 4, 1, -1), (1e-12, 4, 1, -1), (1e-12, 5, 1, -1), (1e-11, 4, 1, -1),
+                                            (1e-10, 4, 1, -1), (1e-10, 3, 1, -1)):
+            props = api.ProblemProperties(rho=0.0)
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm", tolerance=tol)
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+            stp.setGuess(order, predict)
+            stp.setOptimistic(policy)
+            Z, Phi = ro.trochoid(N, h)
+            st = T(ro.pack_state(Z, Phi))
+            stp.initialize(st, True)
+            stp.runSteps(12)
+            torch.cuda.synchronize()
+            s0 = calc.solve_stats()
+            t0 = time.time()
+            stp.runSteps(steps)
+            torch.cuda.synchronize()
+            el = time.time() - t0
+            s1 = calc.solve_stats()
+            its = (s1["total_iterations"] - s0["total_iterations"]) / max(1, s1["total_solves"] - s0["total_solves"])
+            y = st.cpu().numpy()
+            if ref is None:
+                ref = y
+            gs = stp.guessStats()
+            print(f"optimistic N={N} dt={dt} tol={tol:g} order={order} policy={policy} predict={predict}: {steps / el:.1f} steps/s, "
+                  f"{its:.2f} sweeps/solve, first_rel={['%.1e' % v for v in gs['first_rel']]} mask={gs['opt_mask']} "
+                  f"one_sweep={gs['one_sweep_solves']}/{gs['optimistic_solves']} dev_vs_first={rel(y, ref):.2e} "
+                  f"final_rel={s1['residual']:.1e} {stp.stats()}", flush=True)
+
+
+def dmma():
+    print("fp64 peak TFLOP/s", api.measure_fp64_peak())
+    for k, (ms, tf) in api.measure_fp64_tensor_overlap().items():
+        print(f"dmma-overlap {k}: {ms:.3f} ms, {tf:.2f} TFLOP/s", flush=True)
+
+
 def speed():
     print("fp64 peak TFLOP/s", api.measure_fp64_peak(), " 3-register-operand DFMA:", api.measure_fp64_rate_3operand())
     for N in (1024, 4096, 16384, 65536):

@@ -508,6 +508,40 @@ def test_graph_rollback_when_recorded_sweeps_do_not_suffice(api):
     assert rel(res["0"][0], res["1"][0]) <= 1e-12
 
 
+def test_single_sweep_rhs_with_predicted_row_sums(api):
+    """Optimistic stages: with the row sums of the extrapolated iterate predicted from their own history (O(N) work), the first
+    O(N^2) sweep of a solve already verifies the iterate and delivers its velocities -- one sweep per RHS.  The predicted iterate
+    is only ever a starting point: every solve still ends on a verified residual <= tolerance, so the trajectory must agree with
+    the never-optimistic run to the solve tolerance, and with the oracle to the north_star bar."""
+    N, h, dt, steps, tol = 1024, 0.3, 5e-4, 80, 1e-11
+    Z, Phi = ro.trochoid(N, h)
+    y0 = ro.pack_state(Z, Phi)
+    props = api.ProblemProperties(rho=0.0)
+    oprops = ro.ProblemProperties(rho=0.0)
+    out = {}
+    for policy in (0, 1):
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm", tolerance=tol)
+        stp = api.AutonomousRungeKuttaStepper(calc, dt)
+        stp.setGuess(4, 1)
+        stp.setOptimistic(policy)
+        stp.initialize(y0, False)
+        stp.runSteps(steps)
+        out[policy] = (stp.getState(), stp.guessStats(), calc.solve_stats(), stp.stats())
+    gs = out[1][1]
+    assert out[0][1]["optimistic_solves"] == 0
+    assert gs["optimistic_solves"] > 0 and gs["one_sweep_solves"] >= 0.9 * gs["optimistic_solves"], gs
+    assert max(gs["first_rel"]) <= tol, gs            # the guess verified as it stood
+    assert out[1][2]["converged"] and out[0][2]["converged"]
+    # fewer O(N^2) sweeps in total
+    assert out[1][2]["total_iterations"] < 0.75 * out[0][2]["total_iterations"], (out[0][2], out[1][2])
+    assert rel(out[1][0], out[0][0]) <= 1e-9
+    f = lambda s: ro.rhs(s, N, 1, oprops, "water", "cuda")
+    ye = y0.copy()
+    for _ in range(steps):
+        ye = ro.rk4_step(f, ye, dt)
+    assert rel(out[1][0][:N], ye[:N]) <= 1e-9 and rel(out[1][0][N:], ye[N:]) <= 1e-9
+
+
 def test_row_sharded_two_gpus_match_single_gpu(api):
     """N > 1: row-sharded run on two GPUs (torchrun, one rank per GPU) vs the single-GPU run; skipped on a one-GPU box."""
     import subprocess
