@@ -310,7 +310,10 @@ static void choose_sweep_kernel(rb_solver* s) {
     int nSM = 148;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
     const double eff = s->v2_eff;
-    bool v2 = !s->has_image && (eff >= 0.95 || (long)s->N * s->batch <= 4096);
+    // measured on a B200 (MV sweep, us; tiled / persistent): N=256 18.5/12.3, 1024 18.5/18.5, 2048 21.8/25.2, 4096 34.8/37.3,
+    // 8192 84/96, 16384 250/287, 32768 891/968, 65536 3512/3380
+    // ensembles (batch > 1) keep the persistent kernel whenever its schedule fills the SMs
+    bool v2 = !s->has_image && ((eff >= 0.95 && ((long)s->N >= 49152 || s->batch > 1)) || (long)s->N * s->batch <= 1024);
     int force = env_int("RB_SWEEP_V2", -1);
     if (force >= 0) v2 = !s->has_image && force != 0;
     s->use_v2 = v2;
@@ -908,7 +911,7 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     }
     for (int i = first_combined; i < s->fixed_sweeps; ++i) {
         const double* xi = s->xbuf[i & 1];
-        if (i >= first_combined + 1 && s->own_fft_skippable)   // surplus round: almost always skipped -> use the kernel that can skip itself
+        if (i >= first_combined + 1 && s->own_fft_skippable && !s->own_fft)   // surplus round: almost always skipped -> use the kernel that can skip itself
             launch_fft_real_derivative(xi, s->aprime, s->N, s->logN, s->batch, s->fft_tw, 2.0 * kPi / s->N, s->ctrl, st);
         else
             real_derivative(s, xi, s->aprime, s->ctrl);   // own kernel: skips itself once the solve is finished

@@ -102,9 +102,10 @@ __global__ void __launch_bounds__(256) fp64_mix_kernel(double* sink, int iters, 
             if (i < NM)
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                              : "+d"(c0[i]), "+d"(c1[i]) : "d"(ma), "d"(mb));
+            constexpr int PERM = NM > 0 ? NF / (NM > 0 ? NM : 1) : 0;   // DFMAs per mma instruction
             if (NM > 0 && NF > NM) {   // spread the DFMAs between the mma instructions
 #pragma unroll
-                for (int u = 0; u < NF / NM; ++u) f[i * (NF / NM) + u] = fma(f[i * (NF / NM) + u], m, c);
+                for (int u = 0; u < PERM; ++u) f[i * PERM + u] = fma(f[i * PERM + u], m, c);
             } else if (i < NF) {
                 f[i] = fma(f[i], m, c);
             }

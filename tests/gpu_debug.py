@@ -187,6 +187,32 @@ def v2cmp():
     os.environ.pop("RB_SWEEP_V2", None); os.environ.pop("RB_VERBOSE", None)
 
 
+def tune2():
+    """persistent sweep at small N: source groups per CTA (threads = 32 * groups at R = 1), rows per thread, tiled kernel beside it"""
+    for N in (1024, 2048, 4096, 8192):
+        Z, Phi = ro.trochoid(N, 0.4)
+        st = T(ro.pack_state(Z, Phi))
+        cfgs = [dict(RB_SWEEP_V2="0")]
+        for G in (4, 8, 16, 32):
+            cfgs.append(dict(RB_SWEEP_V2="1", RB_V2_GROUPS=str(G), RB_V2_RB="32", RB_V2_R="1"))
+        for G in (4, 8, 16):
+            cfgs.append(dict(RB_SWEEP_V2="1", RB_V2_GROUPS=str(G), RB_V2_RB="64", RB_V2_R="2"))
+        if N >= 4096:
+            for G in (4, 8):
+                cfgs.append(dict(RB_SWEEP_V2="1", RB_V2_GROUPS=str(G), RB_V2_RB="64", RB_V2_R="2", RB_V2_SPLIT="2"))
+        for cfg in cfgs:
+            os.environ.update(cfg)
+            try:
+                props = api.ProblemProperties(rho=0.0)
+                calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+                ms, pairs = calc.benchSweep(st, 50)
+                print(f"tune2 N={N} {cfg}: {ms * 1e3:.1f} us  {20 * pairs / (ms * 1e-3) / 1e12:.2f} TF", flush=True)
+            except Exception as e:
+                print(f"tune2 N={N} {cfg}: FAILED {e}", flush=True)
+            for k in cfg:
+                os.environ.pop(k, None)
+
+
 def ensemble():
     """BASELINE config 5, second half: 1024-member ensemble at N = 512 (replicas only across GPUs)"""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
