@@ -87,6 +87,26 @@ struct CommView {
     int* error_flag = nullptr;           // set when a wait timed out
 };
 
+// work folded into the kernel that closes a solve (finish_solve): the velocity terms a combined sweep left open because their
+// inputs were still being transformed on the side stream, dPhi/dt, and the RK stage / final update of the stepper
+struct FinishPost {
+    double2* vel = nullptr;              // u + i v rows as the sweep left them (nullptr: nothing to do)
+    double2* vel_upper = nullptr;
+    double2* dphi = nullptr;             // dPhi/dt + 0 i (nullptr: computed by a separate kernel)
+    const double2* aprime0 = nullptr;    // a' of the iterate in buffer 0 / 1 (nullptr: the sweep already added V2 a')
+    const double2* aprime1 = nullptr;
+    const double2* V2 = nullptr;
+    const double2* Z = nullptr;
+    int rhs_phi_kind = 0;
+    double depth = 0.0;
+    int update = 0;                      // 0 none, 1: y_out = y0 + c k, 2: y_out += c (k1 + 2 k2 + 2 k3 + k) with c = h/6
+    double c = 0.0;
+    const double2* y0 = nullptr;
+    double2* y_out = nullptr;
+    const double2 *k1 = nullptr, *k2 = nullptr, *k3 = nullptr;
+    size_t BN = 0;
+};
+
 enum SweepMode { kSweepMV = 0, kSweepVEL = 1, kSweepRAW = 2 };
 
 struct SweepArgs {
@@ -135,6 +155,7 @@ struct SweepArgs {
     double2* dphi;                   // dPhi/dt + 0 i -> rhs[BN .. 2BN)  (nullptr: separate kernel)
     double2* raw_out;                // RAW: S_k = sum_{j!=k} cot((z_k - z_j)/2) x_j
     double2* A_out;                  // combined VEL sweeps: A_k of the input iterate (kept for the time extrapolation of the row sums)
+    int defer_aprime;                // VEL sweeps: leave V2 a' and dPhi/dt to finish_solve (a' is transformed beside this sweep)
     CommView comm;                   // row sharding over GPUs (nranks == 1: off)
     // persistent one-wave variant (sweep2_kernel): static schedule of row blocks, in-CTA source split, no global partials
     int v2_RB;                       // rows per row block (multiple of 32 * R)
@@ -187,7 +208,11 @@ void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int bat
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st);
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
                          double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st,
-                         const double2* A0 = nullptr, const double2* A1 = nullptr);
+                         const double2* A0 = nullptr, const double2* A1 = nullptr, const FinishPost* post = nullptr);
+void launch_geometry_guess(const Geometry& g, double2* phiprime_c, int N, int batch, int ncell, double rhoM, double depth,
+                           int finite_image, int use_local, double rho, double U, const double* warm, const HistoryRing& hist,
+                           double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl, double omega, double cK,
+                           cudaStream_t st);
 // krylov_kernels.cu
 void launch_multi_dot(const double* V, size_t ldv, int nvec, const double* w, double* out, int n, cudaStream_t st);
 void launch_multi_axpy(double* w, const double* V, size_t ldv, int nvec, const double* h, double sign, int n, cudaStream_t st);

@@ -122,13 +122,9 @@ __device__ __forceinline__ double2 local_coord(double2 z, double2 zc) {
 // ------------------------------------------------------------------------------------------------
 // geometry: everything that depends on the surface only (once per RHS, reused by every sweep)
 // ------------------------------------------------------------------------------------------------
-__global__ void geometry_kernel(Geometry g, double2* __restrict__ phiprime_c, int N, int batch, int ncell, int physics,
-                                double rhoM, double depth, int finite_image, int use_local, int raw_derivs, double rho,
-                                double U) {
-    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (size_t)N * batch) return;
-    int b = (int)(tid / N);
-    int i = (int)(tid - (size_t)b * N);
+__device__ __forceinline__ void geometry_point(const Geometry& g, double2* __restrict__ phiprime_c, int N, int ncell, double rhoM,
+                                               double depth, int finite_image, int use_local, int raw_derivs, double rho, double U,
+                                               size_t tid, int i, int b) {
     const double2* Zb = g.Z + (size_t)b * N;
     double2 z = Zb[i];
     double2 zp = g.Zp[tid];
@@ -180,6 +176,16 @@ __global__ void geometry_kernel(Geometry g, double2* __restrict__ phiprime_c, in
     if (phiprime_c) g.b[tid] = php.x;    // complex_to_real, L/BaseBoundaryIntegrator.cuh:299
 }
 
+__global__ void geometry_kernel(Geometry g, double2* __restrict__ phiprime_c, int N, int batch, int ncell, int physics,
+                                double rhoM, double depth, int finite_image, int use_local, int raw_derivs, double rho,
+                                double U) {
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (size_t)N * batch) return;
+    int b = (int)(tid / N);
+    int i = (int)(tid - (size_t)b * N);
+    geometry_point(g, phiprime_c, N, ncell, rhoM, depth, finite_image, use_local, raw_derivs, rho, U, tid, i, b);
+}
+
 void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, int ncell, int physics, double rhoM,
                      double depth, int finite_image, int use_local, int raw_derivs, double rho, double U, cudaStream_t st) {
     size_t n = (size_t)N * batch;
@@ -198,12 +204,11 @@ void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, i
 //       (history ring in device memory, position read from a device counter so that one CUDA graph serves every step),
 //   (b) a caller-supplied warm vector,  (c) the first Neumann term omega * b.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__ b, const double* __restrict__ warm,
-                                                       HistoryRing hist, double* __restrict__ x0,
-                                                       double* __restrict__ xsum_part, double* __restrict__ bnorm_part,
-                                                       SolveCtrl* ctrl, double omega, int N, int ncell,
-                                                       const double2* __restrict__ Zp, const double* __restrict__ Mdiag, double cK) {
-    __shared__ double sred[kCell];
+// (b, Zp, Mdiag deliberately not __restrict__: the fused geometry + guess kernel writes them through the Geometry pointers first)
+__device__ __forceinline__ void guess_cell(const double* b, const double* __restrict__ warm, const HistoryRing& hist,
+                                           double* __restrict__ x0, double* __restrict__ xsum_part,
+                                           double* __restrict__ bnorm_part, SolveCtrl* ctrl, double omega, int N, int ncell,
+                                           const double2* Zp, const double* Mdiag, double cK, double* sred) {
     int cell = blockIdx.x, bm = blockIdx.y;
     int i = cell * kCell + threadIdx.x;
     double xv = 0.0, bv = 0.0;
@@ -262,6 +267,42 @@ __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__
     }
 }
 
+__global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__ b, const double* __restrict__ warm,
+                                                       HistoryRing hist, double* __restrict__ x0,
+                                                       double* __restrict__ xsum_part, double* __restrict__ bnorm_part,
+                                                       SolveCtrl* ctrl, double omega, int N, int ncell,
+                                                       const double2* __restrict__ Zp, const double* __restrict__ Mdiag, double cK) {
+    __shared__ double sred[kCell];
+    guess_cell(b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell, Zp, Mdiag, cK, sred);
+}
+
+// geometry of a cell's points followed by the start of the solve for that cell: one launch instead of two (every thread reads back
+// only what it wrote itself: b, Zp, Mdiag of its own point)
+__global__ void __launch_bounds__(kCell) geometry_guess_kernel(Geometry g, double2* __restrict__ phiprime_c, int N, int ncell,
+                                                                double rhoM, double depth, int finite_image, int use_local,
+                                                                int raw_derivs, double rho, double U,
+                                                                const double* __restrict__ warm, HistoryRing hist,
+                                                                double* __restrict__ x0, double* __restrict__ xsum_part,
+                                                                double* __restrict__ bnorm_part, SolveCtrl* ctrl, double omega,
+                                                                double cK) {
+    __shared__ double sred[kCell];
+    const int i = blockIdx.x * kCell + threadIdx.x;
+    const int bm = blockIdx.y;
+    if (i < N)
+        geometry_point(g, phiprime_c, N, ncell, rhoM, depth, finite_image, use_local, raw_derivs, rho, U, (size_t)bm * N + i, i, bm);
+    guess_cell(g.b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell, g.Zp, g.Mdiag, cK, sred);
+}
+
+void launch_geometry_guess(const Geometry& g, double2* phiprime_c, int N, int batch, int ncell, double rhoM, double depth,
+                           int finite_image, int use_local, double rho, double U, const double* warm, const HistoryRing& hist,
+                           double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl, double omega, double cK,
+                           cudaStream_t st) {
+    geometry_guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(g, phiprime_c, N, ncell, rhoM, depth, finite_image, use_local, 1, rho,
+                                                                U, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, cK);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st,
                   const double2* Zp, const double* Mdiag, double cK) {
@@ -279,10 +320,11 @@ __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __res
                                                               const double2* __restrict__ A0, const double2* __restrict__ A1,
                                                               const SolveCtrl* ctrl, double* __restrict__ a_out,
                                                               double2* __restrict__ a_complex, double* __restrict__ xsum_part,
-                                                              HistoryRing hist, int N, int ncell) {
+                                                              HistoryRing hist, int N, int ncell, FinishPost post) {
     __shared__ double sred[kCell];
-    const double* src = (ctrl && ctrl->final_buf) ? buf1 : buf0;
-    const double* nxt = (ctrl && ctrl->final_buf) ? buf0 : buf1;   // combined sweeps: x + omega r of the verified iterate
+    const int fb = (ctrl && ctrl->final_buf) ? 1 : 0;
+    const double* src = fb ? buf1 : buf0;
+    const double* nxt = fb ? buf0 : buf1;   // combined sweeps: x + omega r of the verified iterate
     int cell = blockIdx.x, bm = blockIdx.y;
     int i = cell * kCell + threadIdx.x;
     double v = 0.0;
@@ -295,7 +337,48 @@ __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __res
             const size_t so = (size_t)(*hist.counter % hist.ring) * hist.stride + o;
             const bool keepA = hist.Abase && A0;
             hist.base[so] = (hist.store_next && !keepA) ? nxt[o] : v;   // with row sums the ring must hold the iterate they belong to
-            if (keepA) hist.Abase[so] = ((ctrl && ctrl->final_buf) ? A1 : A0)[o];
+            if (keepA) hist.Abase[so] = (fb ? A1 : A0)[o];
+        }
+        if (post.vel) {
+            // ---- what the sweep epilogue left open: the V2 a' term (its transform ran beside the sweep), dPhi/dt, the RK update ----
+            double2 u = post.vel[o];                  // conj(w) so far
+            double dphi = 0.0;
+            if (post.aprime0) {
+                const double2 ap = (fb ? post.aprime1 : post.aprime0)[o];
+                const double2 v2 = post.V2[o];
+                const double tr = v2.x * ap.x - v2.y * ap.y;
+                const double ti = v2.x * ap.y + v2.y * ap.x;
+                u = make_double2(u.x + tr, u.y - ti);
+                post.vel[o] = u;
+                double2 uu = post.vel_upper[o];
+                post.vel_upper[o] = make_double2(uu.x + tr, uu.y - ti);
+                if (post.dphi) {
+                    const double wr = u.x, wi = -u.y;
+                    const double y = post.Z[o].y;
+                    if (post.rhs_phi_kind == 1) {
+                        dphi = -y + 0.5 * (wr * wr + wi * wi);        // L/createM.cuh:105 at rho = 0
+                    } else {
+                        const double vdw = post.depth / 3.0;           // L/createM.cuh:113-115
+                        dphi = vdw * pow(1.0 + y / post.depth, -3.0) - vdw + (0.5 * wr * wr + 0.5 * wi * wi);
+                    }
+                    post.dphi[o] = make_double2(dphi, 0.0);
+                }
+            } else if (post.dphi) {
+                dphi = post.dphi[o].x;
+            }
+            if (post.update == 1) {          // y_i = y0 + c k   (cublasZaxpy, L/AutonomousRungeKuttaStepper.cuh:349-357)
+                const double2 z0 = post.y0[o], p0 = post.y0[post.BN + o];
+                post.y_out[o] = make_double2(fma(post.c, u.x, z0.x), fma(post.c, u.y, z0.y));
+                post.y_out[post.BN + o] = make_double2(fma(post.c, dphi, p0.x), fma(post.c, 0.0, p0.y));
+            } else if (post.update == 2) {   // y0 += h/6 (k1 + 2 k2 + 2 k3 + k4)   (add_k_vectors + Zaxpy, :243, :361)
+                const double2 a1 = post.k1[o], a2 = post.k2[o], a3 = post.k3[o];
+                const double2 b1 = post.k1[post.BN + o], b2 = post.k2[post.BN + o], b3 = post.k3[post.BN + o];
+                const double2 z0 = post.y_out[o], p0 = post.y_out[post.BN + o];
+                const double sx = a1.x + 2.0 * a2.x + 2.0 * a3.x + u.x, sy = a1.y + 2.0 * a2.y + 2.0 * a3.y + u.y;
+                const double px = b1.x + 2.0 * b2.x + 2.0 * b3.x + dphi, py = b1.y + 2.0 * b2.y + 2.0 * b3.y + 0.0;
+                post.y_out[o] = make_double2(fma(post.c, sx, z0.x), fma(post.c, sy, z0.y));
+                post.y_out[post.BN + o] = make_double2(fma(post.c, px, p0.x), fma(post.c, py, p0.y));
+            }
         }
     }
     double sx = block_reduce_fixed<kCell>(v, sred);
@@ -304,9 +387,11 @@ __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __res
 
 void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl* ctrl, double* a_out, double2* a_complex,
                          double* xsum_part, const HistoryRing& hist, int N, int batch, int ncell, cudaStream_t st,
-                         const double2* A0, const double2* A1) {
+                         const double2* A0, const double2* A1, const FinishPost* post) {
+    FinishPost p;
+    if (post) p = *post;
     finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, A0, A1, ctrl, a_out, a_complex, xsum_part, hist, N,
-                                                              ncell);
+                                                              ncell, p);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -672,7 +757,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                 double2 zp = a.g.Zp[o];
                 double2 v1d = a.g.V1diag[o];
                 double2 v2 = a.g.V2[o];
-                double2 ap = a.aprime[o];
+                const double2 ap = a.defer_aprime ? make_double2(0.0, 0.0) : a.aprime[o];   // deferred: finish_solve adds V2 a'
                 // w = (-i/4pi) S + V1diag a + V2 a',  S = i A  ->  A/(4 pi)
                 double wr = inv4pi * ((sumx - ak) + 2.0 * T[r].x) + v1d.x * ak + (v2.x * ap.x - v2.y * ap.y);
                 double wi = inv4pi * (2.0 * T[r].y) + v1d.y * ak + (v2.x * ap.y + v2.y * ap.x);
@@ -683,7 +768,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                 mirror_store(a.comm, a.vel_lower + o, make_double2(wr, -wi));   // conj, L/WaterVelocities.cuh:241
                 double2 az = cdiv(make_double2(ak, 0.0), zp);       // upper fluid: diagonal -1/(2Zp) instead of +1/(2Zp)
                 a.vel_upper[o] = make_double2(wr - az.x, -(wi - az.y));
-                if (a.dphi) {
+                if (a.dphi && !a.defer_aprime) {
                     double y = a.g.Z[o].y;
                     double kin = 0.5 * wr * wr + 0.5 * wi * wi;
                     double d;

@@ -367,14 +367,14 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
                     double2 zp = a.g.Zp[o];
                     double2 v1d = a.g.V1diag[o];
                     double2 v2 = a.g.V2[o];
-                    double2 ap = a.aprime[o];
+                    const double2 ap = a.defer_aprime ? make_double2(0.0, 0.0) : a.aprime[o];   // deferred: finish_solve adds V2 a'
                     double wr = inv4pi * Ar + v1d.x * xk + (v2.x * ap.x - v2.y * ap.y);
                     double wi = inv4pi * Ai + v1d.y * xk + (v2.x * ap.y + v2.y * ap.x);
                     mirror_store2(a.comm, a.vel_lower + o, make_double2(wr, -wi));
                     double inv = 1.0 / (zp.x * zp.x + zp.y * zp.y);
                     double azx = xk * zp.x * inv, azy = -xk * zp.y * inv;     // a_k / Zp_k
                     a.vel_upper[o] = make_double2(wr - azx, -(wi - azy));
-                    if (a.dphi) {
+                    if (a.dphi && !a.defer_aprime) {
                         double y = a.g.Z[o].y;
                         double d;
                         if (a.rhs_phi_kind == 1) {

@@ -108,6 +108,17 @@ struct rb_solver {
     size_t arena_bytes = 0;
     double2* kbuf[4] = {nullptr, nullptr, nullptr, nullptr};
     double2* Abuf[2] = {nullptr, nullptr};   // row sums A_k of the iterate a combined sweep verified, by iterate-buffer parity (arena)
+    // launch-bound regime (N <= 4096): the a' transform of a round runs on a side stream beside that round's combined sweep (a fork
+    // and a join inside the recorded step); the sweep leaves V2 a' and dPhi/dt to finish_solve, which also does the RK update
+    bool overlap_ok = false;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cufftHandle plan_d2z_side = 0, plan1_side = 0;
+    bool side_plans = false;
+    double2* aprime2[2] = {nullptr, nullptr};   // a' per iterate-buffer parity
+    double2* half_side = nullptr;               // D2Z half spectrum of the side stream
+    FinishPost post_update;                     // set by the stepper before a stage: RK update to fold into finish_solve
+    bool post_update_done = false;
     CommView comm;
     void* peer_mapped[kMaxRanks] = {};
     unsigned long long* epochs = nullptr;   // [2] signal / wait counters + error flag
@@ -177,6 +188,15 @@ static void solver_free(rb_solver* s) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->side_plans) {
+        cufftDestroy(s->plan_d2z_side);
+        cufftDestroy(s->plan1_side);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    for (auto p : {s->aprime2[0], s->aprime2[1], s->half_side})
+        if (p) cudaFree(p);
     if (s->gm_host) cudaFreeHost(s->gm_host);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -310,10 +330,11 @@ static void choose_sweep_kernel(rb_solver* s) {
     int nSM = 148;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
     const double eff = s->v2_eff;
-    // measured on a B200 (MV sweep, us; tiled / persistent): N=256 18.5/12.3, 1024 18.5/18.5, 2048 21.8/25.2, 4096 34.8/37.3,
-    // 8192 84/96, 16384 250/287, 32768 891/968, 65536 3512/3380
-    // ensembles (batch > 1) keep the persistent kernel whenever its schedule fills the SMs
-    bool v2 = !s->has_image && ((eff >= 0.95 && ((long)s->N >= 49152 || s->batch > 1)) || (long)s->N * s->batch <= 1024);
+    // measured on a B200 (MV sweep alone, us; tiled / persistent): N=256 18.5/12.3, 1024 18.5/18.5, 2048 21.8/25.2, 4096 34.8/37.3,
+    // 8192 84/96, 16384 250/287, 32768 891/968, 65536 3512/3380.  Inside a recorded step the persistent kernel still wins up to
+    // N = 4096 (its skipped launches and its combined sweep are cheaper: 2089 against 1889 steps/s at N = 4096).
+    // Ensembles (batch > 1) keep the persistent kernel whenever its schedule fills the SMs.
+    bool v2 = !s->has_image && ((eff >= 0.95 && ((long)s->N >= 49152 || s->batch > 1)) || (long)s->N * s->batch <= 4096);
     int force = env_int("RB_SWEEP_V2", -1);
     if (force >= 0) v2 = !s->has_image && force != 0;
     s->use_v2 = v2;
@@ -486,6 +507,21 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
         s->fft_tw = dmalloc<double2>(N);
         RB_CUDA(cudaMemcpy(s->fft_tw, tw.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
     }
+    if (s->own_fft_skippable && env_int("RB_OVERLAP", 1)) {
+        // every surplus a' of a recorded step can skip itself here, so a' buffers by parity are never overwritten after the solve ended
+        s->overlap_ok = true;
+        RB_CUDA(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        cufft_check(cufftPlanMany(&s->plan1_side, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, batch), "cufftPlanMany(side)");
+        cufft_check(cufftPlanMany(&s->plan_d2z_side, 1, n, nullptr, 1, N, nullptr, 1, N / 2 + 1, CUFFT_D2Z, batch), "cufftPlanMany(side D2Z)");
+        s->side_plans = true;
+        cufft_check(cufftSetStream(s->plan1_side, s->side_stream), "cufftSetStream");
+        cufft_check(cufftSetStream(s->plan_d2z_side, s->side_stream), "cufftSetStream");
+        s->aprime2[0] = dmalloc<double2>(BN);
+        s->aprime2[1] = dmalloc<double2>(BN);
+        s->half_side = dmalloc<double2>(BN);
+    }
     s->combined_ok = env_int("RB_COMBINED", 1) != 0;
     s->hist_store_next = env_int("RB_HIST_NEXT", 1) != 0;
     plan_sweep2(s);
@@ -566,6 +602,18 @@ static void real_derivative(rb_solver* s, const double* x, double2* out, const S
     cufft_check(cufftExecD2Z(s->plan_d2z, (cufftDoubleReal*)x, (cufftDoubleComplex*)half), "fft d2z");
     launch_spectral_multiply_real(half, out, s->N, s->batch, 2.0 * kPi / s->N, s->stream);
     cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)out, (cufftDoubleComplex*)out, CUFFT_INVERSE), "fft inv");
+}
+
+// the same derivative on the side stream (own plans, own half-spectrum buffer): runs beside the sweep of the same round
+static void real_derivative_side(rb_solver* s, const double* x, double2* out, const SolveCtrl* skip_ctrl, bool force_own) {
+    cudaStream_t q = s->side_stream;
+    if (s->own_fft || force_own) {
+        launch_fft_real_derivative(x, out, s->N, s->logN, s->batch, s->fft_tw, 2.0 * kPi / s->N, skip_ctrl, q);
+        return;
+    }
+    cufft_check(cufftExecD2Z(s->plan_d2z_side, (cufftDoubleReal*)x, (cufftDoubleComplex*)s->half_side), "fft d2z (side)");
+    launch_spectral_multiply_real(s->half_side, out, s->N, s->batch, 2.0 * kPi / s->N, q);
+    cufft_check(cufftExecZ2Z(s->plan1_side, (cufftDoubleComplex*)out, (cufftDoubleComplex*)out, CUFFT_INVERSE), "fft inv (side)");
 }
 
 static SweepArgs base_args(rb_solver* s, const double2* Z) {
@@ -889,7 +937,6 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     cudaStream_t st = s->stream;
     const double2* Z = state;
     const double2* Phi = state + BN;
-    surface_stage(s, Z, Phi);
     s->cur_Z = Z;
     s->cur_Phi = Phi;
     double2* user_out = nullptr;
@@ -897,9 +944,13 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
 
     const double* warm = nullptr;
     if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
-    launch_guess(s->b, warm, s->hist, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell,
-                 st, s->Zp(), s->Mdiag, s->cK);
+    // derivatives, then ONE kernel for the geometry of the surface and the start of the solve
+    derivatives(s, Z, Phi, false);
+    launch_geometry_guess(make_geometry(s, Z), s->PhiPc(), s->N, s->batch, s->ncell, s->rhoM, s->props.depth, s->has_image, s->use_local,
+                          s->props.rho, s->props.U, warm, s->hist, s->xbuf[0], s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega,
+                          s->cK, st);
     SweepArgs base = base_args(s, Z);
+    const bool overlap = s->overlap_ok;
     // optimistic: the extrapolated guess is expected to verify as it stands, so sweep 0 is already a combined sweep and a
     // well-predicted RHS costs ONE O(N^2) sweep; otherwise sweep 0 is the cheaper solver sweep that cannot declare convergence
     // (nothing has produced velocities yet)
@@ -911,10 +962,17 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     }
     for (int i = first_combined; i < s->fixed_sweeps; ++i) {
         const double* xi = s->xbuf[i & 1];
-        if (i >= first_combined + 1 && s->own_fft_skippable && !s->own_fft)   // surplus round: almost always skipped -> use the kernel that can skip itself
+        const bool surplus = i >= first_combined + 1;   // almost always skipped -> use the kernel that can skip itself
+        if (overlap) {
+            // fork: a'(x_i) on the side stream while this round's sweep runs; finish_solve adds V2 a' once both have ended
+            RB_CUDA(cudaEventRecord(s->ev_fork, st));
+            RB_CUDA(cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+            real_derivative_side(s, xi, s->aprime2[i & 1], s->ctrl, surplus);
+        } else if (surplus && s->own_fft_skippable && !s->own_fft) {
             launch_fft_real_derivative(xi, s->aprime, s->N, s->logN, s->batch, s->fft_tw, 2.0 * kPi / s->N, s->ctrl, st);
-        else
+        } else {
             real_derivative(s, xi, s->aprime, s->ctrl);   // own kernel: skips itself once the solve is finished
+        }
         SweepArgs a = base;
         a.x = xi;
         a.x_out = s->xbuf[(i + 1) & 1];
@@ -930,14 +988,45 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
         a.rhs_phi_kind = s->rhs_phi_kind;
         a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
         a.A_out = s->hist.Abase ? s->Abuf[i & 1] : nullptr;
+        a.defer_aprime = overlap ? 1 : 0;
         sweep(s, a, kSweepVEL);
         if (s->comm.nranks > 1)
             launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, a.final_buf_on_done, s->bnorm_part, s->ncell, a.tol2, a.max_iters, st);
     }
     HistoryRing hist_out = s->hist;
     hist_out.store_next = s->hist_store_next ? 1 : 0;
+    if (overlap) {   // join
+        RB_CUDA(cudaEventRecord(s->ev_join, s->side_stream));
+        RB_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+    }
+    FinishPost post;
+    const bool fuse_update = s->post_update.update != 0 && s->rhs_phi_kind != 0 && !user_out && !s->props.compute_energies;
+    if (overlap || fuse_update) {
+        post.vel = out;
+        post.vel_upper = s->vel_upper;
+        post.dphi = s->rhs_phi_kind ? out + BN : nullptr;
+        post.V2 = s->V2;
+        post.Z = Z;
+        post.rhs_phi_kind = s->rhs_phi_kind;
+        post.depth = s->props.depth;
+        post.BN = BN;
+        if (overlap) {
+            post.aprime0 = s->aprime2[0];
+            post.aprime1 = s->aprime2[1];
+        }
+        if (fuse_update) {
+            post.update = s->post_update.update;
+            post.c = s->post_update.c;
+            post.y0 = s->post_update.y0;
+            post.y_out = s->post_update.y_out;
+            post.k1 = s->post_update.k1;
+            post.k2 = s->post_update.k2;
+            post.k3 = s->post_update.k3;
+            s->post_update_done = true;
+        }
+    }
     launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, nullptr, s->xsum_a, hist_out, s->N, s->batch, s->ncell, st,
-                        s->hist.Abase ? s->Abuf[0] : nullptr, s->Abuf[1]);
+                        s->hist.Abase ? s->Abuf[0] : nullptr, s->Abuf[1], post.vel ? &post : nullptr);
     s->have_prev_a = true;
     rhs_tail(s, state, out, user_out);
 }
@@ -991,6 +1080,7 @@ struct rb_stepper {
     bool use_graph = true;
     cudaGraphExec_t graph_exec = nullptr;      // the graph in use (owned by graph_cache)
     cudaGraphExec_t graph_cache[16] = {};      // one recorded step per mask of optimistic stages
+    int graph_kernels[16] = {};                // kernels of this library recorded in each (cuFFT's own are not counted)
     int opt_mask = 0;                          // bit i: stage i starts with a combined sweep (its guess verified as it stood lately)
     int graph_mask = 0;                        // mask graph_exec was recorded with
     int opt_policy = 1;                        // RB_OPTIMISTIC: 0 never, 1 adaptive per stage, 2 always
@@ -1054,14 +1144,27 @@ static void issue_step(rb_stepper* st, int fixed_sweeps) {
         rhs(s, y, st->k[i]);
         s->optimistic = false;
     };
-    stage(0, st->y0);
-    launch_stage_update(st->ytmp, st->y0, st->k[0], h * 0.5, n2, cs);
-    stage(1, st->ytmp);
-    launch_stage_update(st->ytmp, st->y0, st->k[1], h * 0.5, n2, cs);
-    stage(2, st->ytmp);
-    launch_stage_update(st->ytmp, st->y0, st->k[2], h, n2, cs);
-    stage(3, st->ytmp);
-    launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n2, cs);
+    // the RK update after a stage is folded into the kernel that closes the stage's solve when the RHS allows it
+    auto staged = [&](int i, const double2* y, int update, double c) {
+        s->post_update = FinishPost();
+        s->post_update.update = update;
+        s->post_update.c = c;
+        s->post_update.y0 = st->y0;
+        s->post_update.y_out = update == 2 ? st->y0 : st->ytmp;
+        s->post_update.k1 = st->k[0];
+        s->post_update.k2 = st->k[1];
+        s->post_update.k3 = st->k[2];
+        s->post_update_done = false;
+        stage(i, y);
+        const bool done = s->post_update_done;
+        s->post_update = FinishPost();
+        s->post_update_done = false;
+        return done;
+    };
+    if (!staged(0, st->y0, 1, h * 0.5)) launch_stage_update(st->ytmp, st->y0, st->k[0], h * 0.5, n2, cs);
+    if (!staged(1, st->ytmp, 1, h * 0.5)) launch_stage_update(st->ytmp, st->y0, st->k[1], h * 0.5, n2, cs);
+    if (!staged(2, st->ytmp, 1, h)) launch_stage_update(st->ytmp, st->y0, st->k[2], h, n2, cs);
+    if (!staged(3, st->ytmp, 2, h / 6.0)) launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n2, cs);
     if (warm) launch_advance_counter(st->d_counter, cs);
     s->hist = HistoryRing();
     s->ctrl = s->ctrl_all;
@@ -1089,6 +1192,7 @@ static void capture_graph(rb_stepper* st, int sweeps) {
         throw;
     }
     RB_CUDA(cudaStreamEndCapture(s->stream, &graph));
+    st->graph_kernels[st->opt_mask & 15] = (int)(rb::g_launch_count - launches_before);   // this library's kernels in one step
     rb::g_launch_count = launches_before;   // recorded, not launched
     RB_CUDA(cudaGraphInstantiate(&slot, graph, 0));
     RB_CUDA(cudaGraphDestroy(graph));
@@ -1099,16 +1203,6 @@ static void capture_graph(rb_stepper* st, int sweeps) {
     st->graph_y0 = st->y0;
     st->graph_hits_below = 0;
     st->graph_captures++;
-}
-
-static size_t kernels_per_step(rb_solver* s, int sweeps) {
-    // geometry path 4 + guess + sweeps + finish + (multiply, scale) + VEL + optional rhs_phi / energies, per stage; 3 stage updates,
-    // final update, counter
-    // derivatives + geometry 4, guess, sweeps, per combined sweep (real->complex, multiply, scale), finish, optional dPhi/dt, energies
-    size_t per_stage = (s->own_fft ? 2 : 3) + 1 + (size_t)sweeps + (size_t)(sweeps - 1) + 1 + (s->rhs_phi_kind ? 0 : 1) +
-                       (s->props.compute_energies ? 1 : 0);
-    if (s->comm.nranks > 1) per_stage += (size_t)sweeps;   // wait kernels
-    return 4 * per_stage + 5;
 }
 
 static void after_step(rb_stepper* st) {
@@ -1150,7 +1244,7 @@ static void stepper_step(rb_stepper* st) {
     }
     const int mask = st->opt_mask;
     RB_CUDA(cudaGraphLaunch(st->graph_exec, s->stream));
-    rb::count_launch((int)kernels_per_step(s, st->graph_sweeps));
+    rb::count_launch(st->graph_kernels[st->opt_mask & 15]);
     st->graph_launches++;
     RB_CUDA(cudaEventRecord(st->ev, s->stream));
     RB_CUDA(cudaEventSynchronize(st->ev));

@@ -213,6 +213,32 @@ def tune2():
                 os.environ.pop(k, None)
 
 
+def overlapcmp():
+    """a' transform beside the combined sweep (graph fork/join) + fused geometry/guess and finish/RK update: step rate and state"""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    for N, dt in ((256, 1e-3), (1024, 1e-3), (2048, 1e-3), (4096, 1e-3), (8192, 5e-4)):
+        ref = None
+        for ov in ("0", "1"):
+            os.environ["RB_OVERLAP"] = ov
+            props = api.ProblemProperties(rho=0.0)
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+            Z, Phi = ro.trochoid(N, 0.4)
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+            st = T(ro.pack_state(Z, Phi))
+            stp.initialize(st, True)
+            stp.runSteps(20)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            stp.runSteps(300)
+            torch.cuda.synchronize()
+            el = time.time() - t0
+            y = st.cpu().numpy()
+            if ref is None:
+                ref = y
+            print(f"overlapcmp N={N} overlap={ov}: {300 / el:.1f} steps/s dev={rel(y, ref):.2e} {stp.stats()} {calc.solve_stats()}", flush=True)
+    os.environ.pop("RB_OVERLAP", None)
+
+
 def ensemble():
     """BASELINE config 5, second half: 1024-member ensemble at N = 512 (replicas only across GPUs)"""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
