@@ -13,6 +13,7 @@
 //   ZPhiDerivative<N,B>, FftDerivative<N,B>   L/Derivatives.cuh:51-108
 //   AutonomousRungeKuttaStepper<T,N>, RK4Options, OdeSolverResult  L/AutonomousRungeKuttaStepper.cuh:24-89, L/RK4Options.h, L/OdeSolver.h
 //   TrajectoryLogger<T,N>               L/TrajectoryLogger.cuh:7-73
+//   RK45_Options, RK45_std_complex<N>, RK45StepResult   L/RK45.cuh:21-27, 95-180, 333-400
 //   createMKernel, createFiniteDepthMKernel, createVelocityMatrices, createHeliumVelocityMatrices,
 //   compute_rhs_phi_expression, compute_rhs_helium_phi_expression   (the __global__ kernels the reference's tests launch)
 #pragma once
@@ -233,6 +234,73 @@ public:
         return OdeSolverResult::ReachedEndTime;
     }
     void getState(T* host) { rb_compat_check(rb_rk4_get_state(st_, reinterpret_cast<rb_complex*>(host)), "rb_rk4_get_state"); }
+};
+
+// ---- adaptive RKF45 (L/RK45.cuh): RK45_Options and RK45_std_complex<N> over any AutonomousProblem<std_complex, N> ---------------
+struct RK45_Options {   // L/RK45.cuh:21-27
+    double atol = 1e-6;
+    double rtol = 1e-3;
+    double h_min = 1e-16;
+    double h_max = 1e10;
+    double initial_timestep = 1e-2;
+};
+enum class RK45StepResult { StepAccepted, StepRejected };
+
+template <size_t N>
+class RK45_std_complex {
+    rb_rk45* r_ = nullptr;
+    AutonomousProblem<std_complex, (int)N>* problem_ = nullptr;
+    static void trampoline(void* user, const rb_complex* state, rb_complex* rhs, void* stream) {
+        auto* p = static_cast<AutonomousProblem<std_complex, (int)N>*>(user);
+        p->setStream(static_cast<cudaStream_t>(stream));
+        p->run(reinterpret_cast<std_complex*>(const_cast<rb_complex*>(state)), reinterpret_cast<std_complex*>(rhs));
+    }
+    static rb_rk45_options make(double tstep, double h_max, double h_min) {
+        rb_rk45_options o{1e-6, 1e-3, h_min, h_max, tstep};
+        return o;
+    }
+public:
+    // the reference's ctor also takes a DataLogger and value loggers (L/RK45.cuh:106); logging is outside this path
+    explicit RK45_std_complex(AutonomousProblem<std_complex, (int)N>& problem, double tstep = 1e-2, double h_max = 1e10,
+                              double h_min = 1e-16, cudaStream_t stream = nullptr)
+        : problem_(&problem) {
+        rb_rk45_options o = make(tstep, h_max, h_min);
+        r_ = rb_rk45_create_generic(N, &RK45_std_complex::trampoline, problem_, &o, stream);
+        if (!r_) throw std::runtime_error(std::string("rb_rk45_create_generic: ") + rb_last_error());
+    }
+    // the boundary-integral RHS runs inside the library (no callback)
+    template <int NP, size_t B>
+    explicit RK45_std_complex(BaseBoundaryIntegralCalculator<NP, B>& problem, double tstep = 1e-2, double h_max = 1e10,
+                              double h_min = 1e-16) {
+        static_assert(2 * NP * B == N, "state size must be 2 * N * batchSize");
+        rb_rk45_options o = make(tstep, h_max, h_min);
+        r_ = rb_rk45_create(problem.handle(), &o);
+        if (!r_) throw std::runtime_error(std::string("rb_rk45_create: ") + rb_last_error());
+    }
+    ~RK45_std_complex() { rb_rk45_destroy(r_); }
+    RK45_std_complex(const RK45_std_complex&) = delete;
+    RK45_std_complex& operator=(const RK45_std_complex&) = delete;
+    void setTolerance(double atol, double rtol) { rb_compat_check(rb_rk45_set_tolerance(r_, atol, rtol), "rb_rk45_set_tolerance"); }
+    void setOptions(const RK45_Options& o) {
+        rb_rk45_options c{o.atol, o.rtol, o.h_min, o.h_max, o.initial_timestep};
+        rb_compat_check(rb_rk45_set_options(r_, &c), "rb_rk45_set_options");
+    }
+    void setMaxRejectedSteps(size_t m) { rb_compat_check(rb_rk45_set_max_rejected(r_, m), "rb_rk45_set_max_rejected"); }
+    void initialize(std_complex* initialState, bool onDevice = false) {
+        rb_compat_check(rb_rk45_initialize(r_, reinterpret_cast<rb_complex*>(initialState), onDevice), "rb_rk45_initialize");
+    }
+    RK45StepResult runStep(int = 0) {
+        int acc = 0;
+        rb_compat_check(rb_rk45_step(r_, &acc), "rb_rk45_step");
+        return acc ? RK45StepResult::StepAccepted : RK45StepResult::StepRejected;
+    }
+    OdeSolverResult runEvolution(double startTime, double endTime) {
+        int res = 0;
+        rb_compat_check(rb_rk45_evolve(r_, startTime, endTime, &res), "rb_rk45_evolve");
+        return res == 0 ? OdeSolverResult::ReachedEndTime : OdeSolverResult::StiffnessDetected;
+    }
+    std_complex* getY() { return reinterpret_cast<std_complex*>(rb_rk45_dev_state(r_)); }
+    double getCurrentTime() const { return rb_rk45_current_time(r_); }
 };
 
 // ---- the kernels the reference's tests launch with <<< >>> (same names, same signatures) ----------------------------------

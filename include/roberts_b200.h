@@ -39,6 +39,7 @@ extern "C" {
 typedef struct rb_complex { double re, im; } rb_complex;      /* L/ExportTypes.cuh:7 c_double */
 typedef struct rb_solver rb_solver;                           /* opaque: one RHS assembler + work buffers */
 typedef struct rb_stepper rb_stepper;                         /* opaque: RK4 stepper bound to a solver */
+typedef struct rb_rk45 rb_rk45;                               /* opaque: adaptive RKF45 stepper (L/RK45.cuh) */
 
 /* physics plugin selector == which BoundaryProblem<N,B> subclass the reference would instantiate */
 enum rb_physics {
@@ -166,6 +167,34 @@ RB_API void rb_free(void* p);
 RB_API int rb_rk4_stage_update(rb_complex* y_out, const rb_complex* y0, const rb_complex* k, double c, size_t n, void* stream);
 RB_API int rb_rk4_final_update(rb_complex* y0, const rb_complex* k1, const rb_complex* k2, const rb_complex* k3,
                                const rb_complex* k4, double h, size_t n, void* stream);
+
+/* ---- adaptive Runge-Kutta-Fehlberg 4(5): RK45Base<T,N> / RK45_std_complex<N> (L/RK45.cuh:103-180, 258-330; kernels
+ *      L/RK45_Kernels.cuh:63-106, L/LinearAlgebra.cuh:10-112).  Same tableau, error norm sqrt(mean((|e|/(atol + rtol max(|y|,|y5|)))^2)),
+ *      step-size controller (safety 0.9, factor in [0.2, 5], no growth on a retry) and k1 reuse after a rejected attempt. ---- */
+typedef struct rb_rk45_options {           /* RK45_Options, L/RK45.cuh:21-27 */
+    double atol;                           /* 1e-6 */
+    double rtol;                           /* 1e-3 */
+    double h_min;                          /* 1e-16 */
+    double h_max;                          /* 1e10 */
+    double initial_timestep;               /* 1e-2 */
+} rb_rk45_options;
+/* AutonomousProblem<T,N>::run(T* state, T* rhs) (L/AutonomousProblem.h:9-28) for problems other than the boundary integral:
+   device pointers, work must be enqueued on `cuda_stream` */
+typedef void (*rb_rhs_fn)(void* user, const rb_complex* state_dev, rb_complex* rhs_dev, void* cuda_stream);
+RB_API rb_rk45* rb_rk45_create(rb_solver* s, const rb_rk45_options* opt);          /* RHS = rb_rhs of s; state = 2 N B complex */
+RB_API rb_rk45* rb_rk45_create_generic(size_t n, rb_rhs_fn f, void* user, const rb_rk45_options* opt, void* stream);
+RB_API int rb_rk45_destroy(rb_rk45* r);
+RB_API int rb_rk45_set_options(rb_rk45* r, const rb_rk45_options* opt);            /* setOptions :140-145 */
+RB_API int rb_rk45_set_tolerance(rb_rk45* r, double atol, double rtol);            /* setTolerance :123-127 */
+RB_API int rb_rk45_set_max_rejected(rb_rk45* r, size_t max_rejected);              /* setMaxRejectedSteps :137-139 (500) */
+RB_API int rb_rk45_initialize(rb_rk45* r, const rb_complex* y0, int on_device);    /* copies, :332-341 */
+RB_API int rb_rk45_step(rb_rk45* r, int* accepted);                                /* runStep :258-304 */
+RB_API int rb_rk45_evolve(rb_rk45* r, double t0, double t1, int* result);          /* runEvolution :194-255; 0 ReachedEndTime, 1 StiffnessDetected */
+RB_API rb_complex* rb_rk45_dev_state(rb_rk45* r);                                  /* getY :130-132 */
+RB_API int rb_rk45_get_state(rb_rk45* r, rb_complex* y_host);
+RB_API double rb_rk45_current_time(rb_rk45* r);                                    /* getCurrentTime :133-135 */
+RB_API double rb_rk45_current_timestep(rb_rk45* r);
+RB_API int rb_rk45_stats(rb_rk45* r, double out_host[4]);   /* accepted steps, rejected attempts, RHS evaluations, last scaled error */
 
 /* ---- multi-GPU (new; the reference is single-GPU, L/utilities.cuh:20): contiguous blocks of 256-row cells of every O(N^2)
  *      sweep are owned by one rank each; all ranks keep the full state and exchange result rows by peer stores over NVLink into

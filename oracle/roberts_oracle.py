@@ -396,6 +396,101 @@ def rk4_evolve(f, y0: np.ndarray, t0: float, t1: float, dt: float, trajectory: b
 
 
 # --------------------------------------------------------------------------
+# adaptive Runge-Kutta-Fehlberg 4(5) (L/RK45.cuh:194-330, L/RK45_Kernels.cuh:15-106)
+# --------------------------------------------------------------------------
+@dataclasses.dataclass
+class RK45Options:
+    """RK45_Options, L/RK45.cuh:21-27."""
+    atol: float = 1e-6
+    rtol: float = 1e-3
+    h_min: float = 1e-16
+    h_max: float = 1e10
+    initial_timestep: float = 1e-2
+
+
+# Fehlberg tableau, L/RK45_Kernels.cuh:18-45
+_RKF_A = ((1.0 / 4.0,),
+          (3.0 / 32.0, 9.0 / 32.0),
+          (1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0),
+          (439.0 / 216.0, -8.0, 3680.0 / 513.0, -845.0 / 4104.0),
+          (-8.0 / 27.0, 2.0, -3544.0 / 2565.0, 1859.0 / 4104.0, -11.0 / 40.0))
+_RKF_B5 = (16.0 / 135.0, 0.0, 6656.0 / 12825.0, 28561.0 / 56430.0, -9.0 / 50.0, 2.0 / 55.0)
+_RKF_B4 = (25.0 / 216.0, 0.0, 1408.0 / 2565.0, 2197.0 / 4104.0, -1.0 / 5.0, 0.0)
+
+
+def rk45_new_timestep(old_h: float, error: float, accepting: bool, h_min: float, h_max: float) -> float:
+    """calculateNewTimestep, L/RK45.cuh:306-330."""
+    safety, minfac, maxfac, expo = 0.9, 0.2, 5.0, 1.0 / 5.0
+    if error == 0.0:
+        return old_h * (maxfac if accepting else 1.0)
+    fac = safety * error ** (-expo)
+    fac = min(max(fac, minfac), maxfac if accepting else 1.0)
+    return min(max(old_h * fac, h_min), h_max)
+
+
+class RK45:
+    """RK45Base<T,N>::runStep / runEvolution (L/RK45.cuh:194-304) for f(y) -> dy/dt on a complex vector."""
+
+    def __init__(self, f, options: RK45Options = None, max_rejected: int = 500):
+        o = options or RK45Options()
+        self.f, self.atol, self.rtol, self.h_min, self.h_max = f, o.atol, o.rtol, o.h_min, o.h_max
+        self.h, self.t = o.initial_timestep, 0.0
+        self.max_rejected = max_rejected
+        self.accepted_prev, self.k1, self.y = True, None, None
+        self.n_accepted = self.n_rejected = self.n_rhs = 0
+        self.scaled_error = 0.0
+
+    def initialize(self, y0):
+        self.y = np.array(y0, np.complex128)
+        self.accepted_prev = True
+
+    def _rhs(self, y):
+        self.n_rhs += 1
+        return self.f(y)
+
+    def run_step(self) -> bool:
+        h, y = self.h, self.y
+        if self.accepted_prev:                       # a rejected attempt keeps k1 (:262-264)
+            self.k1 = self._rhs(y)
+        k = [self.k1]
+        for row in _RKF_A:                           # calculateTempY (:341-367): c1 k1 + c2 k2 + ... + y, left to right
+            acc = (row[0] * h) * k[0]
+            for c, kj in zip(row[1:], k[1:]):
+                acc = acc + (c * h) * kj
+            k.append(self._rhs(acc + y))
+        y5 = y.copy()                                # rk45_error_and_y5 (L/RK45_Kernels.cuh:63-106)
+        e = np.zeros_like(y)
+        for b5, b4, kj in zip(_RKF_B5, _RKF_B4, k):
+            y5 = y5 + (h * b5) * kj
+            e = e + (h * (b5 - b4)) * kj
+        sc = np.maximum(self.atol + self.rtol * np.maximum(np.abs(y), np.abs(y5)), 1e-300)
+        self.scaled_error = float(np.sqrt((1.0 / y.size) * np.sum((np.abs(e) / sc) ** 2)))   # :399
+        accepted = self.scaled_error <= 1.0
+        self.accepted_prev = accepted
+        h_new = rk45_new_timestep(h, self.scaled_error, accepted, self.h_min, self.h_max)
+        if accepted:
+            self.y = y5
+            self.t += h
+            self.n_accepted += 1
+        else:
+            self.n_rejected += 1
+        self.h = h_new
+        return accepted
+
+    def run_evolution(self, t0: float, t1: float) -> str:
+        self.t = t0
+        while True:
+            if self.t >= t1:
+                return "ReachedEndTime"
+            self.h = min(self.h, t1 - self.t)        # never overshoot (:207-211)
+            rejected = 0
+            while not self.run_step():
+                rejected += 1
+                if rejected > self.max_rejected:
+                    return "StiffnessDetected"
+
+
+# --------------------------------------------------------------------------
 # diagnostics (L/Energies.cuh:136-204 functors, scaling :61-128); batch 0 only
 # --------------------------------------------------------------------------
 def energies(Z, Zp, Phi, vel, props: ProblemProperties, physics="water") -> dict:

@@ -23,6 +23,14 @@ class SimProperties(Structure):          # L/ExportTypes.cuh:8-20 ; P/integratio
                 ("use_expansions", c_bool), ("expansion_order", c_int), ("infinite_depth", c_bool)]
 
 
+class rb_rk45_options(Structure):        # RK45_Options, L/RK45.cuh:21-27
+    _fields_ = [("atol", c_double), ("rtol", c_double), ("h_min", c_double), ("h_max", c_double), ("initial_timestep", c_double)]
+
+
+# AutonomousProblem<T,N>::run as a C callback: (user, state_dev, rhs_dev, cuda_stream)
+RB_RHS_FN = ctypes.CFUNCTYPE(None, c_void_p, c_void_p, c_void_p, c_void_p)
+
+
 class RK4SolverOptions(Structure):       # L/ExportTypes.cuh:35-40 ; P/integration/rhs.py:48-53
     _fields_ = [("timeStep", c_double), ("t0", c_double), ("t1", c_double), ("returnTrajectory", c_bool)]
 
@@ -78,6 +86,20 @@ SIGNATURES = {
     "rb_rk4_guess_stats": (c_int, [_P, _D]),
     "rb_rk4_set_optimistic": (c_int, [_P, c_int]),
     "rb_rk4_set_guess": (c_int, [_P, c_int, c_int]),
+    "rb_rk45_create": (_P, [_P, POINTER(rb_rk45_options)]),
+    "rb_rk45_create_generic": (_P, [c_size_t, RB_RHS_FN, _P, POINTER(rb_rk45_options), _P]),
+    "rb_rk45_destroy": (c_int, [_P]),
+    "rb_rk45_set_options": (c_int, [_P, POINTER(rb_rk45_options)]),
+    "rb_rk45_set_tolerance": (c_int, [_P, c_double, c_double]),
+    "rb_rk45_set_max_rejected": (c_int, [_P, c_size_t]),
+    "rb_rk45_initialize": (c_int, [_P, _P, c_int]),
+    "rb_rk45_step": (c_int, [_P, POINTER(c_int)]),
+    "rb_rk45_evolve": (c_int, [_P, c_double, c_double, POINTER(c_int)]),
+    "rb_rk45_dev_state": (_P, [_P]),
+    "rb_rk45_get_state": (c_int, [_P, _P]),
+    "rb_rk45_current_time": (c_double, [_P]),
+    "rb_rk45_current_timestep": (c_double, [_P]),
+    "rb_rk45_stats": (c_int, [_P, _D]),
     "rb_rk4_set_logging": (c_int, [_P, c_size_t, c_size_t]),
     "rb_rk4_copy_trajectory": (c_int, [_P, POINTER(_D), POINTER(c_size_t), POINTER(_P), POINTER(c_size_t)]),
     "rb_free": (None, [_P]),

@@ -351,6 +351,104 @@ def compute_rhs_helium_phi_expression_expansion_terms(Z, V1, result, h, N, order
                                                   _stream_ptr(Z.device)), "rb_rhs_phi_helium_expansion")
 
 
+@dataclasses.dataclass
+class RK45_Options:
+    """L/RK45.cuh:21-27."""
+    atol: float = 1e-6
+    rtol: float = 1e-3
+    h_min: float = 1e-16
+    h_max: float = 1e10
+    initial_timestep: float = 1e-2
+
+    def _c(self):
+        return _lib.rb_rk45_options(self.atol, self.rtol, self.h_min, self.h_max, self.initial_timestep)
+
+
+class RK45_std_complex:
+    """RK45_std_complex<N>(AutonomousProblem&, logger, valueLoggers, tstep, h_max, h_min) (L/RK45.cuh:103-180, 333-400): adaptive
+    Runge-Kutta-Fehlberg 4(5).  `autonomousProblem` is either a BaseBoundaryIntegralCalculator (the boundary-integral RHS runs
+    inside the library) or any object with `run(state, rhs)` taking complex128 CUDA tensors of length `n`, the Python counterpart
+    of AutonomousProblem<T,N>::run (L/AutonomousProblem.h:9-28)."""
+
+    StepAccepted, StepRejected = "StepAccepted", "StepRejected"
+    ReachedEndTime, StiffnessDetected = "ReachedEndTime", "StiffnessDetected"
+
+    def __init__(self, autonomousProblem, tstep: float = 1e-2, h_max: float = 1e10, h_min: float = 1e-16, n: int = None,
+                 device=None):
+        self.lib = _lib.load()
+        opt = RK45_Options(h_min=h_min, h_max=h_max, initial_timestep=tstep)._c()
+        self.problem = autonomousProblem
+        if isinstance(autonomousProblem, BaseBoundaryIntegralCalculator):
+            self.device = autonomousProblem.device
+            self.n = 2 * autonomousProblem.N * autonomousProblem.batchSize
+            self.handle = self.lib.rb_rk45_create(autonomousProblem.handle, ctypes.byref(opt))
+        else:
+            if n is None:
+                raise ValueError("a generic problem needs the state length n")
+            self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+            self.n = int(n)
+            dev = self.device
+
+            def _run(_user, state_ptr, rhs_ptr, _stream):
+                autonomousProblem.run(_view(state_ptr, 2 * self.n, dev, True), _view(rhs_ptr, 2 * self.n, dev, True))
+
+            self._cb = _lib.RB_RHS_FN(_run)   # keep the trampoline alive
+            self.handle = self.lib.rb_rk45_create_generic(self.n, self._cb, None, ctypes.byref(opt), _stream_ptr(self.device))
+        if not self.handle:
+            raise _lib.RobertsError("rb_rk45_create: " + self.lib.rb_last_error().decode())
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.rb_rk45_destroy(h)
+
+    def setTolerance(self, atol, rtol):
+        check(self.lib.rb_rk45_set_tolerance(self.handle, float(atol), float(rtol)), "rb_rk45_set_tolerance")
+
+    def setOptions(self, options: RK45_Options):
+        o = options._c()
+        check(self.lib.rb_rk45_set_options(self.handle, ctypes.byref(o)), "rb_rk45_set_options")
+
+    def setMaxRejectedSteps(self, maxRejected):
+        check(self.lib.rb_rk45_set_max_rejected(self.handle, int(maxRejected)), "rb_rk45_set_max_rejected")
+
+    def initialize(self, initialState, onDevice=False):
+        if onDevice:
+            check(self.lib.rb_rk45_initialize(self.handle, _ptr(initialState), 1), "rb_rk45_initialize")
+        else:
+            host = np.ascontiguousarray(np.asarray(initialState, dtype=np.complex128))
+            check(self.lib.rb_rk45_initialize(self.handle, host.ctypes.data_as(ctypes.c_void_p), 0), "rb_rk45_initialize")
+
+    def runStep(self, _i=0):
+        acc = ctypes.c_int()
+        check(self.lib.rb_rk45_step(self.handle, ctypes.byref(acc)), "rb_rk45_step")
+        return self.StepAccepted if acc.value else self.StepRejected
+
+    def runEvolution(self, startTime, endTime):
+        res = ctypes.c_int()
+        check(self.lib.rb_rk45_evolve(self.handle, float(startTime), float(endTime), ctypes.byref(res)), "rb_rk45_evolve")
+        return self.ReachedEndTime if res.value == 0 else self.StiffnessDetected
+
+    def getY(self):
+        return _view(self.lib.rb_rk45_dev_state(self.handle), 2 * self.n, self.device, True)
+
+    def getState(self):
+        host = np.empty(self.n, np.complex128)
+        check(self.lib.rb_rk45_get_state(self.handle, host.ctypes.data_as(ctypes.c_void_p)), "rb_rk45_get_state")
+        return host
+
+    def getCurrentTime(self):
+        return self.lib.rb_rk45_current_time(self.handle)
+
+    def getCurrentTimeStep(self):
+        return self.lib.rb_rk45_current_timestep(self.handle)
+
+    def stats(self):
+        out = (ctypes.c_double * 4)()
+        check(self.lib.rb_rk45_stats(self.handle, out), "rb_rk45_stats")
+        return dict(accepted=int(out[0]), rejected=int(out[1]), rhs_evaluations=int(out[2]), scaled_error=out[3])
+
+
 def measure_fp64_peak(device=None):
     device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
     out = ctypes.c_double()

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -243,6 +244,13 @@ void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st);
 void launch_stage_update(double2* y_out, const double2* y0, const double2* k, double c, size_t n, cudaStream_t st);
 void launch_final_update(double2* y0, const double2* k1, const double2* k2, const double2* k3, const double2* k4, double h,
                          size_t n, cudaStream_t st);
+// rk45_kernels.cu
+void launch_rk45_stage(const double2* y, const double2* const k[5], double2* out, const double c[5], int nk, size_t n,
+                       cudaStream_t st);
+int rk45_error_blocks(size_t n);
+void launch_rk45_error_y5(const double2* y, const double2* k1, const double2* k3, const double2* k4, const double2* k5,
+                          const double2* k6, double2* y5_out, double h, double atol, double rtol, double* partial,
+                          unsigned int* ticket, double* sumsq, size_t n, cudaStream_t st);
 void launch_fp64_peak(double* sink, int iters, int blocks, cudaStream_t st);
 void launch_fp64_peak3(double* sink, int iters, int blocks, double seed, cudaStream_t st);
 void launch_fp64_mix(double* sink, int iters, int blocks, int nm, int nf, cudaStream_t st);

@@ -192,6 +192,46 @@ static void test_stepper() {
     std::printf("Stepper (App pattern): failures so far %d, E = %.6e\n", failures, ekin + epot);
 }
 
+// TEST(ODE_Solvers, RK45), T/ODESolverTests.cuh:248-421: dz/dt = i z through RK45_std_complex with the reference's own problem class
+// shape (AutonomousProblem<std_complex, N>::run launching a kernel on the stepper's stream); checked against the closed form
+__global__ void flip_x_y(const std_complex* in, std_complex* out, int n) {   // T/ODESolverTests.cuh:25-33: dx/dt = -y, dy/dt = x
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = std_complex(-in[i].imag(), in[i].real());
+}
+template <int N>
+class OscillatoryProblemStdComplex : public AutonomousProblem<std_complex, N> {
+    cudaStream_t stream = nullptr;
+public:
+    void run(std_complex* state, std_complex* rhs) override { flip_x_y<<<(N + 255) / 256, 256, 0, stream>>>(state, rhs, N); }
+    void setStream(cudaStream_t s) override { stream = s; }
+};
+
+static void test_rk45() {
+    constexpr int N = 256;
+    std::vector<std_complex> z0(N), z(N);
+    for (int i = 0; i < N; ++i) z0[i] = std_complex(2 * M_PI * i / N, std::sin(2 * M_PI * i * 0.01));
+    std_complex* dev = nullptr;
+    cudaMalloc(&dev, N * sizeof(std_complex));
+    cudaMemcpy(dev, z0.data(), N * sizeof(std_complex), cudaMemcpyHostToDevice);
+    OscillatoryProblemStdComplex<N> problem;
+    RK45_std_complex<N> stepper(problem, 1e-3);
+    stepper.initialize(dev, true);
+    stepper.setTolerance(1e-8, 1e-8);
+    OdeSolverResult res = stepper.runEvolution(0, 10.0);
+    EXPECT_NEAR(res == OdeSolverResult::ReachedEndTime ? 0.0 : 1.0, 0.0, 0.5, "RK45 reaches the end time");
+    EXPECT_NEAR(stepper.getCurrentTime(), 10.0, 1e-12, "RK45 end time");
+    cudaMemcpy(z.data(), stepper.getY(), N * sizeof(std_complex), cudaMemcpyDeviceToHost);
+    const double c = std::cos(10.0), s = std::sin(10.0);
+    double worst = 0;
+    for (int i = 0; i < N; ++i) {
+        worst = std::max(worst, std::abs(z[i].real() - (z0[i].real() * c - z0[i].imag() * s)));
+        worst = std::max(worst, std::abs(z[i].imag() - (z0[i].real() * s + z0[i].imag() * c)));
+    }
+    EXPECT_NEAR(worst, 0.0, 1e-5, "RK45 rotation by 10 rad (the reference compares with 1e-2)");
+    cudaFree(dev);
+    std::printf("RK45 (reference test pattern): failures so far %d, max error %.3e\n", failures, worst);
+}
+
 int main() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -204,6 +244,7 @@ int main() {
     test_zphi_derivatives();
     test_rhs_phi();
     test_stepper();
+    test_rk45();
     std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
     return failures ? 1 : 0;
 }

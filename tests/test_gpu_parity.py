@@ -542,6 +542,58 @@ def test_single_sweep_rhs_with_predicted_row_sums(api):
     assert rel(out[1][0][:N], ye[:N]) <= 1e-9 and rel(out[1][0][N:], ye[N:]) <= 1e-9
 
 
+def test_rk45_generic_problem_matches_reference_table_and_oracle(api):
+    """TEST(ODE_Solvers, RK45) (T/ODESolverTests.cuh:248-421): dz/dt = i z through RK45_std_complex with a caller-supplied
+    AutonomousProblem::run, setTolerance(1e-8, 1e-8), runEvolution(0, 10); reference table within its own 1e-2, and the oracle's
+    restatement of L/RK45.cuh step for step."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_ode_rotation.npz"))
+    j = np.arange(256)
+    z0 = 2 * np.pi * j / 256 + 1j * np.sin(2 * np.pi * j * 0.01)
+
+    class Oscillatory:           # OscillatoryProblemStdComplex<N>, T/ODESolverTests.cuh:44-71
+        def run(self, state, rhs):
+            rhs.copy_(1j * state)
+
+    stp = api.RK45_std_complex(Oscillatory(), 1e-3, n=256)
+    stp.initialize(T(z0), True)
+    stp.setTolerance(1e-8, 1e-8)
+    assert stp.runEvolution(0.0, 10.0) == stp.ReachedEndTime
+    y = stp.getState()
+    assert np.abs(y.real - g["rk45_x"]).max() <= 1e-2 and np.abs(y.imag - g["rk45_y"]).max() <= 1e-2
+    o = ro.RK45(lambda s: 1j * s, ro.RK45Options(atol=1e-8, rtol=1e-8, initial_timestep=1e-3))
+    o.initialize(z0)
+    assert o.run_evolution(0.0, 10.0) == "ReachedEndTime"
+    st = stp.stats()
+    assert (st["accepted"], st["rejected"], st["rhs_evaluations"]) == (o.n_accepted, o.n_rejected, o.n_rhs)
+    assert np.abs(y - o.y).max() <= 1e-11 and abs(stp.getCurrentTime() - 10.0) <= 1e-12
+    assert np.abs(stp.getY().cpu().numpy() - y).max() == 0.0
+
+
+def test_rk45_on_the_boundary_integral_rhs_matches_oracle(api):
+    """the adaptive stepper over the same RHS as the RK4 path (runSimulationWater takes RK45_Options,
+    L/SimulationRunner.cuh:582-602); step sequence and final state against the oracle."""
+    N, h = 64, 0.3
+    Z, Phi = ro.trochoid(N, h)
+    y0 = ro.pack_state(Z, Phi)
+    props = api.ProblemProperties(rho=0.0)
+    oprops = ro.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+    stp = api.RK45_std_complex(calc)
+    stp.setOptions(api.RK45_Options(atol=1e-9, rtol=1e-9, initial_timestep=1e-3))
+    stp.initialize(y0, False)
+    assert stp.runStep(0) in (stp.StepAccepted, stp.StepRejected)
+    assert stp.runEvolution(stp.getCurrentTime(), 0.05) == stp.ReachedEndTime
+    o = ro.RK45(lambda s: ro.rhs(s, N, 1, oprops, "water", "cuda"), ro.RK45Options(atol=1e-9, rtol=1e-9, initial_timestep=1e-3))
+    o.initialize(y0)
+    o.run_step()
+    assert o.run_evolution(o.t, 0.05) == "ReachedEndTime"
+    st = stp.stats()
+    assert (st["accepted"], st["rejected"]) == (o.n_accepted, o.n_rejected), (st, o.n_accepted, o.n_rejected)
+    y = stp.getState()
+    assert rel(y[:N], o.y[:N]) <= 1e-9 and rel(y[N:], o.y[N:]) <= 1e-9
+    assert abs(stp.getCurrentTimeStep() - o.h) <= 1e-6 * o.h
+
+
 def test_row_sharded_two_gpus_match_single_gpu(api):
     """N > 1: row-sharded run on two GPUs (torchrun, one rank per GPU) vs the single-GPU run; skipped on a one-GPU box."""
     import subprocess
