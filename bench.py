@@ -250,8 +250,16 @@ def run_native(args):
     mv_per_rhs = (it1["total_iterations"] - it0["total_iterations"]) / max(1, it1["total_solves"] - it0["total_solves"])
     # all O(N^2) sweeps executed per step: solver sweeps (incl. the combined verify+velocity ones) + velocity-only sweeps
     sweeps_per_step = (it1["total_iterations"] - it0["total_iterations"] + it1["velocity_sweeps"] - it0["velocity_sweeps"]) / args.steps
-    roofline = {"bound": "fp64", "kernel": "rb::sweep_kernel<MV>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum)
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tf) and world == 1:
+        traffic = json.load(open(tf)).get(str(N), {}).get("dram_bytes_per_launch")
+    kernel = "rb::sweep2_kernel<MV, 2> (persistent)" if N >= 49152 or N <= 4096 else "rb::sweep_kernel<MV> (tiled)"
+    roofline = {"bound": "fp64", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "bound_note": "FP64 vector pipe (DFMA), the roofline north_star names for the O(N^2) summation; HBM traffic per launch "
+                              "is ~1e-4 of what the HBM roofline would allow (working set lives in L2)",
                 "peak_source": "measured live by this library's DFMA-only probe (MEASURED_PEAKS.json holds no FP64 figure); "
                                "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2",
                 "algorithmic_flops_per_launch": F_PAIR * pairs / world, "launch_ms": sweep_ms,

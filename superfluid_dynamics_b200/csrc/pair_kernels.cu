@@ -499,13 +499,14 @@ __device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx
     }
 }
 
-// Solver sweeps need only Re(Zp_k T_k).  Away from the diagonal (no cell-local coordinates, no j == k) the numerator
-//   Re(Zp_k F_j conj(E_k - E_j)) = Re(A_k F_j) - Re(Zp_k) g_j ,   A_k = Zp_k conj(E_k),  g_j = x_j |E_j|^2  (real)
-// costs 3 instructions instead of 4 + 2: 11 FP64-pipe instructions per pair.  The cancellation between the two terms is
-// |E|/|E_k - E_j| <= 1/(cell spacing) ~ 40 (far tiles only), i.e. harmless.
-__device__ __forceinline__ void tile_accumulate_real(const SrcEntry* __restrict__ sh, const double* __restrict__ sg, int tile,
-                                                     const double2 (&ek)[kRowsPerThread], const double2 (&Ak)[kRowsPerThread],
-                                                     const double (&Gre)[kRowsPerThread], double (&accs)[kRowsPerThread]) {
+// Far tiles (no cell-local coordinates, no j == k) and the image sum, every mode: with conj(d) = conj(E_k) - conj(E_j),
+//   T_k = sum_j F_j conj(d)/|d|^2 = conj(E_k) U_k - V_k ,   U_k = sum_j F_j / |d|^2 (complex),  V_k = sum_j g_j / |d|^2 (real),
+//   g_j = x_j |E_j|^2: 2 DADD + DMUL + DFMA + (MUFU + 3 DFMA) + 3 DFMA = 10 FP64-pipe instructions per pair for the 20 algorithmic
+//   flops; the target-side product is applied once per row after the loop.  The two sums cancel by at most |E|/|E_k - E_j|
+//   <= 1/(cell width) ~ 40 in far tiles (<= 1/(1 - e^{-2h}) for the image sources), i.e. ~1e-15 relative in the row sum.
+__device__ __forceinline__ void tile_accumulate_far(const SrcEntry* __restrict__ sh, const double* __restrict__ sg, int tile,
+                                                    const double2 (&ek)[kRowsPerThread], double2 (&U)[kRowsPerThread],
+                                                    double (&V)[kRowsPerThread]) {
 #pragma unroll 4
     for (int s = 0; s < tile; ++s) {
         const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
@@ -517,29 +518,9 @@ __device__ __forceinline__ void tile_accumulate_real(const SrcEntry* __restrict_
             double di = ek[r].y - e.y;
             double n2 = fma(di, di, dr * dr);
             double inv = fast_rcp(n2);
-            double t1 = fma(Ak[r].y, f.y, Gre[r] * gj);      // A.im f.im + Re(Zp) g
-            double num = fma(Ak[r].x, f.x, -t1);              // Re(A F) - Re(Zp) g
-            accs[r] = fma(num, inv, accs[r]);
-        }
-    }
-}
-
-// image sum of a solver sweep: only Re(T_img) enters M x (L/createM.cuh:87-88: the image term carries no Zp_k), so the numerator is
-// Re(F conj(d)) = F_re d_re + F_im d_im: 10 FP64-pipe instructions per pair
-__device__ __forceinline__ void tile_accumulate_image_real(const SrcEntry* __restrict__ sh, int tile,
-                                                           const double2 (&ek)[kRowsPerThread], double2 (&acc)[kRowsPerThread]) {
-#pragma unroll 4
-    for (int s = 0; s < tile; ++s) {
-        const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
-        const double2 f = *reinterpret_cast<const double2*>(&sh[s].fr);
-#pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
-            double dr = ek[r].x - e.x;
-            double di = ek[r].y - e.y;
-            double n2 = fma(di, di, dr * dr);
-            double inv = fast_rcp(n2);
-            double tr = fma(f.y, di, f.x * dr);
-            acc[r].x = fma(tr, inv, acc[r].x);
+            U[r].x = fma(f.x, inv, U[r].x);
+            U[r].y = fma(f.y, inv, U[r].y);
+            V[r] = fma(gj, inv, V[r]);
         }
     }
 }
@@ -549,7 +530,8 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
     __shared__ SrcEntry sh[kCell];
     __shared__ SrcEntry shI[IMAGE ? kCell : 1];
     __shared__ double shg[kCell];
-    constexpr bool REALPATH = (MODE == kSweepMV);   // far tiles of a solver sweep: 11-instruction real-part form
+    __shared__ double shgI[IMAGE ? kCell : 1];
+    constexpr bool REALPATH = (MODE == kSweepMV);   // solver sweeps publish Re(Zp T) only
     __shared__ double sred[kSweepThreads];
     __shared__ unsigned int s_ticket;
 
@@ -568,24 +550,20 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 
     int krow[kRowsPerThread];
     int lrow[kRowsPerThread];
-    double2 acc[kRowsPerThread], accI[kRowsPerThread], ekG[kRowsPerThread], Ak[kRowsPerThread], zpk[kRowsPerThread];
-    double accs[kRowsPerThread], Gre[kRowsPerThread];
+    double2 acc[kRowsPerThread], ekG[kRowsPerThread], zpk[kRowsPerThread], U[kRowsPerThread], UI[kRowsPerThread];
+    double V[kRowsPerThread], VI[kRowsPerThread];
 #pragma unroll
     for (int r = 0; r < kRowsPerThread; ++r) {
         lrow[r] = t + r * kSweepThreads;
         krow[r] = cellK * kCell + lrow[r];
         acc[r] = make_double2(0.0, 0.0);
-        accI[r] = make_double2(0.0, 0.0);
-        accs[r] = 0.0;
+        U[r] = make_double2(0.0, 0.0);
+        UI[r] = make_double2(0.0, 0.0);
+        V[r] = 0.0;
+        VI[r] = 0.0;
         ekG[r] = krow[r] < N ? EG[krow[r]] : make_double2(3.0e150, 0.0);
         zpk[r] = make_double2(0.0, 0.0);
-        Ak[r] = make_double2(0.0, 0.0);
-        Gre[r] = 0.0;
-        if (REALPATH && krow[r] < N) {
-            zpk[r] = a.g.Zp[boff + krow[r]];
-            Ak[r] = make_double2(zpk[r].x * ekG[r].x + zpk[r].y * ekG[r].y, zpk[r].y * ekG[r].x - zpk[r].x * ekG[r].y);   // Zp conj(E_k)
-            Gre[r] = zpk[r].x;
-        }
+        if (REALPATH && krow[r] < N) zpk[r] = a.g.Zp[boff + krow[r]];
     }
 
     const int tile = a.tile;
@@ -612,7 +590,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                     double2 g = EG[j];
                     e.p = g.x; e.q = g.y;
                     e.fr = xj * g.x; e.fi = xj * g.y;
-                    if (REALPATH) shg[s] = xj * (g.x * g.x + g.y * g.y);
+                    shg[s] = xj * (g.x * g.x + g.y * g.y);
                 }
                 sh[s] = e;
                 if (IMAGE) {
@@ -620,12 +598,16 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
                     SrcEntry ei;
                     ei.p = gi.x; ei.q = gi.y; ei.fr = xj * gi.x; ei.fi = xj * gi.y;
                     shI[s] = ei;
+                    shgI[s] = xj * (gi.x * gi.x + gi.y * gi.y);
                 }
             } else {
                 e.p = 1.0e150; e.q = 0.0; e.fr = 0.0; e.fi = 0.0;   // contributes exactly 0
                 sh[s] = e;
-                if (REALPATH) shg[s] = 0.0;
-                if (IMAGE) shI[s] = e;
+                shg[s] = 0.0;
+                if (IMAGE) {
+                    shI[s] = e;
+                    shgI[s] = 0.0;
+                }
             }
         }
         // ---- this tile's view of the targets ---------------------------------------------
@@ -640,12 +622,9 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
         }
         __syncthreads();
         if (dist == 0) tile_accumulate<true>(sh, tile, ek, sd, acc);
-        else if (REALPATH && !near) tile_accumulate_real(sh, shg, tile, ek, Ak, Gre, accs);
+        else if (a.use_local && !near) tile_accumulate_far(sh, shg, tile, ekG, U, V);
         else           tile_accumulate<false>(sh, tile, ek, sd, acc);
-        if (IMAGE) {
-            if (MODE == kSweepMV) tile_accumulate_image_real(shI, tile, ekG, accI);   // only Re(T_img) is needed
-            else tile_accumulate<false>(shI, tile, ekG, sd, accI);
-        }
+        if (IMAGE) tile_accumulate_far(shI, shgI, tile, ekG, UI, VI);
     }
 
     // ---- publish the partial sums, elect the finishing CTA of this row cell --------------------
@@ -653,9 +632,14 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 #pragma unroll
     for (int r = 0; r < kRowsPerThread; ++r) {
         if (krow[r] < N) {
-            if (REALPATH) acc[r] = make_double2(zpk[r].x * acc[r].x - zpk[r].y * acc[r].y + accs[r], 0.0);   // Re(Zp T) of this chunk
+            // far part of this chunk: T += conj(E_k) U - V
+            acc[r].x += fma(ekG[r].x, U[r].x, ekG[r].y * U[r].y) - V[r];
+            acc[r].y += fma(ekG[r].x, U[r].y, -(ekG[r].y * U[r].x));
+            if (REALPATH) acc[r] = make_double2(zpk[r].x * acc[r].x - zpk[r].y * acc[r].y, 0.0);   // Re(Zp T) of this chunk
             a.partial[pbase + krow[r]] = acc[r];
-            if (IMAGE) a.partial_img[pbase + krow[r]] = accI[r];
+            if (IMAGE)
+                a.partial_img[pbase + krow[r]] = make_double2(fma(ekG[r].x, UI[r].x, ekG[r].y * UI[r].y) - VI[r],
+                                                               fma(ekG[r].x, UI[r].y, -(ekG[r].y * UI[r].x)));
         }
     }
     __threadfence();

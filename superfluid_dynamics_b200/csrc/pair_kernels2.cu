@@ -92,26 +92,38 @@ __device__ __forceinline__ void accumulate2(const Src2* __restrict__ sh, int len
     }
 }
 
-// 11-instruction real-part form for the far tiles of a solver sweep (see pair_kernels.cu, tile_accumulate_real)
+// Far tiles (no cell-local coordinates, no j == k), every mode: with conj(d) = conj(E_k) - conj(E_j),
+//   T_k = sum_j F_j conj(d)/|d|^2 = conj(E_k) U_k - V_k ,   U_k = sum_j F_j / |d|^2 (complex),  V_k = sum_j g_j / |d|^2 (real),
+//   g_j = x_j |E_j|^2, so the pair costs 2 DADD + DMUL + DFMA + (MUFU + 3 DFMA) + 3 DFMA = 10 FP64-pipe instructions for the 20
+//   algorithmic flops, and the target-side product is applied once per row after the loop.  The two sums cancel by at most
+//   |E|/|E_k - E_j| <= 1/(cell width) ~ 40 (far tiles only), i.e. ~1e-15 relative in the row sum.
 template <int R>
-__device__ __forceinline__ void accumulate2_real(const Src2* __restrict__ sh, const double* __restrict__ sg, int len,
-                                                 const double2 (&ek)[R], const double2 (&Ak)[R], const double (&Gre)[R],
-                                                 double (&accs)[R]) {
+__device__ __forceinline__ void accumulate2_far(const Src2* __restrict__ sh, const double* __restrict__ sg, int len,
+                                                const double2 (&ek)[R], double2 (&U)[R], double (&V)[R]) {
+    // software pipeline: the shared-memory loads of source s + 1 are issued before the arithmetic of source s (ncu: with the
+    // loads placed next to their first use, short-scoreboard stalls on LDS were the top stall reason of this loop)
+    double2 e = *reinterpret_cast<const double2*>(&sh[0].p);
+    double2 f = *reinterpret_cast<const double2*>(&sh[0].fr);
+    double gj = sg[0];
 #pragma unroll 4
     for (int s = 0; s < len; ++s) {
-        const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
-        const double2 f = *reinterpret_cast<const double2*>(&sh[s].fr);
-        const double gj = sg[s];
+        // (entry `len` is the next piece's first entry or the padding behind the staged tile: loaded, never used)
+        const double2 en = *reinterpret_cast<const double2*>(&sh[s + 1].p);
+        const double2 fn = *reinterpret_cast<const double2*>(&sh[s + 1].fr);
+        const double gn = sg[s + 1];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             double dr = ek[r].x - e.x;
             double di = ek[r].y - e.y;
             double n2 = fma(di, di, dr * dr);
             double inv = fast_rcp2(n2);
-            double t1 = fma(Ak[r].y, f.y, Gre[r] * gj);
-            double num = fma(Ak[r].x, f.x, -t1);
-            accs[r] = fma(num, inv, accs[r]);
+            U[r].x = fma(f.x, inv, U[r].x);
+            U[r].y = fma(f.y, inv, U[r].y);
+            V[r] = fma(gj, inv, V[r]);
         }
+        e = en;
+        f = fn;
+        gj = gn;
     }
 }
 
@@ -129,8 +141,10 @@ constexpr int kMaxStage = 1;   // staged entries per thread and tile (TS <= thre
 
 }  // namespace
 
-template <int MODE, int R>
-__global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const SweepArgs a) {
+// MAXT: launch bound (R = 2: 896 threads = 4 source groups at 72 registers; measured at N = 65536: 3 groups / 672 threads / 80
+// registers 3.56 ms against 3.11 ms -- resident warps matter more than registers here)
+template <int MODE, int R, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) sweep2_kernel(const SweepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x;
     const int TS = a.v2_TS;
@@ -178,23 +192,17 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
         const double2* __restrict__ P0 = a.g.P0 + boff;
         int krow[R];
         bool valid[R];
-        double2 acc[R], ek[R], Ak[R];
-        double accs[R], Gre[R];
+        double2 acc[R], ek[R], ekG[R], U[R];
+        double V[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             krow[r] = row0 + rt * R + r;
             valid[r] = krow[r] < rend;
             acc[r] = make_double2(0.0, 0.0);
-            accs[r] = 0.0;
+            U[r] = make_double2(0.0, 0.0);
+            V[r] = 0.0;
             ek[r] = make_double2(3.0e150, 0.0);
-            Ak[r] = make_double2(0.0, 0.0);
-            Gre[r] = 0.0;
-            if (REALPATH && valid[r]) {
-                const double2 eg = EG[krow[r]];
-                const double2 zp = a.g.Zp[boff + krow[r]];
-                Ak[r] = make_double2(zp.x * eg.x + zp.y * eg.y, zp.y * eg.x - zp.x * eg.y);   // Zp conj(E_k)
-                Gre[r] = zp.x;
-            }
+            ekG[r] = valid[r] ? EG[krow[r]] : make_double2(3.0e150, 0.0);
         }
         const int cellK = min(krow[0], N - 1) / kCell;
         const int cB0 = row0 / kCell, cB1 = (rend - 1) / kCell;
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
                         xs += xj;
                         e.p = pe[u].x; e.q = pe[u].y; e.fr = xj * pe[u].x; e.fi = xj * pe[u].y;
                         sh_far[s] = e;
-                        if (REALPATH) sh_g[s] = xj * (pe[u].x * pe[u].x + pe[u].y * pe[u].y);
+                        sh_g[s] = xj * (pe[u].x * pe[u].x + pe[u].y * pe[u].y);
                         if (pnear) {
                             Src2 n;
                             n.p = pp[u].x; n.q = pp[u].y; n.fr = xj * (1.0 + pp[u].x); n.fi = xj * pp[u].y;
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
                     } else {
                         e.p = 1.0e150; e.q = 0.0; e.fr = 0.0; e.fi = 0.0;   // contributes exactly 0
                         sh_far[s] = e;
-                        if (REALPATH) sh_g[s] = 0.0;
+                        sh_g[s] = 0.0;
                         if (pnear) sh_near[s] = e;
                     }
                 }
@@ -278,18 +286,24 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
                 for (int r = 0; r < R; ++r) sd[r] = krow[r] - jj;
                 const Src2* src = (near ? sh_near : sh_far) + sub0;
                 if (cellJ == cellK) accumulate2<true, R>(src, sublen, ek, sd, acc);
-                else if (REALPATH && !near) accumulate2_real<R>(src, sh_g + sub0, sublen, ek, Ak, Gre, accs);
+                else if (a.use_local && !near) accumulate2_far<R>(src, sh_g + sub0, sublen, ekG, U, V);
                 else                accumulate2<false, R>(src, sublen, ek, sd, acc);
             }
         }
 
         // ---- sum_j x_j (identical in every CTA: same staging pattern, same tree) and the cross-group combine ------------------
         double sumx = block_sum_any(xs, sred, T, P2);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {   // far part of this group's sources: T += conj(E_k) U - V
+            if (!valid[r]) continue;
+            acc[r].x += fma(ekG[r].x, U[r].x, ekG[r].y * U[r].y) - V[r];
+            acc[r].y += fma(ekG[r].x, U[r].y, -(ekG[r].y * U[r].x));
+        }
         if (REALPATH) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {   // Re(Zp T) of this group's sources: complex near part + real far part
+            for (int r = 0; r < R; ++r) {   // solver sweeps only need Re(Zp T)
                 const double2 zp = valid[r] ? a.g.Zp[boff + krow[r]] : make_double2(0.0, 0.0);
-                acc[r] = make_double2(zp.x * acc[r].x - zp.y * acc[r].y + accs[r], 0.0);
+                acc[r] = make_double2(zp.x * acc[r].x - zp.y * acc[r].y, 0.0);
             }
         }
         if (a.v2_groups > 1) {
@@ -470,26 +484,26 @@ __global__ void __launch_bounds__(R == 2 ? 896 : 1024, 1) sweep2_kernel(const Sw
     }
 }
 
-template <int MODE, int R>
+template <int MODE, int R, int MAXT>
 static void launch_one(const SweepArgs& a, const Sweep2Launch& l, cudaStream_t st) {
     static size_t configured = 0;
     if (l.smem > configured) {
-        RB_CUDA(cudaFuncSetAttribute(sweep2_kernel<MODE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
+        RB_CUDA(cudaFuncSetAttribute(sweep2_kernel<MODE, R, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
         configured = l.smem;
     }
-    sweep2_kernel<MODE, R><<<l.grid, l.threads, l.smem, st>>>(a);
+    sweep2_kernel<MODE, R, MAXT><<<l.grid, l.threads, l.smem, st>>>(a);
 }
 
 void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st) {
     if (a.has_image) throw std::runtime_error("sweep2: the image (finite-depth) sum uses the tiled kernel");
     if (a.v2_R == 2) {
-        if (mode == kSweepMV) launch_one<kSweepMV, 2>(a, l, st);
-        else if (mode == kSweepVEL) launch_one<kSweepVEL, 2>(a, l, st);
-        else launch_one<kSweepRAW, 2>(a, l, st);
+        if (mode == kSweepMV) launch_one<kSweepMV, 2, 896>(a, l, st);
+        else if (mode == kSweepVEL) launch_one<kSweepVEL, 2, 896>(a, l, st);
+        else launch_one<kSweepRAW, 2, 896>(a, l, st);
     } else {
-        if (mode == kSweepMV) launch_one<kSweepMV, 1>(a, l, st);
-        else if (mode == kSweepVEL) launch_one<kSweepVEL, 1>(a, l, st);
-        else launch_one<kSweepRAW, 1>(a, l, st);
+        if (mode == kSweepMV) launch_one<kSweepMV, 1, 1024>(a, l, st);
+        else if (mode == kSweepVEL) launch_one<kSweepVEL, 1, 1024>(a, l, st);
+        else launch_one<kSweepRAW, 1, 1024>(a, l, st);
     }
     RB_CUDA(cudaGetLastError());
     count_launch();

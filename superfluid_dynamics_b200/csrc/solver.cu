@@ -302,7 +302,7 @@ static void plan_sweep2(rb_solver* s) {
     s->v2l.grid = (int)std::min<long>((long)s->v2_total_blocks * s->v2_split, env_int("RB_V2_GRID", nSM));
     s->v2l.threads = threads;
     s->v2l.smem = (size_t)s->v2_TS * 32 * (s->use_local ? 2 : 1) + (size_t)threads * R * 16 + (size_t)threads * 8 +
-                  (size_t)s->v2_TS * 8;
+                  (size_t)s->v2_TS * 8 + 16;   // + one padding entry behind g: the far loop loads one source ahead
     if (s->v2_rnorm_part) cudaFree(s->v2_rnorm_part);
     s->v2_rnorm_part = dmalloc<double>(s->v2_total_blocks);
     if (s->v2_partial) cudaFree(s->v2_partial);

@@ -239,6 +239,26 @@ def overlapcmp():
     os.environ.pop("RB_OVERLAP", None)
 
 
+def tune3():
+    """persistent sweep at large N: 4 source groups (896 threads, 72 registers) against 3 (672 threads, 80 registers)"""
+    for N in (65536, 32768):
+        Z, Phi = ro.trochoid(N, 0.4)
+        st = T(ro.pack_state(Z, Phi))
+        for cfg in (dict(RB_SWEEP_V2="1"), dict(RB_SWEEP_V2="1", RB_V2_GROUPS="3"), dict(RB_SWEEP_V2="1", RB_V2_GROUPS="2"),
+                    dict(RB_SWEEP_V2="0")):
+            os.environ.update(cfg)
+            os.environ["RB_VERBOSE"] = "1"
+            try:
+                props = api.ProblemProperties(rho=0.0)
+                calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+                ms, pairs = calc.benchSweep(st, 10)
+                print(f"tune3 N={N} {cfg}: {ms * 1e3:.1f} us  {20 * pairs / (ms * 1e-3) / 1e12:.2f} TF", flush=True)
+            except Exception as e:
+                print(f"tune3 N={N} {cfg}: FAILED {e}", flush=True)
+            for k in list(cfg) + ["RB_VERBOSE"]:
+                os.environ.pop(k, None)
+
+
 def ensemble():
     """BASELINE config 5, second half: 1024-member ensemble at N = 512 (replicas only across GPUs)"""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
