@@ -243,7 +243,7 @@ def run_native(args):
     assert np.isfinite(final).all(), "state blew up"
 
     # ---- roofline of the dominant kernel (the sweep), measured live with CUDA events on the launching stream --------------
-    sweep_ms, pairs = calc.benchSweep(torch.as_tensor(y0, device=dev), 10)
+    sweep_ms, pairs = calc.benchSweep(torch.as_tensor(y0, device=dev), 30)
     peak = api.measure_fp64_peak(dev)
     achieved = F_PAIR * pairs / world / (sweep_ms * 1e-3) / 1e12
     it1 = calc.solve_stats()
@@ -255,7 +255,8 @@ def run_native(args):
     tf = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tf) and world == 1:
         traffic = json.load(open(tf)).get(str(N), {}).get("dram_bytes_per_launch")
-    kernel = "rb::sweep2_kernel<MV, 2> (persistent)" if N >= 49152 or N <= 4096 else "rb::sweep_kernel<MV> (tiled)"
+    kernel = "rb::sweep2_kernel<MV, 1> (persistent)" if N <= 4096 else \
+        ("rb::sweep_kernel<MV, 4 rows/thread> (tiled)" if N >= 49152 else "rb::sweep_kernel<MV, 2 rows/thread> (tiled)")
     roofline = {"bound": "fp64", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "bound_note": "FP64 vector pipe (DFMA), the roofline north_star names for the O(N^2) summation; HBM traffic per launch "

@@ -14,8 +14,7 @@ constexpr double kTwoPiLo = 2.4492935982947064e-16;       // 2 pi - fl(2 pi)
 
 // ---- tiling constants of the pair-interaction (cotangent-sum) kernels -------------------
 constexpr int kCell = 256;           // points per cell == targets (rows) per CTA == max source tile
-constexpr int kSweepThreads = 128;   // threads per CTA of the sweep kernel
-constexpr int kRowsPerThread = 2;    // register blocking: kCell == kSweepThreads * kRowsPerThread
+// the tiled sweep kernel is templated on the rows per thread RPT (2 or 4): kCell / RPT threads per CTA
 constexpr int kMinCellsForLocal = 4; // below this every tile uses the global exponentials
 
 inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
@@ -113,6 +112,7 @@ enum SweepMode { kSweepMV = 0, kSweepVEL = 1, kSweepRAW = 2 };
 struct SweepArgs {
     // sizes
     int N, batch, ncell;             // ncell = ceil(N / kCell)
+    int rows_per_thread;             // tiled kernel: register blocking (2 or 4 rows per thread, CTA = kCell / rows threads)
     int tile;                        // sources per smem tile (64, 128 or 256; divides kCell)
     int tiles_per_chunk;             // source tiles handled by one CTA
     int nchunks;                     // gridDim.y

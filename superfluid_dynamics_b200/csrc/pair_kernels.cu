@@ -412,15 +412,15 @@ struct __align__(16) SrcEntry {   // one source point in shared memory: 2 x LDS.
     double fr, fi;                // F_j = x_j E_j
 };
 
-template <bool DIAG>
-__device__ __forceinline__ void tile_accumulate(const SrcEntry* __restrict__ sh, int tile, const double2 (&ek)[kRowsPerThread],
-                                                const int (&sd)[kRowsPerThread], double2 (&acc)[kRowsPerThread]) {
+template <bool DIAG, int RPT>
+__device__ __forceinline__ void tile_accumulate(const SrcEntry* __restrict__ sh, int tile, const double2 (&ek)[RPT],
+                                                const int (&sd)[RPT], double2 (&acc)[RPT]) {
 #pragma unroll 4
     for (int s = 0; s < tile; ++s) {
         const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
         const double2 f = *reinterpret_cast<const double2*>(&sh[s].fr);
 #pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
+        for (int r = 0; r < RPT; ++r) {
             double dr = ek[r].x - e.x;
             double di = ek[r].y - e.y;
             double n2 = fma(di, di, dr * dr);
@@ -435,11 +435,12 @@ __device__ __forceinline__ void tile_accumulate(const SrcEntry* __restrict__ sh,
 }
 
 // closing of a solver sweep (MV, or VEL in combined mode): per-cell sums, tickets, and the convergence decision by the last CTA
+template <int THREADS>
 __device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx, double sr, int bm, int cellK, double* sred,
                                                    unsigned int* s_ticket) {
     const int t = threadIdx.x;
-    sx = block_reduce_fixed<kSweepThreads>(sx, sred);
-    sr = block_reduce_fixed<kSweepThreads>(sr, sred);
+    sx = block_reduce_fixed<THREADS>(sx, sred);
+    sr = block_reduce_fixed<THREADS>(sr, sred);
     if (a.comm.nranks > 1) __threadfence_system();   // this CTA's remote row stores before its ticket
     __syncthreads();
     if (t == 0) {
@@ -452,7 +453,7 @@ __device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx
     if (*s_ticket != (unsigned)(a.row_cells - 1)) return;
     // ---- level 2: last row cell of this batch member ---------------------------------------
     __threadfence();
-    double rn = block_sum_fixed<kSweepThreads>(a.rnorm_part + (size_t)bm * a.ncell + a.row_cell0, a.row_cells, sred);
+    double rn = block_sum_fixed<THREADS>(a.rnorm_part + (size_t)bm * a.ncell + a.row_cell0, a.row_cells, sred);
     if (a.comm.nranks > 1) {
         // row-sharded: publish this rank's residual sum and signal; the decision is taken by comm_wait_kernel on every
         // rank from the same numbers in the same order
@@ -465,7 +466,7 @@ __device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx
         }
         return;
     }
-    double bn = block_sum_fixed<kSweepThreads>(a.bnorm_part + (size_t)bm * a.ncell, a.ncell, sred);
+    double bn = block_sum_fixed<THREADS>(a.bnorm_part + (size_t)bm * a.ncell, a.ncell, sred);
     if (t == 0) {
         a.member_tickets[bm] = 0u;
         double rel2 = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
@@ -504,16 +505,17 @@ __device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx
 //   g_j = x_j |E_j|^2: 2 DADD + DMUL + DFMA + (MUFU + 3 DFMA) + 3 DFMA = 10 FP64-pipe instructions per pair for the 20 algorithmic
 //   flops; the target-side product is applied once per row after the loop.  The two sums cancel by at most |E|/|E_k - E_j|
 //   <= 1/(cell width) ~ 40 in far tiles (<= 1/(1 - e^{-2h}) for the image sources), i.e. ~1e-15 relative in the row sum.
+template <int RPT>
 __device__ __forceinline__ void tile_accumulate_far(const SrcEntry* __restrict__ sh, const double* __restrict__ sg, int tile,
-                                                    const double2 (&ek)[kRowsPerThread], double2 (&U)[kRowsPerThread],
-                                                    double (&V)[kRowsPerThread]) {
+                                                    const double2 (&ek)[RPT], double2 (&U)[RPT],
+                                                    double (&V)[RPT]) {
 #pragma unroll 4
     for (int s = 0; s < tile; ++s) {
         const double2 e = *reinterpret_cast<const double2*>(&sh[s].p);
         const double2 f = *reinterpret_cast<const double2*>(&sh[s].fr);
         const double gj = sg[s];
 #pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
+        for (int r = 0; r < RPT; ++r) {
             double dr = ek[r].x - e.x;
             double di = ek[r].y - e.y;
             double n2 = fma(di, di, dr * dr);
@@ -525,14 +527,15 @@ __device__ __forceinline__ void tile_accumulate_far(const SrcEntry* __restrict__
     }
 }
 
-template <int MODE, bool IMAGE>
-__global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a) {
+template <int MODE, bool IMAGE, int RPT>
+__global__ void __launch_bounds__(kCell / RPT, RPT == 4 ? 8 : (IMAGE ? 5 : 7)) sweep_kernel(const SweepArgs a) {
+    constexpr int THREADS = kCell / RPT;   // one CTA = one 256-row cell: THREADS threads x RPT rows
     __shared__ SrcEntry sh[kCell];
     __shared__ SrcEntry shI[IMAGE ? kCell : 1];
     __shared__ double shg[kCell];
     __shared__ double shgI[IMAGE ? kCell : 1];
     constexpr bool REALPATH = (MODE == kSweepMV);   // solver sweeps publish Re(Zp T) only
-    __shared__ double sred[kSweepThreads];
+    __shared__ double sred[THREADS];
     __shared__ unsigned int s_ticket;
 
     if ((MODE == kSweepMV || MODE == kSweepVEL) && a.skip_if_done) {
@@ -548,13 +551,13 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
     const double2* __restrict__ EG = a.g.EG + boff;
     const double2* __restrict__ P0 = a.g.P0 + boff;
 
-    int krow[kRowsPerThread];
-    int lrow[kRowsPerThread];
-    double2 acc[kRowsPerThread], ekG[kRowsPerThread], zpk[kRowsPerThread], U[kRowsPerThread], UI[kRowsPerThread];
-    double V[kRowsPerThread], VI[kRowsPerThread];
+    int krow[RPT];
+    int lrow[RPT];
+    double2 acc[RPT], ekG[RPT], zpk[RPT], U[RPT], UI[RPT];
+    double V[RPT], VI[RPT];
 #pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
-        lrow[r] = t + r * kSweepThreads;
+    for (int r = 0; r < RPT; ++r) {
+        lrow[r] = t + r * THREADS;
         krow[r] = cellK * kCell + lrow[r];
         acc[r] = make_double2(0.0, 0.0);
         U[r] = make_double2(0.0, 0.0);
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
         const bool near = a.use_local && (dist == 0 || dist == 1 || dist == a.ncell - 1);
         // ---- stage the source tile -------------------------------------------------------
         __syncthreads();
-        for (int s = t; s < tile; s += kSweepThreads) {
+        for (int s = t; s < tile; s += THREADS) {
             int j = j0 + s;
             SrcEntry e;
             if (j < N) {
@@ -611,26 +614,26 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
             }
         }
         // ---- this tile's view of the targets ---------------------------------------------
-        double2 ek[kRowsPerThread];
-        int sd[kRowsPerThread];
+        double2 ek[RPT];
+        int sd[RPT];
         const double2* __restrict__ tk = EG;
         if (near) tk = (dist == 0) ? P0 : (dist == 1 ? a.g.Pp + boff : a.g.Pm + boff);
 #pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
+        for (int r = 0; r < RPT; ++r) {
             ek[r] = krow[r] < N ? tk[krow[r]] : make_double2(3.0e150, 0.0);
             sd[r] = lrow[r] - (j0 - cellJ * kCell);
         }
         __syncthreads();
-        if (dist == 0) tile_accumulate<true>(sh, tile, ek, sd, acc);
-        else if (a.use_local && !near) tile_accumulate_far(sh, shg, tile, ekG, U, V);
-        else           tile_accumulate<false>(sh, tile, ek, sd, acc);
-        if (IMAGE) tile_accumulate_far(shI, shgI, tile, ekG, UI, VI);
+        if (dist == 0) tile_accumulate<true, RPT>(sh, tile, ek, sd, acc);
+        else if (a.use_local && !near) tile_accumulate_far<RPT>(sh, shg, tile, ekG, U, V);
+        else           tile_accumulate<false, RPT>(sh, tile, ek, sd, acc);
+        if (IMAGE) tile_accumulate_far<RPT>(shI, shgI, tile, ekG, UI, VI);
     }
 
     // ---- publish the partial sums, elect the finishing CTA of this row cell --------------------
     const size_t pbase = ((size_t)bm * a.nchunks + chunk) * N;
 #pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         if (krow[r] < N) {
             // far part of this chunk: T += conj(E_k) U - V
             acc[r].x += fma(ekG[r].x, U[r].x, ekG[r].y * U[r].y) - V[r];
@@ -652,24 +655,24 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
     if (t == 0) *cticket = 0u;   // ready for the next launch
 
     // ---- finishing CTA: fixed-order reduction over chunks + epilogue ---------------------------
-    double2 T[kRowsPerThread], TI[kRowsPerThread];
+    double2 T[RPT], TI[RPT];
 #pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         T[r] = make_double2(0.0, 0.0);
         TI[r] = make_double2(0.0, 0.0);
     }
     {
         // independent loads are issued in batches of 8 (memory-level parallelism), the additions stay in chunk order
-        constexpr int kBatch = IMAGE ? 4 : 8;
+        constexpr int kBatch = (IMAGE ? 4 : 8) * 2 / RPT;
         const size_t cstride = (size_t)N;
         const double2* pbase0 = a.partial + (size_t)bm * a.nchunks * N;
         const double2* ibase0 = IMAGE ? a.partial_img + (size_t)bm * a.nchunks * N : nullptr;
         for (int c0 = 0; c0 < a.nchunks; c0 += kBatch) {
-            double2 v[kRowsPerThread][kBatch], vi[kRowsPerThread][kBatch];
+            double2 v[RPT][kBatch], vi[RPT][kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
 #pragma unroll
-                for (int r = 0; r < kRowsPerThread; ++r) {
+                for (int r = 0; r < RPT; ++r) {
                     const bool ok = (c0 + u) < a.nchunks && krow[r] < N;
                     v[r][u] = ok ? ldcg_d2(pbase0 + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
                     if (IMAGE) vi[r][u] = ok ? ldcg_d2(ibase0 + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
@@ -678,20 +681,20 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
 #pragma unroll
-                for (int r = 0; r < kRowsPerThread; ++r) {
+                for (int r = 0; r < RPT; ++r) {
                     T[r].x += v[r][u].x; T[r].y += v[r][u].y;
                     if (IMAGE) { TI[r].x += vi[r][u].x; TI[r].y += vi[r][u].y; }
                 }
             }
         }
     }
-    const double sumx = block_sum_fixed<kSweepThreads>(a.xsum_part + (size_t)bm * a.ncell, a.ncell, sred);
+    const double sumx = block_sum_fixed<THREADS>(a.xsum_part + (size_t)bm * a.ncell, a.ncell, sred);
     const double inv4pi = 0.25 / kPi;
 
     if (MODE == kSweepMV) {
         double sx = 0.0, sr = 0.0;
 #pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
+        for (int r = 0; r < RPT; ++r) {
             if (krow[r] < N) {
                 const size_t o = boff + krow[r];
                 double xk = x[krow[r]];
@@ -727,14 +730,14 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
             }
             return;
         }
-        solver_sweep_close(a, sx, sr, bm, cellK, sred, &s_ticket);
+        solver_sweep_close<THREADS>(a, sx, sr, bm, cellK, sred, &s_ticket);
         return;
     }
 
     if (MODE == kSweepVEL) {
         double sx = 0.0, sr = 0.0;
 #pragma unroll
-        for (int r = 0; r < kRowsPerThread; ++r) {
+        for (int r = 0; r < RPT; ++r) {
             if (krow[r] < N) {
                 const size_t o = boff + krow[r];
                 double ak = x[krow[r]];
@@ -780,7 +783,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
             }
         }
         if (a.combined) {
-            solver_sweep_close(a, sx, sr, bm, cellK, sred, &s_ticket);
+            solver_sweep_close<THREADS>(a, sx, sr, bm, cellK, sred, &s_ticket);
             return;
         }
         if (a.comm.nranks > 1) {
@@ -800,7 +803,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepArgs a)
 
     // RAW: S_k = i A_k
 #pragma unroll
-    for (int r = 0; r < kRowsPerThread; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         if (krow[r] < N) {
             double xk = x[krow[r]];
             double Ar = (sumx - xk) + 2.0 * T[r].x;
@@ -878,18 +881,24 @@ void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity
     count_launch();
 }
 
-void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st) {
+template <int RPT>
+static void launch_sweep_rpt(const SweepArgs& a, int mode, cudaStream_t st) {
     dim3 grid(a.row_cells, a.nchunks, a.batch);
-    dim3 block(kSweepThreads);
+    dim3 block(kCell / RPT);
     if (a.has_image) {
-        if (mode == kSweepMV) sweep_kernel<kSweepMV, true><<<grid, block, 0, st>>>(a);
-        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, true><<<grid, block, 0, st>>>(a);
+        if (mode == kSweepMV) sweep_kernel<kSweepMV, true, RPT><<<grid, block, 0, st>>>(a);
+        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, true, RPT><<<grid, block, 0, st>>>(a);
         else throw std::runtime_error("raw cotangent sum with image term is not defined");
     } else {
-        if (mode == kSweepMV) sweep_kernel<kSweepMV, false><<<grid, block, 0, st>>>(a);
-        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, false><<<grid, block, 0, st>>>(a);
-        else sweep_kernel<kSweepRAW, false><<<grid, block, 0, st>>>(a);
+        if (mode == kSweepMV) sweep_kernel<kSweepMV, false, RPT><<<grid, block, 0, st>>>(a);
+        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, false, RPT><<<grid, block, 0, st>>>(a);
+        else sweep_kernel<kSweepRAW, false, RPT><<<grid, block, 0, st>>>(a);
     }
+}
+
+void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st) {
+    if (a.rows_per_thread == 4) launch_sweep_rpt<4>(a, mode, st);
+    else launch_sweep_rpt<2>(a, mode, st);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -76,6 +76,7 @@ struct rb_solver {
 
     // chunking of the tiled sweep (pair_kernels.cu)
     int tile = 256, tiles_per_chunk = 1, nchunks = 1;
+    int v1_rows = 2;               // tiled kernel: rows per thread (RB_V1_ROWS)
     // schedule of the persistent sweep (pair_kernels2.cu); used whenever there is no image sum
     bool use_v2 = false;
     int v2_RB = 0, v2_R = 0, v2_groups = 0, v2_spg = 0, v2_TS = 0, v2_bpm = 0, v2_total_blocks = 0;
@@ -204,7 +205,12 @@ static void solver_free(rb_solver* s) {
 
 static void choose_chunking(rb_solver* s) {
     const int N = s->N;
-    const int target = env_int("RB_TARGET_CTAS", 148 * 8);
+    // measured on a B200 (solver sweep, us): N = 65536: 2 rows per thread 3200 (target 1184) / 3108 (2368); 4 rows per thread 3391 / 3011 /
+    // 2931 (4736) / 2893 (9472) / 2875 (18944); 8 rows per thread 3556 at best -- the persistent kernel: 3113;
+    // N = 32768: 832 / 813 | 912 / 830 / 819; N = 16384: 248 / 234 | 314 / 265 / 235; N = 8192: 80.5 / 74.2 | 102 / 84; N = 4096: 32.8 / 32.9 | 41
+    const bool big = N >= 49152;
+    s->v1_rows = env_int("RB_V1_ROWS", big ? 4 : 2) == 4 ? 4 : 2;
+    const int target = env_int("RB_TARGET_CTAS", big ? 148 * 128 : (N >= 8192 ? 148 * 16 : 148 * 8));
     long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
     int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
     int max_chunks = std::max(1, (N + 63) / 64);
@@ -330,11 +336,11 @@ static void choose_sweep_kernel(rb_solver* s) {
     int nSM = 148;
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
     const double eff = s->v2_eff;
-    // measured on a B200 (MV sweep alone, us; tiled / persistent): N=256 18.5/12.3, 1024 18.5/18.5, 2048 21.8/25.2, 4096 34.8/37.3,
-    // 8192 84/96, 16384 250/287, 32768 891/968, 65536 3512/3380.  Inside a recorded step the persistent kernel still wins up to
-    // N = 4096 (its skipped launches and its combined sweep are cheaper: 2089 against 1889 steps/s at N = 4096).
+    // measured on a B200 (solver sweep alone, us; tiled / persistent): N=256 18.5/12.3, 1024 18.5/18.5, 2048 21.8/25.2, 4096 32.8/37.3,
+    // 8192 74/96, 16384 234/287, 32768 813/974, 65536 2931 (4 rows per thread)/3113.  Inside a recorded step the persistent kernel
+    // still wins up to N = 4096 (its skipped launches and its combined sweep are cheaper: 2089 against 1889 steps/s at N = 4096).
     // Ensembles (batch > 1) keep the persistent kernel whenever its schedule fills the SMs.
-    bool v2 = !s->has_image && ((eff >= 0.95 && ((long)s->N >= 49152 || s->batch > 1)) || (long)s->N * s->batch <= 4096);
+    bool v2 = !s->has_image && ((eff >= 0.95 && s->batch > 1) || (long)s->N * s->batch <= 4096);
     int force = env_int("RB_SWEEP_V2", -1);
     if (force >= 0) v2 = !s->has_image && force != 0;
     s->use_v2 = v2;
@@ -622,6 +628,7 @@ static SweepArgs base_args(rb_solver* s, const double2* Z) {
     a.N = s->N;
     a.batch = s->batch;
     a.ncell = s->ncell;
+    a.rows_per_thread = s->v1_rows;
     a.tile = s->tile;
     a.tiles_per_chunk = s->tiles_per_chunk;
     a.nchunks = s->nchunks;

@@ -259,6 +259,25 @@ def tune3():
                 os.environ.pop(k, None)
 
 
+def tune4():
+    """tiled sweep at N = 65536: rows per thread (CTA = 256 / rows threads) against the CTA-count target"""
+    N = 65536
+    Z, Phi = ro.trochoid(N, 0.4)
+    st = T(ro.pack_state(Z, Phi))
+    for rows, target in ((4, 4736), (4, 9472), (4, 18944), (8, 4736), (8, 9472), (8, 18944), (8, 37888)):
+        cfg = dict(RB_SWEEP_V2="0", RB_V1_ROWS=str(rows), RB_TARGET_CTAS=str(target))
+        os.environ.update(cfg)
+        try:
+            props = api.ProblemProperties(rho=0.0)
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+            ms, pairs = calc.benchSweep(st, 8)
+            print(f"tune4 N={N} rows={rows} target={target}: {ms * 1e3:.1f} us  {20 * pairs / (ms * 1e-3) / 1e12:.2f} TF", flush=True)
+        except Exception as e:
+            print(f"tune4 N={N} {cfg}: FAILED {e}", flush=True)
+        for k in cfg:
+            os.environ.pop(k, None)
+
+
 def ensemble():
     """BASELINE config 5, second half: 1024-member ensemble at N = 512 (replicas only across GPUs)"""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
