@@ -185,8 +185,14 @@ def run_native(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner (printed at VERSION and at WARN level) and anything else it
+        # logs go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)      # belt and braces: whatever a native library writes to fd 1 during the run lands on stderr
+        os.dup2(2, 1)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
@@ -323,6 +329,9 @@ def run_native(args):
                     dtype="f64", data="synthetic", config=workload_config(N), roofline=roofline, cpu_baseline=cpu, e2e=e2e,
                     gpu_launches=int(launches), clocks=clocks, solver_iterations_per_rhs=mv_per_rhs,
                     **extra)
+        if world > 1:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
