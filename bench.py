@@ -261,7 +261,7 @@ def run_native(args):
     tf = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tf) and world == 1:
         traffic = json.load(open(tf)).get(str(N), {}).get("dram_bytes_per_launch")
-    kernel = "rb::sweep2_kernel<MV, 1> (persistent)" if N <= 4096 else \
+    kernel = "rb::sweep2_kernel<MV, 1> (persistent)" if N <= 1024 else \
         ("rb::sweep_kernel<MV, 4 rows/thread> (tiled)" if N >= 49152 else "rb::sweep_kernel<MV, 2 rows/thread> (tiled)")
     roofline = {"bound": "fp64", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,

@@ -210,7 +210,7 @@ static void choose_chunking(rb_solver* s) {
     // N = 32768: 832 / 813 | 912 / 830 / 819; N = 16384: 248 / 234 | 314 / 265 / 235; N = 8192: 80.5 / 74.2 | 102 / 84; N = 4096: 32.8 / 32.9 | 41
     const bool big = N >= 49152;
     s->v1_rows = env_int("RB_V1_ROWS", big ? 4 : 2) == 4 ? 4 : 2;
-    const int target = env_int("RB_TARGET_CTAS", big ? 148 * 128 : (N >= 8192 ? 148 * 16 : 148 * 8));
+    const int target = env_int("RB_TARGET_CTAS", big ? 148 * 128 : (N >= 2048 ? 148 * 16 : 148 * 8));
     long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
     int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
     int max_chunks = std::max(1, (N + 63) / 64);
@@ -337,10 +337,10 @@ static void choose_sweep_kernel(rb_solver* s) {
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
     const double eff = s->v2_eff;
     // measured on a B200 (solver sweep alone, us; tiled / persistent): N=256 18.5/12.3, 1024 18.5/18.5, 2048 21.8/25.2, 4096 32.8/37.3,
-    // 8192 74/96, 16384 234/287, 32768 813/974, 65536 2931 (4 rows per thread)/3113.  Inside a recorded step the persistent kernel
-    // still wins up to N = 4096 (its skipped launches and its combined sweep are cheaper: 2089 against 1889 steps/s at N = 4096).
+    // 8192 74/96, 16384 234/287, 32768 813/974, 65536 2875 (4 rows per thread)/3113; recorded RK4 steps per second, tiled / persistent:
+    // N=1024 4074/4073, 2048 3678/3387, 4096 2546/2465, 8192 1126/902.
     // Ensembles (batch > 1) keep the persistent kernel whenever its schedule fills the SMs.
-    bool v2 = !s->has_image && ((eff >= 0.95 && s->batch > 1) || (long)s->N * s->batch <= 4096);
+    bool v2 = !s->has_image && ((eff >= 0.95 && s->batch > 1) || (long)s->N * s->batch <= 1024);
     int force = env_int("RB_SWEEP_V2", -1);
     if (force >= 0) v2 = !s->has_image && force != 0;
     s->use_v2 = v2;

@@ -278,6 +278,30 @@ def tune4():
             os.environ.pop(k, None)
 
 
+def kernelcmp():
+    """step rate with the persistent (v2) against the tiled (v1) sweep kernel in the launch-bound regime"""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    for N, dt in ((1024, 1e-3), (2048, 1e-3), (4096, 1e-3), (8192, 5e-4)):
+        for cfg in (dict(RB_SWEEP_V2="1"), dict(RB_SWEEP_V2="0"), dict(RB_SWEEP_V2="0", RB_TARGET_CTAS="592"),
+                    dict(RB_SWEEP_V2="0", RB_TARGET_CTAS="2368")):
+            os.environ.update(cfg)
+            props = api.ProblemProperties(rho=0.0)
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+            Z, Phi = ro.trochoid(N, 0.4)
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+            st = T(ro.pack_state(Z, Phi))
+            stp.initialize(st, True)
+            stp.runSteps(20)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            stp.runSteps(300)
+            torch.cuda.synchronize()
+            el = time.time() - t0
+            print(f"kernelcmp N={N} {cfg}: {300 / el:.1f} steps/s {stp.stats()}", flush=True)
+            for k in cfg:
+                os.environ.pop(k, None)
+
+
 def ensemble():
     """BASELINE config 5, second half: 1024-member ensemble at N = 512 (replicas only across GPUs)"""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
