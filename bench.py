@@ -7,7 +7,9 @@ A "step" is one classical RK4 step (4 RHS evaluations: FFT derivatives, matrix-f
 O(N^2) velocity summation, fused stage update) of one synthetic trochoidal ("Stokes") surface, h = 0.4, dt = 1e-3.
 Prints ONE JSON line.  Under torchrun (N > 1) the row blocks of every O(N^2) sweep are sharded over the ranks.
 --impl reference times the CPU statement of the same path (oracle port of the reference's NumPy/LAPACK arithmetic) on a
-bounded sample of the same workload on the host cores.
+bounded sample of the same workload on the host cores.  Both arms also report, as context, the RK4 step rate of the
+reference's own CUDA path (its classes compiled unmodified into oracle/_ref/, run in a child process on the same GPU) at the
+sizes it supports (N <= 16384 here; N = 65536 overflows its int indices).
 """
 import argparse
 import json
@@ -93,6 +95,23 @@ def cpu_baseline(N, budget_s=20.0):
                         f"scaled by (N/n)^3, complex mat-vec at n={n_lu} scaled by (N/n)^2; per step = 4 x (3 assemblies + LU + 2 mat-vec)"))
 
 
+def reference_gpu_rates(sizes):
+    """RK4 steps/s of the reference's own CUDA path (oracle/_ref, child process, same GPU) on the bench surface at each N."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        return {}
+    jobs = [dict(op="rk4", kind="water", N=n, props=dict(rho=0.0), state=trochoid_state(n), dt=time_step(n),
+                 warmup=2 if n <= 4096 else 1, steps=8 if n <= 4096 else 2) for n in sizes]
+    out = {}
+    for j, r in zip(jobs, ref_runner.run_jobs(jobs, timeout=240)):
+        if "error" in r:
+            out[j["N"]] = {"error": r["error"][:200]}
+        else:
+            out[j["N"]] = {"steps_per_s": j["steps"] / r["seconds"], "steps": j["steps"], "warmup": j["warmup"],
+                           "finite": bool(np.isfinite(r["state"]).all())}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -108,10 +127,17 @@ def run_reference(args):
         if time.perf_counter() - t_all > 150:
             break
     v = float(np.mean(vals)) if vals else base["value"]
+    # context only (not this line's value): the reference's own CUDA path at the largest bench size it supports, if a GPU is here
+    ref_cuda = None
+    if not args.no_reference_gpu:
+        r = reference_gpu_rates([4096]).get(4096)
+        if r:
+            ref_cuda = dict(r, N=4096, what="reference's own CUDA path (oracle/_ref) on this box's GPU 0; it cannot run N=65536 "
+                                            "(int indices overflow at n >= 46341, L/createM.cuh:52)")
     line = dict(metric=f"RK4 steps/s at N={N}", value=v, unit="steps/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 / v, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                 impl="reference", config=workload_config(N),
-                cpu_baseline=dict(base, value=v),
+                cpu_baseline=dict(base, value=v), reference_cuda=ref_cuda,
                 e2e=dict(value=v, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -306,23 +332,39 @@ def run_native(args):
             t0 = time.perf_counter()
             api.integrate_rk4_host(init, N, 1, props, "water", time_step(N), args.steps)
             extra["e2e_one_call_steps_per_s"] = args.steps / (time.perf_counter() - t0)
-            # the second size the metric names
-            n2 = 4096 if N != 4096 else 65536
-            c2 = api.BaseBoundaryIntegralCalculator(n2, 1, props, api.WaterBoundaryProblem(props), device=dev, guess="warm")
-            s2 = api.AutonomousRungeKuttaStepper(c2, time_step(n2))
-            s2.initialize(torch.as_tensor(trochoid_state(n2), device=dev), True)
-            k2 = 100 if n2 <= 8192 else args.steps
-            s2.runSteps(10 if n2 <= 8192 else 3)
-            torch.cuda.synchronize(dev)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            s2.runSteps(k2)
-            b.record()
-            torch.cuda.synchronize(dev)
-            ms2, pr2 = c2.benchSweep(torch.as_tensor(trochoid_state(n2), device=dev), 20)
-            extra[f"n{n2}"] = {"steps_per_s": k2 / (a.elapsed_time(b) * 1e-3), "steps": k2, "sweep_ms": ms2,
-                               "sweep_tflops": F_PAIR * pr2 / (ms2 * 1e-3) / 1e12,
-                               "sweep_frac_of_fp64_peak": F_PAIR * pr2 / (ms2 * 1e-3) / 1e12 / peak}
+            # the other sizes: N = 4096 (the second size the metric names) and N = 16384, each next to the REFERENCE'S OWN CUDA path
+            # (oracle/_ref/libcusuperhelium_ref.so: its classes compiled unmodified, run in a child process on this same GPU;
+            # N = 65536 is beyond it: int indices overflow at n >= 46341, L/createM.cuh:52)
+            ref_gpu = reference_gpu_rates([n for n in (4096, 16384) if n != N]) if not args.no_reference_gpu else {}
+            for n2 in (4096, 16384, 65536):
+                if n2 == N or (n2 == 65536 and N != 4096):
+                    continue
+                c2 = api.BaseBoundaryIntegralCalculator(n2, 1, props, api.WaterBoundaryProblem(props), device=dev, guess="warm")
+                s2 = api.AutonomousRungeKuttaStepper(c2, time_step(n2))
+                s2.initialize(torch.as_tensor(trochoid_state(n2), device=dev), True)
+                k2 = 100 if n2 <= 8192 else (30 if n2 <= 16384 else args.steps)
+                s2.runSteps(12)
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                s2.runSteps(k2)
+                b.record()
+                torch.cuda.synchronize(dev)
+                ms2, pr2 = c2.benchSweep(torch.as_tensor(trochoid_state(n2), device=dev), 20)
+                extra[f"n{n2}"] = {"steps_per_s": k2 / (a.elapsed_time(b) * 1e-3), "steps": k2, "sweep_ms": ms2,
+                                   "sweep_tflops": F_PAIR * pr2 / (ms2 * 1e-3) / 1e12,
+                                   "sweep_frac_of_fp64_peak": F_PAIR * pr2 / (ms2 * 1e-3) / 1e12 / peak}
+                r = ref_gpu.get(n2)
+                if r and "steps_per_s" in r:
+                    extra[f"n{n2}"]["reference_cuda_steps_per_s"] = r["steps_per_s"]
+                    extra[f"n{n2}"]["speedup_vs_reference_cuda"] = extra[f"n{n2}"]["steps_per_s"] / r["steps_per_s"]
+                elif r:
+                    extra[f"n{n2}"]["reference_cuda"] = r
+                del s2, c2
+            if ref_gpu:
+                extra["reference_cuda_note"] = ("reference_cuda_* = the reference's own CUDA path (BaseBoundaryIntegralCalculator + "
+                                                "AutonomousRungeKuttaStepper compiled unmodified from its sources, oracle/build_ref.py) "
+                                                "on this same GPU, same surface and dt, host clock around the steps after warm-up")
         cpu = cpu_baseline(N) if (world == 1 and not args.no_cpu) else None
         line = dict(metric=f"RK4 steps/s at N={N}", value=value, unit="steps/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -345,7 +387,8 @@ def main():
     ap.add_argument("--n", type=int, default=65536)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-extra", action="store_true", help="skip the N=4096 and one-call extras")
+    ap.add_argument("--no-extra", action="store_true", help="skip the N=4096 / N=16384 and one-call extras")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the compiled reference CUDA path (oracle/_ref)")
     args = ap.parse_args()
     # the stepper tunes the number of recorded sweeps and fills its 4-step stage history during the first steps: warm up past that
     args.warmup = max(args.warmup, 12) if args.impl == "native" else args.warmup

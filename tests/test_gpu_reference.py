@@ -1,0 +1,79 @@
+"""GPU parity against the REFERENCE ITSELF (run with -m gpu on a B200): this repo's CUDA path, called through the C ABI, against
+the reference's own CUDA classes compiled from /root/reference into oracle/_ref/libcusuperhelium_ref.so (oracle/build_ref.py)
+and executed on the same GPU in a child process.  The library is built in the development container (where /root/reference
+exists) and travels to the GPU box; the tests skip, saying so, when it is absent or when the reference's child process did not
+deliver a result -- a numeric difference beyond the tolerance is a failure.
+
+Tolerances (floating point, FP64; relative to the max of the reference's array):
+  * RHS level (velocity, dPhi/dt, vortex-sheet strength a, upper-fluid velocity, derivatives): 1e-10 for water / infinite depth.
+    Expected differences are far smaller, ~1e-15*N + 1e-13 (FFT-derivative noise floor N*eps, common to both; the reference's
+    direct 1/tan carries eps*N/(2 pi) on wrap-around pairs); 1e-9 for the finite-depth helium operator (cond(M) ~ N/2pi:
+    cuSOLVER LU on the reference's side, matrix-free GMRES to 1e-13 on ours).
+  * 100 RK4 steps: 1e-9 in surface position and potential (the north_star bar); energy and volume drift no worse than the
+    reference's own over the same steps.
+  * energies (kinetic, potential, surface, volume flux) of one RHS: 1e-10 absolute-or-relative.
+Measured values: profiles/ (reference_parity report written by tests/gpu_reference_report.py)."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_cases  # noqa: E402
+
+RHS_TOL = {"water": 1e-10, "helium_inf": 1e-10, "helium": 1e-9}
+RK4_TOL = 1e-9
+ENERGY_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from superfluid_dynamics_b200 import api, build
+    build.build(verbose=False)
+    return api
+
+
+@pytest.fixture(scope="module")
+def reference(api):
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref/libcusuperhelium_ref.so absent (built by __graft_entry__.build() where /root/reference exists)")
+    return ref_cases.reference_results()
+
+
+def _ref(reference, case):
+    r = reference[case["name"]]
+    if "error" in r:
+        pytest.skip("the reference did not deliver this case: " + r["error"])
+    return r
+
+
+@pytest.mark.parametrize("case", [c for c in ref_cases.CASES if c["op"] == "rhs"], ids=lambda c: c["name"])
+def test_rhs_matches_the_reference_cuda_path(api, reference, case):
+    """AutonomousProblem::run (L/BaseBoundaryIntegrator.cuh:138-306) on the same state, same GPU."""
+    m = ref_cases.measure(api, case, _ref(reference, case), torch)
+    tol = RHS_TOL[case["physics"]]
+    assert m["converged"]
+    for k in ("velocity", "dphi_dt", "a", "zp", "zpp", "phi_prime"):
+        assert m[k] <= tol, (k, m)
+    assert m["vel_upper"] <= 3 * tol, m
+    for k in ("energy_kinetic", "energy_potential", "energy_surface", "energy_volume_flux"):
+        assert m[k] <= ENERGY_TOL, (k, m)
+
+
+@pytest.mark.parametrize("case", [c for c in ref_cases.CASES if c["op"] == "rk4"], ids=lambda c: c["name"])
+def test_rk4_steps_match_the_reference_stepper(api, reference, case):
+    """AutonomousRungeKuttaStepper<std_complex, 2N>::runStep (L/AutonomousRungeKuttaStepper.cuh:124-307) driven as
+    T/ODESolverTests.cuh:95-110 does; north_star bar 1e-9 after 100 steps, drift no worse than the reference's."""
+    m = ref_cases.measure(api, case, _ref(reference, case), torch)
+    assert m["converged"]
+    assert m["position"] <= RK4_TOL, m
+    assert m["potential"] <= RK4_TOL, m
+    if "energy_drift_ours" in m:
+        assert m["energy_drift_ours"] <= m["energy_drift_reference"] + 1e-12 * max(1.0, m["energy_scale"]), m
+        assert m["volume_drift_ours"] <= m["volume_drift_reference"] + 1e-12, m
