@@ -15,10 +15,16 @@ Parity pinning (see tests/test_oracle.py and tests/golden/):
   * water path: pinned against P/WaterIntegralCalculator.py run in the build
     container (golden vectors committed under tests/golden/), and against the
     closed forms / host loops of T/MatrixMTests.cuh.
-  * helium finite-depth path (createFiniteDepthMKernel,
-    createHeliumVelocityMatrices, compute_rhs_helium_phi_expression*): the
-    reference holds no CPU statement, no test and no golden vector for these
-    kernels -> "parity unpinned"; restated from the CUDA source only.
+  * helium paths (createFiniteDepthMKernel, createHeliumVelocityMatrices,
+    compute_rhs_helium_phi_expression*; infinite depth, surface tension,
+    expansion terms): the reference holds no CPU statement, no test and no
+    golden vector of its own for these kernels.  Pinned instead against
+    OUTPUTS OF THE REFERENCE ITSELF: its CUDA classes compiled unmodified
+    (oracle/build_ref.py) and run on a B200, vectors committed as
+    tests/golden/ref_cuda_golden.npz with the generating script
+    (tests/golden/make_ref_cuda_golden.py); the same file re-pins the water
+    path at the whole-RHS and 100-RK4-step level
+    (tests/test_oracle.py::test_oracle_matches_reference_cuda_golden).
 """
 from __future__ import annotations
 

@@ -821,7 +821,10 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
                                                         const double* __restrict__ bnorm_part, int ncell, double tol2,
                                                         int max_iters) {
     const int lane = threadIdx.x;
-    if (decide && *reinterpret_cast<volatile int*>(&ctrl->done)) return;   // the sweep before skipped itself: nothing to wait for
+    // decide == 1: the sweep before was launched with skip_if_done and has skipped itself (no signal was sent): nothing to wait
+    // for.  decide == 2: that sweep always runs and signals (rb_bench_sweep), so its epoch must always be consumed -- returning
+    // here would leave the peers' flags ahead of wait_epoch and let every later wait pass on stale flags.
+    if (decide == 1 && *reinterpret_cast<volatile int*>(&ctrl->done)) return;
     const unsigned long long expected = *c.wait_epoch + 1ull;
     bool timed_out = false;
     if (lane < c.nranks) {

@@ -682,7 +682,8 @@ static void launch_mv(rb_solver* s, const SweepArgs& base, int i, int skip) {
     a.skip_if_done = skip;
     sweep(s, a, kSweepMV);
     if (s->comm.nranks > 1)
-        launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, a.final_buf_on_done, s->bnorm_part, s->ncell, a.tol2, a.max_iters, s->stream);
+        launch_comm_wait(s->comm, s->ctrl, skip ? 1 : 2, a.out_buf, a.final_buf_on_done, s->bnorm_part, s->ncell, a.tol2, a.max_iters,
+                         s->stream);
 }
 
 static void read_ctrl(rb_solver* s) {

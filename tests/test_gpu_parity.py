@@ -71,7 +71,8 @@ def test_M_and_velocity_matrices(api, N, t):
 
 
 def test_finite_depth_kernels(api):
-    """createFiniteDepthMKernel / createHeliumVelocityMatrices: no reference test exists (parity unpinned); vs the oracle."""
+    """createFiniteDepthMKernel / createHeliumVelocityMatrices: no reference test exists; vs the oracle here, and vs the reference's
+    own CUDA path (whole RHS, finite depth) in tests/test_gpu_reference.py."""
     N, depth = 96, 0.6
     Z, _ = ro.trochoid(N, 0.2)
     Zp, Zpp, _ = ro.trochoid_derivatives(N, 0.2)
