@@ -91,6 +91,36 @@ public:
     int physics() const override { return RB_HELIUM_INF; }
 };
 
+// ---- optomechanically driven film (L/OptomechanicalVariables.h:3-28, L/HeliumDrivenAutonomousProblem.cuh:10-26) ------------------
+struct OptomechanicalVariables {
+    double detuning = 0.0;
+    double gamma = 1.0;
+    double G = 1.0;
+    double Tau = 1.0;
+    double max_intensity = 0.0;
+    double initial_time = 0.0;
+    double location_x0_mode = 0.0;
+    double sigma_optical_mode = 1.0;
+    double Beta = 0.0;
+    double DampingStrength = 0.01;
+};
+inline rb_opto rb_compat_opto(const OptomechanicalVariables& v, const ProblemProperties& p) {
+    rb_opto o;
+    o.detuning = v.detuning; o.gamma = v.gamma; o.G = v.G; o.Tau = v.Tau; o.max_intensity = v.max_intensity;
+    o.initial_time = v.initial_time; o.location_x0_mode = v.location_x0_mode; o.sigma_optical_mode = v.sigma_optical_mode;
+    o.Beta = v.Beta; o.DampingStrength = v.DampingStrength;
+    o.drive_strength = rb_opto_drive_strength(&o, p.base_energy, p.base_time, p.rho);   // L/LightIntensity.cuh:30-33
+    return o;
+}
+template <int N, size_t batchSize>
+class HeliumDrivenAutonomousProblem : public HeliumBoundaryProblem<N, batchSize> {
+public:
+    ProblemProperties& properties;
+    OptomechanicalVariables& variables;
+    HeliumDrivenAutonomousProblem(ProblemProperties& p, OptomechanicalVariables& v)
+        : HeliumBoundaryProblem<N, batchSize>(p), properties(p), variables(v) {}
+};
+
 // energy handles with the reference's getEnergy() (L/Energies.cuh:229-235)
 class RbEnergyView {
     rb_solver* s_;
@@ -183,6 +213,35 @@ public:
 };
 
 // ---- trajectory logger + stepper ------------------------------------------------------------------------------------------
+// DelayedIntensityIntegrator<N,B> (L/DelayedIntensityIntegrator.cuh:9-39) and AugmentedBoundaryIntegrator<N,B>
+// (L/AugmentedBoundaryIntegrator.cuh:10-40): y = [Z | Phi | D] -> [w | dPhi/dt | dD/dt] through rb_augmented_rhs
+template <int N, size_t batchSize>
+class DelayedIntensityIntegrator {
+public:
+    OptomechanicalVariables& variables;
+    explicit DelayedIntensityIntegrator(OptomechanicalVariables& v) : variables(v) {}
+};
+template <int N, size_t batchSize>
+class AugmentedBoundaryIntegrator : public AutonomousProblem<std_complex, 3 * N * (int)batchSize> {
+    std::unique_ptr<BaseBoundaryIntegralCalculator<N, batchSize>> integrator_;
+    std::unique_ptr<DelayedIntensityIntegrator<N, batchSize>> delayed_;
+    ProblemProperties props_;
+public:
+    // the properties are those the calculator was built with (the reference's driven problem keeps a reference to them)
+    AugmentedBoundaryIntegrator(std::unique_ptr<BaseBoundaryIntegralCalculator<N, batchSize>> integrator,
+                                std::unique_ptr<DelayedIntensityIntegrator<N, batchSize>> delayedIntegrator,
+                                const ProblemProperties& properties = ProblemProperties())
+        : integrator_(std::move(integrator)), delayed_(std::move(delayedIntegrator)), props_(properties) {}
+    rb_opto opto() const { return rb_compat_opto(delayed_->variables, props_); }
+    void run(std_complex* initialState, std_complex* rhs) override {
+        rb_opto o = opto();
+        rb_compat_check(rb_augmented_rhs(integrator_->handle(), &o, reinterpret_cast<const rb_complex*>(initialState),
+                                         reinterpret_cast<rb_complex*>(rhs)), "rb_augmented_rhs");
+    }
+    void setStream(cudaStream_t stream) override { integrator_->setStream(stream); }
+    rb_solver* handle() { return integrator_->handle(); }
+};
+
 template <typename T, int N>
 class TrajectoryLogger {
 public:
@@ -205,8 +264,16 @@ public:
 template <typename T, int N>
 class AutonomousRungeKuttaStepper {
     rb_stepper* st_ = nullptr;
+    rb_aug_stepper* aug_ = nullptr;   // set instead of st_ when the problem is an AugmentedBoundaryIntegrator (3 N B state)
     std::shared_ptr<TrajectoryLogger<T, N>> logger_;
 public:
+    template <int NP, size_t B>
+    AutonomousRungeKuttaStepper(AugmentedBoundaryIntegrator<NP, B>& problem, double tstep = 1e-2) {
+        static_assert(3 * NP * (int)B == N, "state size must be 3 * N * batchSize");
+        rb_opto o = problem.opto();
+        aug_ = rb_aug_rk4_create(problem.handle(), &o, tstep);
+        if (!aug_) throw std::runtime_error(std::string("rb_aug_rk4_create: ") + rb_last_error());
+    }
     // the problem must be a BaseBoundaryIntegralCalculator<N/2/B, B>; its solver handle is what the stepper binds to
     template <int NP, size_t B>
     AutonomousRungeKuttaStepper(BaseBoundaryIntegralCalculator<NP, B>& problem, double tstep = 1e-2,
@@ -220,20 +287,37 @@ public:
             rb_compat_check(rb_rk4_set_logging(st_, logger_->every, logger_->capacity), "rb_rk4_set_logging");
         }
     }
-    ~AutonomousRungeKuttaStepper() { rb_rk4_destroy(st_); }
-    void setTimeStep(double tstep) { rb_compat_check(rb_rk4_set_time_step(st_, tstep), "rb_rk4_set_time_step"); }
+    ~AutonomousRungeKuttaStepper() {
+        if (st_) rb_rk4_destroy(st_);
+        if (aug_) rb_aug_rk4_destroy(aug_);
+    }
+    void setTimeStep(double tstep) {
+        if (aug_) rb_compat_check(rb_aug_rk4_set_time_step(aug_, tstep), "rb_aug_rk4_set_time_step");
+        else rb_compat_check(rb_rk4_set_time_step(st_, tstep), "rb_rk4_set_time_step");
+    }
     void setOptions(const RK4Options& o) { setTimeStep(o.initial_timestep); }
     void initialize(T* devY0, bool onDevice = false) {
+        if (aug_) {
+            rb_compat_check(rb_aug_rk4_initialize(aug_, reinterpret_cast<rb_complex*>(devY0), onDevice), "rb_aug_rk4_initialize");
+            return;
+        }
         rb_compat_check(rb_rk4_initialize(st_, reinterpret_cast<rb_complex*>(devY0), onDevice), "rb_rk4_initialize");
         if (logger_) rb_compat_check(rb_rk4_set_logging(st_, logger_->every, logger_->capacity), "rb_rk4_set_logging");
     }
-    void runStep(int = 0) { rb_compat_check(rb_rk4_step(st_), "rb_rk4_step"); }
+    void runStep(int = 0) {
+        if (aug_) rb_compat_check(rb_aug_rk4_step(aug_), "rb_aug_rk4_step");
+        else rb_compat_check(rb_rk4_step(st_), "rb_rk4_step");
+    }
     OdeSolverResult runEvolution(double startTime, double endTime) {
         size_t n = 0;
-        rb_compat_check(rb_rk4_evolve(st_, startTime, endTime, &n), "rb_rk4_evolve");
+        if (aug_) rb_compat_check(rb_aug_rk4_evolve(aug_, startTime, endTime, &n), "rb_aug_rk4_evolve");
+        else rb_compat_check(rb_rk4_evolve(st_, startTime, endTime, &n), "rb_rk4_evolve");
         return OdeSolverResult::ReachedEndTime;
     }
-    void getState(T* host) { rb_compat_check(rb_rk4_get_state(st_, reinterpret_cast<rb_complex*>(host)), "rb_rk4_get_state"); }
+    void getState(T* host) {
+        if (aug_) rb_compat_check(rb_aug_rk4_get_state(aug_, reinterpret_cast<rb_complex*>(host)), "rb_aug_rk4_get_state");
+        else rb_compat_check(rb_rk4_get_state(st_, reinterpret_cast<rb_complex*>(host)), "rb_rk4_get_state");
+    }
 };
 
 // ---- adaptive RKF45 (L/RK45.cuh): RK45_Options and RK45_std_complex<N> over any AutonomousProblem<std_complex, N> ---------------

@@ -40,6 +40,7 @@ typedef struct rb_complex { double re, im; } rb_complex;      /* L/ExportTypes.c
 typedef struct rb_solver rb_solver;                           /* opaque: one RHS assembler + work buffers */
 typedef struct rb_stepper rb_stepper;                         /* opaque: RK4 stepper bound to a solver */
 typedef struct rb_rk45 rb_rk45;                               /* opaque: adaptive RKF45 stepper (L/RK45.cuh) */
+typedef struct rb_aug_stepper rb_aug_stepper;                 /* opaque: RK4 stepper of the optomechanically driven (augmented) system */
 
 /* physics plugin selector == which BoundaryProblem<N,B> subclass the reference would instantiate */
 enum rb_physics {
@@ -196,6 +197,36 @@ RB_API double rb_rk45_current_time(rb_rk45* r);                                 
 RB_API double rb_rk45_current_timestep(rb_rk45* r);
 RB_API int rb_rk45_stats(rb_rk45* r, double out_host[4]);   /* accepted steps, rejected attempts, RHS evaluations, last scaled error */
 
+/* ---- optomechanically driven helium film: the autonomous augmented system y = [Z | Phi | D], D = delayed light intensity
+ *      (what CuSuperHelium.App runs, A/kernel.cu:60-96).  Replaces
+ *      HeliumDrivenAutonomousProblem<N,B> (L/HeliumDrivenAutonomousProblem.cuh:10-26, kernel L/createM.cuh:138-149),
+ *      DelayedIntensityIntegrator<N,B> (L/DelayedIntensityIntegrator.cuh:9-39, kernels L/createM.cuh:151-169),
+ *      AugmentedBoundaryIntegrator<N,B> (L/AugmentedBoundaryIntegrator.cuh:10-40) and LightIntensity (L/LightIntensity.cuh:11-35).
+ *      state / rhs: 3 N B complex, [Z | Phi | D] -> [w | dPhi/dt | dD/dt]. ---- */
+typedef struct rb_opto {          /* OptomechanicalVariables, L/OptomechanicalVariables.h:3-28 (nondimensional values) */
+    double detuning, gamma, G, Tau, max_intensity, initial_time, location_x0_mode, sigma_optical_mode, Beta, DampingStrength;
+    /* LightIntensity::get_current_intensity_drive_strength(variables, properties), L/LightIntensity.cuh:30-33:
+       hbar / (base_energy base_time rho) G / sigma^2 -- a property of (variables, properties); see rb_opto_drive_strength */
+    double drive_strength;
+} rb_opto;
+RB_API void rb_default_opto(rb_opto* v);                                          /* the struct's default member initialisers */
+RB_API double rb_opto_drive_strength(const rb_opto* v, double base_energy, double base_time, double rho);
+RB_API int rb_light_intensity(const rb_complex* Z_dev, double* intensity_dev, const rb_opto* v, size_t n, void* stream);
+/* AugmentedBoundaryIntegrator::run :25-29 = BaseBoundaryIntegralCalculator::run with the driven dPhi/dt, then the delayed-intensity
+   terms.  The reference derives the driven problem from HeliumBoundaryProblem; any physics of the solver is accepted here. */
+RB_API int rb_augmented_rhs(rb_solver* s, const rb_opto* v, const rb_complex* state_dev, rb_complex* rhs_dev);
+/* AutonomousRungeKuttaStepper<std_complex, 3N>(AugmentedBoundaryIntegrator&, dt): classical RK4 over the 3 N B state */
+RB_API rb_aug_stepper* rb_aug_rk4_create(rb_solver* s, const rb_opto* v, double tstep);
+RB_API int rb_aug_rk4_destroy(rb_aug_stepper* st);
+RB_API int rb_aug_rk4_set_time_step(rb_aug_stepper* st, double tstep);
+RB_API int rb_aug_rk4_initialize(rb_aug_stepper* st, rb_complex* y0, int on_device);  /* on_device aliases the caller's 3 N B buffer */
+RB_API int rb_aug_rk4_step(rb_aug_stepper* st);
+RB_API int rb_aug_rk4_run_steps(rb_aug_stepper* st, size_t steps);
+RB_API int rb_aug_rk4_evolve(rb_aug_stepper* st, double t0, double t1, size_t* steps_out);   /* steps = size_t((t1-t0)/dt) */
+RB_API rb_complex* rb_aug_rk4_dev_state(rb_aug_stepper* st);
+RB_API int rb_aug_rk4_get_state(rb_aug_stepper* st, rb_complex* y_host);
+RB_API double rb_aug_rk4_current_time(rb_aug_stepper* st);
+
 /* ---- multi-GPU (new; the reference is single-GPU, L/utilities.cuh:20): contiguous blocks of 256-row cells of every O(N^2)
  *      sweep are owned by one rank each; all ranks keep the full state and exchange result rows by peer stores over NVLink into
  *      a per-rank arena mapped with CUDA IPC.  One process per GPU of one node; ship the handles with any out-of-band channel
@@ -251,6 +282,27 @@ RB_API int integrateSimulationRK4_freeMemory(double* statesOut, double* timesOut
 /* nondimensional variant of the same call (no SI conversion, physics selectable): the plain RK4 path used by bench.py's e2e leg */
 RB_API int rb_integrate_rk4_host(const double* initialState_host, double* finalState_host, size_t N, size_t batch,
                                  const rb_props* props, double dt, size_t steps);
+
+typedef struct COptomechanicalVariables {   /* L/ExportTypes.cuh:41-57 (SI / laboratory units) */
+    double detuning, gamma, G, tau, max_intensity, initial_time, location_x0_mode, sigma_optical_mode, beta, damping_strength;
+} COptomechanicalVariables;
+/* L/Export.cuh:78, L/Export.cu:1108-1209: one RHS of the augmented system.  state = [x | y | phi | D] (4N doubles),
+ * rhs = [vx | vy | dphi/dt | dD/dt]; SI properties and variables are nondimensionalised inside (adimensionalizeProperties,
+ * adimensionalizeOptomechanicalVariables L/Export.cu:1222-1275).  Any N >= 2 (the reference: 32..8192 by switch table). */
+RB_API int calculateRhsAugmentedOptomechanical(double* state, double* rhs, SimProperties* simProperties,
+                                               COptomechanicalVariables* optomechanicalVariables, size_t N);
+/* L/Export.cuh:75-76, L/Export.cu:980-1106: RK4 evolution of the augmented system.  initialState = [x | y | phi | D];
+ * *statesOut = statesCount x 4N doubles [x | y | phi | D] (the reference writes phi a second time into the D block,
+ * L/Export.cu:1046 -- here the block holds D), *timesOut = timesCount doubles; with returnTrajectory = false only the final
+ * state is returned.  Release with the matching _freeMemory. */
+RB_API int integrateAugmentedOptomechanicalSimulationRK4(double* initialState, double** statesOut, size_t* statesCount,
+                                                         double** timesOut, size_t* timesCount, SimProperties* simProperties,
+                                                         RK4SolverOptions* rkOptions,
+                                                         COptomechanicalVariables* optomechanicalVariables, size_t N);
+RB_API int integrateAugmentedOptomechanicalSimulationRK4_freeMemory(double* statesOut, double* timesOut);
+/* nondimensional variant (no SI conversion): [Z | Phi | D] as 4N doubles in, final state out */
+RB_API int rb_integrate_aug_rk4_host(const double* initialState_host, double* finalState_host, size_t N, const rb_props* props,
+                                     const rb_opto* v, double dt, size_t steps);
 
 #ifdef __cplusplus
 }

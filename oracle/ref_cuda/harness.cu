@@ -25,6 +25,8 @@
 #include "HeliumBoundaryProblem.cuh"
 #include "VectorUtilities.cuh"   // appendToVector, used (not included) by L/TrajectoryLogger.cuh:71
 #include "AutonomousRungeKuttaStepper.cuh"
+#include "HeliumDrivenAutonomousProblem.cuh"      // the optomechanically driven film (what A/kernel.cu:60-96 runs)
+#include "AugmentedBoundaryIntegrator.cuh"
 
 #include <chrono>
 #include <cstring>
@@ -33,6 +35,9 @@ extern "C" {
 struct ref_props {
 	double rho, kappa, depth, U, L;
 	int use_expansions, expansion_order, infinite_depth;
+};
+struct ref_opto {   // OptomechanicalVariables, L/OptomechanicalVariables.h
+	double detuning, gamma, G, Tau, max_intensity, initial_time, location_x0_mode, sigma_optical_mode, Beta, DampingStrength;
 };
 }
 
@@ -47,6 +52,15 @@ ProblemProperties toProps(const ref_props* p)
 	q.use_expansions = p->use_expansions != 0; q.expansion_order = p->expansion_order; q.infinite_depth = p->infinite_depth != 0;
 	q.y_min = -1.0; q.y_max = 1.0;
 	return q;
+}
+
+OptomechanicalVariables toOpto(const ref_opto* o)
+{
+	OptomechanicalVariables v;
+	v.detuning = o->detuning; v.gamma = o->gamma; v.G = o->G; v.Tau = o->Tau; v.max_intensity = o->max_intensity;
+	v.initial_time = o->initial_time; v.location_x0_mode = o->location_x0_mode; v.sigma_optical_mode = o->sigma_optical_mode;
+	v.Beta = o->Beta; v.DampingStrength = o->DampingStrength;
+	return v;
 }
 
 int lastError(const char* where)
@@ -128,6 +142,46 @@ int rk4Impl(const ref_props* rp, double* state, double dt, int warmup, int steps
 	return rc;
 }
 
+// the augmented autonomous system [Z | Phi | D] exactly as L/Export.cu:1136-1150 and A/kernel.cu:85-94 assemble it; steps == 0: one RHS
+// into `out` (3N complex); steps > 0: warmup + steps RK4 steps of AutonomousRungeKuttaStepper<std_complex, 3N>, final state into `out`
+template<int N>
+int augImpl(const ref_props* rp, const ref_opto* ro, const double* state, double* out, double dt, int warmup, int steps, double* seconds)
+{
+	ProblemProperties props = toProps(rp);
+	OptomechanicalVariables vars = toOpto(ro);
+	HeliumDrivenAutonomousProblem<N, 1> problem(props, vars);
+	std::unique_ptr<BaseBoundaryIntegralCalculator<N, 1>> calc = std::make_unique<BaseBoundaryIntegralCalculator<N, 1>>(props, problem);
+	AugmentedBoundaryIntegrator<N, 1> integrator(std::move(calc), std::make_unique<DelayedIntensityIntegrator<N, 1>>(vars));
+	std_complex *dState = nullptr, *dRhs = nullptr;
+	if (cudaMalloc(&dState, 3 * N * sizeof(std_complex)) != cudaSuccess) return -3;
+	if (cudaMalloc(&dRhs, 3 * N * sizeof(std_complex)) != cudaSuccess) return -3;
+	cudaMemcpy(dState, state, 3 * N * sizeof(std_complex), cudaMemcpyHostToDevice);
+	cudaMemset(dRhs, 0, 3 * N * sizeof(std_complex));
+	int rc = 0;
+	if (steps <= 0) {
+		integrator.run(dState, dRhs);
+		rc = lastError("augmented run");
+		if (rc == 0) cudaMemcpy(out, dRhs, 3 * N * sizeof(std_complex), cudaMemcpyDeviceToHost);
+	} else {
+		AutonomousRungeKuttaStepper<std_complex, 3 * N> stepper(integrator, dt);
+		stepper.initialize(dState, true);
+		for (int i = 0; i < warmup; i++) stepper.runStep(i);
+		rc = lastError("augmented warm-up steps");
+		if (rc == 0) {
+			auto t0 = std::chrono::steady_clock::now();
+			for (int i = 0; i < steps; i++) stepper.runStep(warmup + i);
+			rc = lastError("augmented steps");
+			auto t1 = std::chrono::steady_clock::now();
+			if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+		}
+		if (rc == 0) cudaMemcpy(out, dState, 3 * N * sizeof(std_complex), cudaMemcpyDeviceToHost);
+	}
+	if (rc == 0) rc = lastError("augmented read-back");
+	cudaFree(dState);
+	cudaFree(dRhs);
+	return rc;
+}
+
 template<int N>
 int rhsKind(int kind, const ref_props* rp, const double* state, double* rhs, double* a, double* vu, double* zp, double* zpp, double* pp, double* en)
 {
@@ -198,6 +252,24 @@ __attribute__((visibility("default"))) int ref_rk4(int kind, int N, const ref_pr
 		}
 	} catch (const std::exception& e) {
 		fprintf(stderr, "ref_rk4: %s\n", e.what());
+		return -2;
+	}
+	return -1;
+}
+
+// augmented optomechanical system, N in {64, 256, 1024}; steps == 0: rhs of `state` into `out`, else the state after the steps
+#define REF_AUG_SIZES(X) X(64) X(256) X(1024)
+__attribute__((visibility("default"))) int ref_augmented(int N, const ref_props* props, const ref_opto* opto, const double* state,
+                                                         double* out, double dt, int warmup, int steps, double* seconds)
+{
+	try {
+		switch (N) {
+#define X(n) case n: return augImpl<n>(props, opto, state, out, dt, warmup, steps, seconds);
+			REF_AUG_SIZES(X)
+#undef X
+		}
+	} catch (const std::exception& e) {
+		fprintf(stderr, "ref_augmented: %s\n", e.what());
 		return -2;
 	}
 	return -1;

@@ -7,6 +7,9 @@ must not take the test runner or bench.py down with it.  Jobs are dicts:
     {"op": "rhs", "kind": "water"|"helium"|"helium_inf", "N": 256, "props": {"rho": 0.0, ...}, "state": complex128[2N]}
         -> rhs complex128[2N], a float64[N], vel_upper, zp, zpp complex128[N], phi_prime float64[N], energies float64[4]
            (kinetic, potential, surface, volume flux: the reference's EnergyContainer / VolumeFlux after that RHS)
+    {"op": "aug_rhs" | "aug_rk4", "N": .., "props": .., "opto": {OptomechanicalVariables fields}, "state": complex128[3N] [, dt, steps]}
+        -> the augmented optomechanical system [Z | Phi | D] (HeliumDrivenAutonomousProblem + AugmentedBoundaryIntegrator):
+           rhs complex128[3N], or the state after the steps and the seconds they took
     {"op": "rk4", ..., "dt": 1e-3, "steps": 100, "warmup": 0}
         -> state complex128[2N] after warmup+steps steps, seconds (host clock around the last `steps` steps, device
            synchronised on both sides), energies of the last RHS evaluated
@@ -35,6 +38,11 @@ class _Props(ctypes.Structure):
                 ("infinite_depth", ctypes.c_int)]
 
 
+class _Opto(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ("detuning", "gamma", "G", "Tau", "max_intensity", "initial_time", "location_x0_mode",
+                                               "sigma_optical_mode", "Beta", "DampingStrength")]
+
+
 def available():
     return os.path.exists(LIB)
 
@@ -57,6 +65,10 @@ def _load():
     lib.ref_rhs.restype = ctypes.c_int
     lib.ref_rk4.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Props), D, ctypes.c_double, ctypes.c_int, ctypes.c_int, D, D]
     lib.ref_rk4.restype = ctypes.c_int
+    if hasattr(lib, "ref_augmented"):
+        lib.ref_augmented.argtypes = [ctypes.c_int, ctypes.POINTER(_Props), ctypes.POINTER(_Opto), D, D, ctypes.c_double, ctypes.c_int,
+                                      ctypes.c_int, D]
+        lib.ref_augmented.restype = ctypes.c_int
     lib.ref_num_sizes.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     lib.ref_num_sizes.restype = ctypes.c_int
     return lib
@@ -75,6 +87,17 @@ def _run_one(lib, job):
     kind = KINDS[job["kind"]]
     p = _props(job.get("props"))
     state = np.ascontiguousarray(job["state"], dtype=np.complex128).copy()
+    if job["op"] in ("aug_rhs", "aug_rk4"):
+        assert state.size == 3 * N
+        o = _Opto(*[float(job["opto"][n]) for n, _ in _Opto._fields_])
+        out = np.zeros(3 * N, np.complex128)
+        sec = ctypes.c_double(0.0)
+        steps = int(job["steps"]) if job["op"] == "aug_rk4" else 0
+        rc = lib.ref_augmented(N, ctypes.byref(p), ctypes.byref(o), _dp(state.view(np.float64)), _dp(out.view(np.float64)),
+                               float(job.get("dt", 0.0)), int(job.get("warmup", 0)), steps, ctypes.byref(sec))
+        if rc != 0:
+            return {"error": f"ref_augmented returned {rc}"}
+        return dict(rhs=out) if steps == 0 else dict(state=out, seconds=sec.value)
     assert state.size == 2 * N
     en = np.zeros(4)
     if job["op"] == "rhs":

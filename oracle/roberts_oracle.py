@@ -534,3 +534,71 @@ def cot_rowsum(Z, x, rows) -> np.ndarray:
     C = cot(d)
     C[np.arange(len(rows)), rows] = 0.0
     return C @ np.asarray(x, np.complex128)
+
+
+# --------------------------------------------------------------------------
+# optomechanically driven film: the autonomous augmented system [Z | Phi | D]
+# (L/OptomechanicalVariables.h, L/LightIntensity.cuh, L/createM.cuh:138-169,
+#  L/HeliumDrivenAutonomousProblem.cuh, L/DelayedIntensityIntegrator.cuh,
+#  L/AugmentedBoundaryIntegrator.cuh)
+# --------------------------------------------------------------------------
+HBAR = 1.054571817e-34  # L/constants.cuh:10
+
+
+@dataclasses.dataclass
+class OptomechanicalVariables:
+    """L/OptomechanicalVariables.h:3-28."""
+    detuning: float = 0.0
+    gamma: float = 1.0
+    G: float = 1.0
+    Tau: float = 1.0
+    max_intensity: float = 0.0
+    initial_time: float = 0.0
+    location_x0_mode: float = 0.0
+    sigma_optical_mode: float = 1.0
+    Beta: float = 0.0
+    DampingStrength: float = 0.01
+
+
+def light_intensity(height, x, v: OptomechanicalVariables):
+    """LightIntensity::compute_intensity / compute_x_profile, L/LightIntensity.cuh:17-29."""
+    profile = np.exp(-(x - v.location_x0_mode) ** 2 / (2 * v.sigma_optical_mode ** 2))
+    delta_f = v.detuning - v.G * height
+    return 0.25 * v.gamma ** 2 * v.max_intensity / (delta_f ** 2 + (v.gamma / 2) ** 2) * profile
+
+
+def drive_strength(v: OptomechanicalVariables, props: ProblemProperties) -> float:
+    """LightIntensity::get_current_intensity_drive_strength, L/LightIntensity.cuh:30-33."""
+    return HBAR / (props.base_energy * props.base_time * props.rho) * v.G / v.sigma_optical_mode ** 2
+
+
+def adimensionalize_optomechanical(v: OptomechanicalVariables, props: ProblemProperties) -> OptomechanicalVariables:
+    """adimensionalizeOptomechanicalVariables, L/Export.cu:1250-1275 (props already nondimensionalised)."""
+    o = dataclasses.replace(v)
+    o.gamma *= props.base_time
+    o.detuning *= props.base_time
+    o.G *= props.base_time * props.base_length
+    o.Tau /= props.base_time
+    o.location_x0_mode /= props.base_length
+    o.sigma_optical_mode /= props.base_length
+    hbar_adim = HBAR / props.base_energy / props.base_time
+    o.Beta *= hbar_adim * o.G / o.Tau / (o.sigma_optical_mode ** 2 * props.rho)
+    return o
+
+
+def augmented_rhs(state: np.ndarray, N: int, props: ProblemProperties, v: OptomechanicalVariables, physics: str = "helium",
+                  deriv: str = "cuda") -> np.ndarray:
+    """AugmentedBoundaryIntegrator::run (L/AugmentedBoundaryIntegrator.cuh:25-29) on [Z | Phi | D] (3N complex):
+    the boundary-integral RHS with HeliumDrivenAutonomousProblem::CalculateRhsPhi (base dPhi/dt, then
+    add_optical_field_drive_terms_no_time_depence, L/createM.cuh:138-149), then DelayedIntensityIntegrator::run
+    (calculate_intensity_delayed_rhs :161-169, add_delayed_intensity_phi_rhs :151-159)."""
+    state = np.asarray(state, np.complex128)
+    out = np.zeros(3 * N, np.complex128)
+    out[:2 * N] = rhs(state[:2 * N], N, 1, props, physics, deriv)
+    Z, D, w = state[:N], state[2 * N:], out[:N]
+    inten = light_intensity(Z.imag, Z.real, v)
+    out[N:2 * N] += v.DampingStrength * w.imag
+    out[N:2 * N] += drive_strength(v, props) * inten
+    out[2 * N:] = v.Beta * inten - 1.0 / v.Tau * D
+    out[N:2 * N] += D
+    return out

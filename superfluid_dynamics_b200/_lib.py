@@ -35,6 +35,16 @@ class RK4SolverOptions(Structure):       # L/ExportTypes.cuh:35-40 ; P/integrati
     _fields_ = [("timeStep", c_double), ("t0", c_double), ("t1", c_double), ("returnTrajectory", c_bool)]
 
 
+class rb_opto(Structure):                # OptomechanicalVariables, L/OptomechanicalVariables.h:3-28 (+ the drive strength)
+    _fields_ = [(n, c_double) for n in ("detuning", "gamma", "G", "Tau", "max_intensity", "initial_time", "location_x0_mode",
+                                        "sigma_optical_mode", "Beta", "DampingStrength", "drive_strength")]
+
+
+class COptomechanicalVariables(Structure):   # L/ExportTypes.cuh:41-57
+    _fields_ = [(n, c_double) for n in ("detuning", "gamma", "G", "tau", "max_intensity", "initial_time", "location_x0_mode",
+                                        "sigma_optical_mode", "beta", "damping_strength")]
+
+
 RB_WATER, RB_HELIUM, RB_HELIUM_INF = 0, 1, 2
 RB_SOLVE_MATRIX_FREE, RB_SOLVE_DENSE_LU = 0, 1
 RB_GUESS_COLD, RB_GUESS_WARM = 0, 1
@@ -126,6 +136,26 @@ SIGNATURES = {
                                        POINTER(SimProperties), POINTER(RK4SolverOptions), c_size_t]),
     "integrateSimulationRK4_freeMemory": (c_int, [_D, _D]),
     "rb_integrate_rk4_host": (c_int, [_D, _D, c_size_t, c_size_t, POINTER(rb_props), c_double, c_size_t]),
+    "rb_default_opto": (None, [POINTER(rb_opto)]),
+    "rb_opto_drive_strength": (c_double, [POINTER(rb_opto), c_double, c_double, c_double]),
+    "rb_light_intensity": (c_int, [_P, _P, POINTER(rb_opto), c_size_t, _P]),
+    "rb_augmented_rhs": (c_int, [_P, POINTER(rb_opto), _P, _P]),
+    "rb_aug_rk4_create": (_P, [_P, POINTER(rb_opto), c_double]),
+    "rb_aug_rk4_destroy": (c_int, [_P]),
+    "rb_aug_rk4_set_time_step": (c_int, [_P, c_double]),
+    "rb_aug_rk4_initialize": (c_int, [_P, _P, c_int]),
+    "rb_aug_rk4_step": (c_int, [_P]),
+    "rb_aug_rk4_run_steps": (c_int, [_P, c_size_t]),
+    "rb_aug_rk4_evolve": (c_int, [_P, c_double, c_double, POINTER(c_size_t)]),
+    "rb_aug_rk4_dev_state": (_P, [_P]),
+    "rb_aug_rk4_get_state": (c_int, [_P, _P]),
+    "rb_aug_rk4_current_time": (c_double, [_P]),
+    "calculateRhsAugmentedOptomechanical": (c_int, [_D, _D, POINTER(SimProperties), POINTER(COptomechanicalVariables), c_size_t]),
+    "integrateAugmentedOptomechanicalSimulationRK4": (c_int, [_D, POINTER(_D), POINTER(c_size_t), POINTER(_D), POINTER(c_size_t),
+                                                              POINTER(SimProperties), POINTER(RK4SolverOptions),
+                                                              POINTER(COptomechanicalVariables), c_size_t]),
+    "integrateAugmentedOptomechanicalSimulationRK4_freeMemory": (c_int, [_D, _D]),
+    "rb_integrate_aug_rk4_host": (c_int, [_D, _D, c_size_t, POINTER(rb_props), POINTER(rb_opto), c_double, c_size_t]),
 }
 
 _lib = None

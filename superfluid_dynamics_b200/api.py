@@ -308,6 +308,130 @@ class AutonomousRungeKuttaStepper:
         return times, states
 
 
+@dataclasses.dataclass
+class OptomechanicalVariables:
+    """L/OptomechanicalVariables.h:3-28 (nondimensional).  `drive_strength` is
+    LightIntensity::get_current_intensity_drive_strength(variables, properties) (L/LightIntensity.cuh:30-33): pass it, or the base
+    units through `set_drive_strength` (the reference's default base units are 1)."""
+    detuning: float = 0.0
+    gamma: float = 1.0
+    G: float = 1.0
+    Tau: float = 1.0
+    max_intensity: float = 0.0
+    initial_time: float = 0.0
+    location_x0_mode: float = 0.0
+    sigma_optical_mode: float = 1.0
+    Beta: float = 0.0
+    DampingStrength: float = 0.01
+    drive_strength: float = None
+
+    def set_drive_strength(self, rho, base_energy=1.0, base_time=1.0):
+        self.drive_strength = _lib.load().rb_opto_drive_strength(ctypes.byref(self._c(0.0)), float(base_energy), float(base_time),
+                                                                 float(rho))
+        return self
+
+    def _c(self, strength=None):
+        v = _lib.rb_opto()
+        for f in ("detuning", "gamma", "G", "Tau", "max_intensity", "initial_time", "location_x0_mode", "sigma_optical_mode", "Beta",
+                  "DampingStrength"):
+            setattr(v, f, float(getattr(self, f)))
+        v.drive_strength = float(self.drive_strength if strength is None else strength)
+        return v
+
+
+class HeliumDrivenAutonomousProblem(HeliumBoundaryProblem):
+    """HeliumDrivenAutonomousProblem<N,B>(ProblemProperties&, OptomechanicalVariables&), L/HeliumDrivenAutonomousProblem.cuh:10-26."""
+
+    def __init__(self, properties: ProblemProperties, variables: OptomechanicalVariables):
+        super().__init__(properties)
+        self.variables = variables
+
+
+class DelayedIntensityIntegrator:
+    """DelayedIntensityIntegrator<N,B>(OptomechanicalVariables&), L/DelayedIntensityIntegrator.cuh:9-39."""
+
+    def __init__(self, variables: OptomechanicalVariables):
+        self.variables = variables
+
+
+class AugmentedBoundaryIntegrator:
+    """AugmentedBoundaryIntegrator<N,B>(integrator, delayedIntegrator), L/AugmentedBoundaryIntegrator.cuh:10-40: the autonomous
+    system y = [Z | Phi | D] (3 N B complex).  The boundary-integral calculator is the one built on a
+    HeliumDrivenAutonomousProblem; its variables and the delayed integrator's must be the same object's values."""
+
+    def __init__(self, integrator: BaseBoundaryIntegralCalculator, delayedIntegrator: DelayedIntensityIntegrator = None,
+                 variables: OptomechanicalVariables = None):
+        self.integrator = integrator
+        self.lib = integrator.lib
+        self.variables = variables or (delayedIntegrator.variables if delayedIntegrator is not None else None)
+        if self.variables is None:
+            raise ValueError("AugmentedBoundaryIntegrator needs the OptomechanicalVariables")
+        if self.variables.drive_strength is None:
+            self.variables.set_drive_strength(integrator.properties.rho)
+        self.N, self.batchSize, self.device = integrator.N, integrator.batchSize, integrator.device
+
+    def run(self, initialState: torch.Tensor, rhs: torch.Tensor):
+        v = self.variables._c()
+        check(self.lib.rb_augmented_rhs(self.integrator.handle, ctypes.byref(v), _ptr(initialState), _ptr(rhs)), "rb_augmented_rhs")
+
+    def setStream(self, stream):
+        self.integrator.setStream(stream)
+
+    def lightIntensity(self, Z: torch.Tensor):
+        out = torch.empty(Z.numel(), dtype=torch.float64, device=Z.device)
+        v = self.variables._c()
+        check(self.lib.rb_light_intensity(_ptr(Z), _ptr(out), ctypes.byref(v), Z.numel(), _stream_ptr(Z.device)), "rb_light_intensity")
+        return out
+
+
+class AugmentedRungeKuttaStepper:
+    """AutonomousRungeKuttaStepper<std_complex, 3N>(AugmentedBoundaryIntegrator&, tstep) (A/kernel.cu:85-96)."""
+
+    def __init__(self, problem: AugmentedBoundaryIntegrator, tstep: float = 1e-2):
+        self.problem = problem
+        self.lib = problem.lib
+        v = problem.variables._c()
+        self.handle = self.lib.rb_aug_rk4_create(problem.integrator.handle, ctypes.byref(v), float(tstep))
+        if not self.handle:
+            raise _lib.RobertsError("rb_aug_rk4_create: " + self.lib.rb_last_error().decode())
+        self._keep = None
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.rb_aug_rk4_destroy(h)
+
+    def setTimeStep(self, tstep):
+        check(self.lib.rb_aug_rk4_set_time_step(self.handle, float(tstep)), "rb_aug_rk4_set_time_step")
+
+    def initialize(self, devY0, onDevice=False):
+        if onDevice:
+            self._keep = devY0
+            check(self.lib.rb_aug_rk4_initialize(self.handle, _ptr(devY0), 1), "rb_aug_rk4_initialize")
+        else:
+            host = np.ascontiguousarray(np.asarray(devY0, dtype=np.complex128))
+            check(self.lib.rb_aug_rk4_initialize(self.handle, host.ctypes.data_as(ctypes.c_void_p), 0), "rb_aug_rk4_initialize")
+
+    def runStep(self, _step=0):
+        check(self.lib.rb_aug_rk4_step(self.handle), "rb_aug_rk4_step")
+
+    def runSteps(self, steps):
+        check(self.lib.rb_aug_rk4_run_steps(self.handle, int(steps)), "rb_aug_rk4_run_steps")
+
+    def runEvolution(self, startTime, endTime):
+        n = ctypes.c_size_t()
+        check(self.lib.rb_aug_rk4_evolve(self.handle, float(startTime), float(endTime), ctypes.byref(n)), "rb_aug_rk4_evolve")
+        return n.value
+
+    def getState(self):
+        host = np.empty(3 * self.problem.N * self.problem.batchSize, np.complex128)
+        check(self.lib.rb_aug_rk4_get_state(self.handle, host.ctypes.data_as(ctypes.c_void_p)), "rb_aug_rk4_get_state")
+        return host
+
+    def currentTime(self):
+        return self.lib.rb_aug_rk4_current_time(self.handle)
+
+
 # ---- the kernels the reference's tests launch by name ------------------------------------------
 def createMKernel(A, Z, Zp, Zpp, rho, n, batchSize=1):
     check(_lib.load().rb_create_M(_ptr(A), _ptr(Z), _ptr(Zp), _ptr(Zpp), float(rho), int(n), int(batchSize), _stream_ptr(A.device)),
@@ -520,3 +644,29 @@ def integrate_rk4_host(initialState, N, batch, properties: ProblemProperties, ph
     check(lib.rb_integrate_rk4_host(_dp(st), _dp(out), int(N), int(batch), ctypes.byref(p), float(dt), int(steps)),
           "rb_integrate_rk4_host")
     return out
+
+
+def calculateRhsAugmentedOptomechanical(state, simProperties: _lib.SimProperties, optomechanicalVariables: _lib.COptomechanicalVariables, N):
+    """L/Export.cuh:78: state = [x | y | phi | D] (4N doubles, SI properties / variables) -> [vx | vy | dphi/dt | dD/dt]."""
+    lib = _lib.load()
+    st = np.ascontiguousarray(state, np.float64)
+    out = np.empty_like(st)
+    check(lib.calculateRhsAugmentedOptomechanical(_dp(st), _dp(out), ctypes.byref(simProperties),
+                                                  ctypes.byref(optomechanicalVariables), int(N)), "calculateRhsAugmentedOptomechanical")
+    return out
+
+
+def integrateAugmentedOptomechanicalSimulationRK4(initialState, simProperties, rkOptions, optomechanicalVariables, N):
+    """L/Export.cuh:75: RK4 evolution of the augmented system; returns (states [count x 4N], times)."""
+    lib = _lib.load()
+    st = np.ascontiguousarray(initialState, np.float64)
+    so, to = ctypes.POINTER(ctypes.c_double)(), ctypes.POINTER(ctypes.c_double)()
+    sc, tc = ctypes.c_size_t(), ctypes.c_size_t()
+    check(lib.integrateAugmentedOptomechanicalSimulationRK4(_dp(st), ctypes.byref(so), ctypes.byref(sc), ctypes.byref(to),
+                                                            ctypes.byref(tc), ctypes.byref(simProperties), ctypes.byref(rkOptions),
+                                                            ctypes.byref(optomechanicalVariables), int(N)),
+          "integrateAugmentedOptomechanicalSimulationRK4")
+    states = np.ctypeslib.as_array(so, shape=(sc.value, 4 * N)).copy() if sc.value else np.zeros((0, 4 * N))
+    times = np.ctypeslib.as_array(to, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
+    lib.integrateAugmentedOptomechanicalSimulationRK4_freeMemory(so, to)
+    return states, times

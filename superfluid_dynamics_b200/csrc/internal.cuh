@@ -244,6 +244,11 @@ void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st);
 void launch_stage_update(double2* y_out, const double2* y0, const double2* k, double c, size_t n, cudaStream_t st);
 void launch_final_update(double2* y0, const double2* k1, const double2* k2, const double2* k3, const double2* k4, double h,
                          size_t n, cudaStream_t st);
+// drive_kernels.cu (rb_opto: include/roberts_b200.h, included before this header by the translation units that use these)
+#ifdef ROBERTS_B200_H
+void launch_light_intensity(const double2* Z, double* out, const rb_opto& v, size_t n, cudaStream_t st);
+void launch_augmented_terms(const double2* state, double2* rhs, const rb_opto& v, size_t BN, cudaStream_t st);
+#endif
 // rk45_kernels.cu
 void launch_rk45_stage(const double2* y, const double2* const k[5], double2* out, const double c[5], int nk, size_t n,
                        cudaStream_t st);

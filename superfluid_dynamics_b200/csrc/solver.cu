@@ -1930,7 +1930,7 @@ int rb_bench_sweep(rb_solver* s, const rb_complex* state_dev, int reps, float* m
 static const double kAlphaHamaker = 3.5e-24;   // L/constants.cuh:11
 
 struct Adim {
-    double base_length, base_acceleration, base_time, kappa, depth, rho;
+    double base_length, base_acceleration, base_time, base_energy, kappa, depth, rho;
 };
 
 // adimensionalizeProperties, L/Export.cu:1222-1246 (the stdout prints of the reference are dropped)
@@ -1939,6 +1939,7 @@ static Adim adimensionalize(double L, double rho, double kappa, double depth, do
     a.base_length = L / (2.0 * kPi);
     a.base_acceleration = 3 * kAlphaHamaker / std::pow(depth, 4);
     a.base_time = std::sqrt(a.base_length / a.base_acceleration);
+    a.base_energy = 3.0 * rhoHelium * kAlphaHamaker * std::pow(a.base_length, 4) / std::pow(depth, 4);   // L/Export.cu:1228
     double surfaceTensionFactor = rhoHelium * a.base_length * a.base_length * a.base_length / (a.base_time * a.base_time);
     a.kappa = kappa / surfaceTensionFactor;
     a.depth = depth / a.base_length;
@@ -2116,6 +2117,300 @@ int rb_integrate_rk4_host(const double* initialState_host, double* finalState_ho
     if (props) p = *props; else rb_default_props(&p);
     std::vector<double> states, times;
     integrate_host(initialState_host, N, batch, p, dt, steps, false, states, times, 0.0);
+    std::memcpy(finalState_host, states.data(), states.size() * sizeof(double));
+    RB_CATCH
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// optomechanically driven film: the autonomous augmented system y = [Z | Phi | D] (drive_kernels.cu) and its classical RK4 stepper
+// (AugmentedBoundaryIntegrator + AutonomousRungeKuttaStepper<std_complex, 3N>, A/kernel.cu:85-96, L/Export.cu:980-1209)
+// ------------------------------------------------------------------------------------------------
+static const double kHbar = 1.054571817e-34;   // L/constants.cuh:10
+
+struct rb_aug_stepper {
+    rb_solver* s = nullptr;
+    rb_opto v;
+    double dt = 1e-2;
+    double t = 0.0;
+    double2* y0 = nullptr;
+    bool owns_y0 = false;
+    double2* k[4] = {nullptr, nullptr, nullptr, nullptr};
+    double2* ytmp = nullptr;
+};
+
+static void aug_rhs(rb_solver* s, const rb_opto& v, const double2* state, double2* out) {
+    rhs(s, state, out);                                         // m_integrator->run, driven problem's base dPhi/dt
+    launch_augmented_terms(state, out, v, s->BN, s->stream);    // drive + damping, then m_delayedIntensityIntegrator->run
+}
+
+static void aug_stepper_free(rb_aug_stepper* st) {
+    if (!st) return;
+    if (st->owns_y0 && st->y0) cudaFree(st->y0);
+    for (auto& k : st->k)
+        if (k) cudaFree(k);
+    if (st->ytmp) cudaFree(st->ytmp);
+    delete st;
+}
+
+// Y1 = Y0 + h/2 k1; Y2 = Y0 + h/2 k2; Y3 = Y0 + h k3; Y0 += h/6 (k1 + 2 k2 + 2 k3 + k4), L/AutonomousRungeKuttaStepper.cuh:124-307
+static void aug_step(rb_aug_stepper* st) {
+    rb_solver* s = st->s;
+    const size_t n = 3 * s->BN;
+    const double h = st->dt;
+    aug_rhs(s, st->v, st->y0, st->k[0]);
+    launch_stage_update(st->ytmp, st->y0, st->k[0], 0.5 * h, n, s->stream);
+    aug_rhs(s, st->v, st->ytmp, st->k[1]);
+    launch_stage_update(st->ytmp, st->y0, st->k[1], 0.5 * h, n, s->stream);
+    aug_rhs(s, st->v, st->ytmp, st->k[2]);
+    launch_stage_update(st->ytmp, st->y0, st->k[2], h, n, s->stream);
+    aug_rhs(s, st->v, st->ytmp, st->k[3]);
+    launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n, s->stream);
+    st->t += h;
+}
+
+// adimensionalizeOptomechanicalVariables, L/Export.cu:1250-1275 (properties already nondimensional: rho = rho / rhoHelium)
+static rb_opto adimensionalize_opto(const COptomechanicalVariables& c, double base_length, double base_time, double base_energy,
+                                    double rho_adim) {
+    rb_opto v;
+    v.detuning = c.detuning * base_time;
+    v.gamma = c.gamma * base_time;
+    v.G = c.G * base_time * base_length;
+    v.Tau = c.tau / base_time;
+    v.max_intensity = c.max_intensity;
+    v.initial_time = c.initial_time;
+    v.location_x0_mode = c.location_x0_mode / base_length;
+    v.sigma_optical_mode = c.sigma_optical_mode / base_length;
+    const double hbar_adim = kHbar / base_energy / base_time;
+    v.Beta = c.beta * (hbar_adim * v.G / (v.Tau) / (v.sigma_optical_mode * v.sigma_optical_mode * rho_adim));
+    v.DampingStrength = c.damping_strength;
+    v.drive_strength = rb_opto_drive_strength(&v, base_energy, base_time, rho_adim);
+    return v;
+}
+
+static void aug_integrate_host(const double* initialState, size_t N, const rb_props& p, const rb_opto& v, double dt, size_t steps,
+                               bool trajectory, double t0, std::vector<double>& states, std::vector<double>& times) {
+    std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, 1, &p), solver_free);
+    std::unique_ptr<rb_aug_stepper, void (*)(rb_aug_stepper*)> st(rb_aug_rk4_create(s.get(), &v, dt), aug_stepper_free);
+    if (!st) throw std::runtime_error(g_last_error);
+    std::vector<double2> host(3 * N);
+    for (size_t i = 0; i < N; ++i) {
+        host[i] = make_double2(initialState[i], initialState[N + i]);
+        host[N + i] = make_double2(initialState[2 * N + i], 0.0);
+        host[2 * N + i] = make_double2(initialState[3 * N + i], 0.0);
+    }
+    if (rb_aug_rk4_initialize(st.get(), (rb_complex*)host.data(), 0) != 0) throw std::runtime_error(g_last_error);
+    st->t = t0;
+    auto unpack = [&](double* out) {
+        if (rb_aug_rk4_get_state(st.get(), (rb_complex*)host.data()) != 0) throw std::runtime_error(g_last_error);
+        for (size_t i = 0; i < N; ++i) {
+            out[i] = host[i].x;
+            out[N + i] = host[i].y;
+            out[2 * N + i] = host[N + i].x;
+            out[3 * N + i] = host[2 * N + i].x;
+        }
+    };
+    states.clear();
+    times.clear();
+    for (size_t i = 0; i < steps; ++i) {
+        aug_step(st.get());
+        if (trajectory) {   // TrajectoryLogger::logTrajectory after every step, L/AutonomousRungeKuttaStepper.cuh:426-428
+            states.resize(states.size() + 4 * N);
+            unpack(states.data() + states.size() - 4 * N);
+            times.push_back(st->t);
+        }
+    }
+    if (!trajectory) {
+        states.resize(4 * N);
+        unpack(states.data());
+    }
+}
+
+extern "C" {
+
+void rb_default_opto(rb_opto* v) {
+    std::memset(v, 0, sizeof(*v));
+    v->gamma = 1.0;
+    v->G = 1.0;
+    v->Tau = 1.0;
+    v->sigma_optical_mode = 1.0;
+    v->DampingStrength = 0.01;
+}
+
+double rb_opto_drive_strength(const rb_opto* v, double base_energy, double base_time, double rho) {
+    return kHbar / (base_energy * base_time * rho) * v->G / (v->sigma_optical_mode * v->sigma_optical_mode);
+}
+
+int rb_light_intensity(const rb_complex* Z_dev, double* intensity_dev, const rb_opto* v, size_t n, void* stream) {
+    RB_TRY
+    launch_light_intensity((const double2*)Z_dev, intensity_dev, *v, n, (cudaStream_t)stream);
+    RB_CATCH
+}
+
+int rb_augmented_rhs(rb_solver* s, const rb_opto* v, const rb_complex* state_dev, rb_complex* rhs_dev) {
+    RB_TRY
+    if (!s || !v) throw std::runtime_error("rb_augmented_rhs: null argument");
+    aug_rhs(s, *v, (const double2*)state_dev, (double2*)rhs_dev);
+    RB_CATCH
+}
+
+rb_aug_stepper* rb_aug_rk4_create(rb_solver* s, const rb_opto* v, double tstep) {
+    try {
+        if (!s || !v) throw std::runtime_error("rb_aug_rk4_create: null argument");
+        std::unique_ptr<rb_aug_stepper, void (*)(rb_aug_stepper*)> st(new rb_aug_stepper, aug_stepper_free);
+        st->s = s;
+        st->v = *v;
+        st->dt = tstep;
+        const size_t n = 3 * s->BN;
+        for (auto& k : st->k) k = dmalloc<double2>(n);
+        st->ytmp = dmalloc<double2>(n);
+        return st.release();
+    } catch (const std::exception& e) {
+        fail(e);
+        return nullptr;
+    }
+}
+
+int rb_aug_rk4_destroy(rb_aug_stepper* st) {
+    RB_TRY
+    if (st) {
+        cudaDeviceSynchronize();
+        aug_stepper_free(st);
+    }
+    RB_CATCH
+}
+
+int rb_aug_rk4_set_time_step(rb_aug_stepper* st, double tstep) {
+    st->dt = tstep;
+    return 0;
+}
+
+int rb_aug_rk4_initialize(rb_aug_stepper* st, rb_complex* y0, int on_device) {
+    RB_TRY
+    const size_t n = 3 * st->s->BN;
+    if (on_device) {
+        if (st->owns_y0 && st->y0) cudaFree(st->y0);
+        st->y0 = (double2*)y0;   // caller keeps ownership, L/AutonomousRungeKuttaStepper.cuh:312-318
+        st->owns_y0 = false;
+    } else {
+        if (!st->owns_y0 || !st->y0) st->y0 = dmalloc<double2>(n);
+        st->owns_y0 = true;
+        RB_CUDA(cudaMemcpyAsync(st->y0, y0, n * sizeof(double2), cudaMemcpyHostToDevice, st->s->stream));
+        RB_CUDA(cudaStreamSynchronize(st->s->stream));
+    }
+    st->t = 0.0;
+    RB_CATCH
+}
+
+int rb_aug_rk4_step(rb_aug_stepper* st) {
+    RB_TRY
+    if (!st->y0) throw std::runtime_error("rb_aug_rk4_step: initialize() has not been called");
+    aug_step(st);
+    RB_CATCH
+}
+
+int rb_aug_rk4_run_steps(rb_aug_stepper* st, size_t steps) {
+    RB_TRY
+    if (!st->y0) throw std::runtime_error("rb_aug_rk4_run_steps: initialize() has not been called");
+    for (size_t i = 0; i < steps; ++i) aug_step(st);
+    RB_CATCH
+}
+
+int rb_aug_rk4_evolve(rb_aug_stepper* st, double t0, double t1, size_t* steps_out) {
+    RB_TRY
+    if (!st->y0) throw std::runtime_error("rb_aug_rk4_evolve: initialize() has not been called");
+    st->t = t0;
+    const size_t steps = static_cast<size_t>((t1 - t0) / st->dt);   // truncation, L/AutonomousRungeKuttaStepper.cuh:421
+    for (size_t i = 0; i < steps; ++i) aug_step(st);
+    RB_CUDA(cudaStreamSynchronize(st->s->stream));
+    if (steps_out) *steps_out = steps;
+    RB_CATCH
+}
+
+rb_complex* rb_aug_rk4_dev_state(rb_aug_stepper* st) { return (rb_complex*)st->y0; }
+
+int rb_aug_rk4_get_state(rb_aug_stepper* st, rb_complex* y_host) {
+    RB_TRY
+    const size_t n = 3 * st->s->BN;
+    RB_CUDA(cudaMemcpyAsync(y_host, st->y0, n * sizeof(double2), cudaMemcpyDeviceToHost, st->s->stream));
+    RB_CUDA(cudaStreamSynchronize(st->s->stream));
+    RB_CATCH
+}
+
+double rb_aug_rk4_current_time(rb_aug_stepper* st) { return st->t; }
+
+int calculateRhsAugmentedOptomechanical(double* state, double* rhs_out, SimProperties* simProperties,
+                                        COptomechanicalVariables* optomechanicalVariables, size_t N) {
+    RB_TRY
+    if (!state || !rhs_out || !simProperties || !optomechanicalVariables)
+        throw std::runtime_error("calculateRhsAugmentedOptomechanical: null argument");
+    Adim ad = adimensionalize(simProperties->L, simProperties->rho, simProperties->kappa, simProperties->depth);
+    rb_props p = helium_props(ad, simProperties->use_expansions, simProperties->expansion_order, simProperties->infinite_depth);
+    rb_opto v = adimensionalize_opto(*optomechanicalVariables, ad.base_length, ad.base_time, ad.base_energy, ad.rho);
+    std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, 1, &p), solver_free);
+    std::vector<double2> host(3 * N);
+    for (size_t i = 0; i < N; ++i) {
+        host[i] = make_double2(state[i], state[N + i]);
+        host[N + i] = make_double2(state[2 * N + i], 0.0);
+        host[2 * N + i] = make_double2(state[3 * N + i], 0.0);
+    }
+    double2* d = dmalloc<double2>(6 * N);
+    RB_CUDA(cudaMemcpyAsync(d, host.data(), 3 * N * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
+    aug_rhs(s.get(), v, d, d + 3 * N);
+    RB_CUDA(cudaMemcpyAsync(host.data(), d + 3 * N, 3 * N * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
+    RB_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(d);
+    for (size_t i = 0; i < N; ++i) {
+        rhs_out[i] = host[i].x;
+        rhs_out[N + i] = host[i].y;
+        rhs_out[2 * N + i] = host[N + i].x;
+        rhs_out[3 * N + i] = host[2 * N + i].x;
+    }
+    RB_CATCH
+}
+
+int integrateAugmentedOptomechanicalSimulationRK4(double* initialState, double** statesOut, size_t* statesCount, double** timesOut,
+                                                  size_t* timesCount, SimProperties* simProperties, RK4SolverOptions* rkOptions,
+                                                  COptomechanicalVariables* optomechanicalVariables, size_t N) {
+    RB_TRY
+    if (!initialState || !statesOut || !statesCount || !simProperties || !rkOptions || !optomechanicalVariables)
+        throw std::runtime_error("integrateAugmentedOptomechanicalSimulationRK4: null argument");
+    Adim ad = adimensionalize(simProperties->L, simProperties->rho, simProperties->kappa, simProperties->depth);
+    rb_props p = helium_props(ad, simProperties->use_expansions, simProperties->expansion_order, simProperties->infinite_depth);
+    p.guess_mode = RB_GUESS_WARM;
+    rb_opto v = adimensionalize_opto(*optomechanicalVariables, ad.base_length, ad.base_time, ad.base_energy, ad.rho);
+    const double dt = rkOptions->timeStep / ad.base_time, t0 = rkOptions->t0 / ad.base_time, t1 = rkOptions->t1 / ad.base_time;
+    const size_t steps = static_cast<size_t>((t1 - t0) / dt);
+    std::vector<double> states, times;
+    aug_integrate_host(initialState, N, p, v, dt, steps, rkOptions->returnTrajectory, t0, states, times);
+    double* so = (double*)std::malloc(std::max<size_t>(states.size(), 1) * sizeof(double));
+    std::memcpy(so, states.data(), states.size() * sizeof(double));
+    *statesOut = so;
+    *statesCount = states.size() / (4 * N);
+    if (timesOut) {
+        double* to = (double*)std::malloc(std::max<size_t>(times.size(), 1) * sizeof(double));
+        std::memcpy(to, times.data(), times.size() * sizeof(double));
+        *timesOut = to;
+    }
+    if (timesCount) *timesCount = times.size();
+    RB_CATCH
+}
+
+int integrateAugmentedOptomechanicalSimulationRK4_freeMemory(double* statesOut, double* timesOut) {
+    std::free(statesOut);
+    std::free(timesOut);
+    return 0;
+}
+
+int rb_integrate_aug_rk4_host(const double* initialState_host, double* finalState_host, size_t N, const rb_props* props,
+                              const rb_opto* v, double dt, size_t steps) {
+    RB_TRY
+    if (!v) throw std::runtime_error("rb_integrate_aug_rk4_host: null optomechanical variables");
+    rb_props p;
+    if (props) p = *props; else rb_default_props(&p);
+    std::vector<double> states, times;
+    aug_integrate_host(initialState_host, N, p, *v, dt, steps, false, 0.0, states, times);
     std::memcpy(finalState_host, states.data(), states.size() * sizeof(double));
     RB_CATCH
 }

@@ -232,6 +232,72 @@ static void test_rk45() {
     std::printf("RK45 (reference test pattern): failures so far %d, max error %.3e\n", failures, worst);
 }
 
+// App pattern of the optomechanically driven film (CuSuperHelium.App/kernel.cu:60-96, augmentedSystem()): a flat film at rest has
+// w = 0 and a vanishing van-der-Waals term, so the augmented RHS is the drive alone:
+//   dPhi/dt = drive_strength * I(x) + D,   dD/dt = Beta * I(x) - D / Tau,   I = Lorentzian(detuning - G y) * Gaussian(x - x0)
+static void test_augmented() {
+    constexpr int N = 128;
+    ProblemProperties properties;
+    properties.depth = 0.0942478;
+    properties.rho = 1;
+    OptomechanicalVariables opto;
+    opto.Beta = 2e-33;
+    opto.detuning = 0.5;
+    opto.G = 3.0;
+    opto.gamma = 2.0;
+    opto.location_x0_mode = PI_d;
+    opto.sigma_optical_mode = 0.8;
+    opto.max_intensity = 1e32;
+    opto.Tau = 0.7;
+    opto.DampingStrength = 0.01;
+    std::vector<std_complex> y0(3 * N), rhs(3 * N);
+    std::vector<double> inten(N);
+    for (int i = 0; i < N; i++) {
+        const double x = 2.0 * PI_d * i / N;
+        y0[i] = std_complex(x, 0.0);
+        y0[N + i] = 0.0;
+        const double df = opto.detuning - opto.G * 0.0;
+        inten[i] = 0.25 * opto.gamma * opto.gamma * opto.max_intensity / (df * df + 0.25 * opto.gamma * opto.gamma) *
+                   std::exp(-(x - opto.location_x0_mode) * (x - opto.location_x0_mode) / (2 * opto.sigma_optical_mode * opto.sigma_optical_mode));
+        y0[2 * N + i] = std_complex(0.3 * opto.Beta * inten[i], 0.0);
+    }
+    HeliumDrivenAutonomousProblem<N, 1> heliumProblem(properties, opto);
+    auto calculator = std::make_unique<BaseBoundaryIntegralCalculator<N, 1>>(properties, heliumProblem);
+    AugmentedBoundaryIntegrator<N, 1> integrator(std::move(calculator), std::make_unique<DelayedIntensityIntegrator<N, 1>>(opto), properties);
+    std_complex *dState = nullptr, *dRhs = nullptr;
+    cudaMalloc(&dState, 3 * N * sizeof(std_complex));
+    cudaMalloc(&dRhs, 3 * N * sizeof(std_complex));
+    cudaMemcpy(dState, y0.data(), 3 * N * sizeof(std_complex), cudaMemcpyHostToDevice);
+    integrator.run(dState, dRhs);
+    cudaDeviceSynchronize();
+    cudaMemcpy(rhs.data(), dRhs, 3 * N * sizeof(std_complex), cudaMemcpyDeviceToHost);
+    const double strength = 1.054571817e-34 / (properties.base_energy * properties.base_time * properties.rho) * opto.G /
+                            (opto.sigma_optical_mode * opto.sigma_optical_mode);
+    for (int i = 0; i < N; i++) {
+        EXPECT_NEAR(std::hypot(rhs[i].real(), rhs[i].imag()), 0.0, 1e-12, "flat film at rest does not move");
+        EXPECT_NEAR(rhs[N + i].real(), strength * inten[i] + y0[2 * N + i].real(), 1e-12, "driven dPhi/dt");
+        EXPECT_NEAR(rhs[2 * N + i].real(), opto.Beta * inten[i] - y0[2 * N + i].real() / opto.Tau, 1e-12, "dD/dt");
+    }
+    AutonomousRungeKuttaStepper<std_complex, 3 * N> stepper(integrator, 1e-3);
+    stepper.initialize(dState, true);
+    for (int i = 0; i < 10; i++) stepper.runStep(i);
+    std::vector<std_complex> y(3 * N);
+    stepper.getState(y.data());
+    double dmax = 0, moved = 0;
+    for (int i = 0; i < N; i++) {
+        // D relaxes towards Beta Tau I with rate 1/Tau (the film has barely moved after 10 steps of 1e-3)
+        const double target = opto.Beta * opto.Tau * inten[i];
+        const double expect = target + (y0[2 * N + i].real() - target) * std::exp(-0.01 / opto.Tau);
+        dmax = std::max(dmax, std::abs(y[2 * N + i].real() - expect));
+        moved = std::max(moved, std::abs(y[N + i].real()));
+    }
+    EXPECT_NEAR(dmax, 0.0, 1e-6, "delayed intensity relaxes exponentially");
+    EXPECT_NEAR(moved > 1e-5 ? 1.0 : 0.0, 1.0, 0.5, "the drive has acted on the potential");
+    cudaFree(dState);
+    cudaFree(dRhs);
+    std::printf("Augmented optomechanical system (App pattern): failures so far %d, |D - analytic| = %.3e, max |Phi| = %.3e\n", failures, dmax, moved);
+}
+
 int main() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -245,6 +311,7 @@ int main() {
     test_rhs_phi();
     test_stepper();
     test_rk45();
+    test_augmented();
     std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
     return failures ? 1 : 0;
 }

@@ -59,8 +59,29 @@ CASES = [
 ]
 
 
+# the optomechanically driven film: App-like properties (A/kernel.cu:77-82: depth 0.0942478, rho = 1, base
+# units 1) and variables chosen so that every term of the augmented RHS is O(1e-2 .. 1e-1): drive strength hbar G / sigma^2 ~ 5e-34
+OPTO = dict(detuning=0.5, gamma=2.0, G=3.0, Tau=0.7, max_intensity=1e32, initial_time=0.0, location_x0_mode=3.0,
+            sigma_optical_mode=0.8, Beta=2e-33, DampingStrength=0.01)
+AUG_CASES = [
+    _case("aug_rhs_N64", "aug_rhs", "helium", 64, 0.1, surface="film", depth=0.0942478, rho=1.0),
+    _case("aug_rhs_N256", "aug_rhs", "helium", 256, 0.1, surface="film", depth=0.0942478, rho=1.0),
+    _case("aug_rhs_N1024", "aug_rhs", "helium", 1024, 0.1, surface="film", depth=0.0942478, rho=1.0),
+    _case("aug_rk4_N64_100", "aug_rk4", "helium", 64, 0.1, surface="film", depth=0.0942478, rho=1.0, dt=1e-3, steps=100),
+    _case("aug_rk4_N256_100", "aug_rk4", "helium", 256, 0.1, surface="film", depth=0.0942478, rho=1.0, dt=1e-3, steps=100),
+]
+for _c in AUG_CASES:
+    _c["opto"] = dict(OPTO)
+CASES = CASES + AUG_CASES
+
+
 def state_of(case):
-    return _surface(case["N"], case["h"], case["surface"], case["props"]["depth"])
+    y = _surface(case["N"], case["h"], case["surface"], case["props"]["depth"])
+    if case["op"].startswith("aug"):
+        a = 2.0 * np.pi * np.arange(case["N"]) / case["N"]
+        D = 0.02 * np.cos(a - 0.4) + 0.01          # delayed intensity block
+        y = np.concatenate([y, D.astype(np.complex128)])
+    return y
 
 
 def reference_results(cases=CASES, timeout=420):
@@ -68,8 +89,10 @@ def reference_results(cases=CASES, timeout=420):
     jobs = []
     for c in cases:
         j = dict(op=c["op"], kind=c["physics"], N=c["N"], props=c["props"], state=state_of(c))
-        if c["op"] == "rk4":
+        if c["op"] in ("rk4", "aug_rk4"):
             j.update(dt=c["dt"], steps=c["steps"], warmup=0)
+        if c["op"].startswith("aug"):
+            j["opto"] = c["opto"]
         jobs.append(j)
     res = ref_runner.run_jobs(jobs, timeout=timeout)
     return {c["name"]: r for c, r in zip(cases, res)}
@@ -95,6 +118,31 @@ def measure(api, case, ref, torch):
     y0 = state_of(case)
     dev = torch.device("cuda:0")
     out = {}
+    if case["op"].startswith("aug"):
+        p = case["props"]
+        props = api.ProblemProperties(rho=p["rho"], kappa=p["kappa"], depth=p["depth"])
+        variables = api.OptomechanicalVariables(**case["opto"])
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumDrivenAutonomousProblem(props, variables),
+                                                  guess="warm" if case["op"] == "aug_rk4" else "cold")
+        integrator = api.AugmentedBoundaryIntegrator(calc, api.DelayedIntensityIntegrator(variables))
+        if case["op"] == "aug_rhs":
+            rhs = torch.zeros(3 * N, dtype=torch.complex128, device=dev)
+            integrator.run(torch.as_tensor(y0, device=dev), rhs)
+            o = rhs.cpu().numpy()
+            out["velocity"] = rel(o[:N], ref["rhs"][:N])
+            out["dphi_dt"] = rel(o[N:2 * N], ref["rhs"][N:2 * N])
+            out["dD_dt"] = rel(o[2 * N:], ref["rhs"][2 * N:])
+        else:
+            stp = api.AugmentedRungeKuttaStepper(integrator, case["dt"])
+            stp.initialize(y0, False)
+            stp.runSteps(case["steps"])
+            y = stp.getState()
+            out["position"] = rel(y[:N], ref["state"][:N])
+            out["potential"] = rel(y[N:2 * N], ref["state"][N:2 * N])
+            out["delayed_intensity"] = rel(y[2 * N:], ref["state"][2 * N:])
+            out["reference_steps_per_s"] = case["steps"] / ref["seconds"] if ref.get("seconds") else None
+        out["converged"] = bool(calc.solve_stats()["converged"])
+        return out
     if case["op"] == "rhs":
         calc = _calc(api, case, compute_energies=True)
         rhs = torch.zeros(2 * N, dtype=torch.complex128, device=dev)

@@ -607,3 +607,102 @@ def test_row_sharded_two_gpus_match_single_gpu(api):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "FAIL" not in r.stdout
+
+
+# ---- optomechanically driven film ------------------------------------------------------------
+def _film_state(N, depth, amp=0.1):
+    al = 2 * np.pi * np.arange(N) / N
+    Z = al - 0.3 * amp * depth * np.sin(al) + 1j * amp * depth * np.cos(al)
+    Phi = 0.2 * amp * depth * np.sin(al)
+    D = 0.02 * np.cos(al - 0.4) + 0.01
+    return np.concatenate([Z, Phi.astype(np.complex128), D.astype(np.complex128)])
+
+
+OPTO = dict(detuning=0.5, gamma=2.0, G=3.0, Tau=0.7, max_intensity=1e32, location_x0_mode=3.0, sigma_optical_mode=0.8, Beta=2e-33,
+            DampingStrength=0.01)
+
+
+@pytest.mark.parametrize("N,batch", [(64, 1), (300, 1), (128, 3)])
+def test_augmented_rhs_and_light_intensity_match_oracle(api, N, batch):
+    """rb_augmented_rhs / rb_light_intensity vs the oracle's restatement of L/createM.cuh:138-169 and L/LightIntensity.cuh:17-33,
+    incl. a ragged N and a batch (layout [Z_b | Phi_b | D_b], 3 N B): 1e-10 relative (thin film, cond(M) ~ N / 2 pi)."""
+    depth = 0.0942478
+    props = api.ProblemProperties(rho=1.0, depth=depth)
+    oprops = ro.ProblemProperties(rho=1.0, depth=depth)
+    v = api.OptomechanicalVariables(**OPTO)
+    ov = ro.OptomechanicalVariables(**OPTO)
+    members = [_film_state(N, depth, 0.1 * (1 + 0.5 * b)) for b in range(batch)]
+    st = np.concatenate([m[blk * N:(blk + 1) * N] for blk in range(3) for m in members])
+    calc = api.BaseBoundaryIntegralCalculator(N, batch, props, api.HeliumDrivenAutonomousProblem(props, v))
+    integ = api.AugmentedBoundaryIntegrator(calc, api.DelayedIntensityIntegrator(v))
+    assert abs(v.drive_strength - ro.drive_strength(ov, oprops)) <= 1e-15 * abs(v.drive_strength)
+    out = torch.zeros(3 * N * batch, dtype=torch.complex128, device="cuda:0")
+    integ.run(T(st), out)
+    o = out.cpu().numpy()
+    for b, m in enumerate(members):
+        e = ro.augmented_rhs(m, N, oprops, ov)
+        for blk in range(3):
+            got = o[(blk * batch + b) * N:(blk * batch + b + 1) * N]
+            assert rel(got, e[blk * N:(blk + 1) * N]) <= 1e-10, (b, blk)
+    inten = integ.lightIntensity(T(members[0][:N])).cpu().numpy()
+    assert rel(inten, ro.light_intensity(members[0][:N].imag, members[0][:N].real, ov)) <= 1e-14
+
+
+def test_augmented_rk4_and_legacy_exports_match_oracle(api):
+    """AutonomousRungeKuttaStepper<std_complex, 3N> over the augmented system (50 steps, 1e-9), device aliasing, runEvolution's
+    truncated step count; calculateRhsAugmentedOptomechanical / integrateAugmentedOptomechanicalSimulationRK4 (L/Export.cuh:75-78)
+    with SI inputs against the oracle's adimensionalize_properties / adimensionalize_optomechanical (L/Export.cu:1222-1275)."""
+    from superfluid_dynamics_b200 import _lib
+    N, depth, dt = 128, 0.0942478, 1e-3
+    props = api.ProblemProperties(rho=1.0, depth=depth)
+    oprops = ro.ProblemProperties(rho=1.0, depth=depth)
+    v = api.OptomechanicalVariables(**OPTO)
+    ov = ro.OptomechanicalVariables(**OPTO)
+    y0 = _film_state(N, depth)
+    f = lambda s: ro.augmented_rhs(s, N, oprops, ov)
+    ye = y0.copy()
+    for _ in range(50):
+        ye = ro.rk4_step(f, ye, dt)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumDrivenAutonomousProblem(props, v), guess="warm")
+    stp = api.AugmentedRungeKuttaStepper(api.AugmentedBoundaryIntegrator(calc, api.DelayedIntensityIntegrator(v)), dt)
+    dev = T(y0)
+    stp.initialize(dev, True)
+    assert stp.runEvolution(0.0, 0.0505) == 50
+    y = stp.getState()
+    assert np.array_equal(y, dev.cpu().numpy())
+    for blk in range(3):
+        assert rel(y[blk * N:(blk + 1) * N], ye[blk * N:(blk + 1) * N]) <= 1e-9, blk
+    assert abs(stp.currentTime() - 0.05) <= 1e-12
+
+    # legacy exports, SI in: a 15 nm film on a 1 um period (A/kernel.cu:79), laboratory-unit optomechanical variables
+    L, d_si = 1e-6, 15e-9
+    sp = _lib.SimProperties(L=L, rho=150.0, kappa=0.0, depth=d_si, use_expansions=False, expansion_order=1, infinite_depth=False)
+    op_si = ro.adimensionalize_properties(ro.ProblemProperties(L=L, rho=150.0, kappa=0.0, depth=d_si))
+    cv = _lib.COptomechanicalVariables(detuning=0.5 / op_si.base_time, gamma=2.0 / op_si.base_time,
+                                       G=3.0 / (op_si.base_time * op_si.base_length), tau=0.7 * op_si.base_time, max_intensity=5e7,
+                                       initial_time=0.0, location_x0_mode=3.0 * op_si.base_length,
+                                       sigma_optical_mode=0.8 * op_si.base_length, beta=1.0, damping_strength=0.01)
+    ov_si = ro.adimensionalize_optomechanical(
+        ro.OptomechanicalVariables(detuning=cv.detuning, gamma=cv.gamma, G=cv.G, Tau=cv.tau, max_intensity=cv.max_intensity,
+                                   location_x0_mode=cv.location_x0_mode, sigma_optical_mode=cv.sigma_optical_mode, Beta=cv.beta,
+                                   DampingStrength=cv.damping_strength), op_si)
+    ys = _film_state(N, op_si.depth)
+    flat = np.concatenate([ys[:N].real, ys[:N].imag, ys[N:2 * N].real, ys[2 * N:].real])
+    got = api.calculateRhsAugmentedOptomechanical(flat, sp, cv, N)
+    e = ro.augmented_rhs(ys, N, op_si, ov_si)
+    exp = np.concatenate([e[:N].real, e[:N].imag, e[N:2 * N].real, e[2 * N:].real])
+    for blk in range(4):
+        assert rel(got[blk * N:(blk + 1) * N], exp[blk * N:(blk + 1) * N]) <= 1e-10, blk
+    opts = _lib.RK4SolverOptions(timeStep=1e-3 * op_si.base_time, t0=0.0, t1=0.0105 * op_si.base_time, returnTrajectory=True)
+    states, times = api.integrateAugmentedOptomechanicalSimulationRK4(flat, sp, opts, cv, N)
+    assert states.shape == (10, 4 * N) and len(times) == 10
+    fs = lambda s: ro.augmented_rhs(s, N, op_si, ov_si)
+    yo = ys.copy()
+    for _ in range(10):
+        yo = ro.rk4_step(fs, yo, 1e-3)
+    expf = np.concatenate([yo[:N].real, yo[:N].imag, yo[N:2 * N].real, yo[2 * N:].real])
+    for blk in range(4):
+        assert rel(states[-1][blk * N:(blk + 1) * N], expf[blk * N:(blk + 1) * N]) <= 1e-9, blk
+    opts.returnTrajectory = False
+    final, t2 = api.integrateAugmentedOptomechanicalSimulationRK4(flat, sp, opts, cv, N)
+    assert final.shape == (1, 4 * N) and len(t2) == 0 and rel(final[0], states[-1]) <= 1e-13

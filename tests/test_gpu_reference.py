@@ -66,6 +66,18 @@ def test_rhs_matches_the_reference_cuda_path(api, reference, case):
         assert m[k] <= ENERGY_TOL, (k, m)
 
 
+@pytest.mark.parametrize("case", [c for c in ref_cases.CASES if c["op"].startswith("aug")], ids=lambda c: c["name"])
+def test_augmented_optomechanical_system_matches_the_reference(api, reference, case):
+    """The driven film y = [Z | Phi | D]: HeliumDrivenAutonomousProblem + DelayedIntensityIntegrator + AugmentedBoundaryIntegrator
+    (L/AugmentedBoundaryIntegrator.cuh:25-29) and AutonomousRungeKuttaStepper<std_complex, 3N>, assembled as L/Export.cu:1136-1150
+    and A/kernel.cu:85-94 do, against rb_augmented_rhs / rb_aug_rk4_*.  Thin film (cond(M) ~ N / 2 pi): 1e-9."""
+    m = ref_cases.measure(api, case, _ref(reference, case), torch)
+    assert m["converged"]
+    keys = ("velocity", "dphi_dt", "dD_dt") if case["op"] == "aug_rhs" else ("position", "potential", "delayed_intensity")
+    for k in keys:
+        assert m[k] <= 1e-9, (k, m)
+
+
 @pytest.mark.parametrize("case", [c for c in ref_cases.CASES if c["op"] == "rk4"], ids=lambda c: c["name"])
 def test_rk4_steps_match_the_reference_stepper(api, reference, case):
     """AutonomousRungeKuttaStepper<std_complex, 2N>::runStep (L/AutonomousRungeKuttaStepper.cuh:124-307) driven as
