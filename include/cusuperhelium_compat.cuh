@@ -320,6 +320,103 @@ public:
     }
 };
 
+// ---- the explicitly time-dependent drive: TimedProblem (L/AutonomousProblem.h:30-51), TimedBoundaryProblem
+//      (L/TimedBoundaryProblem.cuh:6-19), HeliumWithOptomechanicalDrivingProblem<N> (L/HeliumWithDrivingBoundaryProblem.cuh:11-67),
+//      TimedBoundaryIntegrator<N,B> (L/TimedBoundaryIntegrator.cuh:7-49) and RungeKuttaStepper<std_complex, 2N>
+//      (L/RK4_Time_Dependent.cuh:18-460), used as in A/kernel.cu:281-366 and L/Export.cu:797-826 ----------------------------------
+template <typename T, int N>
+class TimedProblem {
+protected:
+    bool saveProgress = true;
+    double currentTime = 0.0;
+public:
+    virtual ~TimedProblem() {}
+    virtual void run(T* initialState, T* rhs) = 0;
+    void setCurrentTime(double time) { currentTime = time; }
+    virtual void setStartingTime(double time) { currentTime = time; }
+    void setSaveProgress(bool save) { saveProgress = save; }
+    virtual void setStream(cudaStream_t stream) = 0;
+};
+template <int N, size_t batchSize>
+class TimedBoundaryProblem : public HeliumBoundaryProblem<N, batchSize> {
+public:
+    ProblemProperties& properties;
+    OptomechanicalVariables variables;
+    TimedBoundaryProblem(ProblemProperties& p, OptomechanicalVariables v)
+        : HeliumBoundaryProblem<N, batchSize>(p), properties(p), variables(v) {}
+};
+template <int N>
+class HeliumWithOptomechanicalDrivingProblem : public TimedBoundaryProblem<N, 1> {
+public:
+    HeliumWithOptomechanicalDrivingProblem(ProblemProperties& p, OptomechanicalVariables v) : TimedBoundaryProblem<N, 1>(p, v) {}
+};
+// The delayed-intensity term (the reference keeps it in the boundary problem, L/DelayedIntensityTerm.cuh) lives in the library's
+// timed stepper object; the integrator owns that object and the RungeKuttaStepper below drives the same one.
+template <int N, size_t batchSize>
+class TimedBoundaryIntegrator : public BaseBoundaryIntegralCalculator<N, batchSize>, public TimedProblem<std_complex, 2 * N * (int)batchSize> {
+    rb_timed_stepper* timed_ = nullptr;
+public:
+    TimedBoundaryIntegrator(ProblemProperties& p, TimedBoundaryProblem<N, batchSize>& problem)
+        : BaseBoundaryIntegralCalculator<N, batchSize>(p, problem) {
+        rb_opto o = rb_compat_opto(problem.variables, p);
+        timed_ = rb_timed_rk4_create(this->handle(), &o, 1e-2);
+        if (!timed_) throw std::runtime_error(std::string("rb_timed_rk4_create: ") + rb_last_error());
+    }
+    ~TimedBoundaryIntegrator() override { rb_timed_rk4_destroy(timed_); }
+    void run(std_complex* initialState, std_complex* rhs) override {
+        rb_compat_check(rb_timed_rhs(timed_, this->currentTime, this->saveProgress, reinterpret_cast<const rb_complex*>(initialState),
+                                     reinterpret_cast<rb_complex*>(rhs)), "rb_timed_rhs");
+    }
+    void setStream(cudaStream_t stream) override { BaseBoundaryIntegralCalculator<N, batchSize>::setStream(stream); }
+    void setStartingTime(double time) override {
+        this->currentTime = time;
+        rb_compat_check(rb_timed_rk4_set_starting_time(timed_, time), "rb_timed_rk4_set_starting_time");
+    }
+    double* delayedIntensity() { return rb_timed_rk4_dev_delayed_intensity(timed_); }
+    rb_timed_stepper* timedHandle() { return timed_; }
+};
+
+template <typename T, int N>
+class RungeKuttaStepper {
+    rb_timed_stepper* st_ = nullptr;   // owned by the TimedBoundaryIntegrator
+    RK4Options options;
+public:
+    template <int NP, size_t B>
+    RungeKuttaStepper(TimedBoundaryIntegrator<NP, B>& timedProblem, double tstep = 1e-2) : st_(timedProblem.timedHandle()) {
+        static_assert(2 * NP * (int)B == N, "state size must be 2 * N * batchSize");
+        setTimeStep(tstep);
+    }
+    void setTimeStep(double tstep) { rb_compat_check(rb_timed_rk4_set_time_step(st_, tstep), "rb_timed_rk4_set_time_step"); }
+    void setOptions(const RK4Options& o) {
+        setTimeStep(o.initial_timestep);
+        options = o;
+        rb_compat_check(rb_timed_rk4_set_logging(st_, o.returnTrajectory), "rb_timed_rk4_set_logging");
+    }
+    void initialize(T* devY0, bool onDevice = false) {
+        rb_compat_check(rb_timed_rk4_initialize(st_, reinterpret_cast<rb_complex*>(devY0), onDevice), "rb_timed_rk4_initialize");
+    }
+    void runStep(int = 0) { rb_compat_check(rb_timed_rk4_step(st_, 0), "rb_timed_rk4_step"); }
+    OdeSolverResult runEvolution(double startTime, double endTime) {
+        size_t n = 0;
+        rb_compat_check(rb_timed_rk4_evolve(st_, startTime, endTime, &n), "rb_timed_rk4_evolve");
+        return OdeSolverResult::ReachedEndTime;
+    }
+    int copyTimesToHost(double** hostTimes, size_t* countHost) {
+        rb_complex* states = nullptr; size_t ns = 0;
+        if (rb_timed_rk4_copy_trajectory(st_, hostTimes, countHost, &states, &ns) != 0) return -1;
+        rb_free(states);
+        return 0;
+    }
+    int copyStatesToHost(T** hostStates, size_t* countHost) {
+        double* times = nullptr; size_t nt = 0;
+        if (rb_timed_rk4_copy_trajectory(st_, &times, &nt, reinterpret_cast<rb_complex**>(hostStates), countHost) != 0) return -1;
+        rb_free(times);
+        return 0;
+    }
+    void getState(T* host) { rb_compat_check(rb_timed_rk4_get_state(st_, reinterpret_cast<rb_complex*>(host)), "rb_timed_rk4_get_state"); }
+    double getCurrentTime() { return rb_timed_rk4_current_time(st_); }
+};
+
 // ---- adaptive RKF45 (L/RK45.cuh): RK45_Options and RK45_std_complex<N> over any AutonomousProblem<std_complex, N> ---------------
 struct RK45_Options {   // L/RK45.cuh:21-27
     double atol = 1e-6;

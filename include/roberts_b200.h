@@ -41,6 +41,7 @@ typedef struct rb_solver rb_solver;                           /* opaque: one RHS
 typedef struct rb_stepper rb_stepper;                         /* opaque: RK4 stepper bound to a solver */
 typedef struct rb_rk45 rb_rk45;                               /* opaque: adaptive RKF45 stepper (L/RK45.cuh) */
 typedef struct rb_aug_stepper rb_aug_stepper;                 /* opaque: RK4 stepper of the optomechanically driven (augmented) system */
+typedef struct rb_timed_stepper rb_timed_stepper;             /* opaque: RK4 stepper of the explicitly time-dependent drive */
 
 /* physics plugin selector == which BoundaryProblem<N,B> subclass the reference would instantiate */
 enum rb_physics {
@@ -227,6 +228,37 @@ RB_API rb_complex* rb_aug_rk4_dev_state(rb_aug_stepper* st);
 RB_API int rb_aug_rk4_get_state(rb_aug_stepper* st, rb_complex* y_host);
 RB_API double rb_aug_rk4_current_time(rb_aug_stepper* st);
 
+/* ---- the same drive in its explicitly time-dependent form: HeliumWithOptomechanicalDrivingProblem<N>
+ *      (L/HeliumWithDrivingBoundaryProblem.cuh:7-67, kernel add_optical_field_drive_terms L/createM.cuh:119-136), the exponential
+ *      integrator DelayedIntensityTerm<N> (L/DelayedIntensityTerm.cuh:9-71), TimedBoundaryIntegrator<N,B>
+ *      (L/TimedBoundaryIntegrator.cuh:8-49) and RungeKuttaStepper<std_complex, 2N>(TimedProblem&) (L/RK4_Time_Dependent.cuh:18-460;
+ *      usage A/kernel.cu:281-366, L/Export.cu:797-826).  State 2 N B complex [Z | Phi]; the delayed intensity lives in the stepper
+ *      and is advanced (saved) by the first RK stage of every step. ---- */
+RB_API rb_timed_stepper* rb_timed_rk4_create(rb_solver* s, const rb_opto* v, double tstep);
+RB_API int rb_timed_rk4_destroy(rb_timed_stepper* st);
+RB_API int rb_timed_rk4_set_time_step(rb_timed_stepper* st, double tstep);
+RB_API int rb_timed_rk4_initialize(rb_timed_stepper* st, rb_complex* y0, int on_device);
+/* TimedBoundaryIntegrator::setStartingTime :44-48: the current time and the delayed term's reference time */
+RB_API int rb_timed_rk4_set_starting_time(rb_timed_stepper* st, double time);
+/* TimedBoundaryIntegrator::run at an explicit time (setCurrentTime + setSaveProgress + run, L/RK4_Time_Dependent.cuh:148-150) */
+RB_API int rb_timed_rhs(rb_timed_stepper* st, double time, int save_progress, const rb_complex* state_dev, rb_complex* rhs_dev);
+/* runStep :145-283: one RK4 step at the stepper's current time (stages at t, t + h/2, t + h/2, t + h; only the first saves the
+   delayed intensity).  As in the reference the time is advanced by the evolution loop, not by runStep: advance_time = 0 is
+   runStep verbatim, advance_time = 1 adds the `currentTime += timeStep` of runEvolution's loop body (:313-325). */
+RB_API int rb_timed_rk4_step(rb_timed_stepper* st, int advance_time);
+/* runEvolution :307-328: setStartingTime(t0), steps = size_t((t1 - t0)/dt) */
+RB_API int rb_timed_rk4_evolve(rb_timed_stepper* st, double t0, double t1, size_t* steps_out);
+/* RK4Options::returnTrajectory (setOptions :29-33) and copyTimesToHost / copyStatesToHost :66-131: with a trajectory, one (time at the
+   START of the step, state after the step) pair per step of rb_timed_rk4_evolve; without, no times and the current state alone.
+   Buffers are malloc'd; release with rb_free. */
+RB_API int rb_timed_rk4_set_logging(rb_timed_stepper* st, int return_trajectory);
+RB_API int rb_timed_rk4_copy_trajectory(rb_timed_stepper* st, double** times_out, size_t* times_count, rb_complex** states_out,
+                                        size_t* states_count);
+RB_API rb_complex* rb_timed_rk4_dev_state(rb_timed_stepper* st);
+RB_API double* rb_timed_rk4_dev_delayed_intensity(rb_timed_stepper* st);                /* DelayedIntensityTerm::delayed_intensity, N B doubles */
+RB_API int rb_timed_rk4_get_state(rb_timed_stepper* st, rb_complex* y_host);
+RB_API double rb_timed_rk4_current_time(rb_timed_stepper* st);
+
 /* ---- multi-GPU (new; the reference is single-GPU, L/utilities.cuh:20): contiguous blocks of 256-row cells of every O(N^2)
  *      sweep are owned by one rank each; all ranks keep the full state and exchange result rows by peer stores over NVLink into
  *      a per-rank arena mapped with CUDA IPC.  One process per GPU of one node; ship the handles with any out-of-band channel
@@ -300,6 +332,14 @@ RB_API int integrateAugmentedOptomechanicalSimulationRK4(double* initialState, d
                                                          RK4SolverOptions* rkOptions,
                                                          COptomechanicalVariables* optomechanicalVariables, size_t N);
 RB_API int integrateAugmentedOptomechanicalSimulationRK4_freeMemory(double* statesOut, double* timesOut);
+/* L/Export.cuh:72-73, L/Export.cu:779-975: RK4 evolution with the explicitly time-dependent drive.  initialState = [x | y | phi];
+ * *statesOut = statesCount x 3N doubles; the logged time of a state is the time at the START of the step that produced it
+ * (L/RK4_Time_Dependent.cuh:318-324); returnTrajectory = false: the final state, no times.  Any N >= 2 (the reference returns 0
+ * without doing anything for an N outside its switch table, L/Export.cu:970). */
+RB_API int integrateOptomechanicalSimulationRK4(double* initialState, double** statesOut, size_t* statesCount, double** timesOut,
+                                                size_t* timesCount, SimProperties* simProperties, RK4SolverOptions* rkOptions,
+                                                COptomechanicalVariables* optomechanicalVariables, size_t N);
+RB_API int integrateOptomechanicalSimulationRK4_freeMemory(double* statesOut, double* timesOut);
 /* nondimensional variant (no SI conversion): [Z | Phi | D] as 4N doubles in, final state out */
 RB_API int rb_integrate_aug_rk4_host(const double* initialState_host, double* finalState_host, size_t N, const rb_props* props,
                                      const rb_opto* v, double dt, size_t steps);

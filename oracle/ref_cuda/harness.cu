@@ -27,6 +27,8 @@
 #include "AutonomousRungeKuttaStepper.cuh"
 #include "HeliumDrivenAutonomousProblem.cuh"      // the optomechanically driven film (what A/kernel.cu:60-96 runs)
 #include "AugmentedBoundaryIntegrator.cuh"
+#include "HeliumWithDrivingBoundaryProblem.cuh"   // the explicitly time-dependent drive (A/kernel.cu:281-366, L/Export.cu:779-975)
+#include "RK4_Time_Dependent.cuh"
 
 #include <chrono>
 #include <cstring>
@@ -182,6 +184,37 @@ int augImpl(const ref_props* rp, const ref_opto* ro, const double* state, double
 	return rc;
 }
 
+// the explicitly time-dependent drive: HeliumWithOptomechanicalDrivingProblem<N> + TimedBoundaryIntegrator<N,1> +
+// RungeKuttaStepper<std_complex, 2N>::runEvolution(t0, t0 + steps*dt), as L/Export.cu:797-826 assembles it; state 2N complex in/out
+template<int N>
+int timedImpl(const ref_props* rp, const ref_opto* ro, double* state, double t0, double dt, int steps, double* seconds)
+{
+	ProblemProperties props = toProps(rp);
+	OptomechanicalVariables vars = toOpto(ro);
+	HeliumWithOptomechanicalDrivingProblem<N> problem(props, vars);
+	TimedBoundaryIntegrator<N, 1> integrator(props, problem);
+	RungeKuttaStepper<std_complex, 2 * N> stepper(integrator);
+	RK4Options options;
+	options.initial_timestep = dt;
+	options.returnTrajectory = false;
+	stepper.setOptions(options);
+	std_complex* dState = nullptr;
+	if (cudaMalloc(&dState, 2 * N * sizeof(std_complex)) != cudaSuccess) return -3;
+	cudaMemcpy(dState, state, 2 * N * sizeof(std_complex), cudaMemcpyHostToDevice);
+	stepper.initialize(dState, true);
+	auto c0 = std::chrono::steady_clock::now();
+	stepper.runEvolution(t0, t0 + (steps + 0.5) * dt);   // steps = size_t((t1 - t0) / dt): the half step keeps the truncation exact
+	int rc = lastError("timed evolution");
+	auto c1 = std::chrono::steady_clock::now();
+	if (seconds) *seconds = std::chrono::duration<double>(c1 - c0).count();
+	if (rc == 0) {
+		cudaMemcpy(state, dState, 2 * N * sizeof(std_complex), cudaMemcpyDeviceToHost);
+		rc = lastError("timed read-back");
+	}
+	cudaFree(dState);
+	return rc;
+}
+
 template<int N>
 int rhsKind(int kind, const ref_props* rp, const double* state, double* rhs, double* a, double* vu, double* zp, double* zpp, double* pp, double* en)
 {
@@ -270,6 +303,22 @@ __attribute__((visibility("default"))) int ref_augmented(int N, const ref_props*
 		}
 	} catch (const std::exception& e) {
 		fprintf(stderr, "ref_augmented: %s\n", e.what());
+		return -2;
+	}
+	return -1;
+}
+
+__attribute__((visibility("default"))) int ref_timed(int N, const ref_props* props, const ref_opto* opto, double* state, double t0,
+                                                     double dt, int steps, double* seconds)
+{
+	try {
+		switch (N) {
+#define X(n) case n: return timedImpl<n>(props, opto, state, t0, dt, steps, seconds);
+			REF_AUG_SIZES(X)
+#undef X
+		}
+	} catch (const std::exception& e) {
+		fprintf(stderr, "ref_timed: %s\n", e.what());
 		return -2;
 	}
 	return -1;

@@ -10,6 +10,9 @@ must not take the test runner or bench.py down with it.  Jobs are dicts:
     {"op": "aug_rhs" | "aug_rk4", "N": .., "props": .., "opto": {OptomechanicalVariables fields}, "state": complex128[3N] [, dt, steps]}
         -> the augmented optomechanical system [Z | Phi | D] (HeliumDrivenAutonomousProblem + AugmentedBoundaryIntegrator):
            rhs complex128[3N], or the state after the steps and the seconds they took
+    {"op": "timed_rk4", "N": .., "props": .., "opto": .., "state": complex128[2N], "t0": 0.0, "dt": .., "steps": ..}
+        -> the explicitly time-dependent drive (HeliumWithOptomechanicalDrivingProblem + TimedBoundaryIntegrator +
+           RungeKuttaStepper::runEvolution): state after the steps, seconds
     {"op": "rk4", ..., "dt": 1e-3, "steps": 100, "warmup": 0}
         -> state complex128[2N] after warmup+steps steps, seconds (host clock around the last `steps` steps, device
            synchronised on both sides), energies of the last RHS evaluated
@@ -65,6 +68,10 @@ def _load():
     lib.ref_rhs.restype = ctypes.c_int
     lib.ref_rk4.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Props), D, ctypes.c_double, ctypes.c_int, ctypes.c_int, D, D]
     lib.ref_rk4.restype = ctypes.c_int
+    if hasattr(lib, "ref_timed"):
+        lib.ref_timed.argtypes = [ctypes.c_int, ctypes.POINTER(_Props), ctypes.POINTER(_Opto), D, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_int, D]
+        lib.ref_timed.restype = ctypes.c_int
     if hasattr(lib, "ref_augmented"):
         lib.ref_augmented.argtypes = [ctypes.c_int, ctypes.POINTER(_Props), ctypes.POINTER(_Opto), D, D, ctypes.c_double, ctypes.c_int,
                                       ctypes.c_int, D]
@@ -87,6 +94,15 @@ def _run_one(lib, job):
     kind = KINDS[job["kind"]]
     p = _props(job.get("props"))
     state = np.ascontiguousarray(job["state"], dtype=np.complex128).copy()
+    if job["op"] == "timed_rk4":
+        assert state.size == 2 * N
+        o = _Opto(*[float(job["opto"][n]) for n, _ in _Opto._fields_])
+        sec = ctypes.c_double(0.0)
+        rc = lib.ref_timed(N, ctypes.byref(p), ctypes.byref(o), _dp(state.view(np.float64)), float(job.get("t0", 0.0)),
+                           float(job["dt"]), int(job["steps"]), ctypes.byref(sec))
+        if rc != 0:
+            return {"error": f"ref_timed returned {rc}"}
+        return dict(state=state, seconds=sec.value)
     if job["op"] in ("aug_rhs", "aug_rk4"):
         assert state.size == 3 * N
         o = _Opto(*[float(job["opto"][n]) for n, _ in _Opto._fields_])

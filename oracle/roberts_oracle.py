@@ -602,3 +602,60 @@ def augmented_rhs(state: np.ndarray, N: int, props: ProblemProperties, v: Optome
     out[2 * N:] = v.Beta * inten - 1.0 / v.Tau * D
     out[N:2 * N] += D
     return out
+
+
+class TimedDrive:
+    """The explicitly time-dependent drive: TimedBoundaryIntegrator<N,1> over HeliumWithOptomechanicalDrivingProblem<N>
+    (L/TimedBoundaryIntegrator.cuh:21-26, L/HeliumWithDrivingBoundaryProblem.cuh:42-45, kernel add_optical_field_drive_terms
+    L/createM.cuh:119-136) with the exponential integrator of DelayedIntensityTermDevice (L/DelayedIntensityTerm.cuh:16-33), and
+    RungeKuttaStepperBase::runStep / runEvolution (L/RK4_Time_Dependent.cuh:145-283, 307-328).  Every point sees the reference
+    time from before the launch (the reference's kernel races on *prev_time; this is the intended reading)."""
+
+    def __init__(self, N: int, props: ProblemProperties, v: OptomechanicalVariables, physics: str = "helium", deriv: str = "cuda"):
+        self.N, self.props, self.v, self.physics, self.deriv = N, props, v, physics, deriv
+        self.delayed = np.zeros(N)
+        self.prev_time = v.initial_time
+        self.t = v.initial_time
+
+    def set_starting_time(self, time: float):
+        self.t = time
+        self.prev_time = time
+
+    def rhs(self, state, time: float, save: bool):
+        N, v = self.N, self.v
+        out = rhs(np.asarray(state, np.complex128), N, 1, self.props, self.physics, self.deriv)
+        Z, w = state[:N], out[:N]
+        inten = light_intensity(Z.imag, Z.real, v)
+        if time == self.prev_time:
+            d = inten.copy()
+        else:
+            a = math.exp(-(time - self.prev_time) / v.Tau)
+            d = a * self.delayed + v.Beta * v.Tau * (1 - a) * inten
+        if save:
+            self.delayed = d
+            self.prev_time = time
+        out[N:] += v.DampingStrength * w.imag
+        out[N:] += v.Beta * d
+        out[N:] += drive_strength(v, self.props) * inten
+        return out
+
+    def step(self, y, h: float):
+        """runStep at the current time (not advanced here, as in the reference)."""
+        half = h * 0.5
+        k1 = self.rhs(y, self.t, True)
+        k2 = self.rhs(y + half * k1, self.t + half, False)
+        k3 = self.rhs(y + half * k2, self.t + half, False)
+        k4 = self.rhs(y + h * k3, self.t + h, False)
+        return y + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+
+    def evolve(self, y, t0: float, t1: float, h: float):
+        """runEvolution: returns (final state, logged times, logged states); a state is logged with the time at the START of its step."""
+        self.set_starting_time(t0)
+        steps = int((t1 - t0) / h)
+        times, states = [], []
+        for _ in range(steps):
+            y = self.step(y, h)
+            times.append(self.t)
+            states.append(y.copy())
+            self.t += h
+        return y, np.array(times), states

@@ -150,6 +150,24 @@ SIGNATURES = {
     "rb_aug_rk4_dev_state": (_P, [_P]),
     "rb_aug_rk4_get_state": (c_int, [_P, _P]),
     "rb_aug_rk4_current_time": (c_double, [_P]),
+    "rb_timed_rk4_create": (_P, [_P, POINTER(rb_opto), c_double]),
+    "rb_timed_rk4_destroy": (c_int, [_P]),
+    "rb_timed_rk4_set_time_step": (c_int, [_P, c_double]),
+    "rb_timed_rk4_initialize": (c_int, [_P, _P, c_int]),
+    "rb_timed_rk4_set_starting_time": (c_int, [_P, c_double]),
+    "rb_timed_rhs": (c_int, [_P, c_double, c_int, _P, _P]),
+    "rb_timed_rk4_step": (c_int, [_P, c_int]),
+    "rb_timed_rk4_evolve": (c_int, [_P, c_double, c_double, POINTER(c_size_t)]),
+    "rb_timed_rk4_set_logging": (c_int, [_P, c_int]),
+    "rb_timed_rk4_copy_trajectory": (c_int, [_P, POINTER(_D), POINTER(c_size_t), POINTER(_P), POINTER(c_size_t)]),
+    "rb_timed_rk4_dev_state": (_P, [_P]),
+    "rb_timed_rk4_dev_delayed_intensity": (_P, [_P]),
+    "rb_timed_rk4_get_state": (c_int, [_P, _P]),
+    "rb_timed_rk4_current_time": (c_double, [_P]),
+    "integrateOptomechanicalSimulationRK4": (c_int, [_D, POINTER(_D), POINTER(c_size_t), POINTER(_D), POINTER(c_size_t),
+                                                     POINTER(SimProperties), POINTER(RK4SolverOptions),
+                                                     POINTER(COptomechanicalVariables), c_size_t]),
+    "integrateOptomechanicalSimulationRK4_freeMemory": (c_int, [_D, _D]),
     "calculateRhsAugmentedOptomechanical": (c_int, [_D, _D, POINTER(SimProperties), POINTER(COptomechanicalVariables), c_size_t]),
     "integrateAugmentedOptomechanicalSimulationRK4": (c_int, [_D, POINTER(_D), POINTER(c_size_t), POINTER(_D), POINTER(c_size_t),
                                                               POINTER(SimProperties), POINTER(RK4SolverOptions),

@@ -384,6 +384,102 @@ class AugmentedBoundaryIntegrator:
         return out
 
 
+class HeliumWithOptomechanicalDrivingProblem(HeliumBoundaryProblem):
+    """HeliumWithOptomechanicalDrivingProblem<N>(ProblemProperties&, OptomechanicalVariables), L/HeliumWithDrivingBoundaryProblem.cuh:7-67:
+    the explicitly time-dependent drive (delayed intensity advanced by an exponential integrator, L/DelayedIntensityTerm.cuh)."""
+
+    def __init__(self, properties: ProblemProperties, variables: OptomechanicalVariables):
+        super().__init__(properties)
+        self.variables = variables
+
+
+class TimedBoundaryIntegrator(BaseBoundaryIntegralCalculator):
+    """TimedBoundaryIntegrator<N,B>(ProblemProperties&, TimedBoundaryProblem&), L/TimedBoundaryIntegrator.cuh:8-49."""
+
+    def __init__(self, N, batchSize, problemProperties, boundaryProblem: HeliumWithOptomechanicalDrivingProblem, **kw):
+        super().__init__(N, batchSize, problemProperties, boundaryProblem, **kw)
+        self.variables = boundaryProblem.variables
+        if self.variables.drive_strength is None:
+            self.variables.set_drive_strength(problemProperties.rho)
+
+
+class RungeKuttaStepper:
+    """RungeKuttaStepper<std_complex, 2N>(TimedProblem&, tstep), L/RK4_Time_Dependent.cuh:18-460.  As in the reference runStep()
+    does not advance the time (runEvolution's loop does); runStep(advance=True) adds that `currentTime += timeStep`."""
+
+    def __init__(self, timedProblem: TimedBoundaryIntegrator, tstep: float = 1e-2):
+        self.problem = timedProblem
+        self.lib = timedProblem.lib
+        v = timedProblem.variables._c()
+        self.handle = self.lib.rb_timed_rk4_create(timedProblem.handle, ctypes.byref(v), float(tstep))
+        if not self.handle:
+            raise _lib.RobertsError("rb_timed_rk4_create: " + self.lib.rb_last_error().decode())
+        self._keep = None
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.rb_timed_rk4_destroy(h)
+
+    def setTimeStep(self, tstep):
+        check(self.lib.rb_timed_rk4_set_time_step(self.handle, float(tstep)), "rb_timed_rk4_set_time_step")
+
+    def setStartingTime(self, time):
+        check(self.lib.rb_timed_rk4_set_starting_time(self.handle, float(time)), "rb_timed_rk4_set_starting_time")
+
+    def initialize(self, devY0, onDevice=False):
+        if onDevice:
+            self._keep = devY0
+            check(self.lib.rb_timed_rk4_initialize(self.handle, _ptr(devY0), 1), "rb_timed_rk4_initialize")
+        else:
+            host = np.ascontiguousarray(np.asarray(devY0, dtype=np.complex128))
+            check(self.lib.rb_timed_rk4_initialize(self.handle, host.ctypes.data_as(ctypes.c_void_p), 0), "rb_timed_rk4_initialize")
+
+    def run(self, time, saveProgress, state: torch.Tensor, rhs: torch.Tensor):
+        """setCurrentTime(time); setSaveProgress(saveProgress); run(state, rhs)."""
+        check(self.lib.rb_timed_rhs(self.handle, float(time), int(bool(saveProgress)), _ptr(state), _ptr(rhs)), "rb_timed_rhs")
+
+    def runStep(self, _step=0, advance=False):
+        check(self.lib.rb_timed_rk4_step(self.handle, int(bool(advance))), "rb_timed_rk4_step")
+
+    def runEvolution(self, startTime, endTime):
+        n = ctypes.c_size_t()
+        check(self.lib.rb_timed_rk4_evolve(self.handle, float(startTime), float(endTime), ctypes.byref(n)), "rb_timed_rk4_evolve")
+        return n.value
+
+    def getState(self):
+        host = np.empty(2 * self.problem.N * self.problem.batchSize, np.complex128)
+        check(self.lib.rb_timed_rk4_get_state(self.handle, host.ctypes.data_as(ctypes.c_void_p)), "rb_timed_rk4_get_state")
+        return host
+
+    def setOptions(self, initial_timestep, returnTrajectory=True):
+        """RK4Options{initial_timestep, returnTrajectory} (L/RK4Options.h)."""
+        self.setTimeStep(initial_timestep)
+        check(self.lib.rb_timed_rk4_set_logging(self.handle, int(bool(returnTrajectory))), "rb_timed_rk4_set_logging")
+
+    def copyTrajectory(self):
+        """copyTimesToHost + copyStatesToHost: (times, states [count x 2 N B])."""
+        tp, tc = ctypes.POINTER(ctypes.c_double)(), ctypes.c_size_t()
+        sp, sc = ctypes.c_void_p(), ctypes.c_size_t()
+        check(self.lib.rb_timed_rk4_copy_trajectory(self.handle, ctypes.byref(tp), ctypes.byref(tc), ctypes.byref(sp), ctypes.byref(sc)),
+              "rb_timed_rk4_copy_trajectory")
+        n = 2 * self.problem.N * self.problem.batchSize
+        times = np.ctypeslib.as_array(tp, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
+        buf = ctypes.cast(sp, ctypes.POINTER(ctypes.c_double))
+        states = np.ctypeslib.as_array(buf, shape=(sc.value, 2 * n)).copy().view(np.complex128) if sc.value else np.zeros((0, n), np.complex128)
+        if tc.value:
+            self.lib.rb_free(ctypes.cast(tp, ctypes.c_void_p))
+        self.lib.rb_free(sp)
+        return times, states
+
+    def delayedIntensity(self):
+        return _view(self.lib.rb_timed_rk4_dev_delayed_intensity(self.handle), self.problem.N * self.problem.batchSize,
+                     self.problem.device)
+
+    def currentTime(self):
+        return self.lib.rb_timed_rk4_current_time(self.handle)
+
+
 class AugmentedRungeKuttaStepper:
     """AutonomousRungeKuttaStepper<std_complex, 3N>(AugmentedBoundaryIntegrator&, tstep) (A/kernel.cu:85-96)."""
 
@@ -669,4 +765,20 @@ def integrateAugmentedOptomechanicalSimulationRK4(initialState, simProperties, r
     states = np.ctypeslib.as_array(so, shape=(sc.value, 4 * N)).copy() if sc.value else np.zeros((0, 4 * N))
     times = np.ctypeslib.as_array(to, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
     lib.integrateAugmentedOptomechanicalSimulationRK4_freeMemory(so, to)
+    return states, times
+
+
+def integrateOptomechanicalSimulationRK4(initialState, simProperties, rkOptions, optomechanicalVariables, N):
+    """L/Export.cuh:72: RK4 evolution with the explicitly time-dependent drive; returns (states [count x 3N], times)."""
+    lib = _lib.load()
+    st = np.ascontiguousarray(initialState, np.float64)
+    so, to = ctypes.POINTER(ctypes.c_double)(), ctypes.POINTER(ctypes.c_double)()
+    sc, tc = ctypes.c_size_t(), ctypes.c_size_t()
+    check(lib.integrateOptomechanicalSimulationRK4(_dp(st), ctypes.byref(so), ctypes.byref(sc), ctypes.byref(to), ctypes.byref(tc),
+                                                   ctypes.byref(simProperties), ctypes.byref(rkOptions),
+                                                   ctypes.byref(optomechanicalVariables), int(N)),
+          "integrateOptomechanicalSimulationRK4")
+    states = np.ctypeslib.as_array(so, shape=(sc.value, 3 * N)).copy() if sc.value else np.zeros((0, 3 * N))
+    times = np.ctypeslib.as_array(to, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
+    lib.integrateOptomechanicalSimulationRK4_freeMemory(so, to)
     return states, times

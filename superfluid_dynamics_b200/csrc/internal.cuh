@@ -248,6 +248,8 @@ void launch_final_update(double2* y0, const double2* k1, const double2* k2, cons
 #ifdef ROBERTS_B200_H
 void launch_light_intensity(const double2* Z, double* out, const rb_opto& v, size_t n, cudaStream_t st);
 void launch_augmented_terms(const double2* state, double2* rhs, const rb_opto& v, size_t BN, cudaStream_t st);
+void launch_timed_drive(double2* rhs_phi, const double2* Z, const double2* w, double* delayed, const rb_opto& v, double time,
+                        double prev_time, int save, size_t BN, cudaStream_t st);
 #endif
 // rk45_kernels.cu
 void launch_rk45_stage(const double2* y, const double2* const k[5], double2* out, const double c[5], int nk, size_t n,

@@ -298,6 +298,106 @@ static void test_augmented() {
     std::printf("Augmented optomechanical system (App pattern): failures so far %d, |D - analytic| = %.3e, max |Phi| = %.3e\n", failures, dmax, moved);
 }
 
+// The explicitly time-dependent drive, assembled as L/Export.cu:797-826 / A/kernel.cu:281-366: a flat film at rest feels
+//   dPhi/dt = Beta * D(t) + drive_strength * I(x),   D(t0) = I,   D(t) = a D_saved + Beta Tau (1 - a) I,  a = exp(-(t - t_saved)/Tau)
+static void test_timed_drive() {
+    constexpr int N = 128;
+    ProblemProperties properties;
+    properties.depth = 0.0942478;
+    properties.rho = 1;
+    OptomechanicalVariables opto;
+    opto.Beta = 2e-33;
+    opto.detuning = 0.5;
+    opto.G = 3.0;
+    opto.gamma = 2.0;
+    opto.location_x0_mode = PI_d;
+    opto.sigma_optical_mode = 0.8;
+    opto.max_intensity = 1e32;
+    opto.Tau = 0.7;
+    opto.DampingStrength = 0.01;
+    std::vector<std_complex> y0(2 * N), rhs(2 * N);
+    std::vector<double> inten(N);
+    double imax = 0;
+    for (int i = 0; i < N; i++) {
+        const double x = 2.0 * PI_d * i / N;
+        y0[i] = std_complex(x, 0.0);
+        y0[N + i] = 0.0;
+        inten[i] = 0.25 * opto.gamma * opto.gamma * opto.max_intensity / (opto.detuning * opto.detuning + 0.25 * opto.gamma * opto.gamma) *
+                   std::exp(-(x - opto.location_x0_mode) * (x - opto.location_x0_mode) / (2 * opto.sigma_optical_mode * opto.sigma_optical_mode));
+        imax = std::max(imax, inten[i]);
+    }
+    HeliumWithOptomechanicalDrivingProblem<N> heliumProblem(properties, opto);
+    TimedBoundaryIntegrator<N, 1> integrator(properties, heliumProblem);
+    std_complex *dState = nullptr, *dRhs = nullptr;
+    cudaMalloc(&dState, 2 * N * sizeof(std_complex));
+    cudaMalloc(&dRhs, 2 * N * sizeof(std_complex));
+    cudaMemcpy(dState, y0.data(), 2 * N * sizeof(std_complex), cudaMemcpyHostToDevice);
+    const double strength = 1.054571817e-34 / (properties.base_energy * properties.base_time * properties.rho) * opto.G /
+                            (opto.sigma_optical_mode * opto.sigma_optical_mode);
+    const double t0 = 0.5, dt = 1e-3;
+    // first call at the starting time: D = I, saved; a later call without saving decays it and leaves the saved value alone
+    integrator.setStartingTime(t0);
+    integrator.setSaveProgress(true);
+    integrator.run(dState, dRhs);
+    cudaDeviceSynchronize();
+    cudaMemcpy(rhs.data(), dRhs, 2 * N * sizeof(std_complex), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < N; i++) {
+        EXPECT_NEAR(std::hypot(rhs[i].real(), rhs[i].imag()), 0.0, 1e-12, "flat film at rest does not move (timed)");
+        EXPECT_NEAR(rhs[N + i].real(), (opto.Beta + strength) * inten[i], 1e-12, "timed dPhi/dt at the starting time");
+    }
+    integrator.setCurrentTime(t0 + 0.1);
+    integrator.setSaveProgress(false);
+    integrator.run(dState, dRhs);
+    cudaDeviceSynchronize();
+    cudaMemcpy(rhs.data(), dRhs, 2 * N * sizeof(std_complex), cudaMemcpyDeviceToHost);
+    std::vector<double> dsaved(N);
+    cudaMemcpy(dsaved.data(), integrator.delayedIntensity(), N * sizeof(double), cudaMemcpyDeviceToHost);
+    const double a1 = std::exp(-0.1 / opto.Tau);
+    for (int i = 0; i < N; i++) {
+        const double d = a1 * inten[i] + opto.Beta * opto.Tau * (1 - a1) * inten[i];
+        EXPECT_NEAR(rhs[N + i].real(), opto.Beta * d + strength * inten[i], 1e-12, "timed dPhi/dt with a decayed delayed intensity");
+        EXPECT_NEAR(dsaved[i] / imax, inten[i] / imax, 1e-14, "saveProgress = false leaves the saved delayed intensity alone");
+    }
+    // evolution with the trajectory: 10 steps from t0, times logged at the START of each step
+    RungeKuttaStepper<std_complex, 2 * N> stepper(integrator);
+    RK4Options options;
+    options.initial_timestep = dt;
+    options.returnTrajectory = true;
+    stepper.setOptions(options);
+    stepper.initialize(dState, true);
+    stepper.runEvolution(t0, t0 + 10.5 * dt);
+    double* times = nullptr;
+    size_t nt = 0, ns = 0;
+    std_complex* states = nullptr;
+    stepper.copyTimesToHost(&times, &nt);
+    stepper.copyStatesToHost(&states, &ns);
+    EXPECT_NEAR((double)nt, 10.0, 0.0, "ten times logged");
+    EXPECT_NEAR((double)ns, 10.0, 0.0, "ten states logged");
+    for (size_t i = 0; i < nt && i < 10; i++) EXPECT_NEAR(times[i], t0 + i * dt, 1e-12, "time at the start of the step");
+    std::vector<std_complex> y(2 * N);
+    stepper.getState(y.data());
+    double moved = 0, dmax = 0, last = 0;
+    cudaMemcpy(dsaved.data(), integrator.delayedIntensity(), N * sizeof(double), cudaMemcpyDeviceToHost);
+    const double a9 = std::exp(-9 * dt / opto.Tau);
+    for (int i = 0; i < N; i++) {
+        moved = std::max(moved, std::abs(y[N + i].real()));
+        if (ns == 10) last = std::max(last, std::fabs(states[9 * 2 * N + N + i].real() - y[N + i].real()));
+        // the first step saves D = I at t0, the nine later ones decay it towards Beta Tau I (the film has barely moved)
+        const double expect = a9 * inten[i] + opto.Beta * opto.Tau * (1 - a9) * inten[i];
+        dmax = std::max(dmax, std::abs(dsaved[i] - expect) / imax);
+    }
+    EXPECT_NEAR(dmax, 0.0, 1e-4, "delayed intensity follows the exponential integrator");
+    EXPECT_NEAR(last, 0.0, 0.0, "last logged state is the current state");
+    EXPECT_NEAR(moved > 1e-4 ? 1.0 : 0.0, 1.0, 0.5, "the timed drive has acted on the potential");
+    EXPECT_NEAR(stepper.getCurrentTime(), t0 + 10 * dt, 1e-12, "current time after the evolution");
+    rb_free(times);
+    rb_free(states);
+    cudaFree(dState);
+    cudaFree(dRhs);
+    std::printf("Time-dependent optomechanical drive (Export pattern): failures so far %d, |D - analytic|/max I = %.3e, max |Phi| = %.3e\n",
+                failures, dmax, moved);
+}
+
 int main() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -312,6 +412,7 @@ int main() {
     test_stepper();
     test_rk45();
     test_augmented();
+    test_timed_drive();
     std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
     return failures ? 1 : 0;
 }

@@ -70,9 +70,15 @@ AUG_CASES = [
     _case("aug_rk4_N64_100", "aug_rk4", "helium", 64, 0.1, surface="film", depth=0.0942478, rho=1.0, dt=1e-3, steps=100),
     _case("aug_rk4_N256_100", "aug_rk4", "helium", 256, 0.1, surface="film", depth=0.0942478, rho=1.0, dt=1e-3, steps=100),
 ]
-for _c in AUG_CASES:
+# the same drive in its explicitly time-dependent form (RK4_Time_Dependent.cuh): state [Z | Phi], delayed intensity inside the stepper
+TIMED_CASES = [
+    _case("timed_rk4_N64_100", "timed_rk4", "helium", 64, 0.1, surface="film", depth=0.0942478, rho=1.0, dt=1e-3, steps=100, t0=0.0),
+    _case("timed_rk4_N256_100_t0", "timed_rk4", "helium", 256, 0.1, surface="film", depth=0.0942478, rho=1.0, dt=1e-3, steps=100, t0=0.25),
+    _case("timed_rk4_N1024_20", "timed_rk4", "helium", 1024, 0.1, surface="film", depth=0.0942478, rho=1.0, dt=1e-3, steps=20, t0=0.0),
+]
+for _c in AUG_CASES + TIMED_CASES:
     _c["opto"] = dict(OPTO)
-CASES = CASES + AUG_CASES
+CASES = CASES + AUG_CASES + TIMED_CASES
 
 
 def state_of(case):
@@ -91,7 +97,9 @@ def reference_results(cases=CASES, timeout=420):
         j = dict(op=c["op"], kind=c["physics"], N=c["N"], props=c["props"], state=state_of(c))
         if c["op"] in ("rk4", "aug_rk4"):
             j.update(dt=c["dt"], steps=c["steps"], warmup=0)
-        if c["op"].startswith("aug"):
+        if c["op"] == "timed_rk4":
+            j.update(dt=c["dt"], steps=c["steps"], t0=c["t0"])
+        if c["op"].startswith("aug") or c["op"] == "timed_rk4":
             j["opto"] = c["opto"]
         jobs.append(j)
     res = ref_runner.run_jobs(jobs, timeout=timeout)
@@ -118,6 +126,21 @@ def measure(api, case, ref, torch):
     y0 = state_of(case)
     dev = torch.device("cuda:0")
     out = {}
+    if case["op"] == "timed_rk4":
+        p = case["props"]
+        props = api.ProblemProperties(rho=p["rho"], kappa=p["kappa"], depth=p["depth"])
+        variables = api.OptomechanicalVariables(**case["opto"])
+        integrator = api.TimedBoundaryIntegrator(N, 1, props, api.HeliumWithOptomechanicalDrivingProblem(props, variables), guess="warm")
+        stp = api.RungeKuttaStepper(integrator, case["dt"])
+        stp.initialize(y0, False)
+        n = stp.runEvolution(case["t0"], case["t0"] + (case["steps"] + 0.5) * case["dt"])
+        y = stp.getState()
+        out["steps_taken"] = int(n)
+        out["position"] = rel(y[:N], ref["state"][:N])
+        out["potential"] = rel(y[N:], ref["state"][N:])
+        out["reference_steps_per_s"] = case["steps"] / ref["seconds"] if ref.get("seconds") else None
+        out["converged"] = bool(integrator.solve_stats()["converged"])
+        return out
     if case["op"].startswith("aug"):
         p = case["props"]
         props = api.ProblemProperties(rho=p["rho"], kappa=p["kappa"], depth=p["depth"])

@@ -706,3 +706,77 @@ def test_augmented_rk4_and_legacy_exports_match_oracle(api):
     opts.returnTrajectory = False
     final, t2 = api.integrateAugmentedOptomechanicalSimulationRK4(flat, sp, opts, cv, N)
     assert final.shape == (1, 4 * N) and len(t2) == 0 and rel(final[0], states[-1]) <= 1e-13
+
+
+def test_time_dependent_drive_matches_oracle(api):
+    """rb_timed_* vs the oracle's TimedDrive (L/createM.cuh:119-136, L/DelayedIntensityTerm.cuh:16-33, L/RK4_Time_Dependent.cuh):
+    one timed RHS with and without saving, runStep's un-advanced time, runEvolution with a starting time, the delayed-intensity
+    buffer, and integrateOptomechanicalSimulationRK4 with SI inputs (times logged at the start of each step)."""
+    from superfluid_dynamics_b200 import _lib
+    N, depth, dt = 128, 0.0942478, 1e-3
+    props = api.ProblemProperties(rho=1.0, depth=depth)
+    oprops = ro.ProblemProperties(rho=1.0, depth=depth)
+    v = api.OptomechanicalVariables(**OPTO)
+    ov = ro.OptomechanicalVariables(**OPTO)
+    y0 = _film_state(N, depth)[:2 * N]
+    integ = api.TimedBoundaryIntegrator(N, 1, props, api.HeliumWithOptomechanicalDrivingProblem(props, v), guess="warm")
+    stp = api.RungeKuttaStepper(integ, dt)
+    td = ro.TimedDrive(N, oprops, ov)
+    # RHS level: first call at t == starting time takes D = I and saves it; a later call decays it
+    stp.setStartingTime(0.3)
+    td.set_starting_time(0.3)
+    out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+    for time, save in ((0.3, True), (0.3005, False), (0.301, True), (0.3015, False)):
+        stp.run(time, save, T(y0), out)
+        e = td.rhs(y0, time, save)
+        assert rel(out.cpu().numpy()[:N], e[:N]) <= 1e-10 and rel(out.cpu().numpy()[N:], e[N:]) <= 1e-10, (time, save)
+        assert rel(stp.delayedIntensity().cpu().numpy(), td.delayed) <= 1e-14
+    # runStep does not advance the time; runStep(advance=True) does
+    stp.initialize(y0, False)
+    stp.setStartingTime(0.0)
+    td.set_starting_time(0.0)
+    stp.runStep()
+    assert stp.currentTime() == 0.0
+    y1 = td.step(y0, dt)
+    assert rel(stp.getState(), y1) <= 1e-10
+    # evolution from a starting time, with the trajectory (time logged at the START of each step)
+    stp.initialize(y0, False)
+    stp.setOptions(dt, returnTrajectory=True)
+    assert stp.runEvolution(0.25, 0.25 + 30.5 * dt) == 30
+    ye, times, states = ro.TimedDrive(N, oprops, ov).evolve(y0, 0.25, 0.25 + 30.5 * dt, dt)
+    y = stp.getState()
+    assert rel(y[:N], ye[:N]) <= 1e-9 and rel(y[N:], ye[N:]) <= 1e-9
+    assert abs(stp.currentTime() - (0.25 + 30 * dt)) <= 1e-12
+    lt, ls = stp.copyTrajectory()
+    assert len(lt) == 30 and np.abs(lt - times).max() <= 1e-12 and ls.shape == (30, 2 * N)
+    assert rel(ls[4], states[4]) <= 1e-9 and np.array_equal(ls[-1], y)
+    stp.setOptions(dt, returnTrajectory=False)
+    lt, ls = stp.copyTrajectory()
+    assert len(lt) == 0 and ls.shape == (1, 2 * N) and np.array_equal(ls[0], y)
+
+    # legacy export, SI in
+    L, d_si = 1e-6, 15e-9
+    sp = _lib.SimProperties(L=L, rho=150.0, kappa=0.0, depth=d_si, use_expansions=False, expansion_order=1, infinite_depth=False)
+    op_si = ro.adimensionalize_properties(ro.ProblemProperties(L=L, rho=150.0, kappa=0.0, depth=d_si))
+    cv = _lib.COptomechanicalVariables(detuning=0.5 / op_si.base_time, gamma=2.0 / op_si.base_time,
+                                       G=3.0 / (op_si.base_time * op_si.base_length), tau=0.7 * op_si.base_time, max_intensity=5e7,
+                                       initial_time=0.0, location_x0_mode=3.0 * op_si.base_length,
+                                       sigma_optical_mode=0.8 * op_si.base_length, beta=1.0, damping_strength=0.01)
+    ov_si = ro.adimensionalize_optomechanical(
+        ro.OptomechanicalVariables(detuning=cv.detuning, gamma=cv.gamma, G=cv.G, Tau=cv.tau, max_intensity=cv.max_intensity,
+                                   location_x0_mode=cv.location_x0_mode, sigma_optical_mode=cv.sigma_optical_mode, Beta=cv.beta,
+                                   DampingStrength=cv.damping_strength), op_si)
+    ys = _film_state(N, op_si.depth)[:2 * N]
+    flat = np.concatenate([ys[:N].real, ys[:N].imag, ys[N:].real])
+    opts = _lib.RK4SolverOptions(timeStep=1e-3 * op_si.base_time, t0=0.1 * op_si.base_time, t1=0.1105 * op_si.base_time,
+                                 returnTrajectory=True)
+    states, times = api.integrateOptomechanicalSimulationRK4(flat, sp, opts, cv, N)
+    yo, to, so = ro.TimedDrive(N, op_si, ov_si).evolve(ys, 0.1, 0.1105, 1e-3)
+    assert states.shape == (10, 3 * N) and len(times) == 10
+    assert np.abs(times - to).max() <= 1e-12 and abs(times[0] - 0.1) <= 1e-12      # time at the START of each step
+    expf = np.concatenate([yo[:N].real, yo[:N].imag, yo[N:].real])
+    for blk in range(3):
+        assert rel(states[-1][blk * N:(blk + 1) * N], expf[blk * N:(blk + 1) * N]) <= 1e-9, blk
+    opts.returnTrajectory = False
+    final, t2 = api.integrateOptomechanicalSimulationRK4(flat, sp, opts, cv, N)
+    assert final.shape == (1, 3 * N) and len(t2) == 0 and rel(final[0], states[-1]) <= 1e-13

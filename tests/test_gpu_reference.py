@@ -78,6 +78,16 @@ def test_augmented_optomechanical_system_matches_the_reference(api, reference, c
         assert m[k] <= 1e-9, (k, m)
 
 
+@pytest.mark.parametrize("case", [c for c in ref_cases.CASES if c["op"] == "timed_rk4"], ids=lambda c: c["name"])
+def test_time_dependent_drive_matches_the_reference(api, reference, case):
+    """RungeKuttaStepper<std_complex, 2N>::runEvolution over TimedBoundaryIntegrator / HeliumWithOptomechanicalDrivingProblem
+    (L/RK4_Time_Dependent.cuh:307-328, assembled as L/Export.cu:797-826) against rb_timed_rk4_evolve, incl. a non-zero starting
+    time.  1e-9 (thin film)."""
+    m = ref_cases.measure(api, case, _ref(reference, case), torch)
+    assert m["converged"] and m["steps_taken"] == case["steps"]
+    assert m["position"] <= 1e-9 and m["potential"] <= 1e-9, m
+
+
 @pytest.mark.parametrize("case", [c for c in ref_cases.CASES if c["op"] == "rk4"], ids=lambda c: c["name"])
 def test_rk4_steps_match_the_reference_stepper(api, reference, case):
     """AutonomousRungeKuttaStepper<std_complex, 2N>::runStep (L/AutonomousRungeKuttaStepper.cuh:124-307) driven as
