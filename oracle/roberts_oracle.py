@@ -659,3 +659,190 @@ class TimedDrive:
             states.append(y.copy())
             self.t += h
         return y, np.array(times), states
+
+
+# --------------------------------------------------------------------------
+# real-state wrapper, finite-difference Jacobian, implicit Gauss-Legendre-2 integrator
+# --------------------------------------------------------------------------
+def real_to_complex_state(y: np.ndarray, N: int) -> np.ndarray:
+    """convertToComplexStateKernel / createInitialState (L/RealBoundaryIntegralCalculator.cuh:4-12, L/JacobianCalculator.cuh:159-166):
+    [x | y | phi] (3N doubles) -> [x + i y | phi + 0 i] (2N complex)."""
+    y = np.asarray(y, np.float64)
+    out = np.empty(2 * N, np.complex128)
+    out[:N] = y[:N] + 1j * y[N:2 * N]
+    out[N:] = y[2 * N:3 * N]
+    return out
+
+
+def complex_to_real_rhs(r: np.ndarray, N: int) -> np.ndarray:
+    """convertToRealRhsKernel (L/RealBoundaryIntegralCalculator.cuh:14-23): [w | dPhi/dt] -> [Re w | Im w | Re dPhi/dt]."""
+    return np.concatenate([r[:N].real, r[:N].imag, r[N:2 * N].real])
+
+
+def real_rhs(y: np.ndarray, N: int, props: ProblemProperties, physics: str = "helium", deriv: str = "cuda") -> np.ndarray:
+    """RealBoundaryItegralCalculator<N>::run (L/RealBoundaryIntegralCalculator.cuh:59-70)."""
+    return complex_to_real_rhs(rhs(real_to_complex_state(y, N), N, 1, props, physics, deriv), N)
+
+
+def perturbed_states(state: np.ndarray, N: int, eps: float) -> np.ndarray:
+    """createInitialBatchedZ (L/JacobianCalculator.cuh:11-77): 3N copies of the complex state [Z | Phi] in the batched layout
+    [Z of member 0 .. Z of member 3N-1 | Phi of member 0 ..]; member b = c N + j has coordinate c (0: x, 1: y, 2: phi) of
+    point j moved by eps."""
+    state = np.asarray(state, np.complex128)
+    B = 3 * N
+    out = np.empty(2 * B * N, np.complex128)
+    Zb = out[:B * N].reshape(B, N)
+    Pb = out[B * N:].reshape(B, N)
+    Zb[:] = state[:N]
+    Pb[:] = state[N:]
+    j = np.arange(N)
+    Zb[j, j] += eps
+    Zb[N + j, j] += 1j * eps
+    Pb[2 * N + j, j] += eps
+    return out
+
+
+def jacobian_fd(y: np.ndarray, N: int, props: ProblemProperties, physics: str = "helium", eps: float = 1e-6, deriv: str = "cuda") -> np.ndarray:
+    """JacobianCalculator<N>::calculateJacobian (L/JacobianCalculator.cuh:226-284) with createJacobianMatrixFromPerturbedRhs
+    (:92-156): central differences of the batched RHS (batch = 3N) at +-eps.  Returns J[r, c] = d f_r / d y_c as a (3N, 3N) array;
+    the reference's buffer is its column-major flattening, `J.ravel(order="F")` (C[c * 3N + r])."""
+    s = real_to_complex_state(y, N)
+    B = 3 * N
+    pos = rhs(perturbed_states(s, N, eps), N, B, props, physics, deriv)
+    neg = rhs(perturbed_states(s, N, -eps), N, B, props, physics, deriv)
+    d = (pos - neg) / (2.0 * eps)
+    J = np.empty((3 * N, 3 * N))
+    w = d[:B * N].reshape(B, N)       # member c: velocity rows
+    p = d[B * N:].reshape(B, N)       # member c: dPhi/dt rows
+    J[:N, :] = w.real.T
+    J[N:2 * N, :] = w.imag.T
+    J[2 * N:, :] = p.real.T
+    return J
+
+
+SQRT3 = 1.7320508075688772935  # L/GLCoefficients.hpp:3
+GL_A = ((0.25, 0.25 - SQRT3 / 6.0), (0.25 + SQRT3 / 6.0, 0.25))   # L/GLCoefficients.hpp:7-10
+GL_B = (0.5, 0.5)
+
+
+@dataclasses.dataclass
+class GaussLegendre2Options:
+    """GaussLegendre2Options (L/GaussLegendre.cuh:70-90; its constructor sets allowSimplifiedFallback = false) and the C struct
+    GaussLegendreOptions (L/ExportTypes.cuh:20-33)."""
+    stepSize: float = 0.01
+    newtonTolerance: float = 1e-10
+    maxNewtonIterations: int = 20
+    allowSimplifiedFallback: bool = False
+    returnTrajectory: bool = True
+    armijo_c: float = 1e-4
+    backtrack: float = 0.5
+    minAlpha: float = 1e-6
+    maxStepsHalves: int = 6
+
+
+def gl2_newton_matrix(J1: np.ndarray, J2: np.ndarray, h: float) -> np.ndarray:
+    """Jacobian of the stage residual R_i = k_i - f(y + h sum_j a_ij k_j): block (i, j) = delta_ij I - h a_ij J_i
+    (P/integration/gauss_legendre.py:40-52).  The CUDA fillMMatrix (L/GaussLegendre.cuh:42-51) stores, read column-major as its
+    LU does, the blocks (1,2) = -h a21 J1 and (2,1) = -h a12 J2, i.e. with the two off-diagonal coefficients exchanged (an inexact
+    Newton matrix; the fixed point is the same) and is launched with grid and block exchanged (:483), which fails for 3N/16 > 32;
+    the Python statement is followed here."""
+    m = J1.shape[0]
+    I = np.eye(m)
+    M = np.empty((2 * m, 2 * m))
+    M[:m, :m] = I - h * GL_A[0][0] * J1
+    M[:m, m:] = -h * GL_A[0][1] * J1
+    M[m:, :m] = -h * GL_A[1][0] * J2
+    M[m:, m:] = I - h * GL_A[1][1] * J2
+    return M
+
+
+def gl2_step(f, J, y: np.ndarray, h: float, opt: GaussLegendre2Options):
+    """GaussLegendre2<N>::gaussLegendreS2Step (L/GaussLegendre.cuh:441-560) == gauss_legendre_s2_step
+    (P/integration/gauss_legendre.py:55-170): damped Newton on the two stage slopes with Armijo backtracking on
+    phi = |R|^2 / 2 and an optional switch to a Jacobian frozen at the base point.  Where the two statements differ the Python one
+    (the intended algorithm) is followed: residual and its norm over BOTH stages (the CUDA cublasDdot runs over 3N of the 6N
+    entries, :606), tolerance relative to 1 + |k| (CUDA: 1 + |k|^2, :607/:469), stage states from the slopes being tested (the CUDA
+    stageStates reads the member buffers k1/k2 whatever slopes residualAndPhi was given, :580-586).  Returns
+    (y_next or None, info)."""
+    y = np.asarray(y, np.float64)
+    m = y.size
+    fy = f(y)
+    k = np.stack([fy, fy.copy()])
+
+    def residual_and_phi(k_):
+        y1 = y + h * (GL_A[0][0] * k_[0] + GL_A[0][1] * k_[1])
+        y2 = y + h * (GL_A[1][0] * k_[0] + GL_A[1][1] * k_[1])
+        R = np.concatenate([k_[0] - f(y1), k_[1] - f(y2)])
+        return R, 0.5 * float(R @ R), y1, y2
+
+    simplified, converged, freeze, Jf = False, False, False, None
+    it = 0
+    res_norm = float("nan")
+    for it in range(opt.maxNewtonIterations):
+        R, phi, y1, y2 = residual_and_phi(k)
+        res_norm = math.sqrt(2.0 * phi)
+        if res_norm <= opt.newtonTolerance * (1.0 + float(np.linalg.norm(k))):
+            converged = True
+            break
+        J1, J2 = (Jf, Jf) if freeze else (J(y1), J(y2))
+        dK = np.linalg.solve(gl2_newton_matrix(J1, J2, h), -R)
+        alpha = 1.0
+        target = phi - opt.armijo_c * alpha * res_norm ** 2
+        while True:
+            kt = np.stack([k[0] + alpha * dK[:m], k[1] + alpha * dK[m:]])
+            _, phit, _, _ = residual_and_phi(kt)
+            if phit <= target:
+                k = kt
+                break
+            alpha *= opt.backtrack
+            target = phi - opt.armijo_c * alpha * res_norm ** 2
+            if alpha < opt.minAlpha:
+                if not freeze and opt.allowSimplifiedFallback:
+                    freeze, simplified = True, True
+                    Jf = J(y)
+                    break
+                return None, dict(nit=it, converged=False, res_norm=res_norm, simplified_used=simplified)
+    else:
+        it = opt.maxNewtonIterations
+    if not converged:
+        R, phi, _, _ = residual_and_phi(k)
+        res_norm = math.sqrt(2.0 * phi)
+    y_next = y + h * (GL_B[0] * k[0] + GL_B[1] * k[1])
+    return y_next, dict(nit=it, converged=converged, res_norm=res_norm, simplified_used=simplified)
+
+
+def gl2_integrate(f, J, y0: np.ndarray, t0: float, t1: float, opt: GaussLegendre2Options):
+    """GaussLegendre2<N>::runEvolution (L/GaussLegendre.cuh:216-299) == integrate_gl2 (P/integration/gauss_legendre.py:173-267): steps of
+    min(stepSize, |t1 - t|) in the direction of t1; a step whose Newton iteration fails is retried with half the size, at most
+    maxStepsHalves times and not below |t1 - t0| / 2^20, and the reduced size is kept for the following steps.  The trajectory
+    starts with (t0, y0).  Returns (times, states) -- with returnTrajectory off, ([], [final state])."""
+    if opt.stepSize < 0.0:
+        raise ValueError("Step size must be positive.")
+    y = np.asarray(y0, np.float64).copy()
+    total = abs(t1 - t0)
+    hmin = total / 2.0 ** 20
+    h = opt.stepSize
+    T, Y = [float(t0)], [y.copy()]
+    t = float(t0)
+    forward = 1.0 if t1 >= t0 else -1.0
+    while (t - t1) * forward < 0.0:
+        htry = min(h, abs(t1 - t)) * forward
+        ok, info = False, None
+        for _ in range(opt.maxStepsHalves + 1):
+            y_next, info = gl2_step(f, J, y, htry, opt)
+            if y_next is not None and info["converged"]:
+                ok = True
+                break
+            if abs(htry) <= hmin:
+                break
+            htry *= 0.5
+        if not ok:
+            raise RuntimeError(f"Gauss-Legendre 2nd Order method failed to converge at t~{t}; residual={info['res_norm']:.3e}; last htry={htry:.3e}")
+        y = y_next
+        t += htry
+        h = abs(htry)
+        T.append(t)
+        Y.append(y.copy())
+    if not opt.returnTrajectory:
+        return np.zeros(0), np.array([y])
+    return np.array(T), np.array(Y)
