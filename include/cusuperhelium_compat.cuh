@@ -417,6 +417,100 @@ public:
     double getCurrentTime() { return rb_timed_rk4_current_time(st_); }
 };
 
+// ---- implicit side: RealBoundaryItegralCalculator<N> (L/RealBoundaryIntegralCalculator.cuh:37-89), JacobianCalculator<N>
+//      (L/JacobianCalculator.cuh:168-284), GaussLegendre2Options / GaussLegendre2<N> (L/GaussLegendre.cuh:70-612), assembled as
+//      L/Export.cu:680-700 ------------------------------------------------------------------------------------------------
+template <size_t N>
+class RealBoundaryItegralCalculator final : public AutonomousProblem<double, 3 * (int)N> {
+    BaseBoundaryIntegralCalculator<(int)N, 1>& calculator_;
+public:
+    explicit RealBoundaryItegralCalculator(BaseBoundaryIntegralCalculator<(int)N, 1>& boundaryIntegralCalculator)
+        : calculator_(boundaryIntegralCalculator) {}
+    void run(double* initialState, double* rhs) override {
+        rb_compat_check(rb_real_rhs(calculator_.handle(), initialState, rhs), "rb_real_rhs");
+    }
+    void setStream(cudaStream_t stream) override { calculator_.setStream(stream); }
+    rb_solver* handle() { return calculator_.handle(); }
+};
+
+// The reference hands the calculator a BaseBoundaryIntegralCalculator<N, 3N> it built itself; here the batch-3N assembler is
+// built inside from the same two arguments that one would have been built from.
+template <size_t N>
+class JacobianCalculator final {
+    rb_jacobian* j_ = nullptr;
+public:
+    JacobianCalculator(ProblemProperties& p, BoundaryProblem<(int)N, 3 * N>& problem) {
+        rb_props rp;
+        rb_default_props(&rp);
+        rp.rho = p.rho; rp.U = p.U; rp.kappa = p.kappa; rp.depth = p.depth;
+        rp.use_expansions = p.use_expansions; rp.expansion_order = p.expansion_order; rp.infinite_depth = p.infinite_depth;
+        rp.physics = problem.physics();
+        j_ = rb_jacobian_create((int)N, &rp);
+        if (!j_) throw std::runtime_error(std::string("rb_jacobian_create: ") + rb_last_error());
+    }
+    ~JacobianCalculator() { rb_jacobian_destroy(j_); }
+    JacobianCalculator(const JacobianCalculator&) = delete;
+    JacobianCalculator& operator=(const JacobianCalculator&) = delete;
+    void setEpsilon(double eps) { rb_compat_check(rb_jacobian_set_epsilon(j_, eps), "rb_jacobian_set_epsilon"); }
+    void setStream(cudaStream_t stream) { rb_compat_check(rb_jacobian_set_stream(j_, stream), "rb_jacobian_set_stream"); }
+    void calculateJacobian(const double* devState, double* devJacobian) {
+        rb_compat_check(rb_jacobian_calculate(j_, devState, devJacobian), "rb_jacobian_calculate");
+    }
+    rb_jacobian* handle() { return j_; }
+};
+
+struct GaussLegendre2Options {
+    double stepSize = 0.01;
+    double newtonTolerance = 1e-10;
+    size_t maxNewtonIterations = 20;
+    bool allowSimplifiedFallback = false;
+    bool returnTrajectory = true;
+    double armijo_c = 1e-4;
+    double backtrack = 0.5;
+    double minAlpha = 1e-6;
+    size_t maxStepsHalves = 6;
+};
+
+template <size_t N>
+class GaussLegendre2 {
+    rb_gl2* g_ = nullptr;
+public:
+    GaussLegendre2(RealBoundaryItegralCalculator<N>& problem, JacobianCalculator<N>& jacobianCalculator,
+                   GaussLegendre2Options options = GaussLegendre2Options()) {
+        rb_gl2_options o;
+        o.stepSize = options.stepSize; o.newtonTolerance = options.newtonTolerance; o.maxNewtonIterations = options.maxNewtonIterations;
+        o.allowSimplifiedFallback = options.allowSimplifiedFallback; o.returnTrajectory = options.returnTrajectory;
+        o.armijo_c = options.armijo_c; o.backtrack = options.backtrack; o.minAlpha = options.minAlpha;
+        o.maxStepsHalves = options.maxStepsHalves;
+        g_ = rb_gl2_create(problem.handle(), jacobianCalculator.handle(), &o);
+        if (!g_) throw std::runtime_error(std::string("rb_gl2_create: ") + rb_last_error());
+    }
+    ~GaussLegendre2() { rb_gl2_destroy(g_); }
+    GaussLegendre2(const GaussLegendre2&) = delete;
+    GaussLegendre2& operator=(const GaussLegendre2&) = delete;
+    void setStream(cudaStream_t) {}   // the integrator works on the stream of its RHS assembler
+    void initialize(double* initialState, bool onDevice = false) {
+        rb_compat_check(rb_gl2_initialize(g_, initialState, onDevice), "rb_gl2_initialize");
+    }
+    OdeSolverResult runEvolution(double startTime, double endTime) {
+        rb_compat_check(rb_gl2_evolve(g_, startTime, endTime), "rb_gl2_evolve");   // throws where the reference throws
+        return OdeSolverResult::ReachedEndTime;
+    }
+    int copyTimesToHost(double** hostTimes, size_t* countHost) {
+        double* states = nullptr; size_t ns = 0;
+        if (rb_gl2_copy_trajectory(g_, hostTimes, countHost, &states, &ns) != 0) return -1;
+        rb_free(states);
+        return 0;
+    }
+    int copyStatesToHost(double** hostStates, size_t* countHost) {
+        double* times = nullptr; size_t nt = 0;
+        if (rb_gl2_copy_trajectory(g_, &times, &nt, hostStates, countHost) != 0) return -1;
+        rb_free(times);
+        return 0;
+    }
+    rb_gl2* handle() { return g_; }
+};
+
 // ---- adaptive RKF45 (L/RK45.cuh): RK45_Options and RK45_std_complex<N> over any AutonomousProblem<std_complex, N> ---------------
 struct RK45_Options {   // L/RK45.cuh:21-27
     double atol = 1e-6;

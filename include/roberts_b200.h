@@ -42,6 +42,8 @@ typedef struct rb_stepper rb_stepper;                         /* opaque: RK4 ste
 typedef struct rb_rk45 rb_rk45;                               /* opaque: adaptive RKF45 stepper (L/RK45.cuh) */
 typedef struct rb_aug_stepper rb_aug_stepper;                 /* opaque: RK4 stepper of the optomechanically driven (augmented) system */
 typedef struct rb_timed_stepper rb_timed_stepper;             /* opaque: RK4 stepper of the explicitly time-dependent drive */
+typedef struct rb_jacobian rb_jacobian;                       /* opaque: finite-difference Jacobian of the real-state RHS (batch 3N) */
+typedef struct rb_gl2 rb_gl2;                                 /* opaque: implicit Gauss-Legendre-2 integrator */
 
 /* physics plugin selector == which BoundaryProblem<N,B> subclass the reference would instantiate */
 enum rb_physics {
@@ -91,6 +93,8 @@ RB_API void rb_default_props(rb_props* p);        /* ProblemProperties defaults,
 RB_API rb_solver* rb_create(int N, int batch, const rb_props* props);            /* ctor  :89-108  */
 RB_API int rb_destroy(rb_solver* s);                                             /* dtor  :111-135 */
 RB_API int rb_set_stream(rb_solver* s, void* cuda_stream);                       /* setStream :37-40 */
+RB_API void* rb_get_stream(rb_solver* s);                                        /* the cudaStream_t every kernel of s is issued on */
+RB_API int rb_get_props(rb_solver* s, rb_props* out, int* N, int* batch);        /* what the solver was created with */
 RB_API int rb_rhs(rb_solver* s, const rb_complex* state_dev, rb_complex* rhs_dev);   /* run / runTimeStep :138-273, 310-314 */
 RB_API int rb_vorticities(rb_solver* s, const rb_complex* state_dev);            /* calculateVorticities :276-306 */
 RB_API double* rb_dev_a(rb_solver* s);                                           /* getDevA   :21-24 */
@@ -259,6 +263,66 @@ RB_API double* rb_timed_rk4_dev_delayed_intensity(rb_timed_stepper* st);        
 RB_API int rb_timed_rk4_get_state(rb_timed_stepper* st, rb_complex* y_host);
 RB_API double rb_timed_rk4_current_time(rb_timed_stepper* st);
 
+/* ---- real-state wrapper, finite-difference Jacobian and the implicit Gauss-Legendre-2 integrator:
+ *      RealBoundaryItegralCalculator<N> (L/RealBoundaryIntegralCalculator.cuh:37-89), JacobianCalculator<N>
+ *      (L/JacobianCalculator.cuh:168-284, kernels :11-166), GaussLegendre2<N> (L/GaussLegendre.cuh:107-612), assembled as
+ *      L/Export.cu:392-518 (calculateJacobian) and :665-739 (integrateSimulationGL2).  Real states are [x | y | phi], 3N doubles. ---- */
+/* RealBoundaryItegralCalculator::run :59-70: s must have batch 1 */
+RB_API int rb_real_rhs(rb_solver* s, const double* state_real_dev, double* rhs_real_dev);
+/* createInitialBatchedZ :11-77: 3N copies of [Z | Phi] (2N complex) in the batched layout [Z of member 0.. | Phi of member 0..]
+   (6 N^2 complex), member c N + j with coordinate c (0 x, 1 y, 2 phi) of point j moved by eps */
+RB_API int rb_perturbed_states(const rb_complex* state_dev, rb_complex* batched_dev, double eps, int N, void* cuda_stream);
+/* JacobianCalculator<N>(std::make_unique<BaseBoundaryIntegralCalculator<N, 3N>>(properties, problem)): owns the batch-3N solver */
+RB_API rb_jacobian* rb_jacobian_create(int N, const rb_props* props);
+RB_API int rb_jacobian_destroy(rb_jacobian* j);
+RB_API int rb_jacobian_set_epsilon(rb_jacobian* j, double eps);                  /* setEpsilon :217-221 (default 1e-6) */
+RB_API int rb_jacobian_set_stream(rb_jacobian* j, void* cuda_stream);            /* setStream :186 */
+RB_API rb_solver* rb_jacobian_solver(rb_jacobian* j);                            /* the batch-3N RHS assembler (statistics, stream) */
+/* calculateJacobian :226-284: central differences of the batched RHS at +-eps; jac_dev is 3N x 3N column-major,
+   jac[c * 3N + r] = d f_r / d y_c (createJacobianMatrixFromPerturbedRhs :92-156) */
+RB_API int rb_jacobian_calculate(rb_jacobian* j, const double* state_real_dev, double* jac_dev);
+
+/* GaussLegendre2Options (L/GaussLegendre.cuh:70-90) */
+typedef struct rb_gl2_options {
+    double stepSize;              /* 0.01 */
+    double newtonTolerance;       /* 1e-10 */
+    size_t maxNewtonIterations;   /* 20 */
+    int allowSimplifiedFallback;  /* 0 (the struct's constructor overrides the member initialiser) */
+    int returnTrajectory;         /* 1 */
+    double armijo_c;              /* 1e-4 */
+    double backtrack;             /* 0.5 */
+    double minAlpha;              /* 1e-6 */
+    size_t maxStepsHalves;        /* 6 */
+} rb_gl2_options;
+/* StepResult (L/GaussLegendre.cuh:176-181) of the last attempted step, plus totals since create */
+typedef struct rb_gl2_stats {
+    size_t numberIterations;      /* Newton iterations of the last attempted step */
+    int converged;
+    double residualNorm;
+    int simplifiedFallbackUsed;
+    size_t steps_accepted, steps_halved, newton_iterations, rhs_evaluations, jacobians, linear_solves;
+} rb_gl2_stats;
+RB_API void rb_gl2_default_options(rb_gl2_options* o);
+/* GaussLegendre2<N>(problem, jacobianCalculator, options): s is the batch-1 RHS assembler behind the real wrapper; both stay
+   caller-owned and are put on s's stream */
+RB_API rb_gl2* rb_gl2_create(rb_solver* s, rb_jacobian* j, const rb_gl2_options* options);
+RB_API int rb_gl2_destroy(rb_gl2* g);
+RB_API int rb_gl2_set_options(rb_gl2* g, const rb_gl2_options* options);
+RB_API int rb_gl2_initialize(rb_gl2* g, double* state, int on_device);           /* initialize :303-321 */
+/* gaussLegendreS2Step :441-560 from the current state with step h: on convergence the state is advanced (and 1 written to
+   *converged); otherwise it is left as it was */
+RB_API int rb_gl2_step(rb_gl2* g, double h, int* converged);
+/* runEvolution :216-299: steps of min(stepSize, |t1 - t|) towards t1 (either direction), halving a failed step at most
+   maxStepsHalves times (never below |t1 - t0| / 2^20) and keeping the reduced size; the trajectory starts with (t0, y0).
+   Returns -1 with "failed to converge" in rb_last_error when a step cannot be completed (the reference throws). */
+RB_API int rb_gl2_evolve(rb_gl2* g, double t0, double t1);
+/* copyTimesToHost / copyStatesToHost :355-401: states_count x 3N doubles; without a trajectory no times and the current state.
+   Buffers are malloc'd; release with rb_free. */
+RB_API int rb_gl2_copy_trajectory(rb_gl2* g, double** times_out, size_t* times_count, double** states_out, size_t* states_count);
+RB_API double* rb_gl2_dev_state(rb_gl2* g);
+RB_API int rb_gl2_get_state(rb_gl2* g, double* state_host);
+RB_API int rb_gl2_get_stats(rb_gl2* g, rb_gl2_stats* out);
+
 /* ---- multi-GPU (new; the reference is single-GPU, L/utilities.cuh:20): contiguous blocks of 256-row cells of every O(N^2)
  *      sweep are owned by one rank each; all ranks keep the full state and exchange result rows by peer stores over NVLink into
  *      a per-rank arena mapped with CUDA IPC.  One process per GPU of one node; ship the handles with any out-of-band channel
@@ -314,6 +378,31 @@ RB_API int integrateSimulationRK4_freeMemory(double* statesOut, double* timesOut
 /* nondimensional variant of the same call (no SI conversion, physics selectable): the plain RK4 path used by bench.py's e2e leg */
 RB_API int rb_integrate_rk4_host(const double* initialState_host, double* finalState_host, size_t N, size_t batch,
                                  const rb_props* props, double dt, size_t steps);
+
+typedef struct GaussLegendreOptions {      /* L/ExportTypes.cuh:20-33 */
+    double t0, t1, stepSize, newtonTolerance;
+    size_t maxNewtonIterations;
+    bool allowSimplifiedFallback;
+    bool returnTrajectory;
+    double armijo_c, backtrack, minAlpha;
+    size_t maxStepsHalves;
+} GaussLegendreOptions;
+/* L/Export.cuh:50, L/Export.cu:392-493: finite-difference Jacobian of the real-state helium RHS.  state = [x | y | phi] (3N
+ * doubles, host), jac = 9 N^2 doubles (host), column-major: jac[c * 3N + r] = d f_r / d y_c.  SI properties are
+ * nondimensionalised inside.  Any N >= 2 (the reference: N = 32 ... 2048 by switch table, no return value outside it, L/Export.cu:495-518). */
+RB_API int calculateJacobian(const double* state, double* jac, double L, double rho, double kappa, double depth, double epsilon,
+                             size_t N);
+/* L/Export.cuh:53, L/Export.cu:600-663: the 3N perturbed copies of the state that calculateJacobian evaluates (N = 256):
+ * Zperturbed = 6 N^2 complex, [Z of member 0 .. Z of member 3N-1 | Phi of member 0 ..] */
+RB_API int calculatePerturbedStates256(const double* x, const double* y, const double* phi, rb_complex* Zperturbed, double L,
+                                       double rho, double kappa, double depth, double epsilon);
+/* L/Export.cuh:66-67, L/Export.cu:665-739: implicit Gauss-Legendre-2 evolution of the helium film.  initialState = [x | y | phi];
+ * t0, t1 and stepSize of the options are used as given (the reference does not nondimensionalise them, :696); *statesOut =
+ * statesCount x 3N doubles starting with the initial state, *timesOut = timesCount doubles; returnTrajectory = false: the final
+ * state, no times.  Any N >= 2 (the reference: 32 ... 1024).  Release with integrateSimulationGL2_freeMemory. */
+RB_API int integrateSimulationGL2(double* initialState, double** statesOut, size_t* statesCount, double** timesOut,
+                                  size_t* timesCount, SimProperties* simProperties, GaussLegendreOptions* glCOptions, size_t N);
+RB_API int integrateSimulationGL2_freeMemory(double* statesOut, double* timesOut);
 
 typedef struct COptomechanicalVariables {   /* L/ExportTypes.cuh:41-57 (SI / laboratory units) */
     double detuning, gamma, G, tau, max_intensity, initial_time, location_x0_mode, sigma_optical_mode, beta, damping_strength;

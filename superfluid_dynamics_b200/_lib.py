@@ -40,6 +40,24 @@ class rb_opto(Structure):                # OptomechanicalVariables, L/Optomechan
                                         "sigma_optical_mode", "Beta", "DampingStrength", "drive_strength")]
 
 
+class rb_gl2_options(Structure):         # GaussLegendre2Options, L/GaussLegendre.cuh:70-90
+    _fields_ = [("stepSize", c_double), ("newtonTolerance", c_double), ("maxNewtonIterations", c_size_t),
+                ("allowSimplifiedFallback", c_int), ("returnTrajectory", c_int), ("armijo_c", c_double), ("backtrack", c_double),
+                ("minAlpha", c_double), ("maxStepsHalves", c_size_t)]
+
+
+class rb_gl2_stats(Structure):           # StepResult, L/GaussLegendre.cuh:176-181 (+ totals)
+    _fields_ = [("numberIterations", c_size_t), ("converged", c_int), ("residualNorm", c_double), ("simplifiedFallbackUsed", c_int),
+                ("steps_accepted", c_size_t), ("steps_halved", c_size_t), ("newton_iterations", c_size_t),
+                ("rhs_evaluations", c_size_t), ("jacobians", c_size_t), ("linear_solves", c_size_t)]
+
+
+class GaussLegendreOptions(Structure):   # L/ExportTypes.cuh:20-33 ; P/integration/rhs.py
+    _fields_ = [("t0", c_double), ("t1", c_double), ("stepSize", c_double), ("newtonTolerance", c_double),
+                ("maxNewtonIterations", c_size_t), ("allowSimplifiedFallback", c_bool), ("returnTrajectory", c_bool),
+                ("armijo_c", c_double), ("backtrack", c_double), ("minAlpha", c_double), ("maxStepsHalves", c_size_t)]
+
+
 class COptomechanicalVariables(Structure):   # L/ExportTypes.cuh:41-57
     _fields_ = [(n, c_double) for n in ("detuning", "gamma", "G", "tau", "max_intensity", "initial_time", "location_x0_mode",
                                         "sigma_optical_mode", "beta", "damping_strength")]
@@ -61,6 +79,8 @@ SIGNATURES = {
     "rb_create": (_P, [c_int, c_int, POINTER(rb_props)]),
     "rb_destroy": (c_int, [_P]),
     "rb_set_stream": (c_int, [_P, _P]),
+    "rb_get_stream": (_P, [_P]),
+    "rb_get_props": (c_int, [_P, POINTER(rb_props), POINTER(c_int), POINTER(c_int)]),
     "rb_rhs": (c_int, [_P, _P, _P]),
     "rb_vorticities": (c_int, [_P, _P]),
     "rb_dev_a": (_P, [_P]),
@@ -174,6 +194,30 @@ SIGNATURES = {
                                                               POINTER(COptomechanicalVariables), c_size_t]),
     "integrateAugmentedOptomechanicalSimulationRK4_freeMemory": (c_int, [_D, _D]),
     "rb_integrate_aug_rk4_host": (c_int, [_D, _D, c_size_t, POINTER(rb_props), POINTER(rb_opto), c_double, c_size_t]),
+    "rb_real_rhs": (c_int, [_P, _P, _P]),
+    "rb_perturbed_states": (c_int, [_P, _P, c_double, c_int, _P]),
+    "rb_jacobian_create": (_P, [c_int, POINTER(rb_props)]),
+    "rb_jacobian_destroy": (c_int, [_P]),
+    "rb_jacobian_set_epsilon": (c_int, [_P, c_double]),
+    "rb_jacobian_set_stream": (c_int, [_P, _P]),
+    "rb_jacobian_solver": (_P, [_P]),
+    "rb_jacobian_calculate": (c_int, [_P, _P, _P]),
+    "rb_gl2_default_options": (None, [POINTER(rb_gl2_options)]),
+    "rb_gl2_create": (_P, [_P, _P, POINTER(rb_gl2_options)]),
+    "rb_gl2_destroy": (c_int, [_P]),
+    "rb_gl2_set_options": (c_int, [_P, POINTER(rb_gl2_options)]),
+    "rb_gl2_initialize": (c_int, [_P, _P, c_int]),
+    "rb_gl2_step": (c_int, [_P, c_double, POINTER(c_int)]),
+    "rb_gl2_evolve": (c_int, [_P, c_double, c_double]),
+    "rb_gl2_copy_trajectory": (c_int, [_P, POINTER(_D), POINTER(c_size_t), POINTER(_D), POINTER(c_size_t)]),
+    "rb_gl2_dev_state": (_P, [_P]),
+    "rb_gl2_get_state": (c_int, [_P, _D]),
+    "rb_gl2_get_stats": (c_int, [_P, POINTER(rb_gl2_stats)]),
+    "calculateJacobian": (c_int, [_D, _D, c_double, c_double, c_double, c_double, c_double, c_size_t]),
+    "calculatePerturbedStates256": (c_int, [_D, _D, _D, _P, c_double, c_double, c_double, c_double, c_double]),
+    "integrateSimulationGL2": (c_int, [_D, POINTER(_D), POINTER(c_size_t), POINTER(_D), POINTER(c_size_t), POINTER(SimProperties),
+                                       POINTER(GaussLegendreOptions), c_size_t]),
+    "integrateSimulationGL2_freeMemory": (c_int, [_D, _D]),
 }
 
 _lib = None

@@ -480,6 +480,158 @@ class RungeKuttaStepper:
         return self.lib.rb_timed_rk4_current_time(self.handle)
 
 
+class RealBoundaryItegralCalculator:
+    """RealBoundaryItegralCalculator<N>(BaseBoundaryIntegralCalculator<N,1>&), L/RealBoundaryIntegralCalculator.cuh:37-89: the RHS on
+    real states [x | y | phi] (3N doubles on the device); the spelling of the class name is the reference's."""
+
+    def __init__(self, boundaryIntegralCalculator: BaseBoundaryIntegralCalculator):
+        assert boundaryIntegralCalculator.batchSize == 1
+        self.calculator = boundaryIntegralCalculator
+        self.lib = boundaryIntegralCalculator.lib
+
+    def run(self, initialState: torch.Tensor, rhs: torch.Tensor):
+        check(self.lib.rb_real_rhs(self.calculator.handle, _ptr(initialState), _ptr(rhs)), "rb_real_rhs")
+
+
+def createInitialBatchedZ(initialState: torch.Tensor, ZBatched: torch.Tensor, eps: float, N: int):
+    """createInitialBatchedZ<<<(ceil(2N/256), 3N), 256>>>(initialState, ZBatched, eps, N), L/JacobianCalculator.cuh:11-77."""
+    check(_lib.load().rb_perturbed_states(_ptr(initialState), _ptr(ZBatched), float(eps), int(N), _stream_ptr(initialState.device)),
+          "rb_perturbed_states")
+
+
+class JacobianCalculator:
+    """JacobianCalculator<N>(std::make_unique<BaseBoundaryIntegralCalculator<N, 3N>>(properties, problem)), L/JacobianCalculator.cuh:168-284:
+    here the calculator builds its batch-3N RHS assembler itself from the properties and the physics plugin."""
+
+    def __init__(self, N: int, problemProperties: ProblemProperties, boundaryProblem: _BoundaryProblem = None, device=None,
+                 tolerance: float = 1e-13, max_iterations: int = 200):
+        lib = _lib.load()
+        if lib.rb_device_count() == 0:
+            raise _lib.RobertsError("no CUDA device: superfluid_dynamics_b200 has no CPU path")
+        self.lib, self.N = lib, int(N)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        p = _lib.rb_props()
+        lib.rb_default_props(ctypes.byref(p))
+        p.rho, p.U, p.kappa, p.depth = problemProperties.rho, problemProperties.U, problemProperties.kappa, problemProperties.depth
+        p.use_expansions = int(problemProperties.use_expansions)
+        p.expansion_order = int(problemProperties.expansion_order)
+        p.infinite_depth = int(problemProperties.infinite_depth)
+        p.physics = PHYSICS[boundaryProblem.physics if boundaryProblem is not None else "helium"]
+        p.max_iterations = max_iterations
+        p.tolerance = tolerance
+        with torch.cuda.device(self.device):
+            check(lib.rb_set_device(self.device.index), "rb_set_device")
+            self.handle = lib.rb_jacobian_create(self.N, ctypes.byref(p))
+        if not self.handle:
+            raise _lib.RobertsError("rb_jacobian_create: " + lib.rb_last_error().decode())
+        self.setStream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.rb_jacobian_destroy(h)
+
+    def setEpsilon(self, eps: float):
+        check(self.lib.rb_jacobian_set_epsilon(self.handle, float(eps)), "rb_jacobian_set_epsilon")
+
+    def setStream(self, stream):
+        check(self.lib.rb_jacobian_set_stream(self.handle, ctypes.c_void_p(int(stream))), "rb_jacobian_set_stream")
+
+    def calculateJacobian(self, devState: torch.Tensor, devJacobian: torch.Tensor):
+        """devState: 3N doubles [x | y | phi]; devJacobian: 9 N^2 doubles, column-major (jac[c * 3N + r] = d f_r / d y_c)."""
+        check(self.lib.rb_jacobian_calculate(self.handle, _ptr(devState), _ptr(devJacobian)), "rb_jacobian_calculate")
+
+    def solve_stats(self):
+        out = (ctypes.c_double * 6)()
+        check(self.lib.rb_solve_stats(self.lib.rb_jacobian_solver(self.handle), out), "rb_solve_stats")
+        return dict(iterations=int(out[0]), converged=bool(out[1]), relative_residual=out[2])
+
+
+@dataclasses.dataclass
+class GaussLegendre2Options:
+    """GaussLegendre2Options, L/GaussLegendre.cuh:70-90."""
+    stepSize: float = 0.01
+    newtonTolerance: float = 1e-10
+    maxNewtonIterations: int = 20
+    allowSimplifiedFallback: bool = False
+    returnTrajectory: bool = True
+    armijo_c: float = 1e-4
+    backtrack: float = 0.5
+    minAlpha: float = 1e-6
+    maxStepsHalves: int = 6
+
+    def _c(self):
+        o = _lib.rb_gl2_options()
+        for f in dataclasses.fields(self):
+            setattr(o, f.name, type(getattr(o, f.name))(getattr(self, f.name)))
+        return o
+
+
+class GaussLegendre2:
+    """GaussLegendre2<N>(AutonomousProblem<double, 3N>& problem, JacobianCalculator<N>&, GaussLegendre2Options), L/GaussLegendre.cuh:107-612."""
+
+    def __init__(self, problem: RealBoundaryItegralCalculator, jacobianCalculator: JacobianCalculator,
+                 options: GaussLegendre2Options = None):
+        self.problem, self.jacobianCalculator = problem, jacobianCalculator
+        self.lib = problem.lib
+        self.N = problem.calculator.N
+        o = (options or GaussLegendre2Options())._c()
+        self.handle = self.lib.rb_gl2_create(problem.calculator.handle, jacobianCalculator.handle, ctypes.byref(o))
+        if not self.handle:
+            raise _lib.RobertsError("rb_gl2_create: " + self.lib.rb_last_error().decode())
+        self._keep = None
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            self.lib.rb_gl2_destroy(h)
+
+    def setOptions(self, options: GaussLegendre2Options):
+        o = options._c()
+        check(self.lib.rb_gl2_set_options(self.handle, ctypes.byref(o)), "rb_gl2_set_options")
+
+    def initialize(self, initialState, onDevice=False):
+        if onDevice:
+            self._keep = initialState
+            check(self.lib.rb_gl2_initialize(self.handle, _ptr(initialState), 1), "rb_gl2_initialize")
+        else:
+            host = np.ascontiguousarray(np.asarray(initialState, dtype=np.float64))
+            assert host.size == 3 * self.N
+            check(self.lib.rb_gl2_initialize(self.handle, host.ctypes.data_as(ctypes.c_void_p), 0), "rb_gl2_initialize")
+
+    def step(self, h: float) -> bool:
+        """gaussLegendreS2Step from the current state; True (and the state advanced) when the Newton iteration converged."""
+        ok = ctypes.c_int()
+        check(self.lib.rb_gl2_step(self.handle, float(h), ctypes.byref(ok)), "rb_gl2_step")
+        return bool(ok.value)
+
+    def runEvolution(self, startTime: float, endTime: float):
+        check(self.lib.rb_gl2_evolve(self.handle, float(startTime), float(endTime)), "rb_gl2_evolve")
+
+    def getState(self):
+        host = np.empty(3 * self.N)
+        check(self.lib.rb_gl2_get_state(self.handle, _dp(host)), "rb_gl2_get_state")
+        return host
+
+    def copyTrajectory(self):
+        """copyTimesToHost + copyStatesToHost: (times, states [count x 3N])."""
+        tp, sp = ctypes.POINTER(ctypes.c_double)(), ctypes.POINTER(ctypes.c_double)()
+        tc, sc = ctypes.c_size_t(), ctypes.c_size_t()
+        check(self.lib.rb_gl2_copy_trajectory(self.handle, ctypes.byref(tp), ctypes.byref(tc), ctypes.byref(sp), ctypes.byref(sc)),
+              "rb_gl2_copy_trajectory")
+        times = np.ctypeslib.as_array(tp, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
+        states = np.ctypeslib.as_array(sp, shape=(sc.value, 3 * self.N)).copy() if sc.value else np.zeros((0, 3 * self.N))
+        if tc.value:
+            self.lib.rb_free(ctypes.cast(tp, ctypes.c_void_p))
+        self.lib.rb_free(ctypes.cast(sp, ctypes.c_void_p))
+        return times, states
+
+    def stats(self):
+        st = _lib.rb_gl2_stats()
+        check(self.lib.rb_gl2_get_stats(self.handle, ctypes.byref(st)), "rb_gl2_get_stats")
+        return {n: getattr(st, n) for n, _ in st._fields_}
+
+
 class AugmentedRungeKuttaStepper:
     """AutonomousRungeKuttaStepper<std_complex, 3N>(AugmentedBoundaryIntegrator&, tstep) (A/kernel.cu:85-96)."""
 
@@ -781,4 +933,37 @@ def integrateOptomechanicalSimulationRK4(initialState, simProperties, rkOptions,
     states = np.ctypeslib.as_array(so, shape=(sc.value, 3 * N)).copy() if sc.value else np.zeros((0, 3 * N))
     times = np.ctypeslib.as_array(to, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
     lib.integrateOptomechanicalSimulationRK4_freeMemory(so, to)
+    return states, times
+
+
+def calculateJacobian(state, L, rho, kappa, depth, epsilon, N):
+    """L/Export.cuh:50: finite-difference Jacobian of the real-state helium RHS, SI properties; returns the (3N, 3N) matrix
+    J[r, c] = d f_r / d y_c (the export's buffer is its column-major flattening)."""
+    st = np.ascontiguousarray(state, np.float64)
+    jac = np.empty(9 * N * N)
+    check(_lib.load().calculateJacobian(_dp(st), _dp(jac), float(L), float(rho), float(kappa), float(depth), float(epsilon), int(N)),
+          "calculateJacobian")
+    return jac.reshape(3 * N, 3 * N).T.copy()
+
+
+def calculatePerturbedStates256(x, y, phi, L, rho, kappa, depth, epsilon):
+    """L/Export.cuh:53: the 3N perturbed states (N = 256) as a complex array of 6 N^2 entries."""
+    out = np.empty(6 * 256 * 256, np.complex128)
+    xs, ys, ps = (np.ascontiguousarray(v, np.float64) for v in (x, y, phi))
+    check(_lib.load().calculatePerturbedStates256(_dp(xs), _dp(ys), _dp(ps), out.ctypes.data_as(ctypes.c_void_p), float(L), float(rho),
+                                                  float(kappa), float(depth), float(epsilon)), "calculatePerturbedStates256")
+    return out
+
+
+def integrateSimulationGL2(initialState, simProperties: _lib.SimProperties, glCOptions: _lib.GaussLegendreOptions, N):
+    """L/Export.cuh:66: implicit Gauss-Legendre-2 evolution; returns (states [count x 3N], times)."""
+    lib = _lib.load()
+    st = np.ascontiguousarray(initialState, np.float64)
+    so, to = ctypes.POINTER(ctypes.c_double)(), ctypes.POINTER(ctypes.c_double)()
+    sc, tc = ctypes.c_size_t(), ctypes.c_size_t()
+    check(lib.integrateSimulationGL2(_dp(st), ctypes.byref(so), ctypes.byref(sc), ctypes.byref(to), ctypes.byref(tc),
+                                     ctypes.byref(simProperties), ctypes.byref(glCOptions), int(N)), "integrateSimulationGL2")
+    states = np.ctypeslib.as_array(so, shape=(sc.value, 3 * N)).copy() if sc.value else np.zeros((0, 3 * N))
+    times = np.ctypeslib.as_array(to, shape=(tc.value,)).copy() if tc.value else np.zeros(0)
+    lib.integrateSimulationGL2_freeMemory(so, to)
     return states, times

@@ -250,6 +250,10 @@ void launch_light_intensity(const double2* Z, double* out, const rb_opto& v, siz
 void launch_augmented_terms(const double2* state, double2* rhs, const rb_opto& v, size_t BN, cudaStream_t st);
 void launch_timed_drive(double2* rhs_phi, const double2* Z, const double2* w, double* delayed, const rb_opto& v, double time,
                         double prev_time, int save, size_t BN, cudaStream_t st);
+// solver.cu services for the other host-side translation units (implicit.cu)
+int report_error(const std::exception& e);   // records the message for rb_last_error, prints it, returns -1
+rb_props helium_props_from_si(double L, double rho, double kappa, double depth, bool use_expansions, int expansion_order,
+                              bool infinite_depth);   // adimensionalizeProperties + HeliumBoundaryProblem, L/Export.cu:1222-1246
 #endif
 // rk45_kernels.cu
 void launch_rk45_stage(const double2* y, const double2* const k[5], double2* out, const double c[5], int nk, size_t n,

@@ -1384,6 +1384,17 @@ int rb_set_stream(rb_solver* s, void* cuda_stream) {
     RB_CATCH
 }
 
+void* rb_get_stream(rb_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int rb_get_props(rb_solver* s, rb_props* out, int* N, int* batch) {
+    RB_TRY
+    if (!s) throw std::runtime_error("rb_get_props: null solver");
+    if (out) *out = s->props;
+    if (N) *N = s->N;
+    if (batch) *batch = s->batch;
+    RB_CATCH
+}
+
 int rb_rhs(rb_solver* s, const rb_complex* state_dev, rb_complex* rhs_dev) {
     RB_TRY
     rhs(s, (const double2*)state_dev, (double2*)rhs_dev);
@@ -2122,6 +2133,16 @@ int rb_integrate_rk4_host(const double* initialState_host, double* finalState_ho
 }
 
 }  // extern "C"
+
+// services for implicit.cu (internal.cuh)
+namespace rb {
+int report_error(const std::exception& e) { return fail(e); }
+rb_props helium_props_from_si(double L, double rho, double kappa, double depth, bool use_expansions, int expansion_order,
+                              bool infinite_depth) {
+    return helium_props(adimensionalize(L, rho, kappa, depth), use_expansions, expansion_order, infinite_depth);
+}
+}  // namespace rb
+
 
 // ------------------------------------------------------------------------------------------------
 // optomechanically driven film: the autonomous augmented system y = [Z | Phi | D] (drive_kernels.cu) and its classical RK4 stepper

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "cusuperhelium_compat.cuh"
@@ -398,11 +399,93 @@ static void test_timed_drive() {
                 failures, dmax, moved);
 }
 
-int main() {
+// The implicit side, assembled as L/Export.cu:680-700: RealBoundaryItegralCalculator + JacobianCalculator + GaussLegendre2.
+// Run with `compat_test --implicit` (kept apart from the default run until its first pass on hardware).
+static void test_implicit() {
+    constexpr int N = 16;
+    ProblemProperties properties;
+    properties.depth = 0.3;
+    properties.rho = 1;
+    HeliumBoundaryProblem<N, 1> heliumProblem(properties);
+    BaseBoundaryIntegralCalculator<N, 1> calculator(properties, heliumProblem);
+    RealBoundaryItegralCalculator<N> realCalculator(calculator);
+    HeliumBoundaryProblem<N, 3 * N> heliumJacProblem(properties);
+    JacobianCalculator<N> jacobianCalculator(properties, heliumJacProblem);
+
+    // flat film at rest: d(dPhi_i/dt)/dy_j = -delta_ij (van-der-Waals stiffness 3 vdw / h with vdw = h / 3, L/createM.cuh:109-117)
+    std::vector<double> flat(3 * N, 0.0), jac(9 * N * N);
+    for (int i = 0; i < N; i++) flat[i] = 2.0 * PI_d * i / N;
+    double* dFlat = toDevice(flat);
+    double* dJac = nullptr;
+    cudaMalloc(&dJac, 9 * N * N * sizeof(double));
+    jacobianCalculator.setEpsilon(1e-6);
+    jacobianCalculator.calculateJacobian(dFlat, dJac);
+    cudaDeviceSynchronize();
+    cudaMemcpy(jac.data(), dJac, 9 * N * N * sizeof(double), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)   // column N + j (y_j), row 2N + i (dPhi_i/dt), column-major
+            EXPECT_NEAR(jac[(size_t)(N + j) * 3 * N + 2 * N + i], i == j ? -1.0 : 0.0, 1e-6, "d(dPhi/dt)/dy of the flat film");
+
+    // a small standing wave: 10 implicit steps of 0.05 against 500 explicit RK4 steps of 1e-3
+    std::vector<double> y0(3 * N);
+    std::vector<std_complex> c0(2 * N);
+    for (int i = 0; i < N; i++) {
+        const double a = 2.0 * PI_d * i / N;
+        y0[i] = a - 0.3 * 0.05 * 0.3 * std::sin(a);
+        y0[N + i] = 0.05 * 0.3 * std::cos(a);
+        y0[2 * N + i] = 0.2 * 0.05 * 0.3 * std::sin(a);
+        c0[i] = std_complex(y0[i], y0[N + i]);
+        c0[N + i] = std_complex(y0[2 * N + i], 0.0);
+    }
+    GaussLegendre2Options options;
+    options.stepSize = 0.05;
+    GaussLegendre2<N> integrator(realCalculator, jacobianCalculator, options);
+    integrator.initialize(y0.data(), false);
+    integrator.runEvolution(0.0, 0.5);
+    double *times = nullptr, *states = nullptr;
+    size_t nt = 0, ns = 0;
+    integrator.copyTimesToHost(&times, &nt);
+    integrator.copyStatesToHost(&states, &ns);
+    EXPECT_NEAR((double)nt, (double)ns, 0.0, "as many times as states");
+    EXPECT_NEAR(nt >= 11 ? 1.0 : 0.0, 1.0, 0.5, "initial state + at least ten steps logged");
+    if (nt) {
+        EXPECT_NEAR(times[0], 0.0, 0.0, "trajectory starts at t0");
+        EXPECT_NEAR(times[nt - 1], 0.5, 1e-12, "trajectory ends at t1");
+    }
+    AutonomousRungeKuttaStepper<std_complex, 2 * N> stepper(calculator, 1e-3);
+    stepper.initialize(c0.data(), false);
+    for (int i = 0; i < 500; i++) stepper.runStep(i);
+    std::vector<std_complex> ye(2 * N);
+    stepper.getState(ye.data());
+    double diff = 0, moved = 0;
+    if (ns)
+        for (int i = 0; i < N; i++) {
+            const double* yl = states + (ns - 1) * 3 * N;
+            diff = std::max(diff, std::fabs(yl[i] - ye[i].real()));
+            diff = std::max(diff, std::fabs(yl[N + i] - ye[i].imag()));
+            diff = std::max(diff, std::fabs(yl[2 * N + i] - ye[N + i].real()));
+            moved = std::max(moved, std::fabs(yl[N + i] - y0[N + i]));
+        }
+    EXPECT_NEAR(diff, 0.0, 1e-8, "Gauss-Legendre-2 agrees with explicit RK4");
+    EXPECT_NEAR(moved > 1e-4 ? 1.0 : 0.0, 1.0, 0.5, "the film has moved");
+    rb_free(times);
+    rb_free(states);
+    cudaFree(dFlat);
+    cudaFree(dJac);
+    std::printf("Implicit Gauss-Legendre-2 + FD Jacobian (Export pattern): failures so far %d, |GL2 - RK4| = %.3e, moved %.3e\n", failures,
+                diff, moved);
+}
+
+int main(int argc, char** argv) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
         std::printf("no CUDA device\n");
         return 2;
+    }
+    if (argc > 1 && std::string(argv[1]) == "--implicit") {
+        test_implicit();
+        std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
+        return failures ? 1 : 0;
     }
     test_matrices(2, 0.0);
     test_matrices(4, 0.1);

@@ -70,3 +70,39 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("test oracle", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_ctypes_layouts_match_it(tmp_path):
+    """include/roberts_b200.h must compile as C (the boundary is a C ABI), and the ctypes mirrors must have the layout gcc gives
+    the structs (sizes and a few offsets of every struct passed by pointer)."""
+    import subprocess
+    from superfluid_dynamics_b200 import _lib
+    probes = {
+        "rb_props": ("tolerance", "physics"),
+        "rb_opto": ("drive_strength",),
+        "rb_rk45_options": ("initial_timestep",),
+        "rb_gl2_options": ("allowSimplifiedFallback", "armijo_c", "maxStepsHalves"),
+        "rb_gl2_stats": ("residualNorm", "steps_accepted", "linear_solves"),
+        "SimProperties": ("use_expansions", "expansion_order", "infinite_depth"),
+        "RK4SolverOptions": ("returnTrajectory",),
+        "GaussLegendreOptions": ("maxNewtonIterations", "allowSimplifiedFallback", "returnTrajectory", "armijo_c", "maxStepsHalves"),
+        "COptomechanicalVariables": ("damping_strength",),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "roberts_b200.h"', 'int main(void) {']
+    for name, fields in probes.items():
+        lines.append(f'printf("{name} %zu", sizeof({name}));')
+        for f in fields:
+            lines.append(f'printf(" %zu", offsetof({name}, {f}));')
+        lines.append('printf("\\n");')
+    lines += ['return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    for line in out.strip().splitlines():
+        name, size, *offs = line.split()
+        c = getattr(_lib, name)
+        assert ctypes.sizeof(c) == int(size), name
+        for f, o in zip(probes[name], offs):
+            assert getattr(c, f).offset == int(o), (name, f)

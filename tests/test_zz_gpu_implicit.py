@@ -1,0 +1,226 @@
+"""GPU parity tests of the implicit side of the path: real-state RHS wrapper, finite-difference
+Jacobian from batched RHS evaluations, implicit Gauss-Legendre-2 integrator and their legacy exports, through the C ABI, against
+the CPU oracle and the trajectories of the reference's own Python integrator (tests/golden/ref_gl2.npz).
+
+STATUS: written after round 1's GPU budget was spent -- the library builds and every symbol loads (CPU tier), but these tests
+have not yet been run on hardware.  They are therefore marked xfail(strict=False): a pass is reported as XPASS, a failure does
+not hide behind the rest of the suite, and the file is named to run last so that nothing here can disturb the verified tests.
+The marker goes away with the first hardware run.
+
+Tolerances: the Jacobian is a central difference with eps = 1e-6 of two RHS evaluations that agree with the oracle's to ~1e-13
+(relative), so entries agree to ~1e-13 / 2e-6 ~ 1e-7 of the RHS scale; Gauss-Legendre steps are solved to the Newton tolerance
+1e-10 (1 + |k|) in both implementations, so trajectories agree to ~1e-9, not to round-off."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
+
+torch = pytest.importorskip("torch")
+from oracle import roberts_oracle as ro  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from superfluid_dynamics_b200 import api, build
+    build.build(verbose=False)
+    return api
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+
+
+def film(N, depth, amp):
+    a = 2 * np.pi * np.arange(N) / N
+    return np.concatenate([a - 0.3 * amp * depth * np.sin(a), amp * depth * np.cos(a), 0.2 * amp * depth * np.sin(a)])
+
+
+@pytest.mark.parametrize("physics,N,depth", [("helium", 64, 0.3), ("helium", 37, 0.3), ("water", 64, 1.0), ("helium_inf", 32, 0.3)])
+def test_real_rhs_matches_oracle(api, physics, N, depth):
+    """rb_real_rhs (RealBoundaryItegralCalculator::run) vs ro.real_rhs; 1e-15 N + 1e-13 relative as for the complex RHS."""
+    props = api.ProblemProperties(rho=0.0 if physics == "water" else 1.0, depth=depth)
+    oprops = ro.ProblemProperties(rho=props.rho, depth=depth)
+    prob = {"water": api.WaterBoundaryProblem, "helium": api.HeliumBoundaryProblem,
+            "helium_inf": api.HeliumInfiniteDepthBoundaryProblem}[physics](props)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, prob)
+    real = api.RealBoundaryItegralCalculator(calc)
+    y = film(N, depth, 0.1)
+    out = torch.zeros(3 * N, dtype=torch.float64, device="cuda:0")
+    real.run(T(y), out)
+    exp = ro.real_rhs(y, N, oprops, physics)
+    got = out.cpu().numpy()
+    tol = 1e-15 * N + 1e-13
+    for blk in range(3):
+        sl = slice(blk * N, (blk + 1) * N)
+        assert np.abs(got[sl] - exp[sl]).max() <= tol * max(np.abs(exp).max(), 1e-300), blk
+
+
+@pytest.mark.parametrize("N", [8, 37, 256])
+def test_perturbed_states_bit_exact(api, N):
+    """createInitialBatchedZ: exactly the oracle's array (which is pinned thread by thread on the reference kernel)."""
+    rng = np.random.default_rng(N)
+    st = rng.standard_normal(2 * N) + 1j * np.concatenate([rng.standard_normal(N), np.zeros(N)])
+    for eps in (1e-6, -1e-6):
+        out = torch.zeros(6 * N * N, dtype=torch.complex128, device="cuda:0")
+        api.createInitialBatchedZ(T(st), out, eps, N)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ro.perturbed_states(st, N, eps))
+    if N == 256:
+        got = api.calculatePerturbedStates256(st[:N].real, st[:N].imag, st[N:].real, 1e-6, 145.0, 0.0, 15e-9, 1e-6)
+        assert np.array_equal(got, ro.perturbed_states(st, N, 1e-6))
+
+
+@pytest.mark.parametrize("physics,N,depth,eps", [("helium", 32, 0.3, 1e-6), ("helium", 24, 0.0942478, 1e-6), ("water", 16, 1.0, 1e-6),
+                                                 ("helium", 64, 0.3, 1e-5)])
+def test_jacobian_matches_oracle(api, physics, N, depth, eps):
+    """JacobianCalculator::calculateJacobian vs ro.jacobian_fd (same central differences): <= 1e-6 of the largest entry
+    (measured floor expected ~1e-9), column-major layout included."""
+    props = api.ProblemProperties(rho=0.0 if physics == "water" else 1.0, depth=depth)
+    oprops = ro.ProblemProperties(rho=props.rho, depth=depth)
+    prob = {"water": api.WaterBoundaryProblem, "helium": api.HeliumBoundaryProblem}[physics](props)
+    jc = api.JacobianCalculator(N, props, prob)
+    jc.setEpsilon(eps)
+    y = film(N, depth, 0.1)
+    J = torch.zeros(9 * N * N, dtype=torch.float64, device="cuda:0")
+    jc.calculateJacobian(T(y), J)
+    torch.cuda.synchronize()
+    assert jc.solve_stats()["converged"]
+    got = J.cpu().numpy().reshape(3 * N, 3 * N).T      # column-major buffer -> J[r, c]
+    exp = ro.jacobian_fd(y, N, oprops, physics, eps)
+    assert np.abs(got - exp).max() <= 1e-6 * np.abs(exp).max()
+    # a second call (warm-started from the first) gives the same matrix
+    jc.calculateJacobian(T(y), J)
+    torch.cuda.synchronize()
+    assert np.abs(J.cpu().numpy().reshape(3 * N, 3 * N).T - exp).max() <= 1e-6 * np.abs(exp).max()
+
+
+def test_calculate_jacobian_export(api):
+    """calculateJacobian (L/Export.cuh:50), SI in: helium film, N = 32."""
+    N, L, d_si, rho_si = 32, 1e-6, 15e-9, 145.0
+    op = ro.adimensionalize_properties(ro.ProblemProperties(L=L, rho=rho_si, kappa=0.0, depth=d_si))
+    y = film(N, op.depth, 0.1)
+    got = api.calculateJacobian(y, L, rho_si, 0.0, d_si, 1e-6, N)
+    exp = ro.jacobian_fd(y, N, op, "helium", 1e-6)
+    assert got.shape == (3 * N, 3 * N)
+    assert np.abs(got - exp).max() <= 1e-6 * np.abs(exp).max()
+
+
+def _golden_case(name):
+    g = np.load(os.path.join(HERE, "golden", "ref_gl2.npz"))
+    N, depth, amp, t0, t1, h, tol, maxit, fallback, halves = g[name + "/params"]
+    return dict(N=int(N), depth=float(depth), t0=float(t0), t1=float(t1), h=float(h), tol=float(tol), maxit=int(maxit),
+                fallback=bool(fallback), halves=int(halves), physics=str(g[name + "/physics"]), y0=g[name + "/y0"], T=g[name + "/T"],
+                Y=g[name + "/Y"])
+
+
+def _integrator(api, c, trajectory=True):
+    props = api.ProblemProperties(rho=0.0 if c["physics"] == "water" else 1.0, depth=c["depth"])
+    prob = {"water": api.WaterBoundaryProblem, "helium": api.HeliumBoundaryProblem}[c["physics"]](props)
+    calc = api.BaseBoundaryIntegralCalculator(c["N"], 1, props, prob, guess="warm")
+    real = api.RealBoundaryItegralCalculator(calc)
+    jc = api.JacobianCalculator(c["N"], props, prob)
+    opt = api.GaussLegendre2Options(stepSize=c["h"], newtonTolerance=c["tol"], maxNewtonIterations=c["maxit"],
+                                    allowSimplifiedFallback=c["fallback"], returnTrajectory=trajectory, maxStepsHalves=c["halves"])
+    return api.GaussLegendre2(real, jc, opt)
+
+
+@pytest.mark.parametrize("name", ["helium_film_N16", "helium_film_N16_backward", "helium_thin_N16_fallback", "water_N16"])
+def test_gl2_matches_reference_python_integrator(api, name):
+    """rb_gl2_evolve against the trajectory of the reference's own P/integration/gauss_legendre.py (golden): same accepted steps
+    and times; states to 1e-8 absolute (positions are O(2 pi): 1.6e-9 relative; Newton tolerance 1e-10 per step on both sides)."""
+    c = _golden_case(name)
+    gl = _integrator(api, c)
+    gl.initialize(c["y0"], False)
+    gl.runEvolution(c["t0"], c["t1"])
+    times, states = gl.copyTrajectory()
+    assert len(times) == len(c["T"]) and np.abs(times - c["T"]).max() <= 1e-14
+    assert states.shape == c["Y"].shape
+    assert np.array_equal(states[0], c["y0"])
+    assert np.abs(states - c["Y"]).max() <= 1e-8
+    assert np.array_equal(gl.getState(), states[-1])
+    st = gl.stats()
+    assert st["converged"] and st["steps_accepted"] == len(c["T"]) - 1 and st["jacobians"] >= 2
+
+
+def test_gl2_final_state_only_single_steps_and_reversibility(api):
+    """returnTrajectory off -> the final state alone, no times; rb_gl2_step advances only on convergence; integrating forward and
+    back returns to the start (the scheme is symmetric) to the Newton tolerance."""
+    c = _golden_case("helium_film_N16")
+    gl = _integrator(api, c, trajectory=False)
+    gl.initialize(c["y0"], False)
+    gl.runEvolution(c["t0"], c["t1"])
+    times, states = gl.copyTrajectory()
+    assert len(times) == 0 and states.shape == (1, 3 * c["N"])
+    assert np.abs(states[0] - c["Y"][-1]).max() <= 1e-8
+    gl.runEvolution(c["t1"], c["t0"])
+    assert np.abs(gl.getState() - c["y0"]).max() <= 1e-7
+    # single steps: one converged step equals the first step of the golden trajectory
+    gl2 = _integrator(api, c)
+    gl2.initialize(T(c["y0"]).clone(), True)
+    assert gl2.step(c["h"])
+    assert np.abs(gl2.getState() - c["Y"][1]).max() <= 1e-8
+    # an impossible request (one Newton iteration, absurd tolerance) does not converge and leaves the state alone
+    before = gl2.getState()
+    gl2.setOptions(api.GaussLegendre2Options(stepSize=c["h"], newtonTolerance=1e-300, maxNewtonIterations=1))
+    assert not gl2.step(c["h"])
+    assert np.array_equal(gl2.getState(), before)
+
+
+def test_integrate_simulation_gl2_export(api):
+    """integrateSimulationGL2 (L/Export.cuh:66), SI properties in, times as given: against the oracle's integrator on the
+    nondimensionalised problem."""
+    from superfluid_dynamics_b200 import _lib
+    N, L, d_si, rho_si = 16, 1e-6, 15e-9, 145.0
+    op = ro.adimensionalize_properties(ro.ProblemProperties(L=L, rho=rho_si, kappa=0.0, depth=d_si))
+    y0 = film(N, op.depth, 0.1)
+    sp = _lib.SimProperties(L=L, rho=rho_si, kappa=0.0, depth=d_si, use_expansions=False, expansion_order=1, infinite_depth=False)
+    go = _lib.GaussLegendreOptions(t0=0.0, t1=0.3, stepSize=0.1, newtonTolerance=1e-10, maxNewtonIterations=20,
+                                   allowSimplifiedFallback=False, returnTrajectory=True, armijo_c=1e-4, backtrack=0.5, minAlpha=1e-6,
+                                   maxStepsHalves=6)
+    states, times = api.integrateSimulationGL2(y0, sp, go, N)
+    To, Yo = ro.gl2_integrate(lambda y: ro.real_rhs(y, N, op, "helium"), lambda y: ro.jacobian_fd(y, N, op, "helium", 1e-6), y0, 0.0,
+                              0.3, ro.GaussLegendre2Options(stepSize=0.1))
+    assert len(times) == len(To) and np.abs(times - To).max() <= 1e-14
+    assert states.shape == Yo.shape and np.abs(states - Yo).max() <= 1e-8
+    go.returnTrajectory = False
+    final, t2 = api.integrateSimulationGL2(y0, sp, go, N)
+    assert final.shape == (1, 3 * N) and len(t2) == 0 and np.abs(final[0] - Yo[-1]).max() <= 1e-8
+
+
+def test_gl2_larger_film_agrees_with_explicit_rk4(api):
+    """N = 64 film, 20 implicit steps of h = 0.05 against 1000 explicit RK4 steps of 1e-3 over the same unit of time (both through
+    the C ABI): they agree to the accuracy of the larger step (2e-12 in the oracle's arithmetic; bar 1e-7)."""
+    N, depth = 64, 0.3
+    c = dict(N=N, depth=depth, h=0.05, tol=1e-11, maxit=20, fallback=False, halves=6, physics="helium")
+    y0 = film(N, depth, 0.05)
+    gl = _integrator(api, c, trajectory=False)
+    gl.initialize(y0, False)
+    gl.runEvolution(0.0, 1.0)
+    yg = gl.getState()
+    props = api.ProblemProperties(rho=1.0, depth=depth)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumBoundaryProblem(props), guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(calc, 1e-3)
+    stp.initialize(ro.real_to_complex_state(y0, N), False)
+    for _ in range(1000):
+        stp.runStep()
+    ye = stp.getState()
+    yr = np.concatenate([ye[:N].real, ye[:N].imag, ye[N:].real])
+    assert np.abs(yg - yr).max() <= 1e-7 and np.abs(yr - y0).max() >= 1e-4
+
+
+def test_cpp_compat_header_implicit_classes(api):
+    """tests/cpp/compat_test.cu --implicit: RealBoundaryItegralCalculator + JacobianCalculator + GaussLegendre2 through the
+    reference's C++ names (cusuperhelium_compat.cuh), assembled as L/Export.cu:680-700."""
+    import subprocess
+    from superfluid_dynamics_b200 import build
+    exe = build.build_compat_test(verbose=False)
+    r = subprocess.run([exe, "--implicit"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASSED" in r.stdout
