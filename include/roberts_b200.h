@@ -313,7 +313,9 @@ RB_API int rb_gl2_initialize(rb_gl2* g, double* state, int on_device);          
    *converged); otherwise it is left as it was */
 RB_API int rb_gl2_step(rb_gl2* g, double h, int* converged);
 /* runEvolution :216-299: steps of min(stepSize, |t1 - t|) towards t1 (either direction), halving a failed step at most
-   maxStepsHalves times (never below |t1 - t0| / 2^20) and keeping the reduced size; the trajectory starts with (t0, y0).
+   maxStepsHalves times (never below |t1 - t0| / 2^20) and keeping the reduced size for the rest of the call (every call starts
+   again from options.stepSize, as the reference's Python statement does; its CUDA class writes the last -- possibly
+   end-truncated -- size back into the options, :290); the trajectory starts with (t0, y0).
    Returns -1 with "failed to converge" in rb_last_error when a step cannot be completed (the reference throws). */
 RB_API int rb_gl2_evolve(rb_gl2* g, double t0, double t1);
 /* copyTimesToHost / copyStatesToHost :355-401: states_count x 3N doubles; without a trajectory no times and the current state.

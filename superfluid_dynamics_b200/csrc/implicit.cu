@@ -436,20 +436,24 @@ static void gl2_log_append(rb_gl2* g, double t) {
     g->times.push_back(t);
 }
 
-// runEvolution, L/GaussLegendre.cuh:216-299 == integrate_gl2, P/integration/gauss_legendre.py:173-267
+// runEvolution, L/GaussLegendre.cuh:216-299 == integrate_gl2, P/integration/gauss_legendre.py:173-267.  As in the Python statement the
+// running step size and the lower bound |t1 - t0| / 2^20 belong to the call: the CUDA class writes the (possibly reduced, possibly
+// end-truncated) size back into its options (:290) and keeps the first call's bound (:226-228), so that a second runEvolution on
+// the same object would start from whatever sliver the first one ended with.
 static void gl2_evolve(rb_gl2* g, double t0, double t1) {
-    rb_gl2_options& o = g->opt;
+    const rb_gl2_options& o = g->opt;
     if (o.stepSize < 0.0) throw std::invalid_argument("Step size must be positive.");
     if (!g->y) throw std::runtime_error("Initial state not set. Call initialize() before running evolution.");
     const size_t n = g->n;
     cudaStream_t st = gl2_stream(g);
     const double total = std::fabs(t1 - t0);
-    if (g->hmin < 0) g->hmin = total / std::pow(2.0, 20);
+    g->hmin = total / std::pow(2.0, 20);
+    double h = o.stepSize;
     if (o.returnTrajectory) gl2_log_append(g, t0);
     double t = t0;
     const double forward = t1 >= t0 ? 1.0 : -1.0;
     while ((t - t1) * forward < 0.0) {
-        double htry = std::min(o.stepSize, std::fabs(t1 - t)) * forward;
+        double htry = std::min(h, std::fabs(t1 - t)) * forward;
         bool ok = false;
         for (size_t i = 0; i < o.maxStepsHalves + 1; ++i) {
             if (gl2_step(g, g->y, g->ynext, htry) && g->stats.converged) {
@@ -468,7 +472,7 @@ static void gl2_evolve(rb_gl2* g, double t0, double t1) {
         }
         RB_CUDA(cudaMemcpyAsync(g->y, g->ynext, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
         t += htry;
-        o.stepSize = std::fabs(htry);   // the (possibly reduced) size is kept for the following steps, :290
+        h = std::fabs(htry);   // the (possibly reduced) size is kept for the following steps of this call
         ++g->stats.steps_accepted;
         if (o.returnTrajectory) gl2_log_append(g, t);
     }
