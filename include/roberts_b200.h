@@ -282,6 +282,12 @@ RB_API rb_solver* rb_jacobian_solver(rb_jacobian* j);                           
    jac[c * 3N + r] = d f_r / d y_c (createJacobianMatrixFromPerturbedRhs :92-156) */
 RB_API int rb_jacobian_calculate(rb_jacobian* j, const double* state_real_dev, double* jac_dev);
 
+/* MatrixSolver<N,1>::solve (cusolverDnDgetrf + Dgetrs, L/MatrixSolver.cuh:114-125): A (n x n, column-major, destroyed) x = b, x
+   returned in b.  blocked = 0: unblocked right-looking LU (two launches per column); 1: panels of 32 columns with the trailing
+   update on the FP64 tensor path; -1: what the library itself uses (RB_LU_BLOCKED).  *info_host = 0, or 1 + the first column
+   without a usable pivot (getrf's info). */
+RB_API int rb_lu_solve(double* A_dev, double* b_dev, int n, int blocked, int* info_host, void* cuda_stream);
+
 /* GaussLegendre2Options (L/GaussLegendre.cuh:70-90) */
 typedef struct rb_gl2_options {
     double stepSize;              /* 0.01 */

@@ -202,6 +202,7 @@ SIGNATURES = {
     "rb_jacobian_set_stream": (c_int, [_P, _P]),
     "rb_jacobian_solver": (_P, [_P]),
     "rb_jacobian_calculate": (c_int, [_P, _P, _P]),
+    "rb_lu_solve": (c_int, [_P, _P, c_int, c_int, POINTER(c_int), _P]),
     "rb_gl2_default_options": (None, [POINTER(rb_gl2_options)]),
     "rb_gl2_create": (_P, [_P, _P, POINTER(rb_gl2_options)]),
     "rb_gl2_destroy": (c_int, [_P]),

@@ -499,6 +499,13 @@ def createInitialBatchedZ(initialState: torch.Tensor, ZBatched: torch.Tensor, ep
           "rb_perturbed_states")
 
 
+def lu_solve(A: torch.Tensor, b: torch.Tensor, n: int, blocked: int = -1) -> int:
+    """MatrixSolver<N,1>::solve (L/MatrixSolver.cuh:114-125): A (n x n column-major, destroyed) x = b in place; returns getrf's info."""
+    info = ctypes.c_int()
+    check(_lib.load().rb_lu_solve(_ptr(A), _ptr(b), int(n), int(blocked), ctypes.byref(info), _stream_ptr(A.device)), "rb_lu_solve")
+    return info.value
+
+
 class JacobianCalculator:
     """JacobianCalculator<N>(std::make_unique<BaseBoundaryIntegralCalculator<N, 3N>>(properties, problem)), L/JacobianCalculator.cuh:168-284:
     here the calculator builds its batch-3N RHS assembler itself from the properties and the physics plugin."""

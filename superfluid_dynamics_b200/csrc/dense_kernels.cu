@@ -10,6 +10,8 @@
 //   cudaMalloc + cudaFreeAsync each)                              L/Energies.cuh:136-327
 //   MatrixSolver<N,1>::solve (cusolverDnDgetrf + Dgetrs)          L/MatrixSolver.cuh:114-125
 // Matrices are column-major A[k + j*n + b*n*n] = entry (row k, col j), exactly as the reference stores them.
+#include <cstdlib>
+
 #include "internal.cuh"
 #include "../../include/roberts_b200_device.cuh"
 
@@ -252,7 +254,13 @@ __global__ void __launch_bounds__(kLuThreads) lu_backsolve_kernel(const double* 
     }
 }
 
-void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st) {
+void launch_lu_backsolve(const double* A, double* b, int n, cudaStream_t st) {
+    lu_backsolve_kernel<<<1, kLuThreads, 0, st>>>(A, b, n);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+void launch_lu_solve_unblocked(double* A, double* b, int n, int* info, cudaStream_t st) {
     RB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     for (int k = 0; k < n; ++k) {
         lu_pivot_kernel<<<1, kLuThreads, 0, st>>>(A, b, n, k, info);
@@ -265,6 +273,16 @@ void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st) {
     lu_backsolve_kernel<<<1, kLuThreads, 0, st>>>(A, b, n);
     RB_CUDA(cudaGetLastError());
     count_launch(2 * n);
+}
+
+// the blocked factorisation (lu_kernels.cu) is selected only on request until it has passed its tests on hardware
+void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st) {
+    static const bool blocked = [] {
+        const char* v = std::getenv("RB_LU_BLOCKED");
+        return v && std::atoi(v) != 0;
+    }();
+    if (blocked && n >= 64) launch_lu_solve_blocked(A, b, n, info, st);
+    else launch_lu_solve_unblocked(A, b, n, info, st);
 }
 
 }  // namespace rb

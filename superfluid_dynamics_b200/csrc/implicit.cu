@@ -571,6 +571,27 @@ int rb_jacobian_calculate(rb_jacobian* j, const double* state_real_dev, double* 
     RB_CATCH
 }
 
+int rb_lu_solve(double* A_dev, double* b_dev, int n, int blocked, int* info_host, void* cuda_stream) {
+    RB_TRY
+    if (!A_dev || !b_dev || n < 1) throw std::runtime_error("rb_lu_solve: bad argument");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int* info = dmalloc<int>(1);
+    int h = 0;
+    try {
+        if (blocked > 0) launch_lu_solve_blocked(A_dev, b_dev, n, info, st);
+        else if (blocked == 0) launch_lu_solve_unblocked(A_dev, b_dev, n, info, st);
+        else launch_lu_solve(A_dev, b_dev, n, info, st);
+        RB_CUDA(cudaMemcpyAsync(&h, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaFree(info);
+        throw;
+    }
+    cudaFree(info);
+    if (info_host) *info_host = h;
+    RB_CATCH
+}
+
 void rb_gl2_default_options(rb_gl2_options* o) {
     o->stepSize = 0.01;
     o->newtonTolerance = 1e-10;

@@ -239,7 +239,11 @@ void launch_rhs_phi_helium_exp(const double2* Z, const double2* V1, double2* res
                                cudaStream_t st);
 void launch_energies(const double2* Z, const double2* Zp, const double2* Phi, const double2* vel, double* out5, int N,
                      int physics, double rho, double U, double depth, double kappa, cudaStream_t st);
-void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st);
+void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st);            // the solve every caller uses
+void launch_lu_solve_unblocked(double* A, double* b, int n, int* info, cudaStream_t st);  // two launches per column
+void launch_lu_backsolve(const double* A, double* b, int n, cudaStream_t st);
+// lu_kernels.cu
+void launch_lu_solve_blocked(double* A, double* b, int n, int* info, cudaStream_t st);    // panels of 32, DMMA trailing update
 // stepper_kernels.cu
 void launch_stage_update(double2* y_out, const double2* y0, const double2* k, double c, size_t n, cudaStream_t st);
 void launch_final_update(double2* y0, const double2* k1, const double2* k2, const double2* k3, const double2* k4, double h,
