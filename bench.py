@@ -361,6 +361,32 @@ def run_native(args):
                 elif r:
                     extra[f"n{n2}"]["reference_cuda"] = r
                 del s2, c2
+            # BASELINE config 5, second half: the 1024-member ensemble at N = 512 (member m: trochoid h_m = 0.05 + 0.35 m / 1023,
+            # SURVEY.md section 8d), batched in one solver; across GPUs the members are replicas, no communication.  An extra: a
+            # failure here is recorded, it never takes the headline down.
+            try:
+                Ne, Be, ke = 512, 1024, 30
+                hs = 0.05 + 0.35 * np.arange(Be) / (Be - 1)
+                members = [trochoid_state(Ne, h) for h in hs]
+                ye = np.concatenate([m_[:Ne] for m_ in members] + [m_[Ne:] for m_ in members])   # [Z of every member | Phi of every member]
+                ce = api.BaseBoundaryIntegralCalculator(Ne, Be, props, api.WaterBoundaryProblem(props), device=dev, guess="warm")
+                se = api.AutonomousRungeKuttaStepper(ce, 1e-3)
+                ste = torch.as_tensor(ye, device=dev)
+                se.initialize(ste, True)
+                se.runSteps(12)
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                se.runSteps(ke)
+                b.record()
+                torch.cuda.synchronize(dev)
+                finite = bool(torch.isfinite(torch.view_as_real(ste)).all())
+                extra["ensemble_1024xN512"] = {"steps_per_s": ke / (a.elapsed_time(b) * 1e-3),
+                                               "member_steps_per_s": Be * ke / (a.elapsed_time(b) * 1e-3), "steps": ke,
+                                               "finite": finite, "converged": bool(ce.solve_stats()["converged"])}
+                del se, ce, ste
+            except Exception as e:  # noqa: BLE001
+                extra["ensemble_1024xN512"] = {"error": repr(e)[:200]}
             if ref_gpu:
                 extra["reference_cuda_note"] = ("reference_cuda_* = the reference's own CUDA path (BaseBoundaryIntegralCalculator + "
                                                 "AutonomousRungeKuttaStepper compiled unmodified from its sources, oracle/build_ref.py) "

@@ -15,7 +15,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
               pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
 
 torch = pytest.importorskip("torch")
