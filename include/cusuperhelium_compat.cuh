@@ -18,6 +18,7 @@
 //   compute_rhs_phi_expression, compute_rhs_helium_phi_expression   (the __global__ kernels the reference's tests launch)
 #pragma once
 #include <cuda_runtime.h>
+#include <cuComplex.h>
 #include <cuda/std/complex>
 
 #include <cstdlib>
@@ -649,3 +650,123 @@ __global__ void compute_rhs_helium_phi_expression(const std_complex* Z, const st
                     0.5 * V1[i].imag() * V1[i].imag();
     }
 }
+
+// ---- the perturbed-state kernels of the Jacobian (T/MatrixMTests.cuh:284-390 launches them as
+//      createInitialState<<<N, 1>>> and createInitialBatchedZ<<<(ceil(2N/256), 3N), 256>>>; L/JacobianCalculator.cuh:11-166) ----------
+__global__ void createInitialState(const double* initialState, std_complex* complexState, size_t N) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    complexState[i] = std_complex(initialState[i], initialState[i + N]);
+    complexState[i + N] = std_complex(initialState[i + 2 * N], 0.0);
+}
+
+// one thread per entry of the 2N-entry state and per batch member b = blockIdx.y = c N + j: a copy of the state with coordinate
+// c (0 x, 1 y, 2 phi) of point j moved by eps, written as [Z of member 0 .. Z of member 3N-1 | Phi of member 0 ..]
+__global__ void createInitialBatchedZ(const std_complex* __restrict__ initialState, std_complex* __restrict__ ZBatched, double eps,
+                                      size_t N) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= 2 * N) return;
+    const size_t b = blockIdx.y, c = b / N, j = b % N;
+    const bool position = tid < N;
+    const size_t i = position ? tid : tid - N;
+    std_complex v = initialState[tid];
+    if (i == j) {
+        if (position && c == 0) v += std_complex(eps, 0.0);
+        else if (position && c == 1) v += std_complex(0.0, eps);
+        else if (!position && c == 2) v += std_complex(eps, 0.0);
+    }
+    ZBatched[(position ? 0 : 3 * N * N) + b * N + i] = v;
+}
+
+// pos / neg: batched RHS (6 N^2 complex) at +eps / -eps; C: 3N x 3N column-major, C[c * 3N + r] = d f_r / d y_c
+__global__ void createJacobianMatrixFromPerturbedRhs(const std_complex* __restrict__ pos, const std_complex* __restrict__ neg,
+                                                     double* __restrict__ C, size_t N, double eps) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * N * N) return;
+    const std_complex d = (pos[i] - neg[i]) / (2.0 * eps);
+    const size_t k = i / N, p = i % N;
+    if (k < 3 * N) {
+        C[k * 3 * N + p] = d.real();
+        C[k * 3 * N + p + N] = d.imag();
+    } else {
+        C[(k - 3 * N) * 3 * N + p + 2 * N] = d.real();
+    }
+}
+
+// ---- complex elementary functions the reference's tests call by name (T/ComplexFunctionsTests.cuh:8-158; L/utilities.cuh:59-63,
+//      270-286, 312-369).  The cotangent is evaluated as (sin u cos u - i sinh v cosh v) / (sin^2 u + sinh^2 v): every term of the
+//      denominator is non-negative, so there is no cancellation anywhere in the plane. ------------------------------------------------
+__device__ inline void sin(cuDoubleComplex z, cuDoubleComplex& zout) {
+    double s, c;
+    sincos(z.x, &s, &c);
+    zout.x = s * cosh(z.y);
+    zout.y = c * sinh(z.y);
+}
+__device__ inline void cos(cuDoubleComplex z, cuDoubleComplex& out) {
+    double s, c;
+    sincos(z.x, &s, &c);
+    out.x = c * cosh(z.y);
+    out.y = -s * sinh(z.y);
+}
+__device__ inline cuDoubleComplex cotangent_complex(cuDoubleComplex a) {
+    const double2 r = rb_dev::cot_half(2.0 * a.x, 2.0 * a.y);
+    return make_cuDoubleComplex(r.x, r.y);
+}
+__global__ void cotangent_complex(const cuDoubleComplex* a, cuDoubleComplex* out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = cotangent_complex(a[i]);
+}
+__device__ __forceinline__ std_complex cot(std_complex z) {
+    const double2 r = rb_dev::cot_half(2.0 * z.real(), 2.0 * z.imag());
+    return std_complex(r.x, r.y);
+}
+// cot((Zk - Zj) / 2), the kernel of every operator on this path
+__device__ inline std_complex cotangent_green_function(std_complex Zk, std_complex Zj) {
+    const double2 r = rb_dev::cot_half(Zk.real() - Zj.real(), Zk.imag() - Zj.imag());
+    return std_complex(r.x, r.y);
+}
+
+// ---- double-double helpers pinned by T/ComplexFunctionsTests.cuh:247-405 (L/PrecisionMath.cuh) -----------------------------------------
+namespace PrecisionMath {
+struct doubledouble {
+    double hi, lo;
+};
+struct dd_complex {
+    doubledouble real;
+    doubledouble imag;
+};
+// a - b = hi + lo exactly (Knuth's branch-free two-sum applied to a and -b)
+__host__ __device__ __forceinline__ void twoDiff(double a, double b, double& hi, double& lo) {
+    hi = a - b;
+    const double bb = a - hi;          // the part of b that was actually subtracted
+    lo = (a - (hi + bb)) + (bb - b);
+}
+// a * b = hi + lo exactly
+__device__ __forceinline__ void twoProd(double a, double b, double& hi, double& lo) {
+    hi = a * b;
+    lo = fma(a, b, -hi);
+}
+__device__ __forceinline__ dd_complex c_twoDiff(std_complex z1, std_complex z2) {
+    dd_complex d;
+    twoDiff(z1.real(), z2.real(), d.real.hi, d.real.lo);
+    twoDiff(z1.imag(), z2.imag(), d.imag.hi, d.imag.lo);
+    return d;
+}
+// 1 / (Z1 - Z2) with the difference and its squared modulus carried in double-double: conj(d) / |d|^2
+__device__ inline std_complex fastPreciseInvSub(std_complex Z1, std_complex Z2) {
+    const dd_complex d = c_twoDiff(Z1, Z2);
+    double rh, rl, ih, il;
+    twoProd(d.real.hi, d.real.hi, rh, rl);
+    rl = fma(2.0 * d.real.hi, d.real.lo, rl);
+    twoProd(d.imag.hi, d.imag.hi, ih, il);
+    il = fma(2.0 * d.imag.hi, d.imag.lo, il);
+    double sh, sl;
+    twoDiff(rh, -ih, sh, sl);          // rh + ih = sh + sl
+    sl += rl + il;
+    const double den = sh + sl, den_lo = sl - (den - sh);
+    double inv = 1.0 / den;
+    inv = fma(inv, fma(-den, inv, 1.0) - den_lo * inv, inv);   // one Newton step against den + den_lo
+    return std_complex((d.real.hi + d.real.lo) * inv, -(d.imag.hi + d.imag.lo) * inv);
+}
+}  // namespace PrecisionMath
+

@@ -476,11 +476,169 @@ static void test_implicit() {
                 diff, moved);
 }
 
+// ---- the complex elementary functions and double-double helpers the reference's tests call by name
+// (CuSuperHelium.Tests/ComplexFunctionsTests.cuh) and the perturbed-state kernels of Kernels.BatchedFormationForJacobian
+// (MatrixMTests.cuh:284-390).  Run with `compat_test --functions`. ----------------------------------------------------------------
+__global__ void complexSinKernel(cuDoubleComplex* zs, cuDoubleComplex* out, int N) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N) sin(zs[idx], out[idx]);
+}
+__global__ void complexCosKernel(cuDoubleComplex* zs, cuDoubleComplex* out, int N) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N) cos(zs[idx], out[idx]);
+}
+__global__ void complexCotKernel(std_complex* zsk, std_complex* zsj, std_complex* out, int N) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N) out[idx] = cotangent_green_function(zsk[idx], zsj[idx]);
+}
+__global__ void test_precision_inversion(std_complex* zsk, std_complex* zsj, std_complex* out, int N) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N) out[idx] = PrecisionMath::fastPreciseInvSub(zsk[idx], zsj[idx]);
+}
+__global__ void test_precision_substraction(std_complex* zsk, std_complex* zsj, std_complex* out, std_complex* low, int N) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N) {
+        PrecisionMath::dd_complex d = PrecisionMath::c_twoDiff(zsk[idx], zsj[idx]);
+        out[idx] = std_complex(d.real.hi, d.imag.hi);
+        low[idx] = std_complex(d.real.lo, d.imag.lo);
+    }
+}
+
+static void test_functions() {
+    constexpr int N = 256;
+    // sin, cos, cot along the diagonal of the first period (imaginary parts up to 2 pi: cosh ~ 268)
+    std::vector<cuDoubleComplex> zs(N), r1(N), r2(N), r3(N);
+    for (int i = 0; i < N; ++i) {
+        const double v = 2 * PI_d / (N + 1) * (i + 1);
+        zs[i] = make_cuDoubleComplex(v, v);
+    }
+    cuDoubleComplex *dz = toDevice(zs), *dout = nullptr;
+    cudaMalloc(&dout, N * sizeof(cuDoubleComplex));
+    complexSinKernel<<<1, N>>>(dz, dout, N);
+    cudaMemcpy(r1.data(), dout, N * sizeof(cuDoubleComplex), cudaMemcpyDeviceToHost);
+    complexCosKernel<<<1, N>>>(dz, dout, N);
+    cudaMemcpy(r2.data(), dout, N * sizeof(cuDoubleComplex), cudaMemcpyDeviceToHost);
+    cotangent_complex<<<1, N>>>(dz, dout, N);
+    cudaMemcpy(r3.data(), dout, N * sizeof(cuDoubleComplex), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < N; ++i) {
+        const cd z(zs[i].x, zs[i].y), s = std::sin(z), c = std::cos(z), ct = c / s;
+        EXPECT_NEAR(std::abs(cd(r1[i].x, r1[i].y) - s) / std::abs(s), 0.0, 4e-15, "complex sin");
+        EXPECT_NEAR(std::abs(cd(r2[i].x, r2[i].y) - c) / std::abs(c), 0.0, 4e-15, "complex cos");
+        EXPECT_NEAR(std::abs(cd(r3[i].x, r3[i].y) - ct) / std::abs(ct), 0.0, 1e-14, "complex cot");
+    }
+    // known answers (mpmath, 40 digits): cot(1e-3 + 2e-3 i), cot(0.7 - 1.3 i), cot(3 + 40 i)
+    {
+        std::vector<cuDoubleComplex> q = {make_cuDoubleComplex(1e-3, 2e-3), make_cuDoubleComplex(0.7, -1.3), make_cuDoubleComplex(3.0, 40.0)};
+        const cd expect[3] = {cd(199.99966666691110686, -400.00066666662221382), cd(0.14933231644907048137, 1.0145011371447459055),
+                              cd(-1.0086068994196989300e-35, -1.0)};
+        cuDoubleComplex* dq = toDevice(q);
+        cotangent_complex<<<1, 32>>>(dq, dq, 3);
+        cudaMemcpy(q.data(), dq, 3 * sizeof(cuDoubleComplex), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 3; ++i) {
+            EXPECT_NEAR(q[i].x, expect[i].real(), 2e-15 * std::abs(expect[i]), "cot known answer (real)");
+            EXPECT_NEAR(q[i].y, expect[i].imag(), 2e-15 * std::abs(expect[i]), "cot known answer (imag)");
+        }
+        cudaFree(dq);
+    }
+    // ComplexFunctionsTests.ComplexCotKernel: Zk = pi (1 + i), Zj = Zk + 0.1 (1 + i); the reference's 50-digit value, its 1e-13
+    // ComplexFunctionsTests.PrecisionInv: Zk = i (1 + i), Zj = Zk - pi (1 + i) -> 1 / (pi (1 + i)), its 1e-13
+    // ComplexFunctionsTests.SubstractionPrecise: hi = -pi, lo = 0 (the subtraction is exact there)
+    {
+        constexpr int M = 16;
+        std::vector<std_complex> zk(M), zj(M), zk2(M), zj2(M), zj3(M), out(M), low(M);
+        for (int i = 0; i < M; ++i) {
+            zk[i] = std_complex(PI_d, PI_d);
+            zj[i] = std_complex(PI_d + 0.1, PI_d + 0.1);
+            zk2[i] = std_complex(i, i);
+            zj2[i] = std_complex(i - PI_d, i - PI_d);
+            zj3[i] = std_complex(i + PI_d, i + PI_d);
+        }
+        std_complex *dk = toDevice(zk), *dj = toDevice(zj), *dk2 = toDevice(zk2), *dj2 = toDevice(zj2), *dj3 = toDevice(zj3);
+        std_complex *dres = nullptr, *dlow = nullptr;
+        cudaMalloc(&dres, M * sizeof(std_complex));
+        cudaMalloc(&dlow, M * sizeof(std_complex));
+        complexCotKernel<<<1, 256>>>(dk, dj, dres, M);
+        cudaMemcpy(out.data(), dres, M * sizeof(std_complex), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < M; ++i) {
+            EXPECT_NEAR(out[i].real(), -9.9833388915330681153509188355277398344111330657474, 1e-13, "cotangent_green_function (real)");
+            EXPECT_NEAR(out[i].imag(), 10.016672219575397493791065794281138271298250914604, 1e-13, "cotangent_green_function (imag)");
+        }
+        test_precision_inversion<<<1, 256>>>(dk2, dj2, dres, M);
+        cudaMemcpy(out.data(), dres, M * sizeof(std_complex), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < M; ++i) {
+            EXPECT_NEAR(out[i].real(), 0.15915494309189533576888376337251436203445964574046, 1e-13, "fastPreciseInvSub (real)");
+            EXPECT_NEAR(out[i].imag(), -0.15915494309189533576888376337251436203445964574046, 1e-13, "fastPreciseInvSub (imag)");
+        }
+        test_precision_substraction<<<1, 256>>>(dk2, dj3, dres, dlow, M);
+        cudaMemcpy(out.data(), dres, M * sizeof(std_complex), cudaMemcpyDeviceToHost);
+        cudaMemcpy(low.data(), dlow, M * sizeof(std_complex), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < M; ++i) {
+            const double exact = (double)i - ((double)i + PI_d);   // exact in double: the operands are within a factor 2..8 of each other
+            EXPECT_NEAR(out[i].real(), exact, 0.0, "c_twoDiff hi (real)");
+            EXPECT_NEAR(out[i].imag(), exact, 0.0, "c_twoDiff hi (imag)");
+            EXPECT_NEAR(out[i].real(), -PI_d, 4e-15, "c_twoDiff hi is -pi to the rounding of i + pi");
+            EXPECT_NEAR(low[i].real(), 0.0, 0.0, "c_twoDiff lo (real)");
+            EXPECT_NEAR(low[i].imag(), 0.0, 0.0, "c_twoDiff lo (imag)");
+        }
+        // and where the subtraction is NOT exact the low part carries what the high part lost
+        double hi, lo;
+        PrecisionMath::twoDiff(1.0, 1e-20, hi, lo);
+        EXPECT_NEAR(hi, 1.0, 0.0, "twoDiff hi");
+        EXPECT_NEAR(lo, -1e-20, 0.0, "twoDiff lo");
+        for (auto p : {dk, dj, dk2, dj2, dj3, dres, dlow}) cudaFree(p);
+    }
+    // Kernels.BatchedFormationForJacobian: the reference's launch geometry, checked entry by entry (the reference test only prints)
+    {
+        constexpr int NB = 64;
+        std::vector<double> state(3 * NB);
+        for (int i = 0; i < NB; ++i) {
+            const double j = 2 * PI_d * i / NB;
+            state[i] = X(j, 0.5, 10, 0.1);
+            state[NB + i] = Y(j, 0.5, 10, 0.1);
+            state[2 * NB + i] = PhiF(j, 0.5, 10, 0.1, 0.0);
+        }
+        const double eps = 1e-6;
+        double* dState = toDevice(state);
+        std_complex *dInit = nullptr, *dB = nullptr;
+        cudaMalloc(&dInit, 2 * NB * sizeof(std_complex));
+        cudaMalloc(&dB, 6 * NB * NB * sizeof(std_complex));
+        createInitialState<<<NB, 1>>>(dState, dInit, NB);
+        createInitialBatchedZ<<<dim3((2 * NB + 255) / 256, 3 * NB, 1), dim3(256, 1, 1)>>>(dInit, dB, eps, NB);
+        std::vector<std_complex> zb(6 * NB * NB);
+        cudaMemcpy(zb.data(), dB, zb.size() * sizeof(std_complex), cudaMemcpyDeviceToHost);
+        int bad = 0;
+        for (int b = 0; b < 3 * NB; ++b)
+            for (int i = 0; i < NB; ++i) {
+                const int c = b / NB, j = b % NB;
+                cd z(state[i], state[NB + i]), p(state[2 * NB + i], 0.0);
+                if (i == j) {
+                    if (c == 0) z += cd(eps, 0);
+                    if (c == 1) z += cd(0, eps);
+                    if (c == 2) p += cd(eps, 0);
+                }
+                const std_complex gz = zb[(size_t)b * NB + i], gp = zb[(size_t)3 * NB * NB + (size_t)b * NB + i];
+                if (gz.real() != z.real() || gz.imag() != z.imag() || gp.real() != p.real() || gp.imag() != p.imag()) ++bad;
+            }
+        EXPECT_NEAR((double)bad, 0.0, 0.0, "createInitialBatchedZ entries");
+        cudaFree(dState);
+        cudaFree(dInit);
+        cudaFree(dB);
+    }
+    cudaFree(dz);
+    cudaFree(dout);
+    std::printf("Complex functions, double-double helpers, perturbed-state kernels: failures so far %d\n", failures);
+}
+
 int main(int argc, char** argv) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
         std::printf("no CUDA device\n");
         return 2;
+    }
+    if (argc > 1 && std::string(argv[1]) == "--functions") {
+        test_functions();
+        std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL PASSED", failures);
+        return failures ? 1 : 0;
     }
     if (argc > 1 && std::string(argv[1]) == "--implicit") {
         test_implicit();

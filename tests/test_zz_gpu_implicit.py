@@ -272,3 +272,15 @@ def test_blocked_and_unblocked_lu_choose_the_same_pivots(api):
         assert api.lu_solve(dA, db, n, blocked) == 0
         xs.append(db.cpu().numpy())
     assert np.abs(xs[0] - xs[1]).max() <= 1e-12 * np.abs(xs[0]).max()
+
+
+def test_cpp_compat_header_named_functions(api):
+    """tests/cpp/compat_test.cu --functions: sin / cos / cotangent_complex / cotangent_green_function, PrecisionMath::c_twoDiff /
+    fastPreciseInvSub, createInitialState / createInitialBatchedZ under the reference's names and launch geometry, with the
+    reference's fixtures and tolerances (CuSuperHelium.Tests/ComplexFunctionsTests.cuh, MatrixMTests.cuh:284-390)."""
+    import subprocess
+    from superfluid_dynamics_b200 import build
+    exe = build.build_compat_test(verbose=False)
+    r = subprocess.run([exe, "--functions"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL PASSED" in r.stdout
