@@ -396,6 +396,7 @@ public:
     void initialize(T* devY0, bool onDevice = false) {
         rb_compat_check(rb_timed_rk4_initialize(st_, reinterpret_cast<rb_complex*>(devY0), onDevice), "rb_timed_rk4_initialize");
     }
+    void setCurrentStream(cudaStream_t) {}   // L/RK4_Time_Dependent.cuh:41-44: the stepper works on the stream of its integrator
     void runStep(int = 0) { rb_compat_check(rb_timed_rk4_step(st_, 0), "rb_timed_rk4_step"); }
     OdeSolverResult runEvolution(double startTime, double endTime) {
         size_t n = 0;
