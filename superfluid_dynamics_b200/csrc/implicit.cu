@@ -292,7 +292,7 @@ struct Staging {
 };
 
 // residualAndPhi, L/GaussLegendre.cuh:589-611: stage states of the slopes k (2n: k1 | k2), f at both, R = k - f, phi = |R|^2 / 2.
-// One host synchronisation.  An RHS whose inner solve did not converge is an error (the reference's LU cannot fail that way).
+// One host synchronisation.
 static Staging gl2_residual_and_phi(rb_gl2* g, const double* y, const double* k, double h) {
     const size_t n = g->n;
     cudaStream_t st = gl2_stream(g);
@@ -352,9 +352,11 @@ static bool gl2_step(rb_gl2* g, const double* ycur, double* dest, double h) {
     RB_CUDA(cudaMemcpyAsync(k + n, k, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
 
     Staging sr{};
+    bool have_sr = false;   // an accepted trial leaves its residual, stage states and norms in place: not evaluated twice
     size_t it = 0;
     for (; it < o.maxNewtonIterations; ++it) {
-        sr = gl2_residual_and_phi(g, ycur, k, h);
+        if (!have_sr) sr = gl2_residual_and_phi(g, ycur, k, h);
+        have_sr = false;
         if (sr.residualNorm <= o.newtonTolerance * (1.0 + sr.normK)) {
             res.converged = 1;
             break;
@@ -391,6 +393,8 @@ static bool gl2_step(rb_gl2* g, const double* ycur, double* dest, double h) {
             first_trial = false;
             if (tr.phi <= target) {
                 std::swap(k, ktrial);
+                sr = tr;
+                have_sr = true;
                 break;
             }
             alpha *= o.backtrack;
@@ -409,7 +413,7 @@ static bool gl2_step(rb_gl2* g, const double* ycur, double* dest, double h) {
             }
         }
     }
-    if (!res.converged) sr = gl2_residual_and_phi(g, ycur, k, h);
+    if (!res.converged && !have_sr) sr = gl2_residual_and_phi(g, ycur, k, h);
     gl2_next_state_kernel<<<blocks_for(n), 256, 0, st>>>(ycur, h, k, k + n, dest, n);
     launched();
     res.numberIterations = it;
