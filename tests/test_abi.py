@@ -106,3 +106,11 @@ def test_header_is_plain_c_and_ctypes_layouts_match_it(tmp_path):
         assert ctypes.sizeof(c) == int(size), name
         for f, o in zip(probes[name], offs):
             assert getattr(c, f).offset == int(o), (name, f)
+
+
+def test_cpp_compat_translation_unit_compiles_and_links(lib):
+    """tests/cpp/compat_test.cu (the reference's class and kernel names from include/cusuperhelium_compat.cuh, the App / Tests / Export
+    usage patterns) must compile for sm_100a and link against the library here, without a GPU; running it is the GPU tier's job."""
+    from superfluid_dynamics_b200 import build
+    exe = build.build_compat_test(verbose=False)
+    assert os.path.exists(exe) and os.access(exe, os.X_OK)
