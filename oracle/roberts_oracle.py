@@ -710,7 +710,15 @@ def jacobian_fd(y: np.ndarray, N: int, props: ProblemProperties, physics: str = 
     B = 3 * N
     pos = rhs(perturbed_states(s, N, eps), N, B, props, physics, deriv)
     neg = rhs(perturbed_states(s, N, -eps), N, B, props, physics, deriv)
-    d = (pos - neg) / (2.0 * eps)
+    return jacobian_from_perturbed(pos, neg, N, eps)
+
+
+def jacobian_from_perturbed(pos: np.ndarray, neg: np.ndarray, N: int, eps: float) -> np.ndarray:
+    """createJacobianMatrixFromPerturbedRhs (L/JacobianCalculator.cuh:92-156): pos / neg are the batched RHS [w of member 0 .. w of
+    member 3N-1 | dPhi/dt of member 0 ..] at +eps / -eps; returns J[r, c] (the reference's buffer is J.ravel(order="F"))."""
+    B = 3 * N
+    diff = np.asarray(pos) - np.asarray(neg)
+    d = diff.real / (2.0 * eps) + 1j * (diff.imag / (2.0 * eps))   # complex / real is component-wise in libcu++ (numpy's is not, to the ulp)
     J = np.empty((3 * N, 3 * N))
     w = d[:B * N].reshape(B, N)       # member c: velocity rows
     p = d[B * N:].reshape(B, N)       # member c: dPhi/dt rows

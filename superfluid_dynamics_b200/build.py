@@ -27,7 +27,7 @@ def build(force=False, verbose=True):
     os.makedirs(LIBDIR, exist_ok=True)
     objdir = os.path.join(LIBDIR, "obj")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, "internal.cuh"), os.path.join(HERE, "..", "include", "roberts_b200.h"),
+    headers = [os.path.join(CSRC, "internal.cuh"), os.path.join(CSRC, "implicit_kernels.cuh"), os.path.join(CSRC, "launch.cuh"), os.path.join(HERE, "..", "include", "roberts_b200.h"),
                os.path.join(HERE, "..", "include", "roberts_b200_device.cuh")]
     objs = []
     procs = []

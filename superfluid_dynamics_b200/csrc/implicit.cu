@@ -22,7 +22,16 @@
 #include <vector>
 
 #include "../../include/roberts_b200.h"
+// The host logic below also compiles under g++ with tests/cpp/cuda_emu.h standing in for the CUDA runtime and a mock of the RHS
+// assembler behind it (RB_EMULATE, tests/cpp/emu_implicit.cpp): the CPU test tier drives rb_jacobian_* / rb_gl2_* and the legacy
+// exports through the reference's trajectories without a GPU (tests/test_kernel_emulation.py).
+#ifdef RB_EMULATE
+#include "cuda_emu.h"
+#else
 #include "internal.cuh"
+#endif
+#include "implicit_kernels.cuh"
+#include "launch.cuh"
 
 using namespace rb;
 
@@ -45,147 +54,6 @@ T* dmalloc(size_t n) {
 
 void check_rc(int rc, const char* what) {
     if (rc != 0) throw std::runtime_error(std::string(what) + ": " + rb_last_error());
-}
-
-// ---- real <-> complex state ---------------------------------------------------------------------------------------------------
-// [x | y | phi] -> [x + i y | phi + 0 i]
-__global__ void real_to_complex_state_kernel(const double* __restrict__ y, double2* __restrict__ s, int N) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    s[i] = make_double2(y[i], y[N + i]);
-    s[N + i] = make_double2(y[2 * N + i], 0.0);
-}
-
-// [w | dPhi/dt] -> [Re w | Im w | Re dPhi/dt]
-__global__ void complex_to_real_rhs_kernel(const double2* __restrict__ r, double* __restrict__ out, int N) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const double2 w = r[i];
-    out[i] = w.x;
-    out[N + i] = w.y;
-    out[2 * N + i] = r[N + i].x;
-}
-
-// ---- finite-difference Jacobian -----------------------------------------------------------------------------------------------
-// grid (ceil(N / 256), 3N, 1 or 2): member b = blockIdx.y = c N + j has coordinate c of point j moved by +eps (z == 0, into `pos`)
-// or -eps (z == 1, into `neg`).  Batched layout: Z of member b at [b N, (b + 1) N), Phi of member b at 3 N^2 + [b N, (b + 1) N).
-__global__ void perturbed_states_kernel(const double2* __restrict__ state, double2* __restrict__ pos, double2* __restrict__ neg,
-                                        double eps, int N) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int b = blockIdx.y;
-    const int c = b / N, j = b - c * N;
-    const double e = blockIdx.z ? -eps : eps;
-    double2* __restrict__ out = blockIdx.z ? neg : pos;
-    double2 z = state[i];
-    double2 p = state[N + i];
-    if (i == j) {
-        if (c == 0) z.x += e;
-        else if (c == 1) z.y += e;
-        else p.x += e;
-    }
-    const size_t BN = (size_t)3 * N * N;
-    out[(size_t)b * N + i] = z;
-    out[BN + (size_t)b * N + i] = p;
-}
-
-// rhs of the batch: [w of member 0 .. w of member 3N-1 | dPhi/dt of member 0 ..]; C is 3N x 3N column-major, column = member
-__global__ void jacobian_from_perturbed_kernel(const double2* __restrict__ pos, const double2* __restrict__ neg,
-                                               double* __restrict__ C, int N, double eps) {
-    const size_t total = (size_t)6 * N * N;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const double2 a = pos[i], m = neg[i];
-    const double d = 2.0 * eps;
-    const double re = (a.x - m.x) / d, im = (a.y - m.y) / d;
-    const size_t k = i / N, p = i - k * N;
-    const size_t n3 = (size_t)3 * N;
-    if (k < n3) {
-        C[k * n3 + p] = re;
-        C[k * n3 + p + N] = im;
-    } else {
-        C[(k - n3) * n3 + p + 2 * N] = re;
-    }
-}
-
-// ---- Gauss-Legendre-2 (L/GLCoefficients.hpp) ----------------------------------------------------------------------------------
-constexpr double kSqrt3 = 1.7320508075688772935;
-constexpr double kA11 = 0.25, kA12 = 0.25 - kSqrt3 / 6.0, kA21 = 0.25 + kSqrt3 / 6.0, kA22 = 0.25;
-constexpr double kB1 = 0.5, kB2 = 0.5;
-
-// y_i = y + h sum_j a_ij k_j
-__global__ void gl2_stage_states_kernel(const double* __restrict__ y, double h, const double* __restrict__ k1,
-                                        const double* __restrict__ k2, double* __restrict__ y1, double* __restrict__ y2, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double a = k1[i], b = k2[i], v = y[i];
-    y1[i] = v + h * (kA11 * a + kA12 * b);
-    y2[i] = v + h * (kA21 * a + kA22 * b);
-}
-
-// R = k - f(y_stage) over both stages (2n entries) with sum R^2 and sum k^2 in the same pass: ONE CTA, fixed summation order
-// (the Newton / Armijo decisions taken from these sums are then reproducible run to run)
-constexpr int kNormThreads = 1024;
-__global__ void __launch_bounds__(kNormThreads) gl2_residual_kernel(const double* __restrict__ fy, const double* __restrict__ k,
-                                                                    double* __restrict__ R, size_t n2, double* __restrict__ sums) {
-    __shared__ double sr[kNormThreads], sk[kNormThreads];
-    double ar = 0.0, ak = 0.0;
-    for (size_t i = threadIdx.x; i < n2; i += kNormThreads) {
-        const double kv = k[i];
-        const double r = kv - fy[i];
-        R[i] = r;
-        ar += r * r;
-        ak += kv * kv;
-    }
-    sr[threadIdx.x] = ar;
-    sk[threadIdx.x] = ak;
-    __syncthreads();
-    for (int w = kNormThreads / 2; w > 0; w >>= 1) {
-        if ((int)threadIdx.x < w) {
-            sr[threadIdx.x] += sr[threadIdx.x + w];
-            sk[threadIdx.x] += sk[threadIdx.x + w];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        sums[0] = sr[0];
-        sums[1] = sk[0];
-    }
-}
-
-// k_trial = k + alpha dK
-__global__ void gl2_trial_kernel(const double* __restrict__ k, double alpha, const double* __restrict__ dK, double* __restrict__ kt,
-                                 size_t n2) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n2) kt[i] = k[i] + alpha * dK[i];
-}
-
-// dK <- -R (right-hand side of the Newton system; the LU solves in place)
-__global__ void gl2_negate_kernel(const double* __restrict__ R, double* __restrict__ out, size_t n2) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n2) out[i] = -R[i];
-}
-
-// Jacobian of the stage residual, 2n x 2n column-major: block (i, j) = delta_ij I - h a_ij J_i  (J_i n x n column-major)
-__global__ void gl2_newton_matrix_kernel(const double* __restrict__ J1, const double* __restrict__ J2, double h,
-                                         double* __restrict__ M, size_t n) {
-    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // row: consecutive threads -> consecutive addresses
-    const size_t c = (size_t)blockIdx.y * blockDim.y + threadIdx.y;
-    if (r >= n || c >= n) return;
-    const double j1 = J1[r + c * n], j2 = J2[r + c * n];
-    const double d = r == c ? 1.0 : 0.0;
-    const size_t ld = 2 * n;
-    M[r + c * ld] = d - h * kA11 * j1;
-    M[r + (c + n) * ld] = -h * kA12 * j1;
-    M[r + n + c * ld] = -h * kA21 * j2;
-    M[r + n + (c + n) * ld] = d - h * kA22 * j2;
-}
-
-// y_next = y + h (b1 k1 + b2 k2)
-__global__ void gl2_next_state_kernel(const double* __restrict__ y, double h, const double* __restrict__ k1,
-                                      const double* __restrict__ k2, double* __restrict__ out, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = y[i] + h * (kB1 * k1[i] + kB2 * k2[i]);
 }
 
 inline unsigned blocks_for(size_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
@@ -222,13 +90,13 @@ static cudaStream_t jacobian_stream(rb_jacobian* j) { return (cudaStream_t)rb_ge
 static void jacobian_calculate(rb_jacobian* j, const double* state_real, double* jac) {
     const int N = j->N;
     cudaStream_t st = jacobian_stream(j);
-    real_to_complex_state_kernel<<<blocks_for(N), 256, 0, st>>>(state_real, j->state, N);
+    RB_LAUNCH_EW(real_to_complex_state_kernel, blocks_for(N), 256, st, state_real, j->state, N);
     launched();
-    perturbed_states_kernel<<<dim3(blocks_for(N), 3 * N, 2), 256, 0, st>>>(j->state, j->zpos, j->zneg, j->eps, N);
+    RB_LAUNCH_EW(perturbed_states_kernel, dim3(blocks_for(N), 3 * N, 2), 256, st, j->state, j->zpos, j->zneg, j->eps, N);
     launched();
     check_rc(rb_rhs(j->batched, (const rb_complex*)j->zpos, (rb_complex*)j->rpos), "rb_rhs (Jacobian, +eps)");
     check_rc(rb_rhs(j->batched, (const rb_complex*)j->zneg, (rb_complex*)j->rneg), "rb_rhs (Jacobian, -eps)");
-    jacobian_from_perturbed_kernel<<<blocks_for((size_t)6 * N * N), 256, 0, st>>>(j->rpos, j->rneg, jac, N, j->eps);
+    RB_LAUNCH_EW(jacobian_from_perturbed_kernel, blocks_for((size_t)6 * N * N), 256, st, j->rpos, j->rneg, jac, N, j->eps);
     launched();
     ++j->calls;
 }
@@ -275,10 +143,10 @@ static void gl2_free(rb_gl2* g) {
 // RealBoundaryItegralCalculator<N>::run, L/RealBoundaryIntegralCalculator.cuh:59-70
 static void real_rhs(rb_solver* s, double2* cstate, double2* crhs, const double* y, double* out, int N) {
     cudaStream_t st = (cudaStream_t)rb_get_stream(s);
-    real_to_complex_state_kernel<<<blocks_for(N), 256, 0, st>>>(y, cstate, N);
+    RB_LAUNCH_EW(real_to_complex_state_kernel, blocks_for(N), 256, st, y, cstate, N);
     launched();
     check_rc(rb_rhs(s, (const rb_complex*)cstate, (rb_complex*)crhs), "rb_rhs");
-    complex_to_real_rhs_kernel<<<blocks_for(N), 256, 0, st>>>(crhs, out, N);
+    RB_LAUNCH_EW(complex_to_real_rhs_kernel, blocks_for(N), 256, st, crhs, out, N);
     launched();
 }
 
@@ -296,11 +164,11 @@ struct Staging {
 static Staging gl2_residual_and_phi(rb_gl2* g, const double* y, const double* k, double h) {
     const size_t n = g->n;
     cudaStream_t st = gl2_stream(g);
-    gl2_stage_states_kernel<<<blocks_for(n), 256, 0, st>>>(y, h, k, k + n, g->ystage, g->ystage + n, n);
+    RB_LAUNCH_EW(gl2_stage_states_kernel, blocks_for(n), 256, st, y, h, k, k + n, g->ystage, g->ystage + n, n);
     launched();
     gl2_rhs(g, g->ystage, g->fy);
     gl2_rhs(g, g->ystage + n, g->fy + n);
-    gl2_residual_kernel<<<1, kNormThreads, 0, st>>>(g->fy, k, g->R, 2 * n, g->sums);
+    RB_LAUNCH(gl2_residual_kernel, 1, kNormThreads, st, g->fy, k, g->R, 2 * n, g->sums);
     launched();
     RB_CUDA(cudaMemcpyAsync(g->h_sums, g->sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     RB_CUDA(cudaStreamSynchronize(st));
@@ -370,10 +238,10 @@ static bool gl2_step(rb_gl2* g, const double* ycur, double* dest, double h) {
         }
         {
             dim3 th(32, 8), bl(blocks_for(n, 32), blocks_for(n, 8));
-            gl2_newton_matrix_kernel<<<bl, th, 0, st>>>(J1, J2, h, g->M, n);
+            RB_LAUNCH_EW(gl2_newton_matrix_kernel, bl, th, st, J1, J2, h, g->M, n);
             launched();
         }
-        gl2_negate_kernel<<<blocks_for(2 * n), 256, 0, st>>>(g->R, g->dK, 2 * n);
+        RB_LAUNCH_EW(gl2_negate_kernel, blocks_for(2 * n), 256, st, g->R, g->dK, 2 * n);
         launched();
         launch_lu_solve(g->M, g->dK, (int)(2 * n), g->lu_info, st);   // MatrixSolver<6N,1>::solve, :487
         RB_CUDA(cudaMemcpyAsync(g->h_info, g->lu_info, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -385,7 +253,7 @@ static bool gl2_step(rb_gl2* g, const double* ycur, double* dest, double h) {
         double target = sr.phi - o.armijo_c * alpha * r2;
         bool first_trial = true;
         while (true) {
-            gl2_trial_kernel<<<blocks_for(2 * n), 256, 0, st>>>(k, alpha, g->dK, ktrial, 2 * n);
+            RB_LAUNCH_EW(gl2_trial_kernel, blocks_for(2 * n), 256, st, k, alpha, g->dK, ktrial, 2 * n);
             launched();
             Staging tr = gl2_residual_and_phi(g, ycur, ktrial, h);   // synchronises: h_info is valid from here on
             if (first_trial && *g->h_info != 0)
@@ -414,7 +282,7 @@ static bool gl2_step(rb_gl2* g, const double* ycur, double* dest, double h) {
         }
     }
     if (!res.converged && !have_sr) sr = gl2_residual_and_phi(g, ycur, k, h);
-    gl2_next_state_kernel<<<blocks_for(n), 256, 0, st>>>(ycur, h, k, k + n, dest, n);
+    RB_LAUNCH_EW(gl2_next_state_kernel, blocks_for(n), 256, st, ycur, h, k, k + n, dest, n);
     launched();
     res.numberIterations = it;
     res.residualNorm = sr.residualNorm;
@@ -513,8 +381,8 @@ int rb_real_rhs(rb_solver* s, const double* state_real_dev, double* rhs_real_dev
 int rb_perturbed_states(const rb_complex* state_dev, rb_complex* batched_dev, double eps, int N, void* cuda_stream) {
     RB_TRY
     if (!state_dev || !batched_dev || N < 1) throw std::runtime_error("rb_perturbed_states: bad argument");
-    perturbed_states_kernel<<<dim3(blocks_for(N), 3 * N, 1), 256, 0, (cudaStream_t)cuda_stream>>>(
-        (const double2*)state_dev, (double2*)batched_dev, nullptr, eps, N);
+    RB_LAUNCH_EW(perturbed_states_kernel, dim3(blocks_for(N), 3 * N, 1), 256, (cudaStream_t)cuda_stream, (const double2*)state_dev,
+                 (double2*)batched_dev, nullptr, eps, N);
     launched();
     RB_CATCH
 }
@@ -779,7 +647,7 @@ int calculatePerturbedStates256(const double* x, const double* y, const double* 
     double2* d = dmalloc<double2>(2 * N + big);
     try {
         RB_CUDA(cudaMemcpy(d, host.data(), 2 * N * sizeof(double2), cudaMemcpyHostToDevice));
-        perturbed_states_kernel<<<dim3(blocks_for(N), 3 * N, 1), 256>>>(d, d + 2 * N, nullptr, epsilon, N);
+        RB_LAUNCH_EW(perturbed_states_kernel, dim3(blocks_for(N), 3 * N, 1), 256, nullptr, d, d + 2 * N, nullptr, epsilon, N);
         launched();
         RB_CUDA(cudaMemcpy(Zperturbed, d + 2 * N, big * sizeof(double2), cudaMemcpyDeviceToHost));
     } catch (...) {

@@ -15,7 +15,14 @@
 //   lu_gemv_kernel    b2  -= L21 b1
 // then the back substitution with U (dense_kernels.cu).  STATUS: written after round 1's GPU minutes were spent; selected only
 // when asked for (RB_LU_BLOCKED=1 or rb_lu_solve(..., blocked = 1)) until it has passed tests/test_zz_gpu_implicit.py on hardware.
+// The kernels and the launch sequence below also compile under g++ with tests/cpp/cuda_emu.h standing in for the CUDA headers
+// (RB_EMULATE): the CPU test tier runs them thread for thread against LAPACK (tests/test_kernel_emulation.py).
+#ifdef RB_EMULATE
+#include "cuda_emu.h"
+#else
 #include "internal.cuh"
+#endif
+#include "launch.cuh"
 
 namespace rb {
 
@@ -131,9 +138,11 @@ __global__ void __launch_bounds__(128) lu_trsm_kernel(double* __restrict__ A, do
         if (i < kb) colp[i] = x[i];
 }
 
+#ifndef RB_EMULATE
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+#endif
 
 constexpr int kTile = 64;
 constexpr int kGemmThreads = 256;
@@ -203,33 +212,38 @@ __global__ void lu_gemv_kernel(const double* __restrict__ A, double* __restrict_
 
 }  // namespace
 
-void launch_lu_backsolve(const double* A, double* b, int n, cudaStream_t st);   // dense_kernels.cu
-
-void launch_lu_solve_blocked(double* A, double* b, int n, int* info, cudaStream_t st) {
+// the factorisation with b eliminated on the fly: on return A holds U in its upper triangle and b holds L^{-1} P b
+void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) {
     int* piv = nullptr;   // pivot rows, stream-ordered allocation: no synchronisation, no state shared between streams
     RB_CUDA(cudaMallocAsync(&piv, (size_t)std::max(n, 1) * sizeof(int), st));
     RB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     int launches = 0;
     for (int k0 = 0; k0 < n; k0 += kNB) {
         const int kb = std::min(kNB, n - k0);
-        lu_panel_kernel<<<1, kPanelThreads, 0, st>>>(A, n, k0, kb, piv, info);
+        RB_LAUNCH(lu_panel_kernel, 1, kPanelThreads, st, A, n, k0, kb, piv, info);
         const int right = n - k0 - kb + 1;   // columns right of the panel, b included
-        lu_swap_kernel<<<(right + 127) / 128, 128, 0, st>>>(A, b, n, k0, kb, piv);
-        lu_trsm_kernel<<<(right + 127) / 128, 128, 0, st>>>(A, b, n, k0, kb);
+        RB_LAUNCH(lu_swap_kernel, (right + 127) / 128, 128, st, A, b, n, k0, kb, (const int*)piv);
+        RB_LAUNCH(lu_trsm_kernel, (right + 127) / 128, 128, st, A, b, n, k0, kb);
         launches += 3;
         const int m = n - k0 - kb;
         if (m > 0) {
             const int tiles = (m + kTile - 1) / kTile;
-            lu_gemm_kernel<<<dim3(tiles, tiles), kGemmThreads, 0, st>>>(A, n, k0, kb);
-            lu_gemv_kernel<<<(m + 255) / 256, 256, 0, st>>>(A, b, n, k0, kb);
+            RB_LAUNCH(lu_gemm_kernel, dim3(tiles, tiles), kGemmThreads, st, A, n, k0, kb);
+            RB_LAUNCH(lu_gemv_kernel, (m + 255) / 256, 256, st, (const double*)A, b, n, k0, kb);
             launches += 2;
         }
     }
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(piv, st);
     RB_CUDA(e);
-    launch_lu_backsolve(A, b, n, st);
     count_launch(launches);
 }
+
+#ifndef RB_EMULATE
+void launch_lu_solve_blocked(double* A, double* b, int n, int* info, cudaStream_t st) {
+    lu_factor_blocked(A, b, n, info, st);
+    launch_lu_backsolve(A, b, n, st);   // dense_kernels.cu
+}
+#endif
 
 }  // namespace rb
