@@ -284,3 +284,36 @@ def test_cpp_compat_header_named_functions(api):
     r = subprocess.run([exe, "--functions"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ALL PASSED" in r.stdout
+
+
+def test_jacobian_columns_are_central_differences_of_the_reference_rhs(api):
+    """The reference's JacobianCalculator cannot be compiled here (its batch-3N calculator does not pass a conforming compiler), but
+    by construction its columns are central differences of the reference's RHS: a sample of columns of rb_jacobian_calculate
+    against (f(y + eps e_c) - f(y - eps e_c)) / 2 eps with f the REFERENCE'S OWN CUDA RHS (oracle/_ref, child process), N = 64."""
+    from oracle import ref_runner
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref/libcusuperhelium_ref.so not built")
+    N, depth, eps = 64, 0.3, 1e-6
+    props = api.ProblemProperties(rho=1.0, depth=depth)
+    prob = api.HeliumBoundaryProblem(props)
+    y = film(N, depth, 0.1)
+    cols = [0, 5, 31, 63, N + 1, N + 17, 2 * N - 1, 2 * N, 2 * N + 40, 3 * N - 1]
+    pd = dict(rho=1.0, kappa=0.0, depth=depth, U=0.0, use_expansions=False, expansion_order=1, infinite_depth=False)
+    jobs = []
+    for c in cols:
+        for sgn in (1.0, -1.0):
+            yy = y.copy()
+            yy[c] += sgn * eps
+            jobs.append(dict(op="rhs", kind="helium", N=N, props=pd, state=ro.real_to_complex_state(yy, N)))
+    res = ref_runner.run_jobs(jobs, timeout=300)
+    assert all("error" not in r for r in res), [r.get("error") for r in res if "error" in r][:2]
+    jc = api.JacobianCalculator(N, props, prob)
+    jc.setEpsilon(eps)
+    J = torch.zeros(9 * N * N, dtype=torch.float64, device="cuda:0")
+    jc.calculateJacobian(T(y), J)
+    torch.cuda.synchronize()
+    got = J.cpu().numpy().reshape(3 * N, 3 * N).T
+    scale = np.abs(got).max()
+    for i, c in enumerate(cols):
+        fp, fm = (ro.complex_to_real_rhs(res[2 * i + k]["rhs"], N) for k in (0, 1))
+        assert np.abs(got[:, c] - (fp - fm) / (2 * eps)).max() <= 1e-6 * scale, c
