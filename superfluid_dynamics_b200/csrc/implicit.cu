@@ -115,6 +115,8 @@ struct rb_gl2 {
     double *ynext = nullptr, *k = nullptr, *ktrial = nullptr, *ystage = nullptr, *fy = nullptr, *R = nullptr, *dK = nullptr;
     double *J1 = nullptr, *J2 = nullptr, *Jf = nullptr, *M = nullptr;
     double2 *cstate = nullptr, *crhs = nullptr;   // RealBoundaryItegralCalculator's devComplexState / devComplexRHS
+    rb_solver* s2 = nullptr;       // owned batch-2 assembler: both stage states in one RHS evaluation
+    double2 *cstate2 = nullptr, *crhs2 = nullptr;   // its [Z_1 | Z_2 | Phi_1 | Phi_2] state and RHS (4N each)
     double* sums = nullptr;        // device [2]
     double* h_sums = nullptr;      // pinned [2]
     int* lu_info = nullptr;
@@ -134,6 +136,9 @@ static void gl2_free(rb_gl2* g) {
     for (void* p : {(void*)g->ynext, (void*)g->k, (void*)g->ktrial, (void*)g->ystage, (void*)g->fy, (void*)g->R, (void*)g->dK, (void*)g->J1,
                     (void*)g->J2, (void*)g->Jf, (void*)g->M, (void*)g->cstate, (void*)g->crhs, (void*)g->sums, (void*)g->lu_info,
                     (void*)g->log})
+        if (p) cudaFree(p);
+    if (g->s2) rb_destroy(g->s2);
+    for (void* p : {(void*)g->cstate2, (void*)g->crhs2})
         if (p) cudaFree(p);
     if (g->h_sums) cudaFreeHost(g->h_sums);
     if (g->h_info) cudaFreeHost(g->h_info);
@@ -160,14 +165,17 @@ struct Staging {
 };
 
 // residualAndPhi, L/GaussLegendre.cuh:589-611: stage states of the slopes k (2n: k1 | k2), f at both, R = k - f, phi = |R|^2 / 2.
-// One host synchronisation.
+// Both stages go through the batch-2 assembler as one RHS evaluation; one host synchronisation.
 static Staging gl2_residual_and_phi(rb_gl2* g, const double* y, const double* k, double h) {
     const size_t n = g->n;
     cudaStream_t st = gl2_stream(g);
-    RB_LAUNCH_EW(gl2_stage_states_kernel, blocks_for(n), 256, st, y, h, k, k + n, g->ystage, g->ystage + n, n);
+    RB_LAUNCH_EW(gl2_stage_states_batched_kernel, blocks_for(g->N), 256, st, y, h, k, k + n, g->ystage, g->ystage + n, g->cstate2,
+                 g->N);
     launched();
-    gl2_rhs(g, g->ystage, g->fy);
-    gl2_rhs(g, g->ystage + n, g->fy + n);
+    check_rc(rb_rhs(g->s2, (const rb_complex*)g->cstate2, (rb_complex*)g->crhs2), "rb_rhs (both stages)");
+    RB_LAUNCH_EW(gl2_batched_rhs_to_real_kernel, blocks_for(g->N), 256, st, g->crhs2, g->fy, g->N);
+    launched();
+    g->stats.rhs_evaluations += 2;
     RB_LAUNCH(gl2_residual_kernel, 1, kNormThreads, st, g->fy, k, g->R, 2 * n, g->sums);
     launched();
     RB_CUDA(cudaMemcpyAsync(g->h_sums, g->sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -179,7 +187,7 @@ static Staging gl2_residual_and_phi(rb_gl2* g, const double* y, const double* k,
     // slopes that throw the stage states far off the surface can leave the inner solve (or the sums) without an answer: such
     // slopes are simply not acceptable to the line search
     double stats[6];
-    check_rc(rb_solve_stats(g->s, stats), "rb_solve_stats");
+    check_rc(rb_solve_stats(g->s2, stats), "rb_solve_stats");
     if (stats[1] == 0.0 || !(r.phi == r.phi)) {
         r.phi = HUGE_VAL;
         r.residualNorm = HUGE_VAL;
@@ -501,6 +509,16 @@ rb_gl2* rb_gl2_create(rb_solver* s, rb_jacobian* j, const rb_gl2_options* option
         g->J2 = dmalloc<double>(n * n);
         g->Jf = dmalloc<double>(n * n);
         g->M = dmalloc<double>(4 * n * n);
+        {
+            rb_props p2;
+            check_rc(rb_get_props(s, &p2, nullptr, nullptr), "rb_get_props");
+            p2.compute_energies = 0;
+            g->s2 = rb_create(N, 2, &p2);
+            if (!g->s2) throw std::runtime_error(std::string("rb_create (batch 2): ") + rb_last_error());
+            check_rc(rb_set_stream(g->s2, rb_get_stream(s)), "rb_set_stream (stage assembler)");
+            g->cstate2 = dmalloc<double2>((size_t)4 * N);
+            g->crhs2 = dmalloc<double2>((size_t)4 * N);
+        }
         g->cstate = dmalloc<double2>((size_t)2 * N);
         g->crhs = dmalloc<double2>((size_t)2 * N);
         g->sums = dmalloc<double>(2);

@@ -78,14 +78,41 @@ constexpr double kSqrt3 = 1.7320508075688772935;
 constexpr double kA11 = 0.25, kA12 = 0.25 - kSqrt3 / 6.0, kA21 = 0.25 + kSqrt3 / 6.0, kA22 = 0.25;
 constexpr double kB1 = 0.5, kB2 = 0.5;
 
-// y_i = y + h sum_j a_ij k_j
-__global__ void gl2_stage_states_kernel(const double* __restrict__ y, double h, const double* __restrict__ k1,
-                                        const double* __restrict__ k2, double* __restrict__ y1, double* __restrict__ y2, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double a = k1[i], b = k2[i], v = y[i];
-    y1[i] = v + h * (kA11 * a + kA12 * b);
-    y2[i] = v + h * (kA21 * a + kA22 * b);
+// stage states y_i = y + h sum_j a_ij k_j, written once as the real vectors y1 | y2 (what the Jacobians are taken at) and once as the batch-2 complex
+// state [Z_1 | Z_2 | Phi_1 | Phi_2] of the RHS assembler: both stages are then ONE batched RHS evaluation
+__global__ void gl2_stage_states_batched_kernel(const double* __restrict__ y, double h, const double* __restrict__ k1,
+                                                const double* __restrict__ k2, double* __restrict__ y1, double* __restrict__ y2,
+                                                double2* __restrict__ cstate, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double s1[3], s2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const size_t q = (size_t)c * N + i;
+        const double a = k1[q], b = k2[q], v = y[q];
+        s1[c] = v + h * (kA11 * a + kA12 * b);
+        s2[c] = v + h * (kA21 * a + kA22 * b);
+        y1[q] = s1[c];
+        y2[q] = s2[c];
+    }
+    cstate[i] = make_double2(s1[0], s1[1]);
+    cstate[N + i] = make_double2(s2[0], s2[1]);
+    cstate[2 * N + i] = make_double2(s1[2], 0.0);
+    cstate[3 * N + i] = make_double2(s2[2], 0.0);
+}
+
+// batched RHS [w_1 | w_2 | dPhi_1/dt | dPhi_2/dt] -> f(y1) | f(y2) as real vectors [Re w | Im w | Re dPhi/dt] each
+__global__ void gl2_batched_rhs_to_real_kernel(const double2* __restrict__ crhs, double* __restrict__ fy, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t n = (size_t)3 * N;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const double2 w = crhs[m * N + i];
+        fy[m * n + i] = w.x;
+        fy[m * n + N + i] = w.y;
+        fy[m * n + 2 * N + i] = crhs[2 * N + m * N + i].x;
+    }
 }
 
 // R = k - f(y_stage) over both stages (2n entries) with sum R^2 and sum k^2 in the same pass: ONE CTA, fixed summation order

@@ -31,8 +31,14 @@ void emu_jacobian_from_perturbed(const double* pos, const double* neg, double* C
                     (const double2*)neg, C, N, eps);
 }
 
-void emu_gl2_stage_states(const double* y, double h, const double* k, double* ystage, size_t n) {
-    emu::launch_seq(gl2_stage_states_kernel, dim3(blocks_for(n)), dim3(256), y, h, k, k + n, ystage, ystage + n, n);
+// both stage states as real vectors (ystage = y1 | y2) and as the batch-2 complex state cstate = [Z_1 | Z_2 | Phi_1 | Phi_2]
+void emu_gl2_stage_states_batched(const double* y, double h, const double* k, double* ystage, double* cstate, int N) {
+    const size_t n = (size_t)3 * N;
+    emu::launch_seq(gl2_stage_states_batched_kernel, dim3(blocks_for(N)), dim3(256), y, h, k, k + n, ystage, ystage + n, (double2*)cstate, N);
+}
+
+void emu_gl2_batched_rhs_to_real(const double* crhs, double* fy, int N) {
+    emu::launch_seq(gl2_batched_rhs_to_real_kernel, dim3(blocks_for(N)), dim3(256), (const double2*)crhs, fy, N);
 }
 
 void emu_gl2_residual(const double* fy, const double* k, double* R, size_t n2, double* sums) {

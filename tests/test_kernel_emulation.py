@@ -76,15 +76,27 @@ def test_jacobian_from_perturbed_kernel(emu, N):
 
 
 def test_gauss_legendre_elementwise_kernels(emu):
-    n = 3 * 41
+    N = 41
+    n = 3 * N
     rng = np.random.default_rng(2)
     y, k, dK, fy = rng.standard_normal(n), rng.standard_normal(2 * n), rng.standard_normal(2 * n), rng.standard_normal(2 * n)
     h, alpha = 0.037, 0.25
     st = np.zeros(2 * n)
-    emu.emu_gl2_stage_states(_p(y), ctypes.c_double(h), _p(k), _p(st), ctypes.c_size_t(n))
+    cs = np.zeros(4 * N, np.complex128)
+    emu.emu_gl2_stage_states_batched(_p(y), ctypes.c_double(h), _p(k), _p(st), _p(cs.view(np.float64)), N)
     A = ro.GL_A
-    assert np.abs(st[:n] - (y + h * (A[0][0] * k[:n] + A[0][1] * k[n:]))).max() <= 1e-15
-    assert np.abs(st[n:] - (y + h * (A[1][0] * k[:n] + A[1][1] * k[n:]))).max() <= 1e-15
+    y1 = y + h * (A[0][0] * k[:n] + A[0][1] * k[n:])
+    y2 = y + h * (A[1][0] * k[:n] + A[1][1] * k[n:])
+    assert np.abs(st[:n] - y1).max() <= 1e-15 and np.abs(st[n:] - y2).max() <= 1e-15
+    # the batch-2 state [Z_1 | Z_2 | Phi_1 | Phi_2] holds exactly the same numbers as the real stage states
+    s1, s2 = ro.real_to_complex_state(st[:n], N), ro.real_to_complex_state(st[n:], N)
+    assert np.array_equal(cs, np.concatenate([s1[:N], s2[:N], s1[N:], s2[N:]]))
+    # and the batched RHS comes back as f(y1) | f(y2) in the real layout
+    r1, r2 = rng.standard_normal(2 * N) + 1j * rng.standard_normal(2 * N), rng.standard_normal(2 * N) + 1j * rng.standard_normal(2 * N)
+    crhs = np.concatenate([r1[:N], r2[:N], r1[N:], r2[N:]])
+    f12 = np.zeros(2 * n)
+    emu.emu_gl2_batched_rhs_to_real(_p(crhs.view(np.float64)), _p(f12), N)
+    assert np.array_equal(f12, np.concatenate([ro.complex_to_real_rhs(r1, N), ro.complex_to_real_rhs(r2, N)]))
     kt = np.zeros(2 * n)
     emu.emu_gl2_trial(_p(k), ctypes.c_double(alpha), _p(dK), _p(kt), ctypes.c_size_t(2 * n))
     assert np.abs(kt - (k + alpha * dK)).max() <= 1e-15
