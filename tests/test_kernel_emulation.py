@@ -24,9 +24,10 @@ def _p(a):
 @pytest.fixture(scope="module")
 def emu():
     src = os.path.join(ROOT, "tests", "cpp", "emu_kernels.cpp")
-    out = os.path.join(ROOT, "superfluid_dynamics_b200", "lib", "libemu_kernels.so")
+    out = os.path.join(ROOT, "tests", "cpp", "_build", "libemu_kernels.so")
     deps = [src, os.path.join(ROOT, "tests", "cpp", "cuda_emu.h"), os.path.join(ROOT, "superfluid_dynamics_b200", "csrc", "lu_kernels.cu"),
-            os.path.join(ROOT, "superfluid_dynamics_b200", "csrc", "implicit_kernels.cuh")]
+            os.path.join(ROOT, "superfluid_dynamics_b200", "csrc", "implicit_kernels.cuh"),
+            os.path.join(ROOT, "superfluid_dynamics_b200", "csrc", "launch.cuh")]
     os.makedirs(os.path.dirname(out), exist_ok=True)
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DRB_EMULATE", "-I",
@@ -159,8 +160,9 @@ def impl():
     """libemu_implicit.so: implicit.cu compiled by g++ (kernels emulated, CUDA runtime stubbed), rb_rhs forwarded to the oracle."""
     from superfluid_dynamics_b200 import _lib
     src = os.path.join(ROOT, "tests", "cpp", "emu_implicit.cpp")
-    out = os.path.join(ROOT, "superfluid_dynamics_b200", "lib", "libemu_implicit.so")
+    out = os.path.join(ROOT, "tests", "cpp", "_build", "libemu_implicit.so")
     csrc = os.path.join(ROOT, "superfluid_dynamics_b200", "csrc")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     deps = [src, os.path.join(ROOT, "tests", "cpp", "cuda_emu.h"), os.path.join(csrc, "implicit.cu"), os.path.join(csrc, "implicit_kernels.cuh"),
             os.path.join(csrc, "launch.cuh"), os.path.join(ROOT, "include", "roberts_b200.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
