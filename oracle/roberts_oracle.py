@@ -824,7 +824,7 @@ def gl2_integrate(f, J, y0: np.ndarray, t0: float, t1: float, opt: GaussLegendre
     min(stepSize, |t1 - t|) in the direction of t1; a step whose Newton iteration fails is retried with half the size, at most
     maxStepsHalves times and not below |t1 - t0| / 2^20, and the reduced size is kept for the following steps.  The trajectory
     starts with (t0, y0).  Returns (times, states) -- with returnTrajectory off, ([], [final state])."""
-    if opt.stepSize < 0.0:
+    if not opt.stepSize > 0.0:
         raise ValueError("Step size must be positive.")
     y = np.asarray(y0, np.float64).copy()
     total = abs(t1 - t0)

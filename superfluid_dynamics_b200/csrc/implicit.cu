@@ -322,7 +322,7 @@ static void gl2_log_append(rb_gl2* g, double t) {
 // the same object would start from whatever sliver the first one ended with.
 static void gl2_evolve(rb_gl2* g, double t0, double t1) {
     const rb_gl2_options& o = g->opt;
-    if (o.stepSize < 0.0) throw std::invalid_argument("Step size must be positive.");
+    if (!(o.stepSize > 0.0)) throw std::invalid_argument("Step size must be positive.");   // the reference tests < 0 only: 0 (or NaN) never ends
     if (!g->y) throw std::runtime_error("Initial state not set. Call initialize() before running evolution.");
     const size_t n = g->n;
     cudaStream_t st = gl2_stream(g);

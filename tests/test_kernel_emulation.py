@@ -325,6 +325,11 @@ def test_implicit_host_logic_options_steps_and_failures(impl):
     # an evolution that cannot converge reports it the way the reference throws it
     assert impl.rb_gl2_evolve(g, 0.0, 0.1) == -1
     assert b"failed to converge" in impl.rb_last_error()
+    # a step size that can never reach the end time is refused (the reference's `< 0` test lets 0 through, into an endless loop)
+    o.stepSize = 0.0
+    impl.rb_gl2_set_options(g, ctypes.byref(o))
+    assert impl.rb_gl2_evolve(g, 0.0, 0.1) == -1 and b"Step size must be positive" in impl.rb_last_error()
+    o.stepSize = c["h"]
     # inner solves that do not converge make every slope unacceptable: same outcome, no hang
     o.newtonTolerance, o.maxNewtonIterations = 1e-10, 20
     impl.rb_gl2_set_options(g, ctypes.byref(o))
