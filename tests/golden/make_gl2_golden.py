@@ -24,6 +24,10 @@ CASES = {
     "helium_film_N16_backward": ("helium", 16, 0.3, 0.05, 0.5, 0.0, 0.05, 1e-10, 20, False, 6),
     "helium_thin_N16_fallback": ("helium", 16, 0.0942478, 0.1, 0.0, 0.23, 0.1, 1e-11, 12, True, 6),
     "water_N16": ("water", 16, 1.0, 0.1, 0.0, 0.3, 0.1, 1e-10, 20, False, 6),
+    # a step too long for 8 Newton iterations: the first attempt fails, the halved step converges and is kept
+    "helium_thin_N16_halving": ("helium", 16, 0.0942478, 0.5, 0.0, 6.0, 6.0, 1e-11, 8, True, 6),
+    # the line search gives up, the Jacobian is frozen at the base point (simplified Newton), the step is halved all the same
+    "helium_thin_N16_fallback_halving": ("helium", 16, 0.0942478, 0.6, 0.0, 3.0, 3.0, 1e-11, 8, True, 6),
 }
 
 

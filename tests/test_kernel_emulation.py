@@ -272,7 +272,8 @@ def _gl2_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_gl2.npz"))
 
 
-@pytest.mark.parametrize("name", ["helium_film_N16", "helium_film_N16_backward", "helium_thin_N16_fallback", "water_N16"])
+@pytest.mark.parametrize("name", ["helium_film_N16", "helium_film_N16_backward", "helium_thin_N16_fallback", "water_N16", "helium_thin_N16_halving",
+                                  "helium_thin_N16_fallback_halving"])
 def test_implicit_host_logic_reproduces_reference_gl2_trajectories(impl, name):
     """rb_gl2_evolve as implicit.cu runs it (Newton iteration, Armijo search, step control, logging) over the oracle's RHS: the
     trajectory of the reference's own Python integrator (golden), to 1e-12 (the Newton systems are solved by a different LU)."""
@@ -289,7 +290,8 @@ def test_implicit_host_logic_reproduces_reference_gl2_trajectories(impl, name):
     assert impl.rb_gl2_get_state(g, _p(final)) == 0 and np.array_equal(final, states[-1])
     st = impl._lib.rb_gl2_stats()
     assert impl.rb_gl2_get_stats(g, ctypes.byref(st)) == 0
-    assert st.converged == 1 and st.steps_accepted == len(c["T"]) - 1 and st.steps_halved == 0
+    assert st.converged == 1 and st.steps_accepted == len(c["T"]) - 1
+    assert (st.steps_halved > 0) == ("halving" in name)
     assert st.jacobians == 2 * st.linear_solves or c["fallback"]
     for h_, f_ in ((g, impl.rb_gl2_destroy), (j, impl.rb_jacobian_destroy), (s, impl.rb_destroy)):
         f_(h_)

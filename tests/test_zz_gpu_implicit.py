@@ -131,7 +131,8 @@ def _integrator(api, c, trajectory=True):
     return api.GaussLegendre2(real, jc, opt)
 
 
-@pytest.mark.parametrize("name", ["helium_film_N16", "helium_film_N16_backward", "helium_thin_N16_fallback", "water_N16"])
+@pytest.mark.parametrize("name", ["helium_film_N16", "helium_film_N16_backward", "helium_thin_N16_fallback", "water_N16", "helium_thin_N16_halving",
+                                  "helium_thin_N16_fallback_halving"])
 def test_gl2_matches_reference_python_integrator(api, name):
     """rb_gl2_evolve against the trajectory of the reference's own P/integration/gauss_legendre.py (golden): same accepted steps
     and times; states to 1e-8 absolute (positions are O(2 pi): 1.6e-9 relative; Newton tolerance 1e-10 per step on both sides)."""
