@@ -22,6 +22,12 @@
 #include <vector>
 
 #define RB_EMULATE 1
+#ifdef RB_EMU_CUDA_HEADERS
+// For sources that include the toolkit's own headers (include/cusuperhelium_compat.cuh: cuda_runtime.h, cuComplex.h, libcu++): the
+// types and the __global__ / __device__ markers are the toolkit's (they compile under g++ as they stand); only the execution model
+// -- the index variables and the launch loops below -- is supplied here.  No runtime call is stubbed in this mode.
+#include <cuda_runtime.h>
+#else
 #define __global__
 #define __device__
 #define __host__
@@ -44,6 +50,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;
+#endif
 
 namespace emu {
 struct Warp {
@@ -94,10 +101,12 @@ inline void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     d1 = s1;
 }
 
+#ifndef RB_EMU_CUDA_HEADERS
 inline void sincos(double x, double* s, double* c) {
     *s = std::sin(x);
     *c = std::cos(x);
 }
+#endif
 
 namespace emu {
 
@@ -153,6 +162,7 @@ void launch_coop(K kernel, dim3 grid, dim3 block, A... args) {
 
 }  // namespace emu
 
+#ifndef RB_EMU_CUDA_HEADERS
 // the handful of runtime calls the host code makes: device memory is host memory here, every stream is synchronous
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 template <typename T>
@@ -200,3 +210,4 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 namespace rb {
 inline void count_launch(int = 1) {}
 }  // namespace rb
+#endif  // RB_EMU_CUDA_HEADERS

@@ -375,3 +375,112 @@ def test_implicit_host_logic_legacy_exports(impl):
                               ro.GaussLegendre2Options(stepSize=0.1))
     assert len(times) == len(To) and np.abs(times - To).max() <= 1e-15
     assert states.shape == Yo.shape and np.abs(states - Yo).max() <= 1e-12
+
+
+# ---- the named functions / kernels of include/cusuperhelium_compat.cuh (tests/cpp/emu_compat.cpp) ------------------------------------
+@pytest.fixture(scope="module")
+def compat():
+    src = os.path.join(ROOT, "tests", "cpp", "emu_compat.cpp")
+    out = os.path.join(ROOT, "tests", "cpp", "_build", "libemu_compat.so")
+    deps = [src, os.path.join(ROOT, "tests", "cpp", "cuda_emu.h"), os.path.join(ROOT, "include", "cusuperhelium_compat.cuh"),
+            os.path.join(ROOT, "include", "roberts_b200_device.cuh"), os.path.join(ROOT, "include", "roberts_b200.h")]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-I",
+                               os.path.join(ROOT, "tests", "cpp"), "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, src, "-o", out])
+    return ctypes.CDLL(out)
+
+
+def _c(a):
+    return np.ascontiguousarray(a, np.complex128)
+
+
+def test_compat_complex_functions_with_the_reference_fixtures(compat):
+    """sin / cos / cotangent_complex / cot / cotangent_green_function under the reference's names, on the fixtures of
+    T/ComplexFunctionsTests.cuh (the diagonal of the first period; Zk = pi (1 + i), Zj = Zk + 0.1 (1 + i) with the reference's
+    50-digit value and its 1e-13) and on known answers computed with mpmath at 40 digits."""
+    N = 256
+    v = 2 * np.pi / (N + 1) * (np.arange(N) + 1)
+    z = _c(v + 1j * v)
+    out = np.zeros_like(z)
+    compat.emuc_sin(_p(z.view(np.float64)), _p(out.view(np.float64)), N)
+    assert (np.abs(out - np.sin(z)) / np.abs(np.sin(z))).max() <= 4e-15
+    compat.emuc_cos(_p(z.view(np.float64)), _p(out.view(np.float64)), N)
+    assert (np.abs(out - np.cos(z)) / np.abs(np.cos(z))).max() <= 4e-15
+    ref = np.cos(z) / np.sin(z)
+    compat.emuc_cotangent_complex(_p(z.view(np.float64)), _p(out.view(np.float64)), N)
+    assert (np.abs(out - ref) / np.abs(ref)).max() <= 1e-14
+    out2 = np.zeros_like(z)
+    compat.emuc_cot(_p(z.view(np.float64)), _p(out2.view(np.float64)), N)
+    assert np.array_equal(out, out2)
+    q = _c([1e-3 + 2e-3j, 0.7 - 1.3j, 3.0 + 40.0j])
+    expect = np.array([199.99966666691110686 - 400.00066666662221382j, 0.14933231644907048137 + 1.0145011371447459055j,
+                       -1.0086068994196989300e-35 - 1.0j])
+    o3 = np.zeros_like(q)
+    compat.emuc_cotangent_complex(_p(q.view(np.float64)), _p(o3.view(np.float64)), 3)
+    assert (np.abs(o3 - expect) / np.abs(expect)).max() <= 1e-15
+    assert abs(o3[2].real - expect[2].real) <= 1e-15 * abs(expect[2].real)          # no cancellation where cosh - cos would lose everything
+    M = 16
+    zk = _c(np.full(M, np.pi + 1j * np.pi))
+    zj = _c(np.full(M, (np.pi + 0.1) + 1j * (np.pi + 0.1)))
+    g = np.zeros(M, np.complex128)
+    compat.emuc_green(_p(zk.view(np.float64)), _p(zj.view(np.float64)), _p(g.view(np.float64)), M)
+    assert np.abs(g.real + 9.9833388915330681153509188355277398344111330657474).max() <= 1e-13
+    assert np.abs(g.imag - 10.016672219575397493791065794281138271298250914604).max() <= 1e-13
+
+
+def test_compat_precision_math_with_the_reference_fixtures(compat):
+    """PrecisionMath::fastPreciseInvSub and c_twoDiff on the fixtures of T/ComplexFunctionsTests.cuh:247-405, plus what those
+    fixtures do not reach: a difference with catastrophic cancellation, where the double-double path must beat plain FP64."""
+    from fractions import Fraction
+    M = 16
+    i = np.arange(M, dtype=np.float64)
+    zk = _c(i + 1j * i)
+    zj = _c((i - np.pi) + 1j * (i - np.pi))
+    r = np.zeros(M, np.complex128)
+    compat.emuc_inv_sub(_p(zk.view(np.float64)), _p(zj.view(np.float64)), _p(r.view(np.float64)), M)
+    e = 0.15915494309189533576888376337251436203445964574046
+    assert np.abs(r.real - e).max() <= 1e-13 and np.abs(r.imag + e).max() <= 1e-13
+    zj3 = _c((i + np.pi) + 1j * (i + np.pi))
+    hi, lo = np.zeros(M, np.complex128), np.zeros(M, np.complex128)
+    compat.emuc_two_diff(_p(zk.view(np.float64)), _p(zj3.view(np.float64)), _p(hi.view(np.float64)), _p(lo.view(np.float64)), M)
+    assert np.array_equal(hi.real, i - (i + np.pi)) and np.array_equal(hi.imag, i - (i + np.pi))
+    assert np.abs(hi.real + np.pi).max() <= 4e-15 and not lo.real.any() and not lo.imag.any()
+    # hi + lo is the exact difference whatever the operands (error-free transformation): checked in rational arithmetic
+    a = _c([1.0 + 3.0j, 1e16 + 1.0j, 0.1 + 0.2j])
+    b = _c([1e-20 + 1e-30j, 1.0 + 1e16j, 0.3 - 0.7j])
+    hi, lo = np.zeros(3, np.complex128), np.zeros(3, np.complex128)
+    compat.emuc_two_diff(_p(a.view(np.float64)), _p(b.view(np.float64)), _p(hi.view(np.float64)), _p(lo.view(np.float64)), 3)
+    for k in range(3):
+        assert Fraction(hi[k].real) + Fraction(lo[k].real) == Fraction(a[k].real) - Fraction(b[k].real)
+        assert Fraction(hi[k].imag) + Fraction(lo[k].imag) == Fraction(a[k].imag) - Fraction(b[k].imag)
+    # 1 / (Z1 - Z2) for nearly equal operands whose difference is not exactly representable in one double
+    z1 = _c([(1.0 + 2.0 ** -30) + (1.0 + 2.0 ** -29) * 1j])
+    z2 = _c([2.0 ** -60 + (2.0 ** -61) * 1j])
+    r = np.zeros(1, np.complex128)
+    compat.emuc_inv_sub(_p(z1.view(np.float64)), _p(z2.view(np.float64)), _p(r.view(np.float64)), 1)
+    dre = Fraction(z1[0].real) - Fraction(z2[0].real)
+    dim = Fraction(z1[0].imag) - Fraction(z2[0].imag)
+    den = dre * dre + dim * dim
+    assert abs(Fraction(r[0].real) - dre / den) <= Fraction(1, 2 ** 51) * abs(dre / den)
+    assert abs(Fraction(r[0].imag) + dim / den) <= Fraction(1, 2 ** 51) * abs(dim / den)
+
+
+@pytest.mark.parametrize("N", [4, 64, 130])
+def test_compat_jacobian_kernels_in_the_reference_geometry(compat, N):
+    """createInitialState<<<N, 1>>>, createInitialBatchedZ<<<(ceil(2N/256), 3N), 256>>> (one thread per entry of the 2N-entry state, the
+    reference's geometry, T/MatrixMTests.cuh:334-364) and createJacobianMatrixFromPerturbedRhs against the oracle, bit for bit."""
+    rng = np.random.default_rng(N)
+    y = rng.standard_normal(3 * N)
+    st = np.zeros(2 * N, np.complex128)
+    compat.emuc_create_initial_state(_p(y), _p(st.view(np.float64)), ctypes.c_size_t(N))
+    assert np.array_equal(st, ro.real_to_complex_state(y, N))
+    zb = np.full(6 * N * N, np.nan + 0j)
+    compat.emuc_create_initial_batched_z(_p(st.view(np.float64)), _p(zb.view(np.float64)), ctypes.c_double(1e-6), ctypes.c_size_t(N))
+    assert np.array_equal(zb, ro.perturbed_states(st, N, 1e-6))
+    pos = rng.standard_normal(6 * N * N) + 1j * rng.standard_normal(6 * N * N)
+    neg = rng.standard_normal(6 * N * N) + 1j * rng.standard_normal(6 * N * N)
+    C = np.full(9 * N * N, np.nan)
+    compat.emuc_jacobian_from_perturbed(_p(pos.view(np.float64)), _p(neg.view(np.float64)), _p(C), ctypes.c_size_t(N), ctypes.c_double(1e-6))
+    assert np.array_equal(C, ro.jacobian_from_perturbed(pos, neg, N, 1e-6).ravel(order="F"))
