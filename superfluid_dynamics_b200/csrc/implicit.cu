@@ -128,6 +128,13 @@ struct rb_gl2 {
     rb_gl2_stats stats{};
 };
 
+// options the Armijo search cannot terminate with are refused up front (the reference would loop forever on them)
+static void gl2_check_options(const rb_gl2_options& o) {
+    if (!(o.backtrack > 0.0 && o.backtrack < 1.0)) throw std::invalid_argument("Gauss-Legendre options: backtrack must lie in (0, 1)");
+    if (!(o.minAlpha > 0.0)) throw std::invalid_argument("Gauss-Legendre options: minAlpha must be positive");
+    if (!(o.newtonTolerance >= 0.0)) throw std::invalid_argument("Gauss-Legendre options: newtonTolerance must not be negative");
+}
+
 static cudaStream_t gl2_stream(rb_gl2* g) { return (cudaStream_t)rb_get_stream(g->s); }
 
 static void gl2_free(rb_gl2* g) {
@@ -495,6 +502,7 @@ rb_gl2* rb_gl2_create(rb_solver* s, rb_jacobian* j, const rb_gl2_options* option
         g->s = s;
         g->jac = j;
         if (options) g->opt = *options; else rb_gl2_default_options(&g->opt);
+        gl2_check_options(g->opt);
         g->N = N;
         const size_t n = g->n = (size_t)3 * N;
         check_rc(rb_set_stream(j->batched, rb_get_stream(s)), "rb_set_stream (Jacobian)");   // one stream: plain program order
@@ -545,6 +553,7 @@ int rb_gl2_destroy(rb_gl2* g) {
 int rb_gl2_set_options(rb_gl2* g, const rb_gl2_options* options) {
     RB_TRY
     if (!g || !options) throw std::runtime_error("rb_gl2_set_options: null argument");
+    gl2_check_options(*options);
     g->opt = *options;
     RB_CATCH
 }

@@ -327,6 +327,10 @@ def test_implicit_host_logic_options_steps_and_failures(impl):
     # an evolution that cannot converge reports it the way the reference throws it
     assert impl.rb_gl2_evolve(g, 0.0, 0.1) == -1
     assert b"failed to converge" in impl.rb_last_error()
+    # options the line search could not terminate with are refused
+    o.backtrack = 1.0
+    assert impl.rb_gl2_set_options(g, ctypes.byref(o)) == -1 and b"backtrack" in impl.rb_last_error()
+    o.backtrack = 0.5
     # a step size that can never reach the end time is refused (the reference's `< 0` test lets 0 through, into an endless loop)
     o.stepSize = 0.0
     impl.rb_gl2_set_options(g, ctypes.byref(o))
