@@ -20,7 +20,38 @@ def film(N, depth, amp):
     return np.concatenate([a - 0.3 * amp * depth * np.sin(a), amp * depth * np.cos(a), 0.2 * amp * depth * np.sin(a)])
 
 
+def dense_mode_rhs_ms(N=4096, reps=3):
+    """BASELINE config 3 ("dense FP64 BIE solve", N = 4096): one RHS with M materialised and factorised (RB_SOLVE_DENSE_LU), through
+    whichever LU the environment selects (RB_LU_BLOCKED), checked against the matrix-free RHS."""
+    import torch
+    from superfluid_dynamics_b200 import api
+    dev = torch.device("cuda:0")
+    a = 2 * np.pi * np.arange(N) / N
+    y0 = np.concatenate([(a - 0.4 * np.sin(a)) + 1j * (0.4 * np.cos(a)), (0.4 * np.sin(a)).astype(np.complex128)])
+    props = api.ProblemProperties(rho=0.0)
+    st = torch.as_tensor(y0, device=dev)
+    outs = {}
+    res = {}
+    for mode in ("dense_lu", "matrix_free"):
+        calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), device=dev, solve_mode=mode)
+        out = torch.zeros(2 * N, dtype=torch.complex128, device=dev)
+        calc.run(st, out)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            calc.run(st, out)
+        torch.cuda.synchronize(dev)
+        res[mode + "_rhs_ms"] = (time.perf_counter() - t0) * 1e3 / reps
+        outs[mode] = out.cpu().numpy()
+    res["dense_vs_matrix_free_rel"] = float(np.abs(outs["dense_lu"] - outs["matrix_free"]).max() / np.abs(outs["matrix_free"]).max())
+    res["blocked_lu"] = os.environ.get("RB_LU_BLOCKED", "0")
+    return res
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--dense-mode":
+        print(json.dumps(dense_mode_rhs_ms()))
+        return
     out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "implicit_report.json")
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     import torch
@@ -69,6 +100,19 @@ def main():
         report["lu"][str(n)] = entry
         print("lu", n, entry, flush=True)
         json.dump(report, open(out_path, "w"), indent=1)
+
+    # the dense solve mode of the hot path at N = 4096 with either factorisation (the choice is read once per process)
+    import subprocess
+    report["dense_mode_N4096"] = {}
+    for blocked in ("0", "1"):
+        env = dict(os.environ, RB_LU_BLOCKED=blocked)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--dense-mode"], env=env, capture_output=True, text=True, timeout=240)
+            report["dense_mode_N4096"]["blocked" if blocked == "1" else "unblocked"] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:  # noqa: BLE001
+            report["dense_mode_N4096"]["blocked" if blocked == "1" else "unblocked"] = {"error": repr(e)[:300]}
+    print("dense mode", report["dense_mode_N4096"], flush=True)
+    json.dump(report, open(out_path, "w"), indent=1)
 
     depth = 0.0942478   # the App's film (A/kernel.cu:79)
     for N in (64, 256, 512):
