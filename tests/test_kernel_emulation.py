@@ -125,7 +125,7 @@ def test_newton_matrix_kernel(emu, n):
     assert np.abs(M.reshape(2 * n, 2 * n).T - exp).max() <= 1e-15      # column-major, every entry written
 
 
-@pytest.mark.parametrize("n", [1, 5, 31, 32, 33, 64, 65, 100, 131])
+@pytest.mark.parametrize("n", [1, 5, 31, 32, 33, 64, 65, 100, 131, 300])
 def test_blocked_lu_kernels_against_lapack(emu, n):
     """lu_kernels.cu thread for thread: panel (pivot search by shuffles, swaps, rank-1 updates), swap, trsm, the 64 x 64 trailing
     update on the emulated m8n8k4 mma, gemv, with b eliminated on the fly; then the upper-triangular solve here."""
