@@ -13,7 +13,7 @@
 //   lu_trsm_kernel    U12 = L11^{-1} A12 (and the same for b's block): one thread per column, L11 in shared memory
 //   lu_gemm_kernel    A22 -= L21 U12: 64 x 64 tiles, 8 warps, 2 x 4 DMMA tiles of 8 x 8 per warp, 8 k-steps of 4
 //   lu_gemv_kernel    b2  -= L21 b1
-// then the back substitution with U (dense_kernels.cu).  STATUS: written after round 1's GPU minutes were spent; selected only
+// then lu_backsolve_blocked_kernel: the back substitution with U, one CTA, 32 columns per pair of barriers.  STATUS: written after round 1's GPU minutes were spent; selected only
 // when asked for (RB_LU_BLOCKED=1 or rb_lu_solve(..., blocked = 1)) until it has passed tests/test_zz_gpu_implicit.py on hardware.
 // The kernels and the launch sequence below also compile under g++ with tests/cpp/cuda_emu.h standing in for the CUDA headers
 // (RB_EMULATE): the CPU test tier runs them thread for thread against LAPACK (tests/test_kernel_emulation.py).
@@ -210,6 +210,41 @@ __global__ void lu_gemv_kernel(const double* __restrict__ A, double* __restrict_
     b[i] = acc;
 }
 
+// U x = b in place, 32 columns at a time from the bottom: warp 0 solves the 32 x 32 triangle in shared memory, then every thread
+// subtracts that block's contribution from the rows above it (coalesced down the columns).  Two block-wide barriers per 32 columns
+// instead of two per column.
+constexpr int kBackThreads = 1024;
+__global__ void __launch_bounds__(kBackThreads) lu_backsolve_blocked_kernel(const double* __restrict__ A, double* __restrict__ b, int n) {
+    __shared__ double Us[kNB][kNB + 1];
+    __shared__ double xs[kNB];
+    const int tid = threadIdx.x;
+    for (int hi = n; hi > 0; hi -= kNB) {
+        const int k0 = hi > kNB ? hi - kNB : 0, w = hi - k0;
+        for (int idx = tid; idx < w * w; idx += kBackThreads) {
+            const int i = idx % w, j = idx / w;
+            Us[i][j] = A[(size_t)(k0 + j) * n + k0 + i];
+        }
+        if (tid < w) xs[tid] = b[k0 + tid];
+        __syncthreads();
+        if (tid < 32) {
+            for (int j = w - 1; j >= 0; --j) {
+                if (tid == j) xs[j] /= Us[j][j];
+                __syncwarp();
+                if (tid < j) xs[tid] -= Us[tid][j] * xs[j];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < k0; i += kBackThreads) {
+            double acc = b[i];
+            for (int j = 0; j < w; ++j) acc -= A[(size_t)(k0 + j) * n + i] * xs[j];
+            b[i] = acc;
+        }
+        if (tid < w) b[k0 + tid] = xs[tid];
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 // the factorisation with b eliminated on the fly: on return A holds U in its upper triangle and b holds L^{-1} P b
@@ -239,11 +274,11 @@ void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) 
     count_launch(launches);
 }
 
-#ifndef RB_EMULATE
 void launch_lu_solve_blocked(double* A, double* b, int n, int* info, cudaStream_t st) {
     lu_factor_blocked(A, b, n, info, st);
-    launch_lu_backsolve(A, b, n, st);   // dense_kernels.cu
+    RB_LAUNCH(lu_backsolve_blocked_kernel, 1, kBackThreads, st, (const double*)A, b, n);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
 }
-#endif
 
 }  // namespace rb

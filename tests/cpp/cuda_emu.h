@@ -71,6 +71,8 @@ inline void __syncthreads() {
     emu::block_bar->arrive_and_wait();
 }
 
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp->bar->arrive_and_wait(); }
+
 template <typename T>
 inline T __shfl_down_sync(unsigned, T v, int delta) {
     static_assert(sizeof(T) <= sizeof(long long), "shuffle of at most 8 bytes");

@@ -69,4 +69,11 @@ int emu_lu_factor_blocked(double* A, double* b, int n) {
     return info;
 }
 
+// the whole blocked solve: factorisation + blocked back substitution; b returns x
+int emu_lu_solve_blocked(double* A, double* b, int n) {
+    int info = 0;
+    rb::launch_lu_solve_blocked(A, b, n, &info, nullptr);
+    return info;
+}
+
 }  // extern "C"

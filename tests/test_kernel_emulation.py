@@ -144,6 +144,21 @@ def test_blocked_lu_kernels_against_lapack(emu, n):
     assert np.abs(A @ x - b).max() <= 1e-11 * np.abs(A).sum(axis=1).max() * np.abs(x).max()
 
 
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 70, 129])
+def test_blocked_lu_solve_with_blocked_back_substitution(emu, n):
+    """launch_lu_solve_blocked end to end: the factorisation above followed by lu_backsolve_blocked_kernel (warp-level triangle solve
+    in shared memory, block-wide update of the rows above); b returns the solution."""
+    rng = np.random.default_rng(200 + n)
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    Af = np.asfortranarray(A).ravel(order="F").copy()
+    x = b.copy()
+    emu.emu_lu_solve_blocked.restype = ctypes.c_int
+    assert emu.emu_lu_solve_blocked(_p(Af), _p(x), n) == 0
+    ref = np.linalg.solve(A, b)
+    assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
 def test_blocked_lu_reports_singular_column(emu):
     n = 70
     rng = np.random.default_rng(1)
