@@ -221,6 +221,24 @@ def comm_row_range(N, rank, nranks):
     return out[0], out[1]
 
 
+def ensemble_member_range(members, rank, nranks):
+    """Members [lo, hi) of an ensemble owned by `rank`: contiguous, sizes differing by at most one, the larger shares first.
+    Ensembles are replicas only -- every rank steps its own members with its own batched solver, nothing is exchanged
+    (SURVEY.md section 8e)."""
+    members, rank, nranks = int(members), int(rank), int(nranks)
+    if nranks < 1 or not 0 <= rank < nranks or members < 0:
+        raise ValueError("bad rank / nranks")
+    q, r = divmod(members, nranks)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def ensemble_state(member_states, N):
+    """Pack per-member states [Z_m | Phi_m] (2N complex each) into the batched layout [Z of every member | Phi of every member]."""
+    ms = [np.asarray(m, np.complex128) for m in member_states]
+    return np.concatenate([m[:N] for m in ms] + [m[N:2 * N] for m in ms])
+
+
 class AutonomousRungeKuttaStepper:
     """AutonomousRungeKuttaStepper<std_complex, 2N>(AutonomousProblem&, tstep, logger)."""
 

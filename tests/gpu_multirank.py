@@ -88,6 +88,39 @@ def main():
     ok = ok and good
     print(f"[rank {rank}] helium N={N} d={depth}: sharded vs single rel err {err:.2e}, {1.0 / res[0][1]:.2f} -> {1.0 / res[1][1]:.2f} "
           f"steps/s on {world} GPUs, {res[1][2]} {'OK' if good else 'FAIL'}", flush=True)
+    # BASELINE config 5, second half: the 1024-member ensemble at N = 512 spread over the ranks (replicas only: every rank steps its
+    # own members, nothing is exchanged); member m: trochoid h_m = 0.05 + 0.35 m / 1023.  Rank 0's first member is checked against
+    # the same member stepped alone.
+    N, B, dt, steps = 512, 1024, 1e-3, 20
+    lo, hi = api.ensemble_member_range(B, rank, world)
+    hs = 0.05 + 0.35 * np.arange(B) / (B - 1)
+    members = [ro.pack_state(*ro.trochoid(N, h)) for h in hs[lo:hi]]
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, hi - lo, props, api.WaterBoundaryProblem(props), device=dev, guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(calc, dt)
+    st = torch.as_tensor(api.ensemble_state(members, N), device=dev)
+    stp.initialize(st, True)
+    stp.runSteps(5)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    stp.runSteps(steps)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    alone = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), device=dev, guess="warm")
+    s1 = api.AutonomousRungeKuttaStepper(alone, dt)
+    s1.initialize(members[0], False)
+    s1.runSteps(5 + steps)
+    got = st.cpu().numpy()
+    mine = np.concatenate([got[:N], got[(hi - lo) * N:(hi - lo) * N + N]])
+    err = np.abs(mine - s1.getState()).max() / np.abs(mine).max()
+    good = err <= 1e-12 and bool(torch.isfinite(torch.view_as_real(st)).all().item())
+    ok = ok and good
+    print(f"[rank {rank}] ensemble {B} x N={N}: members [{lo}, {hi}), {B * steps / (t.item() * 1e-3):.0f} member-steps/s on {world} GPUs "
+          f"(max over ranks), first member vs stepped alone {err:.2e} {'OK' if good else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

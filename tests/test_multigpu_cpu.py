@@ -52,3 +52,24 @@ def test_handle_exchange_world_size_2_gloo():
     assert res[0][1] == [0, 1] and res[1][1] == [0, 1]          # every rank sees every handle, in rank order
     assert res[0][2] == [64, 64]
     assert (res[0][3], res[0][4], res[1][3], res[1][4]) == (0, 2048, 2048, 4096)
+
+
+def test_ensemble_partition_and_packing():
+    import numpy as np
+    from superfluid_dynamics_b200 import api
+    for B in (0, 1, 7, 1024, 1025):
+        for G in (1, 2, 3, 8):
+            ranges = [api.ensemble_member_range(B, r, G) for r in range(G)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == B
+            sizes = [hi - lo for lo, hi in ranges]
+            assert all(a1 == b0 for (_, a1), (b0, _) in zip(ranges, ranges[1:]))
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    with pytest.raises(ValueError):
+        api.ensemble_member_range(8, 2, 2)
+    N = 4
+    members = [np.arange(2 * N) + 100 * m + 0j for m in range(3)]
+    packed = api.ensemble_state(members, N)
+    assert packed.shape == (3 * 2 * N,)
+    for m in range(3):
+        assert np.array_equal(packed[m * N:(m + 1) * N], members[m][:N])
+        assert np.array_equal(packed[3 * N + m * N:3 * N + (m + 1) * N], members[m][N:])
