@@ -33,14 +33,15 @@ constexpr int kPanelThreads = 1024;
 
 __global__ void __launch_bounds__(kPanelThreads) lu_panel_kernel(double* A, int n, int k0, int kb, int* __restrict__ piv,
                                                                   int* __restrict__ info) {
-    __shared__ double s_val[32];
-    __shared__ int s_idx[32];
+    // Three block-wide barriers per column: (1) after the per-warp pivot candidates are in shared memory -- every warp then reduces
+    // the 32 candidates itself, so the winner needs no broadcast (the candidate arrays are double-buffered against the next column);
+    // (2) after the row interchange, which also leaves the pivot row in shared memory; (3) after the rank-1 update of the panel.
+    __shared__ double s_val[2][32];
+    __shared__ int s_idx[2][32];
     __shared__ double s_row[kNB];
-    __shared__ int s_p;
-    __shared__ double s_best;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int j = 0; j < kb; ++j) {
-        const int col = k0 + j;
+        const int col = k0 + j, buf = j & 1;
         double* cptr = A + (size_t)col * n;
         // pivot: largest |A[i, col]|, i >= col; ties to the lowest row (the choice of the unblocked kernel)
         double best = -1.0;
@@ -55,35 +56,32 @@ __global__ void __launch_bounds__(kPanelThreads) lu_panel_kernel(double* A, int 
             const int oi = __shfl_down_sync(0xffffffffu, bi, o);
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+        if (lane == 0) { s_val[buf][warp] = best; s_idx[buf][warp] = bi; }
         __syncthreads();
-        if (warp == 0) {
-            best = s_val[lane];
-            bi = s_idx[lane];
+        best = s_val[buf][lane];
+        bi = s_idx[buf][lane];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_down_sync(0xffffffffu, best, o);
-                const int oi = __shfl_down_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            if (lane == 0) {
-                s_p = bi;
-                s_best = best;
-                piv[col] = bi;
-                if (!(best > 0.0) && *info == 0) *info = col + 1;   // zero (or NaN) column: singular, as getrf's info
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, best, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
-        __syncthreads();
-        const int p = s_p;
-        const bool usable = s_best > 0.0;
-        if (p != col && tid < kb) {
+        best = __shfl_sync(0xffffffffu, best, 0);
+        const int p = __shfl_sync(0xffffffffu, bi, 0);
+        const bool usable = best > 0.0;
+        if (tid == 0) {
+            piv[col] = p;
+            if (!usable && *info == 0) *info = col + 1;   // zero (or NaN) column: singular, as getrf's info
+        }
+        if (tid < kb) {   // row interchange inside the panel; the thread that moves column k0 + tid also knows the new pivot-row entry
             double* q = A + (size_t)(k0 + tid) * n;
-            const double t = q[col];
-            q[col] = q[p];
-            q[p] = t;
+            const double top = q[col], low = q[p];
+            if (p != col) {
+                q[col] = low;
+                q[p] = top;
+            }
+            s_row[tid] = low;
         }
-        __syncthreads();
-        if (tid < kb) s_row[tid] = A[(size_t)(k0 + tid) * n + col];   // the pivot row inside the panel
         __syncthreads();
         if (usable) {
             const double pv = s_row[j];

@@ -85,6 +85,18 @@ inline T __shfl_down_sync(unsigned, T v, int delta) {
     return r;
 }
 
+template <typename T>
+inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) <= sizeof(long long), "shuffle of at most 8 bytes");
+    emu::Warp& w = *emu::warp;
+    std::memcpy(&w.ibuf[emu::lane], &v, sizeof(T));
+    w.bar->arrive_and_wait();
+    T r;
+    std::memcpy(&r, &w.ibuf[src & 31], sizeof(T));
+    w.bar->arrive_and_wait();
+    return r;
+}
+
 // mma.sync.aligned.m8n8k4.row.col.f64: D (8 x 8) += A (8 x 4) B (4 x 8); lane (g, t) holds A[g][t], B[t][g], D[g][2t], D[g][2t + 1]
 inline void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     emu::Warp& w = *emu::warp;
