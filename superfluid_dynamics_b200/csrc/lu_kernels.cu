@@ -6,11 +6,11 @@
 // Replaces (reference, L/ = CuSuperHelium/CuSuperHelium/): MatrixSolver<N,1>::solve = cusolverDnDgetrf + cusolverDnDgetrs,
 // L/MatrixSolver.cuh:114-125.
 //
-// Per panel of 32 columns, five launches:
-//   lu_panel_kernel   one CTA: pivot search (warp shuffles), row swap inside the panel, scale, rank-1 update of the panel
-//   lu_swap_kernel    the panel's row interchanges applied to the columns right of it and to b (the left part, L, is never read
-//                     again because b is eliminated on the fly, exactly as the unblocked kernels of dense_kernels.cu treat it)
-//   lu_trsm_kernel    U12 = L11^{-1} A12 (and the same for b's block): one thread per column, L11 in shared memory
+// Per panel of 32 columns, four launches:
+//   lu_panel_kernel      one CTA: pivot search (warp shuffles), row swap inside the panel, scale, rank-1 update of the panel
+//   lu_swap_trsm_kernel  one thread per column right of the panel and for b: the panel's row interchanges (the left part, L, is
+//                        never read again because b is eliminated on the fly, exactly as the unblocked kernels of dense_kernels.cu
+//                        treat it), then U12 = L11^{-1} A12 with L11 in shared memory
 //   lu_gemm_kernel    A22 -= L21 U12: 64 x 64 tiles, 8 warps, 2 x 4 DMMA tiles of 8 x 8 per warp, 8 k-steps of 4
 //   lu_gemv_kernel    b2  -= L21 b1
 // then lu_backsolve_blocked_kernel: the back substitution with U, one CTA, 32 columns per pair of barriers.  STATUS: written after round 1's GPU minutes were spent; selected only
@@ -98,30 +98,30 @@ __global__ void __launch_bounds__(kPanelThreads) lu_panel_kernel(double* A, int 
 // column c of the augmented matrix [A | b]: c == n addresses b
 __device__ __forceinline__ double* aug_column(double* A, double* b, int n, int c) { return c < n ? A + (size_t)c * n : b; }
 
-__global__ void lu_swap_kernel(double* __restrict__ A, double* __restrict__ b, int n, int k0, int kb, const int* __restrict__ piv) {
+// one thread per column right of the panel (b included): the panel's row interchanges, then U12 = L11^{-1} A12 with L11 (unit lower
+// triangular) in shared memory and the 32 entries of the column in registers
+__global__ void __launch_bounds__(128) lu_swap_trsm_kernel(double* __restrict__ A, double* __restrict__ b, int n, int k0, int kb,
+                                                           const int* __restrict__ piv) {
+    __shared__ double L[kNB][kNB + 1];
+    __shared__ int s_piv[kNB];
+    for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
+        const int i = idx % kb, j = idx / kb;
+        L[i][j] = A[(size_t)(k0 + j) * n + k0 + i];
+    }
+    if ((int)threadIdx.x < kb) s_piv[threadIdx.x] = piv[k0 + threadIdx.x];
+    __syncthreads();
     const int c = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n) return;
     double* colp = aug_column(A, b, n, c);
     for (int j = 0; j < kb; ++j) {
-        const int r = k0 + j, p = piv[r];
+        const int r = k0 + j, p = s_piv[j];
         if (p != r) {
             const double t = colp[r];
             colp[r] = colp[p];
             colp[p] = t;
         }
     }
-}
-
-__global__ void __launch_bounds__(128) lu_trsm_kernel(double* __restrict__ A, double* __restrict__ b, int n, int k0, int kb) {
-    __shared__ double L[kNB][kNB + 1];
-    for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
-        const int i = idx % kb, j = idx / kb;
-        L[i][j] = A[(size_t)(k0 + j) * n + k0 + i];
-    }
-    __syncthreads();
-    const int c = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > n) return;
-    double* colp = aug_column(A, b, n, c) + k0;
+    colp += k0;
     double x[kNB];
 #pragma unroll
     for (int i = 0; i < kNB; ++i) x[i] = i < kb ? colp[i] : 0.0;
@@ -255,9 +255,8 @@ void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) 
         const int kb = std::min(kNB, n - k0);
         RB_LAUNCH(lu_panel_kernel, 1, kPanelThreads, st, A, n, k0, kb, piv, info);
         const int right = n - k0 - kb + 1;   // columns right of the panel, b included
-        RB_LAUNCH(lu_swap_kernel, (right + 127) / 128, 128, st, A, b, n, k0, kb, (const int*)piv);
-        RB_LAUNCH(lu_trsm_kernel, (right + 127) / 128, 128, st, A, b, n, k0, kb);
-        launches += 3;
+        RB_LAUNCH(lu_swap_trsm_kernel, (right + 127) / 128, 128, st, A, b, n, k0, kb, (const int*)piv);
+        launches += 2;
         const int m = n - k0 - kb;
         if (m > 0) {
             const int tiles = (m + kTile - 1) / kTile;
