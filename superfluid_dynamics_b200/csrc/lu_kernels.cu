@@ -11,10 +11,11 @@
 //   lu_swap_trsm_kernel  one thread per column right of the panel and for b: the panel's row interchanges (the left part, L, is
 //                        never read again because b is eliminated on the fly, exactly as the unblocked kernels of dense_kernels.cu
 //                        treat it), then U12 = L11^{-1} A12 with L11 in shared memory
-//   lu_gemm_kernel    A22 -= L21 U12: 64 x 64 tiles, 8 warps, 2 x 4 DMMA tiles of 8 x 8 per warp, 8 k-steps of 4
-//   lu_gemv_kernel    b2  -= L21 b1
-// then lu_backsolve_blocked_kernel: the back substitution with U, one CTA, 32 columns per pair of barriers.  STATUS: written after round 1's GPU minutes were spent; selected only
-// when asked for (RB_LU_BLOCKED=1 or rb_lu_solve(..., blocked = 1)) until it has passed tests/test_zz_gpu_implicit.py on hardware.
+//   lu_gemm_kernel       A22 -= L21 U12: 64 x 64 tiles, 8 warps, 2 x 4 DMMA tiles of 8 x 8 per warp, 8 k-steps of 4
+//   lu_gemv_kernel       b2  -= L21 b1
+// then lu_backsolve_blocked_kernel: the back substitution with U, one CTA, 32 columns per pair of barriers.
+// STATUS: written after round 1's GPU minutes were spent; selected only when asked for (RB_LU_BLOCKED=1 or
+// rb_lu_solve(..., blocked = 1)) until it has passed tests/test_zz_gpu_implicit.py on hardware.
 // The kernels and the launch sequence below also compile under g++ with tests/cpp/cuda_emu.h standing in for the CUDA headers
 // (RB_EMULATE): the CPU test tier runs them thread for thread against LAPACK (tests/test_kernel_emulation.py).
 #ifdef RB_EMULATE
