@@ -36,7 +36,15 @@ extern "C" {
 #define RB_API __attribute__((visibility("default")))
 #endif
 
-typedef struct rb_complex { double re, im; } rb_complex;      /* L/ExportTypes.cuh:7 c_double */
+/* c_double of L/ExportTypes.cuh:7: two doubles, over-aligned to 16 bytes as the reference declares it (__declspec(align(16)),
+ * static_assert(alignof(c_double) == 16) at :78-79) -- the layout of cufftDoubleComplex / double2, so arrays and struct members of
+ * this type land where the reference's would */
+#if defined(_MSC_VER)
+#define RB_ALIGN16 __declspec(align(16))
+#else
+#define RB_ALIGN16 __attribute__((aligned(16)))
+#endif
+typedef struct RB_ALIGN16 rb_complex { double re, im; } rb_complex;
 typedef struct rb_solver rb_solver;                           /* opaque: one RHS assembler + work buffers */
 typedef struct rb_stepper rb_stepper;                         /* opaque: RK4 stepper bound to a solver */
 typedef struct rb_rk45 rb_rk45;                               /* opaque: adaptive RKF45 stepper (L/RK45.cuh) */
@@ -110,6 +118,17 @@ RB_API int rb_energies(rb_solver* s, double out_host[5]);
  * [3] solver sweeps (M*x applications, including the combined verify+velocity sweeps) summed over all solves, [4] number of
  * solves, [5] velocity-only sweeps */
 RB_API int rb_solve_stats(rb_solver* s, double out_host[6]);
+/* How solves ended.  The reference's direct LU (MatrixSolver<N,B>::solve, L/MatrixSolver.cuh:114-172) cannot fail to converge; the
+ * iterations that replace it can, and say so:  converged = the relative residual met the tolerance, nothing else;  stagnated = the
+ * iteration stopped on the round-off floor of the residual (<= 1e-10, no longer contracting) above the tolerance -- accepted, counted
+ * separately;  failed = neither (iteration cap, NaN, a peer rank that never signalled).  Inside the RK4 stepper "last" refers to
+ * the last step and aggregates its four stage solves (converged: all four; stagnated: any; out[4] of rb_solve_stats' residual: the
+ * largest).  out[0] last converged, [1] last stagnated, [2] stagnated solves since creation, [3] failed solves since creation,
+ * [4] largest final relative residual of any accepted solve, [5] strict flag, [6..7] reserved (0). */
+RB_API int rb_solve_status(rb_solver* s, double out_host[8]);
+/* strict (default 1): a failed solve makes rb_rhs / rb_vorticities / rb_rk4_step / ... return -1 with rb_last_error set, and a failed
+ * RK4 step leaves the state as it was before the step.  0: failures are only reported through rb_solve_status. */
+RB_API int rb_set_strict(rb_solver* s, int strict);
 
 /* ---- spectral derivatives (L/Derivatives.cuh) ---- */
 /* ZPhiDerivative<N,B>::exec :311-384 */
@@ -343,6 +362,12 @@ RB_API int rb_comm_error(rb_solver* s);                                         
 RB_API int rb_comm_destroy(rb_solver* s);
 
 /* ---- measurement helpers ---- */
+/* restrict the sweeps of a single-GPU solver to the row cells (256 rows each) [cell0, cell0 + cells) a rank of a row-sharded run would
+ * own (no peer involved; cells <= 0: whole surface again) -- times and tunes a per-rank sweep on one GPU with rb_bench_sweep */
+RB_API int rb_debug_set_row_range(rb_solver* s, int cell0, int cells);
+/* the sweep schedule in use: out[0] kernel (1 tiled, 2 persistent), [1] rows per thread, [2] source tile, [3] tiles per chunk,
+ * [4] source chunks, [5] row cells of this rank, [6] CTAs per sweep, [7] threads per CTA */
+RB_API int rb_sweep_plan(rb_solver* s, int out[8]);
 RB_API unsigned long long rb_launch_count(void);                                  /* kernels of this library launched since load */
 RB_API int rb_measure_fp64_peak(double* tflops_out, void* stream);               /* DFMA-only kernel: the FP64 roofline denominator */
 RB_API int rb_measure_fp64_rate_3operand(double* tflops_out, void* stream);      /* DFMA with three distinct register operands */

@@ -91,6 +91,10 @@ SIGNATURES = {
     "rb_synchronize": (c_int, [_P]),
     "rb_energies": (c_int, [_P, _D]),
     "rb_solve_stats": (c_int, [_P, _D]),
+    "rb_solve_status": (c_int, [_P, _D]),
+    "rb_debug_set_row_range": (c_int, [_P, c_int, c_int]),
+    "rb_sweep_plan": (c_int, [_P, POINTER(c_int)]),
+    "rb_set_strict": (c_int, [_P, c_int]),
     "rb_zphi_derivative": (c_int, [_P, _P, _P, _P, _P, _P]),
     "rb_fft_derivative": (c_int, [_P, _P, _P, c_int, c_double]),
     "rb_create_M": (c_int, [_P, _P, _P, _P, c_double, c_int, c_size_t, _P]),

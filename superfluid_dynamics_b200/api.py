@@ -163,8 +163,15 @@ class BaseBoundaryIntegralCalculator:
     def solve_stats(self):
         out = (ctypes.c_double * 6)()
         check(self.lib.rb_solve_stats(self.handle, out), "rb_solve_stats")
+        st = (ctypes.c_double * 8)()
+        check(self.lib.rb_solve_status(self.handle, st), "rb_solve_status")
         return dict(iterations=int(out[0]), converged=bool(out[1]), residual=out[2], total_iterations=int(out[3]),
-                    total_solves=int(out[4]), velocity_sweeps=int(out[5]))
+                    total_solves=int(out[4]), velocity_sweeps=int(out[5]), stagnated=bool(st[1]), stagnated_solves=int(st[2]),
+                    failed_solves=int(st[3]), worst_residual=st[4], strict=bool(st[5]))
+
+    def setStrict(self, strict=True):
+        """strict (default): a solve that neither converges nor stagnates on the round-off floor raises; False: statistics only."""
+        check(self.lib.rb_set_strict(self.handle, int(bool(strict))), "rb_set_strict")
 
     # --- derivatives (ZPhiDerivative / FftDerivative) ---
     def zPhiDerivative(self, Z, Phi):
@@ -203,6 +210,16 @@ class BaseBoundaryIntegralCalculator:
         ms, pairs = ctypes.c_float(), ctypes.c_double()
         check(self.lib.rb_bench_sweep(self.handle, _ptr(state), reps, ctypes.byref(ms), ctypes.byref(pairs)), "rb_bench_sweep")
         return ms.value, pairs.value
+
+    def debugSetRowRange(self, cell0, cells):
+        """Measurement aid: sweep only the 256-row cells [cell0, cell0 + cells) -- the per-rank share of a row-sharded run, on one GPU."""
+        check(self.lib.rb_debug_set_row_range(self.handle, int(cell0), int(cells)), "rb_debug_set_row_range")
+
+    def sweepPlan(self):
+        out = (ctypes.c_int * 8)()
+        check(self.lib.rb_sweep_plan(self.handle, out), "rb_sweep_plan")
+        return dict(kernel="persistent" if out[0] == 2 else "tiled", rows_per_thread=out[1], tile=out[2], tiles_per_chunk=out[3],
+                    nchunks=out[4], row_cells=out[5], ctas=out[6], threads=out[7])
 
 
 def exchange_handles(blob: bytes, group=None):

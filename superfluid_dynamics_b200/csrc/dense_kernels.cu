@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kLuThreads) lu_pivot_kernel(double* __restrict
         __syncthreads();
     }
     const int p = sidx[0];
-    if (sval[0] == 0.0) {
+    if (!(sval[0] > 0.0)) {   // zero column, or nothing but NaN in it (best stays at its -1 start): same verdict as the blocked panel
         if (threadIdx.x == 0 && *info == 0) *info = k + 1;
         return;
     }

@@ -39,9 +39,36 @@ struct SolveCtrl {
     double prev_rel2;
     unsigned long long max_rel2_bits;   // atomicMax accumulator over batch members (non-negative doubles order as uint64)
     unsigned int members_done;          // level-3 ticket
-    unsigned int pad;
+    int stagnated;       // 1 if the iteration stopped on the round-off floor of the residual (rel <= 1e-10, no longer decreasing)
+                         // WITHOUT meeting the tolerance: reported as its own status, never as converged
     double first_rel2;   // residual of the initial iterate (set by the first sweep of the solve): quality of the guess
 };
+
+// How a solve ended, decided once per sweep from the worst member's ||r||^2/||b||^2 by whichever thread closes the sweep (the last
+// CTA of a sweep kernel, or comm_wait_kernel on a row-sharded run; every rank takes it from the same numbers in the same order).
+//   converged: rel <= tolerance, nothing else.
+//   stagnated: rel <= 1e-10 and no longer contracting (the residual sits on its round-off floor, which grows like N eps): the
+//              iteration cannot do better; the solve ends with converged = 0, stagnated = 1 and the host counts it separately.
+//   neither and iters >= max_iters: the solve failed (done = 1, converged = 0, stagnated = 0).
+#ifdef __CUDACC__
+__device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst, double tol2, int max_iters, int final_buf) {
+    if (!(worst == worst)) worst = 1e300;   // NaN -> "not converged"
+    const int iters = c->iters + 1;
+    const double prev = c->prev_rel2;
+    const bool conv = worst <= tol2;
+    const bool stagnated = !conv && iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
+    c->iters = iters;
+    c->rel2 = worst;
+    c->prev_rel2 = worst;
+    if (iters == 1) c->first_rel2 = worst;
+    c->final_buf = final_buf;
+    if (conv || stagnated || iters >= max_iters) {
+        c->converged = conv ? 1 : 0;
+        c->stagnated = stagnated ? 1 : 0;
+        c->done = 1;
+    }
+}
+#endif
 
 // geometry of the surface, per point; all arrays are [batch][N]
 struct Geometry {

@@ -258,6 +258,7 @@ __device__ __forceinline__ void guess_cell(const double* b, const double* __rest
             ctrl->iters = 0;
             ctrl->final_buf = 0;
             ctrl->converged = 0;
+            ctrl->stagnated = 0;
             ctrl->rel2 = 0.0;
             ctrl->prev_rel2 = 1e300;
             ctrl->first_rel2 = 1e300;
@@ -480,19 +481,7 @@ __device__ __forceinline__ void solver_sweep_close(const SweepArgs& a, double sx
             unsigned long long bits = atomicAdd(&a.ctrl->max_rel2_bits, 0ull);
             double worst = __longlong_as_double((long long)bits);
             volatile SolveCtrl* c = a.ctrl;
-            int iters = c->iters + 1;
-            double prev = c->prev_rel2;
-            bool conv = worst <= a.tol2;
-            bool stagnated = iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
-            c->iters = iters;
-            c->rel2 = worst;
-            c->prev_rel2 = worst;
-            if (iters == 1) c->first_rel2 = worst;
-            c->final_buf = a.final_buf_on_done;
-            if (conv || stagnated || iters >= a.max_iters) {
-                c->converged = (conv || stagnated) ? 1 : 0;
-                c->done = 1;
-            }
+            solve_decide(c, worst, a.tol2, a.max_iters, a.final_buf_on_done);
             c->max_rel2_bits = 0ull;
             c->members_done = 0u;
             __threadfence();
@@ -846,6 +835,7 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
             *c.error_flag = 1;
             ctrl->done = 1;
             ctrl->converged = 0;
+            ctrl->stagnated = 0;
         }
         return;
     }
@@ -860,20 +850,7 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
         double rn = 0.0;
         for (int r = 0; r < c.nranks; ++r) rn += rnp[r];
         double worst = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
-        if (!(worst == worst)) worst = 1e300;
-        int iters = ctrl->iters + 1;
-        double prev = ctrl->prev_rel2;
-        bool conv = worst <= tol2;
-        bool stagnated = iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
-        ctrl->iters = iters;
-        ctrl->rel2 = worst;
-        ctrl->prev_rel2 = worst;
-        if (iters == 1) ctrl->first_rel2 = worst;
-        ctrl->final_buf = final_buf;
-        if (conv || stagnated || iters >= max_iters) {
-            ctrl->converged = (conv || stagnated) ? 1 : 0;
-            ctrl->done = 1;
-        }
+        solve_decide(ctrl, worst, tol2, max_iters, final_buf);
     }
 }
 

@@ -465,21 +465,7 @@ __global__ void __launch_bounds__(MAXT, 1) sweep2_kernel(const SweepArgs a) {
         worst = block_max_any(w, sred, T, P2);
     }
     if (t == 0) {
-        if (!(worst == worst)) worst = 1e300;
-        volatile SolveCtrl* c = a.ctrl;
-        int iters = c->iters + 1;
-        double prev = c->prev_rel2;
-        bool conv = worst <= a.tol2;
-        bool stagnated = iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
-        c->iters = iters;
-        c->rel2 = worst;
-        c->prev_rel2 = worst;
-        if (iters == 1) c->first_rel2 = worst;
-        c->final_buf = a.final_buf_on_done;
-        if (conv || stagnated || iters >= a.max_iters) {
-            c->converged = (conv || stagnated) ? 1 : 0;
-            c->done = 1;
-        }
+        solve_decide(a.ctrl, worst, a.tol2, a.max_iters, a.final_buf_on_done);
         __threadfence();
     }
 }

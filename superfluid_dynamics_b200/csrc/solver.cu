@@ -148,9 +148,14 @@ struct rb_solver {
     // capture mode: fixed sweep count, no host synchronisation inside rb_rhs
     int fixed_sweeps = 0;
 
-    // statistics of the last solve
-    int last_iters = 0, last_converged = 0;
+    // statistics of the last solve (inside the RK4 stepper: of the last step, aggregated over its four stage solves)
+    int last_iters = 0, last_converged = 0, last_stagnated = 0;
     double last_rel = 0;
+    // how solves ended since the solver was created: converged = tolerance met; stagnated = stopped on the round-off floor of the
+    // residual (<= 1e-10) above the tolerance; failed = neither (iteration cap, NaN, a peer that never signalled)
+    long long stagnated_solves = 0, failed_solves = 0;
+    double worst_rel = 0;            // largest final relative residual of any solve that was accepted
+    bool strict = true;              // a failed solve makes the call return -1 (rb_set_strict(s, 0): report through the statistics only)
     int kpred = 0;
     long long total_sweeps = 0;      // sweep kernels launched (including ones that skipped)
     long long sum_iters = 0;         // M*x applications actually performed, summed over solves
@@ -203,6 +208,17 @@ static void solver_free(rb_solver* s) {
     delete s;
 }
 
+// Source chunking of the tiled sweep.  A CTA is one 256-row cell x one chunk of sources; the grid is (row cells, chunks, members).
+// What a choice costs (all measured on a B200, N = 65536, 4 rows per thread, 8 CTAs resident per SM = 1184 slots):
+//   * a CTA among 8 co-resident ones evaluates ~0.2 us per source (256 x 1024 pairs in 207 us), a CTA left alone on an SM at most
+//     ~4x faster (its 2 warps reach 2 of the 4 sub-partitions): a nearly empty last wave costs a quarter of a full one;
+//   * the finishing CTA of a row cell adds its `nchunks` partial sums per row in chunk order, 4-8 loads in flight per thread:
+//     ~1 us per batch of loads AT THE TAIL of the launch, where nothing overlaps it.
+// Round 1 scaled the CTA count with 1 / row cells (target 148 x 128 CTAs), which on a rank owning 32 of the 256 row cells (8 GPUs)
+// gave nchunks = 512: 128 sources per CTA and a 128-batch serial reduction -- the per-rank sweep fell from 0.81 to 0.61 of the FP64
+// peak.  The plan below minimises  waves(nchunks) x t_cta(sources per chunk) + t_finish(nchunks)  over nchunks instead; on a
+// shard it lands on ONE balanced wave (32 cells x 37 chunks = 1184 CTAs at 8 GPUs, 64 x 18 at 4, 128 x 9 at 2), on a whole
+// N = 65536 surface on 64 chunks (13.8 waves) as measured best in round 1.
 static void choose_chunking(rb_solver* s) {
     const int N = s->N;
     // measured on a B200 (solver sweep, us): N = 65536: 2 rows per thread 3200 (target 1184) / 3108 (2368); 4 rows per thread 3391 / 3011 /
@@ -210,24 +226,55 @@ static void choose_chunking(rb_solver* s) {
     // N = 32768: 832 / 813 | 912 / 830 / 819; N = 16384: 248 / 234 | 314 / 265 / 235; N = 8192: 80.5 / 74.2 | 102 / 84; N = 4096: 32.8 / 32.9 | 41
     const bool big = N >= 49152;
     s->v1_rows = env_int("RB_V1_ROWS", big ? 4 : 2) == 4 ? 4 : 2;
-    const int target = env_int("RB_TARGET_CTAS", big ? 148 * 128 : (N >= 2048 ? 148 * 16 : 148 * 8));
-    long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
-    int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
-    int max_chunks = std::max(1, (N + 63) / 64);
+    int nSM = 148;
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
+    const int per_sm = s->v1_rows == 4 ? 8 : (s->has_image ? 5 : 7);   // __launch_bounds__ of sweep_kernel
+    const long slots = (long)nSM * per_sm;
+    const long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
+    const int max_chunks = std::max(1, (N + 63) / 64);
+    int wanted;
+    if (env_int("RB_TARGET_CTAS", 0) > 0) {   // round-1 heuristic, kept for the knob sweeps of tests/gpu_debug.py
+        const int target = env_int("RB_TARGET_CTAS", 0);
+        wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
+    } else {
+        // cost model, in units of "one source evaluated by a CTA with a full SM around it" (~0.2 us)
+        const int wps = kCell / s->v1_rows / 32;                          // warps per CTA
+        const double full_smsp = per_sm * wps / 4.0;                      // warps per sub-partition when the SM is full
+        const double c0 = 16.0;                                           // fixed cost per CTA (prologue, partial store, ticket) ~ 3 us
+        const double fin = 1.25 * (s->v1_rows == 4 ? 1.0 : 0.5) * (s->has_image ? 2.0 : 1.0);   // per chunk, at the tail
+        const double wsat = env_int("RB_WSAT10", 10) / 10.0;              // warps per sub-partition that saturate its FP64 pipe
+        double best = 1e300;
+        wanted = 1;
+        for (int c = 1; c <= max_chunks; ++c) {
+            const int per = (((N + c - 1) / c + 63) / 64) * 64;
+            if (c > 1 && (long)(c - 1) * per >= N) continue;     // the last chunk would be empty
+            const long ctas = rows * c;
+            const long full = ctas / slots, rem = ctas % slots;
+            const double t_cta = per + c0;
+            double waves = (double)full;
+            if (rem) {
+                // a partly filled wave: the busiest sub-partition holds ceil(m wps / 4) warps of the m CTAs on the busiest SM; it
+                // takes that share of a full wave's time, stretched when fewer than `wsat` warps are there to hide the DFMA latency
+                const long m = (rem + nSM - 1) / nSM;
+                const double w = (double)((m * wps + 3) / 4);
+                waves += std::min(1.0, w / full_smsp / std::min(1.0, w / wsat));
+            }
+            const double cost = waves * t_cta + fin * c;
+            if (cost < best * (1.0 - 1e-9)) {
+                best = cost;
+                wanted = c;
+            }
+        }
+    }
     wanted = std::min(wanted, max_chunks);
     wanted = env_int("RB_NCHUNKS", wanted);
     int srcs = (N + wanted - 1) / wanted;
     srcs = ((srcs + 63) / 64) * 64;
-    if (srcs >= 256) {
-        s->tile = 256;
-        s->tiles_per_chunk = (srcs + 255) / 256;
-    } else if (srcs >= 128) {
-        s->tile = 128;
-        s->tiles_per_chunk = 1;
-    } else {
-        s->tile = 64;
-        s->tiles_per_chunk = 1;
-    }
+    // largest tile (fewest barriers) that divides the chunk; the tiles of a chunk never straddle a 256-point cell differently
+    if (srcs % 256 == 0) s->tile = 256;
+    else if (srcs % 128 == 0) s->tile = 128;
+    else s->tile = 64;
+    s->tiles_per_chunk = srcs / s->tile;
     int t = env_int("RB_TILE", 0);
     if (t == 64 || t == 128 || t == 256) {
         s->tile = t;
@@ -235,6 +282,9 @@ static void choose_chunking(rb_solver* s) {
     }
     int per = s->tile * s->tiles_per_chunk;
     s->nchunks = (N + per - 1) / per;
+    if (env_int("RB_VERBOSE", 0))
+        std::fprintf(stderr, "[roberts_b200] tiled sweep plan: N=%d rows/thread=%d row cells=%ld tile=%d tiles/chunk=%d nchunks=%d -> %ld CTAs on %ld slots\n",
+                     N, s->v1_rows, rows, s->tile, s->tiles_per_chunk, s->nchunks, rows * s->nchunks, slots);
 }
 
 static void set_stream(rb_solver* s, cudaStream_t st);
@@ -456,7 +506,7 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     s->member_tickets = dmalloc<unsigned int>(batch);
     s->ctrl_all = dmalloc<SolveCtrl>(4);
     s->ctrl = s->ctrl_all;
-    s->lu_info = dmalloc<int>(1);
+    s->lu_info = dmalloc<int>(batch);   // one per member (dense validation path)
     RB_CUDA(cudaMemset(s->cell_tickets, 0, pc * sizeof(unsigned int)));
     RB_CUDA(cudaMemset(s->member_tickets, 0, batch * sizeof(unsigned int)));
     RB_CUDA(cudaMemset(s->ctrl_all, 0, 4 * sizeof(SolveCtrl)));
@@ -691,7 +741,27 @@ static void read_ctrl(rb_solver* s) {
     RB_CUDA(cudaStreamSynchronize(s->stream));
     s->last_iters = s->h_ctrl->iters;
     s->last_converged = s->h_ctrl->converged;
+    s->last_stagnated = s->h_ctrl->stagnated;
     s->last_rel = std::sqrt(std::max(0.0, s->h_ctrl->rel2));
+}
+
+// Book-keeping of how one solve ended.  The reference's direct LU cannot fail to converge (L/MatrixSolver.cuh:114-172); an iterative
+// solve can, and must not hand an unconverged vortex-sheet strength to its caller silently: a failed solve throws (the C ABI call
+// returns -1, rb_last_error says why) unless rb_set_strict(s, 0) was called; a stagnated one is accepted and counted.
+static void note_solve_end(rb_solver* s, int converged, int stagnated, double rel, int iters, const char* what) {
+    if (converged || stagnated) {
+        if (rel == rel) s->worst_rel = std::max(s->worst_rel, rel);
+        if (stagnated && !converged) s->stagnated_solves++;
+        return;
+    }
+    s->failed_solves++;
+    if (s->strict) {
+        char msg[256];
+        std::snprintf(msg, sizeof msg, "%s: the solve for the vortex-sheet strength did not converge (relative residual %.3e after %d "
+                      "applications of M, tolerance %.1e%s)", what, rel, iters, s->props.tolerance,
+                      s->comm.nranks > 1 ? "; on a row-sharded run also check rb_comm_error" : "");
+        throw std::runtime_error(msg);
+    }
 }
 
 static void account_solve(rb_solver* s) {
@@ -819,10 +889,12 @@ static void gmres_solve(rb_solver* s, const double2* Z) {
     }
     s->last_iters = applies;
     s->last_converged = converged ? 1 : 0;
+    s->last_stagnated = 0;
     s->last_rel = rel;
     account_solve(s);
     launch_finish_solve(s->gm_x, s->gm_x, nullptr, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
     s->have_prev_a = true;
+    note_solve_end(s, s->last_converged, 0, rel, applies, "GMRES");
 }
 
 // M a = b.  On return a (real), ac (complex copy) and the per-cell sums of a are valid on the stream.
@@ -840,12 +912,30 @@ static void solve(rb_solver* s, const double2* Z) {
             else
                 launch_create_M(s->Mdense, Z + o, s->Zp() + o, s->Zpp() + o, s->rhoM, N, 1, st);
             RB_CUDA(cudaMemcpyAsync(s->xbuf[0] + o, s->b + o, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            launch_lu_solve(s->Mdense, s->xbuf[0] + o, N, s->lu_info, st);
+            launch_lu_solve(s->Mdense, s->xbuf[0] + o, N, s->lu_info + bm, st);
         }
         launch_finish_solve(s->xbuf[0], s->xbuf[0], nullptr, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
         s->last_iters = 0;
-        s->last_converged = 1;
+        s->last_stagnated = 0;
         s->last_rel = 0;
+        s->num_solves++;
+        if (s->fixed_sweeps > 0) {   // being recorded into a graph: no host read here, the factorisation's info is left on the device
+            s->last_converged = 1;
+            return;
+        }
+        std::vector<int> infos(s->batch, 0);   // per member: first singular (or non-finite) pivot column + 1, else 0
+        RB_CUDA(cudaMemcpyAsync(infos.data(), s->lu_info, s->batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+        RB_CUDA(cudaStreamSynchronize(st));
+        int info = 0;
+        for (int v : infos)
+            if (v != 0 && info == 0) info = v;
+        s->last_converged = info == 0 ? 1 : 0;
+        if (info != 0) {
+            s->failed_solves++;
+            if (s->strict)
+                throw std::runtime_error("dense LU: M is singular to working precision (zero or non-finite pivot in column " +
+                                         std::to_string(info - 1) + ")");
+        }
         return;
     }
 
@@ -878,6 +968,7 @@ static void solve(rb_solver* s, const double2* Z) {
     }
     launch_finish_solve(s->xbuf[0], s->xbuf[1], s->ctrl, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
     s->have_prev_a = true;
+    if (s->fixed_sweeps <= 0) note_solve_end(s, s->last_converged, s->last_stagnated, s->last_rel, s->last_iters, "Richardson iteration");
 }
 
 static void vorticities(rb_solver* s, const double2* state) {
@@ -1135,6 +1226,8 @@ static void issue_step(rb_stepper* st, int fixed_sweeps) {
     const double h = st->dt;
     const bool warm = s->props.guess_mode == RB_GUESS_WARM && s->matrix_free_solve;
     s->fixed_sweeps = fixed_sweeps;
+    int agg_iters = 0, agg_conv = 1, agg_stag = 0;
+    double agg_rel = 0.0;
     auto stage = [&](int i, const double2* y) {
         s->ctrl = s->ctrl_all + i;
         if (warm) {
@@ -1151,6 +1244,12 @@ static void issue_step(rb_stepper* st, int fixed_sweeps) {
         s->optimistic = fixed_sweeps > 0 && ((st->opt_mask >> i) & 1);
         rhs(s, y, st->k[i]);
         s->optimistic = false;
+        if (fixed_sweeps <= 0) {   // synchronising path: each solve has just reported; keep the step's aggregate
+            agg_iters = std::max(agg_iters, s->last_iters);
+            agg_conv = agg_conv && s->last_converged;
+            agg_stag = agg_stag || s->last_stagnated;
+            agg_rel = std::max(agg_rel, s->last_rel);
+        }
     };
     // the RK update after a stage is folded into the kernel that closes the stage's solve when the RHS allows it
     auto staged = [&](int i, const double2* y, int update, double c) {
@@ -1169,14 +1268,32 @@ static void issue_step(rb_stepper* st, int fixed_sweeps) {
         s->post_update_done = false;
         return done;
     };
-    if (!staged(0, st->y0, 1, h * 0.5)) launch_stage_update(st->ytmp, st->y0, st->k[0], h * 0.5, n2, cs);
-    if (!staged(1, st->ytmp, 1, h * 0.5)) launch_stage_update(st->ytmp, st->y0, st->k[1], h * 0.5, n2, cs);
-    if (!staged(2, st->ytmp, 1, h)) launch_stage_update(st->ytmp, st->y0, st->k[2], h, n2, cs);
-    if (!staged(3, st->ytmp, 2, h / 6.0)) launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n2, cs);
-    if (warm) launch_advance_counter(st->d_counter, cs);
-    s->hist = HistoryRing();
-    s->ctrl = s->ctrl_all;
-    s->fixed_sweeps = 0;
+    auto restore = [&]() {
+        s->hist = HistoryRing();
+        s->ctrl = s->ctrl_all;
+        s->fixed_sweeps = 0;
+        s->optimistic = false;
+        s->post_update = FinishPost();
+        s->post_update_done = false;
+    };
+    try {
+        if (!staged(0, st->y0, 1, h * 0.5)) launch_stage_update(st->ytmp, st->y0, st->k[0], h * 0.5, n2, cs);
+        if (!staged(1, st->ytmp, 1, h * 0.5)) launch_stage_update(st->ytmp, st->y0, st->k[1], h * 0.5, n2, cs);
+        if (!staged(2, st->ytmp, 1, h)) launch_stage_update(st->ytmp, st->y0, st->k[2], h, n2, cs);
+        if (!staged(3, st->ytmp, 2, h / 6.0)) launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n2, cs);
+        if (warm) launch_advance_counter(st->d_counter, cs);
+    } catch (...) {
+        // a stage's solve failed (strict mode): y0 has not been touched yet (the final update is the last thing a step does)
+        restore();
+        throw;
+    }
+    restore();
+    if (fixed_sweeps <= 0) {
+        s->last_iters = agg_iters;
+        s->last_converged = agg_conv;
+        s->last_stagnated = agg_stag;
+        s->last_rel = agg_rel;
+    }
 }
 
 static void capture_graph(rb_stepper* st, int sweeps) {
@@ -1238,7 +1355,7 @@ static void stepper_step(rb_stepper* st) {
     rb_solver* s = st->s;
     const bool graphable = st->use_graph && s->matrix_free_solve && !s->use_gmres;   // GMRES is host-driven
     if (!graphable) {
-        issue_step(st, 0);
+        issue_step(st, 0);   // every stage's solve synchronises and is checked where it ends (note_solve_end)
         if (s->props.guess_mode == RB_GUESS_WARM && s->matrix_free_solve) st->h_counter++;
         after_step(st);
         return;
@@ -1303,9 +1420,36 @@ static void stepper_step(rb_stepper* st) {
         if (st->opt_policy == 0) next_mask = 0;
         if (st->opt_policy == 2) next_mask = 15;
         st->opt_mask = next_mask;
-        s->last_iters = s->h_ctrl[3].iters;
-        s->last_converged = s->h_ctrl[3].converged;
-        s->last_rel = std::sqrt(std::max(0.0, s->h_ctrl[3].rel2));
+        // status of the step = status of its four stage solves together (a stage that ended on the iteration cap, a NaN or a peer
+        // time-out has done = 1 and converged = stagnated = 0)
+        int it_max = 0, all_conv = 1, any_stag = 0, failed = -1;
+        double rel_max = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            const SolveCtrl& c = s->h_ctrl[i];
+            const double rel = std::sqrt(std::max(0.0, c.rel2));
+            it_max = std::max(it_max, c.iters);
+            all_conv = all_conv && c.converged;
+            any_stag = any_stag || (c.stagnated && !c.converged);
+            rel_max = (rel == rel) ? std::max(rel_max, rel) : 1e300;
+            if (!c.converged && !c.stagnated && failed < 0) failed = i;
+        }
+        s->last_iters = it_max;
+        s->last_converged = all_conv;
+        s->last_stagnated = any_stag;
+        s->last_rel = rel_max;
+        if (failed >= 0 && s->strict) {
+            // leave the state as it was before the step and tell the caller
+            RB_CUDA(cudaMemcpyAsync(st->y0, st->ybackup, 2 * s->BN * sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+            if (s->props.guess_mode == RB_GUESS_WARM)
+                RB_CUDA(cudaMemcpyAsync(st->d_counter, &st->h_counter, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+            RB_CUDA(cudaStreamSynchronize(s->stream));
+            const SolveCtrl& c = s->h_ctrl[failed];
+            note_solve_end(s, 0, 0, std::sqrt(std::max(0.0, c.rel2)), c.iters, "RK4 step (state restored)");
+        }
+        for (int i = 0; i < 4; ++i) {
+            const SolveCtrl& c = s->h_ctrl[i];   // (a failed stage in strict mode has thrown above)
+            note_solve_end(s, c.converged, c.stagnated, std::sqrt(std::max(0.0, c.rel2)), c.iters, "RK4 stage");
+        }
         // shrink the recorded sweep count when it has been clearly too large for a while (each skipped sweep costs a launch)
         if (st->graph_sweeps - worst >= 3) {
             if (++st->graph_hits_below >= 8) {
@@ -1432,13 +1576,32 @@ int rb_energies(rb_solver* s, double out_host[5]) {
 
 int rb_solve_stats(rb_solver* s, double out_host[6]) {
     RB_TRY
-    if (s->matrix_free_solve && !s->use_gmres) read_ctrl(s);
     out_host[0] = s->last_iters;
     out_host[1] = s->last_converged;
     out_host[2] = s->last_rel;
     out_host[3] = (double)s->sum_iters;
     out_host[4] = (double)s->num_solves;
     out_host[5] = (double)s->vel_sweeps;
+    RB_CATCH
+}
+
+int rb_solve_status(rb_solver* s, double out_host[8]) {
+    RB_TRY
+    if (!s) throw std::runtime_error("rb_solve_status: null solver");
+    out_host[0] = s->last_converged;
+    out_host[1] = s->last_stagnated;
+    out_host[2] = (double)s->stagnated_solves;
+    out_host[3] = (double)s->failed_solves;
+    out_host[4] = s->worst_rel;
+    out_host[5] = s->strict ? 1.0 : 0.0;
+    out_host[6] = out_host[7] = 0.0;
+    RB_CATCH
+}
+
+int rb_set_strict(rb_solver* s, int strict) {
+    RB_TRY
+    if (!s) throw std::runtime_error("rb_set_strict: null solver");
+    s->strict = strict != 0;
     RB_CATCH
 }
 
@@ -1785,6 +1948,45 @@ int rb_comm_init(rb_solver* s, int rank, int nranks, const char* handles) {
         cudaFree(s->partial_img);
         s->partial_img = dmalloc<double2>((size_t)s->nchunks * s->BN);
     }
+    RB_CATCH
+}
+
+// measurement aid: restrict the sweeps of a single-GPU solver to the row cells [cell0, cell0 + cells) a rank of a row-sharded run
+// would own, without any peer (the other rows of the iterate simply stay as they are): the per-rank sweep of G ranks can be timed
+// and tuned on one GPU with rb_bench_sweep.  cells <= 0 restores the whole surface.
+int rb_debug_set_row_range(rb_solver* s, int cell0, int cells) {
+    RB_TRY
+    if (s->comm.nranks > 1) throw std::runtime_error("rb_debug_set_row_range: the solver is part of a row-sharded run");
+    if (cells <= 0) {
+        cell0 = 0;
+        cells = s->ncell;
+    }
+    if (cell0 < 0 || cell0 + cells > s->ncell) throw std::runtime_error("rb_debug_set_row_range: range outside the surface");
+    RB_CUDA(cudaStreamSynchronize(s->stream));
+    s->row_cell0 = cell0;
+    s->row_cells = cells;
+    plan_sweep2(s);
+    choose_sweep_kernel(s);
+    choose_chunking(s);
+    cudaFree(s->partial);
+    s->partial = dmalloc<double2>((size_t)s->nchunks * s->BN);
+    if (s->has_image) {
+        cudaFree(s->partial_img);
+        s->partial_img = dmalloc<double2>((size_t)s->nchunks * s->BN);
+    }
+    RB_CATCH
+}
+
+int rb_sweep_plan(rb_solver* s, int out[8]) {
+    RB_TRY
+    out[0] = s->use_v2 ? 2 : 1;            // 1 tiled, 2 persistent
+    out[1] = s->v1_rows;
+    out[2] = s->tile;
+    out[3] = s->tiles_per_chunk;
+    out[4] = s->nchunks;
+    out[5] = s->row_cells;
+    out[6] = s->use_v2 ? s->v2l.grid : s->row_cells * s->nchunks * s->batch;   // CTAs per sweep
+    out[7] = s->use_v2 ? s->v2l.threads : kCell / s->v1_rows;
     RB_CATCH
 }
 

@@ -1,0 +1,142 @@
+"""Round-2 measurements on one B200 (diagnostics: prints, never asserts).  Run under gpurun, sections by name:
+    python tests/gpu_round2.py shardtune n4096 ... > gpurun_out/round2.log 2>&1
+"""
+import json
+import os
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import roberts_oracle as ro  # noqa: E402
+from superfluid_dynamics_b200 import api  # noqa: E402
+
+dev = torch.device("cuda:0")
+OUT = os.path.join(ROOT, "gpurun_out")
+os.makedirs(OUT, exist_ok=True)
+RESULTS = {}
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev)
+
+
+def water(N, B=1, **kw):
+    props = api.ProblemProperties(rho=0.0)
+    return api.BaseBoundaryIntegralCalculator(N, B, props, api.WaterBoundaryProblem(props), device=dev, **kw)
+
+
+def with_env(cfg, fn):
+    os.environ.update({k: str(v) for k, v in cfg.items()})
+    try:
+        return fn()
+    finally:
+        for k in cfg:
+            os.environ.pop(k, None)
+
+
+def shardtune():
+    """Per-rank sweep of a row-sharded run, timed on one GPU (rb_debug_set_row_range): source chunks vs time, N = 65536 and 16384."""
+    peak = api.measure_fp64_peak(dev)
+    rows = []
+    for N, cands in ((65536, {1: (0, 4, 8, 9, 18, 37, 64), 2: (0, 9, 18, 27, 37, 128), 4: (0, 9, 18, 37, 55, 74, 256),
+                              8: (0, 9, 18, 23, 37, 74, 111, 148, 512)}),
+                     (16384, {1: (0, 8, 16, 32), 2: (0, 8, 16, 32), 4: (0, 9, 16, 32, 64), 8: (0, 9, 18, 32, 64, 129)})):
+        st = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+        ncell = N // 256
+        for G, ncs in cands.items():
+            for nc in ncs:
+                cfg = {"RB_NCHUNKS": nc} if nc else {}
+
+                def run():
+                    c = water(N)
+                    if G > 1:
+                        c.debugSetRowRange((G // 2) * (ncell // G), ncell // G)
+                    ms, pairs = c.benchSweep(st, 10 if N >= 65536 else 30)
+                    return ms, c.sweepPlan()
+                try:
+                    ms, plan = with_env(cfg, run)
+                    tf = 20.0 * N * (N / G) / (ms * 1e-3) / 1e12
+                    rows.append(dict(N=N, G=G, asked=nc, us=ms * 1e3, tflops=tf, frac=tf / peak, **plan))
+                    print(f"shardtune N={N} G={G} nchunks={'auto' if not nc else nc}: {ms * 1e3:8.1f} us  {tf:5.2f} TF  {tf / peak:.3f}  {plan}",
+                          flush=True)
+                except Exception as e:  # noqa: BLE001
+                    print(f"shardtune N={N} G={G} nchunks={nc}: FAILED {e}", flush=True)
+    RESULTS["shardtune"] = dict(peak=peak, rows=rows)
+
+
+def n4096():
+    """Where the N = 4096 step goes: sweep alone (tiled / persistent, chunk candidates), whole-step rate."""
+    N = 4096
+    st = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+    peak = api.measure_fp64_peak(dev)
+    for cfg in ({}, {"RB_NCHUNKS": 8}, {"RB_NCHUNKS": 16}, {"RB_NCHUNKS": 32}, {"RB_NCHUNKS": 64}, {"RB_SWEEP_V2": 1},
+                {"RB_V1_ROWS": 4, "RB_NCHUNKS": 37}, {"RB_V1_ROWS": 4, "RB_NCHUNKS": 64}):
+        try:
+            def run():
+                c = water(N)
+                ms, pairs = c.benchSweep(st, 100)
+                return ms, c.sweepPlan()
+            ms, plan = with_env(cfg, run)
+            tf = 20.0 * N * N / (ms * 1e-3) / 1e12
+            print(f"n4096 sweep {cfg}: {ms * 1e3:.1f} us {tf:.2f} TF {tf / peak:.3f} {plan}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"n4096 sweep {cfg}: FAILED {e}", flush=True)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    for cfg in ({}, {"RB_NCHUNKS": 16}, {"RB_NCHUNKS": 64}):
+        def run():
+            c = water(N, guess="warm")
+            stp = api.AutonomousRungeKuttaStepper(c, 1e-3)
+            y = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+            stp.initialize(y, True)
+            stp.runSteps(20)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            stp.runSteps(300)
+            b.record()
+            torch.cuda.synchronize()
+            return 300 / (a.elapsed_time(b) * 1e-3), stp.stats(), c.solve_stats()
+        try:
+            rate, ss, cs = with_env(cfg, run)
+            print(f"n4096 steps {cfg}: {rate:.1f} steps/s {ss} {cs}", flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"n4096 steps {cfg}: FAILED {e}", flush=True)
+
+
+def steprates():
+    """RK4 step rate at the bench sizes with the committed defaults."""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    for N, dt, steps in ((1024, 1e-3, 300), (4096, 1e-3, 300), (16384, 1e-4, 60), (65536, 1e-4, 20)):
+        c = water(N, guess="warm")
+        stp = api.AutonomousRungeKuttaStepper(c, dt)
+        y = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+        stp.initialize(y, True)
+        stp.runSteps(14)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        stp.runSteps(steps)
+        b.record()
+        torch.cuda.synchronize()
+        print(f"steprate N={N}: {steps / (a.elapsed_time(b) * 1e-3):.1f} steps/s {stp.stats()} {c.solve_stats()} {c.sweepPlan()}", flush=True)
+
+
+SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates)
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(SECTIONS)
+    for n in names:
+        t0 = time.time()
+        try:
+            SECTIONS[n]()
+        except Exception:  # noqa: BLE001
+            print(f"[{n}] EXCEPTION")
+            traceback.print_exc()
+        print(f"[{n}] done in {time.time() - t0:.1f}s", flush=True)
+    with open(os.path.join(OUT, "round2_results.json"), "a") as f:
+        f.write(json.dumps(RESULTS) + "\n")

@@ -94,6 +94,9 @@ def test_header_is_plain_c_and_ctypes_layouts_match_it(tmp_path):
         for f in fields:
             lines.append(f'printf(" %zu", offsetof({name}, {f}));')
         lines.append('printf("\\n");')
+    # rb_complex = the reference's c_double: 16 bytes, 16-byte aligned (L/ExportTypes.cuh:7, :78-79), also as a struct member
+    lines += ['struct holder { char c; rb_complex z; };',
+              'printf("rb_complex_align %zu %zu %zu\\n", sizeof(rb_complex), (size_t)_Alignof(rb_complex), offsetof(struct holder, z));']
     lines += ['return 0;', '}']
     src = tmp_path / "probe.c"
     src.write_text("\n".join(lines))
@@ -102,6 +105,9 @@ def test_header_is_plain_c_and_ctypes_layouts_match_it(tmp_path):
     out = subprocess.check_output([str(exe)], text=True)
     for line in out.strip().splitlines():
         name, size, *offs = line.split()
+        if name == "rb_complex_align":
+            assert (int(size), int(offs[0]), int(offs[1])) == (16, 16, 16)
+            continue
         c = getattr(_lib, name)
         assert ctypes.sizeof(c) == int(size), name
         for f, o in zip(probes[name], offs):

@@ -338,8 +338,23 @@ def test_rhs_rejects_nothing_silently(api):
     props = api.ProblemProperties(rho=0.0)
     calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), max_iterations=30)
     out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+    with pytest.raises(RuntimeError, match="did not converge"):   # strict (the default): the call itself fails
+        calc.run(T(ro.pack_state(Z, Phi)), out)
+    st = calc.solve_stats()
+    assert not st["converged"] and not st["stagnated"] and st["failed_solves"] == 1
+    calc.setStrict(False)                                          # statistics only: the call returns, the status still says failed
     calc.run(T(ro.pack_state(Z, Phi)), out)
-    assert not calc.solve_stats()["converged"] or not np.isfinite(out.cpu().numpy()).all()
+    st = calc.solve_stats()
+    assert not st["converged"] and not st["stagnated"] and st["failed_solves"] == 2
+    # the same through the stepper: a failed step leaves the state as it was
+    calc.setStrict(True)
+    stp = api.AutonomousRungeKuttaStepper(calc, 1e-3)
+    y0 = T(ro.pack_state(Z, Phi))
+    keep = y0.clone()
+    stp.initialize(y0, True)
+    with pytest.raises(RuntimeError, match="did not converge"):
+        stp.runStep()
+    assert bool((torch.view_as_real(y0) == torch.view_as_real(keep)).all())
 
 
 # ---- RK4 ------------------------------------------------------------------------------------------------------------

@@ -2,10 +2,8 @@
 Jacobian from batched RHS evaluations, implicit Gauss-Legendre-2 integrator and their legacy exports, through the C ABI, against
 the CPU oracle and the trajectories of the reference's own Python integrator (tests/golden/ref_gl2.npz).
 
-STATUS: written after round 1's GPU budget was spent -- the library builds and every symbol loads (CPU tier), but these tests
-have not yet been run on hardware.  They are therefore marked xfail(strict=False): a pass is reported as XPASS, a failure does
-not hide behind the rest of the suite, and the file is named to run last so that nothing here can disturb the verified tests.
-The marker goes away with the first hardware run.
+STATUS: all cases pass on a B200 (round 1's closing driver run: 47 XPASS; round 2: run as ordinary tests, a regression fails the
+suite).  The file is still named to run last.
 
 Tolerances: the Jacobian is a central difference with eps = 1e-6 of two RHS evaluations that agree with the oracle's to ~1e-13
 (relative), so entries agree to ~1e-13 / 2e-6 ~ 1e-7 of the RHS scale; Gauss-Legendre steps are solved to the Newton tolerance
@@ -16,8 +14,7 @@ import numpy as np
 import pytest
 
 STOP_AFTER_TIMEOUT = True   # tests/conftest.py: one timeout skips the rest of this module
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180),
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 torch = pytest.importorskip("torch")
 from oracle import roberts_oracle as ro  # noqa: E402
