@@ -44,6 +44,7 @@ CASES = [
     _case("rhs_water_N256_multimode", "rhs", "water", 256, 0.2, surface="multimode"),
     _case("rhs_water_N1024", "rhs", "water", 1024, 0.4),
     _case("rhs_water_N4096", "rhs", "water", 4096, 0.4),
+    _case("rhs_water_N16384", "rhs", "water", 16384, 0.4),      # the largest size the reference's harness instantiates
     _case("rhs_helium_inf_N256", "rhs", "helium_inf", 256, 0.05, depth=0.3),
     _case("rhs_helium_N256", "rhs", "helium", 256, 0.01, depth=0.3),
     _case("rhs_helium_N256_kappa", "rhs", "helium", 256, 0.01, depth=0.3, kappa=0.01),
@@ -53,7 +54,8 @@ CASES = [
     _case("rk4_water_N64_100", "rk4", "water", 64, 0.1, dt=1e-3, steps=100),
     _case("rk4_water_N256_100", "rk4", "water", 256, 0.3, dt=1e-3, steps=100),
     _case("rk4_water_N1024_100", "rk4", "water", 1024, 0.4, dt=1e-3, steps=100),
-    _case("rk4_water_N4096_20", "rk4", "water", 4096, 0.4, dt=1e-3, steps=20),
+    _case("rk4_water_N4096_100", "rk4", "water", 4096, 0.4, dt=1e-3, steps=100),   # BASELINE config 3 / half of the metric, the full 100 steps
+    _case("rk4_water_N16384_10", "rk4", "water", 16384, 0.4, dt=1e-4, steps=10),   # dt: RK4 stability limit 2.83 (1-h) / (h N/2), DESIGN.md section 5
     _case("rk4_helium_inf_N256_100", "rk4", "helium_inf", 256, 0.05, depth=0.3, dt=1e-3, steps=100),
     _case("rk4_helium_film_N256_100", "rk4", "helium", 256, 0.1, surface="film", depth=0.0942478, dt=1e-3, steps=100),
 ]

@@ -197,6 +197,82 @@ def test_cotangent_sum_is_linear_and_row_local_at_full_size(api):
     assert rel(S1[inner], ro.cot_rowsum(Z, x1, inner)) <= 1e-12
 
 
+def _spot_rows(N):
+    """>= 32 scattered rows: cell boundaries (every 256), the wrap-around ends, the middle, and pseudo-random interior rows."""
+    rng = np.random.default_rng(7)
+    rows = np.r_[0:3, N - 3:N, 254:258, 510:514, N // 2 - 2:N // 2 + 2, N // 3, 2 * N // 3 + 1, rng.integers(0, N, 14)]
+    return np.unique(rows)
+
+
+@pytest.mark.parametrize("N,h,physics", [(65536, 0.4, "water"), (49152, 0.3, "water"), (16384, 0.4, "water")])
+def test_full_rhs_rows_at_the_headline_size_match_direct_evaluation(api, N, h, physics):
+    """The kernels the headline times (tiled sweep, 4 rows per thread at N >= 49152: MV epilogue of the solve, VEL epilogue of the
+    velocities and dPhi/dt) against an independent formula AT the metric's own size, where no dense oracle fits: after rb_rhs, on
+    >= 32 scattered rows k,
+      (1) the solve: | b_k - (M a)_k | / max|b| <= 1e-11, with (M a)_k = Mdiag_k a_k + (1/4pi) Im(Zp_k S_k) (L/createM.cuh:43-63),
+      (2) the velocity: conj[ (-i/4pi) S_k + V1diag_k a_k + V2_k a'_k ] (L/WaterVelocities.cuh:38-70, 217-241),
+      (3) dPhi/dt = -Y + |w|^2 / 2 (L/createM.cuh:96-107 at rho = 0),
+    S_k = sum_{j != k} cot((z_k - z_j)/2) a_j by the oracle's direct 1/tan evaluation (ro.cot_rowsum) of the GPU's own a.
+    Zp, Zpp, b are the GPU's (the derivatives carry N eps .. N^2 eps / 4 of round-off noise in ANY implementation: they are pinned
+    separately at sizes the reference runs); a' = (2 pi / N) D1 a by the oracle's FFT derivative.  Tolerances, relative to the max
+    of the compared array: 1e-11 for (1); 5e-11 for (2) and (3) (the direct 1/tan itself loses eps N / 2 pi = 2e-12 on wrap-around
+    pairs, the FFT derivative of a another N eps)."""
+    Z, Phi = ro.trochoid(N, h)
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    plan = calc.sweepPlan()
+    assert plan["kernel"] == "tiled" and plan["rows_per_thread"] == (4 if N >= 49152 else 2), plan
+    out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+    calc.run(T(ro.pack_state(Z, Phi)), out)
+    st = calc.solve_stats()
+    assert st["converged"] and st["residual"] <= 1e-13, st
+    o = out.cpu().numpy()
+    a = calc.getDevA().cpu().numpy()
+    Zp, Zpp, b = calc.getDevZp().cpu().numpy(), calc.getDevZpp().cpu().numpy(), calc.devPhiPrime.cpu().numpy()
+    rows = _spot_rows(N)
+    assert len(rows) >= 32
+    S = ro.cot_rowsum(Z, a, rows)
+    inv4pi = 0.25 / np.pi
+    Ma = (0.5 + inv4pi * (Zpp[rows] / Zp[rows]).imag) * a[rows] + inv4pi * (Zp[rows] * S).imag
+    res = np.abs(b[rows] - Ma).max() / np.abs(b).max()
+    assert res <= 1e-11, res
+    ap = ro.fft_derivative(a.astype(np.complex128), 2.0 * np.pi / N)
+    w = -1j * inv4pi * S + (-1j * inv4pi * Zpp[rows] / Zp[rows] ** 2 + 0.5 / Zp[rows]) * a[rows] + 1j / (2.0 * np.pi * Zp[rows]) * ap[rows]
+    ev = np.abs(o[rows] - np.conj(w)).max() / np.abs(o[:N]).max()
+    assert ev <= 5e-11, ev
+    dphi = -Z.imag[rows] + 0.5 * np.abs(w) ** 2
+    ed = np.abs(o[N + rows] - dphi).max() / np.abs(o[N:]).max()
+    assert ed <= 5e-11, ed
+    print(f"N={N}: rows {len(rows)}, solve residual {res:.2e}, velocity {ev:.2e}, dPhi/dt {ed:.2e}, {st}")
+
+
+@pytest.mark.parametrize("N,dt", [(65536, 1e-4), (4096, 1e-3)])
+def test_recorded_steps_equal_unrecorded_steps_at_the_headline_size(api, N, dt):
+    """The kernels of a RECORDED step (solver sweep + combined verify-and-velocity sweep with the RK update folded into
+    finish_solve, stage-history start) against the unrecorded sequence (solver sweeps to convergence, then the velocity sweep the
+    test above pins row by row, separate update kernels) at the sizes the metric is quoted on: both integrate the same system with
+    every solve verified to 1e-13, so 8 steps must agree to ~1e-12 (tolerance 1e-11 relative, position and potential)."""
+    props = api.ProblemProperties(rho=0.0)
+    y0 = ro.pack_state(*ro.trochoid(N, 0.4))
+    states = []
+    for no_graph in ("0", "1"):
+        os.environ["RB_NO_GRAPH"] = no_graph
+        try:
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+        finally:
+            os.environ.pop("RB_NO_GRAPH", None)
+        y = T(y0)
+        stp.initialize(y, True)
+        stp.runSteps(8)
+        st, ss = calc.solve_stats(), stp.stats()
+        assert st["converged"] and st["failed_solves"] == 0, st
+        assert (ss["graph_launches"] >= 1) == (no_graph == "0"), ss
+        states.append(y.cpu().numpy())
+    assert rel(states[0][:N], states[1][:N]) <= 1e-11
+    assert rel(states[0][N:], states[1][N:]) <= 1e-11
+
+
 # ---- full RHS -------------------------------------------------------------------------------------------------------
 def _split(state):
     N = len(state) // 3
