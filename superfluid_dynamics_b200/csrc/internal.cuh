@@ -158,6 +158,10 @@ struct SweepArgs {
     double2* partial;                // [batch][nchunks][N] partial T sums
     double2* partial_img;            // same for the image sum
     unsigned int* cell_tickets;      // [batch][ncell]   level-1 counters (zero on entry, reset on exit)
+    int chunk_group, ngroups;        // two-level reduction of the chunk partials: chunks per group (0: single level), number of groups
+    double2* gpartial;               // [batch][ngroups][N] group sums
+    double2* gpartial_img;
+    unsigned int* group_tickets;     // [batch][ncell][ngroups] (zero on entry, reset on exit)
     unsigned int* member_tickets;    // [batch]          level-2 counters
     SolveCtrl* ctrl;
     // physics

@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(kCell / RPT, RPT == 4 ? 8 : (IMAGE ? 5 : 7)) s
         if (IMAGE) tile_accumulate_far<RPT>(shI, shgI, tile, ekG, UI, VI);
     }
 
-    // ---- publish the partial sums, elect the finishing CTA of this row cell --------------------
+    // ---- publish the partial sums; the last CTA(s) of this row cell add them up ----------------------
     const size_t pbase = ((size_t)bm * a.nchunks + chunk) * N;
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
@@ -636,35 +636,27 @@ __global__ void __launch_bounds__(kCell / RPT, RPT == 4 ? 8 : (IMAGE ? 5 : 7)) s
     }
     __threadfence();
     __syncthreads();
-    unsigned int* cticket = a.cell_tickets + (size_t)bm * a.ncell + cellK;
-    if (t == 0) s_ticket = atomicAdd(cticket, 1u);
-    __syncthreads();
-    if (s_ticket != (unsigned)(a.nchunks - 1)) return;
-    __threadfence();
-    if (t == 0) *cticket = 0u;   // ready for the next launch
 
-    // ---- finishing CTA: fixed-order reduction over chunks + epilogue ---------------------------
-    double2 T[RPT], TI[RPT];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        T[r] = make_double2(0.0, 0.0);
-        TI[r] = make_double2(0.0, 0.0);
-    }
-    {
-        // independent loads are issued in batches of 8 (memory-level parallelism), the additions stay in chunk order
+    // sum of `count` consecutive slices (stride N) of a partial-sum workspace for this thread's rows: independent loads are issued in
+    // batches (memory-level parallelism), the additions stay in slice order (deterministic)
+    auto ordered_sum = [&](const double2* __restrict__ base, const double2* __restrict__ ibase, int count, double2 (&T)[RPT],
+                           double2 (&TI)[RPT]) {
         constexpr int kBatch = (IMAGE ? 4 : 8) * 2 / RPT;
         const size_t cstride = (size_t)N;
-        const double2* pbase0 = a.partial + (size_t)bm * a.nchunks * N;
-        const double2* ibase0 = IMAGE ? a.partial_img + (size_t)bm * a.nchunks * N : nullptr;
-        for (int c0 = 0; c0 < a.nchunks; c0 += kBatch) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            T[r] = make_double2(0.0, 0.0);
+            TI[r] = make_double2(0.0, 0.0);
+        }
+        for (int c0 = 0; c0 < count; c0 += kBatch) {
             double2 v[RPT][kBatch], vi[RPT][kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
 #pragma unroll
                 for (int r = 0; r < RPT; ++r) {
-                    const bool ok = (c0 + u) < a.nchunks && krow[r] < N;
-                    v[r][u] = ok ? ldcg_d2(pbase0 + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
-                    if (IMAGE) vi[r][u] = ok ? ldcg_d2(ibase0 + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
+                    const bool ok = (c0 + u) < count && krow[r] < N;
+                    v[r][u] = ok ? ldcg_d2(base + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
+                    if (IMAGE) vi[r][u] = ok ? ldcg_d2(ibase + (size_t)(c0 + u) * cstride + krow[r]) : make_double2(0.0, 0.0);
                 }
             }
 #pragma unroll
@@ -676,7 +668,45 @@ __global__ void __launch_bounds__(kCell / RPT, RPT == 4 ? 8 : (IMAGE ? 5 : 7)) s
                 }
             }
         }
+    };
+
+    double2 T[RPT], TI[RPT];
+    unsigned int* cticket = a.cell_tickets + (size_t)bm * a.ncell + cellK;
+    // Two levels when a.chunk_group > 0: the chunks of a row cell are reduced in groups as the groups complete (overlapped with the
+    // CTAs still computing), and the last group to complete adds the group sums.  The serial tail of a launch shrinks from nchunks
+    // to ~2 sqrt(nchunks) slices; the summation order (chunks in order within a group, groups in order) stays fixed.  One loop
+    // with a single ordered_sum site keeps the register budget of the main loop what it was.
+    const int grp = a.chunk_group;
+    const int g = grp > 0 ? chunk / grp : 0;
+    bool final_level = grp <= 0;
+    for (;;) {
+        unsigned int* ticket = final_level ? cticket : a.group_tickets + ((size_t)bm * a.ncell + cellK) * a.ngroups + g;
+        const int first = final_level ? 0 : g * grp;
+        const bool from_groups = final_level && grp > 0;
+        const int count = final_level ? (grp > 0 ? a.ngroups : a.nchunks) : min(grp, a.nchunks - first);
+        if (t == 0) s_ticket = atomicAdd(ticket, 1u);
+        __syncthreads();
+        if (s_ticket != (unsigned)(count - 1)) return;
+        __threadfence();
+        if (t == 0) *ticket = 0u;   // ready for the next launch
+        const size_t off = from_groups ? (size_t)bm * a.ngroups * N : ((size_t)bm * a.nchunks + first) * N;
+        const double2* src = (from_groups ? a.gpartial : a.partial) + off;
+        const double2* srcI = IMAGE ? (from_groups ? a.gpartial_img : a.partial_img) + off : nullptr;
+        ordered_sum(src, srcI, count, T, TI);
+        if (final_level) break;
+        const size_t gbase = ((size_t)bm * a.ngroups + g) * N;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            if (krow[r] < N) {
+                a.gpartial[gbase + krow[r]] = T[r];
+                if (IMAGE) a.gpartial_img[gbase + krow[r]] = TI[r];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        final_level = true;
     }
+    // ---- epilogue (one CTA per row cell gets here) ---------------------------------------------------
     const double sumx = block_sum_fixed<THREADS>(a.xsum_part + (size_t)bm * a.ncell, a.ncell, sred);
     const double inv4pi = 0.25 / kPi;
 

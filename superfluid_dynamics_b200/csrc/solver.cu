@@ -76,6 +76,7 @@ struct rb_solver {
 
     // chunking of the tiled sweep (pair_kernels.cu)
     int tile = 256, tiles_per_chunk = 1, nchunks = 1;
+    int chunk_group = 0;           // two-level reduction of the chunk partials: chunks per group (0: single level)
     int v1_rows = 2;               // tiled kernel: rows per thread (RB_V1_ROWS)
     // schedule of the persistent sweep (pair_kernels2.cu); used whenever there is no image sum
     bool use_v2 = false;
@@ -98,7 +99,9 @@ struct rb_solver {
     double* xsum_part[2] = {nullptr, nullptr};
     double *xsum_a = nullptr, *rnorm_part = nullptr, *bnorm_part = nullptr, *energies = nullptr;
     double2 *ac = nullptr, *aprime = nullptr, *vel_upper = nullptr;
-    double2 *partial = nullptr, *partial_img = nullptr;
+    double2 *partial = nullptr, *partial_img = nullptr, *gpartial = nullptr, *gpartial_img = nullptr;
+    unsigned int* group_tickets = nullptr;
+    int ngroups = 1;
     unsigned int *cell_tickets = nullptr, *member_tickets = nullptr;
     SolveCtrl* ctrl_all = nullptr;   // [4]: one control block per RK stage (standalone calls use block 0)
     SolveCtrl* ctrl = nullptr;       // the block the next solve uses
@@ -187,7 +190,7 @@ static void solver_free(rb_solver* s) {
         if (s->peer_mapped[r]) cudaIpcCloseMemHandle(s->peer_mapped[r]);
     void* ptrs[] = {s->deriv, s->fwork, s->EG, s->P0, s->Pm, s->Pp, s->EI, s->V1diag, s->V2, s->Mdiag, s->b, s->a,
                     s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
-                    s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->cell_tickets,
+                    s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->gpartial, s->gpartial_img, s->group_tickets, s->cell_tickets,
                     s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state, s->gm_V, s->gm_x, s->gm_t,
                     s->gm_dev, s->gm_invP, s->v2_rnorm_part, s->v2_ticket, s->fft_tw, s->v2_partial, s->v2_xs_part,
                     s->v2_blk_tickets};
@@ -209,68 +212,35 @@ static void solver_free(rb_solver* s) {
 }
 
 // Source chunking of the tiled sweep.  A CTA is one 256-row cell x one chunk of sources; the grid is (row cells, chunks, members).
-// What a choice costs (all measured on a B200, N = 65536, 4 rows per thread, 8 CTAs resident per SM = 1184 slots):
-//   * a CTA among 8 co-resident ones evaluates ~0.2 us per source (256 x 1024 pairs in 207 us), a CTA left alone on an SM at most
-//     ~4x faster (its 2 warps reach 2 of the 4 sub-partitions): a nearly empty last wave costs a quarter of a full one;
-//   * the finishing CTA of a row cell adds its `nchunks` partial sums per row in chunk order, 4-8 loads in flight per thread:
-//     ~1 us per batch of loads AT THE TAIL of the launch, where nothing overlaps it.
-// Round 1 scaled the CTA count with 1 / row cells (target 148 x 128 CTAs), which on a rank owning 32 of the 256 row cells (8 GPUs)
-// gave nchunks = 512: 128 sources per CTA and a 128-batch serial reduction -- the per-rank sweep fell from 0.81 to 0.61 of the FP64
-// peak.  The plan below minimises  waves(nchunks) x t_cta(sources per chunk) + t_finish(nchunks)  over nchunks instead; on a
-// shard it lands on ONE balanced wave (32 cells x 37 chunks = 1184 CTAs at 8 GPUs, 64 x 18 at 4, 128 x 9 at 2), on a whole
-// N = 65536 surface on 64 chunks (13.8 waves) as measured best in round 1.
+// Measured on a B200 (solver sweep alone, us; profiles/r02a_shardtune_*.log, r02b_*), N = 65536, 4 rows per thread, per-rank share
+// of a G-rank run timed on one GPU with rb_debug_set_row_range:
+//   G = 1 (256 row cells): chunks 4 / 8 / 18 / 37 / 64 -> 3450 / 2995 / 2976 / 2887 / 2876          (ideal at the 1-GPU rate: 2876)
+//   G = 2 (128): 9 / 18 / 37 / 128 -> 1600 / 1574 / 1516 / 1479                                      (1438)
+//   G = 4 (64):  9 / 18 / 37 / 74 / 256 -> 884 / 855 / 774 / 736 / 751                               (719)
+//   G = 8 (32):  9 / 18 / 37 / 74 / 148 / 512 -> 605 / 502 / 431 / 404 / 390 / 451                   (359)
+// i.e. one balanced wave (32 x 37 = 1184 CTAs) is NOT the optimum: several waves of CTAs with 256-1024 sources each balance better,
+// until the serial reduction of the chunk partials by the finishing CTA of each row cell (one batch of loads per 4-8 chunks, at the
+// tail of the launch where nothing overlaps it) eats the gain -- which is what the two-level reduction in sweep_kernel removes
+// (groups of ~sqrt(nchunks) chunks are reduced as they complete).  Fewer, longer chunks also cost accuracy: a chunk's sum is one
+// serial accumulation, and at N = 65536 with 8 chunks the residual's round-off floor rises enough to need a third sweep per solve.
 static void choose_chunking(rb_solver* s) {
     const int N = s->N;
-    // measured on a B200 (solver sweep, us): N = 65536: 2 rows per thread 3200 (target 1184) / 3108 (2368); 4 rows per thread 3391 / 3011 /
+    // round 1, whole surfaces: N = 65536: 2 rows per thread 3200 (target 1184) / 3108 (2368); 4 rows per thread 3391 / 3011 /
     // 2931 (4736) / 2893 (9472) / 2875 (18944); 8 rows per thread 3556 at best -- the persistent kernel: 3113;
     // N = 32768: 832 / 813 | 912 / 830 / 819; N = 16384: 248 / 234 | 314 / 265 / 235; N = 8192: 80.5 / 74.2 | 102 / 84; N = 4096: 32.8 / 32.9 | 41
     const bool big = N >= 49152;
     s->v1_rows = env_int("RB_V1_ROWS", big ? 4 : 2) == 4 ? 4 : 2;
-    int nSM = 148;
-    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, s->device);
-    const int per_sm = s->v1_rows == 4 ? 8 : (s->has_image ? 5 : 7);   // __launch_bounds__ of sweep_kernel
-    const long slots = (long)nSM * per_sm;
+    const int target = env_int("RB_TARGET_CTAS", big ? 148 * 128 : (N >= 2048 ? 148 * 16 : 148 * 8));
     const long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
-    const int max_chunks = std::max(1, (N + 63) / 64);
-    int wanted;
-    if (env_int("RB_TARGET_CTAS", 0) > 0) {   // round-1 heuristic, kept for the knob sweeps of tests/gpu_debug.py
-        const int target = env_int("RB_TARGET_CTAS", 0);
-        wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
-    } else {
-        // cost model, in units of "one source evaluated by a CTA with a full SM around it" (~0.2 us)
-        const int wps = kCell / s->v1_rows / 32;                          // warps per CTA
-        const double full_smsp = per_sm * wps / 4.0;                      // warps per sub-partition when the SM is full
-        const double c0 = 16.0;                                           // fixed cost per CTA (prologue, partial store, ticket) ~ 3 us
-        const double fin = 1.25 * (s->v1_rows == 4 ? 1.0 : 0.5) * (s->has_image ? 2.0 : 1.0);   // per chunk, at the tail
-        const double wsat = env_int("RB_WSAT10", 10) / 10.0;              // warps per sub-partition that saturate its FP64 pipe
-        double best = 1e300;
-        wanted = 1;
-        for (int c = 1; c <= max_chunks; ++c) {
-            const int per = (((N + c - 1) / c + 63) / 64) * 64;
-            if (c > 1 && (long)(c - 1) * per >= N) continue;     // the last chunk would be empty
-            const long ctas = rows * c;
-            const long full = ctas / slots, rem = ctas % slots;
-            const double t_cta = per + c0;
-            double waves = (double)full;
-            if (rem) {
-                // a partly filled wave: the busiest sub-partition holds ceil(m wps / 4) warps of the m CTAs on the busiest SM; it
-                // takes that share of a full wave's time, stretched when fewer than `wsat` warps are there to hide the DFMA latency
-                const long m = (rem + nSM - 1) / nSM;
-                const double w = (double)((m * wps + 3) / 4);
-                waves += std::min(1.0, w / full_smsp / std::min(1.0, w / wsat));
-            }
-            const double cost = waves * t_cta + fin * c;
-            if (cost < best * (1.0 - 1e-9)) {
-                best = cost;
-                wanted = c;
-            }
-        }
-    }
+    int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
+    // never below `min_srcs` sources per CTA: the fixed cost of a CTA (prologue, partial store, tickets) is ~3 us ~ 16 sources' worth
+    const int min_srcs = env_int("RB_MIN_SRCS", big ? 256 : 64);
+    const int max_chunks = std::max(1, (N + min_srcs - 1) / min_srcs);
     wanted = std::min(wanted, max_chunks);
     wanted = env_int("RB_NCHUNKS", wanted);
     int srcs = (N + wanted - 1) / wanted;
     srcs = ((srcs + 63) / 64) * 64;
-    // largest tile (fewest barriers) that divides the chunk; the tiles of a chunk never straddle a 256-point cell differently
+    // largest tile (fewest barriers) that divides the chunk; tiles never straddle a 256-point cell
     if (srcs % 256 == 0) s->tile = 256;
     else if (srcs % 128 == 0) s->tile = 128;
     else s->tile = 64;
@@ -282,12 +252,38 @@ static void choose_chunking(rb_solver* s) {
     }
     int per = s->tile * s->tiles_per_chunk;
     s->nchunks = (N + per - 1) / per;
+    // two-level reduction of the chunk partials: groups of ~sqrt(nchunks) chunks (a multiple of 4 = one batch of loads)
+    int grp = 1;
+    if (s->nchunks > 16) {
+        grp = 4;
+        while (grp * grp < s->nchunks) grp += 4;
+    }
+    grp = env_int("RB_CHUNK_GROUP", grp);
+    s->chunk_group = grp >= 2 && grp < s->nchunks ? grp : 0;   // 0: single level
     if (env_int("RB_VERBOSE", 0))
-        std::fprintf(stderr, "[roberts_b200] tiled sweep plan: N=%d rows/thread=%d row cells=%ld tile=%d tiles/chunk=%d nchunks=%d -> %ld CTAs on %ld slots\n",
-                     N, s->v1_rows, rows, s->tile, s->tiles_per_chunk, s->nchunks, rows * s->nchunks, slots);
+        std::fprintf(stderr, "[roberts_b200] tiled sweep plan: N=%d rows/thread=%d row cells=%ld tile=%d tiles/chunk=%d nchunks=%d group=%d -> %ld CTAs\n",
+                     N, s->v1_rows, rows, s->tile, s->tiles_per_chunk, s->nchunks, s->chunk_group, rows * s->nchunks);
 }
 
 static void set_stream(rb_solver* s, cudaStream_t st);
+
+// workspaces of the tiled sweep that depend on the chunking (re-made whenever the plan changes)
+static void alloc_partials(rb_solver* s) {
+    for (void* p : {(void*)s->partial, (void*)s->partial_img, (void*)s->gpartial, (void*)s->gpartial_img, (void*)s->group_tickets})
+        if (p) cudaFree(p);
+    s->partial = s->partial_img = s->gpartial = s->gpartial_img = nullptr;
+    s->group_tickets = nullptr;
+    s->ngroups = s->chunk_group > 0 ? (s->nchunks + s->chunk_group - 1) / s->chunk_group : 1;
+    s->partial = dmalloc<double2>((size_t)s->nchunks * s->BN);
+    if (s->has_image) s->partial_img = dmalloc<double2>((size_t)s->nchunks * s->BN);
+    if (s->chunk_group > 0) {
+        s->gpartial = dmalloc<double2>((size_t)s->ngroups * s->BN);
+        if (s->has_image) s->gpartial_img = dmalloc<double2>((size_t)s->ngroups * s->BN);
+        const size_t nt = (size_t)s->batch * s->ncell * s->ngroups;
+        s->group_tickets = dmalloc<unsigned int>(nt);
+        RB_CUDA(cudaMemset(s->group_tickets, 0, nt * sizeof(unsigned int)));
+    }
+}
 
 // static schedule of the persistent sweep: row blocks of RB rows, (RB/R) x groups threads, staged tiles of groups*spg sources
 static void plan_sweep2(rb_solver* s) {
@@ -500,8 +496,7 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     s->ac = dmalloc<double2>(BN);
     s->aprime = dmalloc<double2>(BN);
     s->vel_upper = dmalloc<double2>(BN);
-    s->partial = dmalloc<double2>((size_t)s->nchunks * BN);
-    if (s->has_image) s->partial_img = dmalloc<double2>((size_t)s->nchunks * BN);
+    alloc_partials(s);
     s->cell_tickets = dmalloc<unsigned int>(pc);
     s->member_tickets = dmalloc<unsigned int>(batch);
     s->ctrl_all = dmalloc<SolveCtrl>(4);
@@ -690,6 +685,11 @@ static SweepArgs base_args(rb_solver* s, const double2* Z) {
     a.g = make_geometry(s, Z);
     a.partial = s->partial;
     a.partial_img = s->partial_img;
+    a.chunk_group = s->chunk_group;
+    a.ngroups = s->ngroups;
+    a.gpartial = s->gpartial;
+    a.gpartial_img = s->gpartial_img;
+    a.group_tickets = s->group_tickets;
     a.cell_tickets = s->cell_tickets;
     a.member_tickets = s->member_tickets;
     a.ctrl = s->ctrl;
@@ -817,8 +817,8 @@ static void gmres_solve(rb_solver* s, const double2* Z) {
 
     std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
     int applies = 0;
-    double rel = 1e300, bnorm = 0.0;
-    bool converged = false;
+    double rel = 1e300, bnorm = 0.0, prev_cycle_rel = 1e300;
+    bool converged = false, stagnated = false;
     const int max_applies = s->props.max_iterations;
     for (int restart = 0; restart < 50 && !converged && applies < max_applies; ++restart) {
         // true residual r = b - M x
@@ -837,6 +837,14 @@ static void gmres_solve(rb_solver* s, const double2* Z) {
             converged = true;
             break;
         }
+        // the true residual after a whole restart cycle no better than half the one before it, and already <= 1e-10: the iteration
+        // sits on the round-off floor of this operator (eps x cond(M), cond ~ N / 2 pi for the thin film) -- same rule, same
+        // status as the Richardson solver's (solve_decide): accepted, reported as stagnated, never as converged
+        if (restart > 0 && rel <= 1e-10 && rel > 0.5 * prev_cycle_rel) {
+            stagnated = true;
+            break;
+        }
+        prev_cycle_rel = rel;
         launch_normalize(V, V, dh, n, st);
         std::fill(g.begin(), g.end(), 0.0);
         g[0] = beta;
@@ -889,12 +897,12 @@ static void gmres_solve(rb_solver* s, const double2* Z) {
     }
     s->last_iters = applies;
     s->last_converged = converged ? 1 : 0;
-    s->last_stagnated = 0;
+    s->last_stagnated = (stagnated && !converged) ? 1 : 0;
     s->last_rel = rel;
     account_solve(s);
     launch_finish_solve(s->gm_x, s->gm_x, nullptr, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
     s->have_prev_a = true;
-    note_solve_end(s, s->last_converged, 0, rel, applies, "GMRES");
+    note_solve_end(s, s->last_converged, s->last_stagnated, rel, applies, "GMRES");
 }
 
 // M a = b.  On return a (real), ac (complex copy) and the per-cell sums of a are valid on the stream.
@@ -1942,12 +1950,7 @@ int rb_comm_init(rb_solver* s, int rank, int nranks, const char* handles) {
     plan_sweep2(s);
     choose_sweep_kernel(s);
     choose_chunking(s);
-    cudaFree(s->partial);
-    s->partial = dmalloc<double2>((size_t)s->nchunks * s->BN);
-    if (s->has_image) {
-        cudaFree(s->partial_img);
-        s->partial_img = dmalloc<double2>((size_t)s->nchunks * s->BN);
-    }
+    alloc_partials(s);
     RB_CATCH
 }
 
@@ -1968,12 +1971,7 @@ int rb_debug_set_row_range(rb_solver* s, int cell0, int cells) {
     plan_sweep2(s);
     choose_sweep_kernel(s);
     choose_chunking(s);
-    cudaFree(s->partial);
-    s->partial = dmalloc<double2>((size_t)s->nchunks * s->BN);
-    if (s->has_image) {
-        cudaFree(s->partial_img);
-        s->partial_img = dmalloc<double2>((size_t)s->nchunks * s->BN);
-    }
+    alloc_partials(s);
     RB_CATCH
 }
 
@@ -2012,6 +2010,7 @@ int rb_comm_destroy(rb_solver* s) {
     plan_sweep2(s);
     choose_sweep_kernel(s);
     choose_chunking(s);
+    alloc_partials(s);
     RB_CATCH
 }
 

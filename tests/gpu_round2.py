@@ -40,32 +40,40 @@ def with_env(cfg, fn):
 
 
 def shardtune():
-    """Per-rank sweep of a row-sharded run, timed on one GPU (rb_debug_set_row_range): source chunks vs time, N = 65536 and 16384."""
+    """Per-rank sweep of a row-sharded run, timed on one GPU (rb_debug_set_row_range): source chunks vs time."""
     peak = api.measure_fp64_peak(dev)
     rows = []
-    for N, cands in ((65536, {1: (0, 4, 8, 9, 18, 37, 64), 2: (0, 9, 18, 27, 37, 128), 4: (0, 9, 18, 37, 55, 74, 256),
-                              8: (0, 9, 18, 23, 37, 74, 111, 148, 512)}),
-                     (16384, {1: (0, 8, 16, 32), 2: (0, 8, 16, 32), 4: (0, 9, 16, 32, 64), 8: (0, 9, 18, 32, 64, 129)})):
+    nc = lambda *v: [{"RB_NCHUNKS": x} if x else {} for x in v]
+    plans = (
+        (65536, {1: nc(0, 37, 64, 128), 2: nc(0, 37, 74, 128, 256), 4: nc(0, 74, 148, 256, 512),
+                 8: nc(0, 74, 148, 256, 512) + [{"RB_NCHUNKS": 148, "RB_CHUNK_GROUP": 1}, {"RB_NCHUNKS": 512, "RB_CHUNK_GROUP": 1},
+                                                {"RB_NCHUNKS": 256, "RB_CHUNK_GROUP": 8}, {"RB_NCHUNKS": 256, "RB_CHUNK_GROUP": 32}]}),
+        (16384, {1: nc(0, 32, 64, 128) + [{"RB_V1_ROWS": 4, "RB_NCHUNKS": 64}, {"RB_V1_ROWS": 4, "RB_NCHUNKS": 128}],
+                 2: nc(0, 32, 64, 128), 4: nc(0, 64, 128, 256) + [{"RB_V1_ROWS": 4, "RB_NCHUNKS": 128}],
+                 8: nc(0, 64, 128, 256) + [{"RB_V1_ROWS": 4, "RB_NCHUNKS": 128}, {"RB_V1_ROWS": 4, "RB_NCHUNKS": 256}]}),
+        (4096, {1: nc(0, 16, 32, 64) + [{"RB_NCHUNKS": 64, "RB_CHUNK_GROUP": 1}, {"RB_V1_ROWS": 4, "RB_NCHUNKS": 64}, {"RB_SWEEP_V2": 1}],
+                2: nc(0, 64), 4: nc(0, 64)}),
+    )
+    for N, cands in plans:
         st = T(ro.pack_state(*ro.trochoid(N, 0.4)))
         ncell = N // 256
-        for G, ncs in cands.items():
-            for nc in ncs:
-                cfg = {"RB_NCHUNKS": nc} if nc else {}
-
+        for G, cfgs in cands.items():
+            for cfg in cfgs:
                 def run():
                     c = water(N)
                     if G > 1:
                         c.debugSetRowRange((G // 2) * (ncell // G), ncell // G)
-                    ms, pairs = c.benchSweep(st, 10 if N >= 65536 else 30)
+                    ms, pairs = c.benchSweep(st, 10 if N >= 65536 else 40)
                     return ms, c.sweepPlan()
                 try:
                     ms, plan = with_env(cfg, run)
                     tf = 20.0 * N * (N / G) / (ms * 1e-3) / 1e12
-                    rows.append(dict(N=N, G=G, asked=nc, us=ms * 1e3, tflops=tf, frac=tf / peak, **plan))
-                    print(f"shardtune N={N} G={G} nchunks={'auto' if not nc else nc}: {ms * 1e3:8.1f} us  {tf:5.2f} TF  {tf / peak:.3f}  {plan}",
+                    rows.append(dict(N=N, G=G, cfg=cfg, us=ms * 1e3, tflops=tf, frac=tf / peak, **plan))
+                    print(f"shardtune N={N} G={G} {cfg}: {ms * 1e3:8.1f} us  {tf:5.2f} TF  {tf / peak:.3f}  "
+                          f"tile={plan['tile']}x{plan['tiles_per_chunk']} nchunks={plan['nchunks']} ctas={plan['ctas']} rpt={plan['rows_per_thread']} {plan['kernel']}",
                           flush=True)
                 except Exception as e:  # noqa: BLE001
-                    print(f"shardtune N={N} G={G} nchunks={nc}: FAILED {e}", flush=True)
+                    print(f"shardtune N={N} G={G} {cfg}: FAILED {e}", flush=True)
     RESULTS["shardtune"] = dict(peak=peak, rows=rows)
 
 
