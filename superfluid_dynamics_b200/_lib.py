@@ -117,6 +117,7 @@ SIGNATURES = {
     "rb_rk4_get_state": (c_int, [_P, _P]),
     "rb_rk4_current_time": (c_double, [_P]),
     "rb_rk4_stats": (c_int, [_P, _D]),
+    "rb_rk4_chunk_stats": (c_int, [_P, _D]),
     "rb_rk4_guess_stats": (c_int, [_P, _D]),
     "rb_rk4_set_optimistic": (c_int, [_P, c_int]),
     "rb_rk4_set_guess": (c_int, [_P, c_int, c_int]),

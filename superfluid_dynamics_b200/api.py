@@ -309,7 +309,10 @@ class AutonomousRungeKuttaStepper:
     def stats(self):
         out = (ctypes.c_double * 4)()
         check(self.lib.rb_rk4_stats(self.handle, out), "rb_rk4_stats")
-        return dict(graph_launches=int(out[0]), graph_captures=int(out[1]), fallback_steps=int(out[2]), graph_sweeps=int(out[3]))
+        ch = (ctypes.c_double * 4)()
+        check(self.lib.rb_rk4_chunk_stats(self.handle, ch), "rb_rk4_chunk_stats")
+        return dict(graph_launches=int(out[0]), graph_captures=int(out[1]), fallback_steps=int(out[2]), graph_sweeps=int(out[3]),
+                    chunk_steps=int(ch[0]), chunks=int(ch[1]), chunks_rolled_back=int(ch[2]))
 
     def guessStats(self):
         out = (ctypes.c_double * 8)()

@@ -193,9 +193,9 @@ static Staging gl2_residual_and_phi(rb_gl2* g, const double* y, const double* k,
     r.normK = std::sqrt(g->h_sums[1]);
     // slopes that throw the stage states far off the surface can leave the inner solve (or the sums) without an answer: such
     // slopes are simply not acceptable to the line search
-    double stats[6];
-    check_rc(rb_solve_stats(g->s2, stats), "rb_solve_stats");
-    if (stats[1] == 0.0 || !(r.phi == r.phi)) {
+    double status[8];   // [0] converged, [1] stagnated on the round-off floor (accepted); neither: the solve failed
+    check_rc(rb_solve_status(g->s2, status), "rb_solve_status");
+    if ((status[0] == 0.0 && status[1] == 0.0) || !(r.phi == r.phi)) {
         r.phi = HUGE_VAL;
         r.residualNorm = HUGE_VAL;
     }
@@ -205,9 +205,9 @@ static Staging gl2_residual_and_phi(rb_gl2* g, const double* y, const double* k,
 static void gl2_jacobian(rb_gl2* g, const double* y, double* J) {
     jacobian_calculate(g->jac, y, J);
     ++g->stats.jacobians;
-    double stats[6];
-    check_rc(rb_solve_stats(g->jac->batched, stats), "rb_solve_stats (Jacobian)");
-    if (stats[1] == 0.0) throw std::runtime_error("Gauss-Legendre: the batched solve behind the Jacobian did not converge");
+    double status[8];
+    check_rc(rb_solve_status(g->jac->batched, status), "rb_solve_status (Jacobian)");
+    if (status[0] == 0.0 && status[1] == 0.0) throw std::runtime_error("Gauss-Legendre: the batched solve behind the Jacobian did not converge");
 }
 
 // gaussLegendreS2Step, L/GaussLegendre.cuh:441-560 == gauss_legendre_s2_step, P/integration/gauss_legendre.py:55-170.
@@ -523,6 +523,9 @@ rb_gl2* rb_gl2_create(rb_solver* s, rb_jacobian* j, const rb_gl2_options* option
             p2.compute_energies = 0;
             g->s2 = rb_create(N, 2, &p2);
             if (!g->s2) throw std::runtime_error(std::string("rb_create (batch 2): ") + rb_last_error());
+            // trial slopes of a diverging Newton iteration can describe surfaces that have no finite RHS: the inner solve then fails,
+            // which the line search must see as "not acceptable" (status below), not as an error of the call
+            check_rc(rb_set_strict(g->s2, 0), "rb_set_strict (stage assembler)");
             check_rc(rb_set_stream(g->s2, rb_get_stream(s)), "rb_set_stream (stage assembler)");
             g->cstate2 = dmalloc<double2>((size_t)4 * N);
             g->crhs2 = dmalloc<double2>((size_t)4 * N);

@@ -70,6 +70,24 @@ __device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst
 }
 #endif
 
+// what the steps of one asynchronously launched chunk of recorded RK4 steps left behind (device memory, folded by the last kernel
+// of every recorded step, read by the host once per chunk instead of once per step)
+struct StepAgg {
+    int steps;             // steps folded in since the host cleared the block
+    int not_done;          // steps in which some stage's solve ran out of recorded sweeps
+    int failed;            // steps in which some stage ended neither converged nor stagnated
+    int stagnated;         // stage solves that ended stagnated (accepted, counted)
+    int max_occupied;      // max over the steps and stages of the sweeps a solve occupied in the recorded sequence
+    int pad;
+    long long sum_iters;   // M*x applications over all solves
+    double worst_rel2;     // largest final ||r||^2/||b||^2
+    double first_rel2[4];  // of the last step: residual of each stage's initial iterate
+    double rel2_last[4];   // of the last step: final residuals
+    int iters_last[4];
+    int conv_last[4];
+    int stag_last[4];
+};
+
 // geometry of the surface, per point; all arrays are [batch][N]
 struct Geometry {
     const double2* Z;      // surface points
@@ -223,6 +241,7 @@ void launch_guess(const double* b, const double* warm, const HistoryRing& hist, 
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st,
                   const double2* Zp = nullptr, const double* Mdiag = nullptr, double cK = 0.0);
 void launch_advance_counter(int* counter, cudaStream_t st);
+void launch_step_end(int* counter, const SolveCtrl* ctrl_all, StepAgg* agg, int opt_mask, cudaStream_t st);
 void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, int final_buf, const double* bnorm_part,
                       int ncell, double tol2, int max_iters, cudaStream_t st);
 // spectral.cu

@@ -399,6 +399,38 @@ void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl
 
 __global__ void advance_counter_kernel(int* counter) { *counter += 1; }
 
+// last kernel of a recorded RK4 step: advance the history counter and fold the four stage solves' control blocks into the chunk
+// aggregate (so that the host can launch several recorded steps back to back and look once)
+__global__ void step_end_kernel(int* counter, const SolveCtrl* __restrict__ ctrl_all, StepAgg* agg, int opt_mask) {
+    if (counter) *counter += 1;
+    if (!agg) return;
+    bool all_done = true, failed = false;
+    for (int i = 0; i < 4; ++i) {
+        const SolveCtrl c = ctrl_all[i];
+        all_done = all_done && c.done;
+        failed = failed || (c.done && !c.converged && !c.stagnated);
+        if (c.stagnated && !c.converged) agg->stagnated += 1;
+        const int occ = c.iters + ((opt_mask >> i) & 1);
+        if (occ > agg->max_occupied) agg->max_occupied = occ;
+        agg->sum_iters += c.iters;
+        if (!(c.rel2 <= agg->worst_rel2)) agg->worst_rel2 = c.rel2;   // NaN sticks
+        agg->first_rel2[i] = c.first_rel2;
+        agg->rel2_last[i] = c.rel2;
+        agg->iters_last[i] = c.iters;
+        agg->conv_last[i] = c.converged;
+        agg->stag_last[i] = c.stagnated;
+    }
+    agg->steps += 1;
+    if (!all_done) agg->not_done += 1;
+    if (failed) agg->failed += 1;
+}
+
+void launch_step_end(int* counter, const SolveCtrl* ctrl_all, StepAgg* agg, int opt_mask, cudaStream_t st) {
+    step_end_kernel<<<1, 1, 0, st>>>(counter, ctrl_all, agg, opt_mask);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 void launch_advance_counter(int* counter, cudaStream_t st) {
     advance_counter_kernel<<<1, 1, 0, st>>>(counter);
     RB_CUDA(cudaGetLastError());

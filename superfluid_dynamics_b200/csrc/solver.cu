@@ -228,13 +228,21 @@ static void choose_chunking(rb_solver* s) {
     // round 1, whole surfaces: N = 65536: 2 rows per thread 3200 (target 1184) / 3108 (2368); 4 rows per thread 3391 / 3011 /
     // 2931 (4736) / 2893 (9472) / 2875 (18944); 8 rows per thread 3556 at best -- the persistent kernel: 3113;
     // N = 32768: 832 / 813 | 912 / 830 / 819; N = 16384: 248 / 234 | 314 / 265 / 235; N = 8192: 80.5 / 74.2 | 102 / 84; N = 4096: 32.8 / 32.9 | 41
+    // round 2, with the two-level reduction (profiles/r02b_shardtune.log), chunks -> us:
+    //   N = 65536: G = 1: 37 / 64 / 74 / 128 -> 2896 / 2873 / 2875 / 2846;  G = 2: 37 / 74 / 128 / 256 -> 1523 / 1483 / 1462 / 1452;
+    //              G = 4: 74 / 148 / 256 / 512 -> 736 / 731 / 728 / 737;    G = 8: 74 / 148 / 256 / 512 -> 386 / 379 / 376 / 381
+    //              (the same 8-GPU shard with the single-level reduction: 148 -> 400, 512 -> 488)
+    //   N = 16384: G = 1: 32 / 64 / 128 -> 241 / 225 / 219, 4 rows per thread 64 / 128 -> 226 / 213;  G = 2: 32 / 64 / 128 -> 144 / 129 / 124;
+    //              G = 4: 64 / 128 / 256 -> 78 / 72 / 73;  G = 8: 64 / 128 / 256 -> 57 / 49 / 47
+    //   N = 4096:  16 / 32 / 64 -> 46 / 37 / 35 (single level at 64: 41)
     const bool big = N >= 49152;
-    s->v1_rows = env_int("RB_V1_ROWS", big ? 4 : 2) == 4 ? 4 : 2;
-    const int target = env_int("RB_TARGET_CTAS", big ? 148 * 128 : (N >= 2048 ? 148 * 16 : 148 * 8));
+    const bool mid = N >= 16384;
+    s->v1_rows = env_int("RB_V1_ROWS", mid ? 4 : 2) == 4 ? 4 : 2;
+    const int target = env_int("RB_TARGET_CTAS", big ? 32768 : (mid ? 148 * 64 : (N >= 2048 ? 148 * 16 : 148 * 8)));
     const long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
     int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);
     // never below `min_srcs` sources per CTA: the fixed cost of a CTA (prologue, partial store, tickets) is ~3 us ~ 16 sources' worth
-    const int min_srcs = env_int("RB_MIN_SRCS", big ? 256 : 64);
+    const int min_srcs = env_int("RB_MIN_SRCS", big ? 256 : (mid ? 128 : 64));
     const int max_chunks = std::max(1, (N + min_srcs - 1) / min_srcs);
     wanted = std::min(wanted, max_chunks);
     wanted = env_int("RB_NCHUNKS", wanted);
@@ -1167,7 +1175,9 @@ static void rhs(rb_solver* s, const double2* state, double2* out) {
 // ------------------------------------------------------------------------------------------------
 // the RK4 stepper
 // ------------------------------------------------------------------------------------------------
-constexpr int kHistRing = 7;   // > max order (6): a repeated step never reads a slot it has already overwritten
+constexpr int kHistRing = 12;  // > max order (6) + the steps of an asynchronously launched chunk: a chunk that is rolled back and
+                               // repeated never reads a slot the failed attempt has overwritten (kChunkMax + order <= kHistRing)
+constexpr int kChunkMax = 6;   // recorded steps launched back to back between two host looks at the solve status
 
 struct rb_stepper {
     rb_solver* s = nullptr;
@@ -1199,6 +1209,12 @@ struct rb_stepper {
     int graph_hits_below = 0;     // consecutive steps that needed far fewer sweeps than captured
     long long graph_launches = 0, graph_captures = 0, fallback_steps = 0;
     cudaEvent_t ev = nullptr;
+    // asynchronous chunks: several recorded steps launched back to back, one host synchronisation per chunk (launch-bound regime)
+    StepAgg* d_agg = nullptr;
+    StepAgg* h_agg = nullptr;     // pinned
+    double2* ycheck = nullptr;    // state at the start of the chunk (rollback)
+    int chunk = 0;                // steps per chunk (0: off)
+    long long chunks_launched = 0, chunks_rolled_back = 0;
     // logging
     size_t log_every = 0, log_capacity = 0, log_count = 0, step_index = 0;
     double2* log_states = nullptr;
@@ -1216,6 +1232,9 @@ static void stepper_free(rb_stepper* st) {
     for (auto p : st->hist)
         if (p) cudaFree(p);
     if (st->d_counter) cudaFree(st->d_counter);
+    if (st->d_agg) cudaFree(st->d_agg);
+    if (st->h_agg) cudaFreeHost(st->h_agg);
+    if (st->ycheck) cudaFree(st->ycheck);
     if (st->log_states) cudaFree(st->log_states);
     delete st;
 }
@@ -1289,7 +1308,9 @@ static void issue_step(rb_stepper* st, int fixed_sweeps) {
         if (!staged(1, st->ytmp, 1, h * 0.5)) launch_stage_update(st->ytmp, st->y0, st->k[1], h * 0.5, n2, cs);
         if (!staged(2, st->ytmp, 1, h)) launch_stage_update(st->ytmp, st->y0, st->k[2], h, n2, cs);
         if (!staged(3, st->ytmp, 2, h / 6.0)) launch_final_update(st->y0, st->k[0], st->k[1], st->k[2], st->k[3], h, n2, cs);
-        if (warm) launch_advance_counter(st->d_counter, cs);
+        // recorded steps end with the kernel that advances the history counter and folds the stage solves' status into the chunk aggregate
+        if (fixed_sweeps > 0) launch_step_end(warm ? st->d_counter : nullptr, s->ctrl_all, st->d_agg, st->opt_mask, cs);
+        else if (warm) launch_advance_counter(st->d_counter, cs);
     } catch (...) {
         // a stage's solve failed (strict mode): y0 has not been touched yet (the final update is the last thing a step does)
         restore();
@@ -1470,6 +1491,99 @@ static void stepper_step(rb_stepper* st) {
     }
     if (s->props.guess_mode == RB_GUESS_WARM) st->h_counter++;
     after_step(st);
+}
+
+// m recorded steps launched back to back, ONE host synchronisation at the end: in the launch-bound regime (N <= 8192: a step is a
+// few hundred microseconds) the host round trip after every step (event wait, status check, next launch) is ~5-10 % of the step.
+// The last kernel of each recorded step folds its four solves' status into a device aggregate; if any step of the chunk ran out of
+// recorded sweeps or failed, the whole chunk is rolled back (state, history counter; the history ring is deep enough that the
+// repeated steps never read a slot the failed attempt overwrote) and the caller redoes it step by step.  Returns false when rolled back.
+static bool stepper_chunk(rb_stepper* st, int m) {
+    rb_solver* s = st->s;
+    cudaStream_t cs = s->stream;
+    const bool warm = s->props.guess_mode == RB_GUESS_WARM;
+    const int mask = st->opt_mask;
+    RB_CUDA(cudaMemcpyAsync(st->ycheck, st->y0, 2 * s->BN * sizeof(double2), cudaMemcpyDeviceToDevice, cs));
+    RB_CUDA(cudaMemsetAsync(st->d_agg, 0, sizeof(StepAgg), cs));
+    for (int j = 0; j < m; ++j) RB_CUDA(cudaGraphLaunch(st->graph_exec, cs));
+    RB_CUDA(cudaMemcpyAsync(st->h_agg, st->d_agg, sizeof(StepAgg), cudaMemcpyDeviceToHost, cs));
+    RB_CUDA(cudaEventRecord(st->ev, cs));
+    RB_CUDA(cudaEventSynchronize(st->ev));
+    rb::count_launch(m * st->graph_kernels[mask & 15]);
+    st->chunks_launched++;
+    const StepAgg& a = *st->h_agg;
+    if (a.steps != m || a.not_done || a.failed) {
+        RB_CUDA(cudaMemcpyAsync(st->y0, st->ycheck, 2 * s->BN * sizeof(double2), cudaMemcpyDeviceToDevice, cs));
+        if (warm) RB_CUDA(cudaMemcpyAsync(st->d_counter, &st->h_counter, sizeof(int), cudaMemcpyHostToDevice, cs));
+        RB_CUDA(cudaStreamSynchronize(cs));
+        st->chunks_rolled_back++;
+        return false;
+    }
+    st->graph_launches += m;
+    s->sum_iters += a.sum_iters;
+    s->num_solves += 4LL * m;
+    s->stagnated_solves += a.stagnated;
+    const double wr = std::sqrt(std::max(0.0, a.worst_rel2));
+    if (wr == wr) s->worst_rel = std::max(s->worst_rel, wr);
+    const double tol2 = s->props.tolerance * s->props.tolerance;
+    int next_mask = 0, it_max = 0, all_conv = 1, any_stag = 0;
+    double rel_max = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        st->first_rel[i] = std::sqrt(std::max(0.0, a.first_rel2[i]));
+        if (a.first_rel2[i] <= 4.0 * tol2) next_mask |= 1 << i;
+        it_max = std::max(it_max, a.iters_last[i]);
+        all_conv = all_conv && a.conv_last[i];
+        any_stag = any_stag || (a.stag_last[i] && !a.conv_last[i]);
+        rel_max = std::max(rel_max, std::sqrt(std::max(0.0, a.rel2_last[i])));
+        if ((mask >> i) & 1) {   // (per-step counts are not kept inside a chunk: the last step stands for all of them)
+            st->opt_stage_solves += m;
+            if (a.iters_last[i] == 1) st->one_sweep_solves += m;
+        }
+    }
+    if (st->opt_policy == 0) next_mask = 0;
+    if (st->opt_policy == 2) next_mask = 15;
+    st->opt_mask = next_mask;
+    s->last_iters = it_max;
+    s->last_converged = all_conv;
+    s->last_stagnated = any_stag;
+    s->last_rel = rel_max;
+    if (st->graph_sweeps - a.max_occupied >= 3) {
+        st->graph_hits_below += m;
+        if (st->graph_hits_below >= 8) {
+            st->graph_sweeps = a.max_occupied + 1;
+            invalidate_graphs(st);
+        }
+    } else {
+        st->graph_hits_below = 0;
+    }
+    if (warm) st->h_counter += m;
+    st->t += m * st->dt;      // (same rounding as m single additions is not required: the time is bookkeeping only)
+    st->step_index += m;
+    return true;
+}
+
+// n steps: asynchronous chunks once the stepper has settled (stage history filled, recorded sweep count tuned), single steps otherwise
+static void stepper_run(rb_stepper* st, size_t n) {
+    rb_solver* s = st->s;
+    size_t i = 0;
+    while (i < n) {
+        const bool graphable = st->use_graph && s->matrix_free_solve && !s->use_gmres;
+        const bool settled = graphable && st->chunk >= 2 && !st->log_every && st->graph_launches >= 8 && st->graph_dt == st->dt &&
+                             st->graph_y0 == st->y0 && st->graph_cache[st->opt_mask & 15] != nullptr && st->graph_hits_below == 0;
+        const int m = (int)std::min<size_t>(st->chunk, n - i);
+        if (settled && m >= 2) {
+            st->graph_exec = st->graph_cache[st->opt_mask & 15];
+            if (stepper_chunk(st, m)) {
+                i += m;
+                continue;
+            }
+            for (int j = 0; j < m; ++j) stepper_step(st);   // rolled back: redo these steps with the per-step checks and fallbacks
+            i += m;
+            continue;
+        }
+        stepper_step(st);
+        ++i;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1726,15 +1840,20 @@ rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
         st->d_counter = dmalloc<int>(1);
         RB_CUDA(cudaMemset(st->d_counter, 0, sizeof(int)));
         RB_CUDA(cudaEventCreateWithFlags(&st->ev, cudaEventDisableTiming));
+        st->d_agg = dmalloc<StepAgg>(1);
+        RB_CUDA(cudaMemset(st->d_agg, 0, sizeof(StepAgg)));
+        RB_CUDA(cudaMallocHost(&st->h_agg, sizeof(StepAgg)));
+        st->ycheck = dmalloc<double2>(n2);
         // extrapolation order of the stage history: 4 points wins where the truncation error of the guess dominates; at large N
         // the round-off noise of the spectral derivatives (~N eps) dominates and the wider stencil amplifies it (measured at
         // N = 65536: 2.00 sweeps per solve with 3 points, 2.10 with 4)
-        st->order = std::max(1, std::min(kHistRing - 1, env_int("RB_GUESS_ORDER", s->N >= 32768 ? 3 : 4)));
+        st->order = std::max(1, std::min(6, env_int("RB_GUESS_ORDER", s->N >= 32768 ? 3 : 4)));
         {
             const int pr = env_int("RB_GUESS_PREDICT", -1);
             st->predict = pr >= 0 ? (pr != 0) : (s->props.tolerance >= 4e-13);
         }
         st->use_graph = env_int("RB_NO_GRAPH", 0) == 0;
+        st->chunk = std::max(0, std::min(kChunkMax, std::min(env_int("RB_ASYNC_STEPS", kChunkMax), kHistRing - st->order)));
         st->opt_policy = std::max(0, std::min(2, env_int("RB_OPTIMISTIC", 1)));
         st->opt_mask = st->opt_policy == 2 ? 15 : 0;
         return up.release();
@@ -1791,7 +1910,7 @@ int rb_rk4_step(rb_stepper* st) {
 int rb_rk4_run_steps(rb_stepper* st, size_t steps) {
     RB_TRY
     if (!st->y0) throw std::runtime_error("rb_rk4_run_steps: initialize() has not been called");
-    for (size_t i = 0; i < steps; ++i) stepper_step(st);
+    stepper_run(st, steps);
     RB_CATCH
 }
 
@@ -1800,7 +1919,7 @@ int rb_rk4_evolve(rb_stepper* st, double t0, double t1, size_t* steps_out) {
     if (!st->y0) throw std::runtime_error("rb_rk4_evolve: initialize() has not been called");
     st->t = t0;
     size_t steps = static_cast<size_t>((t1 - t0) / st->dt);   // truncation, L/AutonomousRungeKuttaStepper.cuh:421
-    for (size_t i = 0; i < steps; ++i) stepper_step(st);
+    stepper_run(st, steps);
     RB_CUDA(cudaStreamSynchronize(st->s->stream));
     if (steps_out) *steps_out = steps;
     RB_CATCH
@@ -1813,6 +1932,13 @@ int rb_rk4_stats(rb_stepper* st, double out_host[4]) {
     out_host[1] = (double)st->graph_captures;
     out_host[2] = (double)st->fallback_steps;
     out_host[3] = (double)st->graph_sweeps;
+    return 0;
+}
+int rb_rk4_chunk_stats(rb_stepper* st, double out_host[4]) {
+    out_host[0] = (double)st->chunk;
+    out_host[1] = (double)st->chunks_launched;
+    out_host[2] = (double)st->chunks_rolled_back;
+    out_host[3] = 0.0;
     return 0;
 }
 int rb_rk4_guess_stats(rb_stepper* st, double out_host[8]) {
@@ -1831,8 +1957,9 @@ int rb_rk4_set_optimistic(rb_stepper* st, int policy) {
 }
 int rb_rk4_set_guess(rb_stepper* st, int order, int predict) {
     RB_TRY
-    if (order < 1 || order >= kHistRing) throw std::runtime_error("rb_rk4_set_guess: order must be in 1..6");
+    if (order < 1 || order > 6) throw std::runtime_error("rb_rk4_set_guess: order must be in 1..6");
     st->order = order;
+    st->chunk = std::max(0, std::min(st->chunk, kHistRing - order));
     st->predict = predict < 0 ? (st->s->props.tolerance >= 4e-13) : (predict != 0);
     stepper_reset_history(st);   // the rings of the two modes hold different iterates
     invalidate_graphs(st);
@@ -2282,7 +2409,7 @@ static void integrate_host(const double* initialState, size_t N, size_t batch, c
         for (size_t r = 0; r < st->log_count; ++r) unpack(all.data() + r * 2 * BN, states.data() + r * 3 * BN);
         times = st->log_times;
     } else {
-        for (size_t i = 0; i < steps; ++i) stepper_step(st.get());
+        stepper_run(st.get(), steps);
         if (rb_rk4_get_state(st.get(), (rb_complex*)host.data()) != 0) throw std::runtime_error(g_last_error);
         states.resize(3 * BN);
         unpack(host.data(), states.data());

@@ -131,6 +131,15 @@ int rb_solve_stats(rb_solver* s, double out[6]) {
     return 0;
 }
 
+int rb_solve_status(rb_solver*, double out[8]) {
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    out[0] = g_force_unconverged ? 0 : 1;
+    out[5] = 1;
+    return 0;
+}
+
+int rb_set_strict(rb_solver*, int) { return 0; }
+
 void rb_free(void* p) { std::free(p); }
 
 // test hooks

@@ -77,14 +77,14 @@ def main():
 
     report = {"lu": {}, "sizes": {}}
     rng = np.random.default_rng(0)
-    for n in (384, 1536, 3072, 6144):
+    for n in (384, 1536, 4096, 6144):
         A = rng.standard_normal((n, n)) + 4.0 * np.eye(n)
         b = rng.standard_normal(n)
         ref = np.linalg.solve(A, b)
         Af = T(np.asfortranarray(A).ravel(order="F"))
         entry = {}
         for name, blocked in (("unblocked", 0), ("blocked_dmma", 1)):
-            if blocked == 0 and n > 3072:
+            if blocked == 0 and n > 4096:
                 continue
             errs = []
 
@@ -97,6 +97,32 @@ def main():
             once()
             entry[name] = {"ms_incl_copies": (time.perf_counter() - t0) * 500.0, "info": errs[-1][0], "rel_err_vs_lapack": errs[-1][1],
                            "gflops": (2.0 / 3.0) * n ** 3 / ((time.perf_counter() - t0) * 0.5) / 1e9}
+        # the routine the reference's MatrixSolver calls (cusolverDnDgetrf + cusolverDnDgetrs, L/MatrixSolver.cuh:123-125), here
+        # through torch.linalg (cuSOLVER backend): library baseline on the same GPU, CUDA events, matrix copy excluded from neither
+        try:
+            torch.backends.cuda.preferred_linalg_library("cusolver")
+            At, bt = T(A), T(b).reshape(n, 1)
+            def cus():
+                LU, piv = torch.linalg.lu_factor(At)
+                return torch.linalg.lu_solve(LU, piv, bt)
+            x = cus()
+            ms = timed(cus, 3)
+            entry["cusolver_getrf_getrs"] = {"ms": ms, "gflops": (2.0 / 3.0) * n ** 3 / (ms * 1e-3) / 1e9,
+                                             "rel_err_vs_lapack": float(np.abs(x.cpu().numpy().ravel() - ref).max() / np.abs(ref).max())}
+        except Exception as e:  # noqa: BLE001
+            entry["cusolver_getrf_getrs"] = {"error": repr(e)[:200]}
+        # the same two factorisations timed with CUDA events (device-to-device copy of A inside: 8 n^2 bytes, ~0.02-0.1 ms)
+        for name, blocked in (("unblocked", 0), ("blocked_dmma", 1)):
+            if name not in entry:
+                continue
+            dA, db = Af.clone(), T(b).clone()
+            def run():
+                dA.copy_(Af)
+                db.copy_(T(b))
+                api.lu_solve(dA, db, n, blocked)
+            ms = timed(run, 2)
+            entry[name]["ms_events"] = ms
+            entry[name]["gflops_events"] = (2.0 / 3.0) * n ** 3 / (ms * 1e-3) / 1e9
         report["lu"][str(n)] = entry
         print("lu", n, entry, flush=True)
         json.dump(report, open(out_path, "w"), indent=1)
