@@ -88,6 +88,23 @@ struct StepAgg {
     int stag_last[4];
 };
 
+// device-driven GMRES cycle (krylov_kernels.cu): per-member least-squares state and the cycle's control block
+constexpr int kGmMax = 16;   // Krylov vectors per recorded cycle
+struct GmMember {
+    double H[(kGmMax + 1) * kGmMax];   // Hessenberg matrix after the rotations (upper triangular part used), H[i * kGmMax + j]
+    double cs[kGmMax], sn[kGmMax];     // Givens rotations
+    double g[kGmMax + 1];              // rotated right-hand side: |g[k]| is the residual norm after k steps
+    double bnorm, rel, first_rel;
+    int k_used;                        // columns this member's correction uses
+    int running;                       // 0: this member's residual estimate met the tolerance (or broke down)
+};
+struct GmCtrl {
+    int done;                          // 1: the cycle has ended (every member finished, or the recorded iterations are used up)
+    int k;                             // Arnoldi steps performed in this cycle
+    int running;                       // scratch: members still running, counted during a kernel
+    unsigned int ticket;               // scratch: member-level ticket
+};
+
 // geometry of the surface, per point; all arrays are [batch][N]
 struct Geometry {
     const double2* Z;      // surface points
@@ -273,6 +290,11 @@ void launch_axpby(double* out, const double* a, double alpha, const double* b, i
 void launch_precond_scale(double2* hat, const double* invP, int N, int n, cudaStream_t st);
 void launch_real_to_complex(const double* x, double2* out, int n, cudaStream_t st);
 void launch_complex_to_real(const double2* c, double* out, double scale, int n, cudaStream_t st);
+void launch_gm_start(const double* b, const double* w, double* V0, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch,
+                     double tol, cudaStream_t st);
+void launch_gm_arnoldi(double* V, size_t ldv, double* w, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch, int k,
+                       int last_k, double tol, cudaStream_t st);
+void launch_gm_correction(const double* V, size_t ldv, double* t, GmMember* members, int N, int batch, cudaStream_t st);
 // dense_kernels.cu
 void launch_create_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double rho, int n, size_t batch,
                      cudaStream_t st);

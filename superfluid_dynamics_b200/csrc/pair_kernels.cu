@@ -875,7 +875,9 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
     // decide == 1: the sweep before was launched with skip_if_done and has skipped itself (no signal was sent): nothing to wait
     // for.  decide == 2: that sweep always runs and signals (rb_bench_sweep), so its epoch must always be consumed -- returning
     // here would leave the peers' flags ahead of wait_epoch and let every later wait pass on stale flags.
-    if (decide == 1 && *reinterpret_cast<volatile int*>(&ctrl->done)) return;
+    // decide == 3: as 1 (the sweep before skipped itself when ctrl->done), but nothing to decide after the wait (operator application
+    // of the recorded GMRES cycle)
+    if ((decide == 1 || decide == 3) && *reinterpret_cast<volatile int*>(&ctrl->done)) return;
     const unsigned long long expected = *c.wait_epoch + 1ull;
     bool timed_out = false;
     if (lane < c.nranks) {
@@ -901,7 +903,7 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
         }
         return;
     }
-    if (!decide) return;
+    if (!decide || decide == 3) return;
     // ||b||^2 over all cells: lanes stride, then a fixed-order combine
     double bl = 0.0;
     for (int i = lane; i < ncell; i += 32) bl += __ldcg(bnorm_part + i);

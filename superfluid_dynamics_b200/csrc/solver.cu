@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -132,6 +133,10 @@ struct rb_solver {
     int gm_m = 0;                  // restart length
     double *gm_V = nullptr, *gm_x = nullptr, *gm_t = nullptr, *gm_dev = nullptr, *gm_invP = nullptr;
     double* gm_host = nullptr;     // pinned
+    // the same solver driven from the device inside recorded RK4 steps (krylov_kernels.cu: gm_*_kernel)
+    bool gm_device = false;
+    GmMember* gm_members = nullptr;
+    GmCtrl* gm_ctrl = nullptr;     // viewed as a SolveCtrl by the sweeps that skip themselves once the cycle has ended (first member: done)
     double* Mdense = nullptr;      // dense validation path, allocated on demand
     int* lu_info = nullptr;
     double2* scratch_state = nullptr;   // legacy host-vector exports
@@ -192,7 +197,7 @@ static void solver_free(rb_solver* s) {
                     s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->gpartial, s->gpartial_img, s->group_tickets, s->cell_tickets,
                     s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state, s->gm_V, s->gm_x, s->gm_t,
-                    s->gm_dev, s->gm_invP, s->v2_rnorm_part, s->v2_ticket, s->fft_tw, s->v2_partial, s->v2_xs_part,
+                    s->gm_dev, s->gm_invP, s->gm_members, s->gm_ctrl, s->v2_rnorm_part, s->v2_ticket, s->fft_tw, s->v2_partial, s->v2_xs_part,
                     s->v2_blk_tickets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -538,6 +543,13 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
             std::fill(invP.begin(), invP.end(), 1.0);
         }
         RB_CUDA(cudaMemcpy(s->gm_invP, invP.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        s->gm_device = env_int("RB_DEVICE_GMRES", 1) != 0;
+        s->gm_members = dmalloc<GmMember>(batch);
+        RB_CUDA(cudaMemset(s->gm_members, 0, (size_t)batch * sizeof(GmMember)));
+        static_assert(sizeof(SolveCtrl) >= sizeof(GmCtrl) && offsetof(SolveCtrl, done) == offsetof(GmCtrl, done),
+                      "the sweeps read GmCtrl::done through a SolveCtrl pointer");
+        s->gm_ctrl = reinterpret_cast<GmCtrl*>(dmalloc<SolveCtrl>(1));
+        RB_CUDA(cudaMemset(s->gm_ctrl, 0, sizeof(SolveCtrl)));
     }
 
     int n[1] = {N};
@@ -779,7 +791,8 @@ static void account_solve(rb_solver* s) {
 
 // ---- restarted GMRES(m), right-preconditioned, classical Gram-Schmidt with re-orthogonalisation -------------------------
 // y = M x for the rows of this rank (published to every rank when sharded); x: any device vector, result in xbuf[1]
-static void apply_M(rb_solver* s, const SweepArgs& base, const double* x) {
+// skip != nullptr: the sweep (and, row-sharded, the wait behind it) returns at once when skip->done is set (recorded GMRES cycle)
+static void apply_M(rb_solver* s, const SweepArgs& base, const double* x, SolveCtrl* skip = nullptr) {
     cudaStream_t st = s->stream;
     launch_finish_solve(x, x, nullptr, nullptr, nullptr, s->xsum_part[0], HistoryRing(), s->N, s->batch, s->ncell, st);
     SweepArgs a = base;
@@ -788,10 +801,12 @@ static void apply_M(rb_solver* s, const SweepArgs& base, const double* x) {
     a.xsum_part = s->xsum_part[0];
     a.xsum_part_out = s->xsum_part[1];
     a.apply_only = 1;
-    a.skip_if_done = 0;
+    a.skip_if_done = skip ? 1 : 0;
+    if (skip) a.ctrl = skip;
     a.out_buf = 1;
     sweep(s, a, kSweepMV);
-    if (s->comm.nranks > 1) launch_comm_wait(s->comm, s->ctrl, 0, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
+    if (s->comm.nranks > 1)
+        launch_comm_wait(s->comm, skip ? skip : s->ctrl, skip ? 3 : 0, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
 }
 
 // out = P^{-1} v  (FFT, divide by the flat-film symbol, inverse FFT); out may alias v
@@ -1146,9 +1161,73 @@ static void rhs_combined(rb_solver* s, const double2* state, double2* out) {
     rhs_tail(s, state, out, user_out);
 }
 
+// RHS of the finite-depth helium operator inside a recorded step: one GMRES cycle of at most K = fixed_sweeps - 2 Arnoldi steps,
+// driven entirely from the device (no host synchronisation), then the velocity sweep in combined mode, which also VERIFIES the
+// solution with the true residual b - M a from the same row sums (the cycle itself stops on the Arnoldi estimate at half the
+// tolerance).  A solve that does not verify leaves its control block "not done": the stepper rolls the step back and redoes it with
+// the host-driven restarted GMRES of gmres_solve.  Sequence per RHS: r0 = b - M x0 | K x [P^-1 v_k, M (.), arnoldi] | x += P^-1 V y |
+// a' | combined velocity sweep.
+static void rhs_gmres_recorded(rb_solver* s, const double2* state, double2* out) {
+    const size_t BN = s->BN;
+    cudaStream_t st = s->stream;
+    const double2* Z = state;
+    const double2* Phi = state + BN;
+    const int n = (int)BN;
+    s->cur_Z = Z;
+    s->cur_Phi = Phi;
+    double2* user_out = nullptr;
+    out = redirect_out(s, out, &user_out);
+    surface_stage(s, Z, Phi);
+    const double* warm = nullptr;
+    if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
+    launch_guess(s->b, warm, s->hist, s->gm_x, s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
+    if (!warm && !s->hist.base) apply_Pinv(s, s->b, s->gm_x);   // cold start: x0 = P^{-1} b
+    SweepArgs base = base_args(s, Z);
+    double* w = s->xbuf[1];
+    SolveCtrl* skip = reinterpret_cast<SolveCtrl*>(s->gm_ctrl);
+    const double tol_in = 0.5 * s->props.tolerance;
+    const int K = std::max(1, std::min(std::min(kGmMax, s->gm_m), s->fixed_sweeps - 2));
+    apply_M(s, base, s->gm_x);                                                      // w = M x0
+    launch_gm_start(s->b, w, s->gm_V, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, tol_in, st);
+    for (int k = 0; k < K; ++k) {
+        apply_Pinv(s, s->gm_V + (size_t)k * BN, s->gm_t);
+        apply_M(s, base, s->gm_t, skip);                                            // w = M P^{-1} v_k
+        launch_gm_arnoldi(s->gm_V, BN, w, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, k, K - 1, tol_in, st);
+    }
+    launch_gm_correction(s->gm_V, BN, s->gm_t, s->gm_members, s->N, s->batch, st);
+    apply_Pinv(s, s->gm_t, s->gm_t);
+    launch_axpby(s->gm_x, s->gm_x, 1.0, s->gm_t, n, st);
+    launch_finish_solve(s->gm_x, s->gm_x, nullptr, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
+    s->have_prev_a = true;
+    real_derivative(s, s->a, s->aprime);
+    SweepArgs a = base;
+    a.x = s->a;
+    a.x_out = s->xbuf[1];                 // (the next Richardson iterate the combined mode also forms: not used here)
+    a.xsum_part = s->xsum_a;
+    a.xsum_part_out = s->xsum_part[1];
+    a.out_buf = 1;
+    a.final_buf_on_done = 0;
+    a.combined = 1;
+    a.skip_if_done = 0;
+    a.max_iters = 1 << 30;                // not verified -> the block stays "not done" -> the stepper's fallback, never a silent accept
+    a.aprime = s->aprime;
+    a.vel_lower = out;
+    a.vel_upper = s->vel_upper;
+    a.rhs_phi_kind = s->rhs_phi_kind;
+    a.dphi = s->rhs_phi_kind ? out + BN : nullptr;
+    sweep(s, a, kSweepVEL);
+    if (s->comm.nranks > 1)
+        launch_comm_wait(s->comm, s->ctrl, 1, a.out_buf, a.final_buf_on_done, s->bnorm_part, s->ncell, a.tol2, a.max_iters, st);
+    rhs_tail(s, state, out, user_out);
+}
+
 static void rhs(rb_solver* s, const double2* state, double2* out) {
     if (s->fixed_sweeps >= 2 && s->matrix_free_solve && !s->use_gmres && s->combined_ok) {
         rhs_combined(s, state, out);
+        return;
+    }
+    if (s->fixed_sweeps >= 3 && s->matrix_free_solve && s->use_gmres && s->gm_device) {
+        rhs_gmres_recorded(s, state, out);
         return;
     }
     const size_t BN = s->BN;
@@ -1382,7 +1461,7 @@ static void invalidate_graphs(rb_stepper* st) {
 
 static void stepper_step(rb_stepper* st) {
     rb_solver* s = st->s;
-    const bool graphable = st->use_graph && s->matrix_free_solve && !s->use_gmres;   // GMRES is host-driven
+    const bool graphable = st->use_graph && s->matrix_free_solve && (!s->use_gmres || s->gm_device);   // host-driven GMRES cannot be recorded
     if (!graphable) {
         issue_step(st, 0);   // every stage's solve synchronises and is checked where it ends (note_solve_end)
         if (s->props.guess_mode == RB_GUESS_WARM && s->matrix_free_solve) st->h_counter++;
@@ -1393,7 +1472,7 @@ static void stepper_step(rb_stepper* st) {
     st->graph_exec = st->graph_cache[st->opt_mask & 15];
     if (!st->graph_exec) {
         int sweeps = st->graph_sweeps > 0 ? st->graph_sweeps : std::min(s->props.max_iterations, 16);
-        sweeps = std::max(sweeps, 2);
+        sweeps = std::max(sweeps, s->use_gmres ? 3 : 2);
         capture_graph(st, sweeps);
     }
     const int mask = st->opt_mask;
@@ -1567,7 +1646,7 @@ static void stepper_run(rb_stepper* st, size_t n) {
     rb_solver* s = st->s;
     size_t i = 0;
     while (i < n) {
-        const bool graphable = st->use_graph && s->matrix_free_solve && !s->use_gmres;
+        const bool graphable = st->use_graph && s->matrix_free_solve && (!s->use_gmres || s->gm_device);
         const bool settled = graphable && st->chunk >= 2 && !st->log_every && st->graph_launches >= 8 && st->graph_dt == st->dt &&
                              st->graph_y0 == st->y0 && st->graph_cache[st->opt_mask & 15] != nullptr && st->graph_hits_below == 0;
         const int m = (int)std::min<size_t>(st->chunk, n - i);
@@ -1853,7 +1932,9 @@ rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
             st->predict = pr >= 0 ? (pr != 0) : (s->props.tolerance >= 4e-13);
         }
         st->use_graph = env_int("RB_NO_GRAPH", 0) == 0;
-        st->chunk = std::max(0, std::min(kChunkMax, std::min(env_int("RB_ASYNC_STEPS", kChunkMax), kHistRing - st->order)));
+        // measured on a B200 (profiles/r02c_async_chunks.log): 4135 vs 4086 steps/s at N = 1024, 2451 vs 2514 at N = 4096, 430 vs 433 at
+        // N = 16384 -- the per-step host round trip is already hidden behind the recorded step, so the chunks are OFF unless asked for
+        st->chunk = std::max(0, std::min(kChunkMax, std::min(env_int("RB_ASYNC_STEPS", 0), kHistRing - st->order)));
         st->opt_policy = std::max(0, std::min(2, env_int("RB_OPTIMISTIC", 1)));
         st->opt_mask = st->opt_policy == 2 ? 15 : 0;
         return up.release();

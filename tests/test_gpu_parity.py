@@ -206,7 +206,7 @@ def _spot_rows(N):
 
 @pytest.mark.parametrize("N,h,physics", [(65536, 0.4, "water"), (49152, 0.3, "water"), (16384, 0.4, "water")])
 def test_full_rhs_rows_at_the_headline_size_match_direct_evaluation(api, N, h, physics):
-    """The kernels the headline times (tiled sweep, 4 rows per thread at N >= 49152: MV epilogue of the solve, VEL epilogue of the
+    """The kernels the headline times (tiled sweep, 4 rows per thread at N >= 16384: MV epilogue of the solve, VEL epilogue of the
     velocities and dPhi/dt) against an independent formula AT the metric's own size, where no dense oracle fits: after rb_rhs, on
     >= 32 scattered rows k,
       (1) the solve: | b_k - (M a)_k | / max|b| <= 1e-11, with (M a)_k = Mdiag_k a_k + (1/4pi) Im(Zp_k S_k) (L/createM.cuh:43-63),
@@ -221,7 +221,7 @@ def test_full_rhs_rows_at_the_headline_size_match_direct_evaluation(api, N, h, p
     props = api.ProblemProperties(rho=0.0)
     calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
     plan = calc.sweepPlan()
-    assert plan["kernel"] == "tiled" and plan["rows_per_thread"] == (4 if N >= 49152 else 2), plan
+    assert plan["kernel"] == "tiled" and plan["rows_per_thread"] == 4, plan    # the kernel the headline times
     out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
     calc.run(T(ro.pack_state(Z, Phi)), out)
     st = calc.solve_stats()
