@@ -275,11 +275,13 @@ void launch_lu_solve_unblocked(double* A, double* b, int n, int* info, cudaStrea
     count_launch(2 * n);
 }
 
-// the blocked factorisation (lu_kernels.cu) is selected only on request until it has passed its tests on hardware
+// the blocked factorisation (lu_kernels.cu: panels of 32 columns, FP64 tensor-core trailing update) is the default from n = 64 up:
+// measured faster than the two-launches-per-column factorisation above at every size tried (n = 384 ... 4096, see lu_kernels.cu);
+// RB_LU_BLOCKED=0 selects the unblocked one
 void launch_lu_solve(double* A, double* b, int n, int* info, cudaStream_t st) {
     static const bool blocked = [] {
         const char* v = std::getenv("RB_LU_BLOCKED");
-        return v && std::atoi(v) != 0;
+        return !v || std::atoi(v) != 0;
     }();
     if (blocked && n >= 64) launch_lu_solve_blocked(A, b, n, info, st);
     else launch_lu_solve_unblocked(A, b, n, info, st);

@@ -14,13 +14,17 @@
 //   lu_gemm_kernel       A22 -= L21 U12: 64 x 64 tiles, 8 warps, 2 x 4 DMMA tiles of 8 x 8 per warp, 8 k-steps of 4
 //   lu_gemv_kernel       b2  -= L21 b1
 // then lu_backsolve_blocked_kernel: the back substitution with U, one CTA, 32 columns per pair of barriers.
-// STATUS: written after round 1's GPU minutes were spent; selected only when asked for (RB_LU_BLOCKED=1 or
-// rb_lu_solve(..., blocked = 1)) until it has passed tests/test_zz_gpu_implicit.py on hardware.
+// Measured on a B200 (profiles/r02c_implicit_report_before_cluster_panel.json, CUDA events, ms; unblocked / blocked with the one-CTA
+// panel / cuSOLVER getrf+getrs): n = 384: 4.2 / 3.3 / 0.98; 1536: 25.4 / 17.3 / 4.4; 4096: 166 / 67 / 18.0; 6144: - / 165 / 32.3 --
+// the blocked factorisation is the default (dense_kernels.cu: launch_lu_solve), and almost all of its time was the one-CTA panel,
+// which the cluster panel below (lu_panel_cluster_kernel) replaces for panels of >= 256 rows.
 // The kernels and the launch sequence below also compile under g++ with tests/cpp/cuda_emu.h standing in for the CUDA headers
 // (RB_EMULATE): the CPU test tier runs them thread for thread against LAPACK (tests/test_kernel_emulation.py).
 #ifdef RB_EMULATE
 #include "cuda_emu.h"
 #else
+#include <cooperative_groups.h>
+
 #include "internal.cuh"
 #endif
 #include "launch.cuh"
@@ -95,6 +99,176 @@ __global__ void __launch_bounds__(kPanelThreads) lu_panel_kernel(double* A, int 
         __syncthreads();
     }
 }
+
+#ifndef RB_EMULATE
+// ---- the panel on a thread-block cluster (sm_100a): the n x 32 panel lives in the DISTRIBUTED shared memory of 8 (or 16) CTAs ----
+// The one-CTA panel above streams the panel through one SM's path to L2 for every column (n = 4096: ~0.5 ms per panel, 64 of the
+// 67 ms of a factorisation).  Here CTA c of the cluster keeps rows [c * rpc, (c + 1) * rpc) of the panel in its shared memory for the
+// whole panel; per column the CTAs exchange ONE pivot candidate each through distributed shared memory and meet at ONE cluster
+// barrier:
+//   * rows are never moved: the row chosen as the pivot of column j is RETIRED where it lies (no CTA writes it again), everybody
+//     reads its 32 entries from the owner's shared memory, and the interchanges LAPACK would have made are replayed on index maps
+//     (pos / loc below) -- the panel is written back to global memory in its final row order, and piv[] holds position-based
+//     pivots exactly as the one-CTA kernel leaves them (the swap + TRSM kernel applies them to the columns right of the panel);
+//   * the candidates are double-buffered by column parity, so a fast CTA can publish column j + 1 while a slow one still reads j;
+//   * the rank-1 update of column j also finds the pivot candidate of column j + 1 (one pass over the rows per column).
+// Pivot choice: largest |a|, ties to the lowest CURRENT POSITION, as getrf / the other two kernels do.
+constexpr int kClusterPanelThreads = 256;
+
+struct PivotCand {
+    double val;
+    int row;       // physical row (global index) of the candidate
+    int pos;       // its current position (global row index after the interchanges so far)
+};
+
+template <int CS>
+__global__ void __launch_bounds__(kClusterPanelThreads) lu_panel_cluster_kernel(double* __restrict__ A, int n, int k0, int kb, int rpc,
+                                                                                 int* __restrict__ piv, int* __restrict__ info) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: panel P[kNB][rpc] | slot[rpc] (int: -1 active, j retired as pivot of column j) | cand[2] | s_row[kNB] | wcand[8]
+    double* P = reinterpret_cast<double*>(smem_raw);
+    int* slot = reinterpret_cast<int*>(P + (size_t)kNB * rpc);
+    PivotCand* cand = reinterpret_cast<PivotCand*>(slot + rpc);           // [2]
+    double* s_row = reinterpret_cast<double*>(cand + 2);                   // [kNB]
+    PivotCand* wcand = reinterpret_cast<PivotCand*>(s_row + kNB);         // [warps]
+    __shared__ int pos_top[kNB];      // physical row at position k0 + i
+    __shared__ int loc_top[kNB];      // position of physical row k0 + i
+    __shared__ int s_p[2];            // winner of the column: physical row, its position
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster.block_rank();
+    const int row0 = k0 + rank * rpc;                        // first physical row of this CTA
+    const int nloc = max(0, min(rpc, n - row0));             // rows held here
+    for (int idx = tid; idx < kb * rpc; idx += kClusterPanelThreads) {
+        const int c = idx / rpc, r = idx - c * rpc;
+        P[idx] = r < nloc ? A[(size_t)(k0 + c) * n + row0 + r] : 0.0;
+    }
+    for (int r = tid; r < rpc; r += kClusterPanelThreads) slot[r] = -1;
+    if (tid < kNB) {
+        pos_top[tid] = k0 + tid;
+        loc_top[tid] = k0 + tid;
+    }
+    __syncthreads();
+    // candidate of column 0
+    PivotCand mine;
+    mine.val = -1.0; mine.row = -1; mine.pos = 0x7fffffff;
+    for (int r = tid; r < nloc; r += kClusterPanelThreads) {
+        const double v = fabs(P[r]);
+        if (v > mine.val) { mine.val = v; mine.row = row0 + r; mine.pos = row0 + r; }   // (positions = rows before any interchange;
+    }                                                                                    //  the strided scan visits them in order)
+
+    for (int j = 0; j < kb; ++j) {
+        const int buf = j & 1;
+        // ---- this CTA's candidate: warp shuffles, then warp 0 over the warps ----
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, mine.val, o);
+            const int orow = __shfl_down_sync(0xffffffffu, mine.row, o);
+            const int opos = __shfl_down_sync(0xffffffffu, mine.pos, o);
+            if (ov > mine.val || (ov == mine.val && opos < mine.pos)) { mine.val = ov; mine.row = orow; mine.pos = opos; }
+        }
+        if (lane == 0) wcand[warp] = mine;
+        __syncthreads();
+        if (warp == 0) {
+            PivotCand c = lane < kClusterPanelThreads / 32 ? wcand[lane] : PivotCand{-1.0, -1, 0x7fffffff};
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, c.val, o);
+                const int orow = __shfl_down_sync(0xffffffffu, c.row, o);
+                const int opos = __shfl_down_sync(0xffffffffu, c.pos, o);
+                if (ov > c.val || (ov == c.val && opos < c.pos)) { c.val = ov; c.row = orow; c.pos = opos; }
+            }
+            if (lane == 0) cand[buf] = c;
+        }
+        cluster.sync();   // every CTA's candidate of column j is published (release / acquire over the cluster)
+        // ---- the winner, identically on every CTA ----
+        if (warp == 0) {
+            PivotCand c{-1.0, -1, 0x7fffffff};
+            if (lane < CS) c = *cluster.map_shared_rank(&cand[buf], lane);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, c.val, o);
+                const int orow = __shfl_down_sync(0xffffffffu, c.row, o);
+                const int opos = __shfl_down_sync(0xffffffffu, c.pos, o);
+                if (ov > c.val || (ov == c.val && opos < c.pos)) { c.val = ov; c.row = orow; c.pos = opos; }
+            }
+            c.val = __shfl_sync(0xffffffffu, c.val, 0);
+            c.row = __shfl_sync(0xffffffffu, c.row, 0);
+            c.pos = __shfl_sync(0xffffffffu, c.pos, 0);
+            const bool usable = c.val > 0.0;
+            int q = c.row, qpos = c.pos;
+            if (!usable) {   // zero (or NaN) column: singular as getrf reports it; "pivot" = the row at the diagonal position, no elimination
+                q = pos_top[j];
+                qpos = k0 + j;
+            }
+            // the pivot row's panel entries, from its owner's shared memory
+            const int owner = (q - k0) / rpc, ql = (q - k0) - owner * rpc;
+            const double* Pown = cluster.map_shared_rank(P, owner);
+            if (lane < kb) s_row[lane] = Pown[(size_t)lane * rpc + ql];
+            if (lane == 0) {
+                s_p[0] = q;
+                s_p[1] = usable ? 1 : 0;
+                // replay of the interchange (positions k0 + j <-> qpos) on the index maps
+                const int u = pos_top[j];                       // physical row now at the diagonal position (a top-origin row)
+                if (qpos - k0 < kb) pos_top[qpos - k0] = u;
+                loc_top[u - k0] = qpos;
+                if (q - k0 < kb) loc_top[q - k0] = k0 + j;
+                pos_top[j] = q;
+                if (rank == 0) {
+                    piv[k0 + j] = qpos;
+                    if (!usable && *info == 0) *info = k0 + j + 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int q = s_p[0];
+        const bool usable = s_p[1] != 0;
+        if (tid == 0 && q >= row0 && q < row0 + nloc) slot[q - row0] = j;   // retired: nobody writes this row again
+        __syncthreads();
+        // ---- rank-1 update of the active rows; candidate of column j + 1 on the way ----
+        mine.val = -1.0; mine.row = -1; mine.pos = 0x7fffffff;
+        if (usable) {
+            const double pv = s_row[j];
+            double* Pj = P + (size_t)j * rpc;
+            for (int r = tid; r < nloc; r += kClusterPanelThreads) {
+                if (slot[r] >= 0) continue;
+                const double l = Pj[r] / pv;
+                Pj[r] = l;
+                for (int c = j + 1; c < kb; ++c) P[(size_t)c * rpc + r] = fma(-l, s_row[c], P[(size_t)c * rpc + r]);
+                if (j + 1 < kb) {
+                    const double v = fabs(P[(size_t)(j + 1) * rpc + r]);
+                    const int phys = row0 + r;
+                    const int ps = (phys - k0 < kb) ? loc_top[phys - k0] : phys;
+                    if (v > mine.val || (v == mine.val && ps < mine.pos)) { mine.val = v; mine.row = phys; mine.pos = ps; }
+                }
+            }
+        } else if (j + 1 < kb) {
+            for (int r = tid; r < nloc; r += kClusterPanelThreads) {
+                if (slot[r] >= 0) continue;
+                const double v = fabs(P[(size_t)(j + 1) * rpc + r]);
+                const int phys = row0 + r;
+                const int ps = (phys - k0 < kb) ? loc_top[phys - k0] : phys;
+                if (v > mine.val || (v == mine.val && ps < mine.pos)) { mine.val = v; mine.row = phys; mine.pos = ps; }
+            }
+        }
+        // (no barrier here: the next column's reduction starts with __syncthreads after the warp candidates, and the candidate
+        //  buffers alternate; s_row / s_p are rewritten only after the next cluster barrier, which every thread of every CTA passes
+        //  after finishing this loop)
+    }
+    cluster.sync();   // nobody reads a peer's panel any more
+    // ---- write the panel back in its final row order ----
+    for (int idx = tid; idx < kb * rpc; idx += kClusterPanelThreads) {
+        const int c = idx / rpc, r = idx - c * rpc;
+        if (r >= nloc) continue;
+        const int phys = row0 + r;
+        const int sj = slot[r];
+        const int where = sj >= 0 ? k0 + sj : ((phys - k0 < kb) ? loc_top[phys - k0] : phys);
+        A[(size_t)(k0 + c) * n + where] = P[idx];
+    }
+}
+#endif   // RB_EMULATE
 
 // column c of the augmented matrix [A | b]: c == n addresses b
 __device__ __forceinline__ double* aug_column(double* A, double* b, int n, int c) { return c < n ? A + (size_t)c * n : b; }
@@ -246,6 +420,66 @@ __global__ void __launch_bounds__(kBackThreads) lu_backsolve_blocked_kernel(cons
 
 }  // namespace
 
+#ifndef RB_EMULATE
+namespace {
+
+size_t cluster_panel_smem(int rpc) {
+    return (size_t)kNB * rpc * sizeof(double) + (size_t)rpc * sizeof(int) + 2 * sizeof(PivotCand) + kNB * sizeof(double) +
+           (kClusterPanelThreads / 32) * sizeof(PivotCand) + 64;
+}
+
+// 0: not usable (too many rows for the cluster's shared memory, or the launch was refused), else the cluster size used
+template <int CS>
+bool try_cluster_panel(double* A, int n, int k0, int kb, int* piv, int* info, cudaStream_t st) {
+    static int state = 0;   // 0 untried, 1 configured, -1 refused by the device
+    if (state < 0) return false;
+    const int m = n - k0;
+    const int rpc = std::max(32, ((m + CS - 1) / CS + 31) / 32 * 32);
+    const size_t smem = cluster_panel_smem(rpc);
+    if (smem > 227 * 1024) return false;
+    auto kern = lu_panel_cluster_kernel<CS>;
+    if (state == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess && CS > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            state = -1;
+            return false;
+        }
+        state = 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS);
+    cfg.blockDim = dim3(kClusterPanelThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, A, n, k0, kb, rpc, piv, info);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        state = -1;   // e.g. a device partition that cannot co-schedule this cluster size: use the one-CTA panel from now on
+        return false;
+    }
+    return true;
+}
+
+bool cluster_panels_enabled() {
+    static const bool on = [] {
+        const char* v = std::getenv("RB_LU_CLUSTER_PANEL");
+        return !v || std::atoi(v) != 0;
+    }();
+    return on;
+}
+
+}  // namespace
+#endif
+
 // the factorisation with b eliminated on the fly: on return A holds U in its upper triangle and b holds L^{-1} P b
 void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) {
     int* piv = nullptr;   // pivot rows, stream-ordered allocation: no synchronisation, no state shared between streams
@@ -254,7 +488,15 @@ void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) 
     int launches = 0;
     for (int k0 = 0; k0 < n; k0 += kNB) {
         const int kb = std::min(kNB, n - k0);
-        RB_LAUNCH(lu_panel_kernel, 1, kPanelThreads, st, A, n, k0, kb, piv, info);
+        bool done = false;
+#ifndef RB_EMULATE
+        // the panel in the distributed shared memory of a cluster of 8 CTAs (16 when the panel is too tall for 8), else one CTA
+        if (cluster_panels_enabled() && n - k0 >= 256) {
+            done = try_cluster_panel<8>(A, n, k0, kb, piv, info, st);
+            if (!done) done = try_cluster_panel<16>(A, n, k0, kb, piv, info, st);
+        }
+#endif
+        if (!done) RB_LAUNCH(lu_panel_kernel, 1, kPanelThreads, st, A, n, k0, kb, piv, info);
         const int right = n - k0 - kb + 1;   // columns right of the panel, b included
         RB_LAUNCH(lu_swap_trsm_kernel, (right + 127) / 128, 128, st, A, b, n, k0, kb, (const int*)piv);
         launches += 2;

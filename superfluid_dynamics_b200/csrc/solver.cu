@@ -242,7 +242,8 @@ static void choose_chunking(rb_solver* s) {
     //   N = 4096:  16 / 32 / 64 -> 46 / 37 / 35 (single level at 64: 41)
     const bool big = N >= 49152;
     const bool mid = N >= 16384;
-    s->v1_rows = env_int("RB_V1_ROWS", mid ? 4 : 2) == 4 ? 4 : 2;
+    // (with the image sum 4 rows per thread spill at 128 registers: helium N = 16384 sweep 416 us against 404 with 2 rows)
+    s->v1_rows = env_int("RB_V1_ROWS", (big || (mid && !s->has_image)) ? 4 : 2) == 4 ? 4 : 2;
     const int target = env_int("RB_TARGET_CTAS", big ? 32768 : (mid ? 148 * 64 : (N >= 2048 ? 148 * 16 : 148 * 8)));
     const long rows = (long)(s->row_cells > 0 ? s->row_cells : s->ncell) * s->batch;
     int wanted = (int)std::max<long>(1, (target + rows - 1) / rows);

@@ -134,7 +134,45 @@ def steprates():
         print(f"steprate N={N}: {steps / (a.elapsed_time(b) * 1e-3):.1f} steps/s {stp.stats()} {c.solve_stats()} {c.sweepPlan()}", flush=True)
 
 
-SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates)
+def helium():
+    """Helium film (finite depth, image term): recorded steps with the device-driven GMRES cycle against the host-driven solver."""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    depth = 0.0942478
+    for N, steps in ((1024, 100), (4096, 60), (16384, 20)):
+        al = 2 * np.pi * np.arange(N) / N
+        y0 = ro.pack_state(al + 1j * 0.1 * depth * np.cos(al), np.zeros(N))
+        finals = {}
+        for dg in (0, 1):
+            def run():
+                props = api.ProblemProperties(rho=0.0, depth=depth)
+                c = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumBoundaryProblem(props), device=dev, guess="warm")
+                stp = api.AutonomousRungeKuttaStepper(c, 1e-3)
+                y = T(y0)
+                stp.initialize(y, True)
+                stp.runSteps(12)
+                torch.cuda.synchronize()
+                it0 = c.solve_stats()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                stp.runSteps(steps)
+                b.record()
+                torch.cuda.synchronize()
+                it1 = c.solve_stats()
+                ms, pairs = c.benchSweep(T(y0), 20)
+                return (steps / (a.elapsed_time(b) * 1e-3), (it1["total_iterations"] - it0["total_iterations"]) / steps, stp.stats(), it1,
+                        y.cpu().numpy(), ms)
+            try:
+                rate, spp, ss, cs, yf, ms = with_env({"RB_DEVICE_GMRES": dg}, run)
+                finals[dg] = yf
+                print(f"helium N={N} device_gmres={dg}: {rate:.1f} steps/s, {spp:.2f} sweeps/step, sweep {ms * 1e3:.1f} us, {ss} {cs}", flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(f"helium N={N} device_gmres={dg}: FAILED {e}", flush=True)
+        if len(finals) == 2:
+            d = np.abs(finals[0] - finals[1]).max() / np.abs(finals[0]).max()
+            print(f"helium N={N}: device-driven vs host-driven final state rel diff {d:.2e}", flush=True)
+
+
+SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, helium=helium)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)

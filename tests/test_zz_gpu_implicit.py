@@ -246,15 +246,33 @@ def test_lu_solve_against_lapack(api, n, blocked):
     assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("n", [4100, 7000])
+def test_blocked_lu_with_cluster_panels_at_large_n(api, n):
+    """The panel in the distributed shared memory of a thread-block cluster (lu_panel_cluster_kernel): 8 CTAs up to ~6600 rows, 16
+    above (n = 7000), odd sizes, pivoting in every column; against LAPACK as above."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    x_true = rng.standard_normal(n)
+    b = A @ x_true
+    dA = T(np.asfortranarray(A).ravel(order="F")).clone()
+    db = T(b).clone()
+    assert api.lu_solve(dA, db, n, 1) == 0
+    x = db.cpu().numpy()
+    back = np.abs(A @ x - b).max() / (np.abs(A).sum(axis=1).max() * np.abs(x).max())
+    assert back <= 1e-13 * n, back
+    ref = np.linalg.solve(A, b)
+    assert np.abs(x - ref).max() <= 1e-7 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("blocked", [0, 1])
-def test_lu_solve_reports_a_singular_column(api, blocked):
-    n = 96
+@pytest.mark.parametrize("n,col", [(96, 40), (600, 37), (600, 570)])
+def test_lu_solve_reports_a_singular_column(api, blocked, n, col):
     rng = np.random.default_rng(7)
     A = rng.standard_normal((n, n))
-    A[:, 40] = 0.0
+    A[:, col] = 0.0
     dA = T(np.asfortranarray(A).ravel(order="F")).clone()
     db = T(rng.standard_normal(n)).clone()
-    assert api.lu_solve(dA, db, n, blocked) == 41
+    assert api.lu_solve(dA, db, n, blocked) == col + 1
 
 
 def test_blocked_and_unblocked_lu_choose_the_same_pivots(api):
