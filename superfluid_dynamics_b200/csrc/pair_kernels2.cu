@@ -127,6 +127,38 @@ __device__ __forceinline__ void accumulate2_far(const Src2* __restrict__ sh, con
     }
 }
 
+// The same 10-instruction form for a piece that contains the targets themselves (j == k masked out by a select on the integer
+// pipe): used when the surface has too few cells for cell-local coordinates (N <= 768, every tile is "near").  There the global
+// exponentials are accurate to eps N / 2 pi <= 1.2e-14 per entry anyway, and the cancellation of conj(E_k) U - V is bounded by the
+// same N / 2 pi <= 122.
+template <int R>
+__device__ __forceinline__ void accumulate2_far_diag(const Src2* __restrict__ sh, const double* __restrict__ sg, int len,
+                                                     const double2 (&ek)[R], const int (&sd)[R], double2 (&U)[R], double (&V)[R]) {
+    double2 e = *reinterpret_cast<const double2*>(&sh[0].p);
+    double2 f = *reinterpret_cast<const double2*>(&sh[0].fr);
+    double gj = sg[0];
+#pragma unroll 4
+    for (int s = 0; s < len; ++s) {
+        const double2 en = *reinterpret_cast<const double2*>(&sh[s + 1].p);
+        const double2 fn = *reinterpret_cast<const double2*>(&sh[s + 1].fr);
+        const double gn = sg[s + 1];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double dr = ek[r].x - e.x;
+            double di = ek[r].y - e.y;
+            double n2 = fma(di, di, dr * dr);
+            double inv = fast_rcp2(n2);
+            inv = (s == sd[r]) ? 0.0 : inv;
+            U[r].x = fma(f.x, inv, U[r].x);
+            U[r].y = fma(f.y, inv, U[r].y);
+            V[r] = fma(gj, inv, V[r]);
+        }
+        e = en;
+        f = fn;
+        gj = gn;
+    }
+}
+
 __device__ __forceinline__ bool cells_near(int cT0, int cT1, int cB0, int cB1, int ncell) {
     for (int cT = cT0; cT <= cT1; ++cT)
         for (int cB = cB0; cB <= cB1; ++cB) {
@@ -274,6 +306,14 @@ __global__ void __launch_bounds__(MAXT, 1) sweep2_kernel(const SweepArgs a) {
                 int dist = cellJ - cellK;
                 if (dist < 0) dist += a.ncell;
                 const bool near = a.use_local && tile_near && (dist == 0 || dist == 1 || dist == a.ncell - 1);
+                int sd[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) sd[r] = krow[r] - jj;
+                if (!a.use_local) {   // few cells: global exponentials everywhere, 10-instruction form everywhere
+                    if (cellJ == cellK) accumulate2_far_diag<R>(sh_far + sub0, sh_g + sub0, sublen, ekG, sd, U, V);
+                    else accumulate2_far<R>(sh_far + sub0, sh_g + sub0, sublen, ekG, U, V);
+                    continue;
+                }
                 const int variant = near ? (dist == 0 ? 1 : (dist == 1 ? 2 : 3)) : 0;
                 if (variant != cur_variant) {
                     const double2* tk = variant == 0 ? EG : (variant == 1 ? P0 : (variant == 2 ? a.g.Pp + boff : a.g.Pm + boff));
@@ -281,9 +321,6 @@ __global__ void __launch_bounds__(MAXT, 1) sweep2_kernel(const SweepArgs a) {
                     for (int r = 0; r < R; ++r) ek[r] = valid[r] ? tk[krow[r]] : make_double2(3.0e150, 0.0);
                     cur_variant = variant;
                 }
-                int sd[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) sd[r] = krow[r] - jj;
                 const Src2* src = (near ? sh_near : sh_far) + sub0;
                 if (cellJ == cellK) accumulate2<true, R>(src, sublen, ek, sd, acc);
                 else if (a.use_local && !near) accumulate2_far<R>(src, sh_g + sub0, sublen, ekG, U, V);
@@ -482,7 +519,11 @@ static void launch_one(const SweepArgs& a, const Sweep2Launch& l, cudaStream_t s
 
 void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st) {
     if (a.has_image) throw std::runtime_error("sweep2: the image (finite-depth) sum uses the tiled kernel");
-    if (a.v2_R == 2) {
+    if (a.v2_R == 4) {   // ensembles: 4 rows per thread, 512 threads (the register blocking of the tiled kernel's large-N variant)
+        if (mode == kSweepMV) launch_one<kSweepMV, 4, 512>(a, l, st);
+        else if (mode == kSweepVEL) launch_one<kSweepVEL, 4, 512>(a, l, st);
+        else launch_one<kSweepRAW, 4, 512>(a, l, st);
+    } else if (a.v2_R == 2) {
         if (mode == kSweepMV) launch_one<kSweepMV, 2, 896>(a, l, st);
         else if (mode == kSweepVEL) launch_one<kSweepVEL, 2, 896>(a, l, st);
         else launch_one<kSweepRAW, 2, 896>(a, l, st);

@@ -312,6 +312,15 @@ static void plan_sweep2(rb_solver* s) {
     if (units32 <= 2L * nSM) {
         R = 1;
         RB = 32;
+    } else if (B > 1 && rows >= 128 && env_int("RB_V2_R4", 1)) {
+        // ensembles: whole members (or 128-row multiples of them) per row block, 4 rows per thread -- the register blocking that
+        // carries the tiled kernel to 0.8 of the FP64 peak; round 1 ran them at 2 rows per thread and 0.39 of the peak
+        R = 4;
+        const long units128 = (long)B * ((rows + 127) / 128);
+        long m = (units128 + nSM - 1) / nSM;
+        m = std::max(1L, std::min(4L, m));
+        m = std::min<long>(m, (rows + 127) / 128);
+        RB = 128 * (int)m;
     } else {
         R = 2;
         const long units64 = (long)B * ((rows + 63) / 64);
@@ -323,7 +332,7 @@ static void plan_sweep2(rb_solver* s) {
     RB = env_int("RB_V2_RB", RB);
     R = env_int("RB_V2_R", R);
     const int nrt = RB / R;
-    const int max_threads = R == 2 ? 896 : 1024;   // launch bounds of sweep2_kernel<., R>
+    const int max_threads = R == 4 ? 512 : (R == 2 ? 896 : 1024);   // launch bounds of sweep2_kernel<., R>
     int G = 1;
     while (nrt * G * 2 <= max_threads && G * 2 <= 32 && N / (G * 2) >= 32) G *= 2;
     G = env_int("RB_V2_GROUPS", G);

@@ -172,7 +172,45 @@ def helium():
             print(f"helium N={N}: device-driven vs host-driven final state rel diff {d:.2e}", flush=True)
 
 
-SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, helium=helium)
+def ensemble():
+    """BASELINE config 5b: 1024 members x N = 512 in one batched solver; 4 rows per thread (default) against round 1's 2."""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    peak = api.measure_fp64_peak(dev)
+    for N, B in ((512, 1024), (256, 2048), (768, 512)):
+        hs = 0.05 + 0.35 * np.arange(B) / (B - 1)
+        sts = [ro.pack_state(*ro.trochoid(N, h)) for h in hs]
+        y0 = api.ensemble_state(sts, N)
+        finals = {}
+        for r4 in (1, 0):
+            def run():
+                c = water(N, B, guess="warm")
+                stp = api.AutonomousRungeKuttaStepper(c, 1e-3)
+                y = T(y0)
+                stp.initialize(y, True)
+                stp.runSteps(12)
+                torch.cuda.synchronize()
+                it0 = c.solve_stats()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                stp.runSteps(30)
+                b.record()
+                torch.cuda.synchronize()
+                it1 = c.solve_stats()
+                ms, pairs = c.benchSweep(T(y0), 20)
+                return 30 / (a.elapsed_time(b) * 1e-3), (it1["total_iterations"] - it0["total_iterations"]) / 30, ms, pairs, c.sweepPlan(), y.cpu().numpy(), it1
+            try:
+                rate, spp, ms, pairs, plan, yf, st = with_env({"RB_V2_R4": r4}, run)
+                finals[r4] = yf
+                tf = 20.0 * pairs / (ms * 1e-3) / 1e12
+                print(f"ensemble {B} x N={N} R4={r4}: {rate:.1f} steps/s ({B * rate:.0f} member-steps/s), {spp:.2f} sweeps/step, sweep {ms * 1e3:.1f} us = "
+                      f"{tf:.2f} TF = {tf / peak:.3f}; step {20.0 * pairs * spp * rate / 1e12 / peak:.3f} of peak; {plan} failed={st['failed_solves']}", flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(f"ensemble {B} x N={N} R4={r4}: FAILED {e}", flush=True)
+        if len(finals) == 2:
+            print(f"ensemble {B} x N={N}: R4 vs R2 final state rel diff {np.abs(finals[0] - finals[1]).max() / np.abs(finals[0]).max():.2e}", flush=True)
+
+
+SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, helium=helium, ensemble=ensemble)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)

@@ -350,6 +350,75 @@ def test_helium_gmres_agrees_with_dense_lu_and_reports_convergence(api):
         assert rel(outs[0][0], outs[1][0]) <= 1e-10
 
 
+def _film(N, depth, amp):
+    al = 2 * np.pi * np.arange(N) / N
+    return ro.pack_state(al - 0.3 * amp * depth * np.sin(al) + 1j * amp * depth * np.cos(al), 0.2 * amp * depth * np.sin(al))
+
+
+def test_recorded_helium_steps_with_the_device_driven_gmres_cycle(api):
+    """Finite-depth helium film inside the RK4 stepper: recorded steps (CUDA graph) whose GMRES cycle -- Arnoldi, Givens rotations,
+    per-member convergence -- runs on the device and is verified by the combined velocity sweep, against the host-driven restarted
+    GMRES (RB_DEVICE_GMRES=0, unrecorded steps): both solve M a = b to 1e-13, so 30 steps agree to ~1e-13 (tolerance 1e-11); and
+    against the oracle's dense-LU RK4 on the same film (north_star bar 1e-9; cond(M) ~ N / 2 pi)."""
+    N, depth, dt, steps = 1024, 0.0942478, 1e-3, 30
+    props = api.ProblemProperties(rho=0.0, depth=depth)
+    y0 = _film(N, depth, 0.1)
+    states = {}
+    for dg in ("1", "0"):
+        os.environ["RB_DEVICE_GMRES"] = dg
+        try:
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumBoundaryProblem(props), guess="warm")
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+        finally:
+            os.environ.pop("RB_DEVICE_GMRES", None)
+        y = T(y0)
+        stp.initialize(y, True)
+        stp.runSteps(steps)
+        st, ss = calc.solve_stats(), stp.stats()
+        assert st["converged"] and st["failed_solves"] == 0, st
+        assert (ss["graph_launches"] >= steps // 2) == (dg == "1"), ss
+        states[dg] = y.cpu().numpy()
+    assert rel(states["1"], states["0"]) <= 1e-11
+    oprops = ro.ProblemProperties(rho=0.0, depth=depth)
+    f = lambda s: ro.rhs(s, N, 1, oprops, "helium", "cuda")
+    ye = y0.copy()
+    for _ in range(5):
+        ye = ro.rk4_step(f, ye, dt)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumBoundaryProblem(props), guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(calc, dt)
+    stp.initialize(y0, False)
+    stp.runSteps(5)
+    assert rel(stp.getState(), ye) <= 1e-9
+
+
+def test_helium_ensemble_members_converge_individually(api):
+    """A batch of films of very different amplitude in one recorded stepper: every member's GMRES cycle stops on its OWN residual
+    against its OWN ||b|| (a member with a small right-hand side is not hidden behind the others), so each member's trajectory
+    equals the one it has when stepped alone (1e-11)."""
+    N, depth, dt, steps = 256, 0.0942478, 1e-3, 12
+    props = api.ProblemProperties(rho=0.0, depth=depth)
+    amps = (0.3, 1e-3, 0.05)
+    members = [_film(N, depth, a) for a in amps]
+    calc = api.BaseBoundaryIntegralCalculator(N, len(amps), props, api.HeliumBoundaryProblem(props), guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(calc, dt)
+    y = T(api.ensemble_state(members, N))
+    stp.initialize(y, True)
+    stp.runSteps(steps)
+    assert calc.solve_stats()["failed_solves"] == 0 and stp.stats()["graph_launches"] >= 1
+    got = y.cpu().numpy()
+    B = len(amps)
+    for m, y0 in enumerate(members):
+        alone = api.BaseBoundaryIntegralCalculator(N, 1, props, api.HeliumBoundaryProblem(props), guess="warm")
+        s1 = api.AutonomousRungeKuttaStepper(alone, dt)
+        s1.initialize(y0, False)
+        s1.runSteps(steps)
+        mine = np.concatenate([got[m * N:(m + 1) * N], got[B * N + m * N:B * N + (m + 1) * N]])
+        e = s1.getState()
+        # position relative to 2 pi; potential relative to ITS OWN scale (the small member's potential is 1e-5 of the large one's)
+        assert rel(mine[:N], e[:N]) <= 1e-11, (m, rel(mine[:N], e[:N]))
+        assert np.abs(mine[N:] - e[N:]).max() <= 1e-9 * np.abs(e[N:]).max() + 1e-16, m
+
+
 def test_dense_lu_and_matrix_free_agree_at_N4096(api):
     """BASELINE config 3: steep trochoid (h = 0.4), N = 4096 -- assemble-and-factorise (the reference's way) vs the matrix-free
     iteration agree to <= 1e-12 per RHS."""
