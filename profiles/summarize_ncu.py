@@ -18,6 +18,10 @@ KEYS = [
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct",
     "smsp__inst_executed_op_shared_ld.sum", "sm__inst_executed_pipe_xu.sum",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",

@@ -16,8 +16,10 @@
 // then lu_backsolve_blocked_kernel: the back substitution with U, one CTA, 32 columns per pair of barriers.
 // Measured on a B200 (profiles/r02c_implicit_report_before_cluster_panel.json, CUDA events, ms; unblocked / blocked with the one-CTA
 // panel / cuSOLVER getrf+getrs): n = 384: 4.2 / 3.3 / 0.98; 1536: 25.4 / 17.3 / 4.4; 4096: 166 / 67 / 18.0; 6144: - / 165 / 32.3 --
-// the blocked factorisation is the default (dense_kernels.cu: launch_lu_solve), and almost all of its time was the one-CTA panel,
-// which the cluster panel below (lu_panel_cluster_kernel) replaces for panels of >= 256 rows.
+// the blocked factorisation is the default (dense_kernels.cu: launch_lu_solve).  ncu launch list at n = 2048 (profiles/
+// r02p_lu_launches_n2048_summary.txt): panel 73 % (215 us per 32 columns), swap + TRSM 12 %, trailing DMMA GEMM 7 %, back
+// substitution 4.5 %, GEMV 3 %: the panel's per-column chain of L2 round trips and barriers is what separates this factorisation
+// from cuSOLVER's (3.7x at n = 4096), not the tensor-core update.
 // The kernels and the launch sequence below also compile under g++ with tests/cpp/cuda_emu.h standing in for the CUDA headers
 // (RB_EMULATE): the CPU test tier runs them thread for thread against LAPACK (tests/test_kernel_emulation.py).
 #ifdef RB_EMULATE
@@ -469,12 +471,14 @@ bool try_cluster_panel(double* A, int n, int k0, int kb, int* piv, int* info, cu
     return true;
 }
 
+// Measured on a B200 (profiles/r02e_implicit_report.json, r02p_lu_profile_*.log): correct (tests/test_zz_gpu_implicit.py runs it at
+// n = 257 ... 7000, clusters of 8 and 16), but NOT faster than the one-CTA panel -- n = 1536: 26 ms against 17, n = 4096: 70 against 67,
+// n = 6144: 145 against 165, and erratic from call to call (72 ... 600 ms at n = 4096; a launch of one 8-CTA cluster with > 100 KB
+// of dynamic shared memory per CTA between small ordinary launches appears to cost far more than the kernel itself).  It is therefore
+// opt-in (RB_LU_CLUSTER_PANEL=1); the default panel is the one-CTA kernel.
 bool cluster_panels_enabled() {
-    static const bool on = [] {
-        const char* v = std::getenv("RB_LU_CLUSTER_PANEL");
-        return !v || std::atoi(v) != 0;
-    }();
-    return on;
+    const char* v = std::getenv("RB_LU_CLUSTER_PANEL");
+    return v && std::atoi(v) != 0;
 }
 
 }  // namespace

@@ -176,7 +176,7 @@ constexpr int kMaxStage = 1;   // staged entries per thread and tile (TS <= thre
 // MAXT: launch bound (R = 2: 896 threads = 4 source groups at 72 registers; measured at N = 65536: 3 groups / 672 threads / 80
 // registers 3.56 ms against 3.11 ms -- resident warps matter more than registers here)
 template <int MODE, int R, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) sweep2_kernel(const SweepArgs a) {
+__global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) sweep2_kernel(const SweepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x;
     const int TS = a.v2_TS;
@@ -519,7 +519,11 @@ static void launch_one(const SweepArgs& a, const Sweep2Launch& l, cudaStream_t s
 
 void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st) {
     if (a.has_image) throw std::runtime_error("sweep2: the image (finite-depth) sum uses the tiled kernel");
-    if (a.v2_R == 4) {   // ensembles: 4 rows per thread, 512 threads (the register blocking of the tiled kernel's large-N variant)
+    if (a.v2_R == 4 && l.threads <= 256) {   // ensembles: 4 rows per thread, two CTAs of 256 threads per SM (one stages / closes
+        if (mode == kSweepMV) launch_one<kSweepMV, 4, 256>(a, l, st);          // its row block while the other evaluates pairs)
+        else if (mode == kSweepVEL) launch_one<kSweepVEL, 4, 256>(a, l, st);
+        else launch_one<kSweepRAW, 4, 256>(a, l, st);
+    } else if (a.v2_R == 4) {
         if (mode == kSweepMV) launch_one<kSweepMV, 4, 512>(a, l, st);
         else if (mode == kSweepVEL) launch_one<kSweepVEL, 4, 512>(a, l, st);
         else launch_one<kSweepRAW, 4, 512>(a, l, st);

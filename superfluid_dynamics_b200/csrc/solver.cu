@@ -332,7 +332,7 @@ static void plan_sweep2(rb_solver* s) {
     RB = env_int("RB_V2_RB", RB);
     R = env_int("RB_V2_R", R);
     const int nrt = RB / R;
-    const int max_threads = R == 4 ? 512 : (R == 2 ? 896 : 1024);   // launch bounds of sweep2_kernel<., R>
+    const int max_threads = R == 4 ? (env_int("RB_V2_R4_THREADS", 256) <= 256 ? 256 : 512) : (R == 2 ? 896 : 1024);   // launch bounds of sweep2_kernel<., R>
     int G = 1;
     while (nrt * G * 2 <= max_threads && G * 2 <= 32 && N / (G * 2) >= 32) G *= 2;
     G = env_int("RB_V2_GROUPS", G);
@@ -374,7 +374,8 @@ static void plan_sweep2(rb_solver* s) {
         const long grid = std::min<long>(items, nSM);
         s->v2_eff = (double)items / ((double)((items + grid - 1) / grid) * nSM);
     }
-    s->v2l.grid = (int)std::min<long>((long)s->v2_total_blocks * s->v2_split, env_int("RB_V2_GRID", nSM));
+    // (R = 4 with 256 threads: two CTAs per SM, so that the staging / closing phases of one row block overlap the pair loop of another)
+    s->v2l.grid = (int)std::min<long>((long)s->v2_total_blocks * s->v2_split, env_int("RB_V2_GRID", (R == 4 && threads <= 256) ? 2 * nSM : nSM));
     s->v2l.threads = threads;
     s->v2l.smem = (size_t)s->v2_TS * 32 * (s->use_local ? 2 : 1) + (size_t)threads * R * 16 + (size_t)threads * 8 +
                   (size_t)s->v2_TS * 8 + 16;   // + one padding entry behind g: the far loop loads one source ahead
@@ -2196,7 +2197,7 @@ int rb_debug_set_row_range(rb_solver* s, int cell0, int cells) {
 int rb_sweep_plan(rb_solver* s, int out[8]) {
     RB_TRY
     out[0] = s->use_v2 ? 2 : 1;            // 1 tiled, 2 persistent
-    out[1] = s->v1_rows;
+    out[1] = s->use_v2 ? s->v2_R : s->v1_rows;
     out[2] = s->tile;
     out[3] = s->tiles_per_chunk;
     out[4] = s->nchunks;
