@@ -176,7 +176,8 @@ RB_API double rb_rk4_current_time(rb_stepper* st);
 RB_API int rb_rk4_stats(rb_stepper* st, double out_host[4]);
 /* asynchronous chunks of rb_rk4_run_steps / rb_rk4_evolve (several recorded steps launched back to back, one host look per chunk; a
    chunk in which any solve ran out of recorded sweeps or failed is rolled back and redone step by step): out[0] steps per chunk
-   (0: off, RB_ASYNC_STEPS), [1] chunks launched, [2] chunks rolled back, [3] reserved */
+   (0: off, RB_ASYNC_STEPS), [1] chunks launched, [2] chunks rolled back, [3] steps recorded without a surplus sweep round that had to
+   be redone (+ 0.5 while such a tight recording is in use) */
 RB_API int rb_rk4_chunk_stats(rb_stepper* st, double out_host[4]);
 /* quality of the extrapolated initial iterates: out[0..3] relative residual of the guess at RK stage 1..4 of the last step,
    [4] mask of stages that currently start with a combined (verify + velocity) sweep, [5] solves started that way so far,

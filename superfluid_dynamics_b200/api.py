@@ -312,7 +312,8 @@ class AutonomousRungeKuttaStepper:
         ch = (ctypes.c_double * 4)()
         check(self.lib.rb_rk4_chunk_stats(self.handle, ch), "rb_rk4_chunk_stats")
         return dict(graph_launches=int(out[0]), graph_captures=int(out[1]), fallback_steps=int(out[2]), graph_sweeps=int(out[3]),
-                    chunk_steps=int(ch[0]), chunks=int(ch[1]), chunks_rolled_back=int(ch[2]))
+                    chunk_steps=int(ch[0]), chunks=int(ch[1]), chunks_rolled_back=int(ch[2]),
+                    tight=bool(ch[3] - int(ch[3]) > 0.25), tight_failures=int(ch[3]))
 
     def guessStats(self):
         out = (ctypes.c_double * 8)()

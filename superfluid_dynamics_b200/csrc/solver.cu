@@ -1297,6 +1297,13 @@ struct rb_stepper {
     double graph_dt = 0;
     double2* graph_y0 = nullptr;
     int graph_hits_below = 0;     // consecutive steps that needed far fewer sweeps than captured
+    // "tight" recording: after a long run of steps that all needed the same number of sweeps, record exactly that many (no surplus,
+    // self-skipping round per solve: at N <= 4096 such a round -- a skipped sweep, its a' transform, the fork / join around it -- is
+    // ~8 % of a step); a step that then runs out of sweeps is rolled back and redone as always, and tight recording is banned for a while
+    bool tight_ok = true;
+    bool tight = false;
+    int tight_hits = 0, tight_ban = 0;
+    long long tight_failures = 0;
     long long graph_launches = 0, graph_captures = 0, fallback_steps = 0;
     cudaEvent_t ev = nullptr;
     // asynchronous chunks: several recorded steps launched back to back, one host synchronisation per chunk (launch-bound regime)
@@ -1517,6 +1524,13 @@ static void stepper_step(rb_stepper* st) {
         }
         worst = std::max(worst, s->kpred);
         int sweeps = std::min(s->props.max_iterations, worst + 4);
+        if (st->tight) {   // a tightly recorded step ran out of sweeps: back to a surplus round, and no new attempt for a while
+            st->tight = false;
+            st->tight_ban = 512;
+            st->tight_failures++;
+            sweeps = std::min(s->props.max_iterations, std::max(worst, st->graph_sweeps) + 2);
+        }
+        st->tight_hits = 0;
         st->graph_sweeps = sweeps;
         st->opt_mask = st->opt_policy == 2 ? 15 : 0;
         invalidate_graphs(st);
@@ -1570,13 +1584,27 @@ static void stepper_step(rb_stepper* st) {
             note_solve_end(s, c.converged, c.stagnated, std::sqrt(std::max(0.0, c.rel2)), c.iters, "RK4 stage");
         }
         // shrink the recorded sweep count when it has been clearly too large for a while (each skipped sweep costs a launch)
+        if (st->tight_ban > 0) st->tight_ban--;
         if (st->graph_sweeps - worst >= 3) {
+            st->tight_hits = 0;
             if (++st->graph_hits_below >= 8) {
                 st->graph_sweeps = worst + 1;
                 invalidate_graphs(st);
             }
         } else {
             st->graph_hits_below = 0;
+            // ... and drop the last surplus round once the count has been the same for 24 steps in a row
+            if (st->tight_ok && !st->tight && st->tight_ban == 0 && st->graph_sweeps - worst >= 1 && worst >= (s->use_gmres ? 3 : 2) &&
+                s->props.guess_mode == RB_GUESS_WARM) {
+                if (++st->tight_hits >= 24) {
+                    st->graph_sweeps = worst;
+                    st->tight = true;
+                    st->tight_hits = 0;
+                    invalidate_graphs(st);
+                }
+            } else if (!st->tight) {
+                st->tight_hits = 0;
+            }
         }
     }
     if (s->props.guess_mode == RB_GUESS_WARM) st->h_counter++;
@@ -1943,6 +1971,7 @@ rb_stepper* rb_rk4_create(rb_solver* s, double tstep) {
             st->predict = pr >= 0 ? (pr != 0) : (s->props.tolerance >= 4e-13);
         }
         st->use_graph = env_int("RB_NO_GRAPH", 0) == 0;
+        st->tight_ok = env_int("RB_TIGHT_GRAPH", 1) != 0;
         // measured on a B200 (profiles/r02c_async_chunks.log): 4135 vs 4086 steps/s at N = 1024, 2451 vs 2514 at N = 4096, 430 vs 433 at
         // N = 16384 -- the per-step host round trip is already hidden behind the recorded step, so the chunks are OFF unless asked for
         st->chunk = std::max(0, std::min(kChunkMax, std::min(env_int("RB_ASYNC_STEPS", 0), kHistRing - st->order)));
@@ -2030,7 +2059,7 @@ int rb_rk4_chunk_stats(rb_stepper* st, double out_host[4]) {
     out_host[0] = (double)st->chunk;
     out_host[1] = (double)st->chunks_launched;
     out_host[2] = (double)st->chunks_rolled_back;
-    out_host[3] = 0.0;
+    out_host[3] = (double)st->tight_failures + (st->tight ? 0.5 : 0.0);   // tightly recorded steps that had to be redone (+ 0.5 while tight)
     return 0;
 }
 int rb_rk4_guess_stats(rb_stepper* st, double out_host[8]) {

@@ -273,6 +273,33 @@ def test_recorded_steps_equal_unrecorded_steps_at_the_headline_size(api, N, dt):
     assert rel(states[0][N:], states[1][N:]) <= 1e-11
 
 
+def test_tight_recording_drops_the_surplus_round_and_keeps_the_trajectory(api):
+    """After a run of steps that all needed the same number of sweeps the stepper records exactly that many (no self-skipping
+    surplus round); a step that then ran out of sweeps would be rolled back and redone.  The trajectory is the one of the ordinary
+    recording (RB_TIGHT_GRAPH=0) to round-off: both verify every solve to 1e-13."""
+    N, dt, steps = 1024, 1e-3, 80
+    props = api.ProblemProperties(rho=0.0)
+    y0 = ro.pack_state(*ro.trochoid(N, 0.4))
+    out = {}
+    for tight in ("1", "0"):
+        os.environ["RB_TIGHT_GRAPH"] = tight
+        try:
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), guess="warm")
+            stp = api.AutonomousRungeKuttaStepper(calc, dt)
+        finally:
+            os.environ.pop("RB_TIGHT_GRAPH", None)
+        y = T(y0)
+        stp.initialize(y, True)
+        stp.runSteps(steps)
+        ss, st = stp.stats(), calc.solve_stats()
+        assert st["converged"] and st["failed_solves"] == 0, st
+        assert ss["tight"] == (tight == "1"), ss
+        if tight == "1":
+            assert ss["graph_sweeps"] == 2 and ss["tight_failures"] == 0, ss
+        out[tight] = y.cpu().numpy()
+    assert rel(out["1"], out["0"]) <= 1e-12
+
+
 # ---- full RHS -------------------------------------------------------------------------------------------------------
 def _split(state):
     N = len(state) // 3
