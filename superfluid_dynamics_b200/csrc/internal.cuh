@@ -288,6 +288,7 @@ void launch_combine(double* out, const double* V, size_t ldv, int nvec, const do
 void launch_normalize(double* vout, const double* w, const double* nrm2, int n, cudaStream_t st);
 void launch_axpby(double* out, const double* a, double alpha, const double* b, int n, cudaStream_t st);
 void launch_precond_scale(double2* hat, const double* invP, int N, int n, cudaStream_t st);
+void launch_precond_scale_half(double2* half, const double* invP, int N, int batch, cudaStream_t st);
 void launch_real_to_complex(const double* x, double2* out, int n, cudaStream_t st);
 void launch_complex_to_real(const double2* c, double* out, double scale, int n, cudaStream_t st);
 void launch_gm_start(const double* b, const double* w, double* V0, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch,

@@ -106,6 +106,24 @@ void launch_precond_scale(double2* hat, const double* invP, int N, int n, cudaSt
     count_launch();
 }
 
+// the same on the half spectrum of a real transform (D2Z -> scale -> Z2D): hat[b][m] *= invP[m] * norm, m <= N/2 (the symbol is
+// symmetric, invP[m] == invP[N - m], so the half spectrum is all there is to scale); norm = 1/N folds the transform pair's
+// normalisation in
+__global__ void precond_scale_half_kernel(double2* __restrict__ half, const double* __restrict__ invP, int nh, int n, double norm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double s = invP[i % nh] * norm;
+    double2 c = half[i];
+    half[i] = make_double2(c.x * s, c.y * s);
+}
+
+void launch_precond_scale_half(double2* half, const double* invP, int N, int batch, cudaStream_t st) {
+    const int nh = N / 2 + 1, n = nh * batch;
+    precond_scale_half_kernel<<<(n + 255) / 256, 256, 0, st>>>(half, invP, nh, n, 1.0 / N);
+    RB_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 __global__ void real_to_complex_kernel(const double* __restrict__ x, double2* __restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = make_double2(x[i], 0.0);

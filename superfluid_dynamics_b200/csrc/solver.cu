@@ -141,7 +141,7 @@ struct rb_solver {
     int* lu_info = nullptr;
     double2* scratch_state = nullptr;   // legacy host-vector exports
 
-    cufftHandle plan1 = 0, plan2 = 0, plan3 = 0, plan_d2z = 0;
+    cufftHandle plan1 = 0, plan2 = 0, plan3 = 0, plan_d2z = 0, plan_z2d = 0;   // plan_z2d: helium preconditioner only
     // shared-memory FFT derivatives (small power-of-two N, launch-bound regime): twiddle table exp(-2 pi i k / N), k < N/2
     bool own_fft = false;
     bool own_fft_skippable = false;
@@ -190,6 +190,7 @@ static void solver_free(rb_solver* s) {
         cufftDestroy(s->plan2);
         cufftDestroy(s->plan3);
         cufftDestroy(s->plan_d2z);
+        if (s->plan_z2d) cufftDestroy(s->plan_z2d);
     }
     for (int r = 0; r < kMaxRanks; ++r)
         if (s->peer_mapped[r]) cudaIpcCloseMemHandle(s->peer_mapped[r]);
@@ -568,6 +569,8 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     cufft_check(cufftPlanMany(&s->plan2, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 2 * batch), "cufftPlanMany(2B)");
     cufft_check(cufftPlanMany(&s->plan3, 1, n, nullptr, 1, N, nullptr, 1, N, CUFFT_Z2Z, 3 * batch), "cufftPlanMany(3B)");
     cufft_check(cufftPlanMany(&s->plan_d2z, 1, n, nullptr, 1, N, nullptr, 1, N / 2 + 1, CUFFT_D2Z, batch), "cufftPlanMany(D2Z)");
+    if (s->use_gmres)
+        cufft_check(cufftPlanMany(&s->plan_z2d, 1, n, nullptr, 1, N / 2 + 1, nullptr, 1, N, CUFFT_Z2D, batch), "cufftPlanMany(Z2D)");
     s->plans = true;
     // the one-CTA radix-2 transform is shared-memory-bandwidth bound (~1.3k cycles per pass at N = 4096): it beats the library's
     // three launches only in the launch-bound regime (measured: faster at N <= 1024, slower at N = 4096)
@@ -624,6 +627,7 @@ static void set_stream(rb_solver* s, cudaStream_t st) {
     cufft_check(cufftSetStream(s->plan2, st), "cufftSetStream");
     cufft_check(cufftSetStream(s->plan3, st), "cufftSetStream");
     cufft_check(cufftSetStream(s->plan_d2z, st), "cufftSetStream");
+    if (s->plan_z2d) cufft_check(cufftSetStream(s->plan_z2d, st), "cufftSetStream");
 }
 
 // ZPhiDerivative::exec into the solver's own buffers (Zp | Zpp | PhiPrime)
@@ -820,16 +824,13 @@ static void apply_M(rb_solver* s, const SweepArgs& base, const double* x, SolveC
         launch_comm_wait(s->comm, skip ? skip : s->ctrl, skip ? 3 : 0, 0, 0, s->bnorm_part, s->ncell, 0.0, 0, st);
 }
 
-// out = P^{-1} v  (FFT, divide by the flat-film symbol, inverse FFT); out may alias v
+// out = P^{-1} v  (real FFT, divide by the flat-film symbol, inverse real FFT: three launches); out may alias v
 static void apply_Pinv(rb_solver* s, const double* v, double* out) {
     cudaStream_t st = s->stream;
-    const int n = (int)s->BN;
-    double2* tmp = s->fwork;   // free between the derivative stage and the a' stage
-    launch_real_to_complex(v, tmp, n, st);
-    cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)tmp, (cufftDoubleComplex*)tmp, CUFFT_FORWARD), "fft fwd");
-    launch_precond_scale(tmp, s->gm_invP, s->N, n, st);
-    cufft_check(cufftExecZ2Z(s->plan1, (cufftDoubleComplex*)tmp, (cufftDoubleComplex*)tmp, CUFFT_INVERSE), "fft inv");
-    launch_complex_to_real(tmp, out, 1.0 / s->N, n, st);
+    double2* half = s->fwork;   // free between the derivative stage and the a' stage; (N/2 + 1) * batch complex values
+    cufft_check(cufftExecD2Z(s->plan_d2z, (cufftDoubleReal*)const_cast<double*>(v), (cufftDoubleComplex*)half), "fft d2z");
+    launch_precond_scale_half(half, s->gm_invP, s->N, s->batch, st);
+    cufft_check(cufftExecZ2D(s->plan_z2d, (cufftDoubleComplex*)half, (cufftDoubleReal*)out), "fft z2d");
 }
 
 static void gmres_solve(rb_solver* s, const double2* Z) {
