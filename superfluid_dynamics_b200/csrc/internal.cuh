@@ -47,8 +47,11 @@ struct SolveCtrl {
 // How a solve ended, decided once per sweep from the worst member's ||r||^2/||b||^2 by whichever thread closes the sweep (the last
 // CTA of a sweep kernel, or comm_wait_kernel on a row-sharded run; every rank takes it from the same numbers in the same order).
 //   converged: rel <= tolerance, nothing else.
-//   stagnated: rel <= 1e-10 and no longer contracting (the residual sits on its round-off floor, which grows like N eps): the
-//              iteration cannot do better; the solve ends with converged = 0, stagnated = 1 and the host counts it separately.
+//   stagnated: rel <= 1e-10 and no longer contracting -- the residual shrank by less than a factor 0.8 in the last sweep (the
+//              slowest contraction the Neumann iteration has on any surface it converges on is ~0.55 per sweep, trochoid
+//              steepness 0.9, which must NOT count: round 1's threshold of 0.5 cut such solves short at 1e-10) -- i.e. the residual
+//              sits on its round-off floor, which grows like N eps: the iteration cannot do better; the solve ends with
+//              converged = 0, stagnated = 1 and the host counts it separately.
 //   neither and iters >= max_iters: the solve failed (done = 1, converged = 0, stagnated = 0).
 #ifdef __CUDACC__
 __device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst, double tol2, int max_iters, int final_buf) {
@@ -56,7 +59,7 @@ __device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst
     const int iters = c->iters + 1;
     const double prev = c->prev_rel2;
     const bool conv = worst <= tol2;
-    const bool stagnated = !conv && iters >= 3 && worst <= 1e-20 && worst > 0.25 * prev;
+    const bool stagnated = !conv && iters >= 3 && worst <= 1e-20 && worst > 0.64 * prev;
     c->iters = iters;
     c->rel2 = worst;
     c->prev_rel2 = worst;

@@ -131,6 +131,8 @@ struct rb_solver {
     // restarted GMRES for the finite-depth helium operator (host-driven, one synchronisation per iteration)
     bool use_gmres = false;
     int gm_m = 0;                  // restart length
+    size_t gm_ld = 0;              // stride of the Krylov vectors (BN rounded up to 32: the real transforms of the preconditioner want
+                                   // 16-byte aligned vectors, also for odd N)
     double *gm_V = nullptr, *gm_x = nullptr, *gm_t = nullptr, *gm_dev = nullptr, *gm_invP = nullptr;
     double* gm_host = nullptr;     // pinned
     // the same solver driven from the device inside recorded RK4 steps (krylov_kernels.cu: gm_*_kernel)
@@ -333,7 +335,7 @@ static void plan_sweep2(rb_solver* s) {
     RB = env_int("RB_V2_RB", RB);
     R = env_int("RB_V2_R", R);
     const int nrt = RB / R;
-    const int max_threads = R == 4 ? (env_int("RB_V2_R4_THREADS", 256) <= 256 ? 256 : 512) : (R == 2 ? 896 : 1024);   // launch bounds of sweep2_kernel<., R>
+    const int max_threads = R == 4 ? (env_int("RB_V2_R4_THREADS", 512) <= 256 ? 256 : 512) : (R == 2 ? 896 : 1024);   // launch bounds of sweep2_kernel<., R>
     int G = 1;
     while (nrt * G * 2 <= max_threads && G * 2 <= 32 && N / (G * 2) >= 32) G *= 2;
     G = env_int("RB_V2_GROUPS", G);
@@ -537,7 +539,8 @@ static rb_solver* solver_create(int N, int batch, const rb_props* pin) {
 
     if (s->use_gmres) {
         s->gm_m = std::max(2, std::min(env_int("RB_GMRES_RESTART", 60), N));
-        s->gm_V = dmalloc<double>((size_t)(s->gm_m + 1) * BN);
+        s->gm_ld = (BN + 31) / 32 * 32;
+        s->gm_V = dmalloc<double>((size_t)(s->gm_m + 1) * s->gm_ld);
         s->gm_x = dmalloc<double>(BN);
         s->gm_t = dmalloc<double>(BN);
         s->gm_dev = dmalloc<double>(4 * (s->gm_m + 4));
@@ -836,7 +839,7 @@ static void apply_Pinv(rb_solver* s, const double* v, double* out) {
 static void gmres_solve(rb_solver* s, const double2* Z) {
     cudaStream_t st = s->stream;
     const int n = (int)s->BN, m = s->gm_m;
-    const size_t ld = s->BN;
+    const size_t ld = s->gm_ld;
     const double tol = s->props.tolerance;
     double* V = s->gm_V;
     double* w = s->xbuf[1];
@@ -1202,11 +1205,11 @@ static void rhs_gmres_recorded(rb_solver* s, const double2* state, double2* out)
     apply_M(s, base, s->gm_x);                                                      // w = M x0
     launch_gm_start(s->b, w, s->gm_V, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, tol_in, st);
     for (int k = 0; k < K; ++k) {
-        apply_Pinv(s, s->gm_V + (size_t)k * BN, s->gm_t);
+        apply_Pinv(s, s->gm_V + (size_t)k * s->gm_ld, s->gm_t);
         apply_M(s, base, s->gm_t, skip);                                            // w = M P^{-1} v_k
-        launch_gm_arnoldi(s->gm_V, BN, w, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, k, K - 1, tol_in, st);
+        launch_gm_arnoldi(s->gm_V, s->gm_ld, w, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, k, K - 1, tol_in, st);
     }
-    launch_gm_correction(s->gm_V, BN, s->gm_t, s->gm_members, s->N, s->batch, st);
+    launch_gm_correction(s->gm_V, s->gm_ld, s->gm_t, s->gm_members, s->N, s->batch, st);
     apply_Pinv(s, s->gm_t, s->gm_t);
     launch_axpby(s->gm_x, s->gm_x, 1.0, s->gm_t, n, st);
     launch_finish_solve(s->gm_x, s->gm_x, nullptr, s->a, s->ac, s->xsum_a, s->hist, s->N, s->batch, s->ncell, st);
