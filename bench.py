@@ -347,7 +347,7 @@ def status_of(calc):
     return {k: s[k] for k in ("converged", "stagnated", "stagnated_solves", "failed_solves", "worst_residual")}
 
 
-def leg_sharded_water(ctx, api, N, steps, warm=14, compare_single=True, ref_gpu=None, peak=None):
+def leg_sharded_water(ctx, api, N, steps, warm=30, compare_single=True, ref_gpu=None, peak=None):
     """Water surface of size N, row-sharded over the ranks of this run: steps/s (runSteps between one event pair), sweep roofline,
     replicas identical, difference to a single-GPU run of the same step count (rank 0)."""
     torch = ctx.torch
@@ -393,7 +393,7 @@ def leg_sharded_water(ctx, api, N, steps, warm=14, compare_single=True, ref_gpu=
     return out
 
 
-def leg_helium(ctx, api, peak, N=16384, steps=10, warm=6):
+def leg_helium(ctx, api, peak, N=16384, steps=10, warm=30):
     """BASELINE config 4: helium film with van-der-Waals forcing, finite depth (image term, F_pair = 40), N = 16384, row-sharded."""
     torch = ctx.torch
     props = api.ProblemProperties(rho=0.0, depth=HELIUM_DEPTH)
@@ -433,7 +433,7 @@ def leg_helium(ctx, api, peak, N=16384, steps=10, warm=6):
     return out
 
 
-def leg_ensemble(ctx, api, peak, Ne=512, Be=1024, steps=30, warm=12):
+def leg_ensemble(ctx, api, peak, Ne=512, Be=1024, steps=30, warm=30):
     """BASELINE config 5, second half: the 1024-member ensemble at N = 512 (member m: trochoid h_m = 0.05 + 0.35 m / 1023,
     SURVEY.md section 8d); the members are spread over the ranks (replicas only: no communication), each rank steps its share in
     one batched solver.  Rank 0's first member is checked against the same member stepped alone."""
@@ -731,8 +731,10 @@ def main():
     ap.add_argument("--extra-timeout", type=float, default=240.0, help="seconds after which the headline is printed without the extras")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the compiled reference CUDA path (oracle/_ref)")
     args = ap.parse_args()
-    # the stepper tunes the number of recorded sweeps and fills its 4-step stage history during the first steps: warm up past that
-    args.warmup = max(args.warmup, 12) if args.impl == "native" else args.warmup
+    # the stepper fills its 4-step stage history and tunes the number of recorded sweeps during the first steps (first graph: 16 sweeps
+    # per solve; after 8 steps that needed far fewer: needed + 1; after 8 more that all needed the same: exactly that many), each
+    # change being a re-capture of the step's CUDA graph: warm up past that (~22 steps) so that no capture falls into the timed region
+    args.warmup = max(args.warmup, 30) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -223,7 +223,7 @@ struct rb_stepper {
     double graph_dt = 0;
     double2* graph_y0 = nullptr;
     int graph_hits_below = 0;     // consecutive steps that needed far fewer sweeps than captured
-    // "tight" recording: after a long run of steps that all needed the same number of sweeps, record exactly that many (no surplus,
+    // "tight" recording: after 8 steps in a row that all needed the same number of sweeps, record exactly that many (no surplus,
     // self-skipping round per solve: at N <= 4096 such a round -- a skipped sweep, its a' transform, the fork / join around it -- is
     // ~8 % of a step); a step that then runs out of sweeps is rolled back and redone as always, and tight recording is banned for a while
     bool tight_ok = true;

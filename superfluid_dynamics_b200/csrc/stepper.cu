@@ -280,10 +280,10 @@ void stepper_step(rb_stepper* st) {
             }
         } else {
             st->graph_hits_below = 0;
-            // ... and drop the last surplus round once the count has been the same for 24 steps in a row
+            // ... and drop the last surplus round once the count has been the same for 8 steps in a row
             if (st->tight_ok && !st->tight && st->tight_ban == 0 && st->graph_sweeps - worst >= 1 && worst >= (s->use_gmres ? 3 : 2) &&
                 s->props.guess_mode == RB_GUESS_WARM) {
-                if (++st->tight_hits >= 24) {
+                if (++st->tight_hits >= 8) {
                     st->graph_sweeps = worst;
                     st->tight = true;
                     st->tight_hits = 0;
