@@ -1,16 +1,21 @@
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv): launches, total and average device time per kernel.
 
-    python profiles/summarize_launches.py gpurun_out/launches.csv "comment line" > profiles/rNN_launches_summary.txt
+    python profiles/summarize_launches.py gpurun_out/launches.csv "comment line" [last N launches] > profiles/rNN_launches_summary.txt
 """
 import collections
 import csv
 import sys
 
 
-def main(path, comment=""):
+def main(path, comment="", last=0):
     hdr = None
     agg = collections.defaultdict(lambda: [0, 0.0])
-    for r in csv.reader(open(path)):
+    rows = list(csv.reader(open(path)))
+    if last:      # only the last `last` launches (steady state of a run whose first steps tune the recorded graph)
+        data = [r for r in rows if len(r) >= 6 and r[0] != "ID" and r[0].isdigit()]
+        keep = set(r[0] for r in data[-last:])
+        rows = [r for r in rows if len(r) < 6 or r[0] == "ID" or r[0] in keep]
+    for r in rows:
         if len(r) < 6:
             continue
         if r[0] == "ID":
@@ -36,4 +41,4 @@ def main(path, comment=""):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "")
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "", int(sys.argv[3]) if len(sys.argv) > 3 else 0)

@@ -119,7 +119,7 @@ struct rb_solver {
     void* peer_mapped[kMaxRanks] = {};
     unsigned long long* epochs = nullptr;   // [2] signal / wait counters + error flag
     int row_cell0 = 0, row_cells = 0;
-    // restarted GMRES for the finite-depth helium operator (host-driven, one synchronisation per iteration)
+    // restarted GMRES for the finite-depth helium operator (device-driven cycles; the host looks once per cycle outside recorded steps)
     bool use_gmres = false;
     int gm_m = 0;                  // restart length
     size_t gm_ld = 0;              // stride of the Krylov vectors (BN rounded up to 32: the real transforms of the preconditioner want
@@ -127,7 +127,7 @@ struct rb_solver {
     double *gm_V = nullptr, *gm_x = nullptr, *gm_t = nullptr, *gm_dev = nullptr, *gm_invP = nullptr;
     double* gm_host = nullptr;     // pinned
     // the same solver driven from the device inside recorded RK4 steps (krylov_kernels.cu: gm_*_kernel)
-    bool gm_device = false;
+    bool gm_device = false;        // recorded steps use the cycle too (RB_DEVICE_GMRES=0: helium steps are not recorded)
     GmMember* gm_members = nullptr;
     GmCtrl* gm_ctrl = nullptr;     // viewed as a SolveCtrl by the sweeps that skip themselves once the cycle has ended (first member: done)
     double* Mdense = nullptr;      // dense validation path, allocated on demand

@@ -106,6 +106,10 @@ struct GmCtrl {
     int k;                             // Arnoldi steps performed in this cycle
     int running;                       // scratch: members still running, counted during a kernel
     unsigned int ticket;               // scratch: member-level ticket
+    int k_total;                       // Arnoldi steps performed since the host cleared the block (all cycles of one solve)
+    int pad;
+    unsigned long long worst_bits;     // scratch: atomicMax accumulator of the members' residuals (non-negative doubles order as uint64)
+    double worst_rel;                  // largest true relative residual over the members at the start of the current cycle
 };
 
 // geometry of the surface, per point; all arrays are [batch][N]
@@ -285,15 +289,8 @@ void launch_geometry_guess(const Geometry& g, double2* phiprime_c, int N, int ba
                            double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl, double omega, double cK,
                            cudaStream_t st);
 // krylov_kernels.cu
-void launch_multi_dot(const double* V, size_t ldv, int nvec, const double* w, double* out, int n, cudaStream_t st);
-void launch_multi_axpy(double* w, const double* V, size_t ldv, int nvec, const double* h, double sign, int n, cudaStream_t st);
-void launch_combine(double* out, const double* V, size_t ldv, int nvec, const double* y, int n, cudaStream_t st);
-void launch_normalize(double* vout, const double* w, const double* nrm2, int n, cudaStream_t st);
 void launch_axpby(double* out, const double* a, double alpha, const double* b, int n, cudaStream_t st);
-void launch_precond_scale(double2* hat, const double* invP, int N, int n, cudaStream_t st);
 void launch_precond_scale_half(double2* half, const double* invP, int N, int batch, cudaStream_t st);
-void launch_real_to_complex(const double* x, double2* out, int n, cudaStream_t st);
-void launch_complex_to_real(const double2* c, double* out, double scale, int n, cudaStream_t st);
 void launch_gm_start(const double* b, const double* w, double* V0, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch,
                      double tol, cudaStream_t st);
 void launch_gm_arnoldi(double* V, size_t ldv, double* w, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch, int k,

@@ -383,13 +383,12 @@ rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     std::memset(s->h_ctrl, 0, 4 * sizeof(SolveCtrl));
 
     if (s->use_gmres) {
-        s->gm_m = std::max(2, std::min(env_int("RB_GMRES_RESTART", 60), N));
+        s->gm_m = std::max(2, std::min(env_int("RB_GMRES_RESTART", kGmMax), std::min(N, kGmMax)));   // Krylov vectors per cycle
         s->gm_ld = (BN + 31) / 32 * 32;
         s->gm_V = dmalloc<double>((size_t)(s->gm_m + 1) * s->gm_ld);
         s->gm_x = dmalloc<double>(BN);
         s->gm_t = dmalloc<double>(BN);
-        s->gm_dev = dmalloc<double>(4 * (s->gm_m + 4));
-        RB_CUDA(cudaMallocHost(&s->gm_host, 4 * (s->gm_m + 4) * sizeof(double)));
+        RB_CUDA(cudaMallocHost(&s->gm_host, std::max(sizeof(GmCtrl), sizeof(SolveCtrl))));
         s->gm_invP = dmalloc<double>(N);
         // flat-film symbol of M: 1/2 + (N/4pi) (e^{-2Hm} + e^{-2H(N-m)}) / (1 - e^{-2HN}),  H = depth
         std::vector<double> invP(N, 2.0);
@@ -651,7 +650,7 @@ static void account_solve(rb_solver* s) {
     s->num_solves++;
 }
 
-// ---- restarted GMRES(m), right-preconditioned, classical Gram-Schmidt with re-orthogonalisation -------------------------
+// ---- restarted GMRES, right-preconditioned, classical Gram-Schmidt with re-orthogonalisation (device-driven cycles) ------------
 // y = M x for the rows of this rank (published to every rank when sharded); x: any device vector, result in xbuf[1]
 // skip != nullptr: the sweep (and, row-sharded, the wait behind it) returns at once when skip->done is set (recorded GMRES cycle)
 static void apply_M(rb_solver* s, const SweepArgs& base, const double* x, SolveCtrl* skip = nullptr) {
@@ -680,102 +679,60 @@ static void apply_Pinv(rb_solver* s, const double* v, double* out) {
     cufft_check(cufftExecZ2D(s->plan_z2d, (cufftDoubleComplex*)half, (cufftDoubleReal*)out), "fft z2d");
 }
 
+// The restarted solver outside recorded steps (standalone rb_rhs / rb_vorticities, the batched RHS behind the finite-difference
+// Jacobian, the stepper's fallback): cycles of at most K Arnoldi steps run on the device exactly as inside a recorded step
+// (krylov_kernels.cu); the host looks ONCE per cycle (round 1: once per Arnoldi step, with the Givens rotations on the host).  Every
+// cycle starts from the TRUE residual b - M x of every member, each member stops on its own residual against its own ||b||, and
+// the solve ends when the worst member has converged -- or stagnated (the true residual after a whole cycle no better than half
+// the one before it and already <= 1e-10: the iteration sits on the round-off floor of this operator, eps x cond(M) with
+// cond ~ N / 2 pi for the thin film; same status as the Richardson solver's) -- or the cap on applications of M is reached.
 static void gmres_solve(rb_solver* s, const double2* Z) {
     cudaStream_t st = s->stream;
-    const int n = (int)s->BN, m = s->gm_m;
-    const size_t ld = s->gm_ld;
+    const int n = (int)s->BN;
     const double tol = s->props.tolerance;
-    double* V = s->gm_V;
     double* w = s->xbuf[1];
-    double* dh = s->gm_dev;            // [0..m+1] pass 1, [m+2..2m+3] pass 2, then norm, then y
-    double* hh = s->gm_host;
-    const int stride = m + 2;
     SweepArgs base = base_args(s, Z);
+    SolveCtrl* skip = reinterpret_cast<SolveCtrl*>(s->gm_ctrl);
 
     const double* warm = nullptr;
     if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
     launch_guess(s->b, warm, s->hist, s->gm_x, s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
     if (!warm && !s->hist.base) apply_Pinv(s, s->b, s->gm_x);   // cold start: x0 = P^{-1} b
+    RB_CUDA(cudaMemsetAsync(s->gm_ctrl, 0, sizeof(GmCtrl), st));
 
-    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
-    int applies = 0;
-    double rel = 1e300, bnorm = 0.0, prev_cycle_rel = 1e300;
-    bool converged = false, stagnated = false;
+    GmCtrl* hc = reinterpret_cast<GmCtrl*>(s->gm_host);          // pinned
+    const int K = std::max(1, std::min(kGmMax, s->gm_m));
     const int max_applies = s->props.max_iterations;
-    for (int restart = 0; restart < 50 && !converged && applies < max_applies; ++restart) {
-        // true residual r = b - M x
-        apply_M(s, base, s->gm_x);
-        applies++;
-        launch_axpby(V, s->b, -1.0, w, n, st);
-        launch_multi_dot(V, ld, 0, V, dh, n, st);           // dh[0] = r.r
-        launch_multi_dot(V, ld, 0, s->b, dh + 1, n, st);     // dh[1] = b.b
-        RB_CUDA(cudaMemcpyAsync(hh, dh, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    int applies = 0;
+    double rel = 1e300, prev_cycle_rel = 1e300;
+    bool converged = false, stagnated = false;
+    for (int cycle = 0; cycle < 64 && applies < max_applies; ++cycle) {
+        apply_M(s, base, s->gm_x);                                                  // w = M x
+        launch_gm_start(s->b, w, s->gm_V, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, tol, st);
+        RB_CUDA(cudaMemcpyAsync(hc, s->gm_ctrl, sizeof(GmCtrl), cudaMemcpyDeviceToHost, st));
         RB_CUDA(cudaStreamSynchronize(st));
-        const double beta = std::sqrt(hh[0]);
-        bnorm = std::sqrt(hh[1]);
-        rel = bnorm > 0 ? beta / bnorm : (beta == 0 ? 0.0 : 1e300);
-        if (!(rel == rel)) break;                             // NaN: give up, reported as not converged
-        if (rel <= tol) {
+        applies = 1 + cycle + hc->k_total;                                          // one residual per cycle + the Arnoldi steps so far
+        rel = hc->worst_rel;
+        if (!(rel == rel) || rel >= 1e300) break;                                   // NaN: give up, reported as failed
+        if (hc->done) {                                                             // every member's true residual <= tolerance
             converged = true;
             break;
         }
-        // the true residual after a whole restart cycle no better than half the one before it, and already <= 1e-10: the iteration
-        // sits on the round-off floor of this operator (eps x cond(M), cond ~ N / 2 pi for the thin film) -- same rule, same
-        // status as the Richardson solver's (solve_decide): accepted, reported as stagnated, never as converged
-        if (restart > 0 && rel <= 1e-10 && rel > 0.5 * prev_cycle_rel) {
+        if (cycle > 0 && rel <= 1e-10 && rel > 0.5 * prev_cycle_rel) {
             stagnated = true;
             break;
         }
         prev_cycle_rel = rel;
-        launch_normalize(V, V, dh, n, st);
-        std::fill(g.begin(), g.end(), 0.0);
-        g[0] = beta;
-        int k_used = 0;
-        for (int k = 0; k < m && applies < max_applies; ++k) {
-            apply_Pinv(s, V + (size_t)k * ld, s->gm_t);
-            apply_M(s, base, s->gm_t);                        // w = M P^{-1} v_k
-            applies++;
-            launch_multi_dot(V, ld, k + 1, w, dh, n, st);
-            launch_multi_axpy(w, V, ld, k + 1, dh, -1.0, n, st);
-            launch_multi_dot(V, ld, k + 1, w, dh + stride, n, st);
-            launch_multi_axpy(w, V, ld, k + 1, dh + stride, -1.0, n, st);
-            launch_multi_dot(V, ld, 0, w, dh + 2 * stride, n, st);
-            launch_normalize(V + (size_t)(k + 1) * ld, w, dh + 2 * stride, n, st);
-            RB_CUDA(cudaMemcpyAsync(hh, dh, (2 * stride + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
-            RB_CUDA(cudaStreamSynchronize(st));
-            for (int j = 0; j <= k; ++j) H[(size_t)j * m + k] = hh[j] + hh[stride + j];
-            H[(size_t)(k + 1) * m + k] = std::sqrt(std::max(0.0, hh[2 * stride]));
-            for (int j = 0; j < k; ++j) {                    // previous rotations
-                double a0 = H[(size_t)j * m + k], a1 = H[(size_t)(j + 1) * m + k];
-                H[(size_t)j * m + k] = cs[j] * a0 + sn[j] * a1;
-                H[(size_t)(j + 1) * m + k] = -sn[j] * a0 + cs[j] * a1;
-            }
-            double a0 = H[(size_t)k * m + k], a1 = H[(size_t)(k + 1) * m + k];
-            double d = std::hypot(a0, a1);
-            cs[k] = d > 0 ? a0 / d : 1.0;
-            sn[k] = d > 0 ? a1 / d : 0.0;
-            H[(size_t)k * m + k] = d;
-            H[(size_t)(k + 1) * m + k] = 0.0;
-            g[k + 1] = -sn[k] * g[k];
-            g[k] = cs[k] * g[k];
-            k_used = k + 1;
-            rel = std::fabs(g[k + 1]) / bnorm;
-            if (!(rel == rel) || rel <= tol) break;
+        const int Kc = std::min(K, max_applies - applies);
+        if (Kc < 1) break;
+        for (int k = 0; k < Kc; ++k) {
+            apply_Pinv(s, s->gm_V + (size_t)k * s->gm_ld, s->gm_t);
+            apply_M(s, base, s->gm_t, skip);                                        // w = M P^{-1} v_k (skips itself once the cycle has ended)
+            launch_gm_arnoldi(s->gm_V, s->gm_ld, w, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, k, Kc - 1, tol, st);
         }
-        if (k_used == 0) break;
-        for (int i = k_used - 1; i >= 0; --i) {               // back substitution
-            double acc = g[i];
-            for (int j = i + 1; j < k_used; ++j) acc -= H[(size_t)i * m + j] * y[j];
-            y[i] = acc / H[(size_t)i * m + i];
-        }
-        std::memcpy(hh, y.data(), k_used * sizeof(double));
-        double* dy = dh + 3 * stride;
-        RB_CUDA(cudaMemcpyAsync(dy, hh, k_used * sizeof(double), cudaMemcpyHostToDevice, st));
-        launch_combine(s->gm_t, V, ld, k_used, dy, n, st);
+        launch_gm_correction(s->gm_V, s->gm_ld, s->gm_t, s->gm_members, s->N, s->batch, st);
         apply_Pinv(s, s->gm_t, s->gm_t);
         launch_axpby(s->gm_x, s->gm_x, 1.0, s->gm_t, n, st);
-        RB_CUDA(cudaStreamSynchronize(st));                   // hh is reused by the next restart
-        if (rel == rel && rel <= tol) converged = true;       // estimate; CGS2 keeps it within round-off of the true residual
     }
     s->last_iters = applies;
     s->last_converged = converged ? 1 : 0;

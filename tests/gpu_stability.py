@@ -23,8 +23,13 @@ for N, h, dt, steps in ((4096, 0.4, 1e-3, 60), (16384, 0.4, 1e-3, 40), (65536, 0
     vals, its = [], []
     t0 = time.time()
     prev = calc.solve_stats()["total_iterations"]
+    blew = None
     for i in range(steps):
-        stp.runStep()
+        try:
+            stp.runStep()
+        except RuntimeError as e:      # strict mode: a solve on a surface that has blown up fails loudly
+            blew = f"step {i + 1}: {str(e)[:110]}"
+            break
         s = calc.solve_stats()
         its.append((s["total_iterations"] - prev) / 4.0); prev = s["total_iterations"]
         vals.append(hf(st, N))
@@ -33,6 +38,10 @@ for N, h, dt, steps in ((4096, 0.4, 1e-3, 60), (16384, 0.4, 1e-3, 40), (65536, 0
     el = time.time() - t0
     v = np.array(vals)
     g = np.log(v[-1] / v[max(0, len(v) // 2)]) / (dt * (len(v) - 1 - max(0, len(v) // 2))) if len(v) > 3 else float("nan")
+    if blew:
+        print(f"N={N} h={h} dt={dt}: BLEW UP at {blew}", flush=True)
+    if len(vals) == 0:
+        continue
     print(f"N={N} h={h} dt={dt}: steps={len(v)} hf[0]={v[0]:.2e} hf[-1]={v[-1]:.2e} growth_rate~{g:.1f}/unit time "
           f"iters/rhs first={its[0]:.1f} last={its[-1]:.1f} {len(v)/el:.2f} steps/s", flush=True)
     print("   hf:", " ".join(f"{x:.1e}" for x in v[::max(1, len(v)//12)]))
