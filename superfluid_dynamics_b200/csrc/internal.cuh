@@ -3,7 +3,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
-#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -25,43 +24,6 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
     }
 }
 #define RB_CUDA(x) ::rb::cuda_check((x), #x, __FILE__, __LINE__)
-
-// ---- programmatic dependent launch (sm_90+): every kernel of a recorded step is launched with the programmatic-stream-serialisation
-// attribute and begins with pdl_prologue(): it lets ITS successor be scheduled at once (launch_dependents) and then waits for its own
-// predecessor to complete and flush (wait) before touching any memory.  A step at N <= 8192 is ~50 launches of 3-40 us; the launch
-// latency and the prologue of each launch now overlap the tail of the one before it (the last CTA's serial epilogue).  RB_PDL=0
-// turns the attribute off (the prologue is then a no-op).  Kernels of other libraries (cuFFT) keep full serialisation on both sides.
-inline bool pdl_enabled() {
-    static const bool on = [] {
-        const char* v = std::getenv("RB_PDL");
-        return !v || std::atoi(v) != 0;
-    }();
-    return on;
-}
-
-__device__ __forceinline__ void pdl_prologue() {
-#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
-
-#ifdef __CUDACC__
-template <typename... KArgs, typename... Args>
-inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    cuda_check(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...), "cudaLaunchKernelEx", __FILE__, __LINE__);
-}
-#endif
 
 // number of kernels of this library launched since load (cuFFT's own kernels are not counted)
 extern unsigned long long g_launch_count;

@@ -9,14 +9,13 @@ namespace rb {
 // out = a + alpha * b   (alpha may be 0 to copy)
 __global__ void axpby_kernel(double* __restrict__ out, const double* __restrict__ a, double alpha, const double* __restrict__ b,
                              int n) {
-    pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = fma(alpha, b[i], a[i]);
 }
 
 void launch_axpby(double* out, const double* a, double alpha, const double* b, int n, cudaStream_t st) {
-    launch_k(axpby_kernel, dim3((n + 255) / 256), dim3(256), 0, st, out, a, alpha, b, n);
+    axpby_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, a, alpha, b, n);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -25,7 +24,6 @@ void launch_axpby(double* out, const double* a, double alpha, const double* b, i
 // symmetric, invP[m] == invP[N - m], so the half spectrum is all there is to scale); norm = 1/N folds the transform pair's
 // normalisation in
 __global__ void precond_scale_half_kernel(double2* __restrict__ half, const double* __restrict__ invP, int nh, int n, double norm) {
-    pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double s = invP[i % nh] * norm;
@@ -35,7 +33,7 @@ __global__ void precond_scale_half_kernel(double2* __restrict__ half, const doub
 
 void launch_precond_scale_half(double2* half, const double* invP, int N, int batch, cudaStream_t st) {
     const int nh = N / 2 + 1, n = nh * batch;
-    launch_k(precond_scale_half_kernel, dim3((n + 255) / 256), dim3(256), 0, st, half, invP, nh, n, 1.0 / N);
+    precond_scale_half_kernel<<<(n + 255) / 256, 256, 0, st>>>(half, invP, nh, n, 1.0 / N);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -98,7 +96,6 @@ __device__ bool last_member(GmCtrl* gc, int batch, int still_running) {
 __global__ void __launch_bounds__(kGmThreads) gm_start_kernel(const double* __restrict__ b, const double* __restrict__ w,
                                                                double* __restrict__ V0, GmMember* members, GmCtrl* gc,
                                                                SolveCtrl* ctrl, int N, int batch, double tol) {
-    pdl_prologue();
     __shared__ double sred[32 * 2];
     __shared__ double sums[2];
     const int m = blockIdx.x;
@@ -146,7 +143,6 @@ __global__ void __launch_bounds__(kGmThreads) gm_start_kernel(const double* __re
 __global__ void __launch_bounds__(kGmThreads) gm_arnoldi_kernel(double* __restrict__ V, size_t ldv, double* __restrict__ w,
                                                                  GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch,
                                                                  int k, int last_k, double tol) {
-    pdl_prologue();
     if (*reinterpret_cast<volatile int*>(&gc->done)) return;
     __shared__ double sred[32 * (kGmMax + 1)];
     __shared__ double h[kGmMax + 1], hsum[kGmMax + 1];
@@ -231,7 +227,6 @@ __global__ void __launch_bounds__(kGmThreads) gm_arnoldi_kernel(double* __restri
 // end of the cycle: y from the triangular system of each member's k_used columns, t = sum_j y_j v_j (the correction before P^-1)
 __global__ void __launch_bounds__(kGmThreads) gm_correction_kernel(const double* __restrict__ V, size_t ldv, double* __restrict__ t,
                                                                     GmMember* members, int N) {
-    pdl_prologue();
     __shared__ double y[kGmMax];
     const int m = blockIdx.x;
     const size_t off = (size_t)m * N;
@@ -255,20 +250,20 @@ __global__ void __launch_bounds__(kGmThreads) gm_correction_kernel(const double*
 
 void launch_gm_start(const double* b, const double* w, double* V0, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch,
                      double tol, cudaStream_t st) {
-    launch_k(gm_start_kernel, dim3(batch), dim3(kGmThreads), 0, st, b, w, V0, members, gc, ctrl, N, batch, tol);
+    gm_start_kernel<<<batch, kGmThreads, 0, st>>>(b, w, V0, members, gc, ctrl, N, batch, tol);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
 
 void launch_gm_arnoldi(double* V, size_t ldv, double* w, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch, int k,
                        int last_k, double tol, cudaStream_t st) {
-    launch_k(gm_arnoldi_kernel, dim3(batch), dim3(kGmThreads), 0, st, V, ldv, w, members, gc, ctrl, N, batch, k, last_k, tol);
+    gm_arnoldi_kernel<<<batch, kGmThreads, 0, st>>>(V, ldv, w, members, gc, ctrl, N, batch, k, last_k, tol);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
 
 void launch_gm_correction(const double* V, size_t ldv, double* t, GmMember* members, int N, int batch, cudaStream_t st) {
-    launch_k(gm_correction_kernel, dim3(batch), dim3(kGmThreads), 0, st, V, ldv, t, members, N);
+    gm_correction_kernel<<<batch, kGmThreads, 0, st>>>(V, ldv, t, members, N);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -179,7 +179,6 @@ __device__ __forceinline__ void geometry_point(const Geometry& g, double2* __res
 __global__ void geometry_kernel(Geometry g, double2* __restrict__ phiprime_c, int N, int batch, int ncell, int physics,
                                 double rhoM, double depth, int finite_image, int use_local, int raw_derivs, double rho,
                                 double U) {
-    pdl_prologue();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (size_t)N * batch) return;
     int b = (int)(tid / N);
@@ -191,7 +190,7 @@ void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, i
                      double depth, int finite_image, int use_local, int raw_derivs, double rho, double U, cudaStream_t st) {
     size_t n = (size_t)N * batch;
     int threads = 128;
-    launch_k(geometry_kernel, dim3((unsigned)((n + threads - 1) / threads)), dim3(threads), 0, st, g, phiprime_c, N, batch, ncell, physics, rhoM,
+    geometry_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(g, phiprime_c, N, batch, ncell, physics, rhoM,
                                                                                    depth, finite_image, use_local, raw_derivs,
                                                                                    rho, U);
     RB_CUDA(cudaGetLastError());
@@ -274,7 +273,6 @@ __global__ void __launch_bounds__(kCell) guess_kernel(const double* __restrict__
                                                        double* __restrict__ xsum_part, double* __restrict__ bnorm_part,
                                                        SolveCtrl* ctrl, double omega, int N, int ncell,
                                                        const double2* __restrict__ Zp, const double* __restrict__ Mdiag, double cK) {
-    pdl_prologue();
     __shared__ double sred[kCell];
     guess_cell(b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell, Zp, Mdiag, cK, sred);
 }
@@ -288,7 +286,6 @@ __global__ void __launch_bounds__(kCell) geometry_guess_kernel(Geometry g, doubl
                                                                 double* __restrict__ x0, double* __restrict__ xsum_part,
                                                                 double* __restrict__ bnorm_part, SolveCtrl* ctrl, double omega,
                                                                 double cK) {
-    pdl_prologue();
     __shared__ double sred[kCell];
     const int i = blockIdx.x * kCell + threadIdx.x;
     const int bm = blockIdx.y;
@@ -301,7 +298,7 @@ void launch_geometry_guess(const Geometry& g, double2* phiprime_c, int N, int ba
                            int finite_image, int use_local, double rho, double U, const double* warm, const HistoryRing& hist,
                            double* x0, double* xsum_part, double* bnorm_part, SolveCtrl* ctrl, double omega, double cK,
                            cudaStream_t st) {
-    launch_k(geometry_guess_kernel, dim3(dim3(ncell, batch)), dim3(kCell), 0, st, g, phiprime_c, N, ncell, rhoM, depth, finite_image, use_local, 1, rho,
+    geometry_guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(g, phiprime_c, N, ncell, rhoM, depth, finite_image, use_local, 1, rho,
                                                                 U, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, cK);
     RB_CUDA(cudaGetLastError());
     count_launch();
@@ -310,7 +307,7 @@ void launch_geometry_guess(const Geometry& g, double2* phiprime_c, int N, int ba
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st,
                   const double2* Zp, const double* Mdiag, double cK) {
-    launch_k(guess_kernel, dim3(dim3(ncell, batch)), dim3(kCell), 0, st, b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell, Zp, Mdiag,
+    guess_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(b, warm, hist, x0, xsum_part, bnorm_part, ctrl, omega, N, ncell, Zp, Mdiag,
                                                        cK);
     RB_CUDA(cudaGetLastError());
     count_launch();
@@ -325,7 +322,6 @@ __global__ void __launch_bounds__(kCell) finish_solve_kernel(const double* __res
                                                               const SolveCtrl* ctrl, double* __restrict__ a_out,
                                                               double2* __restrict__ a_complex, double* __restrict__ xsum_part,
                                                               HistoryRing hist, int N, int ncell, FinishPost post) {
-    pdl_prologue();
     __shared__ double sred[kCell];
     const int fb = (ctrl && ctrl->final_buf) ? 1 : 0;
     const double* src = fb ? buf1 : buf0;
@@ -395,19 +391,17 @@ void launch_finish_solve(const double* buf0, const double* buf1, const SolveCtrl
                          const double2* A0, const double2* A1, const FinishPost* post) {
     FinishPost p;
     if (post) p = *post;
-    launch_k(finish_solve_kernel, dim3(dim3(ncell, batch)), dim3(kCell), 0, st, buf0, buf1, A0, A1, ctrl, a_out, a_complex, xsum_part, hist, N,
+    finish_solve_kernel<<<dim3(ncell, batch), kCell, 0, st>>>(buf0, buf1, A0, A1, ctrl, a_out, a_complex, xsum_part, hist, N,
                                                               ncell, p);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
 
-__global__ void advance_counter_kernel(int* counter) {
-    pdl_prologue(); *counter += 1; }
+__global__ void advance_counter_kernel(int* counter) { *counter += 1; }
 
 // last kernel of a recorded RK4 step: advance the history counter and fold the four stage solves' control blocks into the chunk
 // aggregate (so that the host can launch several recorded steps back to back and look once)
 __global__ void step_end_kernel(int* counter, const SolveCtrl* __restrict__ ctrl_all, StepAgg* agg, int opt_mask) {
-    pdl_prologue();
     if (counter) *counter += 1;
     if (!agg) return;
     bool all_done = true, failed = false;
@@ -432,13 +426,13 @@ __global__ void step_end_kernel(int* counter, const SolveCtrl* __restrict__ ctrl
 }
 
 void launch_step_end(int* counter, const SolveCtrl* ctrl_all, StepAgg* agg, int opt_mask, cudaStream_t st) {
-    launch_k(step_end_kernel, dim3(1), dim3(1), 0, st, counter, ctrl_all, agg, opt_mask);
+    step_end_kernel<<<1, 1, 0, st>>>(counter, ctrl_all, agg, opt_mask);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
 
 void launch_advance_counter(int* counter, cudaStream_t st) {
-    launch_k(advance_counter_kernel, dim3(1), dim3(1), 0, st, counter);
+    advance_counter_kernel<<<1, 1, 0, st>>>(counter);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -556,7 +550,6 @@ __device__ __forceinline__ void tile_accumulate_far(const SrcEntry* __restrict__
 
 template <int MODE, bool IMAGE, int RPT>
 __global__ void __launch_bounds__(kCell / RPT, RPT == 4 ? 8 : (IMAGE ? 5 : 7)) sweep_kernel(const SweepArgs a) {
-    pdl_prologue();
     constexpr int THREADS = kCell / RPT;   // one CTA = one 256-row cell: THREADS threads x RPT rows
     __shared__ SrcEntry sh[kCell];
     __shared__ SrcEntry shI[IMAGE ? kCell : 1];
@@ -878,7 +871,6 @@ __global__ void __launch_bounds__(kCell / RPT, RPT == 4 ? 8 : (IMAGE ? 5 : 7)) s
 __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ctrl, int decide, int parity, int final_buf,
                                                         const double* __restrict__ bnorm_part, int ncell, double tol2,
                                                         int max_iters) {
-    pdl_prologue();
     const int lane = threadIdx.x;
     // decide == 1: the sweep before was launched with skip_if_done and has skipped itself (no signal was sent): nothing to wait
     // for.  decide == 2: that sweep always runs and signals (rb_bench_sweep), so its epoch must always be consumed -- returning
@@ -928,7 +920,7 @@ __global__ void __launch_bounds__(32) comm_wait_kernel(CommView c, SolveCtrl* ct
 
 void launch_comm_wait(const CommView& c, SolveCtrl* ctrl, int decide, int parity, int final_buf, const double* bnorm_part,
                       int ncell, double tol2, int max_iters, cudaStream_t st) {
-    launch_k(comm_wait_kernel, dim3(1), dim3(32), 0, st, c, ctrl, decide, parity, final_buf, bnorm_part, ncell, tol2, max_iters);
+    comm_wait_kernel<<<1, 32, 0, st>>>(c, ctrl, decide, parity, final_buf, bnorm_part, ncell, tol2, max_iters);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -938,13 +930,13 @@ static void launch_sweep_rpt(const SweepArgs& a, int mode, cudaStream_t st) {
     dim3 grid(a.row_cells, a.nchunks, a.batch);
     dim3 block(kCell / RPT);
     if (a.has_image) {
-        if (mode == kSweepMV) launch_k(sweep_kernel<kSweepMV, true, RPT>, dim3(grid), dim3(block), 0, st, a);
-        else if (mode == kSweepVEL) launch_k(sweep_kernel<kSweepVEL, true, RPT>, dim3(grid), dim3(block), 0, st, a);
+        if (mode == kSweepMV) sweep_kernel<kSweepMV, true, RPT><<<grid, block, 0, st>>>(a);
+        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, true, RPT><<<grid, block, 0, st>>>(a);
         else throw std::runtime_error("raw cotangent sum with image term is not defined");
     } else {
-        if (mode == kSweepMV) launch_k(sweep_kernel<kSweepMV, false, RPT>, dim3(grid), dim3(block), 0, st, a);
-        else if (mode == kSweepVEL) launch_k(sweep_kernel<kSweepVEL, false, RPT>, dim3(grid), dim3(block), 0, st, a);
-        else launch_k(sweep_kernel<kSweepRAW, false, RPT>, dim3(grid), dim3(block), 0, st, a);
+        if (mode == kSweepMV) sweep_kernel<kSweepMV, false, RPT><<<grid, block, 0, st>>>(a);
+        else if (mode == kSweepVEL) sweep_kernel<kSweepVEL, false, RPT><<<grid, block, 0, st>>>(a);
+        else sweep_kernel<kSweepRAW, false, RPT><<<grid, block, 0, st>>>(a);
     }
 }
 

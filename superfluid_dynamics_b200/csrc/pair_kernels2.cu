@@ -177,7 +177,6 @@ constexpr int kMaxStage = 1;   // staged entries per thread and tile (TS <= thre
 // registers 3.56 ms against 3.11 ms -- resident warps matter more than registers here)
 template <int MODE, int R, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT <= 256 ? 2 : 1) sweep2_kernel(const SweepArgs a) {
-    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x;
     const int TS = a.v2_TS;
@@ -515,7 +514,7 @@ static void launch_one(const SweepArgs& a, const Sweep2Launch& l, cudaStream_t s
         RB_CUDA(cudaFuncSetAttribute(sweep2_kernel<MODE, R, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
         configured = l.smem;
     }
-    launch_k(sweep2_kernel<MODE, R, MAXT>, dim3(l.grid), dim3(l.threads), l.smem, st, a);
+    sweep2_kernel<MODE, R, MAXT><<<l.grid, l.threads, l.smem, st>>>(a);
 }
 
 void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st) {

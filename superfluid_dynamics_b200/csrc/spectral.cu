@@ -34,7 +34,6 @@ __device__ __forceinline__ double2 d2_coeff(double2 c, int i, int n) {
 // Z - 2 pi j / N  and  Phi - (-(1+rho) pi U / N) j      (ZPhiDerivative ctor tables, L/Derivatives.cuh:282-287)
 __global__ void sub_linear_kernel(const double2* __restrict__ Z, const double2* __restrict__ Phi, double2* __restrict__ zper,
                                   double2* __restrict__ phiper, int N, size_t total, double rho, double U) {
-    pdl_prologue();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
     int i = (int)(tid % N);
@@ -51,7 +50,7 @@ __global__ void sub_linear_kernel(const double2* __restrict__ Z, const double2* 
 void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, double2* out_phiper, int N, int batch,
                        double rho, double U, cudaStream_t st) {
     size_t total = (size_t)N * batch;
-    launch_k(sub_linear_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, Z, Phi, out_zper, out_phiper, N, total, rho, U);
+    sub_linear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Z, Phi, out_zper, out_phiper, N, total, rho, U);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -60,7 +59,6 @@ void launch_sub_linear(const double2* Z, const double2* Phi, double2* out_zper, 
 __global__ void spectral_multiply_zphi_kernel(const double2* __restrict__ hatZ, const double2* __restrict__ hatPhi,
                                               double2* __restrict__ d1z, double2* __restrict__ d2z, double2* __restrict__ d1phi,
                                               int N, size_t total) {
-    pdl_prologue();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
     int i = (int)(tid % N);
@@ -73,7 +71,7 @@ __global__ void spectral_multiply_zphi_kernel(const double2* __restrict__ hatZ, 
 void launch_spectral_multiply_zphi(const double2* hatZ, const double2* hatPhi, double2* out_d1z, double2* out_d2z,
                                    double2* out_d1phi, int N, int batch, cudaStream_t st) {
     size_t total = (size_t)N * batch;
-    launch_k(spectral_multiply_zphi_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, hatZ, hatPhi, out_d1z, out_d2z, out_d1phi, N,
+    spectral_multiply_zphi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(hatZ, hatPhi, out_d1z, out_d2z, out_d1phi, N,
                                                                                    total);
     RB_CUDA(cudaGetLastError());
     count_launch();
@@ -81,7 +79,6 @@ void launch_spectral_multiply_zphi(const double2* hatZ, const double2* hatPhi, d
 
 __global__ void spectral_multiply_kernel(const double2* __restrict__ hat, double2* __restrict__ out, int N, size_t total,
                                          int second) {
-    pdl_prologue();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
     int i = (int)(tid % N);
@@ -91,7 +88,7 @@ __global__ void spectral_multiply_kernel(const double2* __restrict__ hat, double
 
 void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch, int second, cudaStream_t st) {
     size_t total = (size_t)N * batch;
-    launch_k(spectral_multiply_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, hat, out, N, total, second);
+    spectral_multiply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(hat, out, N, total, second);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -100,7 +97,6 @@ void launch_spectral_multiply(const double2* hat, double2* out, int N, int batch
 // Z2Z path is rebuilt with c[N-i] = conj(c[i]); `scale` (2 pi / N) is folded into the coefficients
 __global__ void spectral_multiply_real_kernel(const double2* __restrict__ half, double2* __restrict__ out, int N, size_t total,
                                               double scale) {
-    pdl_prologue();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
     const int nh = N / 2 + 1;
@@ -119,7 +115,7 @@ __global__ void spectral_multiply_real_kernel(const double2* __restrict__ half, 
 
 void launch_spectral_multiply_real(const double2* half, double2* out, int N, int batch, double scale, cudaStream_t st) {
     size_t total = (size_t)N * batch;
-    launch_k(spectral_multiply_real_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, half, out, N, total, scale);
+    spectral_multiply_real_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(half, out, N, total, scale);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -171,7 +167,6 @@ __device__ __forceinline__ double2* fft_stockham(double2* __restrict__ a, double
 __global__ void fft_zphi_kernel(const double2* __restrict__ Z, const double2* __restrict__ Phi, double2* __restrict__ Zp,
                                 double2* __restrict__ Zpp, double2* __restrict__ PhiP, int N, int logN,
                                 const double2* __restrict__ tw, double rho, double U) {
-    pdl_prologue();
     extern __shared__ double2 sm_fft[];
     double2* bufA = sm_fft;
     double2* bufB = sm_fft + N;
@@ -202,7 +197,6 @@ __global__ void fft_zphi_kernel(const double2* __restrict__ Z, const double2* __
 // a' = scale * D1(x) for a real vector x (one CTA per batch member); returns at once when the solve it belongs to is finished
 __global__ void fft_real_derivative_kernel(const double* __restrict__ x, double2* __restrict__ out, int N, int logN,
                                            const double2* __restrict__ tw, double scale, const SolveCtrl* ctrl) {
-    pdl_prologue();
     extern __shared__ double2 sm_fft[];
     if (ctrl && *reinterpret_cast<const volatile int*>(&ctrl->done)) return;
     double2* bufA = sm_fft;
@@ -233,7 +227,7 @@ void launch_fft_zphi(const double2* Z, const double2* Phi, double2* Zp, double2*
                      const double2* tw, double rho, double U, cudaStream_t st) {
     const size_t bytes = (size_t)(3 * N) * sizeof(double2);
     fft_smem_attr((const void*)fft_zphi_kernel, bytes);
-    launch_k(fft_zphi_kernel, dim3(dim3(Phi ? 3 : 2, batch)), dim3(fft_threads(N)), bytes, st, Z, Phi, Zp, Zpp, PhiP, N, logN, tw, rho, U);
+    fft_zphi_kernel<<<dim3(Phi ? 3 : 2, batch), fft_threads(N), bytes, st>>>(Z, Phi, Zp, Zpp, PhiP, N, logN, tw, rho, U);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -242,7 +236,7 @@ void launch_fft_real_derivative(const double* x, double2* out, int N, int logN, 
                                 const SolveCtrl* ctrl, cudaStream_t st) {
     const size_t bytes = (size_t)(3 * N) * sizeof(double2);
     fft_smem_attr((const void*)fft_real_derivative_kernel, bytes);
-    launch_k(fft_real_derivative_kernel, dim3(dim3(1, batch)), dim3(fft_threads(N)), bytes, st, x, out, N, logN, tw, scale, ctrl);
+    fft_real_derivative_kernel<<<dim3(1, batch), fft_threads(N), bytes, st>>>(x, out, N, logN, tw, scale, ctrl);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -250,7 +244,6 @@ void launch_fft_real_derivative(const double* x, double2* out, int N, int logN, 
 // scaling by 2 pi / N (resp. its square) and the linear parts put back (L/Derivatives.cuh:321-324, 374, 380-383)
 __global__ void finish_zphi_kernel(double2* __restrict__ Zp, double2* __restrict__ Zpp, double2* __restrict__ PhiP, int N,
                                    size_t total, double rho, double U) {
-    pdl_prologue();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= total) return;
     const double s1 = 2.0 * kPi / N;
@@ -270,13 +263,12 @@ __global__ void finish_zphi_kernel(double2* __restrict__ Zp, double2* __restrict
 
 void launch_finish_zphi(double2* Zp, double2* Zpp, double2* PhiP, int N, int batch, double rho, double U, cudaStream_t st) {
     size_t total = (size_t)N * batch;
-    launch_k(finish_zphi_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, Zp, Zpp, PhiP, N, total, rho, U);
+    finish_zphi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Zp, Zpp, PhiP, N, total, rho, U);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
 
 __global__ void scale_kernel(double2* __restrict__ v, double s, size_t n) {
-    pdl_prologue();
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n) return;
     double2 a = v[tid];
@@ -284,7 +276,7 @@ __global__ void scale_kernel(double2* __restrict__ v, double s, size_t n) {
 }
 
 void launch_scale(double2* v, double s, size_t n, cudaStream_t st) {
-    launch_k(scale_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, v, s, n);
+    scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, s, n);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -13,7 +13,6 @@ namespace rb {
 
 __global__ void stage_update_kernel(double2* __restrict__ y_out, const double2* __restrict__ y0, const double2* __restrict__ k,
                                     double c, size_t n) {
-    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double2 a = y0[i], b = k[i];
@@ -22,14 +21,13 @@ __global__ void stage_update_kernel(double2* __restrict__ y_out, const double2* 
 }
 
 void launch_stage_update(double2* y_out, const double2* y0, const double2* k, double c, size_t n, cudaStream_t st) {
-    launch_k(stage_update_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, y_out, y0, k, c, n);
+    stage_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y_out, y0, k, c, n);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
 
 __global__ void final_update_kernel(double2* __restrict__ y0, const double2* __restrict__ k1, const double2* __restrict__ k2,
                                     const double2* __restrict__ k3, const double2* __restrict__ k4, double h6, size_t n) {
-    pdl_prologue();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double2 a = k1[i], b = k2[i], c = k3[i], d = k4[i], y = y0[i];
@@ -41,7 +39,7 @@ __global__ void final_update_kernel(double2* __restrict__ y0, const double2* __r
 
 void launch_final_update(double2* y0, const double2* k1, const double2* k2, const double2* k3, const double2* k4, double h,
                          size_t n, cudaStream_t st) {
-    launch_k(final_update_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, y0, k1, k2, k3, k4, h / 6.0, n);
+    final_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(y0, k1, k2, k3, k4, h / 6.0, n);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }
