@@ -31,36 +31,28 @@ __device__ __forceinline__ double fast_rcp(double x) {
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ double2 ldcg_d2(const double2* p) { return __ldcg(p); }
 
-// deterministic block sum of n values from global memory (fixed thread count, fixed tree)
+// deterministic block reduction of one register value: fixed tree -- shuffles inside a warp, then every thread adds the warp sums
+// in warp order (two block barriers instead of one per tree level; the barriers of these reductions sit in the serial tail of a sweep)
 template <int THREADS>
-__device__ double block_sum_fixed(const double* p, int n, double* sred) {
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += THREADS) s += ldcg_d(p + i);
-    sred[threadIdx.x] = s;
-    __syncthreads();
+__device__ __forceinline__ double block_reduce_fixed(double v, double* sred) {
+    static_assert(THREADS % 32 == 0 && THREADS <= 1024, "whole warps");
 #pragma unroll
-    for (int w = THREADS / 2; w > 0; w >>= 1) {
-        if ((int)threadIdx.x < w) sred[threadIdx.x] += sred[threadIdx.x + w];
-        __syncthreads();
-    }
-    double r = sred[0];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) r += sred[w];
     __syncthreads();
     return r;
 }
 
-// deterministic block reduction of one register value
+// deterministic block sum of n values from global memory (fixed thread count, fixed tree)
 template <int THREADS>
-__device__ double block_reduce_fixed(double v, double* sred) {
-    sred[threadIdx.x] = v;
-    __syncthreads();
-#pragma unroll
-    for (int w = THREADS / 2; w > 0; w >>= 1) {
-        if ((int)threadIdx.x < w) sred[threadIdx.x] += sred[threadIdx.x + w];
-        __syncthreads();
-    }
-    double r = sred[0];
-    __syncthreads();
-    return r;
+__device__ __forceinline__ double block_sum_fixed(const double* p, int n, double* sred) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += THREADS) s += ldcg_d(p + i);
+    return block_reduce_fixed<THREADS>(s, sred);
 }
 
 // store a result at the same arena offset on every rank (single GPU: a plain store)
