@@ -129,6 +129,7 @@ struct rb_solver {
     // the same solver driven from the device inside recorded RK4 steps (krylov_kernels.cu: gm_*_kernel)
     bool gm_device = false;        // recorded steps use the cycle too (RB_DEVICE_GMRES=0: helium steps are not recorded)
     GmMember* gm_members = nullptr;
+    double* gm_part = nullptr;     // slice partials of the multi-CTA Arnoldi kernel
     GmCtrl* gm_ctrl = nullptr;     // viewed as a SolveCtrl by the sweeps that skip themselves once the cycle has ended (first member: done)
     double* Mdense = nullptr;      // dense validation path, allocated on demand
     int* lu_info = nullptr;

@@ -100,6 +100,8 @@ struct GmMember {
     double bnorm, rel, first_rel;
     int k_used;                        // columns this member's correction uses
     int running;                       // 0: this member's residual estimate met the tolerance (or broke down)
+    unsigned int bar;                  // arrivals at the in-kernel barriers of the CTAs that share this member (monotonic, never reset)
+    unsigned int gen;                  // Arnoldi steps this member has run since creation: base of the barrier targets (never reset)
 };
 struct GmCtrl {
     int done;                          // 1: the cycle has ended (every member finished, or the recorded iterations are used up)
@@ -293,8 +295,9 @@ void launch_axpby(double* out, const double* a, double alpha, const double* b, i
 void launch_precond_scale_half(double2* half, const double* invP, int N, int batch, cudaStream_t st);
 void launch_gm_start(const double* b, const double* w, double* V0, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch,
                      double tol, cudaStream_t st);
-void launch_gm_arnoldi(double* V, size_t ldv, double* w, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch, int k,
-                       int last_k, double tol, cudaStream_t st);
+void launch_gm_arnoldi(double* V, size_t ldv, double* w, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, double* part, int N, int batch,
+                       int k, int last_k, double tol, cudaStream_t st);
+int gm_arnoldi_slices(int N, int batch);   // CTAs per member of the Arnoldi kernel
 void launch_gm_correction(const double* V, size_t ldv, double* t, GmMember* members, int N, int batch, cudaStream_t st);
 // dense_kernels.cu
 void launch_create_M(double* A, const double2* Z, const double2* Zp, const double2* Zpp, double rho, int n, size_t batch,

@@ -139,52 +139,105 @@ __global__ void __launch_bounds__(kGmThreads) gm_start_kernel(const double* __re
 }
 
 // Arnoldi step k of every member still running: classical Gram-Schmidt twice (CGS2) of w = M P^-1 v_k against v_0..v_k, the new
-// Hessenberg column through the stored and one new Givens rotation, the residual estimate |g_{k+1}| / ||b||
-__global__ void __launch_bounds__(kGmThreads) gm_arnoldi_kernel(double* __restrict__ V, size_t ldv, double* __restrict__ w,
-                                                                 GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch,
-                                                                 int k, int last_k, double tol) {
+// Hessenberg column through the stored and one new Givens rotation, the residual estimate |g_{k+1}| / ||b||.
+// Grid = (C, batch): C CTAs share one member, each owning a contiguous slice of the vectors (its slice of w stays in registers);
+// the three reductions of the step (two projections, one norm) are slice partials in global memory, one in-kernel barrier over the
+// member's C CTAs each, and then EVERY CTA adds the C partials in slice order -- the same numbers everywhere, on every rank.
+// (Round-2 profile, one CTA per member: 150 us per step at N = 16384 -- replicated on every rank of a sharded run, where four sharded
+// image sweeps take 330 us: the step, not the sweep, bounded the helium film on 8 GPUs.)  The host picks C so that all C x batch CTAs
+// are co-resident (C = 1 for ensembles).
+constexpr int kGmSliceThreads = 256;
+constexpr int kGmSlice = 1024;                              // preferred elements per CTA (4 per thread)
+constexpr int kGmPartStride = 2 * (kGmMax + 1) + 2;          // per CTA: projections of pass 0 | of pass 1 | norm (separate slots: a fast CTA
+                                                            // may publish its next partial while a slow one still reads the previous ones)
+
+namespace {
+// barrier over the C CTAs of one member: monotonic arrival counter, target = arrivals expected so far
+__device__ __forceinline__ void member_barrier(unsigned int* bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (atomicAdd(bar, 0u) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kGmSliceThreads) gm_arnoldi_kernel(double* __restrict__ V, size_t ldv, double* __restrict__ w,
+                                                                      GmMember* members, GmCtrl* gc, SolveCtrl* ctrl,
+                                                                      double* __restrict__ part, int N, int batch, int k, int last_k,
+                                                                      double tol) {
     if (*reinterpret_cast<volatile int*>(&gc->done)) return;
     __shared__ double sred[32 * (kGmMax + 1)];
     __shared__ double h[kGmMax + 1], hsum[kGmMax + 1];
-    const int m = blockIdx.x;
+    const int C = gridDim.x, c = blockIdx.x, m = blockIdx.y;
     const size_t off = (size_t)m * N;
     GmMember* mem = members + m;
     const bool running = mem->running != 0;
+    const unsigned int gen = mem->gen;                      // Arnoldi steps this member has run so far: base of its barrier targets (read by every
+                                                            // CTA of the member before its first arrival; advanced by CTA 0 after the last barrier)
     if (running) {
         const int nv = k + 1;
+        const int S = (N + C - 1) / C;                      // this CTA's slice [lo, hi)
+        const int lo = c * S, hi = min(N, lo + S);
         if (threadIdx.x <= kGmMax) hsum[threadIdx.x] = 0.0;
+        double* mypart = part + ((size_t)m * C + c) * kGmPartStride;
+        const double* allpart = part + (size_t)m * C * kGmPartStride;
         for (int pass = 0; pass < 2; ++pass) {
             double acc[kGmMax + 1];
 #pragma unroll
             for (int j = 0; j <= kGmMax; ++j) acc[j] = 0.0;
-            for (int i = threadIdx.x; i < N; i += kGmThreads) {
+            for (int i = lo + threadIdx.x; i < hi; i += kGmSliceThreads) {
                 const double wi = w[off + i];
 #pragma unroll
                 for (int j = 0; j <= kGmMax; ++j)
                     if (j < nv) acc[j] = fma(V[(size_t)j * ldv + off + i], wi, acc[j]);
             }
             block_sums<kGmMax + 1>(acc, nv, sred, h);
-            for (int i = threadIdx.x; i < N; i += kGmThreads) {
+            if (C > 1) {
+                if ((int)threadIdx.x < nv) mypart[pass * (kGmMax + 1) + threadIdx.x] = h[threadIdx.x];
+                member_barrier(&mem->bar, (3u * gen + (unsigned)pass + 1u) * (unsigned)C);
+                if ((int)threadIdx.x < nv) {
+                    double t = 0.0;
+                    for (int cc = 0; cc < C; ++cc) t += __ldcg(allpart + (size_t)cc * kGmPartStride + pass * (kGmMax + 1) + threadIdx.x);
+                    h[threadIdx.x] = t;
+                }
+                __syncthreads();
+            }
+            for (int i = lo + threadIdx.x; i < hi; i += kGmSliceThreads) {
                 double wi = w[off + i];
 #pragma unroll
                 for (int j = 0; j <= kGmMax; ++j)
                     if (j < nv) wi = fma(-h[j], V[(size_t)j * ldv + off + i], wi);
-                w[off + i] = wi;
+                w[off + i] = wi;                            // (each thread re-reads only what it wrote itself)
             }
             if ((int)threadIdx.x < nv) hsum[threadIdx.x] += h[threadIdx.x];
             __syncthreads();
         }
         double nn[1] = {0.0};
-        for (int i = threadIdx.x; i < N; i += kGmThreads) {
+        for (int i = lo + threadIdx.x; i < hi; i += kGmSliceThreads) {
             const double wi = w[off + i];
             nn[0] = fma(wi, wi, nn[0]);
         }
         block_sums<1>(nn, 1, sred, h);
+        if (C > 1) {
+            if (threadIdx.x == 0) mypart[2 * (kGmMax + 1)] = h[0];
+            member_barrier(&mem->bar, (3u * gen + 3u) * (unsigned)C);
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int cc = 0; cc < C; ++cc) t += __ldcg(allpart + (size_t)cc * kGmPartStride + 2 * (kGmMax + 1));
+                h[0] = t;
+            }
+            __syncthreads();
+        }
         const double hk1 = sqrt(h[0]);
         const double inv = hk1 > 0.0 ? 1.0 / hk1 : 0.0;
         double* vn = V + (size_t)(k + 1) * ldv + off;
-        for (int i = threadIdx.x; i < N; i += kGmThreads) vn[i] = w[off + i] * inv;
-        if (threadIdx.x == 0) {
+        for (int i = lo + threadIdx.x; i < hi; i += kGmSliceThreads) vn[i] = w[off + i] * inv;
+        if (c == 0 && threadIdx.x == 0) {
             double col[kGmMax + 2];
             for (int j = 0; j <= k; ++j) col[j] = hsum[j];
             col[k + 1] = hk1;
@@ -195,24 +248,26 @@ __global__ void __launch_bounds__(kGmThreads) gm_arnoldi_kernel(double* __restri
             }
             const double a0 = col[k], a1 = col[k + 1];
             const double d = hypot(a0, a1);
-            const double c = d > 0.0 ? a0 / d : 1.0, sgn = d > 0.0 ? a1 / d : 0.0;
-            mem->cs[k] = c;
+            const double cr = d > 0.0 ? a0 / d : 1.0, sgn = d > 0.0 ? a1 / d : 0.0;
+            mem->cs[k] = cr;
             mem->sn[k] = sgn;
             col[k] = d;
             for (int j = 0; j <= k; ++j) mem->H[j * kGmMax + k] = col[j];
             const double gk = mem->g[k];
             mem->g[k + 1] = -sgn * gk;
-            mem->g[k] = c * gk;
+            mem->g[k] = cr * gk;
             double rel = mem->bnorm > 0.0 ? fabs(mem->g[k + 1]) / mem->bnorm : 0.0;
             if (!(rel == rel)) rel = 1e300;
             mem->rel = rel;
             mem->k_used = k + 1;
             if (rel <= tol || rel >= 1e300) mem->running = 0;
+            mem->gen = gen + 1u;
         }
         __syncthreads();
     }
-    const int still = running ? (members[m].running != 0 ? 1 : 0) : 0;
-    if (last_member(gc, batch, still) && threadIdx.x == 0) {
+    // the launch-level ticket counts every CTA (C x batch); a member is still running if its CTA 0 says so
+    const int still = (running && c == 0) ? (members[m].running != 0 ? 1 : 0) : 0;
+    if (last_member(gc, batch * C, still) && threadIdx.x == 0) {
         const int r = atomicAdd(&gc->running, 0);
         gc->k = k + 1;
         gc->k_total += 1;
@@ -255,9 +310,19 @@ void launch_gm_start(const double* b, const double* w, double* V0, GmMember* mem
     count_launch();
 }
 
-void launch_gm_arnoldi(double* V, size_t ldv, double* w, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, int N, int batch, int k,
-                       int last_k, double tol, cudaStream_t st) {
-    gm_arnoldi_kernel<<<batch, kGmThreads, 0, st>>>(V, ldv, w, members, gc, ctrl, N, batch, k, last_k, tol);
+int gm_arnoldi_slices(int N, int batch) {
+    // CTAs per member: all C x batch CTAs of a launch meet at in-kernel barriers (per member), so those of a member must be resident
+    // together: keep the whole launch within one CTA per SM
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int want = (N + kGmSlice - 1) / kGmSlice;
+    return std::max(1, std::min(want, sms / std::max(1, batch)));
+}
+
+void launch_gm_arnoldi(double* V, size_t ldv, double* w, GmMember* members, GmCtrl* gc, SolveCtrl* ctrl, double* part, int N, int batch,
+                       int k, int last_k, double tol, cudaStream_t st) {
+    const int C = gm_arnoldi_slices(N, batch);
+    gm_arnoldi_kernel<<<dim3(C, batch), kGmSliceThreads, 0, st>>>(V, ldv, w, members, gc, ctrl, part, N, batch, k, last_k, tol);
     RB_CUDA(cudaGetLastError());
     count_launch();
 }

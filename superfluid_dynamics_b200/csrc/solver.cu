@@ -42,7 +42,7 @@ void solver_free(rb_solver* s) {
                     s->arena, s->epochs, s->xsum_a, s->rnorm_part, s->bnorm_part,
                     s->energies, s->ac, s->aprime, s->vel_upper, s->partial, s->partial_img, s->gpartial, s->gpartial_img, s->group_tickets, s->cell_tickets,
                     s->member_tickets, s->ctrl_all, s->Mdense, s->lu_info, s->scratch_state, s->gm_V, s->gm_x, s->gm_t,
-                    s->gm_dev, s->gm_invP, s->gm_members, s->gm_ctrl, s->v2_rnorm_part, s->v2_ticket, s->fft_tw, s->v2_partial, s->v2_xs_part,
+                    s->gm_dev, s->gm_invP, s->gm_members, s->gm_ctrl, s->gm_part, s->v2_rnorm_part, s->v2_ticket, s->fft_tw, s->v2_partial, s->v2_xs_part,
                     s->v2_blk_tickets};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -403,6 +403,8 @@ rb_solver* solver_create(int N, int batch, const rb_props* pin) {
         }
         RB_CUDA(cudaMemcpy(s->gm_invP, invP.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         s->gm_device = env_int("RB_DEVICE_GMRES", 1) != 0;
+        // slice partials of the multi-CTA Arnoldi kernel: [batch][C][2 (kGmMax + 1) + 2]
+        s->gm_part = dmalloc<double>((size_t)batch * gm_arnoldi_slices(N, batch) * (2 * (kGmMax + 1) + 2));
         s->gm_members = dmalloc<GmMember>(batch);
         RB_CUDA(cudaMemset(s->gm_members, 0, (size_t)batch * sizeof(GmMember)));
         static_assert(sizeof(SolveCtrl) >= sizeof(GmCtrl) && offsetof(SolveCtrl, done) == offsetof(GmCtrl, done),
@@ -698,7 +700,7 @@ static void gmres_solve(rb_solver* s, const double2* Z) {
     if (s->props.guess_mode == RB_GUESS_WARM && !s->hist.base && s->have_prev_a) warm = s->a;
     launch_guess(s->b, warm, s->hist, s->gm_x, s->xsum_part[0], s->bnorm_part, s->ctrl, s->omega, s->N, s->batch, s->ncell, st);
     if (!warm && !s->hist.base) apply_Pinv(s, s->b, s->gm_x);   // cold start: x0 = P^{-1} b
-    RB_CUDA(cudaMemsetAsync(s->gm_ctrl, 0, sizeof(GmCtrl), st));
+    RB_CUDA(cudaMemsetAsync(&s->gm_ctrl->k_total, 0, sizeof(int), st));   // (the other fields are (re)set by gm_start_kernel)
 
     GmCtrl* hc = reinterpret_cast<GmCtrl*>(s->gm_host);          // pinned
     const int K = std::max(1, std::min(kGmMax, s->gm_m));
@@ -728,7 +730,7 @@ static void gmres_solve(rb_solver* s, const double2* Z) {
         for (int k = 0; k < Kc; ++k) {
             apply_Pinv(s, s->gm_V + (size_t)k * s->gm_ld, s->gm_t);
             apply_M(s, base, s->gm_t, skip);                                        // w = M P^{-1} v_k (skips itself once the cycle has ended)
-            launch_gm_arnoldi(s->gm_V, s->gm_ld, w, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, k, Kc - 1, tol, st);
+            launch_gm_arnoldi(s->gm_V, s->gm_ld, w, s->gm_members, s->gm_ctrl, s->ctrl, s->gm_part, s->N, s->batch, k, Kc - 1, tol, st);
         }
         launch_gm_correction(s->gm_V, s->gm_ld, s->gm_t, s->gm_members, s->N, s->batch, st);
         apply_Pinv(s, s->gm_t, s->gm_t);
@@ -1008,7 +1010,7 @@ static void rhs_gmres_recorded(rb_solver* s, const double2* state, double2* out)
     for (int k = 0; k < K; ++k) {
         apply_Pinv(s, s->gm_V + (size_t)k * s->gm_ld, s->gm_t);
         apply_M(s, base, s->gm_t, skip);                                            // w = M P^{-1} v_k
-        launch_gm_arnoldi(s->gm_V, s->gm_ld, w, s->gm_members, s->gm_ctrl, s->ctrl, s->N, s->batch, k, K - 1, tol_in, st);
+        launch_gm_arnoldi(s->gm_V, s->gm_ld, w, s->gm_members, s->gm_ctrl, s->ctrl, s->gm_part, s->N, s->batch, k, K - 1, tol_in, st);
     }
     launch_gm_correction(s->gm_V, s->gm_ld, s->gm_t, s->gm_members, s->N, s->batch, st);
     apply_Pinv(s, s->gm_t, s->gm_t);
