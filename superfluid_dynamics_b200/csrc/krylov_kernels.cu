@@ -68,7 +68,7 @@ __device__ void block_sums(double (&v)[NV], int nv, double* sred /* [32][NV] */,
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             if (j < nv) {
-                double x = sred[lane * NV + j];
+                double x = lane < (int)(blockDim.x >> 5) ? sred[lane * NV + j] : 0.0;   // (blocks of fewer than 32 warps)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
                 if (lane == 0) out[j] = x;
