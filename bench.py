@@ -347,12 +347,12 @@ def status_of(calc):
     return {k: s[k] for k in ("converged", "stagnated", "stagnated_solves", "failed_solves", "worst_residual")}
 
 
-def leg_sharded_water(ctx, api, N, steps, warm=30, compare_single=True, ref_gpu=None, peak=None):
+def leg_sharded_water(ctx, api, N, steps, warm=30, compare_single=True, ref_gpu=None, peak=None, dt=None):
     """Water surface of size N, row-sharded over the ranks of this run: steps/s (runSteps between one event pair), sweep roofline,
     replicas identical, difference to a single-GPU run of the same step count (rank 0)."""
     torch = ctx.torch
     props = api.ProblemProperties(rho=0.0)
-    dt = time_step(N)
+    dt = time_step(N) if dt is None else dt
     y0 = trochoid_state(N)
     calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props), device=ctx.dev, guess="warm")
     if ctx.world > 1:
@@ -700,6 +700,11 @@ def run_native(args):
         for n2 in (4096, 16384):
             if n2 != N and n2 // 256 >= world:
                 leg(f"n{n2}", lambda n2=n2: leg_sharded_water(ctx, api, n2, 200 if n2 <= 8192 else 40, ref_gpu=ref_gpu.get(n2), peak=peak))
+        if world == 1 and N == 65536:
+            # the headline's dt = 1e-4 is a round number below RK4's stability limit 2.83 (1 - h) / (h N / 2) = 1.3e-4 for this surface: the
+            # same run at 1.25e-4, the largest stable round step (the sweeps per RHS, hence the rate, depend on dt through the
+            # extrapolated start of the solve)
+            leg("n65536_dt1.25e-4", lambda: leg_sharded_water(ctx, api, 65536, 20, compare_single=False, peak=peak, dt=1.25e-4))
         leg("helium_n16384", lambda: leg_helium(ctx, api, peak))
         leg("ensemble_1024xN512", lambda: leg_ensemble(ctx, api, peak))
         if world == 1:
