@@ -233,12 +233,12 @@ int calculateRhsAugmentedOptomechanical(double* state, double* rhs_out, SimPrope
         host[N + i] = make_double2(state[2 * N + i], 0.0);
         host[2 * N + i] = make_double2(state[3 * N + i], 0.0);
     }
-    double2* d = dmalloc<double2>(6 * N);
+    device_ptr<double2> d_owner = dmalloc_scoped<double2>(6 * N);
+    double2* d = d_owner.get();
     RB_CUDA(cudaMemcpyAsync(d, host.data(), 3 * N * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
     aug_rhs(s.get(), v, d, d + 3 * N);
     RB_CUDA(cudaMemcpyAsync(host.data(), d + 3 * N, 3 * N * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
     RB_CUDA(cudaStreamSynchronize(s->stream));
-    cudaFree(d);
     for (size_t i = 0; i < N; ++i) {
         rhs_out[i] = host[i].x;
         rhs_out[N + i] = host[i].y;

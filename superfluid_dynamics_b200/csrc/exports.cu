@@ -46,12 +46,12 @@ static int rhs_from_vectors(const double* x, const double* y, const double* phi,
         host[i] = make_double2(x[i], y[i]);
         host[BN + i] = make_double2(phi[i], 0.0);
     }
-    double2* dstate = dmalloc<double2>(4 * BN);
+    device_ptr<double2> dstate_owner = dmalloc_scoped<double2>(4 * BN);
+    double2* dstate = dstate_owner.get();
     double2* drhs = dstate + 2 * BN;
     RB_CUDA(cudaMemcpy(dstate, host.data(), 2 * BN * sizeof(double2), cudaMemcpyHostToDevice));
     rhs(s.get(), dstate, drhs);
     RB_CUDA(cudaMemcpy(host.data(), drhs, 2 * BN * sizeof(double2), cudaMemcpyDeviceToHost));
-    cudaFree(dstate);
     for (size_t i = 0; i < BN; ++i) {
         vx[i] = host[i].x;
         vy[i] = host[i].y;
@@ -88,14 +88,14 @@ int calculateVorticities256FromVectors(const rb_complex* Z, const rb_complex* ph
     Adim ad = adimensionalize(L, rho, kappa, depth);
     rb_props p = helium_props(ad, false, 1, false);
     std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, 1, &p), solver_free);
-    double2* dstate = dmalloc<double2>(2 * N);
+    device_ptr<double2> dstate_owner = dmalloc_scoped<double2>(2 * N);
+    double2* dstate = dstate_owner.get();
     RB_CUDA(cudaMemcpy(dstate, Z, N * sizeof(double2), cudaMemcpyHostToDevice));
     RB_CUDA(cudaMemcpy(dstate + N, phi, N * sizeof(double2), cudaMemcpyHostToDevice));
     vorticities(s.get(), dstate);
     RB_CUDA(cudaMemcpy(a, s->a, N * sizeof(double), cudaMemcpyDeviceToHost));
     if (Zp) RB_CUDA(cudaMemcpy(Zp, s->Zp(), N * sizeof(double2), cudaMemcpyDeviceToHost));
     if (Zpp) RB_CUDA(cudaMemcpy(Zpp, s->Zpp(), N * sizeof(double2), cudaMemcpyDeviceToHost));
-    cudaFree(dstate);
     RB_CATCH
 }
 
@@ -105,11 +105,11 @@ int calculateDerivativeFFT256(const rb_complex* input, rb_complex* output) {
     rb_props p;
     rb_default_props(&p);
     std::unique_ptr<rb_solver, void (*)(rb_solver*)> s(solver_create((int)N, 1, &p), solver_free);
-    double2* d = dmalloc<double2>(2 * N);
+    device_ptr<double2> d_owner = dmalloc_scoped<double2>(2 * N);
+    double2* d = d_owner.get();
     RB_CUDA(cudaMemcpy(d, input, N * sizeof(double2), cudaMemcpyHostToDevice));
     fft_derivative(s.get(), d, d + N, 0, 1.0);   // L/Export.cu: FftDerivative<256,1>::exec(in, out)
     RB_CUDA(cudaMemcpy(output, d + N, N * sizeof(double2), cudaMemcpyDeviceToHost));
-    cudaFree(d);
     RB_CATCH
 }
 

@@ -47,6 +47,15 @@ inline T* dmalloc(size_t n) {
     return p;
 }
 
+// a device allocation that is released on every path out of its scope (the legacy exports allocate temporaries and may throw)
+struct DeviceFree {
+    void operator()(void* p) const { cudaFree(p); }
+};
+template <typename T>
+using device_ptr = std::unique_ptr<T, DeviceFree>;
+template <typename T>
+inline device_ptr<T> dmalloc_scoped(size_t n) { return device_ptr<T>(dmalloc<T>(n)); }
+
 inline int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return v ? std::atoi(v) : dflt;
