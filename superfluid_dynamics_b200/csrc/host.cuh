@@ -238,7 +238,7 @@ struct rb_stepper {
     // ~8 % of a step); a step that then runs out of sweeps is rolled back and redone as always, and tight recording is banned for a while
     bool tight_ok = true;
     bool tight = false;
-    int tight_hits = 0, tight_ban = 0;
+    int tight_hits = 0, tight_ban = 0, tight_max = 0;
     long long tight_failures = 0;
     long long graph_launches = 0, graph_captures = 0, fallback_steps = 0;
     cudaEvent_t ev = nullptr;

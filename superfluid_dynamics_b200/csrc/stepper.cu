@@ -283,11 +283,14 @@ void stepper_step(rb_stepper* st) {
             // ... and drop the last surplus round once the count has been the same for 8 steps in a row
             if (st->tight_ok && !st->tight && st->tight_ban == 0 && st->graph_sweeps - worst >= 1 && worst >= (s->use_gmres ? 3 : 2) &&
                 s->props.guess_mode == RB_GUESS_WARM) {
+                st->tight_max = st->tight_hits == 0 ? worst : std::max(st->tight_max, worst);   // the most any of these steps needed
                 if (++st->tight_hits >= 8) {
-                    st->graph_sweeps = worst;
-                    st->tight = true;
+                    if (st->tight_max < st->graph_sweeps) {
+                        st->graph_sweeps = st->tight_max;
+                        st->tight = true;
+                        invalidate_graphs(st);
+                    }
                     st->tight_hits = 0;
-                    invalidate_graphs(st);
                 }
             } else if (!st->tight) {
                 st->tight_hits = 0;
