@@ -27,6 +27,8 @@
 #else
 #include <cooperative_groups.h>
 
+#include <cstring>
+
 #include "internal.cuh"
 #endif
 #include "launch.cuh"
@@ -270,6 +272,183 @@ __global__ void __launch_bounds__(kClusterPanelThreads) lu_panel_cluster_kernel(
         A[(size_t)(k0 + c) * n + where] = P[idx];
     }
 }
+
+// ---- the panel on P co-resident CTAs that meet once per column at a barrier in global memory ---------------------------------------
+// Same algorithm as the cluster kernel above (rows never move, the pivot row is retired where it lies, LAPACK's interchanges are
+// replayed on index maps, the panel is written back in its final row order), without clusters: CTA c keeps rows
+// [c * kCoopRows, (c + 1) * kCoopRows) of the panel in its OWN shared memory (64 KB), and what the CTAs exchange per column goes
+// through L2: every CTA publishes its pivot candidate TOGETHER WITH that row's 32 panel entries (272 bytes), arrives at a monotonic
+// counter, spins until all P have arrived, and reads the P candidates -- the winner's record already holds the pivot row, so one
+// round trip per column is all there is.  Records are double-buffered by column parity.  P <= 128 CTAs of 256 threads are always
+// co-resident on a B200.  Measured (profiles/r02q_lu_panels.txt): ~4.4 us per column against ~12 us for the one-CTA kernel at n = 4096
+// (whose every access to the panel is a round trip to L2); whole factorisation 37 ms against 70 at n = 4096, 287 against 618 at
+// n = 12288, 3.8 against 8.3 at n = 512, equal at n = 700 ... 1300; the same pivots and the same solution in every case.
+constexpr int kCoopRows = 256;             // panel rows per CTA
+constexpr int kCoopThreads = 256;
+constexpr int kCoopMaxCtas = 128;          // panels of up to 32768 rows; 128 CTAs of 256 threads and 64 KB are co-resident on 148 SMs
+
+struct CoopCand {
+    double val;
+    int row, pos;
+    double entries[kNB];
+};
+
+__global__ void __launch_bounds__(kCoopThreads) lu_panel_coop_kernel(double* __restrict__ A, int n, int k0, int kb, int* __restrict__ piv,
+                                                                     int* __restrict__ info, CoopCand* __restrict__ cands /* [2][P] */,
+                                                                     unsigned int* bar, unsigned int bar_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* P = reinterpret_cast<double*>(smem_raw);                 // [kNB][kCoopRows]
+    __shared__ int slot[kCoopRows];                                   // -1 active, j: retired as pivot of column j
+    __shared__ PivotCand wcand[kCoopThreads / 32];
+    __shared__ double s_row[kNB];
+    __shared__ int pos_top[kNB], loc_top[kNB], s_p[2];
+    constexpr int rpc = kCoopRows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncta = gridDim.x, rank = blockIdx.x;
+    const int row0 = k0 + rank * rpc;
+    const int nloc = max(0, min(rpc, n - row0));
+    for (int idx = tid; idx < kb * rpc; idx += kCoopThreads) {
+        const int c = idx / rpc, r = idx - c * rpc;
+        P[idx] = r < nloc ? A[(size_t)(k0 + c) * n + row0 + r] : 0.0;
+    }
+    for (int r = tid; r < rpc; r += kCoopThreads) slot[r] = -1;
+    if (tid < kNB) {
+        pos_top[tid] = k0 + tid;
+        loc_top[tid] = k0 + tid;
+    }
+    __syncthreads();
+    PivotCand mine;
+    mine.val = -1.0; mine.row = -1; mine.pos = 0x7fffffff;
+    for (int r = tid; r < nloc; r += kCoopThreads) {
+        const double v = fabs(P[r]);
+        if (v > mine.val) { mine.val = v; mine.row = row0 + r; mine.pos = row0 + r; }
+    }
+    for (int j = 0; j < kb; ++j) {
+        const int buf = j & 1;
+        // ---- this CTA's candidate ----
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, mine.val, o);
+            const int orow = __shfl_down_sync(0xffffffffu, mine.row, o);
+            const int opos = __shfl_down_sync(0xffffffffu, mine.pos, o);
+            if (ov > mine.val || (ov == mine.val && opos < mine.pos)) { mine.val = ov; mine.row = orow; mine.pos = opos; }
+        }
+        if (lane == 0) wcand[warp] = mine;
+        __syncthreads();
+        if (warp == 0) {
+            PivotCand c = lane < kCoopThreads / 32 ? wcand[lane] : PivotCand{-1.0, -1, 0x7fffffff};
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, c.val, o);
+                const int orow = __shfl_down_sync(0xffffffffu, c.row, o);
+                const int opos = __shfl_down_sync(0xffffffffu, c.pos, o);
+                if (ov > c.val || (ov == c.val && opos < c.pos)) { c.val = ov; c.row = orow; c.pos = opos; }
+            }
+            c.val = __shfl_sync(0xffffffffu, c.val, 0);
+            c.row = __shfl_sync(0xffffffffu, c.row, 0);
+            c.pos = __shfl_sync(0xffffffffu, c.pos, 0);
+            // publish: (value, row, position) and the candidate row's panel entries
+            CoopCand* out = cands + (size_t)buf * ncta + rank;
+            if (lane == 0) { out->val = c.val; out->row = c.row; out->pos = c.pos; }
+            if (lane < kb) out->entries[lane] = c.row >= 0 ? P[(size_t)lane * rpc + (c.row - row0)] : 0.0;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(bar, 1u);
+                const unsigned int target = bar_base + (unsigned)(j + 1) * (unsigned)ncta;
+                while (atomicAdd(bar, 0u) < target) {
+                }
+                __threadfence();
+            }
+            __syncwarp();
+            // ---- the winner, identically on every CTA ----
+            PivotCand w{-1.0, -1, 0x7fffffff};
+            int wcta = lane;
+            for (int c2 = lane; c2 < ncta; c2 += 32) {
+                const CoopCand* cc = cands + (size_t)buf * ncta + c2;
+                const double v = __ldcg(&cc->val);
+                const int vpos = __ldcg(&cc->pos);
+                if (v > w.val || (v == w.val && vpos < w.pos)) { w.val = v; w.row = __ldcg(&cc->row); w.pos = vpos; wcta = c2; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_down_sync(0xffffffffu, w.val, o);
+                const int orow = __shfl_down_sync(0xffffffffu, w.row, o);
+                const int opos = __shfl_down_sync(0xffffffffu, w.pos, o);
+                const int octa = __shfl_down_sync(0xffffffffu, wcta, o);
+                if (ov > w.val || (ov == w.val && opos < w.pos)) { w.val = ov; w.row = orow; w.pos = opos; wcta = octa; }
+            }
+            w.val = __shfl_sync(0xffffffffu, w.val, 0);
+            w.row = __shfl_sync(0xffffffffu, w.row, 0);
+            w.pos = __shfl_sync(0xffffffffu, w.pos, 0);
+            wcta = __shfl_sync(0xffffffffu, wcta, 0);
+            const bool usable = w.val > 0.0;
+            int q = w.row, qpos = w.pos;
+            if (usable) {
+                if (lane < kb) s_row[lane] = __ldcg(&(cands + (size_t)buf * ncta + wcta)->entries[lane]);
+            } else {
+                // zero (or NaN) column: singular as getrf reports it; "pivot" = the row at the diagonal position, no elimination
+                q = pos_top[j];
+                qpos = k0 + j;
+                if (lane < kb) s_row[lane] = 0.0;
+            }
+            if (lane == 0) {
+                s_p[0] = q;
+                s_p[1] = usable ? 1 : 0;
+                const int u = pos_top[j];
+                if (qpos - k0 < kb) pos_top[qpos - k0] = u;
+                loc_top[u - k0] = qpos;
+                if (q - k0 < kb) loc_top[q - k0] = k0 + j;
+                pos_top[j] = q;
+                if (rank == 0) {
+                    piv[k0 + j] = qpos;
+                    if (!usable && *info == 0) *info = k0 + j + 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int q = s_p[0];
+        const bool usable = s_p[1] != 0;
+        if (tid == 0 && q >= row0 && q < row0 + nloc) slot[q - row0] = j;
+        __syncthreads();
+        mine.val = -1.0; mine.row = -1; mine.pos = 0x7fffffff;
+        if (usable) {
+            const double pv = s_row[j];
+            double* Pj = P + (size_t)j * rpc;
+            for (int r = tid; r < nloc; r += kCoopThreads) {
+                if (slot[r] >= 0) continue;
+                const double l = Pj[r] / pv;
+                Pj[r] = l;
+                for (int c = j + 1; c < kb; ++c) P[(size_t)c * rpc + r] = fma(-l, s_row[c], P[(size_t)c * rpc + r]);
+                if (j + 1 < kb) {
+                    const double v = fabs(P[(size_t)(j + 1) * rpc + r]);
+                    const int phys = row0 + r;
+                    const int ps = (phys - k0 < kb) ? loc_top[phys - k0] : phys;
+                    if (v > mine.val || (v == mine.val && ps < mine.pos)) { mine.val = v; mine.row = phys; mine.pos = ps; }
+                }
+            }
+        } else if (j + 1 < kb) {
+            for (int r = tid; r < nloc; r += kCoopThreads) {
+                if (slot[r] >= 0) continue;
+                const double v = fabs(P[(size_t)(j + 1) * rpc + r]);
+                const int phys = row0 + r;
+                const int ps = (phys - k0 < kb) ? loc_top[phys - k0] : phys;
+                if (v > mine.val || (v == mine.val && ps < mine.pos)) { mine.val = v; mine.row = phys; mine.pos = ps; }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- write the panel back in its final row order (every CTA has loaded its rows long ago: it passed the first barrier) ----
+    for (int idx = tid; idx < kb * rpc; idx += kCoopThreads) {
+        const int c = idx / rpc, r = idx - c * rpc;
+        if (r >= nloc) continue;
+        const int phys = row0 + r;
+        const int sj = slot[r];
+        const int where = sj >= 0 ? k0 + sj : ((phys - k0 < kb) ? loc_top[phys - k0] : phys);
+        A[(size_t)(k0 + c) * n + where] = P[idx];
+    }
+}
 #endif   // RB_EMULATE
 
 // column c of the augmented matrix [A | b]: c == n addresses b
@@ -475,12 +654,25 @@ bool try_cluster_panel(double* A, int n, int k0, int kb, int* piv, int* info, cu
 // n = 257 ... 7000, clusters of 8 and 16), but NOT faster than the one-CTA panel -- n = 1536: 26 ms against 17, n = 4096: 70 against 67,
 // n = 6144: 145 against 165, and erratic from call to call (72 ... 600 ms at n = 4096; a launch of one 8-CTA cluster with > 100 KB
 // of dynamic shared memory per CTA between small ordinary launches appears to cost far more than the kernel itself).  It is therefore
-// opt-in (RB_LU_CLUSTER_PANEL=1); the default panel is the one-CTA kernel.
+// opt-in (RB_LU_PANEL=cluster, or the older RB_LU_CLUSTER_PANEL=1); the default panel is the cooperative kernel above.
 bool cluster_panels_enabled() {
     const char* v = std::getenv("RB_LU_CLUSTER_PANEL");
     return v && std::atoi(v) != 0;
 }
 
+}  // namespace
+#endif
+
+#ifndef RB_EMULATE
+namespace {
+// which panel kernel: RB_LU_PANEL = coop (default: P CTAs meeting through L2), one (one CTA), cluster (distributed shared memory)
+int panel_choice() {
+    const char* v = std::getenv("RB_LU_PANEL");
+    if (v && !std::strcmp(v, "one")) return 0;
+    if (v && !std::strcmp(v, "cluster")) return 2;
+    if (cluster_panels_enabled()) return 2;
+    return 1;
+}
 }  // namespace
 #endif
 
@@ -490,12 +682,35 @@ void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) 
     RB_CUDA(cudaMallocAsync(&piv, (size_t)std::max(n, 1) * sizeof(int), st));
     RB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     int launches = 0;
+#ifndef RB_EMULATE
+    const int choice = panel_choice();
+    CoopCand* cands = nullptr;
+    unsigned int* bar = nullptr;
+    unsigned int bar_total = 0;
+    if (choice == 1) {
+        static bool configured = false;
+        if (!configured) {
+            RB_CUDA(cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNB * kCoopRows * (int)sizeof(double)));
+            configured = true;
+        }
+        RB_CUDA(cudaMallocAsync(&cands, (size_t)2 * kCoopMaxCtas * sizeof(CoopCand), st));
+        RB_CUDA(cudaMallocAsync(&bar, sizeof(unsigned int), st));
+        RB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+    }
+#endif
     for (int k0 = 0; k0 < n; k0 += kNB) {
         const int kb = std::min(kNB, n - k0);
         bool done = false;
 #ifndef RB_EMULATE
-        // the panel in the distributed shared memory of a cluster of 8 CTAs (16 when the panel is too tall for 8), else one CTA
-        if (cluster_panels_enabled() && n - k0 >= 256) {
+        const int m_panel = n - k0;
+        const int ncta = (m_panel + kCoopRows - 1) / kCoopRows;
+        if (choice == 1 && m_panel > kCoopRows && ncta <= kCoopMaxCtas) {
+            // P co-resident CTAs, one barrier through L2 per column (a panel of <= 256 rows is one CTA's work anyway)
+            lu_panel_coop_kernel<<<ncta, kCoopThreads, kNB * kCoopRows * sizeof(double), st>>>(A, n, k0, kb, piv, info, cands, bar, bar_total);
+            bar_total += (unsigned)ncta * (unsigned)kb;
+            done = true;
+        } else if (choice == 2 && m_panel >= 256) {
+            // the panel in the distributed shared memory of a cluster of 8 CTAs (16 when the panel is too tall for 8)
             done = try_cluster_panel<8>(A, n, k0, kb, piv, info, st);
             if (!done) done = try_cluster_panel<16>(A, n, k0, kb, piv, info, st);
         }
@@ -514,6 +729,10 @@ void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) 
     }
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(piv, st);
+#ifndef RB_EMULATE
+    if (cands) cudaFreeAsync(cands, st);
+    if (bar) cudaFreeAsync(bar, st);
+#endif
     RB_CUDA(e);
     count_launch(launches);
 }

@@ -19,7 +19,7 @@ A = rng.standard_normal((n, n)) + 4.0 * np.eye(n)
 b = rng.standard_normal(n)
 Af = torch.as_tensor(np.asfortranarray(A).ravel(order="F"), device=dev)
 bf = torch.as_tensor(b, device=dev)
-for rep in range(3):
+for rep in range(int(os.environ.get("REPS", "5"))):
     dA, db = Af.clone(), bf.clone()
     torch.cuda.synchronize()
     t0 = time.perf_counter()

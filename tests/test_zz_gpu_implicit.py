@@ -246,26 +246,47 @@ def test_lu_solve_against_lapack(api, n, blocked):
     assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("n", [300, 1536, 4100, 7000])
-def test_blocked_lu_with_cluster_panels_at_large_n(api, n):
-    """The panel in the distributed shared memory of a thread-block cluster (lu_panel_cluster_kernel): 8 CTAs up to ~6600 rows, 16
-    above (n = 7000), odd sizes, pivoting in every column; against LAPACK as above."""
+@pytest.mark.parametrize("panel", ["coop", "one", "cluster"])
+@pytest.mark.parametrize("n", [300, 1536, 4100, 7000, 8500])
+def test_blocked_lu_panel_variants_at_large_n(api, n, panel):
+    """The three panel kernels of the blocked LU (RB_LU_PANEL, read per factorisation): "coop" (default; lu_panel_coop_kernel, P CTAs of
+    256 rows meeting once per column at a barrier in L2: 2 CTAs at n = 300, 34 at n = 8500, i.e. more than one candidate per lane in
+    the winner search), "one" (one CTA) and "cluster" (distributed shared memory: 8 CTAs up to ~6600 rows, 16 above).  Odd sizes,
+    pivoting in every column; against LAPACK as above."""
+    if panel == "cluster" and n > 7000:
+        pytest.skip("a cluster of 16 CTAs holds panels of up to ~13000 rows only in theory; covered up to 7000")
     rng = np.random.default_rng(n)
     A = rng.standard_normal((n, n))
     x_true = rng.standard_normal(n)
     b = A @ x_true
     dA = T(np.asfortranarray(A).ravel(order="F")).clone()
     db = T(b).clone()
-    os.environ["RB_LU_CLUSTER_PANEL"] = "1"      # opt-in (measured not faster than the one-CTA panel): read per factorisation
+    os.environ["RB_LU_PANEL"] = panel
     try:
         assert api.lu_solve(dA, db, n, 1) == 0
     finally:
-        os.environ.pop("RB_LU_CLUSTER_PANEL", None)
+        os.environ.pop("RB_LU_PANEL", None)
     x = db.cpu().numpy()
     back = np.abs(A @ x - b).max() / (np.abs(A).sum(axis=1).max() * np.abs(x).max())
     assert back <= 1e-13 * n, back
     ref = np.linalg.solve(A, b)
     assert np.abs(x - ref).max() <= 1e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("panel", ["coop", "one"])
+def test_lu_panel_variants_report_a_singular_column_in_a_tall_panel(api, panel):
+    """A zero column met while the panel spans several CTAs: info = column + 1 from every panel kernel (getrf's convention)."""
+    n, col = 1200, 333
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((n, n))
+    A[:, col] = 0.0
+    dA = T(np.asfortranarray(A).ravel(order="F")).clone()
+    db = T(rng.standard_normal(n)).clone()
+    os.environ["RB_LU_PANEL"] = panel
+    try:
+        assert api.lu_solve(dA, db, n, 1) == col + 1
+    finally:
+        os.environ.pop("RB_LU_PANEL", None)
 
 
 @pytest.mark.parametrize("blocked", [0, 1])
