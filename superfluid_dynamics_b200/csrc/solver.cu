@@ -421,10 +421,11 @@ rb_solver* solver_create(int N, int batch, const rb_props* pin) {
     if (s->use_gmres)
         cufft_check(cufftPlanMany(&s->plan_z2d, 1, n, nullptr, 1, N / 2 + 1, nullptr, 1, N, CUFFT_Z2D, batch), "cufftPlanMany(Z2D)");
     s->plans = true;
-    // the one-CTA radix-2 transform is shared-memory-bandwidth bound (~1.3k cycles per pass at N = 4096): it beats the library's
-    // three launches only in the launch-bound regime (measured: faster at N <= 1024, slower at N = 4096)
-    const int own_fft_max = env_int("RB_OWN_FFT_MAX", 1024);
-    if ((N & (N - 1)) == 0 && N >= 4 && N <= 4096 && (long)N * batch <= 4096 && env_int("RB_OWN_FFT", 1)) {
+    // Own one-CTA transforms fused with the coefficient multiply (spectral.cu): radix-2 Stockham below N = 256, the radix-8
+    // register-resident transform for 256 <= N <= 8192.  (The radix-2 one is shared-memory-bandwidth bound, ~1.3k cycles per pass at
+    // N = 4096, and lost against the library's launches above N = 1024; the radix-8 one needs 4 passes there.)
+    const int own_fft_max = env_int("RB_OWN_FFT_MAX", 8192);
+    if ((N & (N - 1)) == 0 && N >= 4 && N <= 8192 && (long)N * batch <= 8192 && env_int("RB_OWN_FFT", 1)) {
         // up to own_fft_max the fused kernels replace the library everywhere; above it they are only used for the a' of the
         // surplus (normally skipped) rounds of a recorded step, because they can skip themselves and the library cannot
         s->own_fft = N <= own_fft_max;

@@ -217,6 +217,188 @@ __global__ void fft_real_derivative_kernel(const double* __restrict__ x, double2
     for (int i = threadIdx.x; i < N; i += blockDim.x) out[off + i] = r[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Radix-8 register-resident transform for 256 <= N <= 8192 (N a power of two): N/8 threads, every thread owns the 8 elements at
+// positions j + r N/8 for the WHOLE derivative (forward transform, coefficient multiply, inverse transform).  Stockham autosort
+// with passes of radix 2^(log2 N mod 3) (first, trivial twiddles, done on the registers the thread already holds) and radix 8
+// (ceil-free: 4 passes at N = 4096 against 12 radix-2 passes); between passes the results are exchanged through ONE padded
+// shared-memory array (position p lives at p + p/8: the stride-8 scatter of the early passes is conflict-free), two barriers per
+// exchange.  The last pass leaves the natural-order result in exactly the register layout the first pass of the next transform
+// reads, and global memory is read and written straight from / to registers (coalesced: consecutive threads, consecutive elements).
+// Twiddles: the seven factors exp(-2 pi i r k / (8 Ns)) of a butterfly are table entries (half circle per pass staged in shared
+// memory, 4 Ns entries), not products.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// multiplication by -i (forward) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ double2 mul_mi(double2 a) { return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x); }
+
+template <bool INV>
+__device__ __forceinline__ void dft4(double2& a0, double2& a1, double2& a2, double2& a3) {
+    const double2 s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = mul_mi<INV>(csub(a1, a3));
+    a0 = cadd(s02, s13);
+    a1 = cadd(d02, d13);
+    a2 = csub(s02, s13);
+    a3 = csub(d02, d13);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft8(double2 (&v)[8]) {
+    dft4<INV>(v[0], v[2], v[4], v[6]);   // even part -> E0..E3 in v[0], v[2], v[4], v[6]
+    dft4<INV>(v[1], v[3], v[5], v[7]);   // odd part  -> O0..O3 in v[1], v[3], v[5], v[7]
+    constexpr double h = 0.70710678118654752440;
+    // W8^k O_k, W8 = exp(-+ 2 pi i / 8)
+    const double2 o0 = v[1];
+    const double2 o1 = INV ? make_double2(h * (v[3].x - v[3].y), h * (v[3].x + v[3].y)) : make_double2(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));
+    const double2 o2 = mul_mi<INV>(v[5]);
+    const double2 o3 = INV ? make_double2(-h * (v[7].x + v[7].y), h * (v[7].x - v[7].y)) : make_double2(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));
+    const double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    v[0] = cadd(e0, o0);
+    v[1] = cadd(e1, o1);
+    v[2] = cadd(e2, o2);
+    v[3] = cadd(e3, o3);
+    v[4] = csub(e0, o0);
+    v[5] = csub(e1, o1);
+    v[6] = csub(e2, o2);
+    v[7] = csub(e3, o3);
+}
+
+__device__ __forceinline__ int fft8_pad(int p) { return p + (p >> 3); }
+
+// number of staged twiddles: 4 Ns per radix-8 pass (N = 8192: 4680 entries; data + twiddles = 222 KB of shared memory)
+__host__ __device__ inline int fft8_twiddle_count(int N, int logN) {
+    int n = 0;
+    for (int Ns = 1 << (logN % 3); Ns * 8 <= N; Ns <<= 3) n += 4 * Ns;
+    return n;
+}
+
+// tw: the per-pass table of solver_create (exp(-i pi k / Ns') at offset Ns' - 1); the radix-8 pass at Ns uses Ns' = 4 Ns:
+// exp(-2 pi i m / (8 Ns)), m < 4 Ns (the other half of the circle is its negative)
+__device__ __forceinline__ void fft8_stage_twiddles(double2* stw, const double2* __restrict__ tw, int N, int logN) {
+    int off = 0;
+    for (int Ns = 1 << (logN % 3); Ns * 8 <= N; Ns <<= 3) {
+        for (int k = threadIdx.x; k < 4 * Ns; k += blockDim.x) stw[off + k] = tw[4 * Ns - 1 + k];
+        off += 4 * Ns;
+    }
+}
+
+// exp(-+ 2 pi i m / (8 Ns)) for m < 8 Ns from the staged half circle: every factor is a correctly rounded table entry (products of
+// twiddles would put 2-3 ulp of noise on every mode -- visible in Zpp, whose k^2 weights amplify the noise floor of the spectrum)
+template <bool INV>
+__device__ __forceinline__ double2 fft8_twiddle(const double2* __restrict__ t, int m, int half) {
+    const bool wrap = m >= half;
+    double2 w = t[wrap ? m - half : m];
+    if (wrap) { w.x = -w.x; w.y = -w.y; }
+    if (INV) w.y = -w.y;
+    return w;
+}
+
+// v[r] = element j + r N/8 on entry and on return (natural order); sm: N + N/8 entries; the caller has synchronised stw
+template <bool INV>
+__device__ __forceinline__ void fft8_transform(double2 (&v)[8], double2* __restrict__ sm, const double2* __restrict__ stw, int N, int logN) {
+    const int j = threadIdx.x, T = N >> 3;
+    const int b = logN % 3;
+    auto exchange = [&]() {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = sm[fft8_pad(j + r * T)];
+        __syncthreads();
+    };
+    if (b == 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jj = j + q * T;
+            sm[fft8_pad(2 * jj)] = cadd(v[q], v[q + 4]);
+            sm[fft8_pad(2 * jj + 1)] = csub(v[q], v[q + 4]);
+        }
+        exchange();
+    } else if (b == 2) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int jj = j + q * T;
+            dft4<INV>(v[q], v[q + 2], v[q + 4], v[q + 6]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sm[fft8_pad(4 * jj + m)] = v[q + 2 * m];
+        }
+        exchange();
+    }
+    int off = 0;
+    for (int Ns = 1 << b; Ns * 8 <= N; Ns <<= 3) {
+        const int k = j & (Ns - 1);
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], fft8_twiddle<INV>(stw + off, r * k, 4 * Ns));
+        }
+        dft8<INV>(v);
+        if (Ns * 8 < N) {
+            const int j0 = ((j - k) << 3) + k;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) sm[fft8_pad(j0 + r * Ns)] = v[r];
+            exchange();
+        }
+        off += 4 * Ns;
+    }
+}
+
+// the three derivatives of one surface, as fft_zphi_kernel: blockIdx.x = role, blockIdx.y = batch member; N/8 threads
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) fft8_zphi_kernel(const double2* __restrict__ Z, const double2* __restrict__ Phi, double2* __restrict__ Zp,
+                                                         double2* __restrict__ Zpp, double2* __restrict__ PhiP, int N, int logN,
+                                                         const double2* __restrict__ tw, double rho, double U) {
+    extern __shared__ double2 sm_fft[];
+    double2* stw = sm_fft + N + (N >> 3);
+    const int role = blockIdx.x;
+    const size_t off = (size_t)blockIdx.y * N;
+    const double2* in = (role == 2 ? Phi : Z) + off;
+    double2* out = (role == 0 ? Zp : (role == 1 ? Zpp : PhiP)) + off;
+    const int j = threadIdx.x, T = N >> 3;
+    fft8_stage_twiddles(stw, tw, N, logN);
+    double2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = j + r * T;
+        v[r] = in[i];
+        v[r].x -= role == 2 ? -(1 + rho) * kPi * U / N * (double)i : 2 * kPi * (double)i / N;
+    }
+    __syncthreads();
+    fft8_transform<false>(v, sm_fft, stw, N, logN);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = role == 1 ? d2_coeff(v[r], j + r * T, N) : d1_coeff(v[r], j + r * T, N);
+    fft8_transform<true>(v, sm_fft, stw, N, logN);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) out[j + r * T] = v[r];
+}
+
+// a' = scale * D1(x) for a real vector x, as fft_real_derivative_kernel
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) fft8_real_derivative_kernel(const double* __restrict__ x, double2* __restrict__ out, int N, int logN,
+                                                                    const double2* __restrict__ tw, double scale, const SolveCtrl* ctrl) {
+    extern __shared__ double2 sm_fft[];
+    if (ctrl && *reinterpret_cast<const volatile int*>(&ctrl->done)) return;
+    double2* stw = sm_fft + N + (N >> 3);
+    const size_t off = (size_t)blockIdx.y * N;
+    const int j = threadIdx.x, T = N >> 3;
+    fft8_stage_twiddles(stw, tw, N, logN);
+    double2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = make_double2(x[off + j + r * T], 0.0);
+    __syncthreads();
+    fft8_transform<false>(v, sm_fft, stw, N, logN);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const double2 c = d1_coeff(v[r], j + r * T, N);
+        v[r] = make_double2(c.x * scale, c.y * scale);
+    }
+    fft8_transform<true>(v, sm_fft, stw, N, logN);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) out[off + j + r * T] = v[r];
+}
+
+static bool fft8_ok(int N) { return N >= 256 && N <= 8192; }
+static size_t fft8_smem(int N, int logN) { return (size_t)(N + (N >> 3) + fft8_twiddle_count(N, logN)) * sizeof(double2); }
+
 static int fft_threads(int N) { return N / 2 >= 1024 ? 1024 : (N / 2 >= 32 ? N / 2 : 32); }
 
 static void fft_smem_attr(const void* fn, size_t bytes) {
@@ -225,6 +407,15 @@ static void fft_smem_attr(const void* fn, size_t bytes) {
 
 void launch_fft_zphi(const double2* Z, const double2* Phi, double2* Zp, double2* Zpp, double2* PhiP, int N, int logN, int batch,
                      const double2* tw, double rho, double U, cudaStream_t st) {
+    if (fft8_ok(N)) {
+        const size_t b8 = fft8_smem(N, logN);
+        auto kern = N <= 4096 ? fft8_zphi_kernel<512> : fft8_zphi_kernel<1024>;   // 512 threads: no register cap, no spills
+        fft_smem_attr((const void*)kern, b8);
+        kern<<<dim3(Phi ? 3 : 2, batch), N / 8, b8, st>>>(Z, Phi, Zp, Zpp, PhiP, N, logN, tw, rho, U);
+        RB_CUDA(cudaGetLastError());
+        count_launch();
+        return;
+    }
     const size_t bytes = (size_t)(3 * N) * sizeof(double2);
     fft_smem_attr((const void*)fft_zphi_kernel, bytes);
     fft_zphi_kernel<<<dim3(Phi ? 3 : 2, batch), fft_threads(N), bytes, st>>>(Z, Phi, Zp, Zpp, PhiP, N, logN, tw, rho, U);
@@ -234,6 +425,15 @@ void launch_fft_zphi(const double2* Z, const double2* Phi, double2* Zp, double2*
 
 void launch_fft_real_derivative(const double* x, double2* out, int N, int logN, int batch, const double2* tw, double scale,
                                 const SolveCtrl* ctrl, cudaStream_t st) {
+    if (fft8_ok(N)) {
+        const size_t b8 = fft8_smem(N, logN);
+        auto kern = N <= 4096 ? fft8_real_derivative_kernel<512> : fft8_real_derivative_kernel<1024>;
+        fft_smem_attr((const void*)kern, b8);
+        kern<<<dim3(1, batch), N / 8, b8, st>>>(x, out, N, logN, tw, scale, ctrl);
+        RB_CUDA(cudaGetLastError());
+        count_launch();
+        return;
+    }
     const size_t bytes = (size_t)(3 * N) * sizeof(double2);
     fft_smem_attr((const void*)fft_real_derivative_kernel, bytes);
     fft_real_derivative_kernel<<<dim3(1, batch), fft_threads(N), bytes, st>>>(x, out, N, logN, tw, scale, ctrl);

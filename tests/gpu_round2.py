@@ -134,6 +134,35 @@ def steprates():
         print(f"steprate N={N}: {steps / (a.elapsed_time(b) * 1e-3):.1f} steps/s {stp.stats()} {c.solve_stats()} {c.sweepPlan()}", flush=True)
 
 
+def fftrates():
+    """RK4 step rate at 1024 < N <= 8192 with the fused radix-8 transforms (default) and with the library transforms (RB_OWN_FFT=0)."""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    for N, dt, steps in ((512, 1e-3, 100), (1024, 1e-3, 100), (2048, 1e-3, 100), (4096, 1e-3, 100), (8192, 1e-3, 60), (8192, 2.5e-4, 60)):
+        for own in ("1", "0"):
+            os.environ["RB_OWN_FFT"] = own
+            try:
+                c = water(N, guess="warm")
+            finally:
+                os.environ.pop("RB_OWN_FFT", None)
+            stp = api.AutonomousRungeKuttaStepper(c, dt)
+            y = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+            stp.initialize(y, True)
+            try:
+                stp.runSteps(40)
+                torch.cuda.synchronize()
+                best = 0.0
+                for _ in range(3):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    stp.runSteps(steps)
+                    b.record()
+                    torch.cuda.synchronize()
+                    best = max(best, steps / (a.elapsed_time(b) * 1e-3))
+                print(f"fftrate N={N} own_fft={own}: {best:.1f} steps/s {stp.stats()}", flush=True)
+            except Exception as e:   # noqa: BLE001
+                print(f"fftrate N={N} own_fft={own}: FAILED {str(e)[:160]} {stp.stats()}", flush=True)
+
+
 def helium():
     """Helium film (finite depth, image term): recorded steps with the device-driven GMRES cycle against the host-driven solver."""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
@@ -210,7 +239,7 @@ def ensemble():
             print(f"ensemble {B} x N={N}: R4 vs R2 final state rel diff {np.abs(finals[0] - finals[1]).max() / np.abs(finals[0]).max():.2e}", flush=True)
 
 
-SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, helium=helium, ensemble=ensemble)
+SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, fftrates=fftrates, helium=helium, ensemble=ensemble)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)

@@ -117,6 +117,50 @@ def test_zphi_derivatives_analytic(api):
     assert np.abs(PhiP.cpu().numpy().real - ePhiP).max() <= 1e-14
 
 
+@pytest.mark.parametrize("batch", [1, 2])
+@pytest.mark.parametrize("N", [128, 256, 512, 1024, 2048, 4096, 8192])
+def test_fused_shared_memory_transforms_on_rough_data(api, N, batch):
+    """ZPhiDerivative::exec (L/Derivatives.cuh:311-384) through the one-CTA fused transforms of spectral.cu -- radix-2 below N = 256,
+    the radix-8 register-resident transform (all three first-pass radices: log2 N mod 3 = 0, 1, 2) up to 8192 -- on data with a
+    full spectrum, so every mode, the pi factor at N/2 and the zeroed mode N/2+1 count; against the oracle's numpy transforms.
+    The real derivative a' = (2 pi / N) D1(a) of the same kernels is checked through the whole RHS below and in test_rhs_*."""
+    rng = np.random.default_rng(N + batch)
+    a = 2 * np.pi * np.arange(N) / N
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, batch, props, api.WaterBoundaryProblem(props))
+    Zs = [a + 0.01 * (rng.standard_normal(N) + 1j * rng.standard_normal(N)) for _ in range(batch)]
+    Phis = [(0.1 * rng.standard_normal(N)).astype(np.complex128) for _ in range(batch)]
+    Zp, PhiP, Zpp = calc.zPhiDerivative(T(np.concatenate(Zs)), T(np.concatenate(Phis)))
+    Zp, PhiP, Zpp = (v.cpu().numpy().reshape(batch, N) for v in (Zp, PhiP, Zpp))
+    for b in range(batch):
+        eZp, ePhiP, eZpp = ro.zphi_derivative(Zs[b], Phis[b], ro.ProblemProperties(rho=0.0))
+        for got, exp in ((Zp[b], eZp), (PhiP[b], ePhiP), (Zpp[b], eZpp)):
+            assert np.abs(got - exp).max() <= 2e-13 * max(1.0, np.abs(exp).max())
+
+
+@pytest.mark.parametrize("N", [2048, 4096, 8192])
+def test_rhs_with_fused_transforms_matches_the_library_transforms(api, N):
+    """The whole RHS (surface derivatives and the a' of the solve) with the fused radix-8 transforms (default up to N = 8192)
+    against the same solver on cuFFT (RB_OWN_FFT=0): identical to round-off.  Round-off here grows like N: the velocity contains
+    V2 a' with a' the spectral derivative of the solved a, which multiplies the 1e-15 noise of a by wavenumbers up to N/2 (measured
+    own-against-library: 8e-14 at N = 1024, 2.2e-13 at 2048, 5.2e-13 at 4096, 7.9e-13 at 8192, a itself to 1.5e-15)."""
+    props = api.ProblemProperties(rho=0.0)
+    Z, Phi = ro.trochoid(N, 0.3)
+    y = T(ro.pack_state(Z, Phi))
+    outs = []
+    for own in ("1", "0"):
+        os.environ["RB_OWN_FFT"] = own
+        try:
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+        finally:
+            os.environ.pop("RB_OWN_FFT", None)
+        out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+        calc.run(y, out)
+        assert calc.solve_stats()["converged"]
+        outs.append(out.cpu().numpy())
+    assert np.abs(outs[0] - outs[1]).max() <= 1e-15 * N * np.abs(outs[1]).max()
+
+
 @pytest.mark.parametrize("N", [2, 4, 8, 64, 1000])
 def test_derivative_nyquist_quirks(api, N):
     """Nyquist-rich data: the CUDA conventions (pi factor, zeroed mode N/2+1) must be reproduced exactly."""

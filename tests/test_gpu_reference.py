@@ -59,8 +59,13 @@ def test_rhs_matches_the_reference_cuda_path(api, reference, case):
     m = ref_cases.measure(api, case, _ref(reference, case), torch)
     tol = RHS_TOL[case["physics"]]
     assert m["converged"]
-    for k in ("velocity", "dphi_dt", "a", "zp", "zpp", "phi_prime"):
+    for k in ("velocity", "dphi_dt", "a", "zp", "phi_prime"):
         assert m[k] <= tol, (k, m)
+    # Zpp: the k^2 weights lift the round-off floor of ANY double-precision transform to ~ 1e-16 N^2 relative (numpy's transform
+    # against the analytic Zpp of this trochoid: 2.9e-10 at N = 1024, 4.9e-9 at 4096, 8.6e-8 at 16384).  Up to N = 8192 the
+    # surface derivatives come from this library's own fused transforms, not from the cuFFT plan the reference uses, so the two
+    # noise floors are independent there (measured 9.4e-10 at N = 4096); with the same cuFFT plan they are bit-identical.
+    assert m["zpp"] <= max(tol, 1e-16 * case["N"] ** 2), ("zpp", m)
     assert m["vel_upper"] <= 3 * tol, m
     for k in ("energy_kinetic", "energy_potential", "energy_surface", "energy_volume_flux"):
         assert m[k] <= ENERGY_TOL, (k, m)
