@@ -618,6 +618,8 @@ def run_native(args):
         traffic = json.load(open(tf)).get(str(N), {}).get("dram_bytes_per_launch")
     plan = calc.sweepPlan()
     kernel = (f"rb::sweep2_kernel<MV> (persistent, {plan['ctas']} CTAs x {plan['threads']} threads)" if plan["kernel"] == "persistent" else
+              f"rb::sweep3_kernel<MV, {plan['rows_per_thread']} rows/warp> (one warp per row group, {plan['ctas']} CTAs x {plan['threads']} threads)"
+              if plan["kernel"] == "warp_rows" else
               f"rb::sweep_kernel<MV, {plan['rows_per_thread']} rows/thread> (tiled: {plan['row_cells']} row cells x {plan['nchunks']} source chunks "
               f"= {plan['ctas']} CTAs x {plan['threads']} threads)")
     step_ms_sweeps = sweeps_per_step * sweep_ms

@@ -218,7 +218,7 @@ class BaseBoundaryIntegralCalculator:
     def sweepPlan(self):
         out = (ctypes.c_int * 8)()
         check(self.lib.rb_sweep_plan(self.handle, out), "rb_sweep_plan")
-        return dict(kernel="persistent" if out[0] == 2 else "tiled", rows_per_thread=out[1], tile=out[2], tiles_per_chunk=out[3],
+        return dict(kernel={1: "tiled", 2: "persistent", 3: "warp_rows"}[out[0]], rows_per_thread=out[1], tile=out[2], tiles_per_chunk=out[3],
                     nchunks=out[4], row_cells=out[5], ctas=out[6], threads=out[7])
 
 

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libroberts_b200.so")
-SOURCES = ["pair_kernels.cu", "pair_kernels2.cu", "spectral.cu", "dense_kernels.cu", "stepper_kernels.cu", "rk45_kernels.cu", "krylov_kernels.cu", "drive_kernels.cu", "implicit.cu", "lu_kernels.cu", "solver.cu", "stepper.cu", "comm.cu", "probes.cu", "exports.cu", "drive.cu", "rk45.cu"]
+SOURCES = ["pair_kernels.cu", "pair_kernels2.cu", "pair_kernels3.cu", "spectral.cu", "dense_kernels.cu", "stepper_kernels.cu", "rk45_kernels.cu", "krylov_kernels.cu", "drive_kernels.cu", "implicit.cu", "lu_kernels.cu", "solver.cu", "stepper.cu", "comm.cu", "probes.cu", "exports.cu", "drive.cu", "rk45.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "128"]

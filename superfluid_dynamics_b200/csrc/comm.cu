@@ -85,14 +85,14 @@ int rb_debug_set_row_range(rb_solver* s, int cell0, int cells) {
 
 int rb_sweep_plan(rb_solver* s, int out[8]) {
     RB_TRY
-    out[0] = s->use_v2 ? 2 : 1;            // 1 tiled, 2 persistent
-    out[1] = s->use_v2 ? s->v2_R : s->v1_rows;
+    out[0] = s->use_v3 ? 3 : (s->use_v2 ? 2 : 1);            // 1 tiled, 2 persistent, 3 warp per row group
+    out[1] = s->use_v3 ? s->v3l.R : (s->use_v2 ? s->v2_R : s->v1_rows);
     out[2] = s->tile;
     out[3] = s->tiles_per_chunk;
     out[4] = s->nchunks;
     out[5] = s->row_cells;
-    out[6] = s->use_v2 ? s->v2l.grid : s->row_cells * s->nchunks * s->batch;   // CTAs per sweep
-    out[7] = s->use_v2 ? s->v2l.threads : kCell / s->v1_rows;
+    out[6] = s->use_v3 ? s->v3l.grid : (s->use_v2 ? s->v2l.grid : s->row_cells * s->nchunks * s->batch);   // CTAs per sweep
+    out[7] = s->use_v3 ? s->v3l.threads : (s->use_v2 ? s->v2l.threads : kCell / s->v1_rows);
     RB_CATCH
 }
 

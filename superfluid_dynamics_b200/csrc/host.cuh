@@ -83,6 +83,8 @@ struct rb_solver {
     bool use_v2 = false;
     int v2_RB = 0, v2_R = 0, v2_groups = 0, v2_spg = 0, v2_TS = 0, v2_bpm = 0, v2_total_blocks = 0;
     Sweep2Launch v2l;
+    bool use_v3 = false;             // warp-per-row-group kernel (one member, no image sum, small N)
+    Sweep3Launch v3l;
     int v2_split = 1;
     double v2_eff = 0.0;
     double* v2_rnorm_part = nullptr;

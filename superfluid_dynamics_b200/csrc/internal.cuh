@@ -255,6 +255,12 @@ struct Sweep2Launch {
     size_t smem = 0;
 };
 
+// warp-per-row-group kernel (pair_kernels3.cu): R rows per warp, TS staged sources per tile
+struct Sweep3Launch {
+    int grid = 0, threads = 0, R = 1, TS = 0, S = 1;   // S warps share a row group (cells split between them)
+    size_t smem = 0;
+};
+
 // ---- launch wrappers (each defined in the .cu named in the comment) -----------------------
 // pair_kernels.cu
 void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, int ncell, int physics,
@@ -263,6 +269,9 @@ void launch_geometry(const Geometry& g, double2* phiprime_c, int N, int batch, i
 void launch_sweep(const SweepArgs& a, int mode, cudaStream_t st);
 // pair_kernels2.cu
 void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStream_t st);
+// pair_kernels3.cu
+void launch_sweep3(const SweepArgs& a, const Sweep3Launch& l, int mode, cudaStream_t st);
+size_t sweep3_smem(int TS);
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st,
                   const double2* Zp = nullptr, const double* Mdiag = nullptr, double cK = 0.0);

@@ -262,10 +262,55 @@ void choose_sweep_kernel(rb_solver* s) {
     int force = env_int("RB_SWEEP_V2", -1);
     if (force >= 0) v2 = !s->has_image && force != 0;
     s->use_v2 = v2;
+    // warp-per-row-group kernel (pair_kernels3.cu): one member, no image sum, at most 16 row groups per SM.  R rows per warp by the
+    // number of rows of this rank, so that the row groups fill the warps of one CTA per SM.
+    s->use_v3 = false;
+    if (!s->has_image && s->batch == 1 && s->N <= 8192) {
+        const int rows = std::min(s->N, (s->row_cell0 + s->row_cells) * kCell) - s->row_cell0 * kCell;
+        int R = rows >= 3072 ? 4 : (rows >= 1536 ? 2 : 1);
+        R = env_int("RB_V3_R", R);
+        R = R >= 4 ? 4 : (R >= 2 ? 2 : 1);
+        const int NG = (rows + R - 1) / R;
+        // one CTA per SM with ~200 KB of shared memory: when the a' transform of a recorded round runs beside the sweep on the side
+        // stream (overlap_ok), one SM is left to it -- otherwise whichever of the two starts second waits for the other's whole CTA
+        const int G = std::max(1, std::min(nSM - (s->overlap_ok ? 1 : 0), NG));
+        const int Wg = (NG + G - 1) / G;                        // row groups per CTA
+        // S warps per row group (they split the cells between them), as long as the CTA stays at 8 warps -- the variant compiled
+        // without a register cap.  Measured (profiles/r02s_sweep3.log, sweep alone, us): N = 4096: R = 4 / S = 1 (7 warps) 26.7,
+        // S = 2 (14 warps, 128 registers, spills) 32.8, R = 2 (14 warps) 28.7; N = 2048: R = 2 / S = 1 14.4, R = 4 / S = 2 14.4,
+        // R = 2 / S = 2 16.6; N = 1024: R = 1 12.3, R = 2 / S = 2 11.7
+        int S = 1;
+        while (S * 2 <= s->ncell && Wg * S * 2 <= 8 && S < 4) S *= 2;
+        S = env_int("RB_V3_S", S);
+        S = std::max(1, std::min(S, std::min(s->ncell, 8)));
+        const int W = Wg * S;
+        if (W <= 16) {
+            s->v3l.R = R;
+            s->v3l.S = S;
+            s->v3l.grid = G;
+            s->v3l.threads = 32 * W;
+            s->v3l.TS = std::min(4096, ((s->N + kCell - 1) / kCell) * kCell);
+            s->v3l.smem = sweep3_smem(s->v3l.TS);
+            // measured on a B200 (profiles/r02s_sweep3.log)
+            const int lo = env_int("RB_V3_MIN_N", 2);
+            s->use_v3 = s->N >= lo;
+            const int f3 = env_int("RB_SWEEP_V3", -1);
+            if (f3 >= 0) s->use_v3 = f3 != 0;
+            if (s->use_v3 && (int)std::max(s->v2_total_blocks, 1) < G) {   // residual partials: one per CTA
+                if (s->v2_rnorm_part) cudaFree(s->v2_rnorm_part);
+                s->v2_rnorm_part = dmalloc<double>(std::max(G, s->v2_total_blocks));
+            }
+            if (s->use_v3) s->use_v2 = false;
+        }
+    }
+    if (env_int("RB_VERBOSE", 0) && s->use_v3)
+        std::fprintf(stderr, "[roberts_b200] sweep3 plan: N=%d R=%d S=%d grid=%d threads=%d TS=%d smem=%zu\n", s->N, s->v3l.R, s->v3l.S,
+                     s->v3l.grid, s->v3l.threads, s->v3l.TS, s->v3l.smem);
 }
 
 static void sweep(rb_solver* s, const SweepArgs& a, int mode) {
-    if (s->use_v2) launch_sweep2(a, s->v2l, mode, s->stream);
+    if (s->use_v3) launch_sweep3(a, s->v3l, mode, s->stream);
+    else if (s->use_v2) launch_sweep2(a, s->v2l, mode, s->stream);
     else launch_sweep(a, mode, s->stream);
     s->total_sweeps++;
 }

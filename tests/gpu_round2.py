@@ -116,6 +116,27 @@ def n4096():
             print(f"n4096 steps {cfg}: FAILED {e}", flush=True)
 
 
+def v3():
+    """The warp-per-row-group sweep (pair_kernels3.cu) against the tiled and the persistent kernel: solver sweep alone, several N."""
+    peak = api.measure_fp64_peak(dev)
+    sizes = [int(v) for v in os.environ.get("V3_SIZES", "512,1024,2048,4096,8192").split(",")]
+    for N in sizes:
+        st = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+        cfgs = [{"RB_SWEEP_V3": 1}] + [{"RB_SWEEP_V3": 1, "RB_V3_R": r, "RB_V3_S": sp} for r in (1, 2, 4) for sp in (1, 2, 4)]
+        cfgs += [{"RB_SWEEP_V3": 0, "RB_SWEEP_V2": 0}, {"RB_SWEEP_V3": 0, "RB_SWEEP_V2": 1}]
+        for cfg in cfgs:
+            try:
+                def run():
+                    c = water(N)
+                    ms, pairs = c.benchSweep(st, 200)
+                    return ms, c.sweepPlan()
+                ms, plan = with_env(cfg, run)
+                tf = 20.0 * N * N / (ms * 1e-3) / 1e12
+                print(f"v3 sweep N={N} {cfg}: {ms * 1e3:.1f} us {tf / peak:.3f} of peak {plan['kernel']} R={plan['rows_per_thread']} ctas={plan['ctas']} thr={plan['threads']}", flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(f"v3 sweep N={N} {cfg}: not available ({str(e)[:60]})", flush=True)
+
+
 def steprates():
     """RK4 step rate at the bench sizes with the committed defaults."""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
@@ -239,7 +260,7 @@ def ensemble():
             print(f"ensemble {B} x N={N}: R4 vs R2 final state rel diff {np.abs(finals[0] - finals[1]).max() / np.abs(finals[0]).max():.2e}", flush=True)
 
 
-SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, fftrates=fftrates, helium=helium, ensemble=ensemble)
+SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, fftrates=fftrates, v3=v3, helium=helium, ensemble=ensemble)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)

@@ -220,6 +220,41 @@ def test_cotangent_sum_matches_direct_evaluation(api, N, h):
     assert rel(S[rows], ro.cot_rowsum(Z, x, rows)) <= 2e-13
 
 
+@pytest.mark.parametrize("N,h", [(2, 0.3), (64, 0.3), (300, 0.3), (1000, 0.4), (1024, 0.4), (1300, 0.2), (1536, 0.4), (2048, 0.4), (3000, 0.3),
+                                 (3072, 0.4), (4096, 0.4), (5000, 0.3), (8192, 0.4)])
+def test_warp_per_row_group_sweep_matches_direct_evaluation_and_the_tiled_kernel(api, N, h):
+    """sweep3_kernel (pair_kernels3.cu; default for 1024 < N <= 8192, forced here at every size): 1, 2 and 4 rows per warp, one and
+    two staged tiles, partial last cell, few-cell surfaces without cell-local coordinates.  (a) the raw cotangent sum against the
+    direct 1/tan evaluation of the oracle, as test_cotangent_sum_matches_direct_evaluation; (b) the whole RHS (solver sweeps,
+    combined velocity sweep, convergence decision) against the same solver on the tiled kernel."""
+    Z, Phi = ro.trochoid(N, h)
+    props = api.ProblemProperties(rho=0.0)
+    x = np.cos(3 * 2 * np.pi * np.arange(N) / N) + 0.3 * np.sin(2 * np.pi * np.arange(N) / N) + 0.1
+    y = T(ro.pack_state(Z, Phi))
+    outs, plans = [], []
+    for v3 in ("1", "0"):
+        os.environ["RB_SWEEP_V3"] = v3
+        os.environ["RB_SWEEP_V2"] = "0"
+        try:
+            calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+        finally:
+            os.environ.pop("RB_SWEEP_V3", None)
+            os.environ.pop("RB_SWEEP_V2", None)
+        plans.append(calc.sweepPlan())
+        if v3 == "1":
+            calc.zPhiDerivative(T(Z), T(Phi.astype(np.complex128)))
+            S = calc.cotangentSum(T(Z), T(x)).cpu().numpy()
+            rows = np.arange(N) if N <= 1300 else np.r_[0:6, N - 6:N, N // 2 - 3:N // 2 + 3, 253:259, 509:515, 1021:1027]
+            assert not np.isnan(S).any()
+            assert rel(S[rows], ro.cot_rowsum(Z, x, rows)) <= 2e-13
+        out = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+        calc.run(y, out)
+        assert calc.solve_stats()["converged"]
+        outs.append(out.cpu().numpy())
+    assert plans[0]["kernel"] == "warp_rows" and plans[1]["kernel"] == "tiled", plans
+    assert rel(outs[0], outs[1]) <= 1e-12
+
+
 def test_cotangent_sum_is_linear_and_row_local_at_full_size(api):
     """Size-independent properties at N = 65536 (BASELINE config 5): linearity in x, and a spot check of rows against the
     direct evaluation (the dense oracle does not fit in host memory at this size)."""
