@@ -22,7 +22,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     ok = True
-    for N, h, dt, steps in ((4096, 0.4, 1e-3, 20), (16384, 0.3, 2e-4, 10), (65536, 0.4, 1e-4, 5)):
+    for N, h, dt, steps in ((2048, 0.4, 1e-3, 20), (4096, 0.4, 1e-3, 20), (8192, 0.3, 2.5e-4, 10), (16384, 0.3, 2e-4, 10), (65536, 0.4, 1e-4, 5)):
         props = api.ProblemProperties(rho=0.0)
         Z, Phi = ro.trochoid(N, h)
         y0 = ro.pack_state(Z, Phi)
