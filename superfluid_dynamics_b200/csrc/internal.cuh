@@ -54,10 +54,11 @@ struct SolveCtrl {
 //              converged = 0, stagnated = 1 and the host counts it separately.
 //   neither and iters >= max_iters: the solve failed (done = 1, converged = 0, stagnated = 0).
 #ifdef __CUDACC__
-__device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst, double tol2, int max_iters, int final_buf) {
+// (iters_before / prev: the block's iters and prev_rel2 -- the second form lets a caller load them early, beside its other loads)
+__device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst, double tol2, int max_iters, int final_buf, int iters_before,
+                                             double prev) {
     if (!(worst == worst)) worst = 1e300;   // NaN -> "not converged"
-    const int iters = c->iters + 1;
-    const double prev = c->prev_rel2;
+    const int iters = iters_before + 1;
     const bool conv = worst <= tol2;
     const bool stagnated = !conv && iters >= 3 && worst <= 1e-20 && worst > 0.64 * prev;
     c->iters = iters;
@@ -70,6 +71,11 @@ __device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst
         c->stagnated = stagnated ? 1 : 0;
         c->done = 1;
     }
+}
+__device__ __forceinline__ void solve_decide(volatile SolveCtrl* c, double worst, double tol2, int max_iters, int final_buf) {
+    const int iters_before = c->iters;
+    const double prev = c->prev_rel2;
+    solve_decide(c, worst, tol2, max_iters, final_buf, iters_before, prev);
 }
 #endif
 

@@ -107,9 +107,10 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
     __shared__ unsigned int s_ticket;
     constexpr bool REALPATH = (MODE == kSweepMV);
 
-    if ((MODE == kSweepMV || MODE == kSweepVEL) && a.skip_if_done) {
-        if (*reinterpret_cast<volatile int*>(&a.ctrl->done)) return;
-    }
+    // "is this solve finished already?": the flag is loaded now and looked at after the prologue's loads have been issued (before
+    // the first barrier), so that it does not cost a round trip of its own
+    int solve_done = 0;
+    if ((MODE == kSweepMV || MODE == kSweepVEL) && a.skip_if_done) solve_done = *reinterpret_cast<volatile int*>(&a.ctrl->done);
     const int t = threadIdx.x, T = blockDim.x, lane = t & 31, w = t >> 5;
     const int N = a.N;
     const double inv4pi = 0.25 / kPi;
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
         }
     }
     bool near_pending = true;
+    if (solve_done) return;      // (uniform over the launch: nothing has been stored yet)
 
     double xs = 0.0;
     for (int j0 = 0; j0 < N; j0 += TS) {
@@ -397,6 +399,12 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
         return;
     }
     double rn = 0.0, bn = 0.0;
+    int iters_before = 0;
+    double prev_rel2 = 0.0;
+    if (t == 0) {                 // (the control block's history, in the same round trip as the partials)
+        iters_before = *reinterpret_cast<volatile int*>(&a.ctrl->iters);
+        prev_rel2 = *reinterpret_cast<volatile double*>(&a.ctrl->prev_rel2);
+    }
     for (int i = t; i < (int)gridDim.x; i += T) rn += __ldcg(a.v2_rnorm_part + i);
     if (a.comm.nranks <= 1)
         for (int i = t; i < a.ncell; i += T) bn += __ldcg(a.bnorm_part + i);       // (same round trip as the residual partials)
@@ -412,10 +420,7 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
     }
     bn = block_sum3(bn, sred);
     const double worst = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
-    if (t == 0) {
-        solve_decide(a.ctrl, worst, a.tol2, a.max_iters, a.final_buf_on_done);
-        __threadfence();
-    }
+    if (t == 0) solve_decide(a.ctrl, worst, a.tol2, a.max_iters, a.final_buf_on_done, iters_before, prev_rel2);
 }
 
 template <int MODE, int R, int MAXT>

@@ -225,8 +225,7 @@ __global__ void fft_real_derivative_kernel(const double* __restrict__ x, double2
 // shared-memory array (position p lives at p + p/8: the stride-8 scatter of the early passes is conflict-free), two barriers per
 // exchange.  The last pass leaves the natural-order result in exactly the register layout the first pass of the next transform
 // reads, and global memory is read and written straight from / to registers (coalesced: consecutive threads, consecutive elements).
-// Twiddles: the seven factors exp(-2 pi i r k / (8 Ns)) of a butterfly are table entries (half circle per pass staged in shared
-// memory, 4 Ns entries), not products.
+// Twiddles: w and w^2 of a butterfly are table entries (2 Ns per pass staged in shared memory), the other five products.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -267,51 +266,67 @@ __device__ __forceinline__ void dft8(double2 (&v)[8]) {
 
 __device__ __forceinline__ int fft8_pad(int p) { return p + (p >> 3); }
 
-// number of staged twiddles: 4 Ns per radix-8 pass (N = 8192: 4680 entries; data + twiddles = 222 KB of shared memory)
+// number of staged twiddles: 2 Ns per radix-8 pass (w and w^2 of every butterfly are table entries)
 __host__ __device__ inline int fft8_twiddle_count(int N, int logN) {
     int n = 0;
-    for (int Ns = 1 << (logN % 3); Ns * 8 <= N; Ns <<= 3) n += 4 * Ns;
+    for (int Ns = 1 << (logN % 3); Ns * 8 <= N; Ns <<= 3) n += 2 * Ns;
     return n;
 }
 
 // tw: the per-pass table of solver_create (exp(-i pi k / Ns') at offset Ns' - 1); the radix-8 pass at Ns uses Ns' = 4 Ns:
-// exp(-2 pi i m / (8 Ns)), m < 4 Ns (the other half of the circle is its negative)
+// exp(-2 pi i m / (8 Ns)), of which m < 2 Ns are staged.  The passes' pieces are loaded as ONE batch per thread (all loads in
+// flight together with the caller's input loads: one L2 round trip), then stored.
+constexpr int kFft8TwBatch = 4;
 __device__ __forceinline__ void fft8_stage_twiddles(double2* stw, const double2* __restrict__ tw, int N, int logN) {
-    int off = 0;
-    for (int Ns = 1 << (logN % 3); Ns * 8 <= N; Ns <<= 3) {
-        for (int k = threadIdx.x; k < 4 * Ns; k += blockDim.x) stw[off + k] = tw[4 * Ns - 1 + k];
-        off += 4 * Ns;
+    const int total = fft8_twiddle_count(N, logN);
+    for (int i0 = threadIdx.x; i0 < total; i0 += kFft8TwBatch * blockDim.x) {
+        double2 w[kFft8TwBatch];
+#pragma unroll
+        for (int u = 0; u < kFft8TwBatch; ++u) {
+            const int i = i0 + u * blockDim.x;
+            w[u] = make_double2(0.0, 0.0);
+            if (i < total) {
+                int off = 0, Ns = 1 << (logN % 3);
+                while (i >= off + 2 * Ns) {   // which pass this entry belongs to
+                    off += 2 * Ns;
+                    Ns <<= 3;
+                }
+                w[u] = tw[4 * Ns - 1 + (i - off)];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kFft8TwBatch; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) stw[i] = w[u];
+        }
     }
 }
 
-// exp(-+ 2 pi i m / (8 Ns)) for m < 8 Ns from the staged half circle: every factor is a correctly rounded table entry (products of
-// twiddles would put 2-3 ulp of noise on every mode -- visible in Zpp, whose k^2 weights amplify the noise floor of the spectrum)
+// v[r] = element j + r N/8 on entry and on return (natural order); sm: one (N <= 4096: two, ping-pong) padded arrays of N + N/8
+// entries; the caller has synchronised stw.  Twiddles of a butterfly: w = exp(-+ 2 pi i k / (8 Ns)) and w^2 from the table, the
+// other five by one or two multiplications (w^3 = w w^2, w^4 = (w^2)^2, w^5 = w^4 w, w^6 = w^4 w^2, w^7 = w^4 w^3) -- seven table
+// reads per butterfly cost more shared-memory wavefronts than the whole exchange (even strides conflict), and the accuracy is the
+// same to the last digit the tests can see.
 template <bool INV>
-__device__ __forceinline__ double2 fft8_twiddle(const double2* __restrict__ t, int m, int half) {
-    const bool wrap = m >= half;
-    double2 w = t[wrap ? m - half : m];
-    if (wrap) { w.x = -w.x; w.y = -w.y; }
-    if (INV) w.y = -w.y;
-    return w;
-}
-
-// v[r] = element j + r N/8 on entry and on return (natural order); sm: N + N/8 entries; the caller has synchronised stw
-template <bool INV>
-__device__ __forceinline__ void fft8_transform(double2 (&v)[8], double2* __restrict__ sm, const double2* __restrict__ stw, int N, int logN) {
+__device__ __forceinline__ void fft8_transform(double2 (&v)[8], double2* __restrict__ sm, const double2* __restrict__ stw, int N, int logN,
+                                               bool two_buffers) {
     const int j = threadIdx.x, T = N >> 3;
     const int b = logN % 3;
+    double2* cur = sm;
+    double2* const other = two_buffers ? sm + N + (N >> 3) : sm;
     auto exchange = [&]() {
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v[r] = sm[fft8_pad(j + r * T)];
-        __syncthreads();
+        for (int r = 0; r < 8; ++r) v[r] = cur[fft8_pad(j + r * T)];
+        if (!two_buffers) __syncthreads();      // (ping-pong: the next writes go to the other array, no second barrier)
+        cur = (cur == sm) ? other : sm;
     };
     if (b == 1) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int jj = j + q * T;
-            sm[fft8_pad(2 * jj)] = cadd(v[q], v[q + 4]);
-            sm[fft8_pad(2 * jj + 1)] = csub(v[q], v[q + 4]);
+            cur[fft8_pad(2 * jj)] = cadd(v[q], v[q + 4]);
+            cur[fft8_pad(2 * jj + 1)] = csub(v[q], v[q + 4]);
         }
         exchange();
     } else if (b == 2) {
@@ -320,7 +335,7 @@ __device__ __forceinline__ void fft8_transform(double2 (&v)[8], double2* __restr
             const int jj = j + q * T;
             dft4<INV>(v[q], v[q + 2], v[q + 4], v[q + 6]);
 #pragma unroll
-            for (int m = 0; m < 4; ++m) sm[fft8_pad(4 * jj + m)] = v[q + 2 * m];
+            for (int m = 0; m < 4; ++m) cur[fft8_pad(4 * jj + m)] = v[q + 2 * m];
         }
         exchange();
     }
@@ -328,18 +343,45 @@ __device__ __forceinline__ void fft8_transform(double2 (&v)[8], double2* __restr
     for (int Ns = 1 << b; Ns * 8 <= N; Ns <<= 3) {
         const int k = j & (Ns - 1);
         if (Ns > 1) {
-#pragma unroll
-            for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], fft8_twiddle<INV>(stw + off, r * k, 4 * Ns));
+            double2 w1 = stw[off + k], w2 = stw[off + 2 * k];
+            if (INV) {
+                w1.y = -w1.y;
+                w2.y = -w2.y;
+            }
+            const double2 w3 = cmul(w1, w2), w4 = cmul(w2, w2);
+            v[1] = cmul(v[1], w1);
+            v[2] = cmul(v[2], w2);
+            v[3] = cmul(v[3], w3);
+            v[4] = cmul(v[4], w4);
+            v[5] = cmul(v[5], cmul(w4, w1));
+            v[6] = cmul(v[6], cmul(w4, w2));
+            v[7] = cmul(v[7], cmul(w4, w3));
         }
         dft8<INV>(v);
         if (Ns * 8 < N) {
             const int j0 = ((j - k) << 3) + k;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) sm[fft8_pad(j0 + r * Ns)] = v[r];
+            for (int r = 0; r < 8; ++r) cur[fft8_pad(j0 + r * Ns)] = v[r];
             exchange();
         }
-        off += 4 * Ns;
+        off += 2 * Ns;
     }
+    // (an even number of exchanges is not guaranteed: the next transform simply starts on whichever array is current -- both are
+    // free here, every thread has passed the last barrier after its last read only if a barrier follows; see the callers)
+}
+
+// d1_coeff / d2_coeff for power-of-two n: 1/n is exact, so the multiplication gives the quotient bit for bit (an FP64 division is
+// ~30 instructions; 24 of them per thread were a fifth of the kernel)
+__device__ __forceinline__ double2 d1_coeff_pow2(double2 c, int i, int n, double inv_n) {
+    if (i < n / 2) return make_double2((-i * c.y) * inv_n, (i * c.x) * inv_n);
+    if (i == n / 2) return make_double2((-kPi * i * c.y) * inv_n, (kPi * i * c.x) * inv_n);
+    if (i == n / 2 + 1) return make_double2(0.0, 0.0);
+    return make_double2((-(i - n) * c.y) * inv_n, ((i - n) * c.x) * inv_n);
+}
+
+__device__ __forceinline__ double2 d2_coeff_pow2(double2 c, int i, int n, double inv_n) {
+    const int k = i <= n / 2 ? i : i - n;
+    return make_double2((-k * k * c.x) * inv_n, (-k * k * c.y) * inv_n);
 }
 
 // the three derivatives of one surface, as fft_zphi_kernel: blockIdx.x = role, blockIdx.y = batch member; N/8 threads
@@ -348,25 +390,29 @@ __global__ void __launch_bounds__(MAXT) fft8_zphi_kernel(const double2* __restri
                                                          double2* __restrict__ Zpp, double2* __restrict__ PhiP, int N, int logN,
                                                          const double2* __restrict__ tw, double rho, double U) {
     extern __shared__ double2 sm_fft[];
-    double2* stw = sm_fft + N + (N >> 3);
+    const bool two = N <= 4096;
+    double2* stw = sm_fft + (two ? 2 : 1) * (N + (N >> 3));
     const int role = blockIdx.x;
     const size_t off = (size_t)blockIdx.y * N;
     const double2* in = (role == 2 ? Phi : Z) + off;
     double2* out = (role == 0 ? Zp : (role == 1 ? Zpp : PhiP)) + off;
     const int j = threadIdx.x, T = N >> 3;
-    fft8_stage_twiddles(stw, tw, N, logN);
+    const double inv_n = 1.0 / (double)N;
     double2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = in[j + r * T];
+    fft8_stage_twiddles(stw, tw, N, logN);     // (its loads fly together with the input loads above)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int i = j + r * T;
-        v[r] = in[i];
-        v[r].x -= role == 2 ? -(1 + rho) * kPi * U / N * (double)i : 2 * kPi * (double)i / N;
+        v[r].x -= role == 2 ? -(1 + rho) * kPi * U / N * (double)i : (2 * kPi * (double)i) * inv_n;   // (= ... / N: N is a power of two)
     }
     __syncthreads();
-    fft8_transform<false>(v, sm_fft, stw, N, logN);
+    fft8_transform<false>(v, sm_fft, stw, N, logN, two);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = role == 1 ? d2_coeff(v[r], j + r * T, N) : d1_coeff(v[r], j + r * T, N);
-    fft8_transform<true>(v, sm_fft, stw, N, logN);
+    for (int r = 0; r < 8; ++r) v[r] = role == 1 ? d2_coeff_pow2(v[r], j + r * T, N, inv_n) : d1_coeff_pow2(v[r], j + r * T, N, inv_n);
+    __syncthreads();                           // every read of the forward transform's last exchange is done
+    fft8_transform<true>(v, sm_fft, stw, N, logN, two);
 #pragma unroll
     for (int r = 0; r < 8; ++r) out[j + r * T] = v[r];
 }
@@ -377,27 +423,29 @@ __global__ void __launch_bounds__(MAXT) fft8_real_derivative_kernel(const double
                                                                     const double2* __restrict__ tw, double scale, const SolveCtrl* ctrl) {
     extern __shared__ double2 sm_fft[];
     if (ctrl && *reinterpret_cast<const volatile int*>(&ctrl->done)) return;
-    double2* stw = sm_fft + N + (N >> 3);
+    const bool two = N <= 4096;
+    double2* stw = sm_fft + (two ? 2 : 1) * (N + (N >> 3));
     const size_t off = (size_t)blockIdx.y * N;
     const int j = threadIdx.x, T = N >> 3;
-    fft8_stage_twiddles(stw, tw, N, logN);
     double2 v[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = make_double2(x[off + j + r * T], 0.0);
+    fft8_stage_twiddles(stw, tw, N, logN);
     __syncthreads();
-    fft8_transform<false>(v, sm_fft, stw, N, logN);
+    fft8_transform<false>(v, sm_fft, stw, N, logN, two);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        const double2 c = d1_coeff(v[r], j + r * T, N);
+        const double2 c = d1_coeff_pow2(v[r], j + r * T, N, 1.0 / (double)N);
         v[r] = make_double2(c.x * scale, c.y * scale);
     }
-    fft8_transform<true>(v, sm_fft, stw, N, logN);
+    __syncthreads();
+    fft8_transform<true>(v, sm_fft, stw, N, logN, two);
 #pragma unroll
     for (int r = 0; r < 8; ++r) out[off + j + r * T] = v[r];
 }
 
 static bool fft8_ok(int N) { return N >= 256 && N <= 8192; }
-static size_t fft8_smem(int N, int logN) { return (size_t)(N + (N >> 3) + fft8_twiddle_count(N, logN)) * sizeof(double2); }
+static size_t fft8_smem(int N, int logN) { return (size_t)((N <= 4096 ? 2 : 1) * (N + (N >> 3)) + fft8_twiddle_count(N, logN)) * sizeof(double2); }
 
 static int fft_threads(int N) { return N / 2 >= 1024 ? 1024 : (N / 2 >= 32 ? N / 2 : 32); }
 

@@ -137,6 +137,49 @@ def v3():
                 print(f"v3 sweep N={N} {cfg}: not available ({str(e)[:60]})", flush=True)
 
 
+def steps_small():
+    """A few recorded RK4 steps at one small size (STEPS_N, default 4096), for ncu launch lists of the launch-bound regime:
+    ncu --metrics gpu__time_duration.sum --clock-control none -s <skip> -c 160 --csv --log-file ... python tests/gpu_round2.py steps_small"""
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    N = int(os.environ.get("STEPS_N", "4096"))
+    c = water(N, guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(c, 1e-3)
+    y = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+    stp.initialize(y, True)
+    stp.runSteps(int(os.environ.get("STEPS_K", "24")))
+    torch.cuda.synchronize()
+    print(f"steps_small N={N}: {stp.stats()} launches so far {api.launch_count() if hasattr(api, 'launch_count') else ''}", flush=True)
+
+
+def kernel_times():
+    """Live per-kernel durations of recorded RK4 steps (torch.profiler / CUPTI activity records, not ncu replays) at STEPS_N."""
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    N = int(os.environ.get("STEPS_N", "4096"))
+    c = water(N, guess="warm")
+    stp = api.AutonomousRungeKuttaStepper(c, float(os.environ.get("STEPS_DT", "1e-3")))
+    y = T(ro.pack_state(*ro.trochoid(N, 0.4)))
+    stp.initialize(y, True)
+    stp.runSteps(60)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        stp.runSteps(40)
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    agg = {}
+    for e in ev:
+        k = e.name.split("(")[0].replace("void ", "").replace("rb::", "")
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+    tot = sum(v[1] for v in agg.values())
+    t0 = min(e.time_range.start for e in ev)
+    t1 = max(e.time_range.end for e in ev)
+    print(f"kernel_times N={N}: 40 steps, span {(t1 - t0) / 40:.1f} us per step, kernel time {tot / 40:.1f} us per step", flush=True)
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"kernel_times   {n / 40:6.1f} per step  {t / n:8.2f} us avg  {100 * t / tot:5.1f} %  {k}", flush=True)
+
+
 def steprates():
     """RK4 step rate at the bench sizes with the committed defaults."""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
@@ -260,7 +303,7 @@ def ensemble():
             print(f"ensemble {B} x N={N}: R4 vs R2 final state rel diff {np.abs(finals[0] - finals[1]).max() / np.abs(finals[0]).max():.2e}", flush=True)
 
 
-SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, fftrates=fftrates, v3=v3, helium=helium, ensemble=ensemble)
+SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, steps_small=steps_small, kernel_times=kernel_times, fftrates=fftrates, v3=v3, helium=helium, ensemble=ensemble)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SECTIONS)
