@@ -357,8 +357,8 @@ __global__ void __launch_bounds__(kCoopThreads) lu_panel_coop_kernel(double* __r
                 __threadfence();
                 atomicAdd(bar, 1u);
                 const unsigned int target = bar_base + (unsigned)(j + 1) * (unsigned)ncta;
-                while (atomicAdd(bar, 0u) < target) {
-                }
+                while (*reinterpret_cast<volatile unsigned int*>(bar) < target) {   // (a load, not an atomic: the pollers must not queue
+                }                                                                    //  in front of the arrivals at the L2 atomic unit)
                 __threadfence();
             }
             __syncwarp();
@@ -456,8 +456,9 @@ __device__ __forceinline__ double* aug_column(double* A, double* b, int n, int c
 
 // one thread per column right of the panel (b included): the panel's row interchanges, then U12 = L11^{-1} A12 with L11 (unit lower
 // triangular) in shared memory and the 32 entries of the column in registers
+// (columns c_begin <= c <= c_last of the augmented matrix: the look-ahead schedule does the next panel's columns first)
 __global__ void __launch_bounds__(128) lu_swap_trsm_kernel(double* __restrict__ A, double* __restrict__ b, int n, int k0, int kb,
-                                                           const int* __restrict__ piv) {
+                                                           const int* __restrict__ piv, int c_begin, int c_last) {
     __shared__ double L[kNB][kNB + 1];
     __shared__ int s_piv[kNB];
     for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) {
@@ -466,8 +467,8 @@ __global__ void __launch_bounds__(128) lu_swap_trsm_kernel(double* __restrict__ 
     }
     if ((int)threadIdx.x < kb) s_piv[threadIdx.x] = piv[k0 + threadIdx.x];
     __syncthreads();
-    const int c = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > n) return;
+    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > c_last) return;
     double* colp = aug_column(A, b, n, c);
     for (int j = 0; j < kb; ++j) {
         const int r = k0 + j, p = s_piv[j];
@@ -501,12 +502,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 constexpr int kTile = 64;
 constexpr int kGemmThreads = 256;
 
-// C[r0.., c0..] -= L21[r0.., 0..kb) * U12[0..kb, c0..), the trailing block starting at row/column t0 = k0 + kb of the n x n matrix
-__global__ void __launch_bounds__(kGemmThreads) lu_gemm_kernel(double* __restrict__ A, int n, int k0, int kb) {
+// C[r0.., c0..] -= L21[r0.., 0..kb) * U12[0..kb, c0..), the trailing block starting at row/column t0 = k0 + kb of the n x n matrix;
+// blockIdx.y + ct0 is the column tile
+__global__ void __launch_bounds__(kGemmThreads) lu_gemm_kernel(double* __restrict__ A, int n, int k0, int kb, int ct0) {
     __shared__ double As[kTile][kNB + 1];   // -L21 tile, As[row][k]
     __shared__ double Bs[kNB][kTile + 1];   //  U12 tile, Bs[k][col]
     const int t0 = k0 + kb;
-    const int r0 = t0 + blockIdx.x * kTile, c0 = t0 + blockIdx.y * kTile;
+    const int r0 = t0 + blockIdx.x * kTile, c0 = t0 + (blockIdx.y + ct0) * kTile;
     const int tid = threadIdx.x;
     for (int idx = tid; idx < kTile * kNB; idx += kGemmThreads) {
         const int i = idx % kTile, j = idx / kTile;   // consecutive threads: consecutive rows of one column of L21
@@ -665,6 +667,11 @@ bool cluster_panels_enabled() {
 
 #ifndef RB_EMULATE
 namespace {
+bool env_flag(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) != 0 : dflt != 0;
+}
+
 // which panel kernel: RB_LU_PANEL = coop (default: P CTAs meeting through L2), one (one CTA), cluster (distributed shared memory)
 int panel_choice() {
     const char* v = std::getenv("RB_LU_PANEL");
@@ -679,6 +686,22 @@ int panel_choice() {
 // the factorisation with b eliminated on the fly: on return A holds U in its upper triangle and b holds L^{-1} P b
 void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) {
     int* piv = nullptr;   // pivot rows, stream-ordered allocation: no synchronisation, no state shared between streams
+#ifndef RB_EMULATE
+    {   // keep the pool's memory across synchronisations (the default threshold of 0 hands it back to the OS at every one, and the
+        // next factorisation's first allocation then maps fresh memory while kernels are already queued)
+        static thread_local bool pool_configured = false;
+        if (!pool_configured) {
+            int dev = 0;
+            cudaMemPool_t pool = nullptr;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = 64ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            pool_configured = true;
+        }
+    }
+#endif
     RB_CUDA(cudaMallocAsync(&piv, (size_t)std::max(n, 1) * sizeof(int), st));
     RB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     int launches = 0;
@@ -698,31 +721,85 @@ void lu_factor_blocked(double* A, double* b, int n, int* info, cudaStream_t st) 
         RB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
     }
 #endif
-    for (int k0 = 0; k0 < n; k0 += kNB) {
-        const int kb = std::min(kNB, n - k0);
+    // one panel factorisation, on stream q
+    auto panel = [&](int k0, int kb, cudaStream_t q) {
         bool done = false;
 #ifndef RB_EMULATE
         const int m_panel = n - k0;
         const int ncta = (m_panel + kCoopRows - 1) / kCoopRows;
         if (choice == 1 && m_panel > kCoopRows && ncta <= kCoopMaxCtas) {
             // P co-resident CTAs, one barrier through L2 per column (a panel of <= 256 rows is one CTA's work anyway)
-            lu_panel_coop_kernel<<<ncta, kCoopThreads, kNB * kCoopRows * sizeof(double), st>>>(A, n, k0, kb, piv, info, cands, bar, bar_total);
+            lu_panel_coop_kernel<<<ncta, kCoopThreads, kNB * kCoopRows * sizeof(double), q>>>(A, n, k0, kb, piv, info, cands, bar, bar_total);
             bar_total += (unsigned)ncta * (unsigned)kb;
             done = true;
         } else if (choice == 2 && m_panel >= 256) {
             // the panel in the distributed shared memory of a cluster of 8 CTAs (16 when the panel is too tall for 8)
-            done = try_cluster_panel<8>(A, n, k0, kb, piv, info, st);
-            if (!done) done = try_cluster_panel<16>(A, n, k0, kb, piv, info, st);
+            done = try_cluster_panel<8>(A, n, k0, kb, piv, info, q);
+            if (!done) done = try_cluster_panel<16>(A, n, k0, kb, piv, info, q);
         }
 #endif
-        if (!done) RB_LAUNCH(lu_panel_kernel, 1, kPanelThreads, st, A, n, k0, kb, piv, info);
-        const int right = n - k0 - kb + 1;   // columns right of the panel, b included
-        RB_LAUNCH(lu_swap_trsm_kernel, (right + 127) / 128, 128, st, A, b, n, k0, kb, (const int*)piv);
-        launches += 2;
+        if (!done) RB_LAUNCH(lu_panel_kernel, 1, kPanelThreads, q, A, n, k0, kb, piv, info);
+        launches++;
+    };
+    auto swap_trsm = [&](int k0, int kb, int c_begin, int c_last, cudaStream_t q) {
+        if (c_last < c_begin) return;
+        RB_LAUNCH(lu_swap_trsm_kernel, (c_last - c_begin + 1 + 127) / 128, 128, q, A, b, n, k0, kb, (const int*)piv, c_begin, c_last);
+        launches++;
+    };
+    bool lookahead = false;
+#ifndef RB_EMULATE
+    // Look-ahead of one panel: the row interchanges, the triangular solve and the trailing update of panel k are done FIRST for
+    // the 64 columns that hold the next two panels; then panel k + 1 is factorised on a second stream while this stream does the
+    // same for the rest of the matrix (disjoint columns; the columns left of a panel are never touched again, b is eliminated
+    // on the fly).  The critical path per panel is the panel itself plus two small launches instead of panel + swap/TRSM + GEMM.
+    static thread_local cudaStream_t side = nullptr;
+    static thread_local cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    lookahead = env_flag("RB_LU_LOOKAHEAD", n >= 4096 ? 1 : 0);   // measured: 13.0 -> 17.3 ms at n = 2048, 23.3 -> 27.6 at 3072, 44 -> 39 at 4096, 108 -> 79 at 7000, 272 -> 231 at 12288
+    if (lookahead && !side) {
+        RB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+    }
+    if (lookahead) {
+        RB_CUDA(cudaEventRecord(ev_main, st));              // allocations and memsets above
+        RB_CUDA(cudaStreamWaitEvent(side, ev_main, 0));
+        panel(0, std::min(kNB, n), side);
+        RB_CUDA(cudaEventRecord(ev_side, side));
+        for (int k0 = 0; k0 < n; k0 += kNB) {
+            const int kb = std::min(kNB, n - k0);
+            const int t0 = k0 + kb, m = n - t0;
+            RB_CUDA(cudaStreamWaitEvent(st, ev_side, 0));   // panel k is factorised
+            const int a_last = std::min(t0 + kTile, n) - 1;  // first column tile: the next two panels' columns
+            const int tiles = (m + kTile - 1) / kTile;
+            if (m > 0) {
+                swap_trsm(k0, kb, t0, a_last, st);
+                RB_LAUNCH(lu_gemm_kernel, dim3(tiles, 1), kGemmThreads, st, A, n, k0, kb, 0);
+                launches++;
+                RB_CUDA(cudaEventRecord(ev_main, st));
+                RB_CUDA(cudaStreamWaitEvent(side, ev_main, 0));
+                panel(t0, std::min(kNB, n - t0), side);
+                RB_CUDA(cudaEventRecord(ev_side, side));
+            }
+            swap_trsm(k0, kb, std::max(a_last + 1, t0), n, st);   // the other columns and b
+            if (m > 0) {
+                if (tiles > 1) {
+                    RB_LAUNCH(lu_gemm_kernel, dim3(tiles, tiles - 1), kGemmThreads, st, A, n, k0, kb, 1);
+                    launches++;
+                }
+                RB_LAUNCH(lu_gemv_kernel, (m + 255) / 256, 256, st, (const double*)A, b, n, k0, kb);
+                launches++;
+            }
+        }
+    }
+#endif
+    for (int k0 = 0; !lookahead && k0 < n; k0 += kNB) {
+        const int kb = std::min(kNB, n - k0);
+        panel(k0, kb, st);
+        swap_trsm(k0, kb, k0 + kb, n, st);
         const int m = n - k0 - kb;
         if (m > 0) {
             const int tiles = (m + kTile - 1) / kTile;
-            RB_LAUNCH(lu_gemm_kernel, dim3(tiles, tiles), kGemmThreads, st, A, n, k0, kb);
+            RB_LAUNCH(lu_gemm_kernel, dim3(tiles, tiles), kGemmThreads, st, A, n, k0, kb, 0);
             RB_LAUNCH(lu_gemv_kernel, (m + 255) / 256, 256, st, (const double*)A, b, n, k0, kb);
             launches += 2;
         }
