@@ -861,6 +861,31 @@ def test_rk45_on_the_boundary_integral_rhs_matches_oracle(api):
     assert abs(stp.getCurrentTimeStep() - o.h) <= 1e-6 * o.h
 
 
+@pytest.mark.parametrize("N,G", [(1024, 2), (2048, 4), (4096, 8), (4096, 3), (8192, 2), (16384, 8)])
+def test_row_range_of_a_shard_gives_the_same_rows(api, N, G):
+    """What rank r of a G-rank row-sharded run computes, on one GPU (rb_debug_set_row_range): the raw cotangent sum restricted to the
+    rank's row cells must equal the same rows of the whole-surface sum -- for the warp-per-row-group kernel (N <= 8192: rows per
+    rank from 512 to 4096, i.e. 1, 2 and 4 rows per warp, shared row groups, two staged tiles) to the last bit or to round-off
+    when the rows per warp differ, for the tiled kernel (N = 16384) to round-off (its chunking changes with the row count)."""
+    Z, Phi = ro.trochoid(N, 0.4)
+    props = api.ProblemProperties(rho=0.0)
+    calc = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    calc.zPhiDerivative(T(Z), T(Phi.astype(np.complex128)))
+    x = np.cos(3 * 2 * np.pi * np.arange(N) / N) + 0.3 * np.sin(2 * np.pi * np.arange(N) / N) + 0.1
+    whole = calc.cotangentSum(T(Z), T(x)).cpu().numpy()
+    ncell = (N + 255) // 256
+    for r in sorted({0, G // 2, G - 1}):
+        c0 = r * ncell // G
+        c1 = (r + 1) * ncell // G
+        calc.debugSetRowRange(c0, c1 - c0)
+        part = calc.cotangentSum(T(Z), T(x)).cpu().numpy()
+        rows = slice(c0 * 256, min(N, c1 * 256))
+        assert rel(part[rows], whole[rows]) <= 1e-13, (r, calc.sweepPlan())
+    calc.debugSetRowRange(0, 0)
+    again = calc.cotangentSum(T(Z), T(x)).cpu().numpy()
+    assert np.array_equal(again, whole)
+
+
 def test_row_sharded_two_gpus_match_single_gpu(api):
     """N > 1: row-sharded run on two GPUs (torchrun, one rank per GPU) vs the single-GPU run; skipped on a one-GPU box."""
     import subprocess
