@@ -264,6 +264,7 @@ struct Sweep2Launch {
 // warp-per-row-group kernel (pair_kernels3.cu): R rows per warp, TS staged sources per tile
 struct Sweep3Launch {
     int grid = 0, threads = 0, R = 1, TS = 0, S = 1;   // S warps share a row group (cells split between them)
+    bool batched = false;                              // ensembles: one member at a time per CTA (TS = padded sources per member)
     size_t smem = 0;
 };
 
@@ -278,6 +279,7 @@ void launch_sweep2(const SweepArgs& a, const Sweep2Launch& l, int mode, cudaStre
 // pair_kernels3.cu
 void launch_sweep3(const SweepArgs& a, const Sweep3Launch& l, int mode, cudaStream_t st);
 size_t sweep3_smem(int TS);
+size_t sweep3b_smem(int NP);
 void launch_guess(const double* b, const double* warm, const HistoryRing& hist, double* x0, double* xsum_part,
                   double* bnorm_part, SolveCtrl* ctrl, double omega, int N, int batch, int ncell, cudaStream_t st,
                   const double2* Zp = nullptr, const double* Mdiag = nullptr, double cK = 0.0);

@@ -92,6 +92,76 @@ __device__ __forceinline__ double block_sum3(double v, double* sred) {
     return r;
 }
 
+// what the epilogue of one row reads besides the row sum (loaded before the pair loops where registers allow)
+struct RowOps {
+    double xk = 0.0, md = 0.0, b = 0.0, y = 0.0;
+    double2 zp = {1.0, 0.0}, v1d = {0.0, 0.0}, v2 = {0.0, 0.0}, ap = {0.0, 0.0};
+};
+
+// o: index of the row in the (batched) arrays
+template <int MODE>
+__device__ __forceinline__ void load_row_ops(const SweepArgs& a, size_t o, RowOps& q) {
+    q.xk = a.x[o];
+    if (MODE != kSweepRAW) {
+        q.zp = a.g.Zp[o];
+        q.md = a.g.Mdiag[o];
+        if (!a.apply_only) q.b = a.g.b[o];
+    }
+    if (MODE == kSweepVEL) {
+        q.v1d = a.g.V1diag[o];
+        q.v2 = a.g.V2[o];
+        if (!a.defer_aprime) q.ap = a.aprime[o];   // deferred: finish_solve adds V2 a'
+        if (a.dphi && !a.defer_aprime) q.y = a.g.Z[o].y;
+    }
+}
+
+// the epilogue of row o from its finished sum `mine` (MV: Re(Zp T) in mine.x; otherwise T); returns the squared residual of the row
+template <int MODE>
+__device__ __forceinline__ double finish_row(const SweepArgs& a, size_t o, const RowOps& q, double sumx, double2 mine) {
+    const double inv4pi = 0.25 / kPi;
+    const double xk = q.xk;
+    const double Ar = (sumx - xk) + 2.0 * mine.x;
+    const double Ai = 2.0 * mine.y;
+    double sr = 0.0;
+    if (MODE == kSweepMV) {
+        const double Mx = fma(q.md, xk, a.cK * fma(q.zp.x, sumx - xk, 2.0 * mine.x));
+        if (a.apply_only) {
+            mirror_store2(a.comm, a.x_out + o, Mx);
+        } else {
+            const double res = q.b - Mx;
+            mirror_store2(a.comm, a.x_out + o, fma(a.omega, res, xk));
+            sr = res * res;
+        }
+    } else if (MODE == kSweepVEL) {
+        const double2 zp = q.zp;
+        const double wr = inv4pi * Ar + q.v1d.x * xk + (q.v2.x * q.ap.x - q.v2.y * q.ap.y);
+        const double wi = inv4pi * Ai + q.v1d.y * xk + (q.v2.x * q.ap.y + q.v2.y * q.ap.x);
+        mirror_store2(a.comm, a.vel_lower + o, make_double2(wr, -wi));
+        const double inv = 1.0 / (zp.x * zp.x + zp.y * zp.y);
+        const double azx = xk * zp.x * inv, azy = -xk * zp.y * inv;     // a_k / Zp_k
+        a.vel_upper[o] = make_double2(wr - azx, -(wi - azy));
+        if (a.dphi && !a.defer_aprime) {
+            double d;
+            if (a.rhs_phi_kind == 1) {
+                d = -q.y + 0.5 * (wr * wr + wi * wi);
+            } else {
+                const double vdw = a.depth / 3.0;
+                d = vdw * pow(1.0 + q.y / a.depth, -3.0) - vdw + (0.5 * wr * wr + 0.5 * wi * wi);
+            }
+            mirror_store2(a.comm, a.dphi + o, make_double2(d, 0.0));
+        }
+        if (a.combined) {   // verify the iterate with the same row sum: r = b - M a; next iterate in case it is needed
+            if (a.A_out) mirror_store2(a.comm, a.A_out + o, make_double2(Ar, Ai));
+            const double res = q.b - fma(q.md, xk, a.cK * (zp.x * Ar - zp.y * Ai));
+            mirror_store2(a.comm, a.x_out + o, fma(a.omega, res, xk));
+            sr = res * res;
+        }
+    } else {
+        a.raw_out[o] = make_double2(-Ai, Ar);
+    }
+    return sr;
+}
+
 }  // namespace
 
 template <int MODE, int R, int MAXT>
@@ -113,7 +183,6 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
     if ((MODE == kSweepMV || MODE == kSweepVEL) && a.skip_if_done) solve_done = *reinterpret_cast<volatile int*>(&a.ctrl->done);
     const int t = threadIdx.x, T = blockDim.x, lane = t & 31, w = t >> 5;
     const int N = a.N;
-    const double inv4pi = 0.25 / kPi;
     const int rows_total = a.v2_row_end - a.v2_row_begin;
     const int NG = (rows_total + R - 1) / R;                                        // row groups of this rank
     const int i0 = (int)(((long long)blockIdx.x * NG) / gridDim.x);
@@ -163,24 +232,11 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
     // (under a register cap -- more than 8 warps -- the operands are loaded after the loops instead: see load_operands below)
     constexpr bool PREFETCH = MAXT <= 256;
     double2 zpr[R];
-    double e_xk = 0.0, e_md = 0.0, e_b = 0.0, e_y = 0.0;
-    double2 e_zp = make_double2(1.0, 0.0), e_v1d = make_double2(0.0, 0.0), e_v2 = make_double2(0.0, 0.0), e_ap = make_double2(0.0, 0.0);
+    RowOps ops;
     auto load_operands = [&]() {
 #pragma unroll
         for (int r = 0; r < R; ++r) zpr[r] = (REALPATH && valid[r]) ? a.g.Zp[krow[r]] : make_double2(0.0, 0.0);
-        if (!myok) return;
-        e_xk = x[myk];
-        if (MODE != kSweepRAW) {
-            e_zp = a.g.Zp[myk];
-            e_md = a.g.Mdiag[myk];
-            if (!a.apply_only) e_b = a.g.b[myk];
-        }
-        if (MODE == kSweepVEL) {
-            e_v1d = a.g.V1diag[myk];
-            e_v2 = a.g.V2[myk];
-            if (!a.defer_aprime) e_ap = a.aprime[myk];
-            if (a.dphi && !a.defer_aprime) e_y = a.g.Z[myk].y;
-        }
+        if (myok) load_row_ops<MODE>(a, (size_t)myk, ops);
     };
     if (PREFETCH) load_operands();
 
@@ -327,53 +383,7 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
                     mine.y += v.y;
                 }
         }
-        if (myok) {
-            const size_t o = (size_t)myk;
-            const double xk = e_xk;
-            const double Ar = (sumx - xk) + 2.0 * mine.x;
-            const double Ai = 2.0 * mine.y;
-            if (MODE == kSweepMV) {
-                const double2 zp = e_zp;
-                const double Mx = fma(e_md, xk, a.cK * fma(zp.x, sumx - xk, 2.0 * mine.x));   // mine.x = Re(Zp T)
-                if (a.apply_only) {
-                    mirror_store2(a.comm, a.x_out + o, Mx);
-                } else {
-                    const double res = e_b - Mx;
-                    mirror_store2(a.comm, a.x_out + o, fma(a.omega, res, xk));
-                    sr = res * res;
-                }
-            } else if (MODE == kSweepVEL) {
-                const double2 zp = e_zp;
-                const double2 v1d = e_v1d;
-                const double2 v2 = e_v2;
-                const double2 ap = e_ap;                                                    // deferred (0): finish_solve adds V2 a'
-                const double wr = inv4pi * Ar + v1d.x * xk + (v2.x * ap.x - v2.y * ap.y);
-                const double wi = inv4pi * Ai + v1d.y * xk + (v2.x * ap.y + v2.y * ap.x);
-                mirror_store2(a.comm, a.vel_lower + o, make_double2(wr, -wi));
-                const double inv = 1.0 / (zp.x * zp.x + zp.y * zp.y);
-                const double azx = xk * zp.x * inv, azy = -xk * zp.y * inv;     // a_k / Zp_k
-                a.vel_upper[o] = make_double2(wr - azx, -(wi - azy));
-                if (a.dphi && !a.defer_aprime) {
-                    const double y = e_y;
-                    double d;
-                    if (a.rhs_phi_kind == 1) {
-                        d = -y + 0.5 * (wr * wr + wi * wi);
-                    } else {
-                        const double vdw = a.depth / 3.0;
-                        d = vdw * pow(1.0 + y / a.depth, -3.0) - vdw + (0.5 * wr * wr + 0.5 * wi * wi);
-                    }
-                    mirror_store2(a.comm, a.dphi + o, make_double2(d, 0.0));
-                }
-                if (a.combined) {   // verify the iterate with the same row sum: r = b - M a; next iterate in case it is needed
-                    if (a.A_out) mirror_store2(a.comm, a.A_out + o, make_double2(Ar, Ai));
-                    const double res = e_b - fma(e_md, xk, a.cK * (zp.x * Ar - zp.y * Ai));
-                    mirror_store2(a.comm, a.x_out + o, fma(a.omega, res, xk));
-                    sr = res * res;
-                }
-            } else {
-                a.raw_out[o] = make_double2(-Ai, Ar);
-            }
-        }
+        if (myok) sr = finish_row<MODE>(a, (size_t)myk, ops, sumx, mine);
     }
 
     // ---- the last CTA of the launch closes the sweep ----
@@ -423,6 +433,191 @@ __global__ void __launch_bounds__(MAXT, 1) sweep3_kernel(const SweepArgs a, cons
     if (t == 0) solve_decide(a.ctrl, worst, a.tol2, a.max_iters, a.final_buf_on_done, iters_before, prev_rel2);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ensembles of small surfaces (batch > 1, N <= 768: no cell-local coordinates, the 10-instruction form on every cell): the same
+// mapping, one MEMBER at a time per CTA.  CTA c steps through the members c, c + G, ...; a member's N sources are staged once
+// (the next member's loads fly during this member's pairs: two shared buffers), the 16 warps walk over the member's row groups
+// (R rows each), every row is finished by the lane butterfly and the epilogue where it was computed; one residual partial per
+// member, the last CTA of the launch takes the decision over the members.  Against sweep2_kernel (lanes = rows, warps = source
+// groups): no cross-group combine through shared memory, no idle phase between staging, pairs and epilogue of a row block.
+// ------------------------------------------------------------------------------------------------
+constexpr int kV3bStage = 4;   // staged entries per thread and member (NP <= 4 T)
+
+__device__ __forceinline__ double block_max3(double v, double* sred) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int w = threadIdx.x >> 5, W = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sred[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < W; ++i) r = fmax(r, sred[i]);
+    return r;
+}
+
+template <int MODE, int R>
+__global__ void __launch_bounds__(kV3MaxWarps * 32, 1) sweep3b_kernel(const SweepArgs a, const int NP) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int LD = NP + kV3Pad;
+    double2* se = reinterpret_cast<double2*>(smem_raw);        // [2][LD]  E_j
+    double2* sf = se + 2 * LD;                                 // [2][LD]  F_j = x_j E_j
+    double* sg = reinterpret_cast<double*>(sf + 2 * LD);       // [2][LD]  g_j = x_j |E_j|^2
+    double* sred = sg + 2 * LD;                                // [32]
+    __shared__ unsigned int s_ticket;
+    constexpr bool REALPATH = (MODE == kSweepMV);
+
+    int solve_done = 0;
+    if ((MODE == kSweepMV || MODE == kSweepVEL) && a.skip_if_done) solve_done = *reinterpret_cast<volatile int*>(&a.ctrl->done);
+    const int t = threadIdx.x, T = blockDim.x, lane = t & 31, w = t >> 5, W = T >> 5;
+    const int N = a.N;
+    const int NG = (N + R - 1) / R;                            // row groups per member
+    const bool solver_sweep = (MODE == kSweepMV && !a.apply_only) || (MODE == kSweepVEL && a.combined);
+
+    double pxv[kV3bStage];
+    double2 pev[kV3bStage];
+    auto prefetch = [&](int m) {
+        const size_t boff = (size_t)m * N;
+#pragma unroll
+        for (int u = 0; u < kV3bStage; ++u) {
+            const int s = t + u * T;
+            pxv[u] = 0.0;
+            pev[u] = make_double2(1.0e150, 0.0);               // padding contributes exactly 0
+            if (m < a.batch && s < N) {
+                pxv[u] = a.x[boff + s];
+                pev[u] = a.g.EG[boff + s];
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+    if (solve_done) return;      // (uniform over the launch: nothing has been stored yet)
+
+    int it = 0;
+    for (int m = blockIdx.x; m < a.batch; m += gridDim.x, ++it) {
+        const int buf = (it & 1) * LD;
+        double xs = 0.0;
+#pragma unroll
+        for (int u = 0; u < kV3bStage; ++u) {
+            const int s = t + u * T;
+            if (s < NP) {
+                xs += pxv[u];
+                se[buf + s] = pev[u];
+                sf[buf + s] = make_double2(pxv[u] * pev[u].x, pxv[u] * pev[u].y);
+                sg[buf + s] = pxv[u] * (pev[u].x * pev[u].x + pev[u].y * pev[u].y);
+            }
+        }
+        const double sumx = block_sum3(xs, sred);              // (its barriers publish the staged member)
+        prefetch(m + gridDim.x);                               // the next member's loads fly during this member's pairs
+        const size_t boff = (size_t)m * N;
+        double sr = 0.0;
+        for (int g = w; g < NG; g += W) {
+            int krow[R];
+            bool valid[R];
+            double2 ekG[R], zpr[R], U[R];
+            double V[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                krow[r] = g * R + r;
+                valid[r] = krow[r] < N;
+                ekG[r] = valid[r] ? se[buf + krow[r]] : make_double2(3.0e150, 0.0);   // (the targets are the staged sources themselves)
+                zpr[r] = (REALPATH && valid[r]) ? a.g.Zp[boff + krow[r]] : make_double2(0.0, 0.0);
+                U[r] = make_double2(0.0, 0.0);
+                V[r] = 0.0;
+            }
+            int myk = krow[0];
+            bool myok = valid[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r)
+                if (lane == r) {
+                    myk = krow[r];
+                    myok = valid[r];
+                }
+            myok = myok && lane < R;
+            RowOps ops;
+            if (myok) load_row_ops<MODE>(a, boff + myk, ops);
+            const int cellK = krow[0] / kCell;
+            for (int c = 0; c < a.ncell; ++c) {
+                const int jj = c * kCell;
+                int sd[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int d = krow[r] - jj - lane;
+                    sd[r] = (d >= 0 && (d & 31) == 0) ? (d >> 5) : -1;
+                }
+                const int so = buf + jj + lane;
+                if (c == cellK) accumulate3_far<R, true>(se + so, sf + so, sg + so, ekG, sd, U, V);
+                else accumulate3_far<R, false>(se + so, sf + so, sg + so, ekG, sd, U, V);
+            }
+            double2 acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {   // T = conj(E_k) U - V
+                acc[r].x = fma(ekG[r].x, U[r].x, ekG[r].y * U[r].y) - V[r];
+                acc[r].y = fma(ekG[r].x, U[r].y, -(ekG[r].y * U[r].x));
+                if (REALPATH) acc[r] = make_double2(zpr[r].x * acc[r].x - zpr[r].y * acc[r].y, 0.0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc[r].x += __shfl_xor_sync(0xffffffffu, acc[r].x, o);
+                    if (!REALPATH) acc[r].y += __shfl_xor_sync(0xffffffffu, acc[r].y, o);
+                }
+            }
+            double2 mine = acc[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r)
+                if (lane == r) mine = acc[r];
+            if (myok) sr += finish_row<MODE>(a, boff + myk, ops, sumx, mine);
+        }
+        if (solver_sweep) {
+            sr = block_sum3(sr, sred);
+            if (t == 0) a.v2_rnorm_part[m] = sr;
+        }
+    }
+
+    // ---- the last CTA of the launch closes the sweep: max over the members of ||r||^2 / ||b||^2 ----
+    if (!solver_sweep) return;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_ticket = atomicAdd(a.v2_ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    if (t == 0) *a.v2_ticket = 0u;
+    int iters_before = 0;
+    double prev_rel2 = 0.0;
+    if (t == 0) {
+        iters_before = *reinterpret_cast<volatile int*>(&a.ctrl->iters);
+        prev_rel2 = *reinterpret_cast<volatile double*>(&a.ctrl->prev_rel2);
+    }
+    double wm = 0.0;
+    for (int m = t; m < a.batch; m += T) {
+        const double rn = __ldcg(a.v2_rnorm_part + m);
+        double bn = 0.0;
+        for (int c = 0; c < a.ncell; ++c) bn += __ldcg(a.bnorm_part + (size_t)m * a.ncell + c);
+        double rel2 = bn > 0.0 ? rn / bn : (rn == 0.0 ? 0.0 : 1e300);
+        if (!(rel2 == rel2)) rel2 = 1e300;
+        wm = fmax(wm, rel2);
+    }
+    const double worst = block_max3(wm, sred);
+    if (t == 0) solve_decide(a.ctrl, worst, a.tol2, a.max_iters, a.final_buf_on_done, iters_before, prev_rel2);
+}
+
+template <int MODE, int R>
+static void launch_one3b(const SweepArgs& a, const Sweep3Launch& l, cudaStream_t st) {
+    static size_t configured = 0;
+    if (l.smem > configured) {
+        RB_CUDA(cudaFuncSetAttribute(sweep3b_kernel<MODE, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem));
+        configured = l.smem;
+    }
+    sweep3b_kernel<MODE, R><<<l.grid, l.threads, l.smem, st>>>(a, l.TS);
+}
+
+template <int R>
+static void launch_mode3b(const SweepArgs& a, const Sweep3Launch& l, int mode, cudaStream_t st) {
+    if (mode == kSweepMV) launch_one3b<kSweepMV, R>(a, l, st);
+    else if (mode == kSweepVEL) launch_one3b<kSweepVEL, R>(a, l, st);
+    else launch_one3b<kSweepRAW, R>(a, l, st);
+}
+
+size_t sweep3b_smem(int NP) { return (size_t)2 * (NP + kV3Pad) * (16 + 16 + 8) + 32 * sizeof(double); }
+
 template <int MODE, int R, int MAXT>
 static void launch_one3(const SweepArgs& a, const Sweep3Launch& l, cudaStream_t st) {
     static size_t configured = 0;
@@ -456,6 +651,15 @@ size_t sweep3_smem(int TS) {
 }
 
 void launch_sweep3(const SweepArgs& a, const Sweep3Launch& l, int mode, cudaStream_t st) {
+    if (l.batched) {
+        if (a.has_image || a.use_local || a.comm.nranks > 1) throw std::runtime_error("sweep3 (ensembles): no image sum, N <= 768, one rank");
+        if (l.R == 4) launch_mode3b<4>(a, l, mode, st);
+        else if (l.R == 2) launch_mode3b<2>(a, l, mode, st);
+        else launch_mode3b<1>(a, l, mode, st);
+        RB_CUDA(cudaGetLastError());
+        count_launch();
+        return;
+    }
     if (a.has_image || a.batch != 1) throw std::runtime_error("sweep3: one member, no image sum");
     if (l.R == 4) launch_mode3<4>(a, l, mode, st);
     else if (l.R == 2) launch_mode3<2>(a, l, mode, st);

@@ -265,6 +265,7 @@ void choose_sweep_kernel(rb_solver* s) {
     // warp-per-row-group kernel (pair_kernels3.cu): one member, no image sum, at most 16 row groups per SM.  R rows per warp by the
     // number of rows of this rank, so that the row groups fill the warps of one CTA per SM.
     s->use_v3 = false;
+    s->v3l.batched = false;
     if (!s->has_image && s->batch == 1 && s->N <= 8192) {
         const int rows = std::min(s->N, (s->row_cell0 + s->row_cells) * kCell) - s->row_cell0 * kCell;
         int R = rows >= 3072 ? 4 : (rows >= 1536 ? 2 : 1);
@@ -301,6 +302,32 @@ void choose_sweep_kernel(rb_solver* s) {
                 s->v2_rnorm_part = dmalloc<double>(std::max(G, s->v2_total_blocks));
             }
             if (s->use_v3) s->use_v2 = false;
+        }
+    }
+    // ensembles of small members (no cell-local coordinates: N <= 768): the same mapping, one member at a time per CTA
+    if (!s->has_image && s->batch > 1 && !s->use_local && s->comm.nranks <= 1 && s->N >= 32) {
+        int R = s->N >= 128 ? 4 : 1;
+        R = env_int("RB_V3_R", R);
+        R = R >= 4 ? 4 : (R >= 2 ? 2 : 1);
+        const int NG = (s->N + R - 1) / R;
+        const int W = std::max(1, std::min(16, NG));
+        const int NP = ((s->N + kCell - 1) / kCell) * kCell;
+        if (NP <= 4 * 32 * W) {
+            // measured (profiles/r02v_ensemble_sweep3b.log, steps/s, this kernel / the persistent or tiled one): 1024 x N=512 394 / 356,
+            // 512 x N=768 359 / 197 (every solve in 2 sweeps instead of 3), 128 x N=512 2071 / 1843; one-cell members and small
+            // batches lose (2048 x N=256 513 / 597, 37 x N=300 2784 / 3368)
+            const bool on = env_int("RB_SWEEP_V3B", (s->N > kCell && s->batch >= 64) ? 1 : 0) != 0;
+            if (on) {
+                s->v3l.R = R;
+                s->v3l.S = 1;
+                s->v3l.batched = true;
+                s->v3l.grid = std::min(nSM, s->batch);
+                s->v3l.threads = 32 * W;
+                s->v3l.TS = NP;
+                s->v3l.smem = sweep3b_smem(NP);
+                s->use_v3 = true;
+                s->use_v2 = false;
+            }
         }
     }
     if (env_int("RB_VERBOSE", 0) && s->use_v3)

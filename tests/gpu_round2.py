@@ -269,12 +269,12 @@ def ensemble():
     """BASELINE config 5b: 1024 members x N = 512 in one batched solver; 4 rows per thread (default) against round 1's 2."""
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     peak = api.measure_fp64_peak(dev)
-    for N, B in ((512, 1024), (256, 2048), (768, 512)):
+    for N, B in ((512, 1024), (256, 2048), (768, 512), (512, 128), (300, 37)):
         hs = 0.05 + 0.35 * np.arange(B) / (B - 1)
         sts = [ro.pack_state(*ro.trochoid(N, h)) for h in hs]
         y0 = api.ensemble_state(sts, N)
         finals = {}
-        for r4 in (1, 0):
+        for r4 in (3, 1):   # 3: the warp-per-row-group mapping (sweep3b_kernel), 1: persistent kernel with 4 rows per thread
             def run():
                 c = water(N, B, guess="warm")
                 stp = api.AutonomousRungeKuttaStepper(c, 1e-3)
@@ -292,7 +292,7 @@ def ensemble():
                 ms, pairs = c.benchSweep(T(y0), 20)
                 return 30 / (a.elapsed_time(b) * 1e-3), (it1["total_iterations"] - it0["total_iterations"]) / 30, ms, pairs, c.sweepPlan(), y.cpu().numpy(), it1
             try:
-                rate, spp, ms, pairs, plan, yf, st = with_env({"RB_V2_R4": r4}, run)
+                rate, spp, ms, pairs, plan, yf, st = with_env({"RB_SWEEP_V3B": 1 if r4 == 3 else 0, "RB_SWEEP_V3": -1}, run)
                 finals[r4] = yf
                 tf = 20.0 * pairs / (ms * 1e-3) / 1e12
                 print(f"ensemble {B} x N={N} R4={r4}: {rate:.1f} steps/s ({B * rate:.0f} member-steps/s), {spp:.2f} sweeps/step, sweep {ms * 1e3:.1f} us = "
@@ -300,7 +300,7 @@ def ensemble():
             except Exception as e:  # noqa: BLE001
                 print(f"ensemble {B} x N={N} R4={r4}: FAILED {e}", flush=True)
         if len(finals) == 2:
-            print(f"ensemble {B} x N={N}: R4 vs R2 final state rel diff {np.abs(finals[0] - finals[1]).max() / np.abs(finals[0]).max():.2e}", flush=True)
+            print(f"ensemble {B} x N={N}: warp-rows vs persistent final state rel diff {np.abs(finals[3] - finals[1]).max() / np.abs(finals[1]).max():.2e}", flush=True)
 
 
 SECTIONS = dict(shardtune=shardtune, n4096=n4096, steprates=steprates, steps_small=steps_small, kernel_times=kernel_times, fftrates=fftrates, v3=v3, helium=helium, ensemble=ensemble)

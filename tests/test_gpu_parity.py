@@ -255,6 +255,34 @@ def test_warp_per_row_group_sweep_matches_direct_evaluation_and_the_tiled_kernel
     assert rel(outs[0], outs[1]) <= 1e-12
 
 
+@pytest.mark.parametrize("N,B", [(64, 7), (300, 5), (512, 3), (768, 2), (512, 160)])
+def test_ensemble_sweep_one_member_per_cta_matches_the_members_stepped_alone(api, N, B):
+    """sweep3b_kernel (pair_kernels3.cu; default for ensembles of >= 64 members with 256 < N <= 768, forced here): every member's
+    RHS from the batched solver against the same member through a solver of its own (batch 1), ragged N, fewer and more members
+    than SMs; and per-member convergence (every member's own residual)."""
+    hs = 0.05 + 0.3 * np.arange(B) / max(B - 1, 1)
+    members = [ro.pack_state(*ro.trochoid(N, h)) for h in hs]
+    props = api.ProblemProperties(rho=0.0)
+    os.environ["RB_SWEEP_V3B"] = "1"
+    try:
+        calc = api.BaseBoundaryIntegralCalculator(N, B, props, api.WaterBoundaryProblem(props))
+    finally:
+        os.environ.pop("RB_SWEEP_V3B", None)
+    assert calc.sweepPlan()["kernel"] == "warp_rows"
+    y = T(api.ensemble_state(members, N))
+    out = torch.zeros(2 * N * B, dtype=torch.complex128, device="cuda:0")
+    calc.run(y, out)
+    assert calc.solve_stats()["converged"]
+    got = out.cpu().numpy()
+    alone = api.BaseBoundaryIntegralCalculator(N, 1, props, api.WaterBoundaryProblem(props))
+    o1 = torch.zeros(2 * N, dtype=torch.complex128, device="cuda:0")
+    for b in sorted({0, B // 2, B - 1}):
+        alone.run(T(members[b]), o1)
+        e = o1.cpu().numpy()
+        mine = np.concatenate([got[b * N:(b + 1) * N], got[B * N + b * N:B * N + (b + 1) * N]])
+        assert rel(mine, e) <= 1e-12, b
+
+
 def test_cotangent_sum_is_linear_and_row_local_at_full_size(api):
     """Size-independent properties at N = 65536 (BASELINE config 5): linearity in x, and a spot check of rows against the
     direct evaluation (the dense oracle does not fit in host memory at this size)."""
